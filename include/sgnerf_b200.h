@@ -1,0 +1,204 @@
+/*
+ * sgnerf_b200.h -- C ABI of libsgnerf_b200.so: SG-NeRF's per-ray render hot path on B200 (sm_100a).
+ *
+ * The reference has no native library; its boundary for this path is (paths relative to the reference):
+ *   - PyCUDA kernel handles returned by lighting_fast_querier.build_cuda()
+ *     (models/neural_points/query_point_indices_worldcoords.py:134-697) and called with raw
+ *     torch data_ptr()s through `Holder` (:21-28, :719-938);
+ *   - the torch modules NeuralPoints.forward (models/neural_points/neural_points.py:942-988),
+ *     PointAggregator.forward (models/aggregators/point_aggregators.py:868-959) and
+ *     ray_march / alpha_ray_march (models/rendering/diff_ray_marching.py:509-573).
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.
+ *   - every pointer is a DEVICE pointer owned by the caller unless marked [host]; the library never
+ *     allocates or frees user-visible memory.  Scratch comes from a caller-supplied workspace whose size
+ *     is queried first (sgn_*_workspace_bytes).  Workspaces must be 256-byte aligned.
+ *   - every launch entry takes a cudaStream_t (as void*) and is asynchronous; nothing synchronises.
+ *   - return value: 0 on success, negative SGN_E_* on error; sgn_last_error() gives a thread-local text.
+ *   - batch size B is 1 throughout (the reference only ever runs B = 1).
+ *   - there is no CPU fallback: without a CUDA device every launch entry returns SGN_E_CUDA.
+ */
+#ifndef SGNERF_B200_H
+#define SGNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGN_OK 0
+#define SGN_E_INVALID (-1)   /* bad argument / unsupported configuration */
+#define SGN_E_CUDA (-2)      /* CUDA runtime error (text in sgn_last_error) */
+#define SGN_E_WORKSPACE (-3) /* workspace too small or misaligned */
+
+#define SGN_MAX_K 32
+
+const char* sgn_last_error(void);
+int sgn_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy grid ("occ vox").  Replaces claim_occ / map_coor2occ / fill_occ2pnts and build_occ_vox
+ * (query_point_indices_worldcoords.py:265-410, :706-778).  The reference rebuilds it on every
+ * query_points() call; here it is built once per point-cloud version and queried many times.
+ * Slot numbering and per-voxel point lists follow the reference's sequential thread order
+ * (first visitor by point index owns the slot; lists are in point-index order; the `voxel_idx > 0`
+ * guard of :395 leaves slot 0 empty; overflow beyond max_o / P uses the same cuRAND XORWOW reservoir
+ * with seeds `index + 2*seconds`).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float origin[3];      /* d_coord_shift = ranges[:3]                                   (:793) */
+    float vsize[3];       /* scaled voxel size = vsize * vscale                           (:73)  */
+    int32_t dim[3];       /* scaled_vdim                                                  (:86)  */
+    int32_t query_size[3];/* occupancy dilation box (map_coor2occ's kernel_size argument) (:797) */
+    int32_t P;            /* max points per voxel                                                */
+    int32_t max_o;        /* max occupied voxels                                                 */
+    uint64_t seconds_claim; /* time.time() at :715 (reservoir seed when > max_o voxels)          */
+    uint64_t seconds_fill;  /* time.time() at :751 (reservoir seed when > P points in a voxel)   */
+} SgnGridCfg;
+
+typedef struct SgnGrid SgnGrid; /* opaque, host-side; holds device pointers into `persistent` */
+
+/* persistent: lives as long as the grid; scratch: only during sgn_grid_build. */
+int sgn_grid_workspace_bytes(int64_t N, const SgnGridCfg* cfg, size_t* persistent_bytes, size_t* scratch_bytes);
+int sgn_grid_build(const float* xyz /*[N,3]*/, int64_t N, int64_t actual_n, const SgnGridCfg* cfg,
+                   void* persistent, size_t persistent_bytes, void* scratch, size_t scratch_bytes,
+                   SgnGrid** out, void* stream);
+int sgn_grid_destroy(SgnGrid* g);
+/* Device pointers of the built structures, for tests and tooling (all int32 unless noted):
+ *   0 cell_slot [X*Y*Z] (= coor_2_occ), 1 occ_bits uint32[ceil(X*Y*Z/32)] (= coor_occ as a bitmask),
+ *   2 slot_coor [max_o*3] (= occ_2_coor), 3 slot_count [max_o] (= occ_numpnts, uncapped),
+ *   4 slot_start [max_o] (offset of the slot's list in cand), 5 cand float4[(x,y,z,bits(pidx))],
+ *   6 counters [4]: {n_claimed (= occ_idx), n_candidates, 0, 0}.                                  */
+int sgn_grid_buffer(const SgnGrid* g, int which, void** ptr, int64_t* n_elements);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray march + K-NN.  Replaces near-far ray positions (diff_ray_marching.py:387), mask_raypos,
+ * the cumsum glue, get_shadingloc[_with_semantic] and query_neigh_along_ray_layered[_semantic_guidance]
+ * (query_point_indices_worldcoords.py:413-681, :811-938) for all R rays in one pass, uncompacted:
+ * row r of the outputs belongs to input ray r.  The reference's two ray compactions (:838, :949)
+ * are pure row selections by `ray_mask` and are left to the caller.
+ *   t            middle_point_ts: [D] shared by all rays (t_per_ray = 0) or [R,D] (t_per_ray = 1)
+ *   ray_label    [R] or NULL.  Non-NULL selects the semantic-guidance kernel and needs pt_label [N],
+ *                pt_label_prob_bits [N,20] (the int32 tensor the reference passes as float*, :916).
+ * Outputs
+ *   sample_pidx  int32 [R,SR,K]  (-1 = empty), slot order identical to the sequential reference
+ *   sample_loc_w f32   [R,SR,3]  (unused slots are (0,0,0), :835)
+ *   sample_mask  int32 [R,SR]    (= sample_loc_mask)
+ *   sample_label int32 [R,SR]    scratch, only touched (and required) with semantic guidance
+ *   ray_mask     int8  [R]       1 iff the ray has at least one neighbour (final mask of :948)
+ * ---------------------------------------------------------------------------------------------- */
+int sgn_query(const SgnGrid* g, const float* campos /*[3]*/, const float* raydir /*[R,3]*/, const float* t,
+              int t_per_ray, int64_t R, int D, int SR, int K, int kernel_size0, float radius2,
+              const int32_t* ray_label, const int32_t* pt_label, const int32_t* pt_label_prob_bits,
+              uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w, int32_t* sample_mask,
+              int32_t* sample_label, int8_t* ray_mask, void* stream);
+
+/* Strict-compat materialisation of NeuralPoints.forward's gathered tensors
+ * (neural_points.py:956-972): out[j, :] = table[max(pidx[j],0), :] for n_rows index entries. */
+int sgn_gather_rows(const float* table /*[N,C]*/, int C, const int32_t* pidx, int64_t n_rows, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Aggregation.  Replaces NeuralPoints.forward's gathers (neural_points.py:956-988, w2pers :838-850),
+ * PointAggregator.forward / linear / viewmlp (point_aggregators.py:868-959, :494-502, :561-786),
+ * positional_encoding (helpers/networks.py:175-192) for the canonical branch (agg_dist_pers=20,
+ * agg_distance_kernel=linear, agg_intrp_order=2, apply_pnt_mask=1, agg_weight_norm=1, Rw2c=identity).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t feat_dim;        /* point_features_dim (32)                       */
+    int32_t num_feat_freqs;  /* 3 */
+    int32_t dist_xyz_freq;   /* 5 */
+    int32_t num_viewdir_freqs; /* 4 */
+    int32_t width;           /* shading_feature_num (256)                     */
+    int32_t n_block1;        /* shading_feature_mlp_layer1 (2)                */
+    int32_t n_block2_bpnet;  /* shading_feature_mlp_layer2_bpnet (0/1)        */
+    int32_t label_dim;       /* 96 when the label embedding is concatenated, else 0 */
+    int32_t n_block3;        /* shading_feature_mlp_layer3 (2)                */
+    int32_t n_color;         /* shading_color_mlp_layer (4)                   */
+    int32_t act_super;       /* 1: softplus(x-1) and sigmoid*1.002-0.001      */
+    float leaky_slope;       /* 0.01                                          */
+} SgnAggCfg;
+
+typedef struct {
+    const float* xyz;        /* [N,3]                                  neural_points.xyz            */
+    const float* embedding;  /* [N,feat_dim]                           neural_points.points_embeding */
+    const float* color;      /* [N,3]                                  neural_points.points_color    */
+    const float* dir;        /* [N,3]                                  neural_points.points_dir      */
+    const float* conf;       /* [N]                                    neural_points.points_conf     */
+    const float* label_emb;  /* [N,label_dim] or NULL                  bpnet_points_embedding        */
+    int64_t N;
+} SgnPointTables;
+
+typedef struct {             /* gradient accumulators (+=); any may be NULL */
+    float* embedding; float* color; float* dir; float* conf;
+} SgnPointGrads;
+
+/* Number of Linear layers for a config and their (in,out) sizes in state_dict order:
+ * block1.*, block2_bpnet.*, block3.*, alpha_branch.0, color_branch.* ; weights are [out,in] row-major
+ * exactly as torch.nn.Linear stores them.  `weights`/`biases` arguments below are [host] arrays of
+ * device pointers in this order. */
+int sgn_agg_num_layers(const SgnAggCfg* cfg);
+int sgn_agg_layer_shape(const SgnAggCfg* cfg, int layer, int* in_features, int* out_features);
+
+#define SGN_PRECISION_FP32 0   /* fp32 SIMT, strict parity mode                                   */
+#define SGN_PRECISION_BF16 1   /* bf16 tcgen05/TMEM tensor-core tiles, fp32 accumulate            */
+
+/* save_for_backward != 0 keeps the per-layer activations in the workspace for sgn_agg_backward. */
+int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t R, int SR, int K, int precision, int save_for_backward,
+                            size_t* bytes);
+
+/*   pidx [R,SR,K], loc_w [R,SR,3] from sgn_query; raydir [R,3]; campos [3]; camrotc2w [3,3] row-major.
+ *   decoded [R,SR,4] (sigma,r,g,b; zero where !ray_valid), ray_valid uint8 [R,SR],
+ *   loc_pers [R,SR,3] (= w2pers(loc_w)) or NULL, weight [R,SR,K] or NULL, conf_coef [R,SR,K] or NULL. */
+int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights /*[host]*/, const float* const* biases /*[host]*/,
+                    const SgnPointTables* tables, const int32_t* pidx, const float* loc_w, const float* raydir,
+                    const float* campos, const float* camrotc2w, int64_t R, int SR, int K, int precision,
+                    int save_for_backward, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
+                    float* conf_coef, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of sgn_agg_forward (autograd of the reference path).  Needs the workspace
+ * of a forward call made with save_for_backward = 1 and the same arguments.  d_weights/d_biases are
+ * [host] arrays of device pointers (accumulated, +=); d_conf_coef may be NULL. */
+int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases,
+                     const SgnPointTables* tables, const int32_t* pidx, const float* loc_w, const float* raydir,
+                     const float* campos, const float* camrotc2w, int64_t R, int SR, int K,
+                     const float* d_decoded /*[R,SR,4]*/, const float* d_conf_coef /*[R,SR,K]*/,
+                     float* const* d_weights, float* const* d_biases, const SgnPointGrads* d_tables,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Compositing.  Replaces ray_march / alpha_ray_march (diff_ray_marching.py:509-573) with
+ * render_func = radiance and blend_func = alpha (blend = 0) or alpha2 (blend = 1)
+ * (diff_render_func.py:36-49), and the step-size glue of
+ * models/neural_points_volumetric_model.py:569-577 (sgn_ray_dist).
+ * ---------------------------------------------------------------------------------------------- */
+int sgn_ray_dist(const float* loc_pers /*[R,SR,3]*/, const uint8_t* ray_valid /*[R,SR]*/, float vsize_z,
+                 int raydist_mode_unit, int64_t R, int SR, float* ray_dist /*[R,SR]*/, void* stream);
+
+/* decoded [R,SR,4]; ray_dist [R,SR]; valid uint8 [R,SR]; bg [3] or NULL.
+ * Outputs (any may be NULL): ray_color [R,3], opacity [R,SR], acc_transmission [R,SR], blend_weight [R,SR],
+ * bg_transmission [R]. */
+int sgn_composite_forward(const float* decoded, const float* ray_dist, const uint8_t* valid, const float* bg,
+                          int blend, int64_t R, int SR, float* ray_color, float* opacity, float* acc_transmission,
+                          float* blend_weight, float* bg_transmission, void* stream);
+
+/* Gradients w.r.t. decoded given cotangents of ray_color [R,3], opacity [R,SR], blend_weight [R,SR],
+ * bg_transmission [R] (any may be NULL).  d_decoded [R,SR,4] is overwritten. */
+int sgn_composite_backward(const float* decoded, const float* ray_dist, const uint8_t* valid, const float* bg,
+                           int blend, int64_t R, int SR, const float* d_ray_color, const float* d_opacity,
+                           const float* d_blend_weight, const float* d_bg_transmission, float* d_decoded,
+                           void* stream);
+
+/* fill_invalid (models/neural_points_volumetric_model.py:158-195) for uncompacted rows:
+ * rows with ray_mask == 0 get bg colour / opacity 0 / is_background 1. */
+int sgn_fill_invalid(const int8_t* ray_mask, const float* bg /*[3]*/, int64_t R, int SR, float* ray_color /*[R,3]*/,
+                     float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGNERF_B200_H */

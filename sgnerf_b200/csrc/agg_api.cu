@@ -1,0 +1,75 @@
+// agg_api.cu -- C-ABI entry points of the aggregator; dispatch on precision.
+#include "agg_common.cuh"
+
+using namespace sgn;
+
+int sgn_agg_fp32_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, int save, size_t* bytes);
+int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                         const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                         int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
+                         float* conf_coef, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                          int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
+                          float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, size_t* bytes);
+int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                       const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+static int check_common(const SgnAggCfg* cfg, AggPlan* P, int64_t R, int SR, int K)
+{
+    int rc = make_plan(cfg, P);
+    if (rc) return rc;
+    SGN_CHECK_ARG(R >= 0 && SR > 0 && K > 0 && K <= SGN_MAX_K, "aggregator: bad R/SR/K");
+    SGN_CHECK_ARG(R * (int64_t)SR * K < (1ll << 31), "aggregator: R*SR*K exceeds int32 indexing; split the rays");
+    return SGN_OK;
+}
+
+extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t R, int SR, int K, int precision, int save_for_backward, size_t* bytes)
+{
+    AggPlan P;
+    int rc = check_common(cfg, &P, R, SR, K);
+    if (rc) return rc;
+    SGN_CHECK_ARG(bytes != nullptr, "sgn_agg_workspace_bytes: bytes is NULL");
+    if (precision == SGN_PRECISION_FP32) return sgn_agg_fp32_workspace_bytes(P, R, SR, K, save_for_backward, bytes);
+    SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
+    SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
+    return sgn_agg_tc_workspace_bytes(P, R, SR, K, bytes);
+}
+
+extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                               const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                               int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,
+                               float* loc_pers, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes, void* stream)
+{
+    AggPlan P;
+    int rc = check_common(cfg, &P, R, SR, K);
+    if (rc) return rc;
+    SGN_CHECK_ARG(weights && biases && tables && pidx && loc_w && raydir && campos && camrotc2w && decoded && ray_valid, "sgn_agg_forward: NULL argument");
+    SGN_CHECK_ARG(tables->xyz && tables->embedding && tables->color && tables->dir, "sgn_agg_forward: xyz/embedding/color/dir tables are required");
+    SGN_CHECK_ARG(P.dims.LD == 0 || tables->label_emb, "sgn_agg_forward: label embedding table missing");
+    if (R == 0) return SGN_OK;
+    if (precision == SGN_PRECISION_FP32)
+        return sgn_agg_fp32_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, save_for_backward, decoded,
+                                    ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
+    SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
+    SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
+    return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
+                              weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                                const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                                int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
+                                float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, void* stream)
+{
+    AggPlan P;
+    int rc = check_common(cfg, &P, R, SR, K);
+    if (rc) return rc;
+    SGN_CHECK_ARG(weights && tables && pidx && raydir && d_decoded, "sgn_agg_backward: NULL argument");
+    if (R == 0) return SGN_OK;
+    return sgn_agg_fp32_backward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, d_decoded, d_conf_coef,
+                                 d_weights, d_biases, d_tables, workspace, workspace_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,121 @@
+// common.cu -- error text, version, and the int32 exclusive scan used by grid build and tuple compaction.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace sgn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------- exclusive scan ----------------
+// k1: each block reduces SCAN_TILE inputs -> partials[b]
+// k2: one block scans the partials in place (exclusive), writes grand total to partials[nb]
+// k3: each block rescans its tile with the block offset and writes out[]; block 0 thread 0 writes out[n]
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = SCAN_TILE / SCAN_THREADS;  // 8
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem /*[SCAN_THREADS/32 + 1]*/)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < SCAN_THREADS / 32 ? smem[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < SCAN_THREADS / 32) smem[lane] = si - s;
+        if (lane == 31) smem[SCAN_THREADS / 32] = si;
+    }
+    __syncthreads();
+    int r = inc - v + smem[w];
+    *total = smem[SCAN_THREADS / 32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int32_t* __restrict__ in, int64_t n, int32_t* partials)
+{
+    __shared__ int sm[SCAN_THREADS / 32 + 1];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++)
+        if (base + i < n) s += in[base + i];
+    int total;
+    block_exclusive_scan(s, &total, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(int32_t* partials, int nb)
+{
+    __shared__ int sm[SCAN_THREADS / 32 + 1];
+    int carry = 0;
+    for (int base = 0; base < nb; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? partials[i] : 0;
+        int total;
+        int e = block_exclusive_scan(v, &total, sm);
+        if (i < nb) partials[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0) partials[nb] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
+                                                                   const int32_t* __restrict__ partials, int nb)
+{
+    __shared__ int sm[SCAN_THREADS / 32 + 1];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    int v[SCAN_PER_THREAD];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    int total;
+    int e = block_exclusive_scan(s, &total, sm) + partials[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        if (base + i < n) out[base + i] = e;
+        e += v[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = partials[nb];
+}
+
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* partials, cudaStream_t st)
+{
+    int nb = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    if (nb == 0) {
+        SGN_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
+        return SGN_OK;
+    }
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, partials);
+    scan_partials_kernel<<<1, SCAN_THREADS, 0, st>>>(partials, nb);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, partials, nb);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+}  // namespace sgn
+
+extern "C" const char* sgn_last_error(void) { return sgn::g_err; }
+extern "C" int sgn_version(void) { return 100; }

@@ -1,0 +1,74 @@
+// common.cuh -- shared helpers for libsgnerf_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sgnerf_b200.h"
+
+namespace sgn {
+
+void set_error(const char* fmt, ...);
+
+#define SGN_CHECK_ARG(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::sgn::set_error(__VA_ARGS__);       \
+            return SGN_E_INVALID;                \
+        }                                        \
+    } while (0)
+
+#define SGN_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::sgn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return SGN_E_CUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define SGN_LAUNCH_CHECK() SGN_CUDA(cudaGetLastError())
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Bump allocator over a caller-supplied workspace.
+struct Arena {
+    char* base;
+    size_t cap, off;
+    Arena(void* p, size_t n) : base((char*)p), cap(n), off(0) {}
+    template <typename T>
+    T* take(size_t n)
+    {
+        size_t bytes = align_up(n * sizeof(T));
+        T* r = (T*)(base ? base + off : nullptr);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+// Exclusive prefix sum of int32 (n up to 2^31), total written to out[n].  Three small kernels.
+// partials must hold cdiv(n, SCAN_TILE) + 1 ints.
+constexpr int SCAN_TILE = 2048;
+int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* partials, cudaStream_t st);
+static inline size_t scan_partials_count(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1); }
+
+// ---- device helpers ----
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Voxel coordinate exactly as the reference computes it: (int)floor((p - shift) / vsize), IEEE fp32.
+__device__ __forceinline__ int vox_coord(float p, float shift, float vsize)
+{
+    return (int)floorf(__fdiv_rn(__fsub_rn(p, shift), vsize));
+}
+
+}  // namespace sgn

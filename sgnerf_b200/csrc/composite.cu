@@ -1,0 +1,282 @@
+// composite.cu -- alpha compositing forward/backward as warp scans, step-size glue, fill_invalid.
+//
+// Reference: ray_march / alpha_ray_march (models/rendering/diff_ray_marching.py:509-573),
+// radiance_render / alpha_blend / alpha2_blend (models/rendering/diff_render_func.py:36-49),
+// ray_dist glue and fill_invalid (models/neural_points_volumetric_model.py:569-577, :158-195).
+//
+// Layout: one warp per ray, lane = sample (chunks of 32 for SR > 32), so every global access is a
+// coalesced run of SR consecutive elements.  HBM-bound: forward moves SR*(16+4+1) B in and
+// SR*4*(#outputs) + 16 B out per ray; nothing is re-read.
+#include "common.cuh"
+
+namespace sgn {
+
+constexpr int COMP_WARPS = 8;        // warps per block
+constexpr int COMP_MAX_CHUNKS = 32;  // SR <= 1024
+
+__device__ __forceinline__ float warp_incl_prod(float v)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v *= t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float warp_incl_max(float v)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = fmaxf(v, t);
+    }
+    return v;
+}
+
+// suffix (reverse inclusive) sum across lanes
+__device__ __forceinline__ float warp_rincl_sum(float v)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += t;
+    }
+    return v;
+}
+
+template <int BLEND>
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+composite_fwd_kernel(const float4* __restrict__ decoded, const float* __restrict__ ray_dist, const uint8_t* __restrict__ valid,
+                     const float* __restrict__ bg, int64_t R, int SR, float* __restrict__ ray_color, float* __restrict__ opacity,
+                     float* __restrict__ acc_t, float* __restrict__ blend_w, float* __restrict__ bg_t)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * COMP_WARPS;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f;
+        for (int base = 0; base < SR; base += 32) {
+            const int s = base + lane;
+            const bool act = s < SR;
+            const int64_t i = r * SR + s;
+            float4 f = act ? __ldg(decoded + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float dist = act ? __ldg(ray_dist + i) : 0.f;
+            float v = (act && __ldg(valid + i)) ? 1.0f : 0.0f;
+            float sigma = f.x * v;
+            float o = 1.0f - expf(-sigma * dist);
+            float x = act ? (1.0f - o) + 1e-10f : 1.0f;
+            float incl = warp_incl_prod(x);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            float T = carry * excl;
+            float w = BLEND == 0 ? o * T : o * T * T;
+            if (act) {
+                if (opacity) opacity[i] = o;
+                if (acc_t) acc_t[i] = T;
+                if (blend_w) blend_w[i] = w;
+                cr += f.y * w; cg += f.z * w; cb += f.w * w;
+            }
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
+        }
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+        if (lane == 0) {
+            if (ray_color) {
+                float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+                if (bg) { b0 = bg[0]; b1 = bg[1]; b2 = bg[2]; }
+                ray_color[r * 3 + 0] = cr + b0 * carry;
+                ray_color[r * 3 + 1] = cg + b1 * carry;
+                ray_color[r * 3 + 2] = cb + b2 * carry;
+            }
+            if (bg_t) bg_t[r] = carry;
+        }
+    }
+}
+
+// Backward.  With x_i = 1 - o_i + eps, T_i = prod_{j<i} x_j, T_end = prod_j x_j, w_i = o_i T_i (alpha) or
+// o_i T_i^2 (alpha2), colour = sum_i w_i c_i + bg T_end:
+//   dL/dc_i  = w_i g_colour
+//   gw_i     = g_colour . c_i + g_blend_i
+//   dL/do_i  = gw_i dw/do + g_opacity_i  -  (1/x_i) [ sum_{j>i} gT_j T_j + gT_end T_end ]
+//   gT_j     = gw_j dw_j/dT_j ,  gT_end = g_colour . bg + g_bgT
+//   dL/dsigma_i = dL/do_i * dist_i * (1 - o_i) ;  d decoded.x = valid * dL/dsigma
+template <int BLEND>
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+composite_bwd_kernel(const float4* __restrict__ decoded, const float* __restrict__ ray_dist, const uint8_t* __restrict__ valid,
+                     const float* __restrict__ bg, int64_t R, int SR, const float* __restrict__ g_color,
+                     const float* __restrict__ g_opacity, const float* __restrict__ g_blend, const float* __restrict__ g_bgt,
+                     float4* __restrict__ d_decoded)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * COMP_WARPS;
+    const int nchunk = (SR + 31) / 32;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        // pass 1: carry-in of every chunk (product of x over all earlier chunks)
+        float carry_in[COMP_MAX_CHUNKS];
+        float carry = 1.0f;
+#pragma unroll 1
+        for (int c = 0; c < nchunk; c++) {
+            const int s = c * 32 + lane;
+            const bool act = s < SR;
+            const int64_t i = r * SR + s;
+            float x = 1.0f;
+            if (act) {
+                float v = __ldg(valid + i) ? 1.0f : 0.0f;
+                float o = 1.0f - expf(-(__ldg(decoded + i).x * v) * __ldg(ray_dist + i));
+                x = (1.0f - o) + 1e-10f;
+            }
+            carry_in[c] = carry;
+            float incl = warp_incl_prod(x);
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
+        }
+        const float T_end = carry;
+        float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f;
+        if (g_color) { gc0 = g_color[r * 3]; gc1 = g_color[r * 3 + 1]; gc2 = g_color[r * 3 + 2]; }
+        float gT_end = g_bgt ? g_bgt[r] : 0.f;
+        if (bg) gT_end += gc0 * bg[0] + gc1 * bg[1] + gc2 * bg[2];
+        float suffix = gT_end * T_end;  // sum over later samples of gT_j T_j, plus the background term
+        // pass 2: chunks in reverse
+#pragma unroll 1
+        for (int c = nchunk - 1; c >= 0; c--) {
+            const int s = c * 32 + lane;
+            const bool act = s < SR;
+            const int64_t i = r * SR + s;
+            float4 f = act ? __ldg(decoded + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float dist = act ? __ldg(ray_dist + i) : 0.f;
+            float v = (act && __ldg(valid + i)) ? 1.0f : 0.0f;
+            float o = 1.0f - expf(-(f.x * v) * dist);
+            float x = act ? (1.0f - o) + 1e-10f : 1.0f;
+            float incl = warp_incl_prod(x);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            float T = carry_in[c] * excl;
+            float w = BLEND == 0 ? o * T : o * T * T;
+            float gw = gc0 * f.y + gc1 * f.z + gc2 * f.w + ((act && g_blend) ? g_blend[i] : 0.f);
+            float dw_do = BLEND == 0 ? T : T * T;
+            float dw_dT = BLEND == 0 ? o : 2.0f * o * T;
+            float gT_T = act ? gw * dw_dT * T : 0.f;
+            float rs = warp_rincl_sum(gT_T);            // inclusive suffix within the chunk
+            float later = (rs - gT_T) + suffix;         // strictly later samples + later chunks + background
+            float go = gw * dw_do + ((act && g_opacity) ? g_opacity[i] : 0.f) - later / x;
+            if (act) {
+                float dsig = go * dist * (1.0f - o) * v;
+                d_decoded[i] = make_float4(dsig, w * gc0, w * gc1, w * gc2);
+            }
+            suffix += __shfl_sync(0xffffffffu, rs, 0);
+        }
+    }
+}
+
+// ray_dist glue, models/neural_points_volumetric_model.py:569-577.
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+ray_dist_kernel(const float* __restrict__ loc_pers, const uint8_t* __restrict__ ray_valid, float vsize_z, int mode_unit,
+                int64_t R, int SR, float* __restrict__ out)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * COMP_WARPS;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        float carry = -INFINITY;
+        for (int base = 0; base < SR; base += 32) {
+            const int s = base + lane;
+            const bool act = s < SR;
+            const int64_t i = r * SR + s;
+            float z = act ? __ldg(loc_pers + i * 3 + 2) : -INFINITY;
+            float cm = fmaxf(carry, warp_incl_max(z));
+            float d;
+            if (s + 1 < SR) {
+                float zn = __ldg(loc_pers + (i + 1) * 3 + 2);
+                d = fmaxf(cm, zn) - cm;
+            } else {
+                d = vsize_z;
+            }
+            bool bad = d < 1e-8f;
+            if (mode_unit > 0) bad = bad || (d > 2.0f * vsize_z);
+            float m = bad ? 1.0f : 0.0f;
+            d = d * (1.0f - m) + m * vsize_z;
+            if (act) out[i] = d * (__ldg(ray_valid + i) ? 1.0f : 0.0f);
+            carry = __shfl_sync(0xffffffffu, cm, 31);
+        }
+    }
+}
+
+__global__ void fill_invalid_kernel(const int8_t* __restrict__ ray_mask, const float* __restrict__ bg, int64_t R, int SR,
+                                    float* ray_color, float* opacity, float* bg_t)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || ray_mask[r] > 0) return;
+    if (ray_color) { ray_color[r * 3] = bg[0]; ray_color[r * 3 + 1] = bg[1]; ray_color[r * 3 + 2] = bg[2]; }
+    if (bg_t) bg_t[r] = 1.0f;
+    if (opacity)
+        for (int s = 0; s < SR; s++) opacity[r * SR + s] = 0.f;
+}
+
+static int comp_grid(int64_t R)
+{
+    int64_t b = (R + COMP_WARPS - 1) / COMP_WARPS;
+    int64_t cap = 148 * 8 * 4;  // a few waves of 148 SMs x 8 resident blocks
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace sgn
+
+using namespace sgn;
+
+extern "C" int sgn_ray_dist(const float* loc_pers, const uint8_t* ray_valid, float vsize_z, int raydist_mode_unit, int64_t R,
+                            int SR, float* ray_dist, void* stream)
+{
+    SGN_CHECK_ARG(R >= 0 && SR > 0, "sgn_ray_dist: bad R/SR");
+    if (R == 0) return SGN_OK;
+    ray_dist_kernel<<<comp_grid(R), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(loc_pers, ray_valid, vsize_z, raydist_mode_unit, R, SR, ray_dist);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_composite_forward(const float* decoded, const float* ray_dist, const uint8_t* valid, const float* bg, int blend,
+                                     int64_t R, int SR, float* ray_color, float* opacity, float* acc_transmission,
+                                     float* blend_weight, float* bg_transmission, void* stream)
+{
+    SGN_CHECK_ARG(R >= 0 && SR > 0 && SR <= 32 * COMP_MAX_CHUNKS, "sgn_composite_forward: SR=%d out of range", SR);
+    SGN_CHECK_ARG(blend == 0 || blend == 1, "sgn_composite_forward: blend must be 0 (alpha) or 1 (alpha2)");
+    if (R == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    if (blend == 0)
+        composite_fwd_kernel<0><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, ray_color,
+                                                                         opacity, acc_transmission, blend_weight, bg_transmission);
+    else
+        composite_fwd_kernel<1><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, ray_color,
+                                                                         opacity, acc_transmission, blend_weight, bg_transmission);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_composite_backward(const float* decoded, const float* ray_dist, const uint8_t* valid, const float* bg, int blend,
+                                      int64_t R, int SR, const float* d_ray_color, const float* d_opacity,
+                                      const float* d_blend_weight, const float* d_bg_transmission, float* d_decoded, void* stream)
+{
+    SGN_CHECK_ARG(R >= 0 && SR > 0 && SR <= 32 * COMP_MAX_CHUNKS, "sgn_composite_backward: SR=%d out of range", SR);
+    SGN_CHECK_ARG(blend == 0 || blend == 1, "sgn_composite_backward: blend must be 0 or 1");
+    if (R == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    if (blend == 0)
+        composite_bwd_kernel<0><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
+                                                                         d_opacity, d_blend_weight, d_bg_transmission, (float4*)d_decoded);
+    else
+        composite_bwd_kernel<1><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
+                                                                         d_opacity, d_blend_weight, d_bg_transmission, (float4*)d_decoded);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_fill_invalid(const int8_t* ray_mask, const float* bg, int64_t R, int SR, float* ray_color, float* opacity,
+                                float* bg_transmission, void* stream)
+{
+    if (R == 0) return SGN_OK;
+    fill_invalid_kernel<<<cdiv(R, 256), 256, 0, (cudaStream_t)stream>>>(ray_mask, bg, R, SR, ray_color, opacity, bg_transmission);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}

@@ -1,0 +1,236 @@
+// query.cu -- ray march over the occupancy bitmask + K-nearest-within-radius search, all rays in one pass.
+//
+// Reference: ray positions (models/rendering/diff_ray_marching.py:387), mask_raypos, the cumsum glue,
+// get_shadingloc[_with_semantic], query_neigh_along_ray_layered[_semantic_guidance]
+// (models/neural_points/query_point_indices_worldcoords.py:413-681, :811-938).
+//
+// march_kernel: one warp per ray.  Lanes test 32 consecutive depth candidates against the 1-bit/voxel
+// occupancy mask; ballot + prefix popcount gives the running index the reference obtains with
+// torch.cumsum (:843-844); the first SR occupied candidates become the shading samples.
+// knn_kernel: one thread per shading sample, visiting voxels and candidates in exactly the reference's
+// order (shell by shell, x outer / z inner, list order) with the same replace-farthest rule, so the K
+// slots come out in the same order as the sequential reference, ties included.  Candidates of a voxel
+// are consecutive float4 (x,y,z,index) records, so the inner loop is one 16-byte load per candidate.
+#include "common.cuh"
+
+struct SgnGrid {
+    SgnGridCfg cfg;
+    int64_t N, vol;
+    int32_t* cell_slot;
+    uint32_t* occ_bits;
+    int32_t* slot_coor;
+    int32_t* slot_count;
+    int32_t* slot_start;
+    float4* cand;
+    int32_t* counters;
+};
+
+namespace sgn {
+
+struct QueryGrid {
+    float ox, oy, oz, vx, vy, vz;
+    int dx, dy, dz;
+    const int32_t* cell_slot;
+    const uint32_t* occ_bits;
+    const int32_t* slot_start;
+    const float4* cand;
+};
+
+constexpr int MARCH_WARPS = 8;
+
+__global__ void __launch_bounds__(MARCH_WARPS * 32)
+march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restrict__ raydir, const float* __restrict__ t,
+             int t_per_ray, int64_t R, int D, int SR, const int32_t* __restrict__ ray_label, float* __restrict__ sample_loc_w,
+             int32_t* __restrict__ sample_mask, int32_t* __restrict__ sample_label, int8_t* __restrict__ ray_mask)
+{
+    const int lane = lane_id();
+    const int64_t r = (int64_t)blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const float cx = campos[0], cy = campos[1], cz = campos[2];
+    const float dx = raydir[3 * r], dy = raydir[3 * r + 1], dz = raydir[3 * r + 2];
+    const float* tr = t_per_ray ? t + r * D : t;
+    const int label = ray_label ? ray_label[r] : 0;
+    int cnt = 0;
+    for (int base = 0; base < D && cnt < SR; base += 32) {
+        const int d = base + lane;
+        bool occ = false;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (d < D) {
+            const float tv = __ldg(tr + d);
+            // campos + raydir * t with separate fp32 multiply and add, as torch evaluates it
+            px = __fadd_rn(cx, __fmul_rn(dx, tv));
+            py = __fadd_rn(cy, __fmul_rn(dy, tv));
+            pz = __fadd_rn(cz, __fmul_rn(dz, tv));
+            const int vx = vox_coord(px, g.ox, g.vx), vy = vox_coord(py, g.oy, g.vy), vz = vox_coord(pz, g.oz, g.vz);
+            if (vx >= 0 && vx < g.dx && vy >= 0 && vy < g.dy && vz >= 0 && vz < g.dz) {
+                const int64_t c = ((int64_t)vx * g.dy + vy) * g.dz + vz;
+                occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
+            }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, occ);
+        const int rank = cnt + __popc(b & ((1u << lane) - 1u));
+        if (occ && rank < SR) {
+            const int64_t o = r * SR + rank;
+            sample_loc_w[3 * o] = px; sample_loc_w[3 * o + 1] = py; sample_loc_w[3 * o + 2] = pz;
+            sample_mask[o] = 1;
+            if (sample_label) sample_label[o] = label;
+        }
+        cnt += __popc(b);
+    }
+    cnt = cnt < SR ? cnt : SR;
+    for (int s = cnt + lane; s < SR; s += 32) {  // unused slots stay at world (0,0,0), mask 0 (:835, :845)
+        const int64_t o = r * SR + s;
+        sample_loc_w[3 * o] = 0.f; sample_loc_w[3 * o + 1] = 0.f; sample_loc_w[3 * o + 2] = 0.f;
+        sample_mask[o] = 0;
+        if (sample_label) sample_label[o] = 0;
+    }
+    if (lane == 0) ray_mask[r] = 0;
+}
+
+template <int KT, bool SEMANTIC>
+__global__ void __launch_bounds__(128)
+knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, const float* __restrict__ sample_loc_w,
+           const int32_t* __restrict__ sample_mask, const int32_t* __restrict__ sample_label, const int32_t* __restrict__ pt_label,
+           const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
+           int8_t* __restrict__ ray_mask)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * SR) return;
+    const int64_t r = idx / SR;
+    int32_t out[KT];
+    float buf[KT];
+#pragma unroll
+    for (int i = 0; i < KT; i++) out[i] = -1;
+    int kid = 0;
+    if (__ldg(sample_mask + idx) > 0) {
+        const float cx = sample_loc_w[3 * idx], cy = sample_loc_w[3 * idx + 1], cz = sample_loc_w[3 * idx + 2];
+        const int fx = vox_coord(cx, g.ox, g.vx), fy = vox_coord(cy, g.oy, g.vy), fz = vox_coord(cz, g.oz, g.vz);
+        const int center_label = SEMANTIC ? sample_label[idx] : 0;
+        int far_ind = 0;
+        float far2 = 0.0f;
+        for (int layer = 0; layer < nlayer; layer++) {
+            const int xlo = max(-fx, -layer), xhi = min(g.dx - fx, layer + 1);
+            const int ylo = max(-fy, -layer), yhi = min(g.dy - fy, layer + 1);
+            const int zlo = max(-fz, -layer), zhi = min(g.dz - fz, layer + 1);
+            for (int x = xlo; x < xhi; x++) {
+                for (int y = ylo; y < yhi; y++) {
+                    const int64_t rowbase = ((int64_t)(fx + x) * g.dy + (fy + y)) * g.dz + fz;
+                    const bool inner = max(abs(x), abs(y)) != layer;  // only |z| == layer qualifies on this row
+                    for (int z = zlo; z < zhi; z++) {
+                        if (inner && abs(z) != layer) continue;
+                        const int occ = __ldg(g.cell_slot + rowbase + z);
+                        if (occ < 0) continue;
+                        const int b = __ldg(g.slot_start + occ), e = __ldg(g.slot_start + occ + 1);
+                        for (int q = b; q < e; q++) {
+                            const float4 c = __ldg(g.cand + q);
+                            const int pidx = __float_as_int(c.w);
+                            if (SEMANTIC) {
+                                const int label_v = pt_label[pidx];
+                                const int label_prob = (int)(__int_as_float(pt_label_prob_bits[(int64_t)pidx * 20 + label_v]) * 10.0f);
+                                const bool ok = (center_label == label_v) || (label_v == 0) || (center_label == 0) ||
+                                                ((center_label != label_v) && ((seconds % 10) <= (uint64_t)(int64_t)(1 - label_prob)));
+                                if (!ok) continue;
+                            }
+                            const float xv = __fsub_rn(c.x, cx), yv = __fsub_rn(c.y, cy), zv = __fsub_rn(c.z, cz);
+                            // nvcc contracts the reference's x*x + y*y + z*z to fma(z,z, fma(x,x, y*y))
+                            const float d2 = __fmaf_rn(zv, zv, __fmaf_rn(xv, xv, __fmul_rn(yv, yv)));
+                            if (radius2 == 0.0f || d2 <= radius2) {
+                                if (kid++ < K) {
+#pragma unroll
+                                    for (int i = 0; i < KT; i++)
+                                        if (i == kid - 1) { out[i] = pidx; buf[i] = d2; }
+                                    if (d2 > far2) { far2 = d2; far_ind = kid - 1; }
+                                } else if (d2 < far2) {
+#pragma unroll
+                                    for (int i = 0; i < KT; i++)
+                                        if (i == far_ind) { out[i] = pidx; buf[i] = d2; }
+                                    far2 = d2;
+#pragma unroll
+                                    for (int i = 0; i < KT; i++)
+                                        if (i < K && buf[i] > far2) { far2 = buf[i]; far_ind = i; }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (kid >= K) break;
+        }
+    }
+    int32_t* o = sample_pidx + idx * K;
+    if (KT == 8 && K == 8) {
+        ((int4*)o)[0] = make_int4(out[0], out[1], out[2], out[3]);
+        ((int4*)o)[1] = make_int4(out[4], out[5], out[6], out[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < KT; i++)
+            if (i < K) o[i] = out[i];
+    }
+    if (kid > 0) ray_mask[r] = 1;  // every writer stores the same value
+}
+
+}  // namespace sgn
+
+using namespace sgn;
+
+extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* raydir, const float* t, int t_per_ray, int64_t R, int D,
+                         int SR, int K, int kernel_size0, float radius2, const int32_t* ray_label, const int32_t* pt_label,
+                         const int32_t* pt_label_prob_bits, uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w,
+                         int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, void* stream)
+{
+    SGN_CHECK_ARG(G != nullptr, "sgn_query: grid is NULL");
+    SGN_CHECK_ARG(R >= 0 && D > 0 && SR > 0, "sgn_query: bad R/D/SR");
+    SGN_CHECK_ARG(K > 0 && K <= SGN_MAX_K, "sgn_query: K=%d out of range (1..%d)", K, SGN_MAX_K);
+    SGN_CHECK_ARG(sample_pidx && sample_loc_w && sample_mask && ray_mask, "sgn_query: NULL output");
+    const bool semantic = ray_label != nullptr;
+    SGN_CHECK_ARG(!semantic || (pt_label && pt_label_prob_bits && sample_label), "sgn_query: semantic guidance needs pt_label, pt_label_prob_bits and sample_label");
+    if (R == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    QueryGrid g;
+    g.ox = G->cfg.origin[0]; g.oy = G->cfg.origin[1]; g.oz = G->cfg.origin[2];
+    g.vx = G->cfg.vsize[0]; g.vy = G->cfg.vsize[1]; g.vz = G->cfg.vsize[2];
+    g.dx = G->cfg.dim[0]; g.dy = G->cfg.dim[1]; g.dz = G->cfg.dim[2];
+    g.cell_slot = G->cell_slot; g.occ_bits = G->occ_bits; g.slot_start = G->slot_start; g.cand = G->cand;
+
+    march_kernel<<<cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st>>>(g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
+                                                                   sample_mask, semantic ? sample_label : nullptr, ray_mask);
+    const int nlayer = (kernel_size0 + 1) / 2;
+    const int nb = cdiv(R * SR, 128);
+    if (K == 8) {
+        if (semantic)
+            knn_kernel<8, true><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
+        else
+            knn_kernel<8, false><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
+                                                      seconds_query, sample_pidx, ray_mask);
+    } else {
+        if (semantic)
+            knn_kernel<SGN_MAX_K, true><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
+        else
+            knn_kernel<SGN_MAX_K, false><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
+                                                              nullptr, seconds_query, sample_pidx, ray_mask);
+    }
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, int C, const int32_t* __restrict__ pidx, int64_t n, float* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    int64_t row = i / C;
+    int c = (int)(i - row * C);
+    int p = pidx[row];
+    p = p < 0 ? 0 : p;
+    out[i] = __ldg(table + (int64_t)p * C + c);
+}
+
+extern "C" int sgn_gather_rows(const float* table, int C, const int32_t* pidx, int64_t n_rows, float* out, void* stream)
+{
+    SGN_CHECK_ARG(C > 0 && n_rows >= 0, "sgn_gather_rows: bad sizes");
+    if (n_rows == 0) return SGN_OK;
+    gather_rows_kernel<<<cdiv(n_rows * C, 256), 256, 0, (cudaStream_t)stream>>>(table, C, pidx, n_rows, out);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}

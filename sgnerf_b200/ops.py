@@ -1,0 +1,352 @@
+"""Tensor-level host API over the C ABI (include/sgnerf_b200.h).
+
+PyTorch is plumbing here: device memory, the current stream and autograd bookkeeping.  All arithmetic of
+the hot path happens in libsgnerf_b200.so; there is no eager/PyTorch fallback -- CPU tensors are rejected.
+"""
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SgnAggCfg, SgnGridCfg, SgnPointGrads, SgnPointTables
+
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, dtype, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"sgnerf_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _workspace(nbytes, device):
+    return torch.empty((max(int(nbytes), 256) + 255) // 256 * 64, dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# occupancy grid
+# ---------------------------------------------------------------------------------------------------------
+def grid_hyperparameters(xyz, vsize, vscale, kernel_size, ranges, radius_limit_scale):
+    """Host-side grid parameters exactly as lighting_fast_querier.get_hyperparameters derives them
+    (reference models/neural_points/query_point_indices_worldcoords.py:66-92): fp32 min/max of the cloud,
+    clamp to `ranges`, pad by scaled_vsize*kernel/2 (a float64 product rounded to fp32), ceil of a float64
+    quotient for the dims, radius from the UNscaled voxel size.  Two small D2H reads; call once per cloud."""
+    vsize64 = np.asarray(vsize, dtype=np.float64)
+    vscale_i = np.asarray(vscale, dtype=np.int32)
+    scaled_vsize = (vsize64 * vscale_i).astype(np.float32)
+    mn = xyz.reshape(-1, 3).min(dim=0)[0].float()
+    mx = xyz.reshape(-1, 3).max(dim=0)[0].float()
+    if ranges is not None:
+        r = torch.as_tensor(np.asarray(ranges, dtype=np.float64), dtype=torch.float32, device=xyz.device)
+        mn = torch.maximum(mn, r[:3])
+        mx = torch.minimum(mx, r[3:])
+    pad64 = scaled_vsize.astype(np.float64) * np.asarray(kernel_size, dtype=np.int64) / 2
+    pad = torch.as_tensor(pad64, dtype=torch.float32, device=xyz.device)
+    mn = mn - pad
+    mx = mx + pad
+    ranges_np = torch.cat([mn, mx]).cpu().numpy().astype(np.float32)
+    vdim = (mx - mn).cpu().numpy().astype(np.float64) / vsize64
+    scaled_vdim = np.ceil(vdim / vscale_i).astype(np.int32)
+    radius = np.float32(radius_limit_scale * max(vsize[0], vsize[1]))
+    return SimpleNamespace(ranges=ranges_np, scaled_vsize=scaled_vsize, scaled_vdim=scaled_vdim,
+                           radius=radius, radius2=np.float32(radius * radius), vsize=list(vsize))
+
+
+class OccGrid:
+    """Device-resident occupancy grid (sgn_grid_build).  Build once per point-cloud version."""
+
+    def __init__(self, xyz, origin, scaled_vsize, dim, query_size, P, max_o, seconds_claim=0, seconds_fill=0,
+                 actual_n=None):
+        self.xyz = _dev(xyz.reshape(-1, 3), torch.float32, "xyz")
+        N = self.xyz.shape[0]
+        cfg = SgnGridCfg()
+        for i in range(3):
+            cfg.origin[i] = float(origin[i]); cfg.vsize[i] = float(scaled_vsize[i])
+            cfg.dim[i] = int(dim[i]); cfg.query_size[i] = int(query_size[i])
+        cfg.P, cfg.max_o = int(P), int(max_o)
+        cfg.seconds_claim, cfg.seconds_fill = int(seconds_claim), int(seconds_fill)
+        self.cfg = cfg
+        pb, sb = C.c_size_t(), C.c_size_t()
+        _lib.call("sgn_grid_workspace_bytes", N, C.byref(cfg), C.byref(pb), C.byref(sb))
+        self._persistent = _workspace(pb.value, self.xyz.device)
+        scratch = _workspace(sb.value, self.xyz.device)
+        handle = C.c_void_p()
+        _lib.call("sgn_grid_build", _ptr(self.xyz), N, N if actual_n is None else int(actual_n), C.byref(cfg),
+                  _ptr(self._persistent), self._persistent.numel() * 4, _ptr(scratch), scratch.numel() * 4,
+                  C.byref(handle), _stream())
+        self._handle = handle
+        self._scratch = scratch  # stream-ordered: keep alive until the build kernels have run
+        self.N, self.P, self.max_o = N, int(P), int(max_o)
+        self.dim = [int(d) for d in dim]
+
+    def buffer(self, which, dtype=torch.int32):
+        """Zero-copy view of an internal buffer (tests/tooling); see sgn_grid_buffer."""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.call("sgn_grid_buffer", self._handle, which, C.byref(p), C.byref(n))
+        base = self._persistent.data_ptr()
+        off = (p.value - base) // 4
+        width = 4 if which == 5 else 1
+        flat = self._persistent[off:off + n.value * width]
+        if which == 5:
+            return flat.view(n.value, 4)
+        return flat.view(dtype)
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            _lib.load().sgn_grid_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def query(grid, campos, raydir, t, SR, K, kernel_size0, radius2, ray_label=None, pt_label=None,
+          pt_label_prob_bits=None, seconds_query=0):
+    """sgn_query.  campos [3], raydir [R,3], t [D] or [R,D] (middle_point_ts).  Uncompacted outputs:
+    sample_pidx int32 [R,SR,K], sample_loc_w f32 [R,SR,3], sample_mask int32 [R,SR], ray_mask int8 [R]."""
+    raydir = _dev(raydir.reshape(-1, 3), torch.float32, "raydir")
+    campos = _dev(campos.reshape(3), torch.float32, "campos")
+    t = _dev(t, torch.float32, "t")
+    R = raydir.shape[0]
+    per_ray = 1 if t.dim() == 2 else 0
+    D = t.shape[-1]
+    if per_ray and t.shape[0] != R:
+        raise ValueError("t must be [D] or [R,D]")
+    dev = raydir.device
+    pidx = torch.empty(R, SR, K, dtype=torch.int32, device=dev)
+    loc_w = torch.empty(R, SR, 3, dtype=torch.float32, device=dev)
+    smask = torch.empty(R, SR, dtype=torch.int32, device=dev)
+    rmask = torch.empty(R, dtype=torch.int8, device=dev)
+    slabel = None
+    if ray_label is not None:
+        ray_label = _dev(ray_label.reshape(-1), torch.int32, "ray_label")
+        pt_label = _dev(pt_label.reshape(-1), torch.int32, "pt_label")
+        pt_label_prob_bits = _dev(pt_label_prob_bits.reshape(-1, 20), torch.int32, "pt_label_prob_bits")
+        slabel = torch.empty(R, SR, dtype=torch.int32, device=dev)
+    _lib.call("sgn_query", grid._handle, _ptr(campos), _ptr(raydir), _ptr(t), per_ray, R, D, SR, K, int(kernel_size0),
+              float(radius2), _ptr(ray_label), _ptr(pt_label), _ptr(pt_label_prob_bits), int(seconds_query),
+              _ptr(pidx), _ptr(loc_w), _ptr(smask), _ptr(slabel), _ptr(rmask), _stream())
+    return pidx, loc_w, smask, rmask
+
+
+def gather_rows(table, pidx):
+    """table [N,C] f32, pidx int32 [...] -> [..., C] with clamp(pidx, 0) (neural_points.py:956-972)."""
+    table = _dev(table, torch.float32, "table")
+    pidx = _dev(pidx, torch.int32, "pidx")
+    Cc = table.shape[-1]
+    out = torch.empty(pidx.shape + (Cc,), dtype=torch.float32, device=table.device)
+    _lib.call("sgn_gather_rows", _ptr(table), Cc, _ptr(pidx), pidx.numel(), _ptr(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# compositing
+# ---------------------------------------------------------------------------------------------------------
+def ray_dist(loc_pers, ray_valid, vsize_z, raydist_mode_unit=1):
+    loc_pers = _dev(loc_pers, torch.float32, "loc_pers")
+    valid = _dev(ray_valid, torch.uint8, "ray_valid")
+    R, SR = loc_pers.shape[-3], loc_pers.shape[-2]
+    out = torch.empty(loc_pers.shape[:-1], dtype=torch.float32, device=loc_pers.device)
+    _lib.call("sgn_ray_dist", _ptr(loc_pers), _ptr(valid), float(vsize_z), int(raydist_mode_unit), R, SR, _ptr(out), _stream())
+    return out
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, decoded, ray_dist_, valid_u8, bg, blend):
+        R, SR = decoded.shape[-3], decoded.shape[-2]
+        dev = decoded.device
+        lead = decoded.shape[:-2]
+        ray_color = torch.empty(lead + (3,), dtype=torch.float32, device=dev)
+        opacity = torch.empty(lead + (SR,), dtype=torch.float32, device=dev)
+        acc = torch.empty_like(opacity)
+        bw = torch.empty_like(opacity)
+        bgt = torch.empty(lead, dtype=torch.float32, device=dev)
+        n_rays = int(np.prod(lead)) if len(lead) else 1
+        _lib.call("sgn_composite_forward", _ptr(decoded), _ptr(ray_dist_), _ptr(valid_u8), _ptr(bg), blend, n_rays, SR,
+                  _ptr(ray_color), _ptr(opacity), _ptr(acc), _ptr(bw), _ptr(bgt), _stream())
+        ctx.save_for_backward(decoded, ray_dist_, valid_u8, bg)
+        ctx.blend, ctx.n_rays, ctx.SR = blend, n_rays, SR
+        ctx.mark_non_differentiable(acc)
+        return ray_color, opacity, acc, bw, bgt
+
+    @staticmethod
+    def backward(ctx, g_color, g_opacity, g_acc, g_bw, g_bgt):
+        decoded, ray_dist_, valid_u8, bg = ctx.saved_tensors
+        c = lambda g: None if g is None else g.contiguous().float()
+        g_color, g_opacity, g_bw, g_bgt = c(g_color), c(g_opacity), c(g_bw), c(g_bgt)
+        d_dec = torch.empty_like(decoded)
+        _lib.call("sgn_composite_backward", _ptr(decoded), _ptr(ray_dist_), _ptr(valid_u8), _ptr(bg), ctx.blend, ctx.n_rays,
+                  ctx.SR, _ptr(g_color), _ptr(g_opacity), _ptr(g_bw), _ptr(g_bgt), _ptr(d_dec), _stream())
+        return d_dec, None, None, None, None
+
+
+def composite(decoded, ray_dist_, ray_valid, bg_color=None, blend=0):
+    """Alpha compositing (differentiable w.r.t. `decoded`).  decoded [...,R,SR,4], ray_dist/ray_valid [...,R,SR].
+    Returns ray_color [...,R,3], opacity, acc_transmission, blend_weight [...,R,SR], bg_transmission [...,R]."""
+    decoded = _dev(decoded, torch.float32, "decoded")
+    ray_dist_ = _dev(ray_dist_, torch.float32, "ray_dist")
+    valid = _dev(ray_valid, torch.uint8, "ray_valid")
+    bg = _dev(bg_color.reshape(3), torch.float32, "bg_color") if bg_color is not None else None
+    if decoded.shape[-1] != 4:
+        raise ValueError("decoded must have 4 channels (sigma, r, g, b)")
+    return _Composite.apply(decoded, ray_dist_, valid, bg, int(blend))
+
+
+def fill_invalid(ray_mask, bg_color, ray_color, opacity=None, bg_transmission=None):
+    """In-place fill_invalid for uncompacted rows (models/neural_points_volumetric_model.py:158-195)."""
+    R = ray_mask.numel()
+    SR = opacity.shape[-1] if opacity is not None else 1
+    _lib.call("sgn_fill_invalid", _ptr(_dev(ray_mask, torch.int8, "ray_mask")), _ptr(_dev(bg_color.reshape(3), torch.float32, "bg")),
+              R, SR, _ptr(ray_color), _ptr(opacity), _ptr(bg_transmission), _stream())
+    return ray_color
+
+
+# ---------------------------------------------------------------------------------------------------------
+# aggregation
+# ---------------------------------------------------------------------------------------------------------
+def agg_cfg(feat_dim=32, num_feat_freqs=3, dist_xyz_freq=5, num_viewdir_freqs=4, width=256, n_block1=2, n_block2_bpnet=0,
+            label_dim=0, n_block3=2, n_color=4, act_super=1, leaky_slope=0.01):
+    return SgnAggCfg(feat_dim, num_feat_freqs, dist_xyz_freq, num_viewdir_freqs, width, n_block1, n_block2_bpnet, label_dim,
+                     n_block3, n_color, act_super, leaky_slope)
+
+
+def agg_layer_shapes(cfg):
+    n = _lib.load().sgn_agg_num_layers(C.byref(cfg))
+    if n < 0:
+        _lib.check(n, "sgn_agg_num_layers")
+    out = []
+    for i in range(n):
+        a, b = C.c_int(), C.c_int()
+        _lib.call("sgn_agg_layer_shape", C.byref(cfg), i, C.byref(a), C.byref(b))
+        out.append((a.value, b.value))
+    return out
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def _tables(xyz, embedding, color, dirs, conf, label_emb):
+    tb = SgnPointTables()
+    tb.xyz, tb.embedding, tb.color, tb.dir = xyz.data_ptr(), embedding.data_ptr(), color.data_ptr(), dirs.data_ptr()
+    tb.conf = conf.data_ptr() if conf is not None else None
+    tb.label_emb = label_emb.data_ptr() if label_emb is not None else None
+    tb.N = xyz.shape[0]
+    return tb
+
+
+class _Aggregate(torch.autograd.Function):
+    """decoded, ray_valid, loc_pers, weight, conf_coef = f(embedding, color, dir, conf, *weights, *biases)."""
+
+    @staticmethod
+    def forward(ctx, meta, embedding, color, dirs, conf, *wb):
+        nl = len(wb) // 2
+        weights, biases = list(wb[:nl]), list(wb[nl:])
+        cfg, xyz, label_emb, pidx, loc_w, raydir, campos, camrot, precision, want_aux = (
+            meta.cfg, meta.xyz, meta.label_emb, meta.pidx, meta.loc_w, meta.raydir, meta.campos, meta.camrot,
+            meta.precision, meta.want_aux)
+        R, SR, K = pidx.shape
+        dev = pidx.device
+        need_grad = any(ctx.needs_input_grad[1:])
+        if need_grad and precision != PRECISION_FP32:
+            raise RuntimeError("sgnerf_b200: training runs the fp32 path; the bf16 tensor-core path is forward-only")
+        nbytes = C.c_size_t()
+        _lib.call("sgn_agg_workspace_bytes", C.byref(cfg), R, SR, K, precision, int(need_grad), C.byref(nbytes))
+        ws = _workspace(nbytes.value, dev)
+        decoded = torch.empty(R, SR, 4, dtype=torch.float32, device=dev)
+        ray_valid = torch.empty(R, SR, dtype=torch.uint8, device=dev)
+        loc_pers = torch.empty(R, SR, 3, dtype=torch.float32, device=dev)
+        weight = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
+        conf_coef = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
+        tb = _tables(xyz, embedding, color, dirs, conf, label_emb)
+        _lib.call("sgn_agg_forward", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w),
+                  _ptr(raydir), _ptr(campos), _ptr(camrot), R, SR, K, precision, int(need_grad), _ptr(decoded), _ptr(ray_valid),
+                  _ptr(loc_pers), _ptr(weight), _ptr(conf_coef), _ptr(ws), ws.numel() * 4, _stream())
+        if need_grad:
+            ctx.meta, ctx.ws, ctx.nl = meta, ws, nl
+            ctx.save_for_backward(embedding, color, dirs, conf, *wb)
+        ctx.mark_non_differentiable(ray_valid, loc_pers)
+        if weight is None:
+            weight = torch.empty(0, device=dev)
+            conf_coef = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(weight)
+        return decoded, ray_valid, loc_pers, weight, conf_coef
+
+    @staticmethod
+    def backward(ctx, g_decoded, g_valid, g_loc, g_weight, g_conf):
+        meta, nl = ctx.meta, ctx.nl
+        embedding, color, dirs, conf, *wb = ctx.saved_tensors
+        weights, biases = list(wb[:nl]), list(wb[nl:])
+        R, SR, K = meta.pidx.shape
+        need = ctx.needs_input_grad
+        z = lambda t, flag: torch.zeros_like(t) if (flag and t is not None) else None
+        d_emb, d_col, d_dir, d_conf = z(embedding, need[1]), z(color, need[2]), z(dirs, need[3]), z(conf, need[4])
+        d_w = [z(w, need[5 + i]) for i, w in enumerate(weights)]
+        d_b = [z(b, need[5 + nl + i]) for i, b in enumerate(biases)]
+        g_decoded = g_decoded.contiguous().float() if g_decoded is not None else torch.zeros(R, SR, 4, device=meta.pidx.device)
+        g_conf_c = None
+        if g_conf is not None and meta.want_aux and g_conf.numel() == R * SR * K:
+            g_conf_c = g_conf.contiguous().float()
+        tb = _tables(meta.xyz, embedding, color, dirs, conf, meta.label_emb)
+        gr = SgnPointGrads()
+        gr.embedding = d_emb.data_ptr() if d_emb is not None else None
+        gr.color = d_col.data_ptr() if d_col is not None else None
+        gr.dir = d_dir.data_ptr() if d_dir is not None else None
+        gr.conf = d_conf.data_ptr() if d_conf is not None else None
+        _lib.call("sgn_agg_backward", C.byref(meta.cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(meta.pidx),
+                  _ptr(meta.loc_w), _ptr(meta.raydir), _ptr(meta.campos), _ptr(meta.camrot), R, SR, K, _ptr(g_decoded),
+                  _ptr(g_conf_c), _ptr_array(d_w), _ptr_array(d_b), C.byref(gr), _ptr(ctx.ws), ctx.ws.numel() * 4, _stream())
+        ctx.ws = None
+        return (None, d_emb, d_col, d_dir, d_conf, *d_w, *d_b)
+
+
+def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb, pidx, loc_w, raydir, campos, camrotc2w,
+              precision=PRECISION_FP32, want_aux=True):
+    """Fused gather + aggregation MLPs (sgn_agg_forward / sgn_agg_backward).
+
+    Tables: xyz [N,3], embedding [N,C], color [N,3], dirs [N,3], conf [N] (or None), label_emb [N,E] (or None).
+    Query outputs: pidx int32 [R,SR,K], loc_w [R,SR,3]; raydir [R,3]; campos [3]; camrotc2w [3,3].
+    Returns decoded [R,SR,4], ray_valid uint8 [R,SR], loc_pers [R,SR,3], weight [R,SR,K], conf_coef [R,SR,K]."""
+    f32 = torch.float32
+    meta = SimpleNamespace(cfg=cfg, xyz=_dev(xyz.reshape(-1, 3), f32, "xyz"), label_emb=_dev(label_emb, f32, "label_emb"),
+                           pidx=_dev(pidx, torch.int32, "pidx"), loc_w=_dev(loc_w, f32, "loc_w"),
+                           raydir=_dev(raydir.reshape(-1, 3), f32, "raydir"), campos=_dev(campos.reshape(3), f32, "campos"),
+                           camrot=_dev(camrotc2w.reshape(3, 3), f32, "camrotc2w"), precision=int(precision), want_aux=bool(want_aux))
+    N = meta.xyz.shape[0]
+    embedding = _dev(embedding.reshape(N, -1), f32, "embedding")
+    color = _dev(color.reshape(N, 3), f32, "color")
+    dirs = _dev(dirs.reshape(N, 3), f32, "dirs")
+    conf = _dev(conf.reshape(N), f32, "conf") if conf is not None else None
+    if meta.label_emb is not None:
+        meta.label_emb = meta.label_emb.reshape(N, -1)
+    shapes = agg_layer_shapes(cfg)
+    if len(weights) != len(shapes) or len(biases) != len(shapes):
+        raise ValueError(f"expected {len(shapes)} weight/bias tensors, got {len(weights)}/{len(biases)}")
+    ws_, bs_ = [], []
+    for (cin, cout), w, b in zip(shapes, weights, biases):
+        if tuple(w.shape) != (cout, cin) or b.numel() != cout:
+            raise ValueError(f"layer shape mismatch: expected weight {(cout, cin)}, got {tuple(w.shape)}")
+        ws_.append(_dev(w, f32, "weight")); bs_.append(_dev(b, f32, "bias"))
+    return _Aggregate.apply(meta, embedding, color, dirs, conf, *ws_, *bs_)

@@ -1,0 +1,79 @@
+"""CPU: the oracle restatement against the golden vectors produced by the REFERENCE's own modules
+(tests/golden/make_golden.py).  Bit-exact where the restatement uses the same torch ops."""
+import ast
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import query_ref as qr
+from oracle import render_ref as rr
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def test_positional_encoding_and_ray_positions(golden_dir):
+    g = load(golden_dir, "pe_rays")
+    x = torch.from_numpy(g["pe_x"])
+    for F, ori in ((3, False), (5, False), (4, True)):
+        assert np.array_equal(rr.positional_encoding(x, F, ori=ori).numpy(), g[f"pe_{F}_{int(ori)}"])
+    campos, raydir = torch.from_numpy(g["rays_campos"]), torch.from_numpy(g["rays_dir"])
+    for jit in (0.0, 0.3):
+        mid = torch.from_numpy(g[f"rays_mid_{jit}"])
+        assert np.array_equal(qr.raypos_from_t(campos, raydir, mid[0]).numpy(), g[f"rays_pos_{jit}"])
+    _, mid = qr.near_far_linear_ray_generation(campos, raydir, 400, 0.1, 8.0, jitter=0.0)
+    assert np.array_equal(mid.numpy(), g["rays_mid_0.0"])
+
+
+@pytest.mark.parametrize("blend", ["alpha", "alpha2"])
+def test_ray_march(golden_dir, blend):
+    g = load(golden_dir, "ray_march")
+    feats = torch.from_numpy(g["feats"]).requires_grad_(True)
+    out = rr.ray_march(torch.from_numpy(g["dist"]), torch.from_numpy(g["valid"]), feats, torch.from_numpy(g["bg"]), blend)
+    names = ["ray_color", "point_color", "opacity", "acc_transmission", "blend_weight", "bg_transmission", "bg_blend_weight"]
+    for n, a in zip(names, out):
+        np.testing.assert_allclose(a.detach().numpy(), g[f"{blend}_{n}"], rtol=0, atol=1e-6, err_msg=n)
+    ((out[0] * torch.from_numpy(g[f"{blend}_cot_color"])).sum() + (out[2] * torch.from_numpy(g[f"{blend}_cot_opacity"])).sum()).backward()
+    np.testing.assert_allclose(feats.grad.numpy(), g[f"{blend}_grad_feats"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["agg_small_plain", "agg_small_semantic", "agg_canonical_plain", "agg_canonical_semantic"])
+def test_aggregator_forward_backward(golden_dir, name):
+    g = load(golden_dir, name)
+    cfg = SimpleNamespace(**ast.literal_eval(str(g["cfg"])))
+    if "P_seed" in g:
+        P = rr.init_params(cfg, seed=int(g["P_seed"]), bias_scale=0.1)
+        sig = np.array([float(sum(v.double().sum() for v in P.values())), float(sum(v.double().abs().sum() for v in P.values()))])
+        np.testing.assert_allclose(sig, g["P_signature"], rtol=1e-9)       # the seeded weights are the ones the golden run used
+    else:
+        P = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("P_")}
+    P = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    inp = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in_")}
+    leaves = {}
+    for k in ("sampled_color", "sampled_dir", "sampled_conf", "sampled_embedding", "sampled_label_embedding"):
+        if k in inp:
+            inp[k] = inp[k].clone().requires_grad_(True)
+            leaves[k] = inp[k]
+    out, ray_valid, weight, conf = rr.aggregator_forward(
+        P, cfg, inp["sampled_color"], inp.get("sampled_label_embedding"), inp["sampled_dir"], inp["sampled_conf"],
+        inp["sampled_embedding"], inp["sampled_xyz_pers"], inp["sampled_xyz"], inp["sample_pnt_mask"], inp["sample_loc"],
+        inp["sample_loc_w"], inp["sample_ray_dirs"])
+    np.testing.assert_allclose(out.detach().numpy(), g["out_decoded"], rtol=0, atol=1e-6)
+    assert np.array_equal(ray_valid.numpy(), g["out_ray_valid"])
+    np.testing.assert_allclose(weight.detach().numpy(), g["out_weight"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(conf.detach().numpy(), g["out_conf"], rtol=0, atol=1e-7)
+    ((out * torch.from_numpy(g["cot_decoded"])).sum() + (conf * torch.from_numpy(g["cot_conf"])).sum()).backward()
+    for k, v in leaves.items():
+        ref = g["g_" + k]
+        np.testing.assert_allclose(v.grad.numpy(), ref, rtol=1e-4, atol=1e-6 * max(1.0, np.abs(ref).max()), err_msg=k)
+    for k, v in P.items():
+        if "gw_" + k in g:
+            ref = g["gw_" + k]
+            np.testing.assert_allclose(v.grad.numpy(), ref, rtol=1e-4, atol=1e-5 * max(1e-3, np.abs(ref).max()), err_msg=k)
+        else:
+            s = g["sig_gw_" + k]
+            np.testing.assert_allclose([float(v.grad.double().sum()), float(v.grad.double().abs().sum())], s, rtol=1e-4, atol=1e-6)
