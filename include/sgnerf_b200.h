@@ -40,6 +40,8 @@ extern "C" {
 
 const char* sgn_last_error(void);
 int sgn_version(void);
+/* Number of kernel launches this library has issued so far in the process (host counter, not thread-safe). */
+uint64_t sgn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Occupancy grid ("occ vox").  Replaces claim_occ / map_coor2occ / fill_occ2pnts and build_occ_vox
@@ -72,7 +74,7 @@ int sgn_grid_destroy(SgnGrid* g);
 /* Device pointers of the built structures, for tests and tooling (all int32 unless noted):
  *   0 cell_slot [X*Y*Z] (= coor_2_occ), 1 occ_bits uint32[ceil(X*Y*Z/32)] (= coor_occ as a bitmask),
  *   2 slot_coor [max_o*3] (= occ_2_coor), 3 slot_count [max_o] (= occ_numpnts, uncapped),
- *   4 slot_start [max_o] (offset of the slot's list in cand), 5 cand float4[(x,y,z,bits(pidx))],
+ *   4 slot_start [max_o+1] (offset of the slot's list in cand), 5 cand float4[(x,y,z,bits(pidx))],
  *   6 counters [4]: {n_claimed (= occ_idx), n_candidates, 0, 0}.                                  */
 int sgn_grid_buffer(const SgnGrid* g, int which, void** ptr, int64_t* n_elements);
 

@@ -42,6 +42,7 @@ class SgnPointGrads(C.Structure):
 SIGNATURES = {
     "sgn_last_error": (C.c_char_p, []),
     "sgn_version": (c_int, []),
+    "sgn_launch_count": (c_u64, []),
     "sgn_grid_workspace_bytes": (c_int, [c_i64, C.POINTER(SgnGridCfg), C.POINTER(c_size), C.POINTER(c_size)]),
     "sgn_grid_build": (c_int, [c_void, c_i64, c_i64, C.POINTER(SgnGridCfg), c_void, c_size, c_void, c_size,
                                C.POINTER(c_void), c_void]),

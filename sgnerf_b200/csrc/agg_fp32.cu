@@ -392,7 +392,7 @@ static int pack_weights(const AggPlan& P, const float* const* weights, AggWs& ws
     for (int l = 0; l < P.n_layers; l++) {
         const LayerInfo& L = P.layers[l];
         const int n = L.npad * L.kpad;
-        pack_weight_kernel<<<cdiv(n, 256), 256, 0, st>>>(weights[l], L.out, L.in, L.npad, L.kpad, ws.Wt[l], ws.Wp[l]);
+        launch(pack_weight_kernel, cdiv(n, 256), 256, 0, st, weights[l], L.out, L.in, L.npad, L.kpad, ws.Wt[l], ws.Wp[l]);
     }
     SGN_LAUNCH_CHECK();
     return SGN_OK;
@@ -408,14 +408,14 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     const int Tm = (int)(S * K), Sm = (int)S;
     float* loc_pers = loc_pers_out ? loc_pers_out : ws.loc_pers;
     SGN_CUDA(cudaMemsetAsync(decoded, 0, sizeof(float) * 4 * (size_t)S, st));
-    agg_prepare_kernel<<<cdiv(S, 128), 128, 0, st>>>(in, S, K, loc_pers, ws.wc, ws.weight_n, weight_out, conf_out, ray_valid, ws.nvalid, ws.svalid);
+    launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, ws.weight_n, weight_out, conf_out, ray_valid, ws.nvalid, ws.svalid);
     int rc;
     if ((rc = exclusive_scan_i32(ws.nvalid, ws.tuple_start, S, ws.partials, st))) return rc;
     if ((rc = exclusive_scan_i32(ws.svalid, ws.sample_cidx, S, ws.partials, st))) return rc;
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
-    agg_index_kernel<<<cdiv(S, 128), 128, 0, st>>>(in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
-    agg_gather_kernel<<<cdiv(Tm, 8), 256, 0, st>>>(in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
+    launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
+    launch(agg_gather_kernel, cdiv(Tm, 8), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
     SGN_LAUNCH_CHECK();
 
     // per-tuple layers
@@ -434,8 +434,8 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     }
     const float* Hlast = cur;
     const int la = P.alpha_layer;
-    agg_alpha_kernel<<<cdiv(Tm, 8), 256, 0, st>>>(Hlast, d.W, weights[la], biases[la], T_ptr, Tm, ws.araw);
-    agg_ksum_kernel<<<cdiv(Sm, 8), 256, 0, st>>>(in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, ws.araw, ws.C0, ws.sigma);
+    launch(agg_alpha_kernel, cdiv(Tm, 8), 256, 0, st, Hlast, d.W, weights[la], biases[la], T_ptr, Tm, ws.araw);
+    launch(agg_ksum_kernel, cdiv(Sm, 8), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, ws.araw, ws.C0, ws.sigma);
     SGN_LAUNCH_CHECK();
 
     // colour MLP
@@ -451,7 +451,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
         cur = out; cur_ld = d.WC; cur_k = d.WC;
     }
     const int ll = P.n_layers - 1;
-    agg_rgb_kernel<<<cdiv(Sm, 8), 256, 0, st>>>(d, S_ptr, Sm, ws.csample, cur, cur_ld, weights[ll], biases[ll], ws.sigma, decoded, ws.sig);
+    launch(agg_rgb_kernel, cdiv(Sm, 8), 256, 0, st, d, S_ptr, Sm, ws.csample, cur, cur_ld, weights[ll], biases[ll], ws.sigma, decoded, ws.sig);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
@@ -540,7 +540,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         if (!out || m_max <= 0) return SGN_OK;
         const int rpb = 512;
         dim3 grid(cdiv(m_max, rpb), cdiv(ncols, 128));
-        colsum_kernel<<<grid, 128, 0, st>>>(dZ, ld, ncols, m_ptr, m_max, rpb, out);
+        launch(colsum_kernel, grid, 128, 0, st, dZ, ld, ncols, m_ptr, m_max, rpb, out);
         SGN_LAUNCH_CHECK();
         return SGN_OK;
     };
@@ -556,7 +556,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     const float* Clast = P.n_color_hidden > 0 ? ws.CH[P.n_color_hidden - 1] : ws.C0;
     const int Clast_ld = P.n_color_hidden > 0 ? d.WC : d.kc0pad;
     const int Clast_k = P.n_color_hidden > 0 ? d.WC : d.kc0;
-    agg_rgb_bwd_kernel<<<cdiv(Sm, 256), 256, 0, st>>>(d, S_ptr, Sm, ws.csample, d_decoded, ws.sig, ws.d_raw);
+    launch(agg_rgb_bwd_kernel, cdiv(Sm, 256), 256, 0, st, d, S_ptr, Sm, ws.csample, d_decoded, ws.sig, ws.d_raw);
     SGN_LAUNCH_CHECK();
     if ((rc = wgrad(ws.d_raw, 8, 3, Clast, Clast_ld, Clast_k, d_weights ? d_weights[ll] : nullptr, P.layers[ll].in, S_ptr, Sm))) return rc;
     if ((rc = bias_grad(ws.d_raw, 8, 3, S_ptr, Sm, d_biases ? d_biases[ll] : nullptr))) return rc;
@@ -594,11 +594,11 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     const float* Hlast = ws.H[nt - 1];
     const int la = P.alpha_layer;
     float* dZ = ws.dZ[0];
-    agg_ksum_bwd_kernel<<<cdiv(Tm, 8), 256, 0, st>>>(in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast, ws.araw,
+    launch(agg_ksum_bwd_kernel, cdiv(Tm, 8), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast, ws.araw,
                                                     weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf);
     SGN_LAUNCH_CHECK();
     if (d_conf_coef && g.conf) {
-        agg_conf_out_bwd_kernel<<<cdiv(S * K, 256), 256, 0, st>>>(pidx, S * K, d_conf_coef, g.conf);
+        launch(agg_conf_out_bwd_kernel, cdiv(S * K, 256), 256, 0, st, pidx, S * K, d_conf_coef, g.conf);
         SGN_LAUNCH_CHECK();
     }
     if ((rc = wgrad(ws.d_araw, 1, 1, Hlast, d.W, d.W, d_weights ? d_weights[la] : nullptr, d.W, T_ptr, Tm))) return rc;
@@ -634,7 +634,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         }
     }
     if (g.embedding || g.color || g.dir) {
-        agg_scatter_kernel<<<cdiv(Tm, 8), 256, 0, st>>>(in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
+        launch(agg_scatter_kernel, cdiv(Tm, 8), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;

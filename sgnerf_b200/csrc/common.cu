@@ -6,6 +6,7 @@
 namespace sgn {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...)
 {
@@ -108,9 +109,9 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* part
         SGN_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
         return SGN_OK;
     }
-    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, partials);
-    scan_partials_kernel<<<1, SCAN_THREADS, 0, st>>>(partials, nb);
-    scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, partials, nb);
+    launch(scan_reduce_kernel, nb, SCAN_THREADS, 0, st, in, n, partials);
+    launch(scan_partials_kernel, 1, SCAN_THREADS, 0, st, partials, nb);
+    launch(scan_apply_kernel, nb, SCAN_THREADS, 0, st, in, out, n, partials, nb);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
@@ -119,3 +120,4 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* part
 
 extern "C" const char* sgn_last_error(void) { return sgn::g_err; }
 extern "C" int sgn_version(void) { return 100; }
+extern "C" uint64_t sgn_launch_count(void) { return sgn::g_launch_count; }

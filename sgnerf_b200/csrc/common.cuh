@@ -55,6 +55,16 @@ constexpr int SCAN_TILE = 2048;
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* partials, cudaStream_t st);
 static inline size_t scan_partials_count(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1); }
 
+// Every kernel launch of the library goes through launch(): it counts launches (sgn_launch_count) so a
+// caller can state how many of OUR kernels ran inside a timed region.
+extern unsigned long long g_launch_count;
+template <typename... KArgs, typename... Args>
+static inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    ++g_launch_count;
+    kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ----
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

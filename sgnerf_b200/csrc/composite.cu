@@ -231,7 +231,7 @@ extern "C" int sgn_ray_dist(const float* loc_pers, const uint8_t* ray_valid, flo
 {
     SGN_CHECK_ARG(R >= 0 && SR > 0, "sgn_ray_dist: bad R/SR");
     if (R == 0) return SGN_OK;
-    ray_dist_kernel<<<comp_grid(R), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(loc_pers, ray_valid, vsize_z, raydist_mode_unit, R, SR, ray_dist);
+    launch(ray_dist_kernel, comp_grid(R), COMP_WARPS * 32, 0, (cudaStream_t)stream, loc_pers, ray_valid, vsize_z, raydist_mode_unit, R, SR, ray_dist);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
@@ -245,10 +245,10 @@ extern "C" int sgn_composite_forward(const float* decoded, const float* ray_dist
     if (R == 0) return SGN_OK;
     auto st = (cudaStream_t)stream;
     if (blend == 0)
-        composite_fwd_kernel<0><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, ray_color,
+        launch(composite_fwd_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, ray_dist, valid, bg, R, SR, ray_color,
                                                                          opacity, acc_transmission, blend_weight, bg_transmission);
     else
-        composite_fwd_kernel<1><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, ray_color,
+        launch(composite_fwd_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, ray_dist, valid, bg, R, SR, ray_color,
                                                                          opacity, acc_transmission, blend_weight, bg_transmission);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
@@ -263,10 +263,10 @@ extern "C" int sgn_composite_backward(const float* decoded, const float* ray_dis
     if (R == 0) return SGN_OK;
     auto st = (cudaStream_t)stream;
     if (blend == 0)
-        composite_bwd_kernel<0><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
+        launch(composite_bwd_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
                                                                          d_opacity, d_blend_weight, d_bg_transmission, (float4*)d_decoded);
     else
-        composite_bwd_kernel<1><<<comp_grid(R), COMP_WARPS * 32, 0, st>>>((const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
+        launch(composite_bwd_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
                                                                          d_opacity, d_blend_weight, d_bg_transmission, (float4*)d_decoded);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
@@ -276,7 +276,7 @@ extern "C" int sgn_fill_invalid(const int8_t* ray_mask, const float* bg, int64_t
                                 float* bg_transmission, void* stream)
 {
     if (R == 0) return SGN_OK;
-    fill_invalid_kernel<<<cdiv(R, 256), 256, 0, (cudaStream_t)stream>>>(ray_mask, bg, R, SR, ray_color, opacity, bg_transmission);
+    launch(fill_invalid_kernel, cdiv(R, 256), 256, 0, (cudaStream_t)stream, ray_mask, bg, R, SR, ray_color, opacity, bg_transmission);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

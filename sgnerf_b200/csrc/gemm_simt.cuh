@@ -117,7 +117,7 @@ static inline int launch_gemm_nn(const GemmNN& p, cudaStream_t st)
 {
     if (p.m_max <= 0) return SGN_OK;
     dim3 grid(cdiv(p.m_max, GBM), cdiv(p.N, GBN));
-    gemm_nn_kernel<<<grid, GTHREADS, 0, st>>>(p);
+    launch(gemm_nn_kernel, grid, GTHREADS, 0, st, p);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
@@ -218,7 +218,7 @@ static inline int launch_gemm_tn(GemmTN p, cudaStream_t st)
     mpb = ((mpb < 256 ? 256 : mpb) + GBK - 1) / GBK * GBK;
     p.m_per_block = mpb;
     dim3 grid(cdiv(p.P, GBM), cdiv(p.Q, GBN), cdiv(p.m_max, mpb));
-    gemm_tn_kernel<<<grid, GTHREADS, 0, st>>>(p);
+    launch(gemm_tn_kernel, grid, GTHREADS, 0, st, p);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

@@ -354,18 +354,18 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
 
     if (actual_n > 0) {
         const int nb = cdiv(actual_n, T);
-        cell_min_kernel<<<nb, T, 0, st>>>(xyz, actual_n, g, (uint32_t*)G->cell_slot);
-        first_flag_kernel<<<cdiv(N, T), T, 0, st>>>(xyz, actual_n, N, g, (const uint32_t*)G->cell_slot, flag);
+        launch(cell_min_kernel, nb, T, 0, st, xyz, actual_n, g, (uint32_t*)G->cell_slot);
+        launch(first_flag_kernel, cdiv(N, T), T, 0, st, xyz, actual_n, N, g, (const uint32_t*)G->cell_slot, flag);
         GRID_TRY(exclusive_scan_i32(flag, rank, N, partials, st));
-        claim_bid_kernel<<<cdiv(N, T), T, 0, st>>>(N, flag, rank, max_o, cfg->seconds_claim, record_writer, G->counters);
-        claim_resolve_kernel<<<nb, T, 0, st>>>(xyz, actual_n, g, flag, rank, cfg->seconds_claim, record_writer, G->cell_slot, G->slot_coor);
-        slot_count_kernel<<<nb, T, 0, st>>>(xyz, actual_n, g, G->cell_slot, G->slot_count);
+        launch(claim_bid_kernel, cdiv(N, T), T, 0, st, N, flag, rank, max_o, cfg->seconds_claim, record_writer, G->counters);
+        launch(claim_resolve_kernel, nb, T, 0, st, xyz, actual_n, g, flag, rank, cfg->seconds_claim, record_writer, G->cell_slot, G->slot_coor);
+        launch(slot_count_kernel, nb, T, 0, st, xyz, actual_n, g, G->cell_slot, G->slot_count);
         GRID_TRY(exclusive_scan_i32(G->slot_count, seg_start, max_o, partials, st));
-        slot_fill_kernel<<<nb, T, 0, st>>>(xyz, actual_n, g, G->cell_slot, seg_start, cursor, seg);
-        slot_canon_kernel<<<cdiv(max_o, T), T, 0, st>>>(max_o, cfg->P, cfg->seconds_fill, G->slot_count, seg_start, seg, ncap);
+        launch(slot_fill_kernel, nb, T, 0, st, xyz, actual_n, g, G->cell_slot, seg_start, cursor, seg);
+        launch(slot_canon_kernel, cdiv(max_o, T), T, 0, st, max_o, cfg->P, cfg->seconds_fill, G->slot_count, seg_start, seg, ncap);
         GRID_TRY(exclusive_scan_i32(ncap, G->slot_start, max_o, partials, st));
-        emit_cand_kernel<<<cdiv(max_o, T), T, 0, st>>>(max_o, xyz, seg_start, seg, G->slot_start, G->cand, G->counters);
-        dilate_kernel<<<cdiv(max_o, T), T, 0, st>>>(g, G->counters, G->slot_coor, G->occ_bits);
+        launch(emit_cand_kernel, cdiv(max_o, T), T, 0, st, max_o, xyz, seg_start, seg, G->slot_start, G->cand, G->counters);
+        launch(dilate_kernel, cdiv(max_o, T), T, 0, st, g, G->counters, G->slot_coor, G->occ_bits);
         GRID_CUDA(cudaGetLastError());
     } else {
         GRID_CUDA(cudaMemsetAsync(G->slot_start, 0, sizeof(int32_t) * ((size_t)max_o + 1), st));

@@ -192,23 +192,23 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     g.dx = G->cfg.dim[0]; g.dy = G->cfg.dim[1]; g.dz = G->cfg.dim[2];
     g.cell_slot = G->cell_slot; g.occ_bits = G->occ_bits; g.slot_start = G->slot_start; g.cand = G->cand;
 
-    march_kernel<<<cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st>>>(g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
+    launch(march_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
                                                                    sample_mask, semantic ? sample_label : nullptr, ray_mask);
     const int nlayer = (kernel_size0 + 1) / 2;
     const int nb = cdiv(R * SR, 128);
     if (K == 8) {
         if (semantic)
-            knn_kernel<8, true><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+            launch(knn_kernel<8, true>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
                                                      pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
         else
-            knn_kernel<8, false><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
+            launch(knn_kernel<8, false>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
                                                       seconds_query, sample_pidx, ray_mask);
     } else {
         if (semantic)
-            knn_kernel<SGN_MAX_K, true><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+            launch(knn_kernel<SGN_MAX_K, true>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
                                                              pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
         else
-            knn_kernel<SGN_MAX_K, false><<<nb, 128, 0, st>>>(g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
+            launch(knn_kernel<SGN_MAX_K, false>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
                                                               nullptr, seconds_query, sample_pidx, ray_mask);
     }
     SGN_LAUNCH_CHECK();
@@ -230,7 +230,7 @@ extern "C" int sgn_gather_rows(const float* table, int C, const int32_t* pidx, i
 {
     SGN_CHECK_ARG(C > 0 && n_rows >= 0, "sgn_gather_rows: bad sizes");
     if (n_rows == 0) return SGN_OK;
-    gather_rows_kernel<<<cdiv(n_rows * C, 256), 256, 0, (cudaStream_t)stream>>>(table, C, pidx, n_rows, out);
+    launch(gather_rows_kernel, cdiv(n_rows * C, 256), 256, 0, (cudaStream_t)stream, table, C, pidx, n_rows, out);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

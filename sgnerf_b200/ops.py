@@ -287,11 +287,10 @@ class _Aggregate(torch.autograd.Function):
         if need_grad:
             ctx.meta, ctx.ws, ctx.nl = meta, ws, nl
             ctx.save_for_backward(embedding, color, dirs, conf, *wb)
-        ctx.mark_non_differentiable(ray_valid, loc_pers)
         if weight is None:
             weight = torch.empty(0, device=dev)
             conf_coef = torch.empty(0, device=dev)
-        ctx.mark_non_differentiable(weight)
+        ctx.mark_non_differentiable(ray_valid, loc_pers, weight)
         return decoded, ray_valid, loc_pers, weight, conf_coef
 
     @staticmethod

@@ -1,0 +1,92 @@
+"""Full per-ray render path on one GPU: query -> aggregation -> step sizes -> compositing -> fill_invalid.
+
+This is the call sequence of the reference's NeuralPointsRayMarching.forward + fill_invalid
+(models/neural_points_volumetric_model.py:541-626, :158-195) with the three differences the B200 design makes:
+the occupancy grid is built once per point-cloud version instead of once per call, all rays of a frame go
+through in one pass (the reference chunks a 640x480 frame into 134 calls, run/test_ft.py:138-187), and rows stay
+uncompacted (ray_mask marks hits) so there is no host synchronisation anywhere in the path.
+"""
+from types import SimpleNamespace
+
+import torch
+
+from . import ops
+
+
+def query_options(vsize=(0.008, 0.008, 0.008), vscale=(2, 2, 2), kernel_size=(3, 3, 3), query_size=(3, 3, 3),
+                  ranges=(-10.0, -10.0, -10.0, 10.0, 10.0, 10.0), radius_limit_scale=4.0, max_o=610000, P=26, SR=24, K=8,
+                  z_depth_dim=400):
+    """Canonical query hyper-parameters."""
+    return SimpleNamespace(vsize=list(vsize), vscale=list(vscale), kernel_size=list(kernel_size), query_size=list(query_size),
+                           ranges=list(ranges) if ranges is not None else None, radius_limit_scale=radius_limit_scale,
+                           max_o=max_o, P=P, SR=SR, K=K, z_depth_dim=z_depth_dim)
+
+
+def middle_point_ts(near, far, D, device, jitter=0.0, n_rays=None, generator=None):
+    """Depths of the D candidates per ray, with the reference's op sequence (diff_ray_marching.py:370-386):
+    linspace -> lerp -> segment * (1 + jitter (U - .5)) -> cumsum -> midpoints.  [D] when jitter == 0, else [R,D]."""
+    tvals = torch.linspace(0, 1, D + 1, device=device).view(1, -1)
+    tvals = near * (1 - tvals) + far * tvals
+    seg = tvals[..., 1:] - tvals[..., :-1]
+    if jitter > 0:
+        rand = torch.rand((1, n_rays, D), device=device, generator=generator)
+        seg = seg * (1 + jitter * (rand - 0.5))
+    else:
+        seg = (seg * (1 + 0.0 * seg))[None]
+    end = torch.cumsum(seg, dim=2)
+    end = torch.cat([torch.zeros((end.shape[0], end.shape[1], 1), device=device), end], dim=2)
+    end = near + end
+    mid = (end[:, :, :-1] + end[:, :, 1:]) / 2
+    return mid[0] if jitter > 0 else mid[0, 0]
+
+
+class RenderScene:
+    """Device-resident state of one scene: xyz + per-point tables, aggregator parameters, occupancy grid."""
+
+    def __init__(self, xyz, embedding, color, dirs, conf, weights, biases, agg_cfg, qopt, label_emb=None, device="cuda"):
+        f = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.float32).to(device).contiguous()
+        self.xyz = f(xyz).reshape(-1, 3)
+        N = self.xyz.shape[0]
+        self.embedding, self.color, self.dirs = f(embedding).reshape(N, -1), f(color).reshape(N, 3), f(dirs).reshape(N, 3)
+        self.conf = f(conf).reshape(N) if conf is not None else None
+        self.label_emb = f(label_emb).reshape(N, -1) if label_emb is not None else None
+        self.weights = [f(w) for w in weights]
+        self.biases = [f(b) for b in biases]
+        self.agg_cfg, self.qopt, self.device = agg_cfg, qopt, device
+        self._grid = None
+        self._hp = None
+
+    def invalidate_grid(self):
+        """Call after the point cloud changed (grow / prune / set_points)."""
+        if self._grid is not None:
+            self._grid.close()
+        self._grid, self._hp = None, None
+
+    def grid(self, seconds=(0, 0)):
+        if self._grid is None:
+            q = self.qopt
+            self._hp = ops.grid_hyperparameters(self.xyz, q.vsize, q.vscale, q.kernel_size, q.ranges, q.radius_limit_scale)
+            self._grid = ops.OccGrid(self.xyz, self._hp.ranges[:3], self._hp.scaled_vsize, self._hp.scaled_vdim, q.query_size,
+                                     q.P, q.max_o, seconds_claim=seconds[0], seconds_fill=seconds[1])
+        return self._grid, self._hp
+
+
+def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision=ops.PRECISION_FP32, t=None, want_aux=False):
+    """Render R rays (device tensors).  Returns a namespace with ray_color [R,3] (misses = bg), ray_mask int8 [R],
+    opacity [R,SR], bg_transmission [R] and, with want_aux, the intermediate tensors."""
+    q = scene.qopt
+    grid, hp = scene.grid()
+    if t is None:
+        t = middle_point_ts(near, far, q.z_depth_dim, raydir.device)
+    pidx, loc_w, smask, rmask = ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2)
+    decoded, ray_valid, loc_pers, weight, conf_coef = ops.aggregate(
+        scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf,
+        scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux)
+    rd = ops.ray_dist(loc_pers, ray_valid, hp.vsize[2], 1)
+    ray_color, opacity, acc, bw, bgt = ops.composite(decoded, rd, ray_valid, bg_color, blend=0)
+    ops.fill_invalid(rmask, bg_color, ray_color, opacity, bgt)
+    out = SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt)
+    if want_aux:
+        out.__dict__.update(pidx=pidx, loc_w=loc_w, sample_mask=smask, decoded=decoded, ray_valid=ray_valid, loc_pers=loc_pers,
+                            weight=weight, conf_coef=conf_coef, ray_dist=rd, blend_weight=bw, acc_transmission=acc)
+    return out

@@ -1,0 +1,174 @@
+"""GPU: fused gather + aggregation (sgn_agg_forward / sgn_agg_backward through the C ABI) against
+(a) the golden vectors produced by the reference's own PointAggregator and (b) the torch oracle on larger seeded inputs.
+
+Tolerances (fp32 strict-parity mode): decoded (sigma, rgb), weights, conf <= 2e-4 abs (north_star: rgb within 1e-3);
+gradients: relative L2 <= 1e-3 per tensor.
+"""
+import ast
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_ref as rr
+from sgnerf_b200 import ops
+
+pytestmark = pytest.mark.gpu
+ATOL = 2e-4
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def cfg_to_c(cfg):
+    return ops.agg_cfg(feat_dim=cfg.point_features_dim, num_feat_freqs=cfg.num_feat_freqs, dist_xyz_freq=cfg.dist_xyz_freq,
+                       num_viewdir_freqs=cfg.num_viewdir_freqs, width=cfg.shading_feature_num,
+                       n_block1=cfg.shading_feature_mlp_layer1, n_block2_bpnet=cfg.shading_feature_mlp_layer2_bpnet,
+                       label_dim=cfg.label_embedding_dim, n_block3=cfg.shading_feature_mlp_layer3,
+                       n_color=cfg.shading_color_mlp_layer, act_super=cfg.act_super, leaky_slope=cfg.leaky_slope)
+
+
+def param_lists(P, cfg, device="cuda", requires_grad=False):
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    w = [P[n + ".weight"].detach().clone().to(device).requires_grad_(requires_grad) for n in names]
+    b = [P[n + ".bias"].detach().clone().to(device).requires_grad_(requires_grad) for n in names]
+    return names, w, b
+
+
+@pytest.mark.parametrize("name", ["agg_small_plain", "agg_small_semantic", "agg_canonical_plain", "agg_canonical_semantic"])
+def test_against_reference_golden(golden_dir, name):
+    """Every (sample, slot) of the golden gathered tensors becomes its own point, so tables + indices reproduce the
+    reference's gathered inputs exactly; outputs and gradients are then compared with the reference's."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = SimpleNamespace(**ast.literal_eval(str(g["cfg"])))
+    if "P_seed" in g:
+        P = rr.init_params(cfg, seed=int(g["P_seed"]), bias_scale=0.1)
+    else:
+        P = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("P_")}
+    names, W, B = param_lists(P, cfg, requires_grad=True)
+    inp = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in_")}
+    mask = inp["sample_pnt_mask"]
+    _, R, SR, K = mask.shape
+    n = R * SR * K
+    pidx = torch.where(mask.reshape(-1), torch.arange(n), torch.full((n,), -1)).reshape(R, SR, K).to(torch.int32).cuda()
+    leaf = lambda t, c: t.reshape(n, c).clone().cuda().requires_grad_(True)
+    emb, col, dr = leaf(inp["sampled_embedding"], cfg.point_features_dim), leaf(inp["sampled_color"], 3), leaf(inp["sampled_dir"], 3)
+    conf = inp["sampled_conf"].reshape(n).clone().cuda().requires_grad_(True)
+    lab = inp["sampled_label_embedding"].reshape(n, -1).cuda() if "sampled_label_embedding" in inp else None
+    campos = torch.tensor([0.3, -0.2, -4.0]).cuda()          # the camera make_golden.py used for the perspective coords
+    out = ops.aggregate(cfg_to_c(cfg), W, B, inp["sampled_xyz"].reshape(n, 3).cuda(), emb, col, dr, conf, lab, pidx,
+                        inp["sample_loc_w"][0].cuda(), inp["sample_ray_dirs"][0, :, 0].cuda(), campos, torch.eye(3).cuda())
+    decoded, ray_valid, loc_pers, weight, conf_coef = out
+    np.testing.assert_allclose(decoded.detach().cpu().numpy(), g["out_decoded"][0], rtol=0, atol=ATOL)
+    assert np.array_equal(ray_valid.cpu().numpy().astype(bool), g["out_ray_valid"][0])
+    np.testing.assert_allclose(weight.detach().cpu().numpy(), g["out_weight"][0], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(loc_pers.cpu().numpy(), inp["sample_loc"][0].numpy(), rtol=1e-5, atol=1e-6)
+    m = mask[0].numpy()
+    np.testing.assert_allclose(conf_coef.detach().cpu().numpy()[m], g["out_conf"][0][m], rtol=0, atol=1e-6)
+    # invalid slots read point 0, as the reference's clamp(pidx, 0) gather does
+    c0 = float(np.clip(inp["sampled_conf"].reshape(-1)[0], 1e-4, 1.0))
+    np.testing.assert_allclose(conf_coef.detach().cpu().numpy()[~m], c0, rtol=0, atol=1e-6)
+
+    cot_d, cot_c = torch.from_numpy(g["cot_decoded"][0]).cuda(), torch.from_numpy(g["cot_conf"][0]).cuda()
+    ((decoded * cot_d).sum() + (conf_coef * cot_c).sum()).backward()
+    mflat = mask.reshape(-1)
+    for t, key, c in ((emb, "g_sampled_embedding", cfg.point_features_dim), (col, "g_sampled_color", 3), (dr, "g_sampled_dir", 3)):
+        ref = torch.from_numpy(g[key]).reshape(n, c) * mflat[:, None]
+        assert rel_l2(t.grad.cpu(), ref) < 1e-3, key
+    ref_conf = torch.from_numpy(g["g_sampled_conf"]).reshape(n) * mflat
+    ref_conf[0] += torch.from_numpy(g["cot_conf"]).reshape(n)[~mflat].sum()
+    assert rel_l2(conf.grad.cpu(), ref_conf) < 1e-3
+    for nme, w, b in zip(names, W, B):
+        for suffix, t in ((".weight", w), (".bias", b)):
+            key = "gw_" + nme + suffix
+            if key in g:
+                assert rel_l2(t.grad.cpu(), torch.from_numpy(g[key])) < 1e-3, key
+            else:
+                s = g["sig_" + key]
+                got = np.array([float(t.grad.double().sum()), float(t.grad.double().abs().sum())])
+                np.testing.assert_allclose(got[1], s[1], rtol=2e-3, err_msg=key)
+                np.testing.assert_allclose(got[0], s[0], rtol=0, atol=2e-3 * max(s[1], 1e-6), err_msg=key)
+
+
+def _random_case(cfg, N, R, SR, K, seed, prefix_mask=True):
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand(N, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 1.0])
+    tables = SimpleNamespace(xyz=xyz, embedding=torch.rand(1, N, cfg.point_features_dim, generator=g) - 0.5,
+                             color=torch.rand(1, N, 3, generator=g), dir=torch.nn.functional.normalize(torch.randn(1, N, 3, generator=g), dim=-1),
+                             conf=torch.rand(1, N, 1, generator=g) * 1.3 - 0.1,
+                             label_embedding=torch.randn(1, N, cfg.label_embedding_dim, generator=g) if cfg.label_embedding_dim else None)
+    pidx = torch.randint(0, N, (R, SR, K), generator=g).to(torch.int32)
+    nv = torch.randint(0, K + 1, (R, SR), generator=g)
+    nv[torch.rand(R, SR, generator=g) < 0.4] = 0
+    if prefix_mask:
+        m = torch.arange(K)[None, None, :] < nv[..., None]
+    else:
+        m = torch.rand(R, SR, K, generator=g) < 0.5
+    pidx[~m] = -1
+    loc_w = torch.rand(R, SR, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 1.0])
+    raydir = torch.randn(R, 3, generator=g)
+    campos = torch.tensor([0.1, -0.1, -0.5])
+    a = 0.3                                                  # a mild rotation keeps camera-space depth well away from zero
+    rot = torch.tensor([[1.0, 0.0, 0.0], [0.0, float(np.cos(a)), float(-np.sin(a))], [0.0, float(np.sin(a)), float(np.cos(a))]])
+    return tables, pidx, loc_w, raydir, campos, rot
+
+
+@pytest.mark.parametrize("semantic", [False, True])
+@pytest.mark.parametrize("prefix_mask", [True, False])
+def test_forward_backward_vs_oracle(semantic, prefix_mask):
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
+    N, R, SR, K = 3000, 37, 24, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=11 + semantic, prefix_mask=prefix_mask)
+    P = rr.init_params(cfg, seed=2, bias_scale=0.1)
+    # oracle (autograd)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    tr = SimpleNamespace(xyz=tables.xyz, label_embedding=tables.label_embedding,
+                         **{k: getattr(tables, k).clone().requires_grad_(True) for k in ("embedding", "color", "dir", "conf")})
+    gn = rr.gather_neighbors(tr, pidx[None], rot[None], campos[None])
+    loc_pers_ref = rr.w2pers_points(loc_w.reshape(-1, 3), rot[None], campos[None]).reshape(1, R, SR, 3)
+    dirs = raydir[None, :, None, :].expand(1, R, SR, 3).contiguous()
+    dec_r, valid_r, w_r, conf_r = rr.aggregator_forward(Pr, cfg, gn.color, gn.label_embedding, gn.dir, gn.conf, gn.embedding, gn.xyz_pers,
+                                                        gn.xyz, gn.pnt_mask, loc_pers_ref, loc_w[None], dirs)
+    g = torch.Generator().manual_seed(5)
+    cot_d, cot_c = torch.randn(R, SR, 4, generator=g), torch.randn(R, SR, K, generator=g) * 0.1
+    ((dec_r[0] * cot_d).sum() + (conf_r[0] * cot_c).sum()).backward()
+    # CUDA
+    names, W, B = param_lists(P, cfg, requires_grad=True)
+    tc = {k: getattr(tables, k).clone().cuda().requires_grad_(True) for k in ("embedding", "color", "dir", "conf")}
+    lab = tables.label_embedding.cuda() if semantic else None
+    dec, valid, loc_pers, w, conf = ops.aggregate(cfg_to_c(cfg), W, B, tables.xyz.cuda(), tc["embedding"], tc["color"], tc["dir"], tc["conf"],
+                                                  lab, pidx.cuda(), loc_w.cuda(), raydir.cuda(), campos.cuda(), rot.cuda())
+    torch.testing.assert_close(dec.detach().cpu(), dec_r[0].detach(), rtol=0, atol=ATOL)
+    assert torch.equal(valid.cpu().bool(), valid_r[0])
+    torch.testing.assert_close(w.cpu(), w_r[0].detach(), rtol=0, atol=1e-5)
+    torch.testing.assert_close(conf.detach().cpu(), conf_r[0].detach(), rtol=0, atol=1e-6)
+    torch.testing.assert_close(loc_pers.cpu(), loc_pers_ref[0], rtol=1e-5, atol=1e-6)
+    ((dec * cot_d.cuda()).sum() + (conf * cot_c.cuda()).sum()).backward()
+    for k in ("embedding", "color", "dir", "conf"):
+        assert rel_l2(tc[k].grad.cpu(), getattr(tr, k).grad) < 1e-3, k
+    for nme, wt, bt in zip(names, W, B):
+        assert rel_l2(wt.grad.cpu(), Pr[nme + ".weight"].grad) < 1e-3, nme
+        assert rel_l2(bt.grad.cpu(), Pr[nme + ".bias"].grad) < 1e-3, nme
+
+
+def test_inference_chunking_and_empty():
+    """R larger than the fp32 inference chunk (4096 rays) must give the same rows as R processed alone; all-empty input gives zeros."""
+    cfg = rr.agg_config(shading_feature_num=64)
+    N, R, SR, K = 2000, 4096 + 300, 4, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=3)
+    P = rr.init_params(cfg, seed=1, bias_scale=0.1)
+    _, W, B = param_lists(P, cfg)
+    args = lambda sl: (tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(), None,
+                       pidx[sl].cuda(), loc_w[sl].cuda(), raydir[sl].cuda(), campos.cuda(), rot.cuda())
+    with torch.no_grad():
+        full = ops.aggregate(cfg_to_c(cfg), W, B, *args(slice(None)))
+        tail = ops.aggregate(cfg_to_c(cfg), W, B, *args(slice(4096, None)))
+        assert torch.equal(full[0][4096:], tail[0]) and torch.equal(full[1][4096:], tail[1])
+        empty = torch.full((5, SR, K), -1, dtype=torch.int32).cuda()
+        out = ops.aggregate(cfg_to_c(cfg), W, B, tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(),
+                            tables.conf.cuda(), None, empty, loc_w[:5].cuda(), raydir[:5].cuda(), campos.cuda(), rot.cuda())
+        assert float(out[0].abs().max()) == 0 and int(out[1].sum()) == 0
