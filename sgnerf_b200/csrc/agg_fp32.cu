@@ -14,374 +14,10 @@
 //   alpha    per tuple  : raw sigma ; ksum per sample : sum_k w conf (sigma, h) ; colour MLP ; rgb
 // The tensor-core (bf16, tcgen05) path lives in agg_tc.cu; this file is the numerically strict one and the
 // one training uses.
-#include "agg_common.cuh"
+#include "agg_kernels.cuh"
 #include "gemm_simt.cuh"
 
 namespace sgn {
-
-// ------------------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------------------
-
-// One thread per sample.  point_aggregators.py:885, :917-925 (dists), :494-502 + :946-947 (weights), :953 (conf).
-__global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __restrict__ loc_pers, float* __restrict__ wc,
-                                   float* __restrict__ weight_n, float* __restrict__ weight_out, float* __restrict__ conf_out, uint8_t* __restrict__ ray_valid,
-                                   int32_t* __restrict__ nvalid, int32_t* __restrict__ svalid)
-{
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    const float lx = in.loc_w[3 * s], ly = in.loc_w[3 * s + 1], lz = in.loc_w[3 * s + 2];
-    {   // w2pers: (p - campos) @ camrotc2w, then (x/z, y/z, z)
-        const float sx = lx - in.campos[0], sy = ly - in.campos[1], sz = lz - in.campos[2];
-        const float* Rm = in.camrot;
-        const float c0 = sx * Rm[0] + sy * Rm[3] + sz * Rm[6];
-        const float c1 = sx * Rm[1] + sy * Rm[4] + sz * Rm[7];
-        const float c2 = sx * Rm[2] + sy * Rm[5] + sz * Rm[8];
-        loc_pers[3 * s] = c0 / c2; loc_pers[3 * s + 1] = c1 / c2; loc_pers[3 * s + 2] = c2;
-    }
-    const int32_t* pi = in.pidx + s * K;
-    float w[SGN_MAX_K];
-    float sum = 0.f;
-    int n = 0;
-    for (int k = 0; k < K; k++) {
-        const int p = pi[k];
-        float wk = 0.f;
-        if (p >= 0) {
-            const float dx = in.tab.xyz[3 * (int64_t)p] - lx, dy = in.tab.xyz[3 * (int64_t)p + 1] - ly, dz = in.tab.xyz[3 * (int64_t)p + 2] - lz;
-            const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-            wk = 1.0f / fmaxf(nrm, 1e-6f);
-            n++;
-        }
-        w[k] = wk;
-        sum += wk;
-    }
-    const float den = fmaxf(sum, 1e-8f);
-    for (int k = 0; k < K; k++) {
-        const int p = pi[k] < 0 ? 0 : pi[k];           // the reference gathers with clamp(pidx, 0) (neural_points.py:958)
-        const float cf = in.tab.conf ? fminf(fmaxf(in.tab.conf[p], 0.0001f), 1.0f) : 1.0f;
-        const float wn = w[k] / den;
-        wc[s * K + k] = wn * cf;
-        weight_n[s * K + k] = wn;
-        if (weight_out) weight_out[s * K + k] = wn;
-        if (conf_out) conf_out[s * K + k] = cf;
-    }
-    ray_valid[s] = n > 0;
-    nvalid[s] = n;
-    svalid[s] = n > 0;
-}
-
-// One thread per sample: tuple j -> (sample, slot), compact sample c -> sample.
-__global__ void agg_index_kernel(const int32_t* __restrict__ pidx, int64_t S, int K, const int32_t* __restrict__ tuple_start,
-                                 const int32_t* __restrict__ sample_cidx, const int32_t* __restrict__ nvalid,
-                                 int32_t* __restrict__ tuple_src, int32_t* __restrict__ csample)
-{
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    if (nvalid[s] == 0) return;
-    csample[sample_cidx[s]] = (int32_t)s;
-    int j = tuple_start[s];
-    for (int k = 0; k < K; k++)
-        if (pidx[s * K + k] >= 0) tuple_src[j++] = (int32_t)(s * K + k);
-}
-
-// One warp per tuple.  X0 layout = reference `feat` (:603-611):
-//   [0,C) embedding | C + 2*(d*F+f) + {0:sin,1:cos} of emb_d * 2^f | then the same for the 6 dists with F = dist_xyz_freq.
-// E7 = [colour(3) | dir - viewdir (3) | dir . viewdir | 0]  (:639-652).
-__global__ void __launch_bounds__(256)
-agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
-                  const float* __restrict__ loc_pers, float* __restrict__ X0, float* __restrict__ L, float* __restrict__ E7)
-{
-    const int lane = lane_id();
-    const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
-    const int flat = tuple_src[j];
-    const int64_t s = flat / K;
-    const int64_t r = s / SR;
-    const int64_t p = in.pidx[flat];
-    float* x = X0 + j * d.k0pad;
-    const int C = d.C, F = d.F, FD = d.FD;
-    for (int c = lane; c < C; c += 32) {
-        const float e = __ldg(in.tab.embedding + p * C + c);
-        x[c] = e;
-        float fr = 1.0f;
-        for (int f = 0; f < F; f++) {
-            const float a = e * fr;
-            x[C + 2 * (c * F + f)] = sinf(a);
-            x[C + 2 * (c * F + f) + 1] = cosf(a);
-            fr *= 2.0f;
-        }
-    }
-    const int base = C + 2 * C * F;
-    if (lane < 6) {
-        const float px = in.tab.xyz[3 * p], py = in.tab.xyz[3 * p + 1], pz = in.tab.xyz[3 * p + 2];
-        float dist;
-        if (lane < 3) {
-            dist = in.tab.xyz[3 * p + lane] - in.loc_w[3 * s + lane];
-        } else {
-            // point in perspective coords (neural_points.py:845-850), then :920-922
-            const float sx = px - in.campos[0], sy = py - in.campos[1], sz = pz - in.campos[2];
-            const float* Rm = in.camrot;
-            const float c0 = sx * Rm[0] + sy * Rm[3] + sz * Rm[6];
-            const float c1 = sx * Rm[1] + sy * Rm[4] + sz * Rm[7];
-            const float c2 = sx * Rm[2] + sy * Rm[5] + sz * Rm[8];
-            const float xp = c0 / c2, yp = c1 / c2, zp = c2;
-            const float lxp = loc_pers[3 * s], lyp = loc_pers[3 * s + 1], lzp = loc_pers[3 * s + 2];
-            dist = lane == 3 ? xp * zp - lxp * lzp : (lane == 4 ? yp * zp - lyp * lzp : zp - lzp);
-        }
-        float fr = 1.0f;
-        for (int f = 0; f < FD; f++) {
-            const float a = dist * fr;
-            x[base + 2 * (lane * FD + f)] = sinf(a);
-            x[base + 2 * (lane * FD + f) + 1] = cosf(a);
-            fr *= 2.0f;
-        }
-    }
-    for (int c = d.k0 + lane; c < d.k0pad; c += 32) x[c] = 0.f;
-    if (L) {
-        for (int c = lane; c < d.LD; c += 32) L[j * d.LD + c] = __ldg(in.tab.label_emb + p * d.LD + c);
-    }
-    if (lane < 8) {
-        float v = 0.f;
-        const float vx = in.raydir[3 * r], vy = in.raydir[3 * r + 1], vz = in.raydir[3 * r + 2];
-        const float dx = in.tab.dir[3 * p], dy = in.tab.dir[3 * p + 1], dz = in.tab.dir[3 * p + 2];
-        if (lane < 3) v = in.tab.color[3 * p + lane];
-        else if (lane == 3) v = dx - vx;
-        else if (lane == 4) v = dy - vy;
-        else if (lane == 5) v = dz - vz;
-        else if (lane == 6) v = dx * vx + dy * vy + dz * vz;
-        E7[j * 8 + lane] = v;
-    }
-}
-
-// One warp per tuple: raw alpha = h . wa + ba   (alpha_branch, a single Linear)
-__global__ void __launch_bounds__(256)
-agg_alpha_kernel(const float* __restrict__ H, int W, const float* __restrict__ wa, const float* __restrict__ ba,
-                 const int32_t* __restrict__ T_ptr, int T_max, float* __restrict__ araw)
-{
-    const int lane = lane_id();
-    const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
-    float acc = 0.f;
-    for (int c = lane; c < W; c += 32) acc = fmaf(H[j * W + c], __ldg(wa + c), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) araw[j] = acc + ba[0];
-}
-
-__device__ __forceinline__ float softplus1(float x)  // torch.nn.Softplus(beta=1, threshold=20)
-{
-    return x > 20.0f ? x : log1pf(expf(x));
-}
-
-// One warp per compact sample: sigma = sum_k wc * softplus(raw - 1), F = sum_k wc * h  -> C0[:, :W];
-// C0[:, W:W+6*FV] = viewdir encoding (ori=True, first three stripped): sin(v_d 2^f) d-major, then cos (:579-585).
-__global__ void __launch_bounds__(256)
-agg_ksum_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample,
-                const int32_t* __restrict__ tuple_start, const int32_t* __restrict__ nvalid, const float* __restrict__ wc,
-                const float* __restrict__ H, const float* __restrict__ araw, float* __restrict__ C0, float* __restrict__ sigma)
-{
-    const int lane = lane_id();
-    const int Sv = min(*S_ptr, S_max);
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= Sv) return;
-    const int64_t s = csample[c];
-    const int j0 = tuple_start[s], n = nvalid[s];
-    const int W = d.W;
-    float wk[SGN_MAX_K];
-    {
-        int q = 0;
-        for (int k = 0; k < K; k++)
-            if (in.pidx[s * K + k] >= 0) wk[q++] = wc[s * K + k];
-    }
-    float sg = 0.f;
-    for (int q = 0; q < n; q++) {
-        const float a = araw[j0 + q];
-        sg += wk[q] * (d.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f));
-    }
-    float* row = C0 + c * d.kc0pad;
-    for (int col = lane; col < W; col += 32) {
-        float acc = 0.f;
-        for (int q = 0; q < n; q++) acc += H[(int64_t)(j0 + q) * W + col] * wk[q];
-        row[col] = acc;
-    }
-    const int64_t r = s / SR;
-    const int FV = d.FV;
-    for (int i = lane; i < 3 * FV; i += 32) {
-        const int dd = i / FV, f = i - dd * FV;
-        const float a = in.raydir[3 * r + dd] * exp2f((float)f);
-        row[W + i] = sinf(a);
-        row[W + 3 * FV + i] = cosf(a);
-    }
-    for (int col = W + 6 * FV + lane; col < d.kc0pad; col += 32) row[col] = 0.f;
-    if (lane == 0) sigma[c] = sg;
-}
-
-// One warp per compact sample: rgb = sigmoid(c . Wlast^T + b) (*1.002 - 0.001), decoded[s] = (sigma, rgb)
-__global__ void __launch_bounds__(256)
-agg_rgb_kernel(AggDims d, const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample,
-               const float* __restrict__ Cin, int Wc, const float* __restrict__ Wl, const float* __restrict__ bl,
-               const float* __restrict__ sigma, float* __restrict__ decoded, float* __restrict__ sig_out)
-{
-    const int lane = lane_id();
-    const int Sv = min(*S_ptr, S_max);
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= Sv) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int col = lane; col < Wc; col += 32) {
-        const float x = Cin[c * Wc + col];
-        a0 = fmaf(x, __ldg(Wl + col), a0);
-        a1 = fmaf(x, __ldg(Wl + Wc + col), a1);
-        a2 = fmaf(x, __ldg(Wl + 2 * Wc + col), a2);
-    }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane == 0) {
-        const float s0 = 1.0f / (1.0f + expf(-(a0 + bl[0]))), s1 = 1.0f / (1.0f + expf(-(a1 + bl[1]))), s2 = 1.0f / (1.0f + expf(-(a2 + bl[2])));
-        const float m = d.act_super ? 1.002f : 1.0f, o = d.act_super ? 0.001f : 0.0f;
-        const int64_t s = csample[c];
-        ((float4*)decoded)[s] = make_float4(sigma[c], s0 * m - o, s1 * m - o, s2 * m - o);
-        if (sig_out) ((float4*)sig_out)[c] = make_float4(s0, s1, s2, 0.f);
-    }
-}
-
-// W [N,K] (torch Linear) -> Wt [Kpad, Npad] (k-major, forward B operand) and Wp [Npad, Kpad] (dgrad B operand)
-__global__ void pack_weight_kernel(const float* __restrict__ W, int N, int Kin, int Npad, int Kpad, float* __restrict__ Wt, float* __restrict__ Wp)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Npad * Kpad) return;
-    const int n = i / Kpad, k = i - n * Kpad;
-    const float v = (n < N && k < Kin) ? W[(size_t)n * Kin + k] : 0.f;
-    Wp[(size_t)n * Kpad + k] = v;
-    Wt[(size_t)k * Npad + n] = v;
-}
-
-// ---- backward-only kernels ----
-
-// column sums: out[c] += sum_m X[m, c]  (bias gradients)
-__global__ void __launch_bounds__(128)
-colsum_kernel(const float* __restrict__ X, int ld, int ncols, const int32_t* __restrict__ m_ptr, int m_max, int rows_per_block, float* __restrict__ out)
-{
-    const int M = min(*m_ptr, m_max);
-    const int c = blockIdx.y * 128 + threadIdx.x;
-    const int m0 = blockIdx.x * rows_per_block;
-    if (m0 >= M || c >= ncols) return;
-    const int m1 = min(M, m0 + rows_per_block);
-    float acc = 0.f;
-    for (int m = m0; m < m1; m++) acc += X[(size_t)m * ld + c];
-    atomicAdd(out + c, acc);
-}
-
-// One warp per compact sample: d_raw[c, 0:3] = d_rgb * scale * sig (1 - sig), padded to 8 columns
-__global__ void __launch_bounds__(256)
-agg_rgb_bwd_kernel(AggDims d, const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample,
-                   const float* __restrict__ d_decoded, const float* __restrict__ sig, float* __restrict__ d_raw)
-{
-    const int Sv = min(*S_ptr, S_max);
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Sv) return;
-    const float4 g = ((const float4*)d_decoded)[csample[c]];
-    const float4 sg = ((const float4*)sig)[c];
-    const float m = d.act_super ? 1.002f : 1.0f;
-    float* o = d_raw + c * 8;
-    o[0] = g.y * m * sg.x * (1.f - sg.x);
-    o[1] = g.z * m * sg.y * (1.f - sg.y);
-    o[2] = g.w * m * sg.z * (1.f - sg.z);
-    o[3] = o[4] = o[5] = o[6] = o[7] = 0.f;
-}
-
-// One warp per tuple: backward of ksum + alpha.  Writes dZ = dH (.) leaky'(H) for the last tuple layer,
-// d_araw[j], and accumulates d_conf (straight-through clamp: d conf_coef / d conf = 1).
-__global__ void __launch_bounds__(256)
-agg_ksum_bwd_kernel(AggIn in, AggDims d, int K, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
-                    const int32_t* __restrict__ sample_cidx, const float* __restrict__ wc, const float* __restrict__ weight_n,
-                    const float* __restrict__ H, const float* __restrict__ araw, const float* __restrict__ wa,
-                    const float* __restrict__ dC0, int lddc0, const float* __restrict__ d_decoded, float* __restrict__ dZ,
-                    float* __restrict__ d_araw, float* __restrict__ d_conf)
-{
-    const int lane = lane_id();
-    const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
-    const int flat = tuple_src[j];
-    const int64_t s = flat / K;
-    const int64_t c = sample_cidx[s];
-    const float w = wc[flat];
-    const float dsig = d_decoded[4 * s];
-    const float a = araw[j];
-    float act, dact;
-    if (d.act_super) {
-        const float x = a - 1.0f;
-        act = softplus1(x);
-        dact = x > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-x));
-    } else {
-        act = fmaxf(a, 0.f);
-        dact = a > 0.f ? 1.0f : 0.f;
-    }
-    const float da = w * dsig * dact;
-    const int W = d.W;
-    float dot = 0.f;
-    for (int col = lane; col < W; col += 32) {
-        const float h = H[j * W + col];
-        const float df = dC0[c * lddc0 + col];
-        dot = fmaf(h, df, dot);
-        const float dh = w * df + da * __ldg(wa + col);
-        dZ[j * W + col] = dh * (h > 0.f ? 1.0f : d.slope);
-    }
-    dot = warp_sum(dot);
-    if (lane == 0) {
-        d_araw[j] = da;
-        if (d_conf) {
-            const float d_wc = act * dsig + dot;
-            atomicAdd(d_conf + in.pidx[flat], weight_n[flat] * d_wc);
-        }
-    }
-}
-
-// cotangent of the conf_coefficient output (all slots, invalid ones use point 0 like the reference's clamp(pidx,0) gather)
-__global__ void agg_conf_out_bwd_kernel(const int32_t* __restrict__ pidx, int64_t n, const float* __restrict__ d_conf_coef, float* __restrict__ d_conf)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float g = d_conf_coef[i];
-    if (g != 0.f) atomicAdd(d_conf + (pidx[i] < 0 ? 0 : pidx[i]), g);
-}
-
-// One warp per tuple: scatter-add into the point tables.
-//   d emb_c = dX0[c] + sum_f 2^f (cos_cf dsin_cf - sin_cf dcos_cf)   (sin/cos read back from the saved X0)
-//   d colour = dE7[0:3] ; d dir = dE7[3:6] + viewdir * dE7[6]
-__global__ void __launch_bounds__(256)
-agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
-                   const float* __restrict__ X0, const float* __restrict__ dX0, const float* __restrict__ dE7, SgnPointGrads g)
-{
-    const int lane = lane_id();
-    const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
-    const int flat = tuple_src[j];
-    const int64_t p = in.pidx[flat];
-    const int C = d.C, F = d.F;
-    if (g.embedding) {
-        const float* x = X0 + j * d.k0pad;
-        const float* dx = dX0 + j * d.k0pad;
-        for (int c = lane; c < C; c += 32) {
-            float acc = dx[c], fr = 1.0f;
-            for (int f = 0; f < F; f++) {
-                const int o = C + 2 * (c * F + f);
-                acc += fr * (x[o + 1] * dx[o] - x[o] * dx[o + 1]);
-                fr *= 2.0f;
-            }
-            atomicAdd(g.embedding + p * C + c, acc);
-        }
-    }
-    if (dE7) {
-        const float* e = dE7 + j * 8;
-        if (g.color && lane < 3) atomicAdd(g.color + 3 * p + lane, e[lane]);
-        if (g.dir && lane >= 3 && lane < 6) {
-            const int64_t r = (flat / K) / SR;
-            atomicAdd(g.dir + 3 * p + (lane - 3), e[lane] + in.raydir[3 * r + (lane - 3)] * e[6]);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // host orchestration

@@ -1,18 +1,635 @@
-// agg_tc.cu -- bf16 tensor-core (tcgen05/TMEM/TMA) aggregator path.  Placeholder until the fused kernel lands.
-#include "agg_common.cuh"
+// agg_tc.cu -- bf16 tensor-core aggregator forward: ONE fused persistent kernel for
+//   gather + positional encoding -> per-neighbour MLP (block1 / block3) -> alpha -> K-weighted sums,
+// built on tcgen05.mma (accumulators in TMEM), bulk-TMA weight streaming and mbarrier pipelines (sm_100a).
+//
+// Reference: PointAggregator.viewmlp (models/aggregators/point_aggregators.py:561-786) on the canonical
+// non-semantic branch; the per-sample colour MLP that follows runs as separate launches (see bottom).
+//
+// Tile = 128 valid (sample, neighbour) tuples (rows), compacted in sample order.  Per CTA (1 per SM, persistent):
+//
+//   warps 0-3  epilogue : TMEM -> registers (tcgen05.ld) -> +bias, LeakyReLU -> bf16 -> next layer's A operand in
+//                         shared memory (128B-swizzled K-major panels); last layer: alpha dot product and the
+//                         K-weighted segmented sums over the rows of each sample -> F[S,256], sigma[S]
+//   warps 4-7  gather   : for the NEXT tile, one thread per row: point tables -> [emb | PE(emb) | PE(dists)] (bf16)
+//                         straight into the swizzled X0 operand panels, plus [colour | dir-view | dir.view]
+//   warp  8    producer : cp.async.bulk (TMA, UBLKCP) of pre-swizzled 32 KB weight panels into a 2-stage ring
+//   warp  9    MMA      : one thread issues tcgen05.mma 128x256x16 (bf16 in, fp32 accumulate in TMEM); two
+//                         256-column accumulators alternate per layer so layer l+1's MMAs on K-panel p start as soon
+//                         as the epilogue of layer l has written activation panel p
+//
+// Shared memory (bytes): X0 5 x 16 KB | activations 4 x 16 KB (aliased by the K-sum staging) | weight ring 2 x 32 KB |
+// row metadata | mbarriers  = ~211 KB.  TMEM: 512 columns (2 accumulators of 128 lanes x 256 fp32 columns).
+#include <cuda_bf16.h>
+
+#include "agg_kernels.cuh"
+#include "gemm_simt.cuh"
+
+namespace sgn {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_W = 256;                 // layer width == accumulator columns
+constexpr int TC_C = 32, TC_F = 3, TC_FD = 5;
+constexpr int TC_K0 = TC_C * (1 + 2 * TC_F) + 2 * TC_FD * 6;   // 284
+constexpr int TC_MAX_LAYERS = 8;
+constexpr int PANEL_A = TC_ROWS * 128;    // 16 KB: 128 rows x 64 bf16
+constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
+constexpr int X0_PANELS = 5, AM_PANELS = 4, B_STAGES = 2;
+constexpr int E7_COL0 = 32;               // inside X0 panel 4: cols [32,48) tile parity 0, [48,64) parity 1
+constexpr int STG_LD = 33;                // staging row pitch (floats): conflict-free row writes and column walks
+
+constexpr int OFF_X0 = 0;
+constexpr int OFF_AM = OFF_X0 + X0_PANELS * PANEL_A;            // 81920
+constexpr int OFF_B = OFF_AM + AM_PANELS * PANEL_A;             // 147456
+constexpr int OFF_META = OFF_B + B_STAGES * PANEL_B;            // 212992
+constexpr int META_BYTES = 2 * TC_ROWS * 12;                    // wc (f32), cs (i32), cross (i32), double buffered
+constexpr int OFF_BAR = OFF_META + META_BYTES;
+constexpr int N_BARS = 2 * B_STAGES + 2 + AM_PANELS + 4 + 2;
+constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
+constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
+static_assert(TC_ROWS * STG_LD * 4 <= AM_PANELS * PANEL_A, "staging must fit in the activation panels");
+static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
+
+enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
+
+struct TcParams {
+    AggIn in;
+    int K, SR;
+    const int32_t* T_ptr; int T_max;
+    const int32_t* tuple_src; const int32_t* tuple_start; const int32_t* nvalid; const int32_t* sample_cidx;
+    const float* loc_pers; const float* wc;
+    const uint8_t* wpack;                  // pre-swizzled bf16 weight panels, all layers back to back
+    int n_layers;
+    int kind[TC_MAX_LAYERS];
+    int first_panel[TC_MAX_LAYERS + 1];
+    const float* bias[TC_MAX_LAYERS];
+    const float* wa; const float* ba;
+    float slope; int act_super;
+    float* F; int ldF; float* sigma;       // outputs, per compact sample
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = 256
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_W >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+
+// byte offset of element (row, col) inside a 128B-swizzled K-major panel set (64 columns per panel)
+__device__ __forceinline__ uint32_t sw_off(int row, int col)
+{
+    return (uint32_t)((col >> 6) * PANEL_A + row * 128 + ((((col >> 3) & 7) ^ (row & 7)) << 4) + (col & 7) * 2);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    float* meta_wc = (float*)(smem + OFF_META);                    // [2][128]
+    int32_t* meta_cs = (int32_t*)(smem + OFF_META + 2 * TC_ROWS * 4);
+    int32_t* meta_cross = (int32_t*)(smem + OFF_META + 4 * TC_ROWS * 4);
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    // barrier indices
+    const int B_FULL = 0, B_EMPTY = B_STAGES, X0_FULL = 2 * B_STAGES, X0_EMPTY = X0_FULL + 1, A_FULL = X0_EMPTY + 1,
+              D_FULL = A_FULL + AM_PANELS, D_EMPTY = D_FULL + 2, META_FREE = D_EMPTY + 2;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(smem + OFF_TMEMPTR);
+
+    const int T = min(*p.T_ptr, p.T_max);
+    const int ntiles = (T + TC_ROWS - 1) / TC_ROWS;
+
+    if (tid == 0) {
+        for (int s = 0; s < B_STAGES; s++) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
+        mbar_init(BAR(X0_FULL), 128); mbar_init(BAR(X0_EMPTY), 1);
+        for (int i = 0; i < AM_PANELS; i++) mbar_init(BAR(A_FULL + i), 128);
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); mbar_init(BAR(META_FREE + i), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp < 4) {
+        // =========================================================== EPILOGUE (row = tid, TMEM lane quadrant = warp)
+        const int row = tid;
+        uint32_t ph_dfull[2] = {0, 0};
+        uint32_t lcount = 0;                                   // global layer counter -> accumulator buffer
+        uint32_t tcount = 0;
+        float* stg = (float*)(smem + OFF_AM) + warp * 32 * STG_LD;          // this warp's 32 x 33 staging rows
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const int mb = tcount & 1;
+            for (int l = 0; l < p.n_layers; l++, lcount++) {
+                const int db = lcount & 1;
+                const bool last = (l == p.n_layers - 1);
+                mbar_wait(BAR(D_FULL + db), ph_dfull[db]);
+                ph_dfull[db] ^= 1;
+                tc_fence_after();
+                const float* bias = p.bias[l];
+                float araw = 0.f;
+                const float my_wc = last ? meta_wc[mb * TC_ROWS + row] : 0.f;
+#pragma unroll 1
+                for (int c = 0; c < TC_W / 32; c++) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + (uint32_t)(db * TC_W + c * 32) + ((uint32_t)(warp * 32) << 16), v);
+                    float h[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bb = __ldg((const float4*)(bias + c * 32 + i));
+                        float x0 = __uint_as_float(v[i]) + bb.x, x1 = __uint_as_float(v[i + 1]) + bb.y;
+                        float x2 = __uint_as_float(v[i + 2]) + bb.z, x3 = __uint_as_float(v[i + 3]) + bb.w;
+                        h[i] = fmaxf(x0, x0 * p.slope); h[i + 1] = fmaxf(x1, x1 * p.slope);
+                        h[i + 2] = fmaxf(x2, x2 * p.slope); h[i + 3] = fmaxf(x3, x3 * p.slope);
+                    }
+                    if (!last) {
+                        // next layer's A operand: activation panel c/2, 16-byte chunks (c&1)*4 .. +3 of this row
+                        const uint32_t rowbase = sbase + OFF_AM + (c >> 1) * PANEL_A + row * 128;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int ch = (c & 1) * 4 + q;
+                            sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                                   pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                        }
+                        if (c & 1) {
+                            fence_proxy_async();
+                            mbar_arrive(BAR(A_FULL + (c >> 1)));
+                        }
+                    } else {
+                        // alpha dot product + K-weighted segmented sums of this warp's 32 rows
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 w4 = __ldg((const float4*)(p.wa + c * 32 + i));
+                            araw = fmaf(h[i], w4.x, araw); araw = fmaf(h[i + 1], w4.y, araw);
+                            araw = fmaf(h[i + 2], w4.z, araw); araw = fmaf(h[i + 3], w4.w, araw);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) stg[lane * STG_LD + i] = h[i] * my_wc;
+                        __syncwarp();
+                        const int32_t* cs = meta_cs + mb * TC_ROWS + warp * 32;
+                        const int32_t* cr = meta_cross + mb * TC_ROWS + warp * 32;
+                        float acc = 0.f;
+                        int cur = cs[0];
+                        for (int i = 0; i < 32; i++) {
+                            const int ci = cs[i];
+                            if (ci != cur) {
+                                if (cur >= 0) {
+                                    float* dst = p.F + (size_t)cur * p.ldF + c * 32 + lane;
+                                    if (cr[i - 1]) atomicAdd(dst, acc); else *dst = acc;
+                                }
+                                acc = 0.f; cur = ci;
+                            }
+                            acc += stg[i * STG_LD + lane];
+                        }
+                        if (cur >= 0) {
+                            float* dst = p.F + (size_t)cur * p.ldF + c * 32 + lane;
+                            if (cr[31]) atomicAdd(dst, acc); else *dst = acc;
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(BAR(D_EMPTY + db));
+                if (last) {
+                    // sigma: segmented sum of wc * act(raw alpha) over the rows of each sample (within the warp)
+                    const float a = araw + p.ba[0];
+                    const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
+                    const float val = act * my_wc;
+                    const int mycs = meta_cs[mb * TC_ROWS + row];
+                    const int mycross = meta_cross[mb * TC_ROWS + row];
+                    const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
+                    const bool head = (lane == 0) || (prevcs != mycs);
+                    float sum = val;
+                    bool open = true;
+                    for (int dlt = 1; dlt < 32; dlt++) {
+                        const float vj = __shfl_down_sync(0xffffffffu, val, dlt);
+                        const int cj = __shfl_down_sync(0xffffffffu, mycs, dlt);
+                        open = open && (lane + dlt < 32) && (cj == mycs);
+                        if (open) sum += vj;
+                    }
+                    if (head && mycs >= 0) {
+                        if (mycross) atomicAdd(p.sigma + mycs, sum); else p.sigma[mycs] = sum;
+                    }
+                    mbar_arrive(BAR(META_FREE + mb));
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // =========================================================== GATHER (row = tid - 128) for this CTA's tiles, one ahead
+        const int row = tid - 128;
+        uint32_t ph_x0empty = 1, ph_meta[2] = {1, 1};
+        uint32_t tcount = 0;
+        const float* Rm = p.in.camrot;
+        const float r00 = Rm[0], r01 = Rm[1], r02 = Rm[2], r10 = Rm[3], r11 = Rm[4], r12 = Rm[5], r20 = Rm[6], r21 = Rm[7], r22 = Rm[8];
+        const float cpx = p.in.campos[0], cpy = p.in.campos[1], cpz = p.in.campos[2];
+        const uint32_t x0 = sbase + OFF_X0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+            const int mb = tcount & 1;
+            mbar_wait(BAR(X0_EMPTY), ph_x0empty); ph_x0empty ^= 1;
+            mbar_wait(BAR(META_FREE + mb), ph_meta[mb]); ph_meta[mb] ^= 1;
+            const int64_t j = (int64_t)tile * TC_ROWS + row;
+            const bool live = j < T;
+            float wcv = 0.f; int csv = -1, crossv = 0;
+            float emb[TC_C];
+            float dist[6];
+            float e7[8];
+#pragma unroll
+            for (int i = 0; i < TC_C; i++) emb[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; i++) dist[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) e7[i] = 0.f;
+            if (live) {
+                const int flat = p.tuple_src[j];
+                const int64_t s = flat / p.K;
+                const int64_t r = s / p.SR;
+                const int64_t pt = p.in.pidx[flat];
+                wcv = p.wc[flat];
+                csv = p.sample_cidx[s];
+                const int st = p.tuple_start[s], nv = p.nvalid[s];
+                crossv = (st >> 5) != ((st + nv - 1) >> 5);
+                const float4* ep = (const float4*)(p.in.tab.embedding + pt * TC_C);
+#pragma unroll
+                for (int i = 0; i < TC_C / 4; i++) {
+                    const float4 e = __ldg(ep + i);
+                    emb[4 * i] = e.x; emb[4 * i + 1] = e.y; emb[4 * i + 2] = e.z; emb[4 * i + 3] = e.w;
+                }
+                const float px = p.in.tab.xyz[3 * pt], py = p.in.tab.xyz[3 * pt + 1], pz = p.in.tab.xyz[3 * pt + 2];
+                dist[0] = px - p.in.loc_w[3 * s]; dist[1] = py - p.in.loc_w[3 * s + 1]; dist[2] = pz - p.in.loc_w[3 * s + 2];
+                const float sx = px - cpx, sy = py - cpy, sz = pz - cpz;
+                const float c0 = sx * r00 + sy * r10 + sz * r20, c1 = sx * r01 + sy * r11 + sz * r21, c2 = sx * r02 + sy * r12 + sz * r22;
+                const float xp = c0 / c2, yp = c1 / c2;
+                const float lxp = p.loc_pers[3 * s], lyp = p.loc_pers[3 * s + 1], lzp = p.loc_pers[3 * s + 2];
+                dist[3] = xp * c2 - lxp * lzp; dist[4] = yp * c2 - lyp * lzp; dist[5] = c2 - lzp;
+                const float vx = p.in.raydir[3 * r], vy = p.in.raydir[3 * r + 1], vz = p.in.raydir[3 * r + 2];
+                const float dx = p.in.tab.dir[3 * pt], dy = p.in.tab.dir[3 * pt + 1], dz = p.in.tab.dir[3 * pt + 2];
+                e7[0] = p.in.tab.color[3 * pt]; e7[1] = p.in.tab.color[3 * pt + 1]; e7[2] = p.in.tab.color[3 * pt + 2];
+                e7[3] = dx - vx; e7[4] = dy - vy; e7[5] = dz - vz; e7[6] = dx * vx + dy * vy + dz * vz;
+            }
+            // cols [0,32): embedding
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                sts128(x0 + sw_off(row, 8 * q), pack_bf16(emb[8 * q], emb[8 * q + 1]), pack_bf16(emb[8 * q + 2], emb[8 * q + 3]),
+                       pack_bf16(emb[8 * q + 4], emb[8 * q + 5]), pack_bf16(emb[8 * q + 6], emb[8 * q + 7]));
+            // cols 32 + 2*(c*F + f) + {0: sin, 1: cos}: base angle by sincosf, octaves by the double-angle recurrence
+#pragma unroll
+            for (int c = 0; c < TC_C; c++) {
+                float sn, cs_;
+                __sincosf(emb[c], &sn, &cs_);
+#pragma unroll
+                for (int f = 0; f < TC_F; f++) {
+                    sts32(x0 + sw_off(row, TC_C + 2 * (c * TC_F + f)), pack_bf16(sn, cs_));
+                    const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
+                    sn = s2; cs_ = c2;
+                }
+            }
+            constexpr int DB = TC_C * (1 + 2 * TC_F);     // 224
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                float sn, cs_;
+                __sincosf(dist[d], &sn, &cs_);
+#pragma unroll
+                for (int f = 0; f < TC_FD; f++) {
+                    sts32(x0 + sw_off(row, DB + 2 * (d * TC_FD + f)), pack_bf16(sn, cs_));
+                    const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
+                    sn = s2; cs_ = c2;
+                }
+            }
+            sts32(x0 + sw_off(row, TC_K0), 0u); sts32(x0 + sw_off(row, TC_K0 + 2), 0u);      // cols 284..287 = 0
+            // E7 slot of this tile parity: cols 256 + 32 + 16*mb .. +15 (panel 4)
+            {
+                const int col = 4 * 64 + E7_COL0 + 16 * mb;
+                sts128(x0 + sw_off(row, col), pack_bf16(e7[0], e7[1]), pack_bf16(e7[2], e7[3]), pack_bf16(e7[4], e7[5]), pack_bf16(e7[6], 0.f));
+                sts128(x0 + sw_off(row, col + 8), 0u, 0u, 0u, 0u);
+            }
+            meta_wc[mb * TC_ROWS + row] = wcv;
+            meta_cs[mb * TC_ROWS + row] = csv;
+            meta_cross[mb * TC_ROWS + row] = crossv;
+            fence_proxy_async();
+            mbar_arrive(BAR(X0_FULL));
+        }
+    } else if (warp == 8) {
+        // =========================================================== PRODUCER: weight panels through the ring
+        if (lane == 0) {
+            uint32_t ph_empty[B_STAGES];
+            for (int s = 0; s < B_STAGES; s++) ph_empty[s] = 1;
+            uint32_t n = 0;
+            const int total_panels = p.first_panel[p.n_layers];
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int pi = 0; pi < total_panels; pi++, n++) {
+                    const int s = n % B_STAGES;
+                    mbar_wait(BAR(B_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
+                    mbar_expect_tx(BAR(B_FULL + s), PANEL_B);
+                    bulk_g2s(sbase + OFF_B + s * PANEL_B, p.wpack + (size_t)pi * PANEL_B, PANEL_B, BAR(B_FULL + s));
+                }
+            }
+        }
+    } else {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t ph_full[B_STAGES];
+            for (int s = 0; s < B_STAGES; s++) ph_full[s] = 0;
+            uint32_t ph_x0full = 0, ph_afull[AM_PANELS] = {0, 0, 0, 0}, ph_dempty[2] = {1, 1};
+            uint32_t n = 0, lcount = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+                const int mb = tcount & 1;
+                for (int l = 0; l < p.n_layers; l++, lcount++) {
+                    const int db = lcount & 1;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(db * TC_W);
+                    mbar_wait(BAR(D_EMPTY + db), ph_dempty[db]); ph_dempty[db] ^= 1;
+                    const int np = p.first_panel[l + 1] - p.first_panel[l];
+                    const int kind = p.kind[l];
+                    if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X0_FULL), ph_x0full); ph_x0full ^= 1; }
+                    uint32_t acc = 0;
+                    for (int kp = 0; kp < np; kp++, n++) {
+                        uint32_t a_addr;
+                        int ksteps = 4;
+                        if (kind == LAYER_FROM_X0) {
+                            a_addr = sbase + OFF_X0 + kp * PANEL_A;
+                            if (kp == 4) ksteps = 2;                      // cols 256..287
+                        } else if (kp < AM_PANELS) {
+                            mbar_wait(BAR(A_FULL + kp), ph_afull[kp]); ph_afull[kp] ^= 1;
+                            a_addr = sbase + OFF_AM + kp * PANEL_A;
+                        } else {                                          // [colour | dir - view | dir.view] K-step of block3.0
+                            a_addr = sbase + OFF_X0 + 4 * PANEL_A + (E7_COL0 + 16 * mb) * 2;
+                            ksteps = 1;
+                        }
+                        const int s = n % B_STAGES;
+                        mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1;
+                        tc_fence_after();
+                        const uint32_t b_addr = sbase + OFF_B + s * PANEL_B;
+                        for (int k = 0; k < ksteps; k++) {
+                            tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
+                            acc = 1;
+                        }
+                        tc_commit(BAR(B_EMPTY + s));
+                    }
+                    if (kind == LAYER_FROM_X0) tc_commit(BAR(X0_EMPTY));
+                    tc_commit(BAR(D_FULL + db));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels
+// torch Linear weight [N=256, K_in] fp32 -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (32 KB each)
+__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Kin, int npanels, uint8_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 bf16)
+    if (i >= npanels * TC_W * 8) return;
+    const int ch = i & 7, n = (i >> 3) % TC_W, pnl = i / (TC_W * 8);
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int k = pnl * 64 + ch * 8 + 2 * e;
+        const float a = k < Kin ? W[(size_t)n * Kin + k] : 0.f, b = (k + 1) < Kin ? W[(size_t)n * Kin + k + 1] : 0.f;
+        w[e] = pack_bf16(a, b);
+    }
+    uint4* dst = (uint4*)(out + (size_t)pnl * PANEL_B + n * 128 + ((ch ^ (n & 7)) << 4));
+    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// samples whose tuple rows straddle a 32-row boundary are accumulated with atomics: zero their outputs first
+__global__ void __launch_bounds__(256)
+tc_zero_cross_kernel(const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample, const int32_t* __restrict__ tuple_start,
+                     const int32_t* __restrict__ nvalid, float* __restrict__ F, int ldF, int W, float* __restrict__ sigma)
+{
+    const int lane = lane_id();
+    const int Sv = min(*S_ptr, S_max);
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= Sv) return;
+    const int s = csample[c];
+    const int st = tuple_start[s], nv = nvalid[s];
+    if ((st >> 5) == ((st + nv - 1) >> 5)) return;
+    for (int col = lane; col < W; col += 32) F[c * ldF + col] = 0.f;
+    if (lane == 0) sigma[c] = 0.f;
+}
+
+// C0[:, W : W + 6 FV] = view-direction encoding (ori=True, first three stripped), rest of the padding = 0
+__global__ void tc_viewdir_kernel(AggDims d, int SR, const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample,
+                                  const float* __restrict__ raydir, float* __restrict__ C0)
+{
+    const int Sv = min(*S_ptr, S_max);
+    const int nper = d.kc0pad - d.W;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Sv * nper) return;
+    const int64_t c = i / nper;
+    const int o = (int)(i - c * nper);
+    const int64_t r = csample[c] / SR;
+    float v = 0.f;
+    if (o < 6 * d.FV) {
+        const int isc = o >= 3 * d.FV, q = isc ? o - 3 * d.FV : o;
+        const int dd = q / d.FV, f = q - dd * d.FV;
+        const float a = raydir[3 * r + dd] * exp2f((float)f);
+        v = isc ? cosf(a) : sinf(a);
+    }
+    C0[c * d.kc0pad + d.W + o] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-case (every slot valid) workspace
+
+struct TcWs {
+    int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample;
+    float *loc_pers, *weight_n, *wc, *C0, *sigma, *sig;
+    float* CH[2];
+    float* Wt[AGG_MAX_LAYERS];
+    float* Wp[AGG_MAX_LAYERS];
+    uint8_t* wpack;
+};
+
+static size_t tc_carve(const AggPlan& P, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
+{
+    const AggDims& d = P.dims;
+    Arena A(base, cap);
+    const size_t S = (size_t)Rc * SR, T = S * K;
+    ws->nvalid = A.take<int32_t>(S + 1); ws->svalid = A.take<int32_t>(S + 1);
+    ws->tuple_start = A.take<int32_t>(S + 1); ws->sample_cidx = A.take<int32_t>(S + 1);
+    ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
+    ws->tuple_src = A.take<int32_t>(T + 1); ws->csample = A.take<int32_t>(S + 1);
+    ws->loc_pers = A.take<float>(S * 3); ws->weight_n = A.take<float>(T); ws->wc = A.take<float>(T);
+    ws->C0 = A.take<float>(S * d.kc0pad); ws->sigma = A.take<float>(S); ws->sig = A.take<float>(S * 4);
+    ws->CH[0] = A.take<float>(S * d.WC); ws->CH[1] = A.take<float>(S * d.WC);
+    for (int l = P.color_layer0; l < P.n_layers; l++) {
+        ws->Wt[l] = A.take<float>((size_t)P.layers[l].kpad * P.layers[l].npad);
+        ws->Wp[l] = A.take<float>((size_t)P.layers[l].kpad * P.layers[l].npad);
+    }
+    size_t panels = 0;
+    for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
+    ws->wpack = A.take<uint8_t>(panels * PANEL_B);
+    return A.off;
+}
+
+static int tc_supported(const AggPlan& P)
+{
+    const AggDims& d = P.dims;
+    SGN_CHECK_ARG(d.C == TC_C && d.F == TC_F && d.FD == TC_FD && d.W == TC_W,
+                  "bf16 tensor-core path is built for feat_dim=32, num_feat_freqs=3, dist_xyz_freq=5, width=256 (got %d,%d,%d,%d); use SGN_PRECISION_FP32",
+                  d.C, d.F, d.FD, d.W);
+    SGN_CHECK_ARG(d.LD == 0, "bf16 tensor-core path does not take the label embedding yet (label_dim=%d); use SGN_PRECISION_FP32", d.LD);
+    SGN_CHECK_ARG(P.n_tuple_layers <= TC_MAX_LAYERS, "bf16 tensor-core path: at most %d per-neighbour layers", TC_MAX_LAYERS);
+    for (int t = 0; t < P.n_tuple_layers; t++)
+        SGN_CHECK_ARG(P.layers[t].extra != EXTRA_LABEL, "bf16 tensor-core path: label input unsupported");
+    return SGN_OK;
+}
+
+}  // namespace sgn
 
 using namespace sgn;
 
-int sgn_agg_tc_workspace_bytes(const AggPlan&, int64_t, int, int, size_t*)
+int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, size_t* bytes)
 {
-    set_error("aggregator: SGN_PRECISION_BF16 is not built in this revision");
-    return SGN_E_INVALID;
+    int rc = tc_supported(P);
+    if (rc) return rc;
+    TcWs ws;
+    *bytes = tc_carve(P, R < TC_CHUNK ? R : TC_CHUNK, SR, K, nullptr, 0, &ws);
+    return SGN_OK;
 }
 
-int sgn_agg_tc_forward(const AggPlan&, const float* const*, const float* const*, const SgnPointTables*, const int32_t*, const float*,
-                       const float*, const float*, const float*, int64_t, int, int, float*, uint8_t*, float*, float*, float*, void*, size_t,
-                       cudaStream_t)
+int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                       const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* weight_out, float* conf_out,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st)
 {
-    set_error("aggregator: SGN_PRECISION_BF16 is not built in this revision");
-    return SGN_E_INVALID;
+    int rc = tc_supported(P);
+    if (rc) return rc;
+    const AggDims& d = P.dims;
+    const int64_t chunk = R < TC_CHUNK ? R : TC_CHUNK;
+    TcWs ws;
+    const size_t need = tc_carve(P, chunk, SR, K, workspace, workspace_bytes, &ws);
+    if (need > workspace_bytes || ((uintptr_t)workspace & 255)) {
+        set_error("sgn_agg_forward(bf16): workspace too small or misaligned (need %zu bytes, got %zu)", need, workspace_bytes);
+        return SGN_E_WORKSPACE;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_set = true;
+    }
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+
+    // weights: bf16 swizzled panels for the per-neighbour layers, fp32 packs for the colour branch
+    TcParams tp = {};
+    tp.first_panel[0] = 0;
+    for (int t = 0; t < P.n_tuple_layers; t++) {
+        const LayerInfo& L = P.layers[t];
+        const int np = (L.in + 63) / 64;
+        launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], L.in, np, ws.wpack + (size_t)tp.first_panel[t] * PANEL_B);
+        tp.first_panel[t + 1] = tp.first_panel[t] + np;
+        tp.kind[t] = t == 0 ? LAYER_FROM_X0 : (L.extra == EXTRA_COLORDIR ? LAYER_FROM_ACT_E7 : LAYER_FROM_ACT);
+        tp.bias[t] = biases[t];
+    }
+    for (int l = P.color_layer0; l < P.n_layers; l++) {
+        const LayerInfo& L = P.layers[l];
+        launch(pack_weight_kernel, cdiv(L.npad * L.kpad, 256), 256, 0, st, weights[l], L.out, L.in, L.npad, L.kpad, ws.Wt[l], ws.Wp[l]);
+    }
+    SGN_LAUNCH_CHECK();
+    tp.n_layers = P.n_tuple_layers;
+    tp.wpack = ws.wpack;
+    tp.wa = weights[P.alpha_layer]; tp.ba = biases[P.alpha_layer];
+    tp.slope = d.slope; tp.act_super = d.act_super;
+    tp.K = K; tp.SR = SR;
+
+    for (int64_t r0 = 0; r0 < R; r0 += chunk) {
+        const int64_t Rc = R - r0 < chunk ? R - r0 : chunk;
+        const int64_t S = Rc * SR;
+        const int Tm = (int)(S * K), Sm = (int)S;
+        AggIn in;
+        in.tab = *tables;
+        in.pidx = pidx + r0 * SR * K; in.loc_w = loc_w + r0 * SR * 3; in.raydir = raydir + r0 * 3; in.campos = campos; in.camrot = camrotc2w;
+        float* dec = decoded + r0 * SR * 4;
+        float* loc_pers = loc_pers_out ? loc_pers_out + r0 * SR * 3 : ws.loc_pers;
+        SGN_CUDA(cudaMemsetAsync(dec, 0, sizeof(float) * 4 * (size_t)S, st));
+        launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, ws.weight_n, weight_out ? weight_out + r0 * SR * K : nullptr,
+               conf_out ? conf_out + r0 * SR * K : nullptr, ray_valid + r0 * SR, ws.nvalid, ws.svalid);
+        if ((rc = exclusive_scan_i32(ws.nvalid, ws.tuple_start, S, ws.partials, st))) return rc;
+        if ((rc = exclusive_scan_i32(ws.svalid, ws.sample_cidx, S, ws.partials, st))) return rc;
+        const int32_t* T_ptr = ws.tuple_start + S;
+        const int32_t* S_ptr = ws.sample_cidx + S;
+        launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
+        launch(tc_zero_cross_kernel, cdiv(Sm, 8), 256, 0, st, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.C0, d.kc0pad, d.W, ws.sigma);
+        launch(tc_viewdir_kernel, cdiv((int64_t)Sm * (d.kc0pad - d.W), 256), 256, 0, st, d, SR, S_ptr, Sm, ws.csample, in.raydir, ws.C0);
+
+        tp.in = in;
+        tp.T_ptr = T_ptr; tp.T_max = Tm;
+        tp.tuple_src = ws.tuple_src; tp.tuple_start = ws.tuple_start; tp.nvalid = ws.nvalid; tp.sample_cidx = ws.sample_cidx;
+        tp.loc_pers = loc_pers; tp.wc = ws.wc;
+        tp.F = ws.C0; tp.ldF = d.kc0pad; tp.sigma = ws.sigma;
+        const int max_tiles = cdiv(Tm, TC_ROWS);
+        launch(agg_tuple_tc_kernel, max_tiles < n_sm ? max_tiles : n_sm, 320, TC_SMEM, st, tp);
+        SGN_LAUNCH_CHECK();
+
+        // colour MLP (fp32 SIMT for now) + rgb
+        const float* cur = ws.C0;
+        int cur_ld = d.kc0pad, cur_k = d.kc0pad;
+        for (int c = 0; c < P.n_color_hidden; c++) {
+            const int l = P.color_layer0 + c;
+            GemmNN g = {};
+            g.A1 = cur; g.lda1 = cur_ld; g.B1 = ws.Wt[l]; g.ldb1 = P.layers[l].npad; g.K1 = cur_k;
+            g.C = ws.CH[c & 1]; g.ldc = d.WC; g.N = d.WC; g.m_ptr = S_ptr; g.m_max = Sm; g.bias = biases[l]; g.epi = EPI_BIAS_LEAKY; g.slope = d.slope;
+            if ((rc = launch_gemm_nn(g, st))) return rc;
+            cur = ws.CH[c & 1]; cur_ld = d.WC; cur_k = d.WC;
+        }
+        const int ll = P.n_layers - 1;
+        launch(agg_rgb_kernel, cdiv(Sm, 8), 256, 0, st, d, S_ptr, Sm, ws.csample, cur, cur_ld, weights[ll], biases[ll], ws.sigma, dec, ws.sig);
+        SGN_LAUNCH_CHECK();
+    }
+    return SGN_OK;
 }

@@ -25,7 +25,7 @@ struct GemmNN {
 
 constexpr int GBM = 128, GBN = 128, GBK = 8, GTHREADS = 256, GPAD = 4;
 
-__global__ void __launch_bounds__(GTHREADS) gemm_nn_kernel(GemmNN p)
+static __global__ void __launch_bounds__(GTHREADS) gemm_nn_kernel(GemmNN p)
 {
     const int M = min(*p.m_ptr, p.m_max);
     const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
@@ -130,7 +130,7 @@ struct GemmTN {
     const int* m_ptr; int m_max; int m_per_block;
 };
 
-__global__ void __launch_bounds__(GTHREADS) gemm_tn_kernel(GemmTN p)
+static __global__ void __launch_bounds__(GTHREADS) gemm_tn_kernel(GemmTN p)
 {
     const int M = min(*p.m_ptr, p.m_max);
     const int mb = blockIdx.z * p.m_per_block;

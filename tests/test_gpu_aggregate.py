@@ -172,3 +172,28 @@ def test_inference_chunking_and_empty():
         out = ops.aggregate(cfg_to_c(cfg), W, B, tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(),
                             tables.conf.cuda(), None, empty, loc_w[:5].cuda(), raydir[:5].cuda(), campos.cuda(), rot.cuda())
         assert float(out[0].abs().max()) == 0 and int(out[1].sum()) == 0
+
+
+@pytest.mark.parametrize("R,SR", [(3, 24), (300, 24), (41, 80)])
+def test_bf16_tensor_core_path_vs_fp32(R, SR):
+    """bf16 tcgen05 path (forward only) against the fp32 strict path on the same inputs.
+    Stated bf16 tolerance (operands rounded to bf16, fp32 accumulate): |d rgb| <= 1e-2, |d sigma| <= 2e-2 * max(1, |sigma|);
+    validity masks, weights and conf coefficients are computed in fp32 on both paths and must be identical."""
+    cfg = rr.agg_config()
+    N, K = 5000, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=21 + R)
+    P = rr.init_params(cfg, seed=3, bias_scale=0.1)
+    _, W, B = param_lists(P, cfg)
+    args = (tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(), None,
+            pidx.cuda(), loc_w.cuda(), raydir.cuda(), campos.cuda(), rot.cuda())
+    with torch.no_grad():
+        ref = ops.aggregate(cfg_to_c(cfg), W, B, *args, precision=ops.PRECISION_FP32)
+        out = ops.aggregate(cfg_to_c(cfg), W, B, *args, precision=ops.PRECISION_BF16)
+    torch.cuda.synchronize()
+    assert torch.equal(out[1], ref[1])
+    torch.testing.assert_close(out[3], ref[3], rtol=0, atol=0)
+    torch.testing.assert_close(out[4], ref[4], rtol=0, atol=0)
+    d_rgb = float((out[0][..., 1:] - ref[0][..., 1:]).abs().max())
+    sig_err = ((out[0][..., 0] - ref[0][..., 0]).abs() / ref[0][..., 0].abs().clamp(min=1.0))
+    print(f"bf16 vs fp32: max |d rgb| = {d_rgb:.3e}, max rel |d sigma| = {float(sig_err.max()):.3e}")
+    assert d_rgb <= 1e-2 and float(sig_err.max()) <= 2e-2
