@@ -20,9 +20,9 @@
 // Shared memory (bytes): X0 5 x 16 KB | activations 4 x 16 KB (aliased by the K-sum staging) | weight ring 2 x 32 KB |
 // row metadata | mbarriers  = ~211 KB.  TMEM: 512 columns (2 accumulators of 128 lanes x 256 fp32 columns).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "agg_kernels.cuh"
-#include "gemm_simt.cuh"
 
 namespace sgn {
 
@@ -65,6 +65,7 @@ struct TcParams {
     const float* wa; const float* ba;
     float slope; int act_super;
     float* F; int ldF; float* sigma;       // outputs, per compact sample
+    int dbg;                               // SGN_TC_DEBUG bitmask (profiling experiments only; results invalid when != 0)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -121,6 +122,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void stsf(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ldsf(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         uint32_t ph_dfull[2] = {0, 0};
         uint32_t lcount = 0;                                   // global layer counter -> accumulator buffer
         uint32_t tcount = 0;
-        float* stg = (float*)(smem + OFF_AM) + warp * 32 * STG_LD;          // this warp's 32 x 33 staging rows
+        const uint32_t stg_a = sbase + OFF_AM + (uint32_t)(warp * 32 * STG_LD) * 4u;     // this warp's 32 x 33 staging rows
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int mb = tcount & 1;
             for (int l = 0; l < p.n_layers; l++, lcount++) {
@@ -180,11 +188,21 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                 tc_fence_after();
                 const float* bias = p.bias[l];
                 float araw = 0.f;
-                const float my_wc = last ? meta_wc[mb * TC_ROWS + row] : 0.f;
+                float my_wc = 0.f;
+                int mycs = -1, mycross = 0;
+                unsigned seg_heads = 0;                             // bit i: row i of this warp starts a new sample
+                if (last) {
+                    my_wc = meta_wc[mb * TC_ROWS + row];
+                    mycs = meta_cs[mb * TC_ROWS + row];
+                    mycross = meta_cross[mb * TC_ROWS + row];
+                    const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
+                    seg_heads = __ballot_sync(0xffffffffu, lane == 0 || prevcs != mycs);
+                }
 #pragma unroll 1
                 for (int c = 0; c < TC_W / 32; c++) {
                     uint32_t v[32];
                     tc_ld32(tmem_base + (uint32_t)(db * TC_W + c * 32) + ((uint32_t)(warp * 32) << 16), v);
+                    if (p.dbg & 8) { if (!last && (c & 1)) { fence_proxy_async(); mbar_arrive(BAR(A_FULL + (c >> 1))); } continue; }
                     float h[32];
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -207,8 +225,10 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                             fence_proxy_async();
                             mbar_arrive(BAR(A_FULL + (c >> 1)));
                         }
-                    } else {
-                        // alpha dot product + K-weighted segmented sums of this warp's 32 rows
+                    } else if (!(p.dbg & 16)) {
+                        // alpha dot product + K-weighted segmented sums over the rows of each sample (this warp's 32 rows):
+                        // transpose through shared memory (lane = row -> lane = column), then a fully unrolled walk over
+                        // the rows whose segment ends are warp-uniform (seg_heads), all loads issued up front
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 w4 = __ldg((const float4*)(p.wa + c * 32 + i));
@@ -217,26 +237,25 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                         }
                         __syncwarp();
 #pragma unroll
-                        for (int i = 0; i < 32; i++) stg[lane * STG_LD + i] = h[i] * my_wc;
+                        for (int i = 0; i < 32; i++) stsf(stg_a + (uint32_t)(lane * STG_LD + i) * 4u, h[i] * my_wc);
                         __syncwarp();
-                        const int32_t* cs = meta_cs + mb * TC_ROWS + warp * 32;
-                        const int32_t* cr = meta_cross + mb * TC_ROWS + warp * 32;
+                        float t[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) t[i] = ldsf(stg_a + (uint32_t)(i * STG_LD + lane) * 4u);
                         float acc = 0.f;
-                        int cur = cs[0];
+#pragma unroll
                         for (int i = 0; i < 32; i++) {
-                            const int ci = cs[i];
-                            if (ci != cur) {
-                                if (cur >= 0) {
-                                    float* dst = p.F + (size_t)cur * p.ldF + c * 32 + lane;
-                                    if (cr[i - 1]) atomicAdd(dst, acc); else *dst = acc;
+                            acc += t[i];
+                            const bool seg_end = (i == 31) || ((seg_heads >> (i + 1)) & 1u);
+                            if (seg_end) {                       // warp-uniform
+                                const int ci = __shfl_sync(0xffffffffu, mycs, i);
+                                const int cr = __shfl_sync(0xffffffffu, mycross, i);
+                                if (ci >= 0) {
+                                    float* dst = p.F + (size_t)ci * p.ldF + c * 32 + lane;
+                                    if (cr) atomicAdd(dst, acc); else *dst = acc;
                                 }
-                                acc = 0.f; cur = ci;
+                                acc = 0.f;
                             }
-                            acc += stg[i * STG_LD + lane];
-                        }
-                        if (cur >= 0) {
-                            float* dst = p.F + (size_t)cur * p.ldF + c * 32 + lane;
-                            if (cr[31]) atomicAdd(dst, acc); else *dst = acc;
                         }
                     }
                 }
@@ -247,13 +266,10 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                     const float a = araw + p.ba[0];
                     const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
                     const float val = act * my_wc;
-                    const int mycs = meta_cs[mb * TC_ROWS + row];
-                    const int mycross = meta_cross[mb * TC_ROWS + row];
-                    const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
-                    const bool head = (lane == 0) || (prevcs != mycs);
+                    const bool head = (seg_heads >> lane) & 1u;
                     float sum = val;
                     bool open = true;
-                    for (int dlt = 1; dlt < 32; dlt++) {
+                    for (int dlt = 1; dlt < p.K; dlt++) {         // a sample has at most K rows
                         const float vj = __shfl_down_sync(0xffffffffu, val, dlt);
                         const int cj = __shfl_down_sync(0xffffffffu, mycs, dlt);
                         open = open && (lane + dlt < 32) && (cj == mycs);
@@ -277,8 +293,6 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         const uint32_t x0 = sbase + OFF_X0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int mb = tcount & 1;
-            mbar_wait(BAR(X0_EMPTY), ph_x0empty); ph_x0empty ^= 1;
-            mbar_wait(BAR(META_FREE + mb), ph_meta[mb]); ph_meta[mb] ^= 1;
             const int64_t j = (int64_t)tile * TC_ROWS + row;
             const bool live = j < T;
             float wcv = 0.f; int csv = -1, crossv = 0;
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
             for (int i = 0; i < 6; i++) dist[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; i++) e7[i] = 0.f;
-            if (live) {
+            if (live && !(p.dbg & 4)) {
                 const int flat = p.tuple_src[j];
                 const int64_t s = flat / p.K;
                 const int64_t r = s / p.SR;
@@ -318,12 +332,16 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                 e7[0] = p.in.tab.color[3 * pt]; e7[1] = p.in.tab.color[3 * pt + 1]; e7[2] = p.in.tab.color[3 * pt + 2];
                 e7[3] = dx - vx; e7[4] = dy - vy; e7[5] = dz - vz; e7[6] = dx * vx + dy * vy + dz * vz;
             }
+            // the global loads above are in flight while the previous tile still owns the X0 panels
+            mbar_wait(BAR(X0_EMPTY), ph_x0empty); ph_x0empty ^= 1;
+            mbar_wait(BAR(META_FREE + mb), ph_meta[mb]); ph_meta[mb] ^= 1;
             // cols [0,32): embedding
 #pragma unroll
             for (int q = 0; q < 4; q++)
                 sts128(x0 + sw_off(row, 8 * q), pack_bf16(emb[8 * q], emb[8 * q + 1]), pack_bf16(emb[8 * q + 2], emb[8 * q + 3]),
                        pack_bf16(emb[8 * q + 4], emb[8 * q + 5]), pack_bf16(emb[8 * q + 6], emb[8 * q + 7]));
             // cols 32 + 2*(c*F + f) + {0: sin, 1: cos}: base angle by sincosf, octaves by the double-angle recurrence
+            if (!(p.dbg & 2))
 #pragma unroll
             for (int c = 0; c < TC_C; c++) {
                 float sn, cs_;
@@ -371,6 +389,7 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                 for (int pi = 0; pi < total_panels; pi++, n++) {
                     const int s = n % B_STAGES;
                     mbar_wait(BAR(B_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
+                    if (p.dbg & 1) { mbar_arrive(BAR(B_FULL + s)); continue; }
                     mbar_expect_tx(BAR(B_FULL + s), PANEL_B);
                     bulk_g2s(sbase + OFF_B + s * PANEL_B, p.wpack + (size_t)pi * PANEL_B, PANEL_B, BAR(B_FULL + s));
                 }
@@ -426,13 +445,257 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
     if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+
+// ================================================================================================ colour branch
+// Per-sample colour MLP on tensor cores (point_aggregators.py:298-309 raw2out_color, :771-786): one persistent CTA per SM,
+// tile = 128 compact samples.  All hidden-layer weights stay resident in shared memory (bf16, 128B-swizzled K-major
+// panels); the A operand of the first layer is streamed: loader warps read the fp32 K-sums F[c, 0:256] written by the
+// per-neighbour kernel, round to bf16 and write 16 KB swizzled panels into a 2-stage ring, the fifth panel holds the
+// view-direction encoding.  The 128-wide activations live in place in two panels; the last Linear (128 -> 3), the
+// sigmoid and the (sigma, r, g, b) store are fused into the last epilogue.
+//   warps 0-3 epilogue | warps 4-7 loaders | warp 8 MMA issuer (and the one-off weight load)
+constexpr int CW = 128;                                   // colour hidden width
+constexpr int C_PANEL = CW * 128;                         // 16 KB: 128 rows x 64 bf16 (A and B panels alike)
+constexpr int C_K0_PANELS = 5, C_RING = 2, C_MAX_HIDDEN = 3;
+constexpr int COFF_W = 0;                                                   // resident weights: 5 + 2 + 2 panels
+constexpr int C_W_PANELS = C_K0_PANELS + 2 * (C_MAX_HIDDEN - 1);
+constexpr int COFF_RING = COFF_W + C_W_PANELS * C_PANEL;
+constexpr int COFF_ACT = COFF_RING + C_RING * C_PANEL;
+constexpr int COFF_BIAS = COFF_ACT + 2 * C_PANEL;                           // [3][128] hidden biases
+constexpr int COFF_WL = COFF_BIAS + C_MAX_HIDDEN * CW * 4;                  // [3][128] last Linear + its bias [4]
+constexpr int COFF_BAR = COFF_WL + 3 * CW * 4 + 16;
+constexpr int C_NBARS = 1 + 2 * C_RING + 2 + 4;
+constexpr int COFF_TMEMPTR = COFF_BAR + C_NBARS * 8;
+constexpr int C_SMEM = COFF_TMEMPTR + 16 + 1024;
+static_assert(C_SMEM <= 232448, "colour kernel exceeds the 227 KB shared memory limit");
+constexpr uint32_t C_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+
+struct ColParams {
+    const int32_t* S_ptr; int S_max;
+    const int32_t* csample;            // compact sample -> sample
+    const float* F; int ldF;           // [S_v, ldF] K-sums (first 256 columns)
+    const float* sigma;                // [S_v]
+    const float* raydir; int SR;
+    const uint8_t* wpack;              // packed hidden-layer weights, C_PANEL each, layer after layer
+    int n_hidden;                      // colour layers followed by an activation (1..3)
+    int fv;                            // num_viewdir_freqs
+    const float* bias[C_MAX_HIDDEN];
+    const float* wl; const float* bl;  // last Linear [3,128], [3]
+    float slope; int act_super;
+    float* decoded;                    // [S,4]
+};
+
+__global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_constant__ ColParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = sbase + COFF_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+    const int W_FULL = 0, R_FULL = 1, R_EMPTY = R_FULL + C_RING, A_FULL = R_EMPTY + C_RING, D_FULL = A_FULL + 2, D_EMPTY = D_FULL + 2;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(smem + COFF_TMEMPTR);
+    float* s_bias = (float*)(smem + COFF_BIAS);
+    float* s_wl = (float*)(smem + COFF_WL);
+
+    const int Sv = min(*p.S_ptr, p.S_max);
+    const int ntiles = (Sv + TC_ROWS - 1) / TC_ROWS;
+    const int n_wpanels = C_K0_PANELS + 2 * (p.n_hidden - 1);
+
+    if (tid == 0) {
+        mbar_init(BAR(W_FULL), 1);
+        for (int s = 0; s < C_RING; s++) { mbar_init(BAR(R_FULL + s), 128); mbar_init(BAR(R_EMPTY + s), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < p.n_hidden * CW; i += blockDim.x) s_bias[i] = p.bias[i / CW][i % CW];
+    for (int i = tid; i < 3 * CW; i += blockDim.x) s_wl[i] = p.wl[i];
+    if (tid < 3) s_wl[3 * CW + tid] = p.bl[tid];
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp < 4) {
+        // =========================================================== EPILOGUE
+        const int row = tid;
+        uint32_t ph_dfull[2] = {0, 0};
+        uint32_t lcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t c = (int64_t)tile * TC_ROWS + row;
+            for (int l = 0; l < p.n_hidden; l++, lcount++) {
+                const int db = lcount & 1;
+                const bool last = (l == p.n_hidden - 1);
+                mbar_wait(BAR(D_FULL + db), ph_dfull[db]);
+                ph_dfull[db] ^= 1;
+                tc_fence_after();
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < CW / 32; ch++) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + (uint32_t)(db * CW + ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+                    float h[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bb = *(const float4*)(s_bias + l * CW + ch * 32 + i);
+                        float x0 = __uint_as_float(v[i]) + bb.x, x1 = __uint_as_float(v[i + 1]) + bb.y;
+                        float x2 = __uint_as_float(v[i + 2]) + bb.z, x3 = __uint_as_float(v[i + 3]) + bb.w;
+                        h[i] = fmaxf(x0, x0 * p.slope); h[i + 1] = fmaxf(x1, x1 * p.slope);
+                        h[i + 2] = fmaxf(x2, x2 * p.slope); h[i + 3] = fmaxf(x3, x3 * p.slope);
+                    }
+                    if (!last) {
+                        const uint32_t rowbase = sbase + COFF_ACT + (ch >> 1) * C_PANEL + row * 128;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int k = (ch & 1) * 4 + q;
+                            sts128(rowbase + ((k ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                                   pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                        }
+                        if (ch & 1) {
+                            fence_proxy_async();
+                            mbar_arrive(BAR(A_FULL + (ch >> 1)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 w0 = *(const float4*)(s_wl + ch * 32 + i);
+                            const float4 w1 = *(const float4*)(s_wl + CW + ch * 32 + i);
+                            const float4 w2 = *(const float4*)(s_wl + 2 * CW + ch * 32 + i);
+                            o0 = fmaf(h[i], w0.x, o0); o0 = fmaf(h[i + 1], w0.y, o0); o0 = fmaf(h[i + 2], w0.z, o0); o0 = fmaf(h[i + 3], w0.w, o0);
+                            o1 = fmaf(h[i], w1.x, o1); o1 = fmaf(h[i + 1], w1.y, o1); o1 = fmaf(h[i + 2], w1.z, o1); o1 = fmaf(h[i + 3], w1.w, o1);
+                            o2 = fmaf(h[i], w2.x, o2); o2 = fmaf(h[i + 1], w2.y, o2); o2 = fmaf(h[i + 2], w2.z, o2); o2 = fmaf(h[i + 3], w2.w, o2);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(BAR(D_EMPTY + db));
+                if (last && c < Sv) {
+                    const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
+                                s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
+                    const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
+                    ((float4*)p.decoded)[p.csample[c]] = make_float4(p.sigma[c], s0 * m - o, s1 * m - o, s2 * m - o);
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // =========================================================== LOADERS: F (fp32, global) -> bf16 ring panels
+        const int lt = tid - 128;
+        const int sub = lt & 15, rgrp = lt >> 4;              // 16 threads per row (float4 each), 8 rows per pass
+        uint32_t ph_empty[C_RING];
+        for (int s = 0; s < C_RING; s++) ph_empty[s] = 1;
+        uint32_t n = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t c0 = (int64_t)tile * TC_ROWS;
+            for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
+                const int s = n % C_RING;
+                const uint32_t base = sbase + COFF_RING + s * C_PANEL;
+                if (kp < 4) {
+                    float4 f[16];
+#pragma unroll
+                    for (int pass = 0; pass < 16; pass++) {
+                        const int r = pass * 8 + rgrp;
+                        f[pass] = (c0 + r < Sv) ? __ldg((const float4*)(p.F + (size_t)(c0 + r) * p.ldF + kp * 64 + sub * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
+#pragma unroll
+                    for (int pass = 0; pass < 16; pass++) {
+                        const int r = pass * 8 + rgrp;
+                        const uint32_t a = base + r * 128 + (((sub >> 1) ^ (r & 7)) << 4) + (sub & 1) * 8;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(pack_bf16(f[pass].x, f[pass].y)), "r"(pack_bf16(f[pass].z, f[pass].w)) : "memory");
+                    }
+                } else {
+                    // view-direction encoding (ori=True, first three stripped): sin(v_d 2^f) d-major, then the cosines; cols [6 fv, 32) = 0
+                    const int r = lt;
+                    float vals[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) vals[i] = 0.f;
+                    if (c0 + r < Sv) {
+                        const int64_t ray = p.csample[c0 + r] / p.SR;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            if (i < 3 * p.fv) {
+                                const int dd = i / p.fv, f = i - dd * p.fv;
+                                float sn, cs;
+                                sincosf(p.raydir[3 * ray + dd] * exp2f((float)f), &sn, &cs);
+#pragma unroll
+                                for (int j = 0; j < 32; j++) {
+                                    if (j == i) vals[j] = sn;
+                                    if (j == i + 3 * p.fv) vals[j] = cs;
+                                }
+                            }
+                        }
+                    }
+                    mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        sts128(base + r * 128 + ((q ^ (r & 7)) << 4), pack_bf16(vals[8 * q], vals[8 * q + 1]), pack_bf16(vals[8 * q + 2], vals[8 * q + 3]),
+                               pack_bf16(vals[8 * q + 4], vals[8 * q + 5]), pack_bf16(vals[8 * q + 6], vals[8 * q + 7]));
+                }
+                fence_proxy_async();
+                mbar_arrive(BAR(R_FULL + s));
+            }
+        }
+    } else {
+        // =========================================================== MMA issuer (+ one-off resident weight load)
+        if (lane == 0) {
+            mbar_expect_tx(BAR(W_FULL), (uint32_t)n_wpanels * C_PANEL);
+            for (int i = 0; i < n_wpanels; i++) bulk_g2s(sbase + COFF_W + i * C_PANEL, p.wpack + (size_t)i * C_PANEL, C_PANEL, BAR(W_FULL));
+            mbar_wait(BAR(W_FULL), 0);
+            uint32_t ph_full[C_RING];
+            for (int s = 0; s < C_RING; s++) ph_full[s] = 0;
+            uint32_t ph_afull[2] = {0, 0}, ph_dempty[2] = {1, 1};
+            uint32_t n = 0, lcount = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int l = 0; l < p.n_hidden; l++, lcount++) {
+                    const int db = lcount & 1;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(db * CW);
+                    mbar_wait(BAR(D_EMPTY + db), ph_dempty[db]); ph_dempty[db] ^= 1;
+                    uint32_t acc = 0;
+                    if (l == 0) {
+                        for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
+                            const int s = n % C_RING;
+                            mbar_wait(BAR(R_FULL + s), ph_full[s]); ph_full[s] ^= 1;
+                            tc_fence_after();
+                            const uint32_t a_addr = sbase + COFF_RING + s * C_PANEL, b_addr = sbase + COFF_W + kp * C_PANEL;
+                            const int ksteps = kp < 4 ? 4 : 2;
+                            for (int k = 0; k < ksteps; k++) {
+                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), C_IDESC, acc);
+                                acc = 1;
+                            }
+                            tc_commit(BAR(R_EMPTY + s));
+                        }
+                    } else {
+                        for (int kp = 0; kp < 2; kp++) {
+                            mbar_wait(BAR(A_FULL + kp), ph_afull[kp]); ph_afull[kp] ^= 1;
+                            tc_fence_after();
+                            const uint32_t a_addr = sbase + COFF_ACT + kp * C_PANEL;
+                            const uint32_t b_addr = sbase + COFF_W + (C_K0_PANELS + 2 * (l - 1) + kp) * C_PANEL;
+                            for (int k = 0; k < 4; k++) {
+                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), C_IDESC, acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    tc_commit(BAR(D_FULL + db));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ small kernels
 // torch Linear weight [N=256, K_in] fp32 -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (32 KB each)
-__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Kin, int npanels, uint8_t* __restrict__ out)
+__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, int Kin, int npanels, uint8_t* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 bf16)
-    if (i >= npanels * TC_W * 8) return;
-    const int ch = i & 7, n = (i >> 3) % TC_W, pnl = i / (TC_W * 8);
+    if (i >= npanels * Nrows * 8) return;
+    const int ch = i & 7, n = (i >> 3) % Nrows, pnl = i / (Nrows * 8);
     uint32_t w[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -440,7 +703,7 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Kin, int 
         const float a = k < Kin ? W[(size_t)n * Kin + k] : 0.f, b = (k + 1) < Kin ? W[(size_t)n * Kin + k + 1] : 0.f;
         w[e] = pack_bf16(a, b);
     }
-    uint4* dst = (uint4*)(out + (size_t)pnl * PANEL_B + n * 128 + ((ch ^ (n & 7)) << 4));
+    uint4* dst = (uint4*)(out + (size_t)pnl * Nrows * 128 + n * 128 + ((ch ^ (n & 7)) << 4));
     *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -460,37 +723,13 @@ tc_zero_cross_kernel(const int32_t* __restrict__ S_ptr, int S_max, const int32_t
     if (lane == 0) sigma[c] = 0.f;
 }
 
-// C0[:, W : W + 6 FV] = view-direction encoding (ori=True, first three stripped), rest of the padding = 0
-__global__ void tc_viewdir_kernel(AggDims d, int SR, const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample,
-                                  const float* __restrict__ raydir, float* __restrict__ C0)
-{
-    const int Sv = min(*S_ptr, S_max);
-    const int nper = d.kc0pad - d.W;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)Sv * nper) return;
-    const int64_t c = i / nper;
-    const int o = (int)(i - c * nper);
-    const int64_t r = csample[c] / SR;
-    float v = 0.f;
-    if (o < 6 * d.FV) {
-        const int isc = o >= 3 * d.FV, q = isc ? o - 3 * d.FV : o;
-        const int dd = q / d.FV, f = q - dd * d.FV;
-        const float a = raydir[3 * r + dd] * exp2f((float)f);
-        v = isc ? cosf(a) : sinf(a);
-    }
-    C0[c * d.kc0pad + d.W + o] = v;
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-case (every slot valid) workspace
 
 struct TcWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample;
-    float *loc_pers, *weight_n, *wc, *C0, *sigma, *sig;
-    float* CH[2];
-    float* Wt[AGG_MAX_LAYERS];
-    float* Wp[AGG_MAX_LAYERS];
-    uint8_t* wpack;
+    float *loc_pers, *weight_n, *wc, *C0, *sigma;
+    uint8_t *wpack, *cpack;
 };
 
 static size_t tc_carve(const AggPlan& P, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
@@ -503,15 +742,11 @@ static size_t tc_carve(const AggPlan& P, int64_t Rc, int SR, int K, void* base, 
     ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1); ws->csample = A.take<int32_t>(S + 1);
     ws->loc_pers = A.take<float>(S * 3); ws->weight_n = A.take<float>(T); ws->wc = A.take<float>(T);
-    ws->C0 = A.take<float>(S * d.kc0pad); ws->sigma = A.take<float>(S); ws->sig = A.take<float>(S * 4);
-    ws->CH[0] = A.take<float>(S * d.WC); ws->CH[1] = A.take<float>(S * d.WC);
-    for (int l = P.color_layer0; l < P.n_layers; l++) {
-        ws->Wt[l] = A.take<float>((size_t)P.layers[l].kpad * P.layers[l].npad);
-        ws->Wp[l] = A.take<float>((size_t)P.layers[l].kpad * P.layers[l].npad);
-    }
+    ws->C0 = A.take<float>(S * d.W); ws->sigma = A.take<float>(S);
     size_t panels = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
+    ws->cpack = A.take<uint8_t>((size_t)C_W_PANELS * C_PANEL);
     return A.off;
 }
 
@@ -523,6 +758,9 @@ static int tc_supported(const AggPlan& P)
                   d.C, d.F, d.FD, d.W);
     SGN_CHECK_ARG(d.LD == 0, "bf16 tensor-core path does not take the label embedding yet (label_dim=%d); use SGN_PRECISION_FP32", d.LD);
     SGN_CHECK_ARG(P.n_tuple_layers <= TC_MAX_LAYERS, "bf16 tensor-core path: at most %d per-neighbour layers", TC_MAX_LAYERS);
+    SGN_CHECK_ARG(P.n_color_hidden >= 1 && P.n_color_hidden <= C_MAX_HIDDEN && d.WC == CW && d.FV <= 5,
+                  "bf16 tensor-core path: colour branch must have 2..%d layers of width %d and num_viewdir_freqs <= 5; use SGN_PRECISION_FP32",
+                  C_MAX_HIDDEN + 1, CW);
     for (int t = 0; t < P.n_tuple_layers; t++)
         SGN_CHECK_ARG(P.layers[t].extra != EXTRA_LABEL, "bf16 tensor-core path: label input unsupported");
     return SGN_OK;
@@ -559,26 +797,34 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     static bool attr_set = false;
     if (!attr_set) {
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        SGN_CUDA(cudaFuncSetAttribute(agg_color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
         attr_set = true;
     }
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
 
-    // weights: bf16 swizzled panels for the per-neighbour layers, fp32 packs for the colour branch
+    // weights -> bf16 panels in the 128B-swizzled shared-memory image (per call: they may have been updated by the optimiser)
     TcParams tp = {};
     tp.first_panel[0] = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) {
         const LayerInfo& L = P.layers[t];
         const int np = (L.in + 63) / 64;
-        launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], L.in, np, ws.wpack + (size_t)tp.first_panel[t] * PANEL_B);
+        launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], TC_W, L.in, np, ws.wpack + (size_t)tp.first_panel[t] * PANEL_B);
         tp.first_panel[t + 1] = tp.first_panel[t] + np;
         tp.kind[t] = t == 0 ? LAYER_FROM_X0 : (L.extra == EXTRA_COLORDIR ? LAYER_FROM_ACT_E7 : LAYER_FROM_ACT);
         tp.bias[t] = biases[t];
     }
-    for (int l = P.color_layer0; l < P.n_layers; l++) {
-        const LayerInfo& L = P.layers[l];
-        launch(pack_weight_kernel, cdiv(L.npad * L.kpad, 256), 256, 0, st, weights[l], L.out, L.in, L.npad, L.kpad, ws.Wt[l], ws.Wp[l]);
+    ColParams cp = {};
+    {
+        int pnl = 0;
+        for (int c = 0; c < P.n_color_hidden; c++) {
+            const int l = P.color_layer0 + c;
+            const int np = c == 0 ? C_K0_PANELS : 2;
+            launch(tc_pack_weight_kernel, cdiv((int64_t)np * CW * 8, 256), 256, 0, st, weights[l], CW, P.layers[l].in, np, ws.cpack + (size_t)pnl * C_PANEL);
+            pnl += np;
+            cp.bias[c] = biases[l];
+        }
     }
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
@@ -586,6 +832,10 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     tp.wa = weights[P.alpha_layer]; tp.ba = biases[P.alpha_layer];
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;
+    { const char* e = getenv("SGN_TC_DEBUG"); tp.dbg = e ? atoi(e) : 0; }
+    cp.wpack = ws.cpack; cp.n_hidden = P.n_color_hidden; cp.fv = d.FV;
+    cp.wl = weights[P.n_layers - 1]; cp.bl = biases[P.n_layers - 1];
+    cp.slope = d.slope; cp.act_super = d.act_super; cp.SR = SR;
 
     for (int64_t r0 = 0; r0 < R; r0 += chunk) {
         const int64_t Rc = R - r0 < chunk ? R - r0 : chunk;
@@ -604,31 +854,21 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         const int32_t* T_ptr = ws.tuple_start + S;
         const int32_t* S_ptr = ws.sample_cidx + S;
         launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
-        launch(tc_zero_cross_kernel, cdiv(Sm, 8), 256, 0, st, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.C0, d.kc0pad, d.W, ws.sigma);
-        launch(tc_viewdir_kernel, cdiv((int64_t)Sm * (d.kc0pad - d.W), 256), 256, 0, st, d, SR, S_ptr, Sm, ws.csample, in.raydir, ws.C0);
+        launch(tc_zero_cross_kernel, cdiv(Sm, 8), 256, 0, st, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.C0, d.W, d.W, ws.sigma);
 
         tp.in = in;
         tp.T_ptr = T_ptr; tp.T_max = Tm;
         tp.tuple_src = ws.tuple_src; tp.tuple_start = ws.tuple_start; tp.nvalid = ws.nvalid; tp.sample_cidx = ws.sample_cidx;
         tp.loc_pers = loc_pers; tp.wc = ws.wc;
-        tp.F = ws.C0; tp.ldF = d.kc0pad; tp.sigma = ws.sigma;
+        tp.F = ws.C0; tp.ldF = d.W; tp.sigma = ws.sigma;
         const int max_tiles = cdiv(Tm, TC_ROWS);
         launch(agg_tuple_tc_kernel, max_tiles < n_sm ? max_tiles : n_sm, 320, TC_SMEM, st, tp);
-        SGN_LAUNCH_CHECK();
 
-        // colour MLP (fp32 SIMT for now) + rgb
-        const float* cur = ws.C0;
-        int cur_ld = d.kc0pad, cur_k = d.kc0pad;
-        for (int c = 0; c < P.n_color_hidden; c++) {
-            const int l = P.color_layer0 + c;
-            GemmNN g = {};
-            g.A1 = cur; g.lda1 = cur_ld; g.B1 = ws.Wt[l]; g.ldb1 = P.layers[l].npad; g.K1 = cur_k;
-            g.C = ws.CH[c & 1]; g.ldc = d.WC; g.N = d.WC; g.m_ptr = S_ptr; g.m_max = Sm; g.bias = biases[l]; g.epi = EPI_BIAS_LEAKY; g.slope = d.slope;
-            if ((rc = launch_gemm_nn(g, st))) return rc;
-            cur = ws.CH[c & 1]; cur_ld = d.WC; cur_k = d.WC;
-        }
-        const int ll = P.n_layers - 1;
-        launch(agg_rgb_kernel, cdiv(Sm, 8), 256, 0, st, d, S_ptr, Sm, ws.csample, cur, cur_ld, weights[ll], biases[ll], ws.sigma, dec, ws.sig);
+        // per-sample colour MLP + rgb + (sigma, r, g, b) store
+        cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.C0; cp.ldF = d.W; cp.sigma = ws.sigma;
+        cp.raydir = in.raydir; cp.decoded = dec;
+        const int max_ctiles = cdiv(Sm, TC_ROWS);
+        launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, 288, C_SMEM, st, cp);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;
