@@ -30,19 +30,21 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_W = 256;                 // layer width == accumulator columns
 constexpr int TC_C = 32, TC_F = 3, TC_FD = 5;
 constexpr int TC_K0 = TC_C * (1 + 2 * TC_F) + 2 * TC_FD * 6;   // 284
-constexpr int TC_MAX_LAYERS = 8;
+constexpr int TC_MAX_LAYERS = 6;
 constexpr int PANEL_A = TC_ROWS * 128;    // 16 KB: 128 rows x 64 bf16
 constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
 constexpr int X0_PANELS = 5, AM_PANELS = 4, B_STAGES = 2;
 constexpr int E7_COL0 = 32;               // inside X0 panel 4: cols [32,48) tile parity 0, [48,64) parity 1
-constexpr int STG_LD = 33;                // staging row pitch (floats): conflict-free row writes and column walks
 
+constexpr int STG_LD = 33;                // last-layer staging row pitch (floats): conflict-free row writes and column walks
 constexpr int OFF_X0 = 0;
 constexpr int OFF_AM = OFF_X0 + X0_PANELS * PANEL_A;            // 81920
 constexpr int OFF_B = OFF_AM + AM_PANELS * PANEL_A;             // 147456
 constexpr int OFF_META = OFF_B + B_STAGES * PANEL_B;            // 212992
 constexpr int META_BYTES = 2 * TC_ROWS * 12;                    // wc (f32), cs (i32), cross (i32), double buffered
-constexpr int OFF_BAR = OFF_META + META_BYTES;
+constexpr int OFF_BIAS = OFF_META + META_BYTES;                 // [TC_MAX_LAYERS][256] biases + wa[256]
+constexpr int BIAS_BYTES = (TC_MAX_LAYERS + 1) * TC_W * 4;
+constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int N_BARS = 2 * B_STAGES + 2 + AM_PANELS + 4 + 2;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
@@ -73,11 +75,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// spinning in the issue slots of the epilogue / gather warps that share its scheduler
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
@@ -102,6 +107,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
                    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+// the wait names the destination registers as in/out operands so no use of them can be scheduled above it
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
@@ -128,6 +156,40 @@ __device__ __forceinline__ float ldsf(uint32_t addr)
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
+}
+__device__ __forceinline__ int ldsi(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// One row of the K-sum walk, as a single asm so that none of its (chunk-invariant) bit tests can be hoisted into registers:
+// row address = base + popc(heads & prefix) * ld_bytes; plain store if (st_plain & bit), reduction if (st_atom & bit).
+__device__ __forceinline__ void ksum_store(const float* base, float v, uint32_t st_plain, uint32_t st_atom, uint32_t heads, uint32_t bit,
+                                           uint32_t prefix, uint32_t ld_bytes)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 t, n;\n\t.reg .b64 off, a;\n\t"
+        "and.b32 t, %2, %5;\n\tsetp.ne.u32 p, t, 0;\n\t"
+        "and.b32 t, %3, %5;\n\tsetp.ne.u32 q, t, 0;\n\t"
+        "and.b32 n, %4, %6;\n\tpopc.b32 n, n;\n\t"
+        "mul.wide.u32 off, n, %7;\n\tadd.s64 a, %0, off;\n\t"
+        "@p st.global.f32 [a], %1;\n\t@q red.global.add.f32 [a], %1;\n\t}"
+        ::"l"(base), "f"(v), "r"(st_plain), "r"(st_atom), "r"(heads), "r"(bit), "r"(prefix), "r"(ld_bytes) : "memory");
+}
+__device__ __forceinline__ void st_global_pred(float* addr, float v, uint32_t flag)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(flag) : "memory");
+}
+__device__ __forceinline__ void red_global_pred(float* addr, float v, uint32_t flag)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(flag) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
@@ -162,6 +224,10 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         for (int i = 0; i < 2; i++) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); mbar_init(BAR(META_FREE + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < (p.n_layers + 1) * TC_W; i += blockDim.x) {
+        const int l = i / TC_W, c = i - l * TC_W;
+        ((float*)(smem + OFF_BIAS))[i] = l < p.n_layers ? p.bias[l][c] : p.wa[c];
+    }
     if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -177,61 +243,98 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         uint32_t ph_dfull[2] = {0, 0};
         uint32_t lcount = 0;                                   // global layer counter -> accumulator buffer
         uint32_t tcount = 0;
-        const uint32_t stg_a = sbase + OFF_AM + (uint32_t)(warp * 32 * STG_LD) * 4u;     // this warp's 32 x 33 staging rows
+        long long pf_wait = 0, pf_ld = 0, pf_mid = 0, pf_last = 0, pf_sigma = 0, pf_t0 = 0;
+        const bool prof = (p.dbg & 32) != 0;
+        const uint32_t bias_a = sbase + OFF_BIAS;                              // [n_layers][256] f32, then wa[256]
+        const uint32_t wa_a = bias_a + (uint32_t)(p.n_layers * TC_W) * 4u;
+        const uint32_t stg_a = sbase + OFF_AM + (uint32_t)(warp * 32 * STG_LD) * 4u;     // this warp's 32 x 33 staging rows (last layer)
+        const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+        const uint32_t act_row = sbase + OFF_AM + row * 128;
+        const float slope = p.slope;
+
+        // bias + LeakyReLU on one 32-column chunk
+        auto activate = [&](const uint32_t(&vv)[32], uint32_t bias_chunk, float(&h)[32]) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 bb = lds128f(bias_chunk + i * 4);
+                const float x0 = __uint_as_float(vv[i]) + bb.x, x1 = __uint_as_float(vv[i + 1]) + bb.y;
+                const float x2 = __uint_as_float(vv[i + 2]) + bb.z, x3 = __uint_as_float(vv[i + 3]) + bb.w;
+                h[i] = fmaxf(x0, x0 * slope); h[i + 1] = fmaxf(x1, x1 * slope);
+                h[i + 2] = fmaxf(x2, x2 * slope); h[i + 3] = fmaxf(x3, x3 * slope);
+            }
+        };
+        // hidden layer: bf16 activations into the next layer's A operand (panel c/2, 16-byte chunks (c&1)*4 .. +3 of this row)
+        auto mid_chunk = [&](int c, const uint32_t(&vv)[32], uint32_t bias_l) {
+            if (p.dbg & 8) return;
+            float h[32];
+            activate(vv, bias_l + c * 128, h);
+            const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int ch = (c & 1) * 4 + q;
+                sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                       pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+            }
+        };
+
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int mb = tcount & 1;
             for (int l = 0; l < p.n_layers; l++, lcount++) {
                 const int db = lcount & 1;
                 const bool last = (l == p.n_layers - 1);
+                if (prof) pf_t0 = clock64();
                 mbar_wait(BAR(D_FULL + db), ph_dfull[db]);
                 ph_dfull[db] ^= 1;
                 tc_fence_after();
-                const float* bias = p.bias[l];
-                float araw = 0.f;
-                float my_wc = 0.f;
-                int mycs = -1, mycross = 0;
-                unsigned seg_heads = 0;                             // bit i: row i of this warp starts a new sample
-                if (last) {
-                    my_wc = meta_wc[mb * TC_ROWS + row];
-                    mycs = meta_cs[mb * TC_ROWS + row];
-                    mycross = meta_cross[mb * TC_ROWS + row];
-                    const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
-                    seg_heads = __ballot_sync(0xffffffffu, lane == 0 || prevcs != mycs);
-                }
+                if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
+                const uint32_t bias_l = bias_a + (uint32_t)(l * TC_W) * 4u;
+                const uint32_t acc_addr = tmem_base + (uint32_t)(db * TC_W) + lane_field;
+                // software pipeline over the 8 chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is processed
+                uint32_t v0[32], v1[32];
+                tc_ld32_nowait(acc_addr, v0);
+                if (!last) {
 #pragma unroll 1
-                for (int c = 0; c < TC_W / 32; c++) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + (uint32_t)(db * TC_W + c * 32) + ((uint32_t)(warp * 32) << 16), v);
-                    if (p.dbg & 8) { if (!last && (c & 1)) { fence_proxy_async(); mbar_arrive(BAR(A_FULL + (c >> 1))); } continue; }
-                    float h[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 bb = __ldg((const float4*)(bias + c * 32 + i));
-                        float x0 = __uint_as_float(v[i]) + bb.x, x1 = __uint_as_float(v[i + 1]) + bb.y;
-                        float x2 = __uint_as_float(v[i + 2]) + bb.z, x3 = __uint_as_float(v[i + 3]) + bb.w;
-                        h[i] = fmaxf(x0, x0 * p.slope); h[i + 1] = fmaxf(x1, x1 * p.slope);
-                        h[i + 2] = fmaxf(x2, x2 * p.slope); h[i + 3] = fmaxf(x3, x3 * p.slope);
+                    for (int cp = 0; cp < TC_W / 64; cp++) {
+                        long long q0 = 0;
+                        if (prof) q0 = clock64();
+                        tc_wait_ld(v0);
+                        if (prof) pf_ld += clock64() - q0;
+                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
+                        mid_chunk(2 * cp, v0, bias_l);
+                        if (prof) q0 = clock64();
+                        tc_wait_ld(v1);
+                        if (prof) pf_ld += clock64() - q0;
+                        if (cp + 1 < TC_W / 64) tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 64), v0);
+                        mid_chunk(2 * cp + 1, v1, bias_l);
+                        fence_proxy_async();
+                        mbar_arrive(BAR(A_FULL + cp));
                     }
-                    if (!last) {
-                        // next layer's A operand: activation panel c/2, 16-byte chunks (c&1)*4 .. +3 of this row
-                        const uint32_t rowbase = sbase + OFF_AM + (c >> 1) * PANEL_A + row * 128;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int ch = (c & 1) * 4 + q;
-                            sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
-                                   pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
-                        }
-                        if (c & 1) {
-                            fence_proxy_async();
-                            mbar_arrive(BAR(A_FULL + (c >> 1)));
-                        }
-                    } else if (!(p.dbg & 16)) {
-                        // alpha dot product + K-weighted segmented sums over the rows of each sample (this warp's 32 rows):
-                        // transpose through shared memory (lane = row -> lane = column), then a fully unrolled walk over
-                        // the rows whose segment ends are warp-uniform (seg_heads), all loads issued up front
+                    if (prof) { const long long t1 = clock64(); pf_mid += t1 - pf_t0; pf_t0 = t1; }
+                    tc_fence_before();
+                    mbar_arrive(BAR(D_EMPTY + db));
+                } else {
+                    // last layer: alpha dot product and the K-weighted sums over the rows of each sample.  The chunk is transposed
+                    // through shared memory (lane = row -> lane = column); the walk down the 32 rows is branch-free: segment
+                    // heads / ends are warp-uniform bit masks and the stores are predicated.
+                    const float my_wc = meta_wc[mb * TC_ROWS + row];
+                    const int mycs = meta_cs[mb * TC_ROWS + row];
+                    const int mycross = meta_cross[mb * TC_ROWS + row];
+                    const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
+                    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prevcs != mycs);
+                    const unsigned ends = (heads >> 1) | 0x80000000u;
+                    const unsigned validm = __ballot_sync(0xffffffffu, mycs >= 0);
+                    const unsigned st_plain = ends & validm & ~__ballot_sync(0xffffffffu, mycross != 0);
+                    const unsigned st_atom = ends & validm & __ballot_sync(0xffffffffu, mycross != 0);
+                    const int cs0 = __shfl_sync(0xffffffffu, mycs, 0);
+                    const uint32_t ld_bytes = (uint32_t)p.ldF * 4u;
+                    float araw = 0.f;
+                    auto last_chunk = [&](int c, const uint32_t(&vv)[32]) {
+                        if (p.dbg & 24) return;
+                        float h[32];
+                        activate(vv, bias_l + c * 128, h);
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            const float4 w4 = __ldg((const float4*)(p.wa + c * 32 + i));
+                            const float4 w4 = lds128f(wa_a + c * 128 + i * 4);
                             araw = fmaf(h[i], w4.x, araw); araw = fmaf(h[i + 1], w4.y, araw);
                             araw = fmaf(h[i + 2], w4.z, araw); araw = fmaf(h[i + 3], w4.w, araw);
                         }
@@ -242,57 +345,65 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                         float t[32];
 #pragma unroll
                         for (int i = 0; i < 32; i++) t[i] = ldsf(stg_a + (uint32_t)(i * STG_LD + lane) * 4u);
+                        // compact sample ids are consecutive along the rows: id(row i) = cs0 + (#heads in rows 0..i) - 1
+                        const float* fcol = p.F + (size_t)max(cs0 - 1, -1) * p.ldF + c * 32 + lane;
                         float acc = 0.f;
 #pragma unroll
                         for (int i = 0; i < 32; i++) {
-                            acc += t[i];
-                            const bool seg_end = (i == 31) || ((seg_heads >> (i + 1)) & 1u);
-                            if (seg_end) {                       // warp-uniform
-                                const int ci = __shfl_sync(0xffffffffu, mycs, i);
-                                const int cr = __shfl_sync(0xffffffffu, mycross, i);
-                                if (ci >= 0) {
-                                    float* dst = p.F + (size_t)ci * p.ldF + c * 32 + lane;
-                                    if (cr) atomicAdd(dst, acc); else *dst = acc;
-                                }
-                                acc = 0.f;
-                            }
+                            acc = ((heads >> i) & 1u) ? t[i] : acc + t[i];
+                            ksum_store(fcol, acc, st_plain, st_atom, heads, 1u << i, 0xffffffffu >> (31 - i), ld_bytes);
                         }
+                    };
+#pragma unroll 1
+                    for (int cp = 0; cp < TC_W / 64; cp++) {
+                        tc_wait_ld(v0);
+                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
+                        last_chunk(2 * cp, v0);
+                        tc_wait_ld(v1);
+                        if (cp + 1 < TC_W / 64) tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 64), v0);
+                        last_chunk(2 * cp + 1, v1);
                     }
-                }
-                tc_fence_before();
-                mbar_arrive(BAR(D_EMPTY + db));
-                if (last) {
-                    // sigma: segmented sum of wc * act(raw alpha) over the rows of each sample (within the warp)
+                    if (prof) { const long long t1 = clock64(); pf_last += t1 - pf_t0; pf_t0 = t1; }
+                    tc_fence_before();
+                    mbar_arrive(BAR(D_EMPTY + db));
+                    // sigma: segmented sum of wc * act(raw alpha) over the rows of each sample (a sample has at most K rows)
                     const float a = araw + p.ba[0];
                     const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
                     const float val = act * my_wc;
-                    const bool head = (seg_heads >> lane) & 1u;
                     float sum = val;
                     bool open = true;
-                    for (int dlt = 1; dlt < p.K; dlt++) {         // a sample has at most K rows
+                    for (int dlt = 1; dlt < p.K; dlt++) {
                         const float vj = __shfl_down_sync(0xffffffffu, val, dlt);
                         const int cj = __shfl_down_sync(0xffffffffu, mycs, dlt);
                         open = open && (lane + dlt < 32) && (cj == mycs);
                         if (open) sum += vj;
                     }
-                    if (head && mycs >= 0) {
+                    if (((heads >> lane) & 1u) && mycs >= 0) {
                         if (mycross) atomicAdd(p.sigma + mycs, sum); else p.sigma[mycs] = sum;
                     }
+                    __syncwarp();
                     mbar_arrive(BAR(META_FREE + mb));
+                    if (prof) { const long long t1 = clock64(); pf_sigma += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
         }
+        if (prof && blockIdx.x == 0 && lane == 0)
+            printf("epi warp %d: tiles %u wait %lld [tmem-ld wait in mid %lld] mid(%d layers) %lld last %lld sigma %lld (cycles/tile)\n", warp, tcount,
+                   pf_wait / max(tcount, 1u), pf_ld / max(tcount, 1u), p.n_layers - 1, pf_mid / max(tcount, 1u), pf_last / max(tcount, 1u), pf_sigma / max(tcount, 1u));
     } else if (warp < 8) {
         // =========================================================== GATHER (row = tid - 128) for this CTA's tiles, one ahead
         const int row = tid - 128;
         uint32_t ph_x0empty = 1, ph_meta[2] = {1, 1};
         uint32_t tcount = 0;
+        long long gf_load = 0, gf_wait = 0, gf_write = 0, gf_t0 = 0;
+        const bool prof = (p.dbg & 32) != 0;
         const float* Rm = p.in.camrot;
         const float r00 = Rm[0], r01 = Rm[1], r02 = Rm[2], r10 = Rm[3], r11 = Rm[4], r12 = Rm[5], r20 = Rm[6], r21 = Rm[7], r22 = Rm[8];
         const float cpx = p.in.campos[0], cpy = p.in.campos[1], cpz = p.in.campos[2];
         const uint32_t x0 = sbase + OFF_X0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int mb = tcount & 1;
+            if (prof) gf_t0 = clock64();
             const int64_t j = (int64_t)tile * TC_ROWS + row;
             const bool live = j < T;
             float wcv = 0.f; int csv = -1, crossv = 0;
@@ -333,8 +444,10 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                 e7[3] = dx - vx; e7[4] = dy - vy; e7[5] = dz - vz; e7[6] = dx * vx + dy * vy + dz * vz;
             }
             // the global loads above are in flight while the previous tile still owns the X0 panels
+            if (prof) { const long long t1 = clock64(); gf_load += t1 - gf_t0; gf_t0 = t1; }
             mbar_wait(BAR(X0_EMPTY), ph_x0empty); ph_x0empty ^= 1;
             mbar_wait(BAR(META_FREE + mb), ph_meta[mb]); ph_meta[mb] ^= 1;
+            if (prof) { const long long t1 = clock64(); gf_wait += t1 - gf_t0; gf_t0 = t1; }
             // cols [0,32): embedding
 #pragma unroll
             for (int q = 0; q < 4; q++)
@@ -377,7 +490,10 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
             meta_cross[mb * TC_ROWS + row] = crossv;
             fence_proxy_async();
             mbar_arrive(BAR(X0_FULL));
+            if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
         }
+        if (prof && blockIdx.x == 0 && lane == 0)
+            printf("gather warp %d: tiles %u issue-loads %lld wait-slot %lld expand+write %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u), gf_wait / max(tcount, 1u), gf_write / max(tcount, 1u));
     } else if (warp == 8) {
         // =========================================================== PRODUCER: weight panels through the ring
         if (lane == 0) {
