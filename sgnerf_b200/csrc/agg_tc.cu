@@ -41,14 +41,16 @@ constexpr int OFF_X0 = 0;
 constexpr int OFF_AM = OFF_X0 + X0_PANELS * PANEL_A;            // 81920
 constexpr int OFF_B = OFF_AM + AM_PANELS * PANEL_A;             // 147456
 constexpr int OFF_META = OFF_B + B_STAGES * PANEL_B;            // 212992
-constexpr int META_BYTES = 2 * TC_ROWS * 12;                    // wc (f32), cs (i32), cross (i32), double buffered
+constexpr int META_BYTES = 2 * TC_ROWS * 16;                    // wc (f32), cs (i32), cross (i32), partial alpha (f32); double buffered
 constexpr int OFF_BIAS = OFF_META + META_BYTES;                 // [TC_MAX_LAYERS][256] biases + wa[256]
 constexpr int BIAS_BYTES = (TC_MAX_LAYERS + 1) * TC_W * 4;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
-constexpr int N_BARS = 2 * B_STAGES + 2 + AM_PANELS + 4 + 2;
+constexpr int A_CHUNKS = TC_W / 32;           // activation hand-over granularity: 32 columns = two K-steps
+constexpr int N_BARS = 2 * B_STAGES + 2 + A_CHUNKS + 4 + 2 + 1;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
-static_assert(TC_ROWS * STG_LD * 4 <= AM_PANELS * PANEL_A, "staging must fit in the activation panels");
+constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 12, TC_MMA_WARP = 13, TC_THREADS = 14 * 32;
+static_assert(TC_EPI_WARPS * 32 * STG_LD * 4 <= AM_PANELS * PANEL_A, "staging must fit in the activation panels");
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
@@ -197,7 +199,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
+__global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -207,11 +209,12 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
     float* meta_wc = (float*)(smem + OFF_META);                    // [2][128]
     int32_t* meta_cs = (int32_t*)(smem + OFF_META + 2 * TC_ROWS * 4);
     int32_t* meta_cross = (int32_t*)(smem + OFF_META + 4 * TC_ROWS * 4);
+    float* meta_araw = (float*)(smem + OFF_META + 6 * TC_ROWS * 4);  // [2][128] alpha partial of the upper column half
     const uint32_t bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     // barrier indices
     const int B_FULL = 0, B_EMPTY = B_STAGES, X0_FULL = 2 * B_STAGES, X0_EMPTY = X0_FULL + 1, A_FULL = X0_EMPTY + 1,
-              D_FULL = A_FULL + AM_PANELS, D_EMPTY = D_FULL + 2, META_FREE = D_EMPTY + 2;
+              D_FULL = A_FULL + A_CHUNKS, D_EMPTY = D_FULL + 2, META_FREE = D_EMPTY + 2, ARAW_FULL = META_FREE + 2;
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + OFF_TMEMPTR);
 
     const int T = min(*p.T_ptr, p.T_max);
@@ -220,15 +223,16 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
     if (tid == 0) {
         for (int s = 0; s < B_STAGES; s++) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
         mbar_init(BAR(X0_FULL), 128); mbar_init(BAR(X0_EMPTY), 1);
-        for (int i = 0; i < AM_PANELS; i++) mbar_init(BAR(A_FULL + i), 128);
-        for (int i = 0; i < 2; i++) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); mbar_init(BAR(META_FREE + i), 128); }
+        for (int i = 0; i < A_CHUNKS; i++) mbar_init(BAR(A_FULL + i), 128);
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), TC_EPI_WARPS * 32); mbar_init(BAR(META_FREE + i), TC_EPI_WARPS * 32); }
+        mbar_init(BAR(ARAW_FULL), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < (p.n_layers + 1) * TC_W; i += blockDim.x) {
         const int l = i / TC_W, c = i - l * TC_W;
         ((float*)(smem + OFF_BIAS))[i] = l < p.n_layers ? p.bias[l][c] : p.wa[c];
     }
-    if (warp == 9) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -237,18 +241,21 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp < 4) {
-        // =========================================================== EPILOGUE (row = tid, TMEM lane quadrant = warp)
-        const int row = tid;
+    if (warp < TC_EPI_WARPS) {
+        // =========================================================== EPILOGUE: warp = (column half, TMEM lane quadrant)
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int c0 = half * (A_CHUNKS / 2);                  // this warp's 4 chunks of 32 columns
         uint32_t ph_dfull[2] = {0, 0};
+        uint32_t ph_araw = 0;
         uint32_t lcount = 0;                                   // global layer counter -> accumulator buffer
         uint32_t tcount = 0;
-        long long pf_wait = 0, pf_ld = 0, pf_mid = 0, pf_last = 0, pf_sigma = 0, pf_t0 = 0;
+        long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_sigma = 0, pf_t0 = 0;
         const bool prof = (p.dbg & 32) != 0;
         const uint32_t bias_a = sbase + OFF_BIAS;                              // [n_layers][256] f32, then wa[256]
         const uint32_t wa_a = bias_a + (uint32_t)(p.n_layers * TC_W) * 4u;
         const uint32_t stg_a = sbase + OFF_AM + (uint32_t)(warp * 32 * STG_LD) * 4u;     // this warp's 32 x 33 staging rows (last layer)
-        const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
         const uint32_t act_row = sbase + OFF_AM + row * 128;
         const float slope = p.slope;
 
@@ -265,16 +272,19 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         };
         // hidden layer: bf16 activations into the next layer's A operand (panel c/2, 16-byte chunks (c&1)*4 .. +3 of this row)
         auto mid_chunk = [&](int c, const uint32_t(&vv)[32], uint32_t bias_l) {
-            if (p.dbg & 8) return;
-            float h[32];
-            activate(vv, bias_l + c * 128, h);
-            const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
+            if (!(p.dbg & 8)) {
+                float h[32];
+                activate(vv, bias_l + c * 128, h);
+                const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int ch = (c & 1) * 4 + q;
-                sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
-                       pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                for (int q = 0; q < 4; q++) {
+                    const int ch = (c & 1) * 4 + q;
+                    sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                           pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                }
             }
+            fence_proxy_async();
+            mbar_arrive(BAR(A_FULL + c));
         };
 
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
@@ -288,45 +298,35 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                 tc_fence_after();
                 if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
                 const uint32_t bias_l = bias_a + (uint32_t)(l * TC_W) * 4u;
-                const uint32_t acc_addr = tmem_base + (uint32_t)(db * TC_W) + lane_field;
-                // software pipeline over the 8 chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is processed
+                const uint32_t acc_addr = tmem_base + (uint32_t)(db * TC_W + c0 * 32) + lane_field;
+                // software pipeline over this warp's 4 chunks: the TMEM load of the next chunk is in flight while one is processed
                 uint32_t v0[32], v1[32];
                 tc_ld32_nowait(acc_addr, v0);
                 if (!last) {
 #pragma unroll 1
-                    for (int cp = 0; cp < TC_W / 64; cp++) {
-                        long long q0 = 0;
-                        if (prof) q0 = clock64();
+                    for (int cp = 0; cp < 2; cp++) {
                         tc_wait_ld(v0);
-                        if (prof) pf_ld += clock64() - q0;
                         tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                        mid_chunk(2 * cp, v0, bias_l);
-                        if (prof) q0 = clock64();
+                        mid_chunk(c0 + 2 * cp, v0, bias_l);
                         tc_wait_ld(v1);
-                        if (prof) pf_ld += clock64() - q0;
-                        if (cp + 1 < TC_W / 64) tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 64), v0);
-                        mid_chunk(2 * cp + 1, v1, bias_l);
-                        fence_proxy_async();
-                        mbar_arrive(BAR(A_FULL + cp));
+                        if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
+                        mid_chunk(c0 + 2 * cp + 1, v1, bias_l);
                     }
                     if (prof) { const long long t1 = clock64(); pf_mid += t1 - pf_t0; pf_t0 = t1; }
                     tc_fence_before();
                     mbar_arrive(BAR(D_EMPTY + db));
                 } else {
-                    // last layer: alpha dot product and the K-weighted sums over the rows of each sample.  The chunk is transposed
-                    // through shared memory (lane = row -> lane = column); the walk down the 32 rows is branch-free: segment
-                    // heads / ends are warp-uniform bit masks and the stores are predicated.
+                    // last layer: alpha dot product and the K-weighted sums over the rows of each sample.  A chunk is transposed
+                    // through shared memory (lane = row -> lane = column); rows of one sample are consecutive, so the sums are a walk
+                    // over the warp-uniform list of segments (heads bit mask) with one coalesced 128-byte store per segment.
                     const float my_wc = meta_wc[mb * TC_ROWS + row];
                     const int mycs = meta_cs[mb * TC_ROWS + row];
                     const int mycross = meta_cross[mb * TC_ROWS + row];
                     const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
                     const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prevcs != mycs);
-                    const unsigned ends = (heads >> 1) | 0x80000000u;
                     const unsigned validm = __ballot_sync(0xffffffffu, mycs >= 0);
-                    const unsigned st_plain = ends & validm & ~__ballot_sync(0xffffffffu, mycross != 0);
-                    const unsigned st_atom = ends & validm & __ballot_sync(0xffffffffu, mycross != 0);
+                    const unsigned crossm = __ballot_sync(0xffffffffu, mycross != 0);
                     const int cs0 = __shfl_sync(0xffffffffu, mycs, 0);
-                    const uint32_t ld_bytes = (uint32_t)p.ldF * 4u;
                     float araw = 0.f;
                     auto last_chunk = [&](int c, const uint32_t(&vv)[32]) {
                         if (p.dbg & 24) return;
@@ -342,57 +342,70 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
 #pragma unroll
                         for (int i = 0; i < 32; i++) stsf(stg_a + (uint32_t)(lane * STG_LD + i) * 4u, h[i] * my_wc);
                         __syncwarp();
-                        float t[32];
-#pragma unroll
-                        for (int i = 0; i < 32; i++) t[i] = ldsf(stg_a + (uint32_t)(i * STG_LD + lane) * 4u);
-                        // compact sample ids are consecutive along the rows: id(row i) = cs0 + (#heads in rows 0..i) - 1
-                        const float* fcol = p.F + (size_t)max(cs0 - 1, -1) * p.ldF + c * 32 + lane;
-                        float acc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            acc = ((heads >> i) & 1u) ? t[i] : acc + t[i];
-                            ksum_store(fcol, acc, st_plain, st_atom, heads, 1u << i, 0xffffffffu >> (31 - i), ld_bytes);
+                        // compact sample ids are consecutive along the rows: the k-th segment of the warp is sample cs0 + k
+                        float* frow = p.F + (size_t)max(cs0, 0) * p.ldF + c * 32 + lane;
+                        unsigned m = heads;
+                        int start = 0;
+                        uint32_t rd = stg_a + (uint32_t)lane * 4u;
+                        while (m) {                                               // warp-uniform
+                            m &= m - 1;
+                            const int end = m ? __ffs(m) - 1 : 32;
+                            float acc = 0.f;
+#pragma unroll 4
+                            for (int r = start; r < end; r++, rd += STG_LD * 4) acc += ldsf(rd);
+                            if ((validm >> start) & 1u) {
+                                if ((crossm >> start) & 1u) atomicAdd(frow, acc); else *frow = acc;
+                            }
+                            frow += p.ldF;
+                            start = end;
                         }
                     };
 #pragma unroll 1
-                    for (int cp = 0; cp < TC_W / 64; cp++) {
+                    for (int cp = 0; cp < 2; cp++) {
                         tc_wait_ld(v0);
                         tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                        last_chunk(2 * cp, v0);
+                        last_chunk(c0 + 2 * cp, v0);
                         tc_wait_ld(v1);
-                        if (cp + 1 < TC_W / 64) tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 64), v0);
-                        last_chunk(2 * cp + 1, v1);
+                        if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
+                        last_chunk(c0 + 2 * cp + 1, v1);
                     }
                     if (prof) { const long long t1 = clock64(); pf_last += t1 - pf_t0; pf_t0 = t1; }
                     tc_fence_before();
                     mbar_arrive(BAR(D_EMPTY + db));
-                    // sigma: segmented sum of wc * act(raw alpha) over the rows of each sample (a sample has at most K rows)
-                    const float a = araw + p.ba[0];
-                    const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
-                    const float val = act * my_wc;
-                    float sum = val;
-                    bool open = true;
-                    for (int dlt = 1; dlt < p.K; dlt++) {
-                        const float vj = __shfl_down_sync(0xffffffffu, val, dlt);
-                        const int cj = __shfl_down_sync(0xffffffffu, mycs, dlt);
-                        open = open && (lane + dlt < 32) && (cj == mycs);
-                        if (open) sum += vj;
+                    if (half == 1) {
+                        // hand the alpha partial of columns 128..255 to the warp that owns the same rows in the lower half
+                        meta_araw[mb * TC_ROWS + row] = araw;
+                        mbar_arrive(BAR(ARAW_FULL));
+                    } else {
+                        mbar_wait(BAR(ARAW_FULL), ph_araw); ph_araw ^= 1;
+                        // sigma: segmented sum of wc * act(raw alpha) over the rows of each sample (a sample has at most K rows)
+                        const float a = araw + meta_araw[mb * TC_ROWS + row] + p.ba[0];
+                        const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
+                        const float val = act * my_wc;
+                        float sum = val;
+                        bool open = true;
+                        for (int dlt = 1; dlt < p.K; dlt++) {
+                            const float vj = __shfl_down_sync(0xffffffffu, val, dlt);
+                            const int cj = __shfl_down_sync(0xffffffffu, mycs, dlt);
+                            open = open && (lane + dlt < 32) && (cj == mycs);
+                            if (open) sum += vj;
+                        }
+                        if (((heads >> lane) & 1u) && mycs >= 0) {
+                            if (mycross) atomicAdd(p.sigma + mycs, sum); else p.sigma[mycs] = sum;
+                        }
+                        __syncwarp();
                     }
-                    if (((heads >> lane) & 1u) && mycs >= 0) {
-                        if (mycross) atomicAdd(p.sigma + mycs, sum); else p.sigma[mycs] = sum;
-                    }
-                    __syncwarp();
                     mbar_arrive(BAR(META_FREE + mb));
                     if (prof) { const long long t1 = clock64(); pf_sigma += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
         }
         if (prof && blockIdx.x == 0 && lane == 0)
-            printf("epi warp %d: tiles %u wait %lld [tmem-ld wait in mid %lld] mid(%d layers) %lld last %lld sigma %lld (cycles/tile)\n", warp, tcount,
-                   pf_wait / max(tcount, 1u), pf_ld / max(tcount, 1u), p.n_layers - 1, pf_mid / max(tcount, 1u), pf_last / max(tcount, 1u), pf_sigma / max(tcount, 1u));
-    } else if (warp < 8) {
-        // =========================================================== GATHER (row = tid - 128) for this CTA's tiles, one ahead
-        const int row = tid - 128;
+            printf("epi warp %d: tiles %u wait %lld mid(%d layers) %lld last %lld sigma %lld (cycles/tile)\n", warp, tcount,
+                   pf_wait / max(tcount, 1u), p.n_layers - 1, pf_mid / max(tcount, 1u), pf_last / max(tcount, 1u), pf_sigma / max(tcount, 1u));
+    } else if (warp < TC_PRODUCER_WARP) {
+        // =========================================================== GATHER (one thread per row) for this CTA's tiles, one ahead
+        const int row = tid - TC_GATHER_WARP0 * 32;
         uint32_t ph_x0empty = 1, ph_meta[2] = {1, 1};
         uint32_t tcount = 0;
         long long gf_load = 0, gf_wait = 0, gf_write = 0, gf_t0 = 0;
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         }
         if (prof && blockIdx.x == 0 && lane == 0)
             printf("gather warp %d: tiles %u issue-loads %lld wait-slot %lld expand+write %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u), gf_wait / max(tcount, 1u), gf_write / max(tcount, 1u));
-    } else if (warp == 8) {
+    } else if (warp == TC_PRODUCER_WARP) {
         // =========================================================== PRODUCER: weight panels through the ring
         if (lane == 0) {
             uint32_t ph_empty[B_STAGES];
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         if (lane == 0) {
             uint32_t ph_full[B_STAGES];
             for (int s = 0; s < B_STAGES; s++) ph_full[s] = 0;
-            uint32_t ph_x0full = 0, ph_afull[AM_PANELS] = {0, 0, 0, 0}, ph_dempty[2] = {1, 1};
+            uint32_t ph_x0full = 0, ph_afull = 0, ph_dempty[2] = {1, 1};   // ph_afull: one phase bit per activation chunk
             uint32_t n = 0, lcount = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
                 const int mb = tcount & 1;
@@ -529,25 +542,37 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
                     if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X0_FULL), ph_x0full); ph_x0full ^= 1; }
                     uint32_t acc = 0;
                     for (int kp = 0; kp < np; kp++, n++) {
-                        uint32_t a_addr;
-                        int ksteps = 4;
-                        if (kind == LAYER_FROM_X0) {
-                            a_addr = sbase + OFF_X0 + kp * PANEL_A;
-                            if (kp == 4) ksteps = 2;                      // cols 256..287
-                        } else if (kp < AM_PANELS) {
-                            mbar_wait(BAR(A_FULL + kp), ph_afull[kp]); ph_afull[kp] ^= 1;
-                            a_addr = sbase + OFF_AM + kp * PANEL_A;
-                        } else {                                          // [colour | dir - view | dir.view] K-step of block3.0
-                            a_addr = sbase + OFF_X0 + 4 * PANEL_A + (E7_COL0 + 16 * mb) * 2;
-                            ksteps = 1;
-                        }
                         const int s = n % B_STAGES;
-                        mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1;
-                        tc_fence_after();
                         const uint32_t b_addr = sbase + OFF_B + s * PANEL_B;
-                        for (int k = 0; k < ksteps; k++) {
-                            tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
-                            acc = 1;
+                        if (kind != LAYER_FROM_X0 && kp < AM_PANELS) {
+                            // activation panel kp arrives as two 32-column chunks; each is two K-steps
+                            const uint32_t a_addr = sbase + OFF_AM + kp * PANEL_A;
+                            for (int hc = 0; hc < 2; hc++) {
+                                const int c = 2 * kp + hc;
+                                mbar_wait(BAR(A_FULL + c), (ph_afull >> c) & 1u); ph_afull ^= 1u << c;
+                                if (hc == 0) { mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1; }
+                                tc_fence_after();
+                                for (int k = 2 * hc; k < 2 * hc + 2; k++) {
+                                    tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
+                                    acc = 1;
+                                }
+                            }
+                        } else {
+                            uint32_t a_addr;
+                            int ksteps = 4;
+                            if (kind == LAYER_FROM_X0) {
+                                a_addr = sbase + OFF_X0 + kp * PANEL_A;
+                                if (kp == 4) ksteps = 2;                      // cols 256..287
+                            } else {                                          // [colour | dir - view | dir.view] K-step of block3.0
+                                a_addr = sbase + OFF_X0 + 4 * PANEL_A + (E7_COL0 + 16 * mb) * 2;
+                                ksteps = 1;
+                            }
+                            mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1;
+                            tc_fence_after();
+                            for (int k = 0; k < ksteps; k++) {
+                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
+                                acc = 1;
+                            }
                         }
                         tc_commit(BAR(B_EMPTY + s));
                     }
@@ -558,7 +583,7 @@ __global__ void __launch_bounds__(320, 1) agg_tuple_tc_kernel(const __grid_const
         }
     }
     __syncthreads();
-    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (warp == TC_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 
@@ -978,7 +1003,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         tp.loc_pers = loc_pers; tp.wc = ws.wc;
         tp.F = ws.C0; tp.ldF = d.W; tp.sigma = ws.sigma;
         const int max_tiles = cdiv(Tm, TC_ROWS);
-        launch(agg_tuple_tc_kernel, max_tiles < n_sm ? max_tiles : n_sm, 320, TC_SMEM, st, tp);
+        launch(agg_tuple_tc_kernel, max_tiles < n_sm ? max_tiles : n_sm, TC_THREADS, TC_SMEM, st, tp);
 
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
         cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.C0; cp.ldF = d.W; cp.sigma = ws.sigma;
