@@ -36,21 +36,19 @@ constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
 constexpr int X0_PANELS = 5, AM_PANELS = 4, B_STAGES = 2;
 constexpr int E7_COL0 = 32;               // inside X0 panel 4: cols [32,48) tile parity 0, [48,64) parity 1
 
-constexpr int STG_LD = 33;                // last-layer staging row pitch (floats): conflict-free row writes and column walks
 constexpr int OFF_X0 = 0;
 constexpr int OFF_AM = OFF_X0 + X0_PANELS * PANEL_A;            // 81920
 constexpr int OFF_B = OFF_AM + AM_PANELS * PANEL_A;             // 147456
 constexpr int OFF_META = OFF_B + B_STAGES * PANEL_B;            // 212992
-constexpr int META_BYTES = 2 * TC_ROWS * 16;                    // wc (f32), cs (i32), cross (i32), partial alpha (f32); double buffered
+constexpr int META_BYTES = 2 * TC_ROWS * 16 + 2 * TC_ROWS * 4 + TC_ROWS * 4;   // per row {wc, keep, dest row, -} x2 | raw alpha x2 | sigma terms
 constexpr int OFF_BIAS = OFF_META + META_BYTES;                 // [TC_MAX_LAYERS][256] biases + wa[256]
 constexpr int BIAS_BYTES = (TC_MAX_LAYERS + 1) * TC_W * 4;
 constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
 constexpr int A_CHUNKS = TC_W / 32;           // activation hand-over granularity: 32 columns = two K-steps
-constexpr int N_BARS = 2 * B_STAGES + 2 + A_CHUNKS + 4 + 2 + 1;
+constexpr int N_BARS = 2 * B_STAGES + 2 + A_CHUNKS + 4 + 2;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
 constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 12, TC_MMA_WARP = 13, TC_THREADS = 14 * 32;
-static_assert(TC_EPI_WARPS * 32 * STG_LD * 4 <= AM_PANELS * PANEL_A, "staging must fit in the activation panels");
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
@@ -59,7 +57,8 @@ struct TcParams {
     AggIn in;
     int K, SR;
     const int32_t* T_ptr; int T_max;
-    const int32_t* tuple_src; const int32_t* tuple_start; const int32_t* nvalid; const int32_t* sample_cidx;
+    const int32_t* tuple_src; const int32_t* tuple_start; const int32_t* sample_cidx;
+    int n_tiles_cap;
     const float* loc_pers; const float* wc;
     const uint8_t* wpack;                  // pre-swizzled bf16 weight panels, all layers back to back
     int n_layers;
@@ -68,7 +67,8 @@ struct TcParams {
     const float* bias[TC_MAX_LAYERS];
     const float* wa; const float* ba;
     float slope; int act_super;
-    float* F; int ldF; float* sigma;       // outputs, per compact sample
+    float* F; float* sigma;                // outputs [S_cap + tiles + 1][256] / [..]: per compact sample, then one carry row per tile, then a dummy row
+    int S_cap;
     int dbg;                               // SGN_TC_DEBUG bitmask (profiling experiments only; results invalid when != 0)
 };
 
@@ -141,6 +141,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
 // kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = 256
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_W >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
 
+// last layer, operands swapped (D^T = W H^T): M = 128 features (two halves), N = 128 tuples
+constexpr uint32_t TC_IDESC_T = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
 // byte offset of element (row, col) inside a 128B-swizzled K-major panel set (64 columns per panel)
 __device__ __forceinline__ uint32_t sw_off(int row, int col)
 {
@@ -185,6 +188,8 @@ __device__ __forceinline__ void ksum_store(const float* base, float v, uint32_t 
         "@p st.global.f32 [a], %1;\n\t@q red.global.add.f32 [a], %1;\n\t}"
         ::"l"(base), "f"(v), "r"(st_plain), "r"(st_atom), "r"(heads), "r"(bit), "r"(prefix), "r"(ld_bytes) : "memory");
 }
+__device__ __forceinline__ void st_global_f32(float* addr, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_shared_f32(uint32_t addr, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void st_global_pred(float* addr, float v, uint32_t flag)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(flag) : "memory");
@@ -206,15 +211,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    float* meta_wc = (float*)(smem + OFF_META);                    // [2][128]
-    int32_t* meta_cs = (int32_t*)(smem + OFF_META + 2 * TC_ROWS * 4);
-    int32_t* meta_cross = (int32_t*)(smem + OFF_META + 4 * TC_ROWS * 4);
-    float* meta_araw = (float*)(smem + OFF_META + 6 * TC_ROWS * 4);  // [2][128] alpha partial of the upper column half
+    // per-row metadata of a tile, double buffered: float4 {wc, keep (0 at the first row of a sample, else 1), dest row (int bits), 0}
+    float4* meta = (float4*)(smem + OFF_META);                     // [2][128]
+    float* araw_sh = (float*)(smem + OFF_META + 2 * TC_ROWS * 16); // [2][128] raw alpha, summed over the 8 epilogue warps
+    float* sig_sh = araw_sh + 2 * TC_ROWS;                         // [128] wc * act(alpha) per row
     const uint32_t bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     // barrier indices
     const int B_FULL = 0, B_EMPTY = B_STAGES, X0_FULL = 2 * B_STAGES, X0_EMPTY = X0_FULL + 1, A_FULL = X0_EMPTY + 1,
-              D_FULL = A_FULL + A_CHUNKS, D_EMPTY = D_FULL + 2, META_FREE = D_EMPTY + 2, ARAW_FULL = META_FREE + 2;
+              D_FULL = A_FULL + A_CHUNKS, D_EMPTY = D_FULL + 2, META_FREE = D_EMPTY + 2;
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + OFF_TMEMPTR);
 
     const int T = min(*p.T_ptr, p.T_max);
@@ -225,7 +230,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
         mbar_init(BAR(X0_FULL), 128); mbar_init(BAR(X0_EMPTY), 1);
         for (int i = 0; i < A_CHUNKS; i++) mbar_init(BAR(A_FULL + i), 128);
         for (int i = 0; i < 2; i++) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), TC_EPI_WARPS * 32); mbar_init(BAR(META_FREE + i), TC_EPI_WARPS * 32); }
-        mbar_init(BAR(ARAW_FULL), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < (p.n_layers + 1) * TC_W; i += blockDim.x) {
@@ -245,16 +249,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
         // =========================================================== EPILOGUE: warp = (column half, TMEM lane quadrant)
         const int quad = warp & 3, half = warp >> 2;
         const int row = quad * 32 + lane;
-        const int c0 = half * (A_CHUNKS / 2);                  // this warp's 4 chunks of 32 columns
+        // hidden layers: this warp owns the 32-column chunks half, half+2, half+4, half+6, so the two chunks of an activation
+        // panel are produced side by side by the two halves and the MMA issuer can consume the panels in order
+
         uint32_t ph_dfull[2] = {0, 0};
-        uint32_t ph_araw = 0;
         uint32_t lcount = 0;                                   // global layer counter -> accumulator buffer
         uint32_t tcount = 0;
         long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_sigma = 0, pf_t0 = 0;
         const bool prof = (p.dbg & 32) != 0;
         const uint32_t bias_a = sbase + OFF_BIAS;                              // [n_layers][256] f32, then wa[256]
         const uint32_t wa_a = bias_a + (uint32_t)(p.n_layers * TC_W) * 4u;
-        const uint32_t stg_a = sbase + OFF_AM + (uint32_t)(warp * 32 * STG_LD) * 4u;     // this warp's 32 x 33 staging rows (last layer)
         const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
         const uint32_t act_row = sbase + OFF_AM + row * 128;
         const float slope = p.slope;
@@ -298,100 +302,87 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                 tc_fence_after();
                 if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
                 const uint32_t bias_l = bias_a + (uint32_t)(l * TC_W) * 4u;
-                const uint32_t acc_addr = tmem_base + (uint32_t)(db * TC_W + c0 * 32) + lane_field;
+                const uint32_t acc_addr = tmem_base + (uint32_t)(db * TC_W + half * 32) + lane_field;
                 // software pipeline over this warp's 4 chunks: the TMEM load of the next chunk is in flight while one is processed
                 uint32_t v0[32], v1[32];
-                tc_ld32_nowait(acc_addr, v0);
                 if (!last) {
+                    tc_ld32_nowait(acc_addr, v0);
 #pragma unroll 1
                     for (int cp = 0; cp < 2; cp++) {
                         tc_wait_ld(v0);
-                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                        mid_chunk(c0 + 2 * cp, v0, bias_l);
+                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 128 + 64), v1);
+                        mid_chunk(half + 4 * cp, v0, bias_l);
                         tc_wait_ld(v1);
-                        if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
-                        mid_chunk(c0 + 2 * cp + 1, v1, bias_l);
+                        if (cp == 0) tc_ld32_nowait(acc_addr + 128u, v0);
+                        mid_chunk(half + 4 * cp + 2, v1, bias_l);
                     }
                     if (prof) { const long long t1 = clock64(); pf_mid += t1 - pf_t0; pf_t0 = t1; }
                     tc_fence_before();
                     mbar_arrive(BAR(D_EMPTY + db));
                 } else {
-                    // last layer: alpha dot product and the K-weighted sums over the rows of each sample.  A chunk is transposed
-                    // through shared memory (lane = row -> lane = column); rows of one sample are consecutive, so the sums are a walk
-                    // over the warp-uniform list of segments (heads bit mask) with one coalesced 128-byte store per segment.
-                    const float my_wc = meta_wc[mb * TC_ROWS + row];
-                    const int mycs = meta_cs[mb * TC_ROWS + row];
-                    const int mycross = meta_cross[mb * TC_ROWS + row];
-                    const int prevcs = __shfl_up_sync(0xffffffffu, mycs, 1);
-                    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prevcs != mycs);
-                    const unsigned validm = __ballot_sync(0xffffffffu, mycs >= 0);
-                    const unsigned crossm = __ballot_sync(0xffffffffu, mycross != 0);
-                    const int cs0 = __shfl_sync(0xffffffffu, mycs, 0);
-                    float araw = 0.f;
-                    auto last_chunk = [&](int c, const uint32_t(&vv)[32]) {
+                    // last layer, computed transposed (D^T = W H^T): TMEM lane = output feature, TMEM column = tuple row.  This thread
+                    // owns feature f for all 128 rows of the tile, so the K-weighted sum over the consecutive rows of a sample is a
+                    // sequential, branch-free walk in registers: acc = acc * keep + wc * h, stored to the sample's row of F after every
+                    // tuple (later rows of the same sample overwrite earlier ones; 32 lanes = 32 features = one 128-byte store).
+                    const int f = half * 128 + quad * 32 + lane;
+                    const float bias_f = ldsf(bias_l + f * 4), wa_f = ldsf(wa_a + f * 4);
+                    const uint32_t meta_a = sbase + OFF_META + (uint32_t)(mb * TC_ROWS) * 16u;
+                    const uint32_t araw_a = sbase + OFF_META + 2 * TC_ROWS * 16 + (uint32_t)(mb * TC_ROWS) * 4u;
+                    const uint32_t accT = tmem_base + (uint32_t)(db * TC_W + half * 128) + lane_field;
+                    float* fcol = p.F + f;
+                    float acc = 0.f;
+                    auto last_chunk = [&](int cc, uint32_t(&vv)[32]) {
                         if (p.dbg & 24) return;
-                        float h[32];
-                        activate(vv, bias_l + c * 128, h);
+                        float pa[32];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 w4 = lds128f(wa_a + c * 128 + i * 4);
-                            araw = fmaf(h[i], w4.x, araw); araw = fmaf(h[i + 1], w4.y, araw);
-                            araw = fmaf(h[i + 2], w4.z, araw); araw = fmaf(h[i + 3], w4.w, araw);
+                        for (int i = 0; i < 32; i++) {
+                            const float x = __uint_as_float(vv[i]) + bias_f;
+                            const float h = fmaxf(x, x * slope);
+                            const float4 m = lds128f(meta_a + (uint32_t)(cc * 32 + i) * 16u);          // warp-uniform address
+                            acc = fmaf(acc, m.y, h * m.x);
+                            st_global_f32(fcol + (size_t)(uint32_t)__float_as_int(m.z) * TC_W, acc);
+                            pa[i] = h * wa_f;
                         }
-                        __syncwarp();
+                        // alpha: sum over the 32 features of this warp for each of the 32 rows (transpose-reduce, 31 shuffles),
+                        // lane i ends up with the partial of row cc*32 + i; the 8 warps meet in shared memory
 #pragma unroll
-                        for (int i = 0; i < 32; i++) stsf(stg_a + (uint32_t)(lane * STG_LD + i) * 4u, h[i] * my_wc);
-                        __syncwarp();
-                        // compact sample ids are consecutive along the rows: the k-th segment of the warp is sample cs0 + k
-                        float* frow = p.F + (size_t)max(cs0, 0) * p.ldF + c * 32 + lane;
-                        unsigned m = heads;
-                        int start = 0;
-                        uint32_t rd = stg_a + (uint32_t)lane * 4u;
-                        while (m) {                                               // warp-uniform
-                            m &= m - 1;
-                            const int end = m ? __ffs(m) - 1 : 32;
-                            float acc = 0.f;
-#pragma unroll 4
-                            for (int r = start; r < end; r++, rd += STG_LD * 4) acc += ldsf(rd);
-                            if ((validm >> start) & 1u) {
-                                if ((crossm >> start) & 1u) atomicAdd(frow, acc); else *frow = acc;
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            const bool up = (lane & sft) != 0;
+#pragma unroll
+                            for (int i = 0; i < sft; i++) {
+                                const float send = up ? pa[i] : pa[i + sft];
+                                const float keepv = up ? pa[i + sft] : pa[i];
+                                pa[i] = keepv + __shfl_xor_sync(0xffffffffu, send, sft);
                             }
-                            frow += p.ldF;
-                            start = end;
                         }
+                        red_shared_f32(araw_a + (uint32_t)(cc * 32 + lane) * 4u, pa[0]);
                     };
+                    tc_ld32_nowait(accT, v0);
 #pragma unroll 1
                     for (int cp = 0; cp < 2; cp++) {
                         tc_wait_ld(v0);
-                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                        last_chunk(c0 + 2 * cp, v0);
+                        tc_ld32_nowait(accT + (uint32_t)(cp * 64 + 32), v1);
+                        last_chunk(2 * cp, v0);
                         tc_wait_ld(v1);
-                        if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
-                        last_chunk(c0 + 2 * cp + 1, v1);
+                        if (cp == 0) tc_ld32_nowait(accT + 64u, v0);
+                        last_chunk(2 * cp + 1, v1);
                     }
                     if (prof) { const long long t1 = clock64(); pf_last += t1 - pf_t0; pf_t0 = t1; }
                     tc_fence_before();
                     mbar_arrive(BAR(D_EMPTY + db));
-                    if (half == 1) {
-                        // hand the alpha partial of columns 128..255 to the warp that owns the same rows in the lower half
-                        meta_araw[mb * TC_ROWS + row] = araw;
-                        mbar_arrive(BAR(ARAW_FULL));
-                    } else {
-                        mbar_wait(BAR(ARAW_FULL), ph_araw); ph_araw ^= 1;
-                        // sigma: segmented sum of wc * act(raw alpha) over the rows of each sample (a sample has at most K rows)
-                        const float a = araw + meta_araw[mb * TC_ROWS + row] + p.ba[0];
+                    // sigma = sum over the rows of a sample of wc * act(alpha): the lower four warps take one row each
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (half == 0) {
+                        const int r = quad * 32 + lane;
+                        const float4 m = meta[mb * TC_ROWS + r];
+                        const float a = araw_sh[mb * TC_ROWS + r] + p.ba[0];
                         const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
-                        const float val = act * my_wc;
-                        float sum = val;
-                        bool open = true;
-                        for (int dlt = 1; dlt < p.K; dlt++) {
-                            const float vj = __shfl_down_sync(0xffffffffu, val, dlt);
-                            const int cj = __shfl_down_sync(0xffffffffu, mycs, dlt);
-                            open = open && (lane + dlt < 32) && (cj == mycs);
-                            if (open) sum += vj;
-                        }
-                        if (((heads >> lane) & 1u) && mycs >= 0) {
-                            if (mycross) atomicAdd(p.sigma + mycs, sum); else p.sigma[mycs] = sum;
+                        sig_sh[r] = (p.dbg & 24) ? 0.f : act * m.x;
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (m.y == 0.f) {                        // first row of a sample (within this tile)
+                            float sum = sig_sh[r];
+                            for (int q = r + 1; q < TC_ROWS && meta[mb * TC_ROWS + q].y != 0.f; q++) sum += sig_sh[q];
+                            p.sigma[(uint32_t)__float_as_int(m.z)] = sum;
                         }
                         __syncwarp();
                     }
@@ -419,7 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
             if (prof) gf_t0 = clock64();
             const int64_t j = (int64_t)tile * TC_ROWS + row;
             const bool live = j < T;
-            float wcv = 0.f; int csv = -1, crossv = 0;
+            float wcv = 0.f, keepv = 0.f; int drow = p.S_cap + p.n_tiles_cap;       // dead rows: weight 0, dummy destination row
             float emb[TC_C];
             float dist[6];
             float e7[8];
@@ -435,9 +426,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                 const int64_t r = s / p.SR;
                 const int64_t pt = p.in.pidx[flat];
                 wcv = p.wc[flat];
-                csv = p.sample_cidx[s];
-                const int st = p.tuple_start[s], nv = p.nvalid[s];
-                crossv = (st >> 5) != ((st + nv - 1) >> 5);
+                const int st = p.tuple_start[s];
+                // a sample continued from the previous tile accumulates into this tile's carry row (added back by the colour kernel)
+                drow = st < tile * TC_ROWS ? p.S_cap + tile : p.sample_cidx[s];
+                keepv = (j == st || row == 0) ? 0.f : 1.f;
                 const float4* ep = (const float4*)(p.in.tab.embedding + pt * TC_C);
 #pragma unroll
                 for (int i = 0; i < TC_C / 4; i++) {
@@ -498,9 +490,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                 sts128(x0 + sw_off(row, col), pack_bf16(e7[0], e7[1]), pack_bf16(e7[2], e7[3]), pack_bf16(e7[4], e7[5]), pack_bf16(e7[6], 0.f));
                 sts128(x0 + sw_off(row, col + 8), 0u, 0u, 0u, 0u);
             }
-            meta_wc[mb * TC_ROWS + row] = wcv;
-            meta_cs[mb * TC_ROWS + row] = csv;
-            meta_cross[mb * TC_ROWS + row] = crossv;
+            meta[mb * TC_ROWS + row] = make_float4(wcv, keepv, __int_as_float(drow), 0.f);
+            araw_sh[mb * TC_ROWS + row] = 0.f;
             fence_proxy_async();
             mbar_arrive(BAR(X0_FULL));
             if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
@@ -541,6 +532,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                     const int kind = p.kind[l];
                     if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X0_FULL), ph_x0full); ph_x0full ^= 1; }
                     uint32_t acc = 0;
+                    const bool swapped = (l == p.n_layers - 1);          // last layer: D^T = W H^T (see the epilogue)
+                    auto issue = [&](uint32_t a_addr, uint32_t b_addr, int k0, int k1) {
+                        for (int k = k0; k < k1; k++) {
+                            if (!swapped) {
+                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
+                            } else {
+                                tc_mma(d_tmem, umma_desc(b_addr + k * 32), umma_desc(a_addr + k * 32), TC_IDESC_T, acc);
+                                tc_mma(d_tmem + 128u, umma_desc(b_addr + 128 * 128 + k * 32), umma_desc(a_addr + k * 32), TC_IDESC_T, acc);
+                            }
+                            acc = 1;
+                        }
+                    };
                     for (int kp = 0; kp < np; kp++, n++) {
                         const int s = n % B_STAGES;
                         const uint32_t b_addr = sbase + OFF_B + s * PANEL_B;
@@ -552,10 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                                 mbar_wait(BAR(A_FULL + c), (ph_afull >> c) & 1u); ph_afull ^= 1u << c;
                                 if (hc == 0) { mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1; }
                                 tc_fence_after();
-                                for (int k = 2 * hc; k < 2 * hc + 2; k++) {
-                                    tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
-                                    acc = 1;
-                                }
+                                issue(a_addr, b_addr, 2 * hc, 2 * hc + 2);
                             }
                         } else {
                             uint32_t a_addr;
@@ -569,10 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                             }
                             mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1;
                             tc_fence_after();
-                            for (int k = 0; k < ksteps; k++) {
-                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
-                                acc = 1;
-                            }
+                            issue(a_addr, b_addr, 0, ksteps);
                         }
                         tc_commit(BAR(B_EMPTY + s));
                     }
@@ -604,7 +601,8 @@ constexpr int COFF_RING = COFF_W + C_W_PANELS * C_PANEL;
 constexpr int COFF_ACT = COFF_RING + C_RING * C_PANEL;
 constexpr int COFF_BIAS = COFF_ACT + 2 * C_PANEL;                           // [3][128] hidden biases
 constexpr int COFF_WL = COFF_BIAS + C_MAX_HIDDEN * CW * 4;                  // [3][128] last Linear + its bias [4]
-constexpr int COFF_BAR = COFF_WL + 3 * CW * 4 + 16;
+constexpr int COFF_CARRY = COFF_WL + 3 * CW * 4 + 16;                       // [2][128] carry row of each sample of the tile (-1: none)
+constexpr int COFF_BAR = COFF_CARRY + 2 * TC_ROWS * 4;
 constexpr int C_NBARS = 1 + 2 * C_RING + 2 + 4;
 constexpr int COFF_TMEMPTR = COFF_BAR + C_NBARS * 8;
 constexpr int C_SMEM = COFF_TMEMPTR + 16 + 1024;
@@ -614,8 +612,9 @@ constexpr uint32_t C_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW
 struct ColParams {
     const int32_t* S_ptr; int S_max;
     const int32_t* csample;            // compact sample -> sample
-    const float* F; int ldF;           // [S_v, ldF] K-sums (first 256 columns)
-    const float* sigma;                // [S_v]
+    const float* F;                    // [S_cap + tiles + 1][256] K-sums per compact sample, then the per-tile carry rows
+    const float* sigma;                // same row indexing
+    const int32_t* tuple_start; const int32_t* nvalid; int S_cap;
     const float* raydir; int SR;
     const uint8_t* wpack;              // packed hidden-layer weights, C_PANEL each, layer after layer
     int n_hidden;                      // colour layers followed by an activation (1..3)
@@ -624,6 +623,7 @@ struct ColParams {
     const float* wl; const float* bl;  // last Linear [3,128], [3]
     float slope; int act_super;
     float* decoded;                    // [S,4]
+    int dbg;
 };
 
 __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_constant__ ColParams p)
@@ -714,11 +714,15 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 }
                 tc_fence_before();
                 mbar_arrive(BAR(D_EMPTY + db));
-                if (last && c < Sv) {
+                if (last && c < Sv && !(p.dbg & 256)) {
                     const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
                                 s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
                     const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
-                    ((float4*)p.decoded)[p.csample[c]] = make_float4(p.sigma[c], s0 * m - o, s1 * m - o, s2 * m - o);
+                    const int sidx = p.csample[c];
+                    const int st = p.tuple_start[sidx], t2 = (st + p.nvalid[sidx] - 1) >> 7;
+                    float sg = p.sigma[c];
+                    if ((st >> 7) != t2) sg += p.sigma[p.S_cap + t2];
+                    ((float4*)p.decoded)[sidx] = make_float4(sg, s0 * m - o, s1 * m - o, s2 * m - o);
                 }
             }
         }
@@ -729,8 +733,22 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
         uint32_t ph_empty[C_RING];
         for (int s = 0; s < C_RING; s++) ph_empty[s] = 1;
         uint32_t n = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int32_t* s_carry = (int32_t*)(smem + COFF_CARRY);
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
             const int64_t c0 = (int64_t)tile * TC_ROWS;
+            // samples whose tuples straddle two tiles of the per-neighbour kernel left their second part in that tile's carry row
+            int32_t* carry = s_carry + (tcount & 1) * TC_ROWS;
+            {
+                int cr = -1;
+                if (c0 + lt < Sv) {
+                    const int sidx = p.csample[c0 + lt];
+                    const int st = p.tuple_start[sidx], t2 = (st + p.nvalid[sidx] - 1) >> 7;
+                    if ((st >> 7) != t2) cr = p.S_cap + t2;
+                }
+                carry[lt] = cr;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
                 const int s = n % C_RING;
                 const uint32_t base = sbase + COFF_RING + s * C_PANEL;
@@ -739,7 +757,12 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
 #pragma unroll
                     for (int pass = 0; pass < 16; pass++) {
                         const int r = pass * 8 + rgrp;
-                        f[pass] = (c0 + r < Sv) ? __ldg((const float4*)(p.F + (size_t)(c0 + r) * p.ldF + kp * 64 + sub * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[pass] = (c0 + r < Sv && !(p.dbg & 128)) ? __ldg((const float4*)(p.F + (size_t)(c0 + r) * TC_W + kp * 64 + sub * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int cr = carry[r];
+                        if (cr >= 0) {
+                            const float4 g = __ldg((const float4*)(p.F + (size_t)cr * TC_W + kp * 64 + sub * 4));
+                            f[pass].x += g.x; f[pass].y += g.y; f[pass].z += g.z; f[pass].w += g.w;
+                        }
                     }
                     mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
 #pragma unroll
@@ -754,7 +777,7 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                     float vals[32];
 #pragma unroll
                     for (int i = 0; i < 32; i++) vals[i] = 0.f;
-                    if (c0 + r < Sv) {
+                    if (c0 + r < Sv && !(p.dbg & 64)) {
                         const int64_t ray = p.csample[c0 + r] / p.SR;
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
@@ -848,22 +871,6 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, in
     *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// samples whose tuple rows straddle a 32-row boundary are accumulated with atomics: zero their outputs first
-__global__ void __launch_bounds__(256)
-tc_zero_cross_kernel(const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample, const int32_t* __restrict__ tuple_start,
-                     const int32_t* __restrict__ nvalid, float* __restrict__ F, int ldF, int W, float* __restrict__ sigma)
-{
-    const int lane = lane_id();
-    const int Sv = min(*S_ptr, S_max);
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= Sv) return;
-    const int s = csample[c];
-    const int st = tuple_start[s], nv = nvalid[s];
-    if ((st >> 5) == ((st + nv - 1) >> 5)) return;
-    for (int col = lane; col < W; col += 32) F[c * ldF + col] = 0.f;
-    if (lane == 0) sigma[c] = 0.f;
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-case (every slot valid) workspace
 
@@ -883,7 +890,8 @@ static size_t tc_carve(const AggPlan& P, int64_t Rc, int SR, int K, void* base, 
     ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1); ws->csample = A.take<int32_t>(S + 1);
     ws->loc_pers = A.take<float>(S * 3); ws->weight_n = A.take<float>(T); ws->wc = A.take<float>(T);
-    ws->C0 = A.take<float>(S * d.W); ws->sigma = A.take<float>(S);
+    const size_t ext = S + T / TC_ROWS + 2;          // compact samples + one carry row per tile + dummy row
+    ws->C0 = A.take<float>(ext * d.W); ws->sigma = A.take<float>(ext);
     size_t panels = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
@@ -974,6 +982,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;
     { const char* e = getenv("SGN_TC_DEBUG"); tp.dbg = e ? atoi(e) : 0; }
+    cp.dbg = tp.dbg;
     cp.wpack = ws.cpack; cp.n_hidden = P.n_color_hidden; cp.fv = d.FV;
     cp.wl = weights[P.n_layers - 1]; cp.bl = biases[P.n_layers - 1];
     cp.slope = d.slope; cp.act_super = d.act_super; cp.SR = SR;
@@ -995,18 +1004,19 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         const int32_t* T_ptr = ws.tuple_start + S;
         const int32_t* S_ptr = ws.sample_cidx + S;
         launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
-        launch(tc_zero_cross_kernel, cdiv(Sm, 8), 256, 0, st, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.C0, d.W, d.W, ws.sigma);
 
         tp.in = in;
         tp.T_ptr = T_ptr; tp.T_max = Tm;
-        tp.tuple_src = ws.tuple_src; tp.tuple_start = ws.tuple_start; tp.nvalid = ws.nvalid; tp.sample_cidx = ws.sample_cidx;
+        tp.tuple_src = ws.tuple_src; tp.tuple_start = ws.tuple_start; tp.sample_cidx = ws.sample_cidx;
+        tp.S_cap = Sm; tp.n_tiles_cap = cdiv(Tm, TC_ROWS);
         tp.loc_pers = loc_pers; tp.wc = ws.wc;
-        tp.F = ws.C0; tp.ldF = d.W; tp.sigma = ws.sigma;
+        tp.F = ws.C0; tp.sigma = ws.sigma;
         const int max_tiles = cdiv(Tm, TC_ROWS);
         launch(agg_tuple_tc_kernel, max_tiles < n_sm ? max_tiles : n_sm, TC_THREADS, TC_SMEM, st, tp);
 
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
-        cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.C0; cp.ldF = d.W; cp.sigma = ws.sigma;
+        cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.C0; cp.sigma = ws.sigma;
+        cp.tuple_start = ws.tuple_start; cp.nvalid = ws.nvalid; cp.S_cap = Sm;
         cp.raydir = in.raydir; cp.decoded = dec;
         const int max_ctiles = cdiv(Sm, TC_ROWS);
         launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, 288, C_SMEM, st, cp);
