@@ -149,9 +149,10 @@ int sgn_agg_layer_shape(const SgnAggCfg* cfg, int layer, int* in_features, int* 
 #define SGN_PRECISION_FP32 0   /* fp32 SIMT, strict parity mode                                   */
 #define SGN_PRECISION_BF16 1   /* bf16 tcgen05/TMEM tensor-core tiles, fp32 accumulate            */
 
-/* save_for_backward != 0 keeps the per-layer activations in the workspace for sgn_agg_backward. */
-int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t R, int SR, int K, int precision, int save_for_backward,
-                            size_t* bytes);
+/* save_for_backward != 0 keeps the per-layer activations in the workspace for sgn_agg_backward.
+ * N = number of points in the tables (the bf16 path keeps one 448-byte operand row per point in the workspace). */
+int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t N, int64_t R, int SR, int K, int precision,
+                            int save_for_backward, size_t* bytes);
 
 /*   pidx [R,SR,K], loc_w [R,SR,3] from sgn_query; raydir [R,3]; campos [3]; camrotc2w [3,3] row-major.
  *   decoded [R,SR,4] (sigma,r,g,b; zero where !ray_valid), ray_valid uint8 [R,SR],

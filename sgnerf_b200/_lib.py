@@ -53,7 +53,7 @@ SIGNATURES = {
     "sgn_gather_rows": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void]),
     "sgn_agg_num_layers": (c_int, [C.POINTER(SgnAggCfg)]),
     "sgn_agg_layer_shape": (c_int, [C.POINTER(SgnAggCfg), c_int, C.POINTER(c_int), C.POINTER(c_int)]),
-    "sgn_agg_workspace_bytes": (c_int, [C.POINTER(SgnAggCfg), c_i64, c_int, c_int, c_int, c_int, C.POINTER(c_size)]),
+    "sgn_agg_workspace_bytes": (c_int, [C.POINTER(SgnAggCfg), c_i64, c_i64, c_int, c_int, c_int, c_int, C.POINTER(c_size)]),
     "sgn_agg_forward": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                 c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
                                 c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void]),

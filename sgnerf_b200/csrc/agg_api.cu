@@ -1,4 +1,6 @@
 // agg_api.cu -- C-ABI entry points of the aggregator; dispatch on precision.
+#include <stdlib.h>
+
 #include "agg_common.cuh"
 
 using namespace sgn;
@@ -12,7 +14,14 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
                           const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                           int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
                           float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, cudaStream_t st);
-int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, size_t* bytes);
+int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes);
+// first-generation tensor-core kernel, selected with SGN_TC_V=1 (A/B runs only)
+int sgn_agg_tc_v1_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, size_t* bytes);
+int sgn_agg_tc_v1_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                          int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
+                          void* workspace, size_t workspace_bytes, cudaStream_t st);
+static bool tc_use_v1() { const char* e = getenv("SGN_TC_V"); return e && e[0] == '1'; }
 int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                        const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                        int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
@@ -27,7 +36,7 @@ static int check_common(const SgnAggCfg* cfg, AggPlan* P, int64_t R, int SR, int
     return SGN_OK;
 }
 
-extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t R, int SR, int K, int precision, int save_for_backward, size_t* bytes)
+extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t N, int64_t R, int SR, int K, int precision, int save_for_backward, size_t* bytes)
 {
     AggPlan P;
     int rc = check_common(cfg, &P, R, SR, K);
@@ -36,7 +45,15 @@ extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t R, int SR, 
     if (precision == SGN_PRECISION_FP32) return sgn_agg_fp32_workspace_bytes(P, R, SR, K, save_for_backward, bytes);
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
     SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
-    return sgn_agg_tc_workspace_bytes(P, R, SR, K, bytes);
+    SGN_CHECK_ARG(N >= 0, "sgn_agg_workspace_bytes: bad N");
+    if (tc_use_v1()) {
+        size_t b1 = 0, b2 = 0;
+        if ((rc = sgn_agg_tc_v1_workspace_bytes(P, R, SR, K, &b1))) return rc;
+        if ((rc = sgn_agg_tc_workspace_bytes(P, N, R, SR, K, &b2))) return rc;
+        *bytes = b1 > b2 ? b1 : b2;
+        return SGN_OK;
+    }
+    return sgn_agg_tc_workspace_bytes(P, N, R, SR, K, bytes);
 }
 
 extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
@@ -56,6 +73,9 @@ extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights
                                     ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
     SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
+    if (tc_use_v1())
+        return sgn_agg_tc_v1_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
+                                     weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
     return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
                               weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -1,65 +1,71 @@
-// agg_tc.cu -- bf16 tensor-core aggregator forward: ONE fused persistent kernel for
-//   gather + positional encoding -> per-neighbour MLP (block1 / block3) -> alpha -> K-weighted sums,
-// built on tcgen05.mma (accumulators in TMEM), bulk-TMA weight streaming and mbarrier pipelines (sm_100a).
+// agg_tc.cu -- bf16 tensor-core aggregator forward (sm_100a): tcgen05.mma with accumulators in TMEM, bulk-TMA weight
+// streaming, mbarrier pipelines.  Two fused persistent kernels:
+//   agg_tuple_tc_kernel : gather -> per-neighbour MLP (block1 / block3) -> alpha -> K-weighted sums per sample
+//   agg_color_tc_kernel : per-sample colour MLP -> sigmoid -> (sigma, r, g, b)
 //
-// Reference: PointAggregator.viewmlp (models/aggregators/point_aggregators.py:561-786) on the canonical
-// non-semantic branch; the per-sample colour MLP that follows runs as separate launches (see bottom).
+// Reference: PointAggregator.viewmlp (models/aggregators/point_aggregators.py:561-786) on the canonical non-semantic branch.
 //
-// Tile = 128 valid (sample, neighbour) tuples (rows), compacted in sample order.  Per CTA (1 per SM, persistent):
+// Tile = the valid (sample, neighbour) tuples of consecutive samples, at most 128 rows; tiles are sample aligned (a sample's
+// rows never straddle two tiles): tile t owns the samples whose first tuple index lies in [t*TW, (t+1)*TW), TW = 128-(K-1).
 //
-//   warps 0-3  epilogue : TMEM -> registers (tcgen05.ld) -> +bias, LeakyReLU -> bf16 -> next layer's A operand in
-//                         shared memory (128B-swizzled K-major panels); last layer: alpha dot product and the
-//                         K-weighted segmented sums over the rows of each sample -> F[S,256], sigma[S]
-//   warps 4-7  gather   : for the NEXT tile, one thread per row: point tables -> [emb | PE(emb) | PE(dists)] (bf16)
-//                         straight into the swizzled X0 operand panels, plus [colour | dir-view | dir.view]
-//   warp  8    producer : cp.async.bulk (TMA, UBLKCP) of pre-swizzled 32 KB weight panels into a 2-stage ring
-//   warp  9    MMA      : one thread issues tcgen05.mma 128x256x16 (bf16 in, fp32 accumulate in TMEM); two
-//                         256-column accumulators alternate per layer so layer l+1's MMAs on K-panel p start as soon
-//                         as the epilogue of layer l has written activation panel p
-//
-// Shared memory (bytes): X0 5 x 16 KB | activations 4 x 16 KB (aliased by the K-sum staging) | weight ring 2 x 32 KB |
-// row metadata | mbarriers  = ~211 KB.  TMEM: 512 columns (2 accumulators of 128 lanes x 256 fp32 columns).
+// Per CTA (one per SM, persistent) two tile SLOTS ping-pong: while the epilogue warps turn the accumulator of one slot into
+// the next layer's operand, the tensor pipe runs the other slot's MMAs.
+//   warps 0-7  epilogue : TMEM -> registers (tcgen05.ld) -> +bias, LeakyReLU -> bf16 -> written IN PLACE over the slot's A
+//                         panels (128B-swizzled, K-major) as the next layer's operand.  Last layer: also the alpha dot
+//                         product, then the selection matrix Sel[sample slot][row] = w*conf (bf16) next to the activations.
+//   warps 8-11 gather   : one thread per row: cp.async of the point's precomputed bf16 row [emb | PE(emb)] (448 B) into the
+//                         swizzled panels, PE(dists) and [colour | dir-view | dir.view] computed per tuple
+//   warp  12   producer : cp.async.bulk (TMA) of pre-swizzled 32 KB weight panels into a 2-stage ring
+//   warp  13   MMA      : one thread issues tcgen05.mma 128x256x16 per K-step; after the last layer one more small MMA,
+//                         F^T[feature][sample slot] = H^T (MN-major view of the same activation panels) x Sel^T,
+//                         does the K-weighted sum over the rows of every sample on the tensor core
+// Shared memory: 2 slots x 5 panels x 16 KB | weight ring 2 x 32 KB | 1.5 KB row scratch | mbarriers  (~226 KB).
+// TMEM: 512 columns = one 128 x 256 fp32 accumulator per slot.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "agg_kernels.cuh"
+#include "tc_ptx.cuh"
 
 namespace sgn {
 
 constexpr int TC_ROWS = 128;
 constexpr int TC_W = 256;                 // layer width == accumulator columns
 constexpr int TC_C = 32, TC_F = 3, TC_FD = 5;
-constexpr int TC_K0 = TC_C * (1 + 2 * TC_F) + 2 * TC_FD * 6;   // 284
+constexpr int TC_PT_COLS = TC_C * (1 + 2 * TC_F);              // 224 per-point columns: emb | PE(emb)
+constexpr int TC_PT_BYTES = TC_PT_COLS * 2;                    // 448
+constexpr int TC_K0 = TC_PT_COLS + 2 * TC_FD * 6;              // 284
 constexpr int TC_MAX_LAYERS = 6;
-constexpr int PANEL_A = TC_ROWS * 128;    // 16 KB: 128 rows x 64 bf16
+constexpr int PANEL_A = TC_PANEL_BYTES;   // 16 KB: 128 rows x 64 bf16
 constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
-constexpr int X0_PANELS = 5, AM_PANELS = 4, B_STAGES = 2;
-constexpr int E7_COL0 = 32;               // inside X0 panel 4: cols [32,48) tile parity 0, [48,64) parity 1
+constexpr int SLOT_PANELS = 5, SLOT_BYTES = SLOT_PANELS * PANEL_A, B_STAGES = 2;
+constexpr int E7_COL0 = 32;               // inside panel 4: cols [32,48) hold [colour | dir-view | dir.view | 0]
+constexpr int KS_SLOTS = 64;              // sample slots per K-sum pass (Sel^T = 2 K-panels x 64 x 128 B = panel 4)
 
-constexpr int OFF_X0 = 0;
-constexpr int OFF_AM = OFF_X0 + X0_PANELS * PANEL_A;            // 81920
-constexpr int OFF_B = OFF_AM + AM_PANELS * PANEL_A;             // 147456
-constexpr int OFF_META = OFF_B + B_STAGES * PANEL_B;            // 212992
-constexpr int META_BYTES = 2 * TC_ROWS * 16 + 2 * TC_ROWS * 4 + TC_ROWS * 4;   // per row {wc, keep, dest row, -} x2 | raw alpha x2 | sigma terms
-constexpr int OFF_BIAS = OFF_META + META_BYTES;                 // [TC_MAX_LAYERS][256] biases + wa[256]
-constexpr int BIAS_BYTES = (TC_MAX_LAYERS + 1) * TC_W * 4;
-constexpr int OFF_BAR = OFF_BIAS + BIAS_BYTES;
-constexpr int A_CHUNKS = TC_W / 32;           // activation hand-over granularity: 32 columns = two K-steps
-constexpr int N_BARS = 2 * B_STAGES + 2 + A_CHUNKS + 4 + 2;
+constexpr int OFF_SLOT0 = 0;
+constexpr int OFF_WRING = 2 * SLOT_BYTES;                       // 163840
+constexpr int OFF_ARAW = OFF_WRING + B_STAGES * PANEL_B;        // 229376: [128] alpha partial of the upper column half
+constexpr int OFF_SIG = OFF_ARAW + TC_ROWS * 4;                 // [128] w*conf*act(alpha) per row
+constexpr int OFF_SLOTID = OFF_SIG + TC_ROWS * 4;               // [128] sample slot of the row (-1: dead row)
+constexpr int OFF_BAR = OFF_SLOTID + TC_ROWS * 4;
+constexpr int N_BARS = 2 * B_STAGES + 8;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
 constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 12, TC_MMA_WARP = 13, TC_THREADS = 14 * 32;
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
+constexpr uint32_t IDESC_LAYER = tc_idesc(TC_ROWS, TC_W);
+constexpr uint32_t IDESC_KSUM = tc_idesc(128, KS_SLOTS, 1);    // A = H^T read MN-major from the activation panels
 
 struct TcParams {
     AggIn in;
     int K, SR;
-    const int32_t* T_ptr; int T_max;
-    const int32_t* tuple_src; const int32_t* tuple_start; const int32_t* sample_cidx;
-    int n_tiles_cap;
+    const int32_t* ntiles_ptr; int ntiles_cap;
+    const int2* tile_tab;                  // [ntiles + 1] {first tuple, first compact sample} of every tile, then the totals
+    const int32_t* tuple_src; const int32_t* sample_cidx;
     const float* loc_pers; const float* wc;
+    const uint8_t* ptab;                   // [N][224] bf16 per-point rows
     const uint8_t* wpack;                  // pre-swizzled bf16 weight panels, all layers back to back
     int n_layers;
     int kind[TC_MAX_LAYERS];
@@ -67,141 +73,22 @@ struct TcParams {
     const float* bias[TC_MAX_LAYERS];
     const float* wa; const float* ba;
     float slope; int act_super;
-    float* F; float* sigma;                // outputs [S_cap + tiles + 1][256] / [..]: per compact sample, then one carry row per tile, then a dummy row
-    int S_cap;
-    int dbg;                               // SGN_TC_DEBUG bitmask (profiling experiments only; results invalid when != 0)
+    float* F; float* sigma;                // outputs per compact sample: [S][256], [S]
+    int dbg;                               // SGN_TC_DEBUG bitmask (timing experiments only; results invalid when != 0)
 };
 
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
-// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint expires) instead of
-// spinning in the issue slots of the epilogue / gather warps that share its scheduler
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+// A operand read MN-major (M = 64-element atoms 16 KB apart (LBO), K = 8-row groups 1 KB apart (SBO)), 128-byte swizzle
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr)
 {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-    } while (!ok);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(PANEL_A >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-}
-// the wait names the destination registers as in/out operands so no use of them can be scheduled above it
-__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
-                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
-                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
-                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-                 :: "memory");
-}
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO), descriptor version 1 (Blackwell)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16, A = B = bf16 (K-major), D = f32, M = 128, N = 256
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_W >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
-
-// last layer, operands swapped (D^T = W H^T): M = 128 features (two halves), N = 128 tuples
-constexpr uint32_t TC_IDESC_T = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-// byte offset of element (row, col) inside a 128B-swizzled K-major panel set (64 columns per panel)
-__device__ __forceinline__ uint32_t sw_off(int row, int col)
-{
-    return (uint32_t)((col >> 6) * PANEL_A + row * 128 + ((((col >> 3) & 7) ^ (row & 7)) << 4) + (col & 7) * 2);
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b)
-{
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void stsf(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ float ldsf(uint32_t addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ int ldsi(uint32_t addr)
-{
-    int v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr)
-{
-    float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-// One row of the K-sum walk, as a single asm so that none of its (chunk-invariant) bit tests can be hoisted into registers:
-// row address = base + popc(heads & prefix) * ld_bytes; plain store if (st_plain & bit), reduction if (st_atom & bit).
-__device__ __forceinline__ void ksum_store(const float* base, float v, uint32_t st_plain, uint32_t st_atom, uint32_t heads, uint32_t bit,
-                                           uint32_t prefix, uint32_t ld_bytes)
-{
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b32 t, n;\n\t.reg .b64 off, a;\n\t"
-        "and.b32 t, %2, %5;\n\tsetp.ne.u32 p, t, 0;\n\t"
-        "and.b32 t, %3, %5;\n\tsetp.ne.u32 q, t, 0;\n\t"
-        "and.b32 n, %4, %6;\n\tpopc.b32 n, n;\n\t"
-        "mul.wide.u32 off, n, %7;\n\tadd.s64 a, %0, off;\n\t"
-        "@p st.global.f32 [a], %1;\n\t@q red.global.add.f32 [a], %1;\n\t}"
-        ::"l"(base), "f"(v), "r"(st_plain), "r"(st_atom), "r"(heads), "r"(bit), "r"(prefix), "r"(ld_bytes) : "memory");
-}
-__device__ __forceinline__ void st_global_f32(float* addr, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ void red_shared_f32(uint32_t addr, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ void st_global_pred(float* addr, float v, uint32_t flag)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(flag) : "memory");
-}
-__device__ __forceinline__ void red_global_pred(float* addr, float v, uint32_t flag)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(v), "r"(flag) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
@@ -211,30 +98,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // per-row metadata of a tile, double buffered: float4 {wc, keep (0 at the first row of a sample, else 1), dest row (int bits), 0}
-    float4* meta = (float4*)(smem + OFF_META);                     // [2][128]
-    float* araw_sh = (float*)(smem + OFF_META + 2 * TC_ROWS * 16); // [2][128] raw alpha, summed over the 8 epilogue warps
-    float* sig_sh = araw_sh + 2 * TC_ROWS;                         // [128] wc * act(alpha) per row
+    float* araw_sh = (float*)(smem + OFF_ARAW);
+    float* sig_sh = (float*)(smem + OFF_SIG);
+    int32_t* slot_sh = (int32_t*)(smem + OFF_SLOTID);
     const uint32_t bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    // barrier indices
-    const int B_FULL = 0, B_EMPTY = B_STAGES, X0_FULL = 2 * B_STAGES, X0_EMPTY = X0_FULL + 1, A_FULL = X0_EMPTY + 1,
-              D_FULL = A_FULL + A_CHUNKS, D_EMPTY = D_FULL + 2, META_FREE = D_EMPTY + 2;
+    const int W_FULL = 0, W_EMPTY = B_STAGES, X_FULL = 2 * B_STAGES, BUF_FREE = X_FULL + 2, D_FULL = BUF_FREE + 2, A_READY = D_FULL + 2;
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + OFF_TMEMPTR);
 
-    const int T = min(*p.T_ptr, p.T_max);
-    const int ntiles = (T + TC_ROWS - 1) / TC_ROWS;
+    const int ntiles = min(*p.ntiles_ptr, p.ntiles_cap);
+    const int npairs = (ntiles + 1) >> 1;
 
     if (tid == 0) {
-        for (int s = 0; s < B_STAGES; s++) { mbar_init(BAR(B_FULL + s), 1); mbar_init(BAR(B_EMPTY + s), 1); }
-        mbar_init(BAR(X0_FULL), 128); mbar_init(BAR(X0_EMPTY), 1);
-        for (int i = 0; i < A_CHUNKS; i++) mbar_init(BAR(A_FULL + i), 128);
-        for (int i = 0; i < 2; i++) { mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), TC_EPI_WARPS * 32); mbar_init(BAR(META_FREE + i), TC_EPI_WARPS * 32); }
+        for (int s = 0; s < B_STAGES; s++) { mbar_init(BAR(W_FULL + s), 1); mbar_init(BAR(W_EMPTY + s), 1); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(BAR(X_FULL + s), 128); mbar_init(BAR(BUF_FREE + s), 1);
+            mbar_init(BAR(D_FULL + s), 1); mbar_init(BAR(A_READY + s), TC_EPI_WARPS * 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < (p.n_layers + 1) * TC_W; i += blockDim.x) {
-        const int l = i / TC_W, c = i - l * TC_W;
-        ((float*)(smem + OFF_BIAS))[i] = l < p.n_layers ? p.bias[l][c] : p.wa[c];
     }
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
@@ -246,273 +127,276 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp < TC_EPI_WARPS) {
-        // =========================================================== EPILOGUE: warp = (column half, TMEM lane quadrant)
-        const int quad = warp & 3, half = warp >> 2;
+        // =========================================================== EPILOGUE: warp = (column half h2, TMEM lane quadrant)
+        const int quad = warp & 3, h2 = warp >> 2;
         const int row = quad * 32 + lane;
-        // hidden layers: this warp owns the 32-column chunks half, half+2, half+4, half+6, so the two chunks of an activation
-        // panel are produced side by side by the two halves and the MMA issuer can consume the panels in order
-
-        uint32_t ph_dfull[2] = {0, 0};
-        uint32_t lcount = 0;                                   // global layer counter -> accumulator buffer
-        uint32_t tcount = 0;
-        long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_sigma = 0, pf_t0 = 0;
-        const bool prof = (p.dbg & 32) != 0;
-        const uint32_t bias_a = sbase + OFF_BIAS;                              // [n_layers][256] f32, then wa[256]
-        const uint32_t wa_a = bias_a + (uint32_t)(p.n_layers * TC_W) * 4u;
+        const int et = tid;                                      // 0..255
+        uint32_t ph_d[2] = {0, 0};
         const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
-        const uint32_t act_row = sbase + OFF_AM + row * 128;
         const float slope = p.slope;
+        const float ba = p.ba[0];
+        long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_drain = 0, pf_t0 = 0;
+        const bool prof = (p.dbg & 32) != 0;
+        uint32_t tcount = 0;
 
-        // bias + LeakyReLU on one 32-column chunk
-        auto activate = [&](const uint32_t(&vv)[32], uint32_t bias_chunk, float(&h)[32]) {
+        for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
+            bool have[2]; int nslots[2], c0[2], slr[2]; float wcr[2];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 bb = lds128f(bias_chunk + i * 4);
-                const float x0 = __uint_as_float(vv[i]) + bb.x, x1 = __uint_as_float(vv[i + 1]) + bb.y;
-                const float x2 = __uint_as_float(vv[i + 2]) + bb.z, x3 = __uint_as_float(vv[i + 3]) + bb.w;
-                h[i] = fmaxf(x0, x0 * slope); h[i + 1] = fmaxf(x1, x1 * slope);
-                h[i + 2] = fmaxf(x2, x2 * slope); h[i + 3] = fmaxf(x3, x3 * slope);
-            }
-        };
-        // hidden layer: bf16 activations into the next layer's A operand (panel c/2, 16-byte chunks (c&1)*4 .. +3 of this row)
-        auto mid_chunk = [&](int c, const uint32_t(&vv)[32], uint32_t bias_l) {
-            if (!(p.dbg & 8)) {
-                float h[32];
-                activate(vv, bias_l + c * 128, h);
-                const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int ch = (c & 1) * 4 + q;
-                    sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
-                           pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+            for (int s = 0; s < 2; s++) {
+                const int tile = 2 * pc + s;
+                have[s] = tile < ntiles;
+                nslots[s] = 0; c0[s] = 0; slr[s] = -1; wcr[s] = 0.f;
+                if (have[s]) {
+                    const int2 a = p.tile_tab[tile], b = p.tile_tab[tile + 1];
+                    c0[s] = a.y; nslots[s] = b.y - a.y;
+                    if (row < b.x - a.x) {
+                        const int flat = p.tuple_src[a.x + row];
+                        wcr[s] = p.wc[flat];
+                        slr[s] = p.sample_cidx[flat / p.K] - a.y;
+                    }
+                    tcount++;
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(BAR(A_FULL + c));
-        };
-
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-            const int mb = tcount & 1;
-            for (int l = 0; l < p.n_layers; l++, lcount++) {
-                const int db = lcount & 1;
+            for (int l = 0; l < p.n_layers; l++) {
                 const bool last = (l == p.n_layers - 1);
-                if (prof) pf_t0 = clock64();
-                mbar_wait(BAR(D_FULL + db), ph_dfull[db]);
-                ph_dfull[db] ^= 1;
-                tc_fence_after();
-                if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
-                const uint32_t bias_l = bias_a + (uint32_t)(l * TC_W) * 4u;
-                const uint32_t acc_addr = tmem_base + (uint32_t)(db * TC_W + half * 32) + lane_field;
-                // software pipeline over this warp's 4 chunks: the TMEM load of the next chunk is in flight while one is processed
-                uint32_t v0[32], v1[32];
-                if (!last) {
+                const float* bias_l = p.bias[l] + h2 * 128;
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    if (!have[s]) continue;
+                    if (prof) pf_t0 = clock64();
+                    mbar_wait(BAR(D_FULL + s), ph_d[s]); ph_d[s] ^= 1;
+                    tc_fence_after();
+                    if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
+                    const uint32_t acc_addr = tmem_base + (uint32_t)(s * TC_W + h2 * 128) + lane_field;
+                    const uint32_t act_row = sbase + OFF_SLOT0 + s * SLOT_BYTES + (h2 * 2) * PANEL_A + row * 128;
+                    float araw = 0.f;
+                    // one 32-column chunk: bias + LeakyReLU (+ alpha partial) -> bf16 -> this row's 64 bytes of panel h2*2 + c/2
+                    auto chunk = [&](int c, const uint32_t(&vv)[32]) {
+                        if (p.dbg & 8) return;
+                        float h[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 bb = __ldg((const float4*)(bias_l + c * 32 + i));
+                            const float x0 = __uint_as_float(vv[i]) + bb.x, x1 = __uint_as_float(vv[i + 1]) + bb.y;
+                            const float x2 = __uint_as_float(vv[i + 2]) + bb.z, x3 = __uint_as_float(vv[i + 3]) + bb.w;
+                            h[i] = fmaxf(x0, x0 * slope); h[i + 1] = fmaxf(x1, x1 * slope);
+                            h[i + 2] = fmaxf(x2, x2 * slope); h[i + 3] = fmaxf(x3, x3 * slope);
+                        }
+                        if (last) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 w4 = __ldg((const float4*)(p.wa + h2 * 128 + c * 32 + i));
+                                araw = fmaf(h[i], w4.x, araw); araw = fmaf(h[i + 1], w4.y, araw);
+                                araw = fmaf(h[i + 2], w4.z, araw); araw = fmaf(h[i + 3], w4.w, araw);
+                            }
+                        }
+                        const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int ch = (c & 1) * 4 + q;
+                            sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                                   pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                        }
+                    };
+                    uint32_t v0[32], v1[32];
                     tc_ld32_nowait(acc_addr, v0);
 #pragma unroll 1
                     for (int cp = 0; cp < 2; cp++) {
                         tc_wait_ld(v0);
-                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 128 + 64), v1);
-                        mid_chunk(half + 4 * cp, v0, bias_l);
+                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
+                        chunk(2 * cp, v0);
                         tc_wait_ld(v1);
-                        if (cp == 0) tc_ld32_nowait(acc_addr + 128u, v0);
-                        mid_chunk(half + 4 * cp + 2, v1, bias_l);
+                        if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
+                        chunk(2 * cp + 1, v1);
                     }
-                    if (prof) { const long long t1 = clock64(); pf_mid += t1 - pf_t0; pf_t0 = t1; }
+                    if (!last) {
+                        tc_fence_before();
+                        fence_proxy_async();
+                        mbar_arrive(BAR(A_READY + s));
+                        if (prof) { const long long t1 = clock64(); pf_mid += t1 - pf_t0; pf_t0 = t1; }
+                        continue;
+                    }
+                    // ---- last layer: H is in the panels; alpha, sigma terms and the selection matrix of K-sum pass 0
+                    const uint32_t sel_base = sbase + OFF_SLOT0 + s * SLOT_BYTES + 4 * PANEL_A;
+                    if (h2 == 1) araw_sh[row] = araw;
+                    {
+                        const uint32_t z = sel_base + et * 64;
+                        sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
+                    }
+                    epi_bar();
+                    if (h2 == 0) {
+                        const float a = araw + araw_sh[row] + ba;
+                        const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
+                        sig_sh[row] = (p.dbg & 24) ? 0.f : act * wcr[s];
+                        slot_sh[row] = slr[s];
+                        if (slr[s] >= 0 && slr[s] < KS_SLOTS) {
+                            const int n = slr[s];
+                            const __nv_bfloat16 wb = __float2bfloat16_rn(wcr[s]);
+                            sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + n * 128 + ((((row & 63) >> 3) ^ (n & 7)) << 4) + (row & 7) * 2,
+                                  *reinterpret_cast<const uint16_t*>(&wb));
+                        }
+                    }
+                    epi_bar();
                     tc_fence_before();
-                    mbar_arrive(BAR(D_EMPTY + db));
-                } else {
-                    // last layer, computed transposed (D^T = W H^T): TMEM lane = output feature, TMEM column = tuple row.  This thread
-                    // owns feature f for all 128 rows of the tile, so the K-weighted sum over the consecutive rows of a sample is a
-                    // sequential, branch-free walk in registers: acc = acc * keep + wc * h, stored to the sample's row of F after every
-                    // tuple (later rows of the same sample overwrite earlier ones; 32 lanes = 32 features = one 128-byte store).
-                    const int f = half * 128 + quad * 32 + lane;
-                    const float bias_f = ldsf(bias_l + f * 4), wa_f = ldsf(wa_a + f * 4);
-                    const uint32_t meta_a = sbase + OFF_META + (uint32_t)(mb * TC_ROWS) * 16u;
-                    const uint32_t araw_a = sbase + OFF_META + 2 * TC_ROWS * 16 + (uint32_t)(mb * TC_ROWS) * 4u;
-                    const uint32_t accT = tmem_base + (uint32_t)(db * TC_W + half * 128) + lane_field;
-                    float* fcol = p.F + f;
-                    float acc = 0.f;
-                    auto last_chunk = [&](int cc, uint32_t(&vv)[32]) {
-                        if (p.dbg & 24) return;
-                        float pa[32];
-#pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            const float x = __uint_as_float(vv[i]) + bias_f;
-                            const float h = fmaxf(x, x * slope);
-                            const float4 m = lds128f(meta_a + (uint32_t)(cc * 32 + i) * 16u);          // warp-uniform address
-                            acc = fmaf(acc, m.y, h * m.x);
-                            st_global_f32(fcol + (size_t)(uint32_t)__float_as_int(m.z) * TC_W, acc);
-                            pa[i] = h * wa_f;
+                    fence_proxy_async();
+                    mbar_arrive(BAR(A_READY + s));
+                    if (h2 == 1) {
+                        // sigma of a sample = sum of its rows' terms; the thread of the sample's first row does it
+                        const int me = slot_sh[row];
+                        if (me >= 0 && (row == 0 || slot_sh[row - 1] != me)) {
+                            float sum = sig_sh[row];
+                            for (int q = row + 1; q < TC_ROWS && slot_sh[q] == me; q++) sum += sig_sh[q];
+                            p.sigma[c0[s] + me] = sum;
                         }
-                        // alpha: sum over the 32 features of this warp for each of the 32 rows (transpose-reduce, 31 shuffles),
-                        // lane i ends up with the partial of row cc*32 + i; the 8 warps meet in shared memory
-#pragma unroll
-                        for (int sft = 16; sft >= 1; sft >>= 1) {
-                            const bool up = (lane & sft) != 0;
-#pragma unroll
-                            for (int i = 0; i < sft; i++) {
-                                const float send = up ? pa[i] : pa[i + sft];
-                                const float keepv = up ? pa[i + sft] : pa[i];
-                                pa[i] = keepv + __shfl_xor_sync(0xffffffffu, send, sft);
-                            }
-                        }
-                        red_shared_f32(araw_a + (uint32_t)(cc * 32 + lane) * 4u, pa[0]);
-                    };
-                    tc_ld32_nowait(accT, v0);
-#pragma unroll 1
-                    for (int cp = 0; cp < 2; cp++) {
-                        tc_wait_ld(v0);
-                        tc_ld32_nowait(accT + (uint32_t)(cp * 64 + 32), v1);
-                        last_chunk(2 * cp, v0);
-                        tc_wait_ld(v1);
-                        if (cp == 0) tc_ld32_nowait(accT + 64u, v0);
-                        last_chunk(2 * cp + 1, v1);
                     }
                     if (prof) { const long long t1 = clock64(); pf_last += t1 - pf_t0; pf_t0 = t1; }
-                    tc_fence_before();
-                    mbar_arrive(BAR(D_EMPTY + db));
-                    // sigma = sum over the rows of a sample of wc * act(alpha): the lower four warps take one row each
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (half == 0) {
-                        const int r = quad * 32 + lane;
-                        const float4 m = meta[mb * TC_ROWS + r];
-                        const float a = araw_sh[mb * TC_ROWS + r] + p.ba[0];
-                        const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
-                        sig_sh[r] = (p.dbg & 24) ? 0.f : act * m.x;
-                        asm volatile("bar.sync 2, 128;" ::: "memory");
-                        if (m.y == 0.f) {                        // first row of a sample (within this tile)
-                            float sum = sig_sh[r];
-                            for (int q = r + 1; q < TC_ROWS && meta[mb * TC_ROWS + q].y != 0.f; q++) sum += sig_sh[q];
-                            p.sigma[(uint32_t)__float_as_int(m.z)] = sum;
+                }
+            }
+            // ---- drain the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F[c0 + slot][feature]
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                if (!have[s]) continue;
+                const int npass = (nslots[s] + KS_SLOTS - 1) / KS_SLOTS;
+                const int f = h2 * 128 + quad * 32 + lane;
+                const uint32_t sel_base = sbase + OFF_SLOT0 + s * SLOT_BYTES + 4 * PANEL_A;
+                for (int pass = 0; pass < npass; pass++) {
+                    if (prof) pf_t0 = clock64();
+                    mbar_wait(BAR(D_FULL + s), ph_d[s]); ph_d[s] ^= 1;
+                    tc_fence_after();
+                    const int ns = min(KS_SLOTS, nslots[s] - pass * KS_SLOTS);
+                    float* fcol = p.F + (size_t)(c0[s] + pass * KS_SLOTS) * TC_W + f;
+                    const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_SLOTS) + lane_field;
+#pragma unroll 1
+                    for (int j = 0; j < KS_SLOTS / 32; j++) {
+                        if (32 * j >= ns) break;
+                        uint32_t v[32];
+                        tc_ld32(d_addr + 32 * j, v);
+                        if (!(p.dbg & 16)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++)
+                                if (32 * j + i < ns) fcol[(size_t)(32 * j + i) * TC_W] = __uint_as_float(v[i]);
                         }
-                        __syncwarp();
                     }
-                    mbar_arrive(BAR(META_FREE + mb));
-                    if (prof) { const long long t1 = clock64(); pf_sigma += t1 - pf_t0; pf_t0 = t1; }
+                    tc_fence_before();
+                    if (pass + 1 < npass) {
+                        // next 64 sample slots: rebuild Sel (the MMA of this pass has completed, nobody reads it now)
+                        const uint32_t z = sel_base + et * 64;
+                        sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
+                        epi_bar();
+                        const int n = slr[s] - (pass + 1) * KS_SLOTS;
+                        if (h2 == 0 && n >= 0 && n < KS_SLOTS) {
+                            const __nv_bfloat16 wb = __float2bfloat16_rn(wcr[s]);
+                            sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + n * 128 + ((((row & 63) >> 3) ^ (n & 7)) << 4) + (row & 7) * 2,
+                                  *reinterpret_cast<const uint16_t*>(&wb));
+                        }
+                        fence_proxy_async();
+                    }
+                    mbar_arrive(BAR(A_READY + s));
+                    if (prof) { const long long t1 = clock64(); pf_drain += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
         }
         if (prof && blockIdx.x == 0 && lane == 0)
-            printf("epi warp %d: tiles %u wait %lld mid(%d layers) %lld last %lld sigma %lld (cycles/tile)\n", warp, tcount,
-                   pf_wait / max(tcount, 1u), p.n_layers - 1, pf_mid / max(tcount, 1u), pf_last / max(tcount, 1u), pf_sigma / max(tcount, 1u));
+            printf("epi warp %d: tiles %u wait %lld hidden %lld last %lld drain %lld (cycles/tile)\n", warp, tcount, pf_wait / max(tcount, 1u),
+                   pf_mid / max(tcount, 1u), pf_last / max(tcount, 1u), pf_drain / max(tcount, 1u));
     } else if (warp < TC_PRODUCER_WARP) {
-        // =========================================================== GATHER (one thread per row) for this CTA's tiles, one ahead
+        // =========================================================== GATHER: one thread per row
         const int row = tid - TC_GATHER_WARP0 * 32;
-        uint32_t ph_x0empty = 1, ph_meta[2] = {1, 1};
-        uint32_t tcount = 0;
-        long long gf_load = 0, gf_wait = 0, gf_write = 0, gf_t0 = 0;
-        const bool prof = (p.dbg & 32) != 0;
+        uint32_t ph_free[2] = {1, 1};
         const float* Rm = p.in.camrot;
         const float r00 = Rm[0], r01 = Rm[1], r02 = Rm[2], r10 = Rm[3], r11 = Rm[4], r12 = Rm[5], r20 = Rm[6], r21 = Rm[7], r22 = Rm[8];
         const float cpx = p.in.campos[0], cpy = p.in.campos[1], cpz = p.in.campos[2];
-        const uint32_t x0 = sbase + OFF_X0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-            const int mb = tcount & 1;
-            if (prof) gf_t0 = clock64();
-            const int64_t j = (int64_t)tile * TC_ROWS + row;
-            const bool live = j < T;
-            float wcv = 0.f, keepv = 0.f; int drow = p.S_cap + p.n_tiles_cap;       // dead rows: weight 0, dummy destination row
-            float emb[TC_C];
-            float dist[6];
-            float e7[8];
+        long long gf_load = 0, gf_wait = 0, gf_write = 0, gf_t0 = 0;
+        const bool prof = (p.dbg & 32) != 0;
+        uint32_t tcount = 0;
+        for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
+#pragma unroll 1
+            for (int s = 0; s < 2; s++) {
+                const int tile = 2 * pc + s;
+                if (tile >= ntiles) continue;
+                tcount++;
+                if (prof) gf_t0 = clock64();
+                const int2 ta = p.tile_tab[tile], tb = p.tile_tab[tile + 1];
+                const bool live = row < tb.x - ta.x && !(p.dbg & 4);
+                float dist[6], e7[8];
 #pragma unroll
-            for (int i = 0; i < TC_C; i++) emb[i] = 0.f;
+                for (int i = 0; i < 6; i++) dist[i] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 6; i++) dist[i] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) e7[i] = 0.f;
-            if (live && !(p.dbg & 4)) {
-                const int flat = p.tuple_src[j];
-                const int64_t s = flat / p.K;
-                const int64_t r = s / p.SR;
-                const int64_t pt = p.in.pidx[flat];
-                wcv = p.wc[flat];
-                const int st = p.tuple_start[s];
-                // a sample continued from the previous tile accumulates into this tile's carry row (added back by the colour kernel)
-                drow = st < tile * TC_ROWS ? p.S_cap + tile : p.sample_cidx[s];
-                keepv = (j == st || row == 0) ? 0.f : 1.f;
-                const float4* ep = (const float4*)(p.in.tab.embedding + pt * TC_C);
-#pragma unroll
-                for (int i = 0; i < TC_C / 4; i++) {
-                    const float4 e = __ldg(ep + i);
-                    emb[4 * i] = e.x; emb[4 * i + 1] = e.y; emb[4 * i + 2] = e.z; emb[4 * i + 3] = e.w;
+                for (int i = 0; i < 8; i++) e7[i] = 0.f;
+                int64_t pt = 0;
+                if (live) {
+                    const int flat = p.tuple_src[ta.x + row];
+                    const int64_t sm = flat / p.K;
+                    const int64_t r = sm / p.SR;
+                    pt = p.in.pidx[flat];
+                    const float px = p.in.tab.xyz[3 * pt], py = p.in.tab.xyz[3 * pt + 1], pz = p.in.tab.xyz[3 * pt + 2];
+                    dist[0] = px - p.in.loc_w[3 * sm]; dist[1] = py - p.in.loc_w[3 * sm + 1]; dist[2] = pz - p.in.loc_w[3 * sm + 2];
+                    const float sx = px - cpx, sy = py - cpy, sz = pz - cpz;
+                    const float c0 = sx * r00 + sy * r10 + sz * r20, c1 = sx * r01 + sy * r11 + sz * r21, c2 = sx * r02 + sy * r12 + sz * r22;
+                    const float xp = c0 / c2, yp = c1 / c2;
+                    const float lxp = p.loc_pers[3 * sm], lyp = p.loc_pers[3 * sm + 1], lzp = p.loc_pers[3 * sm + 2];
+                    dist[3] = xp * c2 - lxp * lzp; dist[4] = yp * c2 - lyp * lzp; dist[5] = c2 - lzp;
+                    const float vx = p.in.raydir[3 * r], vy = p.in.raydir[3 * r + 1], vz = p.in.raydir[3 * r + 2];
+                    const float dx = p.in.tab.dir[3 * pt], dy = p.in.tab.dir[3 * pt + 1], dz = p.in.tab.dir[3 * pt + 2];
+                    e7[0] = p.in.tab.color[3 * pt]; e7[1] = p.in.tab.color[3 * pt + 1]; e7[2] = p.in.tab.color[3 * pt + 2];
+                    e7[3] = dx - vx; e7[4] = dy - vy; e7[5] = dz - vz; e7[6] = dx * vx + dy * vy + dz * vz;
                 }
-                const float px = p.in.tab.xyz[3 * pt], py = p.in.tab.xyz[3 * pt + 1], pz = p.in.tab.xyz[3 * pt + 2];
-                dist[0] = px - p.in.loc_w[3 * s]; dist[1] = py - p.in.loc_w[3 * s + 1]; dist[2] = pz - p.in.loc_w[3 * s + 2];
-                const float sx = px - cpx, sy = py - cpy, sz = pz - cpz;
-                const float c0 = sx * r00 + sy * r10 + sz * r20, c1 = sx * r01 + sy * r11 + sz * r21, c2 = sx * r02 + sy * r12 + sz * r22;
-                const float xp = c0 / c2, yp = c1 / c2;
-                const float lxp = p.loc_pers[3 * s], lyp = p.loc_pers[3 * s + 1], lzp = p.loc_pers[3 * s + 2];
-                dist[3] = xp * c2 - lxp * lzp; dist[4] = yp * c2 - lyp * lzp; dist[5] = c2 - lzp;
-                const float vx = p.in.raydir[3 * r], vy = p.in.raydir[3 * r + 1], vz = p.in.raydir[3 * r + 2];
-                const float dx = p.in.tab.dir[3 * pt], dy = p.in.tab.dir[3 * pt + 1], dz = p.in.tab.dir[3 * pt + 2];
-                e7[0] = p.in.tab.color[3 * pt]; e7[1] = p.in.tab.color[3 * pt + 1]; e7[2] = p.in.tab.color[3 * pt + 2];
-                e7[3] = dx - vx; e7[4] = dy - vy; e7[5] = dz - vz; e7[6] = dx * vx + dy * vy + dz * vz;
-            }
-            // the global loads above are in flight while the previous tile still owns the X0 panels
-            if (prof) { const long long t1 = clock64(); gf_load += t1 - gf_t0; gf_t0 = t1; }
-            mbar_wait(BAR(X0_EMPTY), ph_x0empty); ph_x0empty ^= 1;
-            mbar_wait(BAR(META_FREE + mb), ph_meta[mb]); ph_meta[mb] ^= 1;
-            if (prof) { const long long t1 = clock64(); gf_wait += t1 - gf_t0; gf_t0 = t1; }
-            // cols [0,32): embedding
+                if (prof) { const long long t1 = clock64(); gf_load += t1 - gf_t0; gf_t0 = t1; }
+                mbar_wait(BAR(BUF_FREE + s), ph_free[s]); ph_free[s] ^= 1;
+                if (prof) { const long long t1 = clock64(); gf_wait += t1 - gf_t0; gf_t0 = t1; }
+                const uint32_t x0 = sbase + OFF_SLOT0 + s * SLOT_BYTES;
+                if (live) {
+                    // cols [0,224): the point's precomputed row, 28 x 16 bytes
+                    const uint8_t* src = p.ptab + (size_t)pt * TC_PT_BYTES;
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                sts128(x0 + sw_off(row, 8 * q), pack_bf16(emb[8 * q], emb[8 * q + 1]), pack_bf16(emb[8 * q + 2], emb[8 * q + 3]),
-                       pack_bf16(emb[8 * q + 4], emb[8 * q + 5]), pack_bf16(emb[8 * q + 6], emb[8 * q + 7]));
-            // cols 32 + 2*(c*F + f) + {0: sin, 1: cos}: base angle by sincosf, octaves by the double-angle recurrence
-            if (!(p.dbg & 2))
+                    for (int i = 0; i < TC_PT_BYTES / 16; i++) cp_async16(x0 + sw_off(row, 8 * i), src + 16 * i);
+                    // cols 224 + 2*(d*FD + f) + {0: sin, 1: cos}: base angle by sincosf, octaves by the double-angle recurrence
 #pragma unroll
-            for (int c = 0; c < TC_C; c++) {
-                float sn, cs_;
-                __sincosf(emb[c], &sn, &cs_);
+                    for (int d = 0; d < 6; d++) {
+                        float sn, cs_;
+                        __sincosf(dist[d], &sn, &cs_);
 #pragma unroll
-                for (int f = 0; f < TC_F; f++) {
-                    sts32(x0 + sw_off(row, TC_C + 2 * (c * TC_F + f)), pack_bf16(sn, cs_));
-                    const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
-                    sn = s2; cs_ = c2;
+                        for (int f = 0; f < TC_FD; f++) {
+                            sts32(x0 + sw_off(row, TC_PT_COLS + 2 * (d * TC_FD + f)), pack_bf16(sn, cs_));
+                            const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
+                            sn = s2; cs_ = c2;
+                        }
+                    }
+                    sts32(x0 + sw_off(row, TC_K0), 0u); sts32(x0 + sw_off(row, TC_K0 + 2), 0u);      // cols 284..287 = 0
+                    const int col = 4 * 64 + E7_COL0;
+                    sts128(x0 + sw_off(row, col), pack_bf16(e7[0], e7[1]), pack_bf16(e7[2], e7[3]), pack_bf16(e7[4], e7[5]), pack_bf16(e7[6], 0.f));
+                    sts128(x0 + sw_off(row, col + 8), 0u, 0u, 0u, 0u);
+                } else {
+                    // dead row: all-zero operand (what is left in the slot from the previous tile must not reach the MMAs)
+#pragma unroll
+                    for (int i = 0; i < (4 * 64 + E7_COL0 + 16) / 8; i++) sts128(x0 + sw_off(row, 8 * i), 0u, 0u, 0u, 0u);
                 }
+                cp_async_wait_all();
+                fence_proxy_async();
+                mbar_arrive(BAR(X_FULL + s));
+                if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
             }
-            constexpr int DB = TC_C * (1 + 2 * TC_F);     // 224
-#pragma unroll
-            for (int d = 0; d < 6; d++) {
-                float sn, cs_;
-                __sincosf(dist[d], &sn, &cs_);
-#pragma unroll
-                for (int f = 0; f < TC_FD; f++) {
-                    sts32(x0 + sw_off(row, DB + 2 * (d * TC_FD + f)), pack_bf16(sn, cs_));
-                    const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
-                    sn = s2; cs_ = c2;
-                }
-            }
-            sts32(x0 + sw_off(row, TC_K0), 0u); sts32(x0 + sw_off(row, TC_K0 + 2), 0u);      // cols 284..287 = 0
-            // E7 slot of this tile parity: cols 256 + 32 + 16*mb .. +15 (panel 4)
-            {
-                const int col = 4 * 64 + E7_COL0 + 16 * mb;
-                sts128(x0 + sw_off(row, col), pack_bf16(e7[0], e7[1]), pack_bf16(e7[2], e7[3]), pack_bf16(e7[4], e7[5]), pack_bf16(e7[6], 0.f));
-                sts128(x0 + sw_off(row, col + 8), 0u, 0u, 0u, 0u);
-            }
-            meta[mb * TC_ROWS + row] = make_float4(wcv, keepv, __int_as_float(drow), 0.f);
-            araw_sh[mb * TC_ROWS + row] = 0.f;
-            fence_proxy_async();
-            mbar_arrive(BAR(X0_FULL));
-            if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
         }
         if (prof && blockIdx.x == 0 && lane == 0)
-            printf("gather warp %d: tiles %u issue-loads %lld wait-slot %lld expand+write %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u), gf_wait / max(tcount, 1u), gf_write / max(tcount, 1u));
+            printf("gather warp %d: tiles %u issue-loads %lld wait-slot %lld copy+expand %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u),
+                   gf_wait / max(tcount, 1u), gf_write / max(tcount, 1u));
     } else if (warp == TC_PRODUCER_WARP) {
-        // =========================================================== PRODUCER: weight panels through the ring
+        // =========================================================== PRODUCER: weight panels through the ring, once per (layer, slot)
         if (lane == 0) {
             uint32_t ph_empty[B_STAGES];
             for (int s = 0; s < B_STAGES; s++) ph_empty[s] = 1;
             uint32_t n = 0;
-            const int total_panels = p.first_panel[p.n_layers];
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int pi = 0; pi < total_panels; pi++, n++) {
-                    const int s = n % B_STAGES;
-                    mbar_wait(BAR(B_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
-                    if (p.dbg & 1) { mbar_arrive(BAR(B_FULL + s)); continue; }
-                    mbar_expect_tx(BAR(B_FULL + s), PANEL_B);
-                    bulk_g2s(sbase + OFF_B + s * PANEL_B, p.wpack + (size_t)pi * PANEL_B, PANEL_B, BAR(B_FULL + s));
-                }
+            for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
+                const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
+                for (int l = 0; l < p.n_layers; l++)
+                    for (int s = 0; s < nslot; s++)
+                        for (int pi = p.first_panel[l]; pi < p.first_panel[l + 1]; pi++, n++) {
+                            const int st = n % B_STAGES;
+                            mbar_wait(BAR(W_EMPTY + st), ph_empty[st]); ph_empty[st] ^= 1;
+                            if (p.dbg & 1) { mbar_arrive(BAR(W_FULL + st)); continue; }
+                            mbar_expect_tx(BAR(W_FULL + st), PANEL_B);
+                            bulk_g2s(sbase + OFF_WRING + st * PANEL_B, p.wpack + (size_t)pi * PANEL_B, PANEL_B, BAR(W_FULL + st));
+                        }
             }
         }
     } else {
@@ -520,61 +404,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
         if (lane == 0) {
             uint32_t ph_full[B_STAGES];
             for (int s = 0; s < B_STAGES; s++) ph_full[s] = 0;
-            uint32_t ph_x0full = 0, ph_afull = 0, ph_dempty[2] = {1, 1};   // ph_afull: one phase bit per activation chunk
-            uint32_t n = 0, lcount = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-                const int mb = tcount & 1;
-                for (int l = 0; l < p.n_layers; l++, lcount++) {
-                    const int db = lcount & 1;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(db * TC_W);
-                    mbar_wait(BAR(D_EMPTY + db), ph_dempty[db]); ph_dempty[db] ^= 1;
+            uint32_t ph_x[2] = {0, 0}, ph_a[2] = {1, 1};
+            uint32_t n = 0;
+            for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
+                const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
+                int npass[2] = {0, 0};
+                for (int s = 0; s < nslot; s++)
+                    npass[s] = (p.tile_tab[2 * pc + s + 1].y - p.tile_tab[2 * pc + s].y + KS_SLOTS - 1) / KS_SLOTS;
+                for (int l = 0; l < p.n_layers; l++) {
                     const int np = p.first_panel[l + 1] - p.first_panel[l];
                     const int kind = p.kind[l];
-                    if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X0_FULL), ph_x0full); ph_x0full ^= 1; }
-                    uint32_t acc = 0;
-                    const bool swapped = (l == p.n_layers - 1);          // last layer: D^T = W H^T (see the epilogue)
-                    auto issue = [&](uint32_t a_addr, uint32_t b_addr, int k0, int k1) {
-                        for (int k = k0; k < k1; k++) {
-                            if (!swapped) {
-                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), TC_IDESC, acc);
-                            } else {
-                                tc_mma(d_tmem, umma_desc(b_addr + k * 32), umma_desc(a_addr + k * 32), TC_IDESC_T, acc);
-                                tc_mma(d_tmem + 128u, umma_desc(b_addr + 128 * 128 + k * 32), umma_desc(a_addr + k * 32), TC_IDESC_T, acc);
-                            }
-                            acc = 1;
-                        }
-                    };
-                    for (int kp = 0; kp < np; kp++, n++) {
-                        const int s = n % B_STAGES;
-                        const uint32_t b_addr = sbase + OFF_B + s * PANEL_B;
-                        if (kind != LAYER_FROM_X0 && kp < AM_PANELS) {
-                            // activation panel kp arrives as two 32-column chunks; each is two K-steps
-                            const uint32_t a_addr = sbase + OFF_AM + kp * PANEL_A;
-                            for (int hc = 0; hc < 2; hc++) {
-                                const int c = 2 * kp + hc;
-                                mbar_wait(BAR(A_FULL + c), (ph_afull >> c) & 1u); ph_afull ^= 1u << c;
-                                if (hc == 0) { mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1; }
-                                tc_fence_after();
-                                issue(a_addr, b_addr, 2 * hc, 2 * hc + 2);
-                            }
-                        } else {
-                            uint32_t a_addr;
+                    for (int s = 0; s < nslot; s++) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
+                        const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
+                        mbar_wait(BAR(A_READY + s), ph_a[s]); ph_a[s] ^= 1;
+                        if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X_FULL + s), ph_x[s]); ph_x[s] ^= 1; }
+                        tc_fence_after();
+                        uint32_t acc = 0;
+                        for (int kp = 0; kp < np; kp++, n++) {
+                            const int st = n % B_STAGES;
+                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
+                            uint32_t a_addr = a_base + kp * PANEL_A;
                             int ksteps = 4;
-                            if (kind == LAYER_FROM_X0) {
-                                a_addr = sbase + OFF_X0 + kp * PANEL_A;
-                                if (kp == 4) ksteps = 2;                      // cols 256..287
-                            } else {                                          // [colour | dir - view | dir.view] K-step of block3.0
-                                a_addr = sbase + OFF_X0 + 4 * PANEL_A + (E7_COL0 + 16 * mb) * 2;
-                                ksteps = 1;
+                            if (kp == 4) {
+                                if (kind == LAYER_FROM_X0) ksteps = 2;                                   // cols 256..287
+                                else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view] of block3.0
                             }
-                            mbar_wait(BAR(B_FULL + s), ph_full[s]); ph_full[s] ^= 1;
+                            mbar_wait(BAR(W_FULL + st), ph_full[st]); ph_full[st] ^= 1;
                             tc_fence_after();
-                            issue(a_addr, b_addr, 0, ksteps);
+                            for (int k = 0; k < ksteps; k++) {
+                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), IDESC_LAYER, acc);
+                                acc = 1;
+                            }
+                            tc_commit(BAR(W_EMPTY + st));
                         }
-                        tc_commit(BAR(B_EMPTY + s));
+                        tc_commit(BAR(D_FULL + s));
                     }
-                    if (kind == LAYER_FROM_X0) tc_commit(BAR(X0_EMPTY));
-                    tc_commit(BAR(D_FULL + db));
+                }
+                // K-weighted sums: F^T[256 features (two M = 128 halves)][64 sample slots] = H^T x Sel^T, K = the tile's 128 rows
+                for (int s = 0; s < nslot; s++) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
+                    const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
+                    const uint32_t sel = a_base + 4 * PANEL_A;
+                    for (int pass = 0; pass < npass[s]; pass++) {
+                        mbar_wait(BAR(A_READY + s), ph_a[s]); ph_a[s] ^= 1;
+                        tc_fence_after();
+                        for (int half = 0; half < 2; half++)
+                            for (int ks = 0; ks < TC_ROWS / 16; ks++)
+                                tc_mma(d_tmem + (uint32_t)(half * KS_SLOTS), umma_desc_mn(a_base + (2 * half) * PANEL_A + ks * 2048),
+                                       umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
+                        tc_commit(BAR(D_FULL + s));
+                    }
+                    tc_commit(BAR(BUF_FREE + s));
                 }
             }
         }
@@ -582,7 +463,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
     __syncthreads();
     if (warp == TC_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
-
 
 // ================================================================================================ colour branch
 // Per-sample colour MLP on tensor cores (point_aggregators.py:298-309 raw2out_color, :771-786): one persistent CTA per SM,
@@ -601,20 +481,18 @@ constexpr int COFF_RING = COFF_W + C_W_PANELS * C_PANEL;
 constexpr int COFF_ACT = COFF_RING + C_RING * C_PANEL;
 constexpr int COFF_BIAS = COFF_ACT + 2 * C_PANEL;                           // [3][128] hidden biases
 constexpr int COFF_WL = COFF_BIAS + C_MAX_HIDDEN * CW * 4;                  // [3][128] last Linear + its bias [4]
-constexpr int COFF_CARRY = COFF_WL + 3 * CW * 4 + 16;                       // [2][128] carry row of each sample of the tile (-1: none)
-constexpr int COFF_BAR = COFF_CARRY + 2 * TC_ROWS * 4;
+constexpr int COFF_BAR = COFF_WL + 3 * CW * 4 + 16;
 constexpr int C_NBARS = 1 + 2 * C_RING + 2 + 4;
 constexpr int COFF_TMEMPTR = COFF_BAR + C_NBARS * 8;
 constexpr int C_SMEM = COFF_TMEMPTR + 16 + 1024;
 static_assert(C_SMEM <= 232448, "colour kernel exceeds the 227 KB shared memory limit");
-constexpr uint32_t C_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+constexpr uint32_t C_IDESC = tc_idesc(TC_ROWS, CW);
 
 struct ColParams {
     const int32_t* S_ptr; int S_max;
     const int32_t* csample;            // compact sample -> sample
-    const float* F;                    // [S_cap + tiles + 1][256] K-sums per compact sample, then the per-tile carry rows
-    const float* sigma;                // same row indexing
-    const int32_t* tuple_start; const int32_t* nvalid; int S_cap;
+    const float* F;                    // [S][256] K-weighted feature sums per compact sample
+    const float* sigma;                // [S]
     const float* raydir; int SR;
     const uint8_t* wpack;              // packed hidden-layer weights, C_PANEL each, layer after layer
     int n_hidden;                      // colour layers followed by an activation (1..3)
@@ -718,11 +596,7 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                     const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
                                 s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
                     const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
-                    const int sidx = p.csample[c];
-                    const int st = p.tuple_start[sidx], t2 = (st + p.nvalid[sidx] - 1) >> 7;
-                    float sg = p.sigma[c];
-                    if ((st >> 7) != t2) sg += p.sigma[p.S_cap + t2];
-                    ((float4*)p.decoded)[sidx] = make_float4(sg, s0 * m - o, s1 * m - o, s2 * m - o);
+                    ((float4*)p.decoded)[p.csample[c]] = make_float4(p.sigma[c], s0 * m - o, s1 * m - o, s2 * m - o);
                 }
             }
         }
@@ -733,22 +607,8 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
         uint32_t ph_empty[C_RING];
         for (int s = 0; s < C_RING; s++) ph_empty[s] = 1;
         uint32_t n = 0;
-        int32_t* s_carry = (int32_t*)(smem + COFF_CARRY);
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t c0 = (int64_t)tile * TC_ROWS;
-            // samples whose tuples straddle two tiles of the per-neighbour kernel left their second part in that tile's carry row
-            int32_t* carry = s_carry + (tcount & 1) * TC_ROWS;
-            {
-                int cr = -1;
-                if (c0 + lt < Sv) {
-                    const int sidx = p.csample[c0 + lt];
-                    const int st = p.tuple_start[sidx], t2 = (st + p.nvalid[sidx] - 1) >> 7;
-                    if ((st >> 7) != t2) cr = p.S_cap + t2;
-                }
-                carry[lt] = cr;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
             for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
                 const int s = n % C_RING;
                 const uint32_t base = sbase + COFF_RING + s * C_PANEL;
@@ -758,11 +618,6 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                     for (int pass = 0; pass < 16; pass++) {
                         const int r = pass * 8 + rgrp;
                         f[pass] = (c0 + r < Sv && !(p.dbg & 128)) ? __ldg((const float4*)(p.F + (size_t)(c0 + r) * TC_W + kp * 64 + sub * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int cr = carry[r];
-                        if (cr >= 0) {
-                            const float4 g = __ldg((const float4*)(p.F + (size_t)cr * TC_W + kp * 64 + sub * 4));
-                            f[pass].x += g.x; f[pass].y += g.y; f[pass].z += g.z; f[pass].w += g.w;
-                        }
                     }
                     mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
 #pragma unroll
@@ -871,16 +726,58 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, in
     *dst = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Per-point operand rows: ptab[p] = bf16 [emb (32) | sin, cos of emb_c * 2^f, (c, f) major (192)] -- exactly the first 224
+// columns of the reference's `feat` (point_aggregators.py:603-611).  One warp per point, lane = channel.
+__global__ void __launch_bounds__(256) tc_point_rows_kernel(const float* __restrict__ emb, int64_t N, uint8_t* __restrict__ ptab)
+{
+    const int64_t pnt = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pnt >= N) return;
+    const int c = threadIdx.x & 31;
+    const float e = emb[pnt * TC_C + c];
+    uint8_t* row = ptab + (size_t)pnt * TC_PT_BYTES;
+    *(__nv_bfloat16*)(row + 2 * c) = __float2bfloat16_rn(e);
+    float sn, cs_;
+    __sincosf(e, &sn, &cs_);
+    uint32_t* pe = (uint32_t*)(row + 2 * TC_C + 4 * TC_F * c);
+#pragma unroll
+    for (int f = 0; f < TC_F; f++) {
+        pe[f] = pack_bf16(sn, cs_);
+        const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
+        sn = s2; cs_ = c2;
+    }
+}
+
+// Tile table: tile t owns the compact samples whose first tuple index lies in [t*TW, (t+1)*TW).  One thread per compact sample.
+__global__ void tc_tile_kernel(const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ T_ptr, const int32_t* __restrict__ csample,
+                               const int32_t* __restrict__ tuple_start, int TW, int2* __restrict__ tile_tab, int32_t* __restrict__ ntiles)
+{
+    const int Sv = min(*S_ptr, S_max);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && Sv == 0) *ntiles = 0;
+    if (c >= Sv) return;
+    const int st = tuple_start[csample[c]];
+    const int t = st / TW;
+    const int tprev = c == 0 ? -1 : tuple_start[csample[c - 1]] / TW;
+    if (t != tprev) tile_tab[t] = make_int2(st, c);
+    if (c == Sv - 1) {
+        tile_tab[t + 1] = make_int2(*T_ptr, Sv);
+        *ntiles = t + 1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-case (every slot valid) workspace
 
 struct TcWs {
-    int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample;
-    float *loc_pers, *weight_n, *wc, *C0, *sigma;
-    uint8_t *wpack, *cpack;
+    int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles;
+    int2* tile_tab;
+    float *loc_pers, *weight_n, *wc, *F, *sigma;
+    uint8_t *wpack, *cpack, *ptab;
 };
 
-static size_t tc_carve(const AggPlan& P, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
+static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
+
+static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
 {
     const AggDims& d = P.dims;
     Arena A(base, cap);
@@ -889,17 +786,19 @@ static size_t tc_carve(const AggPlan& P, int64_t Rc, int SR, int K, void* base, 
     ws->tuple_start = A.take<int32_t>(S + 1); ws->sample_cidx = A.take<int32_t>(S + 1);
     ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1); ws->csample = A.take<int32_t>(S + 1);
+    ws->ntiles = A.take<int32_t>(4);
+    ws->tile_tab = A.take<int2>(T / tile_width(K) + 3);
     ws->loc_pers = A.take<float>(S * 3); ws->weight_n = A.take<float>(T); ws->wc = A.take<float>(T);
-    const size_t ext = S + T / TC_ROWS + 2;          // compact samples + one carry row per tile + dummy row
-    ws->C0 = A.take<float>(ext * d.W); ws->sigma = A.take<float>(ext);
+    ws->F = A.take<float>((S + 1) * d.W); ws->sigma = A.take<float>(S + 1);
     size_t panels = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
     ws->cpack = A.take<uint8_t>((size_t)C_W_PANELS * C_PANEL);
+    ws->ptab = A.take<uint8_t>((size_t)N * TC_PT_BYTES);
     return A.off;
 }
 
-static int tc_supported(const AggPlan& P)
+static int tc_supported(const AggPlan& P, int K)
 {
     const AggDims& d = P.dims;
     SGN_CHECK_ARG(d.C == TC_C && d.F == TC_F && d.FD == TC_FD && d.W == TC_W,
@@ -910,6 +809,7 @@ static int tc_supported(const AggPlan& P)
     SGN_CHECK_ARG(P.n_color_hidden >= 1 && P.n_color_hidden <= C_MAX_HIDDEN && d.WC == CW && d.FV <= 5,
                   "bf16 tensor-core path: colour branch must have 2..%d layers of width %d and num_viewdir_freqs <= 5; use SGN_PRECISION_FP32",
                   C_MAX_HIDDEN + 1, CW);
+    SGN_CHECK_ARG(K <= 32, "bf16 tensor-core path: K <= 32");
     for (int t = 0; t < P.n_tuple_layers; t++)
         SGN_CHECK_ARG(P.layers[t].extra != EXTRA_LABEL, "bf16 tensor-core path: label input unsupported");
     return SGN_OK;
@@ -919,12 +819,12 @@ static int tc_supported(const AggPlan& P)
 
 using namespace sgn;
 
-int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, size_t* bytes)
+int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes)
 {
-    int rc = tc_supported(P);
+    int rc = tc_supported(P, K);
     if (rc) return rc;
     TcWs ws;
-    *bytes = tc_carve(P, R < TC_CHUNK ? R : TC_CHUNK, SR, K, nullptr, 0, &ws);
+    *bytes = tc_carve(P, N, R < TC_CHUNK ? R : TC_CHUNK, SR, K, nullptr, 0, &ws);
     return SGN_OK;
 }
 
@@ -933,12 +833,12 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
                        int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* weight_out, float* conf_out,
                        void* workspace, size_t workspace_bytes, cudaStream_t st)
 {
-    int rc = tc_supported(P);
+    int rc = tc_supported(P, K);
     if (rc) return rc;
     const AggDims& d = P.dims;
     const int64_t chunk = R < TC_CHUNK ? R : TC_CHUNK;
     TcWs ws;
-    const size_t need = tc_carve(P, chunk, SR, K, workspace, workspace_bytes, &ws);
+    const size_t need = tc_carve(P, tables->N, chunk, SR, K, workspace, workspace_bytes, &ws);
     if (need > workspace_bytes || ((uintptr_t)workspace & 255)) {
         set_error("sgn_agg_forward(bf16): workspace too small or misaligned (need %zu bytes, got %zu)", need, workspace_bytes);
         return SGN_E_WORKSPACE;
@@ -953,7 +853,8 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
 
-    // weights -> bf16 panels in the 128B-swizzled shared-memory image (per call: they may have been updated by the optimiser)
+    // per call (weights and embeddings may have been updated by the optimiser): bf16 weight panels in the 128B-swizzled
+    // shared-memory image, and the per-point operand rows [emb | PE(emb)]
     TcParams tp = {};
     tp.first_panel[0] = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) {
@@ -975,9 +876,10 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
             cp.bias[c] = biases[l];
         }
     }
+    launch(tc_point_rows_kernel, cdiv(tables->N, 8), 256, 0, st, tables->embedding, tables->N, ws.ptab);
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
-    tp.wpack = ws.wpack;
+    tp.wpack = ws.wpack; tp.ptab = ws.ptab;
     tp.wa = weights[P.alpha_layer]; tp.ba = biases[P.alpha_layer];
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;
@@ -986,6 +888,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     cp.wpack = ws.cpack; cp.n_hidden = P.n_color_hidden; cp.fv = d.FV;
     cp.wl = weights[P.n_layers - 1]; cp.bl = biases[P.n_layers - 1];
     cp.slope = d.slope; cp.act_super = d.act_super; cp.SR = SR;
+    const int TW = tile_width(K);
 
     for (int64_t r0 = 0; r0 < R; r0 += chunk) {
         const int64_t Rc = R - r0 < chunk ? R - r0 : chunk;
@@ -1004,19 +907,19 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         const int32_t* T_ptr = ws.tuple_start + S;
         const int32_t* S_ptr = ws.sample_cidx + S;
         launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
+        launch(tc_tile_kernel, cdiv(S, 256), 256, 0, st, S_ptr, Sm, T_ptr, ws.csample, ws.tuple_start, TW, ws.tile_tab, ws.ntiles);
 
         tp.in = in;
-        tp.T_ptr = T_ptr; tp.T_max = Tm;
-        tp.tuple_src = ws.tuple_src; tp.tuple_start = ws.tuple_start; tp.sample_cidx = ws.sample_cidx;
-        tp.S_cap = Sm; tp.n_tiles_cap = cdiv(Tm, TC_ROWS);
+        tp.ntiles_ptr = ws.ntiles; tp.ntiles_cap = Tm / TW + 1;
+        tp.tile_tab = ws.tile_tab;
+        tp.tuple_src = ws.tuple_src; tp.sample_cidx = ws.sample_cidx;
         tp.loc_pers = loc_pers; tp.wc = ws.wc;
-        tp.F = ws.C0; tp.sigma = ws.sigma;
-        const int max_tiles = cdiv(Tm, TC_ROWS);
-        launch(agg_tuple_tc_kernel, max_tiles < n_sm ? max_tiles : n_sm, TC_THREADS, TC_SMEM, st, tp);
+        tp.F = ws.F; tp.sigma = ws.sigma;
+        const int max_pairs = (tp.ntiles_cap + 1) / 2;
+        launch(agg_tuple_tc_kernel, max_pairs < n_sm ? max_pairs : n_sm, TC_THREADS, TC_SMEM, st, tp);
 
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
-        cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.C0; cp.sigma = ws.sigma;
-        cp.tuple_start = ws.tuple_start; cp.nvalid = ws.nvalid; cp.S_cap = Sm;
+        cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.F; cp.sigma = ws.sigma;
         cp.raydir = in.raydir; cp.decoded = dec;
         const int max_ctiles = cdiv(Sm, TC_ROWS);
         launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, 288, C_SMEM, st, cp);

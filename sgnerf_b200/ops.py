@@ -273,7 +273,7 @@ class _Aggregate(torch.autograd.Function):
         if need_grad and precision != PRECISION_FP32:
             raise RuntimeError("sgnerf_b200: training runs the fp32 path; the bf16 tensor-core path is forward-only")
         nbytes = C.c_size_t()
-        _lib.call("sgn_agg_workspace_bytes", C.byref(cfg), R, SR, K, precision, int(need_grad), C.byref(nbytes))
+        _lib.call("sgn_agg_workspace_bytes", C.byref(cfg), xyz.shape[0], R, SR, K, precision, int(need_grad), C.byref(nbytes))
         ws = _workspace(nbytes.value, dev)
         decoded = torch.empty(R, SR, 4, dtype=torch.float32, device=dev)
         ray_valid = torch.empty(R, SR, dtype=torch.uint8, device=dev)
