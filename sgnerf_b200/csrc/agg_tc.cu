@@ -34,28 +34,35 @@ constexpr int TC_W = 256;                 // layer width == accumulator columns
 constexpr int TC_C = 32, TC_F = 3, TC_FD = 5;
 constexpr int TC_PT_COLS = TC_C * (1 + 2 * TC_F);              // 224 per-point columns: emb | PE(emb)
 constexpr int TC_PT_BYTES = TC_PT_COLS * 2;                    // 448
-constexpr int TC_K0 = TC_PT_COLS + 2 * TC_FD * 6;              // 284
+constexpr int TC_K0 = TC_PT_COLS + 2 * TC_FD * 6;              // 284; cols 284, 285 of the operand hold 1.0 (bias columns)
+static_assert(TC_K0 + 2 <= 4 * 64 + 32, "the two bias columns must fit in the first layer K padding");
 constexpr int TC_MAX_LAYERS = 6;
 constexpr int PANEL_A = TC_PANEL_BYTES;   // 16 KB: 128 rows x 64 bf16
 constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
 constexpr int SLOT_PANELS = 5, SLOT_BYTES = SLOT_PANELS * PANEL_A, B_STAGES = 2;
-constexpr int E7_COL0 = 32;               // inside panel 4: cols [32,48) hold [colour | dir-view | dir.view | 0]
+constexpr int E7_COL0 = 32;               // inside panel 4: cols [32,48) hold [colour | dir-view | dir.view | 1 | 1 | 0..]
+constexpr int ONES_KSTEP = 1;             // K-step of panel 4 that holds operand cols 272..287, i.e. the two 1.0 columns at 12, 13
+constexpr int META_CHUNK = 6;             // 16-byte chunk of a row of panel 4 that carries {w*conf, sample slot, first compact sample, #slots}
 constexpr int KS_SLOTS = 64;              // sample slots per K-sum pass (Sel^T = 2 K-panels x 64 x 128 B = panel 4)
+constexpr int BIAS_PANEL_B = TC_W * 32;   // 8 KB: compact (unswizzled) [256 x 16] bias K-step
+constexpr int ALPHA_N = 16;               // alpha_branch as an N = 16 MMA (row 0 = the weight vector)
+constexpr int ALPHA_PANEL_B = 4 * ALPHA_N * 128;                // 8 KB: [16 x 256] in four 128B-swizzled K panels
+constexpr int ALPHA_COL = 128;            // accumulator columns [128, 144) of the slot receive alpha
 
 constexpr int OFF_SLOT0 = 0;
 constexpr int OFF_WRING = 2 * SLOT_BYTES;                       // 163840
-constexpr int OFF_ARAW = OFF_WRING + B_STAGES * PANEL_B;        // 229376: [128] alpha partial of the upper column half
-constexpr int OFF_SIG = OFF_ARAW + TC_ROWS * 4;                 // [128] w*conf*act(alpha) per row
+constexpr int OFF_SIG = OFF_WRING + B_STAGES * PANEL_B;         // 229376: [128] w*conf*act(alpha) per row
 constexpr int OFF_SLOTID = OFF_SIG + TC_ROWS * 4;               // [128] sample slot of the row (-1: dead row)
 constexpr int OFF_BAR = OFF_SLOTID + TC_ROWS * 4;
 constexpr int N_BARS = 2 * B_STAGES + 8;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
-constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 12, TC_MMA_WARP = 13, TC_THREADS = 14 * 32;
+constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 16, TC_MMA_WARP = 17, TC_THREADS = 18 * 32;
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
 constexpr uint32_t IDESC_LAYER = tc_idesc(TC_ROWS, TC_W);
+constexpr uint32_t IDESC_ALPHA = tc_idesc(TC_ROWS, ALPHA_N);
 constexpr uint32_t IDESC_KSUM = tc_idesc(128, KS_SLOTS, 1);    // A = H^T read MN-major from the activation panels
 
 struct TcParams {
@@ -67,11 +74,12 @@ struct TcParams {
     const float* loc_pers; const float* wc;
     const uint8_t* ptab;                   // [N][224] bf16 per-point rows
     const uint8_t* wpack;                  // pre-swizzled bf16 weight panels, all layers back to back
+    const uint8_t* bpack[TC_MAX_LAYERS];   // compact bias K-step of the layer, or NULL when the bias rides in a weight panel
+    const uint8_t* apack;                  // alpha_branch panel
     int n_layers;
     int kind[TC_MAX_LAYERS];
     int first_panel[TC_MAX_LAYERS + 1];
-    const float* bias[TC_MAX_LAYERS];
-    const float* wa; const float* ba;
+    const float* ba;
     float slope; int act_super;
     float* F; float* sigma;                // outputs per compact sample: [S][256], [S]
     int dbg;                               // SGN_TC_DEBUG bitmask (timing experiments only; results invalid when != 0)
@@ -82,13 +90,39 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr)
 {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(PANEL_A >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand without swizzle: 8 x 16-byte core matrices, the two K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO)
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void sig_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128u(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
+{
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+// LeakyReLU on a pair, after rounding to bf16: max(x, slope * x)
+__device__ __forceinline__ uint32_t leaky_pack(uint32_t a, uint32_t b, __nv_bfloat162 slope2)
+{
+    const __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(a), __uint_as_float(b));
+    const __nv_bfloat162 h = __hmax2(x, __hmul2(x, slope2));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
@@ -98,7 +132,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    float* araw_sh = (float*)(smem + OFF_ARAW);
     float* sig_sh = (float*)(smem + OFF_SIG);
     int32_t* slot_sh = (int32_t*)(smem + OFF_SLOTID);
     const uint32_t bar0 = sbase + OFF_BAR;
@@ -133,69 +166,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
         const int et = tid;                                      // 0..255
         uint32_t ph_d[2] = {0, 0};
         const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
-        const float slope = p.slope;
+        const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
         const float ba = p.ba[0];
         long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_drain = 0, pf_t0 = 0;
         const bool prof = (p.dbg & 32) != 0;
         uint32_t tcount = 0;
 
         for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
-            bool have[2]; int nslots[2], c0[2], slr[2]; float wcr[2];
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const int tile = 2 * pc + s;
-                have[s] = tile < ntiles;
-                nslots[s] = 0; c0[s] = 0; slr[s] = -1; wcr[s] = 0.f;
-                if (have[s]) {
-                    const int2 a = p.tile_tab[tile], b = p.tile_tab[tile + 1];
-                    c0[s] = a.y; nslots[s] = b.y - a.y;
-                    if (row < b.x - a.x) {
-                        const int flat = p.tuple_src[a.x + row];
-                        wcr[s] = p.wc[flat];
-                        slr[s] = p.sample_cidx[flat / p.K] - a.y;
-                    }
-                    tcount++;
-                }
-            }
+            const int nslot_tiles = (2 * pc + 1 < ntiles) ? 2 : 1;
+            int nslots[2] = {0, 0}, c0[2] = {0, 0}, slr[2] = {-1, -1};
+            float wcr[2] = {0.f, 0.f};
+            tcount += nslot_tiles;
             for (int l = 0; l < p.n_layers; l++) {
                 const bool last = (l == p.n_layers - 1);
-                const float* bias_l = p.bias[l] + h2 * 128;
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
-                    if (!have[s]) continue;
+                    if (s >= nslot_tiles) continue;
                     if (prof) pf_t0 = clock64();
                     mbar_wait(BAR(D_FULL + s), ph_d[s]); ph_d[s] ^= 1;
                     tc_fence_after();
                     if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
+                    const uint32_t slot_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
+                    if (l == 0) {
+                        // this row's {w*conf, sample slot, first compact sample of the tile, #sample slots}, left by the gather thread
+                        const uint4 m = lds128u(slot_base + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4));
+                        wcr[s] = __uint_as_float(m.x); slr[s] = (int)m.y; c0[s] = (int)m.z; nslots[s] = (int)m.w;
+                    }
                     const uint32_t acc_addr = tmem_base + (uint32_t)(s * TC_W + h2 * 128) + lane_field;
-                    const uint32_t act_row = sbase + OFF_SLOT0 + s * SLOT_BYTES + (h2 * 2) * PANEL_A + row * 128;
-                    float araw = 0.f;
-                    // one 32-column chunk: bias + LeakyReLU (+ alpha partial) -> bf16 -> this row's 64 bytes of panel h2*2 + c/2
+                    const uint32_t act_row = slot_base + (h2 * 2) * PANEL_A + row * 128;
+                    // one 32-column chunk: (bias is part of the GEMM) LeakyReLU in bf16 -> this row's 64 bytes of panel h2*2 + c/2
                     auto chunk = [&](int c, const uint32_t(&vv)[32]) {
                         if (p.dbg & 8) return;
-                        float h[32];
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 bb = __ldg((const float4*)(bias_l + c * 32 + i));
-                            const float x0 = __uint_as_float(vv[i]) + bb.x, x1 = __uint_as_float(vv[i + 1]) + bb.y;
-                            const float x2 = __uint_as_float(vv[i + 2]) + bb.z, x3 = __uint_as_float(vv[i + 3]) + bb.w;
-                            h[i] = fmaxf(x0, x0 * slope); h[i + 1] = fmaxf(x1, x1 * slope);
-                            h[i + 2] = fmaxf(x2, x2 * slope); h[i + 3] = fmaxf(x3, x3 * slope);
-                        }
-                        if (last) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 w4 = __ldg((const float4*)(p.wa + h2 * 128 + c * 32 + i));
-                                araw = fmaf(h[i], w4.x, araw); araw = fmaf(h[i + 1], w4.y, araw);
-                                araw = fmaf(h[i + 2], w4.z, araw); araw = fmaf(h[i + 3], w4.w, araw);
-                            }
-                        }
                         const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const int ch = (c & 1) * 4 + q;
-                            sts128(rowbase + ((ch ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
-                                   pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                            sts128(rowbase + ((ch ^ (row & 7)) << 4), leaky_pack(vv[8 * q], vv[8 * q + 1], slope2), leaky_pack(vv[8 * q + 2], vv[8 * q + 3], slope2),
+                                   leaky_pack(vv[8 * q + 4], vv[8 * q + 5], slope2), leaky_pack(vv[8 * q + 6], vv[8 * q + 7], slope2));
                         }
                     };
                     uint32_t v0[32], v1[32];
@@ -209,53 +216,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                         if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
                         chunk(2 * cp + 1, v1);
                     }
-                    if (!last) {
-                        tc_fence_before();
-                        fence_proxy_async();
-                        mbar_arrive(BAR(A_READY + s));
-                        if (prof) { const long long t1 = clock64(); pf_mid += t1 - pf_t0; pf_t0 = t1; }
-                        continue;
-                    }
-                    // ---- last layer: H is in the panels; alpha, sigma terms and the selection matrix of K-sum pass 0
-                    const uint32_t sel_base = sbase + OFF_SLOT0 + s * SLOT_BYTES + 4 * PANEL_A;
-                    if (h2 == 1) araw_sh[row] = araw;
-                    {
+                    if (last) {
+                        // H is in the panels; selection matrix of K-sum pass 0 next to it: Sel[sample slot][row] = w*conf (bf16)
+                        const uint32_t sel_base = slot_base + 4 * PANEL_A;
                         const uint32_t z = sel_base + et * 64;
                         sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
-                    }
-                    epi_bar();
-                    if (h2 == 0) {
-                        const float a = araw + araw_sh[row] + ba;
-                        const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
-                        sig_sh[row] = (p.dbg & 24) ? 0.f : act * wcr[s];
-                        slot_sh[row] = slr[s];
-                        if (slr[s] >= 0 && slr[s] < KS_SLOTS) {
+                        epi_bar();
+                        if (h2 == 0 && slr[s] >= 0 && slr[s] < KS_SLOTS) {
                             const int n = slr[s];
                             const __nv_bfloat16 wb = __float2bfloat16_rn(wcr[s]);
                             sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + n * 128 + ((((row & 63) >> 3) ^ (n & 7)) << 4) + (row & 7) * 2,
                                   *reinterpret_cast<const uint16_t*>(&wb));
                         }
                     }
-                    epi_bar();
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(BAR(A_READY + s));
-                    if (h2 == 1) {
-                        // sigma of a sample = sum of its rows' terms; the thread of the sample's first row does it
-                        const int me = slot_sh[row];
-                        if (me >= 0 && (row == 0 || slot_sh[row - 1] != me)) {
-                            float sum = sig_sh[row];
-                            for (int q = row + 1; q < TC_ROWS && slot_sh[q] == me; q++) sum += sig_sh[q];
-                            p.sigma[c0[s] + me] = sum;
-                        }
-                    }
-                    if (prof) { const long long t1 = clock64(); pf_last += t1 - pf_t0; pf_t0 = t1; }
+                    if (prof) { const long long t1 = clock64(); if (last) pf_last += t1 - pf_t0; else pf_mid += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
-            // ---- drain the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F[c0 + slot][feature]
+            // ---- alpha / sigma, and the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F[c0 + slot][feature]
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                if (!have[s]) continue;
+                if (s >= nslot_tiles) continue;
                 const int npass = (nslots[s] + KS_SLOTS - 1) / KS_SLOTS;
                 const int f = h2 * 128 + quad * 32 + lane;
                 const uint32_t sel_base = sbase + OFF_SLOT0 + s * SLOT_BYTES + 4 * PANEL_A;
@@ -263,6 +246,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                     if (prof) pf_t0 = clock64();
                     mbar_wait(BAR(D_FULL + s), ph_d[s]); ph_d[s] ^= 1;
                     tc_fence_after();
+                    if (pass == 0 && h2 == 0) {
+                        // sigma of a sample = sum over its rows of w*conf*act(alpha); alpha came out of the alpha_branch MMA
+                        const float a = __uint_as_float(tc_ld1(tmem_base + (uint32_t)(s * TC_W + ALPHA_COL) + lane_field)) + ba;
+                        const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
+                        sig_sh[row] = (p.dbg & 24) ? 0.f : act * wcr[s];
+                        slot_sh[row] = slr[s];
+                        sig_bar();
+                        const int me = slr[s];
+                        if (me >= 0 && (row == 0 || slot_sh[row - 1] != me)) {
+                            float sum = sig_sh[row];
+                            for (int q = row + 1; q < TC_ROWS && slot_sh[q] == me; q++) sum += sig_sh[q];
+                            p.sigma[c0[s] + me] = sum;
+                        }
+                        sig_bar();
+                    }
                     const int ns = min(KS_SLOTS, nslots[s] - pass * KS_SLOTS);
                     float* fcol = p.F + (size_t)(c0[s] + pass * KS_SLOTS) * TC_W + f;
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_SLOTS) + lane_field;
@@ -297,88 +295,94 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
             }
         }
         if (prof && blockIdx.x == 0 && lane == 0)
-            printf("epi warp %d: tiles %u wait %lld hidden %lld last %lld drain %lld (cycles/tile)\n", warp, tcount, pf_wait / max(tcount, 1u),
+            printf("epi warp %d: tiles %u (of %d) wait %lld hidden %lld last %lld drain %lld (cycles/tile)\n", warp, tcount, ntiles, pf_wait / max(tcount, 1u),
                    pf_mid / max(tcount, 1u), pf_last / max(tcount, 1u), pf_drain / max(tcount, 1u));
     } else if (warp < TC_PRODUCER_WARP) {
-        // =========================================================== GATHER: one thread per row
-        const int row = tid - TC_GATHER_WARP0 * 32;
-        uint32_t ph_free[2] = {1, 1};
+        // =========================================================== GATHER: warps 8-11 feed slot 0, warps 12-15 slot 1; one thread per row
+        const int s = (warp - TC_GATHER_WARP0) >> 2;
+        const int row = tid - (TC_GATHER_WARP0 + 4 * s) * 32;
+        uint32_t ph_free = 1;
         const float* Rm = p.in.camrot;
         const float r00 = Rm[0], r01 = Rm[1], r02 = Rm[2], r10 = Rm[3], r11 = Rm[4], r12 = Rm[5], r20 = Rm[6], r21 = Rm[7], r22 = Rm[8];
         const float cpx = p.in.campos[0], cpy = p.in.campos[1], cpz = p.in.campos[2];
         long long gf_load = 0, gf_wait = 0, gf_write = 0, gf_t0 = 0;
         const bool prof = (p.dbg & 32) != 0;
         uint32_t tcount = 0;
+        const uint32_t x0 = sbase + OFF_SLOT0 + s * SLOT_BYTES;
+        const uint32_t one_one = pack_bf16(1.0f, 1.0f);
         for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
-#pragma unroll 1
-            for (int s = 0; s < 2; s++) {
-                const int tile = 2 * pc + s;
-                if (tile >= ntiles) continue;
-                tcount++;
-                if (prof) gf_t0 = clock64();
-                const int2 ta = p.tile_tab[tile], tb = p.tile_tab[tile + 1];
-                const bool live = row < tb.x - ta.x && !(p.dbg & 4);
-                float dist[6], e7[8];
+            const int tile = 2 * pc + s;
+            if (tile >= ntiles) continue;
+            tcount++;
+            if (prof) gf_t0 = clock64();
+            // ---- everything that does not need the slot: indices, point data, PE(dists), [colour | dir-view | dir.view], in registers
+            const int2 ta = p.tile_tab[tile], tb = p.tile_tab[tile + 1];
+            const bool live = row < tb.x - ta.x && !(p.dbg & 4);
+            uint32_t pe[32], e7p[4] = {0u, 0u, 0u, 0u};
+            float wcv = 0.f; int slot = -1;
+            const uint8_t* src = p.ptab;
+            if (live) {
+                const int flat = p.tuple_src[ta.x + row];
+                const int64_t sm = flat / p.K;
+                const int64_t r = sm / p.SR;
+                const int64_t pt = p.in.pidx[flat];
+                src = p.ptab + (size_t)pt * TC_PT_BYTES;
+                prefetch_l2(src); prefetch_l2(src + 128); prefetch_l2(src + 256); prefetch_l2(src + 384);
+                wcv = p.wc[flat];
+                slot = p.sample_cidx[sm] - ta.y;
+                float dist[6];
+                const float px = p.in.tab.xyz[3 * pt], py = p.in.tab.xyz[3 * pt + 1], pz = p.in.tab.xyz[3 * pt + 2];
+                dist[0] = px - p.in.loc_w[3 * sm]; dist[1] = py - p.in.loc_w[3 * sm + 1]; dist[2] = pz - p.in.loc_w[3 * sm + 2];
+                const float sx = px - cpx, sy = py - cpy, sz = pz - cpz;
+                const float c0 = sx * r00 + sy * r10 + sz * r20, c1 = sx * r01 + sy * r11 + sz * r21, c2 = sx * r02 + sy * r12 + sz * r22;
+                const float xp = c0 / c2, yp = c1 / c2;
+                const float lxp = p.loc_pers[3 * sm], lyp = p.loc_pers[3 * sm + 1], lzp = p.loc_pers[3 * sm + 2];
+                dist[3] = xp * c2 - lxp * lzp; dist[4] = yp * c2 - lyp * lzp; dist[5] = c2 - lzp;
+                const float vx = p.in.raydir[3 * r], vy = p.in.raydir[3 * r + 1], vz = p.in.raydir[3 * r + 2];
+                const float dx = p.in.tab.dir[3 * pt], dy = p.in.tab.dir[3 * pt + 1], dz = p.in.tab.dir[3 * pt + 2];
+                e7p[0] = pack_bf16(p.in.tab.color[3 * pt], p.in.tab.color[3 * pt + 1]);
+                e7p[1] = pack_bf16(p.in.tab.color[3 * pt + 2], dx - vx);
+                e7p[2] = pack_bf16(dy - vy, dz - vz);
+                e7p[3] = pack_bf16(dx * vx + dy * vy + dz * vz, 1.0f);
+                // pe[d*FD + f] = (sin, cos)(dist_d * 2^f): base angle by sincosf, octaves by the double-angle recurrence
 #pragma unroll
-                for (int i = 0; i < 6; i++) dist[i] = 0.f;
+                for (int d = 0; d < 6; d++) {
+                    float sn, cs_;
+                    __sincosf(dist[d], &sn, &cs_);
 #pragma unroll
-                for (int i = 0; i < 8; i++) e7[i] = 0.f;
-                int64_t pt = 0;
-                if (live) {
-                    const int flat = p.tuple_src[ta.x + row];
-                    const int64_t sm = flat / p.K;
-                    const int64_t r = sm / p.SR;
-                    pt = p.in.pidx[flat];
-                    const float px = p.in.tab.xyz[3 * pt], py = p.in.tab.xyz[3 * pt + 1], pz = p.in.tab.xyz[3 * pt + 2];
-                    dist[0] = px - p.in.loc_w[3 * sm]; dist[1] = py - p.in.loc_w[3 * sm + 1]; dist[2] = pz - p.in.loc_w[3 * sm + 2];
-                    const float sx = px - cpx, sy = py - cpy, sz = pz - cpz;
-                    const float c0 = sx * r00 + sy * r10 + sz * r20, c1 = sx * r01 + sy * r11 + sz * r21, c2 = sx * r02 + sy * r12 + sz * r22;
-                    const float xp = c0 / c2, yp = c1 / c2;
-                    const float lxp = p.loc_pers[3 * sm], lyp = p.loc_pers[3 * sm + 1], lzp = p.loc_pers[3 * sm + 2];
-                    dist[3] = xp * c2 - lxp * lzp; dist[4] = yp * c2 - lyp * lzp; dist[5] = c2 - lzp;
-                    const float vx = p.in.raydir[3 * r], vy = p.in.raydir[3 * r + 1], vz = p.in.raydir[3 * r + 2];
-                    const float dx = p.in.tab.dir[3 * pt], dy = p.in.tab.dir[3 * pt + 1], dz = p.in.tab.dir[3 * pt + 2];
-                    e7[0] = p.in.tab.color[3 * pt]; e7[1] = p.in.tab.color[3 * pt + 1]; e7[2] = p.in.tab.color[3 * pt + 2];
-                    e7[3] = dx - vx; e7[4] = dy - vy; e7[5] = dz - vz; e7[6] = dx * vx + dy * vy + dz * vz;
-                }
-                if (prof) { const long long t1 = clock64(); gf_load += t1 - gf_t0; gf_t0 = t1; }
-                mbar_wait(BAR(BUF_FREE + s), ph_free[s]); ph_free[s] ^= 1;
-                if (prof) { const long long t1 = clock64(); gf_wait += t1 - gf_t0; gf_t0 = t1; }
-                const uint32_t x0 = sbase + OFF_SLOT0 + s * SLOT_BYTES;
-                if (live) {
-                    // cols [0,224): the point's precomputed row, 28 x 16 bytes
-                    const uint8_t* src = p.ptab + (size_t)pt * TC_PT_BYTES;
-#pragma unroll
-                    for (int i = 0; i < TC_PT_BYTES / 16; i++) cp_async16(x0 + sw_off(row, 8 * i), src + 16 * i);
-                    // cols 224 + 2*(d*FD + f) + {0: sin, 1: cos}: base angle by sincosf, octaves by the double-angle recurrence
-#pragma unroll
-                    for (int d = 0; d < 6; d++) {
-                        float sn, cs_;
-                        __sincosf(dist[d], &sn, &cs_);
-#pragma unroll
-                        for (int f = 0; f < TC_FD; f++) {
-                            sts32(x0 + sw_off(row, TC_PT_COLS + 2 * (d * TC_FD + f)), pack_bf16(sn, cs_));
-                            const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
-                            sn = s2; cs_ = c2;
-                        }
+                    for (int f = 0; f < TC_FD; f++) {
+                        pe[d * TC_FD + f] = pack_bf16(sn, cs_);
+                        const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
+                        sn = s2; cs_ = c2;
                     }
-                    sts32(x0 + sw_off(row, TC_K0), 0u); sts32(x0 + sw_off(row, TC_K0 + 2), 0u);      // cols 284..287 = 0
-                    const int col = 4 * 64 + E7_COL0;
-                    sts128(x0 + sw_off(row, col), pack_bf16(e7[0], e7[1]), pack_bf16(e7[2], e7[3]), pack_bf16(e7[4], e7[5]), pack_bf16(e7[6], 0.f));
-                    sts128(x0 + sw_off(row, col + 8), 0u, 0u, 0u, 0u);
-                } else {
-                    // dead row: all-zero operand (what is left in the slot from the previous tile must not reach the MMAs)
-#pragma unroll
-                    for (int i = 0; i < (4 * 64 + E7_COL0 + 16) / 8; i++) sts128(x0 + sw_off(row, 8 * i), 0u, 0u, 0u, 0u);
                 }
-                cp_async_wait_all();
-                fence_proxy_async();
-                mbar_arrive(BAR(X_FULL + s));
-                if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
+                pe[30] = one_one; pe[31] = 0u;                                   // cols 284, 285 = 1 (bias columns), 286, 287 = 0
             }
+            if (prof) { const long long t1 = clock64(); gf_load += t1 - gf_t0; gf_t0 = t1; }
+            mbar_wait(BAR(BUF_FREE + s), ph_free); ph_free ^= 1;
+            if (prof) { const long long t1 = clock64(); gf_wait += t1 - gf_t0; gf_t0 = t1; }
+            if (live) {
+                // cols [0,224): the point's precomputed row, 28 x 16 bytes; cols [224,288): PE(dists) + bias columns; [288,304): E7 | 1 | 1
+#pragma unroll
+                for (int i = 0; i < TC_PT_BYTES / 16; i++) cp_async16(x0 + sw_off(row, 8 * i), src + 16 * i);
+#pragma unroll
+                for (int q = 0; q < 8; q++) sts128(x0 + sw_off(row, TC_PT_COLS + 8 * q), pe[4 * q], pe[4 * q + 1], pe[4 * q + 2], pe[4 * q + 3]);
+                const int col = 4 * 64 + E7_COL0;
+                sts128(x0 + sw_off(row, col), e7p[0], e7p[1], e7p[2], e7p[3]);
+                sts128(x0 + sw_off(row, col + 8), pack_bf16(1.0f, 0.f), 0u, 0u, 0u);
+            } else {
+                // dead row: all-zero operand (what is left in the slot from the previous tile must not reach the MMAs)
+#pragma unroll
+                for (int i = 0; i < (4 * 64 + E7_COL0 + 16) / 8; i++) sts128(x0 + sw_off(row, 8 * i), 0u, 0u, 0u, 0u);
+            }
+            sts128(x0 + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4), __float_as_uint(wcv), (uint32_t)slot, (uint32_t)ta.y, (uint32_t)(tb.y - ta.y));
+            cp_async_wait_all();
+            fence_proxy_async();
+            mbar_arrive(BAR(X_FULL + s));
+            if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
         }
         if (prof && blockIdx.x == 0 && lane == 0)
-            printf("gather warp %d: tiles %u issue-loads %lld wait-slot %lld copy+expand %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u),
+            printf("gather warp %d: tiles %u prepare %lld wait-slot %lld copy %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u),
                    gf_wait / max(tcount, 1u), gf_write / max(tcount, 1u));
     } else if (warp == TC_PRODUCER_WARP) {
         // =========================================================== PRODUCER: weight panels through the ring, once per (layer, slot)
@@ -386,17 +390,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
             uint32_t ph_empty[B_STAGES];
             for (int s = 0; s < B_STAGES; s++) ph_empty[s] = 1;
             uint32_t n = 0;
+            auto push = [&](const uint8_t* srcp, uint32_t bytes) {
+                const int st = n % B_STAGES;
+                mbar_wait(BAR(W_EMPTY + st), ph_empty[st]); ph_empty[st] ^= 1;
+                n++;
+                if (p.dbg & 1) { mbar_arrive(BAR(W_FULL + st)); return; }
+                mbar_expect_tx(BAR(W_FULL + st), bytes);
+                bulk_g2s(sbase + OFF_WRING + st * PANEL_B, srcp, bytes, BAR(W_FULL + st));
+            };
             for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
                 const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
                 for (int l = 0; l < p.n_layers; l++)
-                    for (int s = 0; s < nslot; s++)
-                        for (int pi = p.first_panel[l]; pi < p.first_panel[l + 1]; pi++, n++) {
-                            const int st = n % B_STAGES;
-                            mbar_wait(BAR(W_EMPTY + st), ph_empty[st]); ph_empty[st] ^= 1;
-                            if (p.dbg & 1) { mbar_arrive(BAR(W_FULL + st)); continue; }
-                            mbar_expect_tx(BAR(W_FULL + st), PANEL_B);
-                            bulk_g2s(sbase + OFF_WRING + st * PANEL_B, p.wpack + (size_t)pi * PANEL_B, PANEL_B, BAR(W_FULL + st));
-                        }
+                    for (int s = 0; s < nslot; s++) {
+                        for (int pi = p.first_panel[l]; pi < p.first_panel[l + 1]; pi++) push(p.wpack + (size_t)pi * PANEL_B, PANEL_B);
+                        if (p.bpack[l]) push(p.bpack[l], BIAS_PANEL_B);
+                    }
+                for (int s = 0; s < nslot; s++) push(p.apack, ALPHA_PANEL_B);
             }
         }
     } else {
@@ -406,6 +415,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
             for (int s = 0; s < B_STAGES; s++) ph_full[s] = 0;
             uint32_t ph_x[2] = {0, 0}, ph_a[2] = {1, 1};
             uint32_t n = 0;
+            auto next_stage = [&]() -> uint32_t {
+                const int st = n % B_STAGES;
+                mbar_wait(BAR(W_FULL + st), ph_full[st]); ph_full[st] ^= 1;
+                tc_fence_after();
+                return (uint32_t)st;
+            };
             for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
                 const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
                 int npass[2] = {0, 0};
@@ -421,27 +436,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                         if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X_FULL + s), ph_x[s]); ph_x[s] ^= 1; }
                         tc_fence_after();
                         uint32_t acc = 0;
-                        for (int kp = 0; kp < np; kp++, n++) {
-                            const int st = n % B_STAGES;
-                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
+                        for (int kp = 0; kp < np; kp++) {
                             uint32_t a_addr = a_base + kp * PANEL_A;
                             int ksteps = 4;
                             if (kp == 4) {
                                 if (kind == LAYER_FROM_X0) ksteps = 2;                                   // cols 256..287
-                                else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view] of block3.0
+                                else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view | 1 | 1] of block3.0
                             }
-                            mbar_wait(BAR(W_FULL + st), ph_full[st]); ph_full[st] ^= 1;
-                            tc_fence_after();
+                            const uint32_t st = next_stage();
+                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
                             for (int k = 0; k < ksteps; k++) {
                                 tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), IDESC_LAYER, acc);
                                 acc = 1;
                             }
-                            tc_commit(BAR(W_EMPTY + st));
+                            tc_commit(BAR(W_EMPTY + st)); n++;
+                        }
+                        if (p.bpack[l]) {
+                            // bias: one more K-step, A = the operand columns that hold (.., 1, 1, 0, 0), B = the compact bias panel
+                            const uint32_t st = next_stage();
+                            tc_mma(d_tmem, umma_desc(a_base + 4 * PANEL_A + ONES_KSTEP * 32), umma_desc_nosw(sbase + OFF_WRING + st * PANEL_B), IDESC_LAYER, 1u);
+                            tc_commit(BAR(W_EMPTY + st)); n++;
                         }
                         tc_commit(BAR(D_FULL + s));
                     }
                 }
-                // K-weighted sums: F^T[256 features (two M = 128 halves)][64 sample slots] = H^T x Sel^T, K = the tile's 128 rows
+                // alpha = H x wa^T (N = 16, column 0), then the K-weighted sums
+                // F^T[256 features (two M = 128 halves)][64 sample slots] = H^T x Sel^T, K = the tile's 128 rows
                 for (int s = 0; s < nslot; s++) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
                     const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
@@ -449,6 +469,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                     for (int pass = 0; pass < npass[s]; pass++) {
                         mbar_wait(BAR(A_READY + s), ph_a[s]); ph_a[s] ^= 1;
                         tc_fence_after();
+                        if (pass == 0) {
+                            const uint32_t st = next_stage();
+                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
+                            for (int kp = 0; kp < 4; kp++)
+                                for (int k = 0; k < 4; k++)
+                                    tc_mma(d_tmem + ALPHA_COL, umma_desc(a_base + kp * PANEL_A + k * 32), umma_desc(b_addr + kp * (ALPHA_N * 128) + k * 32),
+                                           IDESC_ALPHA, (kp | k) != 0);
+                            tc_commit(BAR(W_EMPTY + st)); n++;
+                        }
                         for (int half = 0; half < 2; half++)
                             for (int ks = 0; ks < TC_ROWS / 16; ks++)
                                 tc_mma(d_tmem + (uint32_t)(half * KS_SLOTS), umma_desc_mn(a_base + (2 * half) * PANEL_A + ks * 2048),
@@ -709,23 +738,6 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// torch Linear weight [N=256, K_in] fp32 -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (32 KB each)
-__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, int Kin, int npanels, uint8_t* __restrict__ out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 bf16)
-    if (i >= npanels * Nrows * 8) return;
-    const int ch = i & 7, n = (i >> 3) % Nrows, pnl = i / (Nrows * 8);
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const int k = pnl * 64 + ch * 8 + 2 * e;
-        const float a = k < Kin ? W[(size_t)n * Kin + k] : 0.f, b = (k + 1) < Kin ? W[(size_t)n * Kin + k + 1] : 0.f;
-        w[e] = pack_bf16(a, b);
-    }
-    uint4* dst = (uint4*)(out + (size_t)pnl * Nrows * 128 + n * 128 + ((ch ^ (n & 7)) << 4));
-    *dst = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 // Per-point operand rows: ptab[p] = bf16 [emb (32) | sin, cos of emb_c * 2^f, (c, f) major (192)] -- exactly the first 224
 // columns of the reference's `feat` (point_aggregators.py:603-611).  One warp per point, lane = channel.
 __global__ void __launch_bounds__(256) tc_point_rows_kernel(const float* __restrict__ emb, int64_t N, uint8_t* __restrict__ ptab)
@@ -765,6 +777,42 @@ __global__ void tc_tile_kernel(const int32_t* __restrict__ S_ptr, int S_max, con
     }
 }
 
+// torch Linear weight [Nvalid, K_in] fp32 -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (Nrows x 128 bytes each).
+// With `bias`, columns K_in and K_in + 1 carry the bias split into two bf16 (hi + lo): the matching operand columns hold 1.0.
+__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, int Nvalid, int Kin, int npanels, const float* __restrict__ bias,
+                                      uint8_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 bf16)
+    if (i >= npanels * Nrows * 8) return;
+    const int ch = i & 7, n = (i >> 3) % Nrows, pnl = i / (Nrows * 8);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = pnl * 64 + ch * 8 + e;
+        float x = 0.f;
+        if (n < Nvalid) {
+            if (k < Kin) x = W[(size_t)n * Kin + k];
+            else if (bias && k == Kin) x = __bfloat162float(__float2bfloat16_rn(bias[n]));
+            else if (bias && k == Kin + 1) x = bias[n] - __bfloat162float(__float2bfloat16_rn(bias[n]));
+        }
+        v[e] = x;
+    }
+    uint4* dst = (uint4*)(out + (size_t)pnl * Nrows * 128 + n * 128 + ((ch ^ (n & 7)) << 4));
+    *dst = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// Compact bias K-step [256 x 16] bf16, K-major without swizzle (8 x 16-byte core matrices: offset(n, k) = (n/8)*256 + (k/8)*128 + (n%8)*16
+// + (k%8)*2): bias hi / lo at k = 12, 13 -- the positions of the 1.0 columns inside operand K-step ONES_KSTEP of panel 4.
+__global__ void tc_pack_bias_kernel(const float* __restrict__ bias, uint8_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= TC_W * 16) return;
+    const int n = i >> 4, k = i & 15;
+    const float hi = __bfloat162float(__float2bfloat16_rn(bias[n]));
+    const float x = k == 12 ? hi : (k == 13 ? bias[n] - hi : 0.f);
+    *(__nv_bfloat16*)(out + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = __float2bfloat16_rn(x);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-case (every slot valid) workspace
 
@@ -772,7 +820,7 @@ struct TcWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles;
     int2* tile_tab;
     float *loc_pers, *weight_n, *wc, *F, *sigma;
-    uint8_t *wpack, *cpack, *ptab;
+    uint8_t *wpack, *cpack, *ptab, *bpack, *apack;
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
@@ -794,6 +842,8 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
     ws->cpack = A.take<uint8_t>((size_t)C_W_PANELS * C_PANEL);
+    ws->bpack = A.take<uint8_t>((size_t)TC_MAX_LAYERS * BIAS_PANEL_B);
+    ws->apack = A.take<uint8_t>(ALPHA_PANEL_B);
     ws->ptab = A.take<uint8_t>((size_t)N * TC_PT_BYTES);
     return A.off;
 }
@@ -860,10 +910,17 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     for (int t = 0; t < P.n_tuple_layers; t++) {
         const LayerInfo& L = P.layers[t];
         const int np = (L.in + 63) / 64;
-        launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], TC_W, L.in, np, ws.wpack + (size_t)tp.first_panel[t] * PANEL_B);
-        tp.first_panel[t + 1] = tp.first_panel[t] + np;
         tp.kind[t] = t == 0 ? LAYER_FROM_X0 : (L.extra == EXTRA_COLORDIR ? LAYER_FROM_ACT_E7 : LAYER_FROM_ACT);
-        tp.bias[t] = biases[t];
+        // the bias rides in the weight panel where the operand has spare columns (first layer, colour/dir layer), else in its own K-step
+        const bool folded = tp.kind[t] != LAYER_FROM_ACT;
+        launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], TC_W, TC_W, L.in, np, folded ? biases[t] : (const float*)nullptr,
+               ws.wpack + (size_t)tp.first_panel[t] * PANEL_B);
+        tp.first_panel[t + 1] = tp.first_panel[t] + np;
+        tp.bpack[t] = nullptr;
+        if (!folded) {
+            tp.bpack[t] = ws.bpack + (size_t)t * BIAS_PANEL_B;
+            launch(tc_pack_bias_kernel, cdiv(TC_W * 16, 256), 256, 0, st, biases[t], ws.bpack + (size_t)t * BIAS_PANEL_B);
+        }
     }
     ColParams cp = {};
     {
@@ -871,16 +928,18 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         for (int c = 0; c < P.n_color_hidden; c++) {
             const int l = P.color_layer0 + c;
             const int np = c == 0 ? C_K0_PANELS : 2;
-            launch(tc_pack_weight_kernel, cdiv((int64_t)np * CW * 8, 256), 256, 0, st, weights[l], CW, P.layers[l].in, np, ws.cpack + (size_t)pnl * C_PANEL);
+            launch(tc_pack_weight_kernel, cdiv((int64_t)np * CW * 8, 256), 256, 0, st, weights[l], CW, CW, P.layers[l].in, np, (const float*)nullptr,
+                   ws.cpack + (size_t)pnl * C_PANEL);
             pnl += np;
             cp.bias[c] = biases[l];
         }
     }
+    launch(tc_pack_weight_kernel, cdiv((int64_t)4 * ALPHA_N * 8, 256), 256, 0, st, weights[P.alpha_layer], ALPHA_N, 1, TC_W, 4, (const float*)nullptr, ws.apack);
     launch(tc_point_rows_kernel, cdiv(tables->N, 8), 256, 0, st, tables->embedding, tables->N, ws.ptab);
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
     tp.wpack = ws.wpack; tp.ptab = ws.ptab;
-    tp.wa = weights[P.alpha_layer]; tp.ba = biases[P.alpha_layer];
+    tp.apack = ws.apack; tp.ba = biases[P.alpha_layer];
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;
     { const char* e = getenv("SGN_TC_DEBUG"); tp.dbg = e ? atoi(e) : 0; }
