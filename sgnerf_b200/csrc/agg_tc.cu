@@ -81,9 +81,18 @@ struct TcParams {
     int first_panel[TC_MAX_LAYERS + 1];
     const float* ba;
     float slope; int act_super;
-    float* F; float* sigma;                // outputs per compact sample: [S][256], [S]
+    uint8_t* F; float* sigma;              // outputs per compact sample: F (bf16, colour-kernel operand image, see f_image_off), sigma [S]
     int dbg;                               // SGN_TC_DEBUG bitmask (timing experiments only; results invalid when != 0)
 };
+
+// K-weighted feature sums F[c][f] are stored as the colour kernel's first-layer A operand: per 128 compact samples four
+// 16 KB panels (64 features each) in the 128B-swizzled K-major shared-memory image, so that kernel loads them with plain bulk copies.
+constexpr int F_TILE_BYTES = 4 * TC_PANEL_BYTES;
+__device__ __forceinline__ size_t f_image_off(int c, int f)
+{
+    const int r = c & 127;
+    return (size_t)(c >> 7) * F_TILE_BYTES + (f >> 6) * TC_PANEL_BYTES + r * 128 + ((((f & 63) >> 3) ^ (r & 7)) << 4) + (f & 7) * 2;
+}
 
 // A operand read MN-major (M = 64-element atoms 16 KB apart (LBO), K = 8-row groups 1 KB apart (SBO)), 128-byte swizzle
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr)
@@ -98,6 +107,12 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(r));
+    return r != 0;
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                         sig_bar();
                     }
                     const int ns = min(KS_SLOTS, nslots[s] - pass * KS_SLOTS);
-                    float* fcol = p.F + (size_t)(c0[s] + pass * KS_SLOTS) * TC_W + f;
+                    const int cbase = c0[s] + pass * KS_SLOTS;
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_SLOTS) + lane_field;
 #pragma unroll 1
                     for (int j = 0; j < KS_SLOTS / 32; j++) {
@@ -272,7 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                         if (!(p.dbg & 16)) {
 #pragma unroll
                             for (int i = 0; i < 32; i++)
-                                if (32 * j + i < ns) fcol[(size_t)(32 * j + i) * TC_W] = __uint_as_float(v[i]);
+                                if (32 * j + i < ns) *(__nv_bfloat16*)(p.F + f_image_off(cbase + 32 * j + i, f)) = __float2bfloat16_rn(__uint_as_float(v[i]));
                         }
                     }
                     tc_fence_before();
@@ -409,31 +424,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
             }
         }
     } else {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
-            uint32_t ph_full[B_STAGES];
-            for (int s = 0; s < B_STAGES; s++) ph_full[s] = 0;
-            uint32_t ph_x[2] = {0, 0}, ph_a[2] = {1, 1};
+        // =========================================================== MMA issuer: the whole warp walks the (warp-uniform) schedule, one
+        // elected lane issues each tcgen05 instruction -- keeps descriptors and addresses on the uniform datapath
+        {
+            uint32_t ph_full = 0, ph_x = 0, ph_a = 3;                       // phase bits, one per stage / slot
             uint32_t n = 0;
             auto next_stage = [&]() -> uint32_t {
-                const int st = n % B_STAGES;
-                mbar_wait(BAR(W_FULL + st), ph_full[st]); ph_full[st] ^= 1;
+                const uint32_t st = n % B_STAGES;
+                mbar_wait(BAR(W_FULL + st), (ph_full >> st) & 1u); ph_full ^= 1u << st;
                 tc_fence_after();
-                return (uint32_t)st;
+                return st;
+            };
+            auto release_stage = [&](uint32_t st) {
+                if (elect_one()) tc_commit(BAR(W_EMPTY + st));
+                n++;
             };
             for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
                 const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
-                int npass[2] = {0, 0};
-                for (int s = 0; s < nslot; s++)
-                    npass[s] = (p.tile_tab[2 * pc + s + 1].y - p.tile_tab[2 * pc + s].y + KS_SLOTS - 1) / KS_SLOTS;
+                int npass0 = (p.tile_tab[2 * pc + 1].y - p.tile_tab[2 * pc].y + KS_SLOTS - 1) / KS_SLOTS, npass1 = 0;
+                if (nslot == 2) npass1 = (p.tile_tab[2 * pc + 2].y - p.tile_tab[2 * pc + 1].y + KS_SLOTS - 1) / KS_SLOTS;
                 for (int l = 0; l < p.n_layers; l++) {
                     const int np = p.first_panel[l + 1] - p.first_panel[l];
                     const int kind = p.kind[l];
+                    const bool own_bias_step = p.bpack[l] != nullptr;
                     for (int s = 0; s < nslot; s++) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
                         const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
-                        mbar_wait(BAR(A_READY + s), ph_a[s]); ph_a[s] ^= 1;
-                        if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X_FULL + s), ph_x[s]); ph_x[s] ^= 1; }
+                        mbar_wait(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
+                        if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X_FULL + s), (ph_x >> s) & 1u); ph_x ^= 1u << s; }
                         tc_fence_after();
                         uint32_t acc = 0;
                         for (int kp = 0; kp < np; kp++) {
@@ -444,20 +462,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                                 else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view | 1 | 1] of block3.0
                             }
                             const uint32_t st = next_stage();
-                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
+                            uint64_t ad = umma_desc(a_addr), bd = umma_desc(sbase + OFF_WRING + st * PANEL_B);
                             for (int k = 0; k < ksteps; k++) {
-                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), IDESC_LAYER, acc);
-                                acc = 1;
+                                if (elect_one()) tc_mma(d_tmem, ad, bd, IDESC_LAYER, acc);
+                                acc = 1; ad += 2; bd += 2;                                               // next K-step: +32 bytes
                             }
-                            tc_commit(BAR(W_EMPTY + st)); n++;
+                            release_stage(st);
                         }
-                        if (p.bpack[l]) {
+                        if (own_bias_step) {
                             // bias: one more K-step, A = the operand columns that hold (.., 1, 1, 0, 0), B = the compact bias panel
                             const uint32_t st = next_stage();
-                            tc_mma(d_tmem, umma_desc(a_base + 4 * PANEL_A + ONES_KSTEP * 32), umma_desc_nosw(sbase + OFF_WRING + st * PANEL_B), IDESC_LAYER, 1u);
-                            tc_commit(BAR(W_EMPTY + st)); n++;
+                            if (elect_one())
+                                tc_mma(d_tmem, umma_desc(a_base + 4 * PANEL_A + ONES_KSTEP * 32), umma_desc_nosw(sbase + OFF_WRING + st * PANEL_B), IDESC_LAYER, 1u);
+                            release_stage(st);
                         }
-                        tc_commit(BAR(D_FULL + s));
+                        if (elect_one()) tc_commit(BAR(D_FULL + s));
                     }
                 }
                 // alpha = H x wa^T (N = 16, column 0), then the K-weighted sums
@@ -466,25 +485,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                     const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
                     const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
                     const uint32_t sel = a_base + 4 * PANEL_A;
-                    for (int pass = 0; pass < npass[s]; pass++) {
-                        mbar_wait(BAR(A_READY + s), ph_a[s]); ph_a[s] ^= 1;
+                    const int npass = s == 0 ? npass0 : npass1;
+                    for (int pass = 0; pass < npass; pass++) {
+                        mbar_wait(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
                         tc_fence_after();
                         if (pass == 0) {
                             const uint32_t st = next_stage();
                             const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
-                            for (int kp = 0; kp < 4; kp++)
-                                for (int k = 0; k < 4; k++)
-                                    tc_mma(d_tmem + ALPHA_COL, umma_desc(a_base + kp * PANEL_A + k * 32), umma_desc(b_addr + kp * (ALPHA_N * 128) + k * 32),
-                                           IDESC_ALPHA, (kp | k) != 0);
-                            tc_commit(BAR(W_EMPTY + st)); n++;
+                            for (int kp = 0; kp < 4; kp++) {
+                                uint64_t ad = umma_desc(a_base + kp * PANEL_A), bd = umma_desc(b_addr + kp * (ALPHA_N * 128));
+                                for (int k = 0; k < 4; k++) {
+                                    if (elect_one()) tc_mma(d_tmem + ALPHA_COL, ad, bd, IDESC_ALPHA, (kp | k) != 0);
+                                    ad += 2; bd += 2;
+                                }
+                            }
+                            release_stage(st);
                         }
-                        for (int half = 0; half < 2; half++)
-                            for (int ks = 0; ks < TC_ROWS / 16; ks++)
-                                tc_mma(d_tmem + (uint32_t)(half * KS_SLOTS), umma_desc_mn(a_base + (2 * half) * PANEL_A + ks * 2048),
-                                       umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
-                        tc_commit(BAR(D_FULL + s));
+                        for (int half = 0; half < 2; half++) {
+                            uint64_t ad = umma_desc_mn(a_base + (2 * half) * PANEL_A);
+                            for (int ks = 0; ks < TC_ROWS / 16; ks++) {
+                                if (elect_one())
+                                    tc_mma(d_tmem + (uint32_t)(half * KS_SLOTS), ad, umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
+                                ad += 2048 >> 4;                                                         // next 16 rows of the tile
+                            }
+                        }
+                        if (elect_one()) tc_commit(BAR(D_FULL + s));
                     }
-                    tc_commit(BAR(BUF_FREE + s));
+                    if (elect_one()) tc_commit(BAR(BUF_FREE + s));
                 }
             }
         }
@@ -496,9 +523,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
 // ================================================================================================ colour branch
 // Per-sample colour MLP on tensor cores (point_aggregators.py:298-309 raw2out_color, :771-786): one persistent CTA per SM,
 // tile = 128 compact samples.  All hidden-layer weights stay resident in shared memory (bf16, 128B-swizzled K-major
-// panels); the A operand of the first layer is streamed: loader warps read the fp32 K-sums F[c, 0:256] written by the
-// per-neighbour kernel, round to bf16 and write 16 KB swizzled panels into a 2-stage ring, the fifth panel holds the
-// view-direction encoding.  The 128-wide activations live in place in two panels; the last Linear (128 -> 3), the
+// panels); the A operand of the first layer is streamed: the per-neighbour kernel left the K-sums F as bf16 in exactly the
+// swizzled panel image, so four bulk copies (TMA) per tile bring them into a 2-stage ring (the next tile is prefetched into
+// L2 meanwhile); the fifth panel, the view-direction encoding, is computed by the loader warps.  The 128-wide activations live in place in two panels; the last Linear (128 -> 3), the
 // sigmoid and the (sigma, r, g, b) store are fused into the last epilogue.
 //   warps 0-3 epilogue | warps 4-7 loaders | warp 8 MMA issuer (and the one-off weight load)
 constexpr int CW = 128;                                   // colour hidden width
@@ -520,7 +547,7 @@ constexpr uint32_t C_IDESC = tc_idesc(TC_ROWS, CW);
 struct ColParams {
     const int32_t* S_ptr; int S_max;
     const int32_t* csample;            // compact sample -> sample
-    const float* F;                    // [S][256] K-weighted feature sums per compact sample
+    const uint8_t* F;                  // K-weighted feature sums per compact sample, bf16 operand image (f_image_off)
     const float* sigma;                // [S]
     const float* raydir; int SR;
     const uint8_t* wpack;              // packed hidden-layer weights, C_PANEL each, layer after layer
@@ -552,7 +579,7 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
 
     if (tid == 0) {
         mbar_init(BAR(W_FULL), 1);
-        for (int s = 0; s < C_RING; s++) { mbar_init(BAR(R_FULL + s), 128); mbar_init(BAR(R_EMPTY + s), 1); }
+        for (int s = 0; s < C_RING; s++) { mbar_init(BAR(R_FULL + s), 1); mbar_init(BAR(R_EMPTY + s), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -630,31 +657,31 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
             }
         }
     } else if (warp < 8) {
-        // =========================================================== LOADERS: F (fp32, global) -> bf16 ring panels
+        // =========================================================== LOADERS: F panels by bulk copy, view-direction panel computed
         const int lt = tid - 128;
-        const int sub = lt & 15, rgrp = lt >> 4;              // 16 threads per row (float4 each), 8 rows per pass
         uint32_t ph_empty[C_RING];
         for (int s = 0; s < C_RING; s++) ph_empty[s] = 1;
         uint32_t n = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t c0 = (int64_t)tile * TC_ROWS;
+            if (lt == 0 && tile + (int)gridDim.x < ntiles) {
+                const uint8_t* nxt = p.F + (size_t)(tile + gridDim.x) * F_TILE_BYTES;
+                for (int i = 0; i < 4; i++)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + i * C_PANEL), "r"((uint32_t)C_PANEL) : "memory");
+            }
             for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
                 const int s = n % C_RING;
                 const uint32_t base = sbase + COFF_RING + s * C_PANEL;
                 if (kp < 4) {
-                    float4 f[16];
-#pragma unroll
-                    for (int pass = 0; pass < 16; pass++) {
-                        const int r = pass * 8 + rgrp;
-                        f[pass] = (c0 + r < Sv && !(p.dbg & 128)) ? __ldg((const float4*)(p.F + (size_t)(c0 + r) * TC_W + kp * 64 + sub * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (lt == 0) {
+                        mbar_wait(BAR(R_EMPTY + s), ph_empty[s]);
+                        if (p.dbg & 128) mbar_arrive(BAR(R_FULL + s));
+                        else {
+                            mbar_expect_tx(BAR(R_FULL + s), C_PANEL);
+                            bulk_g2s(base, p.F + (size_t)tile * F_TILE_BYTES + kp * C_PANEL, C_PANEL, BAR(R_FULL + s));
+                        }
                     }
-                    mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
-#pragma unroll
-                    for (int pass = 0; pass < 16; pass++) {
-                        const int r = pass * 8 + rgrp;
-                        const uint32_t a = base + r * 128 + (((sub >> 1) ^ (r & 7)) << 4) + (sub & 1) * 8;
-                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(pack_bf16(f[pass].x, f[pass].y)), "r"(pack_bf16(f[pass].z, f[pass].w)) : "memory");
-                    }
+                    ph_empty[s] ^= 1;
                 } else {
                     // view-direction encoding (ori=True, first three stripped): sin(v_d 2^f) d-major, then the cosines; cols [6 fv, 32) = 0
                     const int r = lt;
@@ -682,9 +709,10 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                     for (int q = 0; q < 4; q++)
                         sts128(base + r * 128 + ((q ^ (r & 7)) << 4), pack_bf16(vals[8 * q], vals[8 * q + 1]), pack_bf16(vals[8 * q + 2], vals[8 * q + 3]),
                                pack_bf16(vals[8 * q + 4], vals[8 * q + 5]), pack_bf16(vals[8 * q + 6], vals[8 * q + 7]));
+                    fence_proxy_async();
+                    asm volatile("bar.sync 3, 128;" ::: "memory");
+                    if (lt == 0) mbar_arrive(BAR(R_FULL + s));
                 }
-                fence_proxy_async();
-                mbar_arrive(BAR(R_FULL + s));
             }
         }
     } else {
@@ -819,15 +847,14 @@ constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-cas
 struct TcWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles;
     int2* tile_tab;
-    float *loc_pers, *weight_n, *wc, *F, *sigma;
-    uint8_t *wpack, *cpack, *ptab, *bpack, *apack;
+    float *loc_pers, *weight_n, *wc, *sigma;
+    uint8_t *wpack, *cpack, *ptab, *bpack, *apack, *F;
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
 
 static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
 {
-    const AggDims& d = P.dims;
     Arena A(base, cap);
     const size_t S = (size_t)Rc * SR, T = S * K;
     ws->nvalid = A.take<int32_t>(S + 1); ws->svalid = A.take<int32_t>(S + 1);
@@ -837,7 +864,7 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     ws->ntiles = A.take<int32_t>(4);
     ws->tile_tab = A.take<int2>(T / tile_width(K) + 3);
     ws->loc_pers = A.take<float>(S * 3); ws->weight_n = A.take<float>(T); ws->wc = A.take<float>(T);
-    ws->F = A.take<float>((S + 1) * d.W); ws->sigma = A.take<float>(S + 1);
+    ws->F = A.take<uint8_t>((S / TC_ROWS + 2) * F_TILE_BYTES); ws->sigma = A.take<float>(S + 1);
     size_t panels = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
