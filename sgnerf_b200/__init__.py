@@ -6,4 +6,4 @@ Importing the package does not need a GPU; every compute call does (there is no 
 """
 __version__ = "0.1.0"
 
-from . import _lib, ops, pipeline, synth  # noqa: F401
+from . import _lib, dist, modules, ops, pipeline, synth  # noqa: F401

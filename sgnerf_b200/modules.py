@@ -1,0 +1,395 @@
+"""Reference-shaped modules over the C ABI: `lighting_fast_querier`, `NeuralPoints`, `PointAggregator`, `ray_march`,
+`alpha_ray_march` -- same names, argument lists, return tuples and state_dict keys as the reference classes they replace:
+
+    lighting_fast_querier   models/neural_points/query_point_indices_worldcoords.py:47-132
+    NeuralPoints            models/neural_points/neural_points.py:77, :312-420 (ctor), :520-665 (prune/grow/set_*), :942-988 (forward)
+    PointAggregator         models/aggregators/point_aggregators.py:12, :256-296 (ctor), :312-418 (viewmlp_init), :868-959 (forward)
+    ray_march               models/rendering/diff_ray_marching.py:509-555, alpha_ray_march :558-573
+
+They are drop-ins for models/neural_points_volumetric_model.py.  Only the canonical branch of the
+reference is built (which_agg_model=viewmlp, agg_distance_kernel=linear, agg_dist_pers=20, agg_intrp_order=2,
+wcoord_query=1, near_far_linear ray generation, radiance render, alpha/alpha2 blend); any other option raises.  All arithmetic
+runs in libsgnerf_b200.so -- there is no PyTorch fallback, CPU tensors are rejected.
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, pipeline
+
+
+def _opt(opt, name, default):
+    return getattr(opt, name, default)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# lazy gathers
+# ---------------------------------------------------------------------------------------------------------
+class GatheredRows:
+    """Stand-in for one of NeuralPoints.forward's gathered tensors ([1,R,SR,K,C] = table[clamp(pidx,0)],
+    neural_points.py:956-972).  The fused aggregator never needs the dense tensor; `.materialize()` (or
+    torch.as_tensor(handle.materialize())) builds it with sgn_gather_rows for code that does."""
+
+    def __init__(self, ctx, table, cols=None):
+        self.ctx, self.table, self.cols = ctx, table, cols
+
+    @property
+    def shape(self):
+        C = self.table.shape[-1] if self.cols is None else self.cols.stop - self.cols.start
+        return torch.Size(tuple(self.ctx.pidx.shape) + (C,))
+
+    def materialize(self):
+        t = self.table.reshape(-1, self.table.shape[-1])
+        out = ops.gather_rows(t.detach(), self.ctx.pidx.clamp(min=0))
+        if self.cols is not None:
+            out = out[..., self.cols]
+        return out
+
+
+class GatheredPers(GatheredRows):
+    """sampled_xyz_pers: the gathered points in camera-perspective coordinates (neural_points.py:762, :838-850)."""
+
+    def materialize(self):
+        xyz = super().materialize()                                            # [1,R,SR,K,3]
+        c = self.ctx
+        flat = lighting_fast_querier.w2pers(xyz.reshape(1, -1, 3), c.camrotc2w[None], c.campos[None])
+        return flat.reshape(xyz.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# querier
+# ---------------------------------------------------------------------------------------------------------
+class lighting_fast_querier:
+    """World-coordinate voxel-grid querier.  The occupancy grid is built once per point-cloud version (keyed on the
+    tensor's storage and version counter) instead of once per call."""
+
+    def __init__(self, device, opt):
+        self.device, self.opt = device, opt
+        self._grid, self._grid_key, self._hp = None, None, None
+        if _opt(opt, "wcoord_query", 1) <= 0:
+            raise NotImplementedError("sgnerf_b200: only the world-coordinate querier (--wcoord_query 1) is built")
+        if _opt(opt, "inverse", 0) > 0:
+            raise NotImplementedError("sgnerf_b200: --inverse ray generation is not built")
+
+    def clean_up(self):                      # a no-op in the reference too (query_point_indices_worldcoords.py:62-64)
+        pass
+
+    def invalidate(self):
+        if self._grid is not None:
+            self._grid.close()
+        self._grid, self._grid_key, self._hp = None, None, None
+
+    def _get_grid(self, xyz):
+        key = (xyz.data_ptr(), xyz._version, tuple(xyz.shape))
+        if self._grid is None or key != self._grid_key:
+            self.invalidate()
+            o = self.opt
+            self._hp = ops.grid_hyperparameters(xyz, o.vsize, o.vscale, o.kernel_size, _opt(o, "ranges", None), o.radius_limit_scale)
+            self._grid = ops.OccGrid(xyz, self._hp.ranges[:3], self._hp.scaled_vsize, self._hp.scaled_vdim, o.query_size, o.P, o.max_o)
+            self._grid_key = key
+        return self._grid, self._hp
+
+    @staticmethod
+    def w2pers(point_xyz_w, camrotc2w, campos):
+        shift = point_xyz_w - campos[:, None, :]
+        c = torch.sum(shift[..., None, :] * torch.transpose(camrotc2w, 1, 2)[:, None, None, ...], dim=-1)
+        return torch.stack([c[..., 0] / c[..., 2], c[..., 1] / c[..., 2], c[..., 2]], dim=-1)
+
+    def query_uncompacted(self, point_xyz_w_tensor, near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor,
+                          points_label_tensor=None, points_label_prob_tensor=None, ray_label_tensor=None, t=None):
+        """Row r of the outputs belongs to input ray r (no host synchronisation).  Used by the fused path."""
+        o = self.opt
+        xyz = point_xyz_w_tensor.reshape(-1, 3)
+        grid, hp = self._get_grid(xyz)
+        raydir = ray_dirs_tensor.reshape(-1, 3)
+        if t is None:
+            jitter = 0.3 if _opt(o, "is_train", 0) > 0 else 0.0
+            t = pipeline.middle_point_ts(float(near_depth), float(far_depth), o.z_depth_dim, raydir.device, jitter=jitter,
+                                         n_rays=raydir.shape[0])
+        kw = {}
+        if _opt(o, "semantic_guidance", 0) == 1:
+            prob = points_label_prob_tensor.reshape(-1, points_label_prob_tensor.shape[-1])
+            kw = dict(ray_label=ray_label_tensor.reshape(-1).to(torch.int32), pt_label=points_label_tensor.reshape(-1).to(torch.int32),
+                      pt_label_prob_bits=prob.view(torch.int32) if prob.is_floating_point() else prob.to(torch.int32))
+        pidx, loc_w, smask, rmask = ops.query(grid, cam_pos_tensor.reshape(3), raydir, t, o.SR, o.K, o.kernel_size[0], hp.radius2, **kw)
+        return pidx, loc_w, smask, rmask, hp
+
+    def query_points(self, pixel_idx_tensor, point_xyz_pers_tensor, point_xyz_w_tensor, actual_numpoints_tensor, h, w, intrinsic,
+                     near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor, cam_rot_tensor, pixel_label_tensor=None,
+                     points_label_tensor=None, points_label_prob_tensor=None, ray_label_tensor=None):
+        near_depth, far_depth = np.asarray(near_depth).item(), np.asarray(far_depth).item()
+        pidx, loc_w, _, rmask, hp = self.query_uncompacted(point_xyz_w_tensor, near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor,
+                                                           points_label_tensor, points_label_prob_tensor, ray_label_tensor)
+        sel = rmask > 0                                           # the reference compacts the rays with >= 1 neighbour (:946-952)
+        sample_pidx = pidx[sel][None]
+        sample_loc_w = loc_w[sel][None]
+        sample_ray_dirs = ray_dirs_tensor.reshape(-1, 3)[sel][None, :, None, :].expand(-1, -1, self.opt.SR, -1).contiguous()
+        sample_loc = self.w2pers(sample_loc_w, cam_rot_tensor, cam_pos_tensor)
+        return (sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, rmask[None], np.asarray(hp.vsize, dtype=np.float32), hp.ranges)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NeuralPoints
+# ---------------------------------------------------------------------------------------------------------
+class NeuralPoints(nn.Module):
+    @staticmethod
+    def modify_commandline_options(parser, is_train=True):
+        """The reference's own NeuralPoints.modify_commandline_options registers these flags (neural_points.py:80-310);
+        when this class replaces it the option parser still imports the reference's method, so nothing is added here."""
+        return parser
+
+    def __init__(self, num_channels, size, opt, device, checkpoint=None, feature_init_method='rand', reg_weight=0., feedforward=0):
+        super().__init__()
+        self.opt, self.device = opt, device
+        self.grid_vox_sz = 0
+        self.points_conf = self.points_dir = self.points_color = self.eulers = None
+        self.points_label = self.points_label_prob = self.bpnet_points_embedding = self.points_feats = None
+        self.Rw2c = torch.eye(3, device=device, dtype=torch.float32)
+        self.reg_weight = reg_weight
+        self.querier = lighting_fast_querier(device, opt)
+        if checkpoint:
+            saved = torch.load(checkpoint, map_location=device) if isinstance(checkpoint, str) else checkpoint
+            g = lambda k: saved.get("neural_points." + k)
+            self.xyz = nn.Parameter(g("xyz").to(device))
+            for name in ("points_embeding", "points_conf", "points_dir", "points_color", "eulers"):
+                v = g(name)
+                setattr(self, name, nn.Parameter(v.to(device)) if v is not None else None)
+            if g("Rw2c") is not None:
+                self.Rw2c = nn.Parameter(g("Rw2c").to(device))
+        elif feedforward:
+            self.xyz, self.points_embeding = None, None        # filled by set_points (MVS feed-forward initialisation)
+        else:
+            # feature_init_method == 'rand': U(-.5, .5) (neural_points.py:386); the cloud itself arrives through set_points
+            n = int(size)
+            self.xyz = nn.Parameter(torch.zeros(n, 3, device=device))
+            emb = torch.rand(1, n, num_channels, device=device) - 0.5 if feature_init_method == 'rand' else torch.zeros(1, n, num_channels, device=device)
+            self.points_embeding = nn.Parameter(emb)
+        if self.xyz is not None:
+            self.xyz.requires_grad = _opt(opt, "xyz_grad", 0) > 0
+
+    # ---- point-cloud edits: every one of them moves the tensors, so the querier's grid key changes on its own ----
+    def reset_querier(self):
+        self.querier.clean_up()
+        self.querier.invalidate()
+
+    def set_points(self, points_xyz, points_feats, points_embeding, points_label=None, points_color=None, points_dir=None,
+                   points_conf=None, points_semantic=None, parameter=False, Rw2c=None, eulers=None):
+        wrap = (lambda t, grad=True: nn.Parameter(t, requires_grad=grad)) if parameter else (lambda t, grad=True: t)
+        three = lambda t: None if t is None else (t if t.dim() == 3 else t[None, ...])
+        self.xyz = wrap(points_xyz.reshape(-1, 3), _opt(self.opt, "xyz_grad", 0) > 0)
+        self.points_feats = None if points_feats is None else wrap(points_feats, False)
+        self.points_label = None if points_label is None else wrap(points_label, False)
+        self.points_embeding = wrap(three(points_embeding))
+        self.points_conf = None if points_conf is None else wrap(three(points_conf))
+        self.points_dir = None if points_dir is None else wrap(three(points_dir))
+        self.points_color = None if points_color is None else wrap(three(points_color))
+        self.eulers = None if eulers is None else wrap(eulers, False)
+        if Rw2c is not None:
+            self.Rw2c = wrap(Rw2c, False)
+        self.reset_querier()
+
+    def editing_set_points(self, points_xyz, points_embeding, points_color=None, points_dir=None, points_conf=None, parameter=False,
+                           Rw2c=None, eulers=None):
+        self.set_points(points_xyz, None, points_embeding, points_color=points_color, points_dir=points_dir, points_conf=points_conf,
+                        parameter=parameter, Rw2c=Rw2c, eulers=eulers)
+
+    def set_bpnet_feats(self, points_label_prob, points_label, bpnet_points_embedding):
+        self.points_label_prob = points_label_prob
+        self.points_label = points_label
+        self.bpnet_points_embedding = bpnet_points_embedding if bpnet_points_embedding.dim() == 3 else bpnet_points_embedding[None, ...]
+
+    def prune(self, thresh):
+        mask = self.points_conf[0, :, 0] >= thresh
+        self.xyz = nn.Parameter(self.xyz[mask, :], requires_grad=self.xyz.requires_grad)
+        for name in ("points_embeding", "points_conf", "points_dir", "points_color"):
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, nn.Parameter(t[:, mask, :]))
+        if self.points_label is not None:
+            self.points_label = self.points_label[mask]
+        self.reset_querier()
+
+    def grow_points(self, add_xyz, add_embedding, add_color, add_dir, add_conf, add_label=None, add_eulers=None, add_Rw2c=None):
+        self.xyz = nn.Parameter(torch.cat([self.xyz, add_xyz], dim=0), requires_grad=self.xyz.requires_grad)
+        cat = lambda cur, add: nn.Parameter(torch.cat([cur, add[None, ...] if add.dim() == 2 else add], dim=1))
+        if self.points_embeding is not None:
+            self.points_embeding = cat(self.points_embeding, add_embedding)
+        if self.points_conf is not None:
+            self.points_conf = cat(self.points_conf, add_conf)
+        if self.points_dir is not None:
+            self.points_dir = cat(self.points_dir, add_dir)
+        if self.points_color is not None:
+            self.points_color = cat(self.points_color, add_color)
+        if self.points_label is not None and add_label is not None:
+            self.points_label = torch.cat([self.points_label, add_label], dim=0)
+        self.reset_querier()
+
+    def getPointsData(self):
+        return self.xyz.data.cpu().numpy().copy(), None if self.points_feats is None else self.points_feats.data.cpu().numpy().copy()
+
+    def null_grad(self):
+        for name in ("points_embeding", "xyz"):
+            t = getattr(self, name)
+            if t is not None:
+                t.grad = None
+
+    def reg_loss(self):
+        return self.reg_weight * torch.mean(torch.pow(self.points_embeding, 2))
+
+    def w2pers(self, point_xyz, camrotc2w, campos):
+        return lighting_fast_querier.w2pers(point_xyz[None, ...] if point_xyz.dim() == 2 else point_xyz, camrotc2w, campos)
+
+    def forward(self, inputs):
+        camrotc2w, campos = inputs["camrotc2w"], inputs["campos"]
+        near, far = float(torch.min(inputs["near"])), float(torch.max(inputs["far"]))
+        raydir = inputs["raydir"]
+        if _opt(self.opt, "NN", 2) < 0:
+            raise NotImplementedError("sgnerf_b200: query_vox_grid (NN < 0) is not built")
+        semantic = _opt(self.opt, "semantic_guidance", 0) == 1 or _opt(self.opt, "predict_semantic", 0) == 1
+        kw = {}
+        if _opt(self.opt, "semantic_guidance", 0) == 1:
+            kw = dict(points_label_tensor=self.points_label, points_label_prob_tensor=self.points_label_prob,
+                      ray_label_tensor=inputs["pixel_label"])
+        pidx_u, loc_w_u, _, rmask, hp = self.querier.query_uncompacted(self.xyz, near, far, raydir, campos, **kw)
+        sel = rmask > 0                                          # host sync, as in the reference (:946); the fused frame path avoids it
+        sample_pidx = pidx_u[sel][None].contiguous()
+        sample_loc_w = loc_w_u[sel][None].contiguous()
+        rd = raydir.reshape(-1, 3)[sel]
+        sample_ray_dirs = rd[None, :, None, :].expand(-1, -1, self.opt.SR, -1).contiguous()
+        sample_loc = lighting_fast_querier.w2pers(sample_loc_w, camrotc2w, campos)
+        ctx = SimpleNamespace(neural_points=self, pidx=sample_pidx, loc_w=sample_loc_w, raydir=rd.contiguous(), campos=campos.reshape(3),
+                              camrotc2w=camrotc2w.reshape(3, 3), vsize=hp.vsize)
+        xyz_tab = self.xyz[None, ...]
+        g = lambda table, cols=None: None if table is None else GatheredRows(ctx, table, cols)
+        sampled_label_embedding = g(self.bpnet_points_embedding) if semantic and self.bpnet_points_embedding is not None else None
+        ctx.use_label = sampled_label_embedding is not None
+        vsize = np.asarray(hp.vsize, dtype=np.float32)
+        return (g(self.points_color), sampled_label_embedding, self.Rw2c, g(self.points_dir), g(self.points_conf), g(self.points_embeding),
+                GatheredPers(ctx, xyz_tab), g(xyz_tab), sample_pidx >= 0, sample_loc, sample_loc_w, sample_ray_dirs, rmask[None], vsize,
+                self.grid_vox_sz)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# PointAggregator
+# ---------------------------------------------------------------------------------------------------------
+def _init_seq(seq, slope):
+    """Xavier-uniform initialisation of helpers/networks.py:120-172 (init_seq): gain('leaky_relu', slope) for a Linear
+    followed by the activation, gain 1 for the last module of the Sequential; biases 0."""
+    mods = list(seq)
+
+    def xavier(m, gain):
+        if isinstance(m, nn.Linear):
+            fan_out, fan_in = m.weight.shape
+            std = gain * math.sqrt(2.0 / (fan_in + fan_out))
+            m.weight.data.uniform_(-std * math.sqrt(3.0), std * math.sqrt(3.0))
+            if m.bias is not None:
+                m.bias.data.zero_()
+    for a, b in zip(mods[:-1], mods[1:]):
+        xavier(a, nn.init.calculate_gain('leaky_relu', slope) if isinstance(b, nn.LeakyReLU) else 1.0)
+    xavier(mods[-1], 1.0)
+
+
+class PointAggregator(nn.Module):
+    @staticmethod
+    def modify_commandline_options(parser, is_train=True):
+        return parser                      # flags are registered by the reference's own method (point_aggregators.py:15-254)
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        if _opt(opt, "which_agg_model", "viewmlp") != "viewmlp" or _opt(opt, "agg_distance_kernel", "linear") != "linear":
+            raise NotImplementedError("sgnerf_b200: only which_agg_model=viewmlp with agg_distance_kernel=linear is built")
+        if _opt(opt, "agg_dist_pers", 20) != 20 or _opt(opt, "agg_intrp_order", 2) != 2 or _opt(opt, "act_type", "LeakyReLU") != "LeakyReLU":
+            raise NotImplementedError("sgnerf_b200: canonical agg_dist_pers=20 / agg_intrp_order=2 / LeakyReLU only")
+        if _opt(opt, "shading_feature_mlp_layer2", 0) != 0 or _opt(opt, "shading_feature_mlp_layer0", 0) != 0:
+            raise NotImplementedError("sgnerf_b200: block0 / block2 (shading_feature_mlp_layer0/2) are not built")
+        slope = 0.01
+        C, W = opt.point_features_dim, opt.shading_feature_num
+        self.label_dim = 96 if _opt(opt, "shading_feature_mlp_layer2_bpnet", 0) > 0 else 0
+        in_ch = C + 2 * opt.num_feat_freqs * C + 2 * opt.dist_xyz_freq * 6
+        seqs = []
+
+        def mlp(cin, widths, final_act):
+            mods = []
+            for i, w in enumerate(widths):
+                mods.append(nn.Linear(cin, w))
+                if final_act or i < len(widths) - 1:
+                    mods.append(nn.LeakyReLU(slope, inplace=True))
+                cin = w
+            return nn.Sequential(*mods)
+        self.block1 = mlp(in_ch, [W] * opt.shading_feature_mlp_layer1, True); seqs.append(self.block1)
+        n2 = _opt(opt, "shading_feature_mlp_layer2_bpnet", 0)
+        if n2 > 0:
+            self.block2_bpnet = mlp(W + self.label_dim, [W] * n2, True); seqs.append(self.block2_bpnet)
+        self.block3 = mlp(W + 3 + 4, [W] * opt.shading_feature_mlp_layer3, True); seqs.append(self.block3)
+        na = opt.shading_alpha_mlp_layer
+        if na != 1:
+            raise NotImplementedError("sgnerf_b200: shading_alpha_mlp_layer must be 1")
+        self.alpha_branch = mlp(W, [1], False); seqs.append(self.alpha_branch)
+        nc = opt.shading_color_mlp_layer
+        self.color_branch = mlp(W + 2 * opt.num_viewdir_freqs * 3, [W // 2] * (nc - 1) + [3], False); seqs.append(self.color_branch)
+        for s in seqs:
+            _init_seq(s, slope)
+        self.cfg = ops.agg_cfg(feat_dim=C, num_feat_freqs=opt.num_feat_freqs, dist_xyz_freq=opt.dist_xyz_freq,
+                               num_viewdir_freqs=opt.num_viewdir_freqs, width=W, n_block1=opt.shading_feature_mlp_layer1,
+                               n_block2_bpnet=n2, label_dim=self.label_dim, n_block3=opt.shading_feature_mlp_layer3, n_color=nc,
+                               act_super=_opt(opt, "act_super", 1), leaky_slope=slope)
+
+    def _linears(self):
+        seqs = [self.block1] + ([self.block2_bpnet] if hasattr(self, "block2_bpnet") else []) + [self.block3, self.alpha_branch, self.color_branch]
+        return [m for s in seqs for m in s if isinstance(m, nn.Linear)]
+
+    def forward(self, sampled_color, sampled_label_embedding, sampled_Rw2c, sampled_dir, sampled_conf, sampled_embedding, sampled_xyz_pers,
+                sampled_xyz, sample_pnt_mask, sample_loc, sample_loc_w, sample_ray_dirs, vsize, grid_vox_sz):
+        if not isinstance(sampled_embedding, GatheredRows):
+            raise TypeError("sgnerf_b200.PointAggregator takes the handles returned by sgnerf_b200.NeuralPoints.forward (fused gather); "
+                            "dense gathered tensors are not accepted and there is no PyTorch fallback")
+        ctx = sampled_embedding.ctx
+        npnts = ctx.neural_points
+        lin = self._linears()
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        precision = ops.PRECISION_FP32 if (training or self.label_dim > 0 or _opt(self.opt, "sgn_precision", "auto") == "fp32") else ops.PRECISION_BF16
+        opt = self.opt
+        want = not ((_opt(opt, "sparse_loss_weight", 0) <= 0) and ("conf_coefficient" not in _opt(opt, "zero_one_loss_items", "")) and _opt(opt, "prob", 0) == 0)
+        label = npnts.bpnet_points_embedding[0] if (self.label_dim > 0 and npnts.bpnet_points_embedding is not None) else None
+        decoded, ray_valid, _, weight, conf = ops.aggregate(
+            self.cfg, [m.weight for m in lin], [m.bias for m in lin], npnts.xyz, npnts.points_embeding[0], npnts.points_color[0],
+            npnts.points_dir[0], None if npnts.points_conf is None else npnts.points_conf[0, :, 0], label, ctx.pidx[0], ctx.loc_w[0],
+            ctx.raydir, ctx.campos, ctx.camrotc2w, precision=precision, want_aux=want)
+        out = (decoded[None], ray_valid[None].bool(), weight[None] if want else None, conf[None] if want else None)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ray marching
+# ---------------------------------------------------------------------------------------------------------
+def _blend_id(blend_func):
+    name = getattr(blend_func, "__name__", str(blend_func))
+    if name == "alpha_blend":
+        return 0
+    if name == "alpha2_blend":
+        return 1
+    raise NotImplementedError(f"sgnerf_b200: blend function {name} is not built (alpha / alpha2 only)")
+
+
+def ray_march(ray_dist, ray_valid, ray_features, render_func, blend_func, bg_color=None):
+    """7-tuple of diff_ray_marching.py:509-555: (ray_color, point_color, opacity, acc_transmission, blend_weight[...,None],
+    background_transmission[...,None], background_blend_weight)."""
+    if getattr(render_func, "__name__", "") not in ("radiance_render",):
+        raise NotImplementedError("sgnerf_b200: only the radiance render function is built")
+    blend = _blend_id(blend_func)
+    bg = None if bg_color is None else bg_color.to(ray_features.device).float().reshape(-1)[:3]
+    ray_color, opacity, acc, bw, bgt = ops.composite(ray_features, ray_dist, ray_valid, bg, blend=blend)
+    bgt = bgt[..., None]
+    return ray_color, ray_features[..., 1:4], opacity, acc, bw[..., None], bgt, (bgt if blend == 0 else bgt * bgt)
+
+
+def alpha_ray_march(ray_dist, ray_valid, ray_features, blend_func):
+    """5-tuple of diff_ray_marching.py:558-573."""
+    blend = _blend_id(blend_func)
+    _, opacity, acc, bw, bgt = ops.composite(ray_features, ray_dist, ray_valid, None, blend=blend)
+    bgt = bgt[..., None]
+    return opacity, acc, bw[..., None], bgt, (bgt if blend == 0 else bgt * bgt)

@@ -269,7 +269,7 @@ class _Aggregate(torch.autograd.Function):
             meta.precision, meta.want_aux)
         R, SR, K = pidx.shape
         dev = pidx.device
-        need_grad = any(ctx.needs_input_grad[1:])
+        need_grad = meta.grad_enabled and any(ctx.needs_input_grad[1:])    # forward() itself always runs with grad mode off
         if need_grad and precision != PRECISION_FP32:
             raise RuntimeError("sgnerf_b200: training runs the fp32 path; the bf16 tensor-core path is forward-only")
         nbytes = C.c_size_t()
@@ -332,7 +332,8 @@ def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb
     meta = SimpleNamespace(cfg=cfg, xyz=_dev(xyz.reshape(-1, 3), f32, "xyz"), label_emb=_dev(label_emb, f32, "label_emb"),
                            pidx=_dev(pidx, torch.int32, "pidx"), loc_w=_dev(loc_w, f32, "loc_w"),
                            raydir=_dev(raydir.reshape(-1, 3), f32, "raydir"), campos=_dev(campos.reshape(3), f32, "campos"),
-                           camrot=_dev(camrotc2w.reshape(3, 3), f32, "camrotc2w"), precision=int(precision), want_aux=bool(want_aux))
+                           camrot=_dev(camrotc2w.reshape(3, 3), f32, "camrotc2w"), precision=int(precision), want_aux=bool(want_aux),
+                           grad_enabled=torch.is_grad_enabled())
     N = meta.xyz.shape[0]
     embedding = _dev(embedding.reshape(N, -1), f32, "embedding")
     color = _dev(color.reshape(N, 3), f32, "color")

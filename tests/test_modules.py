@@ -1,0 +1,133 @@
+"""Drop-in modules (sgnerf_b200/modules.py): state_dict parity on the CPU; on the GPU the reference's own call sequence
+(NeuralPointsRayMarching.forward, models/neural_points_volumetric_model.py:541-607) through our NeuralPoints / PointAggregator /
+ray_march against the oracle's render of the same scene."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import query_ref as qr
+from oracle import render_ref as rr
+
+
+def make_opt(**kw):
+    o = SimpleNamespace(
+        vsize=[0.008, 0.008, 0.008], vscale=[2, 2, 2], kernel_size=[3, 3, 3], query_size=[3, 3, 3], ranges=[-10.0, -10.0, -10.0, 10.0, 10.0, 10.0],
+        radius_limit_scale=4.0, max_o=610000, P=26, SR=24, K=8, z_depth_dim=400, NN=2, wcoord_query=1, inverse=0, is_train=0,
+        semantic_guidance=0, predict_semantic=0, xyz_grad=0,
+        which_agg_model="viewmlp", agg_distance_kernel="linear", agg_dist_pers=20, agg_intrp_order=2, act_type="LeakyReLU", act_super=1,
+        point_features_dim=32, num_feat_freqs=3, dist_xyz_freq=5, num_viewdir_freqs=4, shading_feature_num=256,
+        shading_feature_mlp_layer0=0, shading_feature_mlp_layer1=2, shading_feature_mlp_layer2=0, shading_feature_mlp_layer2_bpnet=0,
+        shading_feature_mlp_layer3=2, shading_alpha_mlp_layer=1, shading_color_mlp_layer=4, shading_color_channel_num=3,
+        sparse_loss_weight=0, zero_one_loss_items="conf_coefficient", prob=0, raydist_mode_unit=1)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+@pytest.mark.parametrize("semantic", [False, True])
+def test_state_dict_matches_reference_layout(semantic):
+    """Same keys, order and shapes as the reference PointAggregator's state_dict (point_aggregators.py:312-418): the oracle's
+    layer table is checked against the reference class itself by tests/golden/make_golden.py."""
+    from sgnerf_b200 import modules
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
+    agg = modules.PointAggregator(make_opt(shading_feature_mlp_layer2_bpnet=1 if semantic else 0))
+    sd = agg.state_dict()
+    want = []
+    for name, cin, cout in rr.layer_shapes(cfg):
+        want += [(name + ".weight", (cout, cin)), (name + ".bias", (cout,))]
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == want
+    agg.load_state_dict(rr.init_params(cfg, seed=0))          # a reference-shaped checkpoint loads unchanged
+    # init_seq statistics: biases zero, weights inside the Xavier-uniform bound
+    fresh = modules.PointAggregator(make_opt())
+    for k, v in fresh.state_dict().items():
+        if k.endswith(".bias"):
+            assert float(v.abs().max()) == 0.0
+    w = fresh.state_dict()["block1.0.weight"]
+    gain = np.sqrt(2.0 / (1 + 0.01 ** 2))
+    assert float(w.abs().max()) <= gain * np.sqrt(2.0 / (w.shape[0] + w.shape[1])) * np.sqrt(3.0) + 1e-6
+
+
+def test_unsupported_options_raise():
+    from sgnerf_b200 import modules
+    with pytest.raises(NotImplementedError):
+        modules.PointAggregator(make_opt(agg_distance_kernel="quadric"))
+    with pytest.raises(NotImplementedError):
+        modules.lighting_fast_querier("cpu", make_opt(wcoord_query=0))
+    agg = modules.PointAggregator(make_opt())
+    with pytest.raises(TypeError):            # dense tensors are not accepted: no PyTorch fallback
+        agg(*([torch.zeros(1)] * 14))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("train", [False, True])
+def test_reference_call_sequence_vs_oracle(train):
+    from sgnerf_b200 import modules, synth
+    from tests import util
+    from sgnerf_b200.modules import alpha_ray_march, ray_march
+    dev = "cuda"
+    torch.manual_seed(0)
+    s = synth.scene_c0(n_points=20_000, n_rays=300)
+    opt = make_opt()
+    cfg = rr.agg_config()
+    P = rr.init_params(cfg, seed=0, bias_scale=0.05)
+    tabs = synth.make_point_tables(s.xyz.shape[0], 32, 0, seed=0, conf_spread=0.2)
+
+    npnts = modules.NeuralPoints(32, s.xyz.shape[0], opt, dev, feedforward=1)
+    npnts.set_points(torch.from_numpy(s.xyz).to(dev), None, tabs.embedding.to(dev), points_color=tabs.color.to(dev), points_dir=tabs.dir.to(dev),
+                     points_conf=tabs.conf.to(dev), parameter=True)
+    agg = modules.PointAggregator(opt).to(dev)
+    agg.load_state_dict(P)
+    if not train:
+        agg.requires_grad_(False)
+    campos, rot = torch.from_numpy(s.campos)[None].to(dev), torch.from_numpy(s.camrotc2w)[None].to(dev)
+    raydir = torch.from_numpy(s.raydir)[None].to(dev)
+    inputs = {"pixel_idx": torch.zeros(1, raydir.shape[1], 2, device=dev), "camrotc2w": rot, "campos": campos, "near": torch.tensor([s.near]),
+              "far": torch.tensor([s.far]), "h": torch.tensor([480]), "w": torch.tensor([640]), "intrinsic": torch.eye(3)[None], "raydir": raydir,
+              "pixel_label": None}
+    ctx = torch.enable_grad() if train else torch.no_grad()
+    with ctx:
+        (sampled_color, sampled_label_embedding, sampled_Rw2c, sampled_dir, sampled_conf, sampled_embedding, sampled_xyz_pers, sampled_xyz,
+         sample_pnt_mask, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask_tensor, vsize, grid_vox_sz) = npnts(inputs)
+        decoded, ray_valid, weight, conf_coefficient = agg(sampled_color, sampled_label_embedding, sampled_Rw2c, sampled_dir, sampled_conf,
+                                                           sampled_embedding, sampled_xyz_pers, sampled_xyz, sample_pnt_mask, sample_loc,
+                                                           sample_loc_w, sample_ray_dirs, vsize, grid_vox_sz)
+        # the caller's own glue (neural_points_volumetric_model.py:569-577), kept in torch exactly as the reference has it
+        ray_dist = torch.cummax(sample_loc[..., 2], dim=-1)[0]
+        ray_dist = torch.cat([ray_dist[..., 1:] - ray_dist[..., :-1], torch.full((1, ray_dist.shape[1], 1), float(vsize[2]), device=dev)], dim=-1)
+        mask = torch.logical_or(ray_dist < 1e-8, ray_dist > 2 * float(vsize[2])).float()
+        ray_dist = (ray_dist * (1.0 - mask) + mask * float(vsize[2])) * ray_valid.float()
+        blend = lambda opacity, acc: opacity * acc
+        blend.__name__ = "alpha_blend"
+        render = lambda f: f[..., 1:4]
+        render.__name__ = "radiance_render"
+        out = ray_march(ray_dist, ray_valid, decoded, render, blend, torch.ones(1, 3, device=dev))
+    ray_color, point_color, opacity, acc_transmission, blend_weight, background_transmission, background_blend_weight = out
+    # oracle
+    t = util.shared_t(s.near, s.far, opt.z_depth_dim)
+    orc = util.oracle_query(s, qr.default_opt(SR=24), t)
+    o_pidx, o_loc, o_loc_w, o_dirs, o_mask, o_vsize, _, _ = orc
+    assert np.array_equal(ray_mask_tensor[0].cpu().numpy(), o_mask[0].numpy())
+    assert np.array_equal(sampled_embedding.ctx.pidx.cpu().numpy(), o_pidx.numpy())
+    tables = SimpleNamespace(xyz=torch.from_numpy(s.xyz), embedding=tabs.embedding, color=tabs.color, dir=tabs.dir, conf=tabs.conf, label_embedding=None)
+    ref = rr.render_from_query(P, cfg, tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, torch.from_numpy(s.camrotc2w)[None],
+                               torch.from_numpy(s.campos)[None], o_vsize, torch.ones(3))
+    sel = o_mask[0] > 0
+    tol = 1e-3 if train else 1e-2          # training runs the fp32 kernels (1e-3 bar); inference the bf16 tensor-core ones (stated 1e-2)
+    torch.testing.assert_close(ray_color[0].detach().cpu(), ref.coarse_raycolor[0][sel], rtol=0, atol=tol)
+    assert tuple(point_color.shape) == tuple(decoded.shape[:-1]) + (3,) and blend_weight.shape[-1] == 1 and background_transmission.shape[-1] == 1
+    torch.testing.assert_close(background_blend_weight, background_transmission)
+    assert weight is not None and conf_coefficient is not None and tuple(weight.shape) == tuple(sample_pnt_mask.shape)
+    # lazily gathered tensors have the reference's shapes and contents
+    emb = sampled_embedding.materialize()
+    assert tuple(emb.shape) == tuple(sample_pnt_mask.shape) + (32,)
+    want = tabs.embedding[0][o_pidx[0].clamp(min=0).long()]
+    torch.testing.assert_close(emb[0].cpu(), want)
+    a5 = alpha_ray_march(ray_dist, ray_valid, decoded.detach(), blend)
+    torch.testing.assert_close(a5[0], opacity.detach())
+    if train:
+        loss = (ray_color ** 2).mean() + 1e-4 * (conf_coefficient ** 2).mean()
+        loss.backward()
+        assert npnts.points_embeding.grad is not None and float(npnts.points_embeding.grad.abs().sum()) > 0
+        assert agg.block1[0].weight.grad is not None and npnts.xyz.grad is None
