@@ -39,31 +39,34 @@ static_assert(TC_K0 + 2 <= 4 * 64 + 32, "the two bias columns must fit in the fi
 constexpr int TC_MAX_LAYERS = 6;
 constexpr int PANEL_A = TC_PANEL_BYTES;   // 16 KB: 128 rows x 64 bf16
 constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
-constexpr int SLOT_PANELS = 5, SLOT_BYTES = SLOT_PANELS * PANEL_A, B_STAGES = 2;
+constexpr int PANEL_BH = PANEL_B / 2;     // 16 KB: this CTA's half (128 of the 256 output columns) of a weight panel
+constexpr int SLOT_PANELS = 5, SLOT_BYTES = SLOT_PANELS * PANEL_A, B_STAGES = 4;
 constexpr int E7_COL0 = 32;               // inside panel 4: cols [32,48) hold [colour | dir-view | dir.view | 1 | 1 | 0..]
 constexpr int ONES_KSTEP = 1;             // K-step of panel 4 that holds operand cols 272..287, i.e. the two 1.0 columns at 12, 13
 constexpr int META_CHUNK = 6;             // 16-byte chunk of a row of panel 4 that carries {w*conf, sample slot, first compact sample, #slots}
-constexpr int KS_SLOTS = 64;              // sample slots per K-sum pass (Sel^T = 2 K-panels x 64 x 128 B = panel 4)
-constexpr int BIAS_PANEL_B = TC_W * 32;   // 8 KB: compact (unswizzled) [256 x 16] bias K-step
-constexpr int ALPHA_N = 16;               // alpha_branch as an N = 16 MMA (row 0 = the weight vector)
-constexpr int ALPHA_PANEL_B = 4 * ALPHA_N * 128;                // 8 KB: [16 x 256] in four 128B-swizzled K panels
-constexpr int ALPHA_COL = 128;            // accumulator columns [128, 144) of the slot receive alpha
+constexpr int KS_SLOTS = 56;              // sample slots per CTA and K-sum pass (Sel^T = 2 K-panels x 56 x 128 B, inside panel 4)
+constexpr int KS_N = 2 * KS_SLOTS;        // the pair's K-sum MMA: columns [0,56) = leader CTA's samples, [56,112) = peer CTA's
+constexpr int BIAS_PANEL_B = TC_W * 32;   // 8 KB: compact (unswizzled) [256 x 16] bias K-step (4 KB per CTA)
+constexpr int ALPHA_N = 16;               // alpha_branch as an N = 16 MMA (row 0 = the weight vector; 8 rows per CTA)
+constexpr int ALPHA_PANEL_B = 4 * ALPHA_N * 128;                // 8 KB: per CTA four 1 KB K panels of 8 rows
+constexpr int ALPHA_COL = 2 * KS_N;       // accumulator columns [224, 240) of the slot receive alpha
 
 constexpr int OFF_SLOT0 = 0;
 constexpr int OFF_WRING = 2 * SLOT_BYTES;                       // 163840
-constexpr int OFF_SIG = OFF_WRING + B_STAGES * PANEL_B;         // 229376: [128] w*conf*act(alpha) per row
+constexpr int OFF_SIG = OFF_WRING + B_STAGES * PANEL_BH;        // 229376: [128] w*conf*act(alpha) per row
 constexpr int OFF_SLOTID = OFF_SIG + TC_ROWS * 4;               // [128] sample slot of the row (-1: dead row)
 constexpr int OFF_BAR = OFF_SLOTID + TC_ROWS * 4;
-constexpr int N_BARS = 2 * B_STAGES + 8;
+constexpr int N_BARS = 3 * B_STAGES + 8;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
 constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 16, TC_MMA_WARP = 17, TC_THREADS = 18 * 32;
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
-constexpr uint32_t IDESC_LAYER = tc_idesc(TC_ROWS, TC_W);
-constexpr uint32_t IDESC_ALPHA = tc_idesc(TC_ROWS, ALPHA_N);
-constexpr uint32_t IDESC_KSUM = tc_idesc(128, KS_SLOTS, 1);    // A = H^T read MN-major from the activation panels
+// cta_group::2: one MMA spans the CTA pair, M = 256 = this CTA's 128 rows + the peer's, each CTA supplies half of B's N rows
+constexpr uint32_t IDESC_LAYER = tc_idesc(2 * TC_ROWS, TC_W);
+constexpr uint32_t IDESC_ALPHA = tc_idesc(2 * TC_ROWS, ALPHA_N);
+constexpr uint32_t IDESC_KSUM = tc_idesc(256, KS_N, 1);        // A = H^T read MN-major from the activation panels
 
 struct TcParams {
     AggIn in;
@@ -104,6 +107,48 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr)
 {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
 }
+// ---- cluster (CTA pair) primitives
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier of this CTA whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    } while (!ok);
+}
+// pair-wide MMA, issued by the leader CTA only
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -140,37 +185,48 @@ __device__ __forceinline__ uint32_t leaky_pack(uint32_t a, uint32_t b, __nv_bflo
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
+// Launched as clusters of two CTAs (a CTA pair on the two SMs of a TPC).  Every CTA gathers, activates and reduces its OWN
+// tiles; only the MMAs are shared: the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2, M = 256 = its 128 rows +
+// the peer's 128 rows, and each CTA streams and holds only its half of every weight panel (N split) -- half the shared-memory
+// operand traffic and half the L2 weight traffic per SM.  Per pair-cycle a cluster works on four tiles: (slot 0|1) x (rank 0|1).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
 
     float* sig_sh = (float*)(smem + OFF_SIG);
     int32_t* slot_sh = (int32_t*)(smem + OFF_SLOTID);
     const uint32_t bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int W_FULL = 0, W_EMPTY = B_STAGES, X_FULL = 2 * B_STAGES, BUF_FREE = X_FULL + 2, D_FULL = BUF_FREE + 2, A_READY = D_FULL + 2;
+    // W_FULL / W_EMPTY / D_FULL / BUF_FREE: one per CTA.  PEER_W (the peer's weight stage has landed), X_FULL, A_READY: the
+    // leader's instances collect arrivals from both CTAs (the peer arrives through the cluster address).
+    const int W_FULL = 0, W_EMPTY = B_STAGES, PEER_W = 2 * B_STAGES, X_FULL = 3 * B_STAGES, BUF_FREE = X_FULL + 2, D_FULL = BUF_FREE + 2, A_READY = D_FULL + 2;
+    auto LEADER_BAR = [&](int i) { return map_to_cta(BAR(i), 0); };
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + OFF_TMEMPTR);
 
     const int ntiles = min(*p.ntiles_ptr, p.ntiles_cap);
-    const int npairs = (ntiles + 1) >> 1;
+    const int ncycles = (ntiles + 3) >> 2;                          // pair-cycles of the whole grid: 4 tiles each
+    const int cl0 = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
     if (tid == 0) {
-        for (int s = 0; s < B_STAGES; s++) { mbar_init(BAR(W_FULL + s), 1); mbar_init(BAR(W_EMPTY + s), 1); }
+        for (int s = 0; s < B_STAGES; s++) { mbar_init(BAR(W_FULL + s), 1); mbar_init(BAR(W_EMPTY + s), 1); mbar_init(BAR(PEER_W + s), 1); }
         for (int s = 0; s < 2; s++) {
-            mbar_init(BAR(X_FULL + s), 128); mbar_init(BAR(BUF_FREE + s), 1);
-            mbar_init(BAR(D_FULL + s), 1); mbar_init(BAR(A_READY + s), TC_EPI_WARPS * 32);
+            mbar_init(BAR(X_FULL + s), 2 * 4); mbar_init(BAR(BUF_FREE + s), 1);
+            mbar_init(BAR(D_FULL + s), 1); mbar_init(BAR(A_READY + s), 2 * TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync();                                                 // both CTAs' barriers are initialised before anyone arrives remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -179,34 +235,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
         const int quad = warp & 3, h2 = warp >> 2;
         const int row = quad * 32 + lane;
         const int et = tid;                                      // 0..255
-        uint32_t ph_d[2] = {0, 0};
+        uint32_t ph_d = 0;
         const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
         const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
         const float ba = p.ba[0];
         long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_drain = 0, pf_t0 = 0;
         const bool prof = (p.dbg & 32) != 0;
         uint32_t tcount = 0;
+        const uint32_t a_ready0 = LEADER_BAR(A_READY);
+        // this warp's part of "slot s is ready for the next MMA": every lane's writes are fenced, then one arrival for the warp
+        auto warp_ready = [&](int s) {
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a_ready0 + 8u * s);
+        };
 
-        for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
-            const int nslot_tiles = (2 * pc + 1 < ntiles) ? 2 : 1;
-            int nslots[2] = {0, 0}, c0[2] = {0, 0}, slr[2] = {-1, -1};
-            float wcr[2] = {0.f, 0.f};
-            tcount += nslot_tiles;
+        for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
+            int nslots0 = 0, nslots1 = 0, npass0 = 1, npass1 = 1, c00 = 0, c01 = 0, slr0 = -1, slr1 = -1;
+            float wcr0 = 0.f, wcr1 = 0.f;
+            tcount += 2;
             for (int l = 0; l < p.n_layers; l++) {
                 const bool last = (l == p.n_layers - 1);
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
-                    if (s >= nslot_tiles) continue;
                     if (prof) pf_t0 = clock64();
-                    mbar_wait(BAR(D_FULL + s), ph_d[s]); ph_d[s] ^= 1;
+                    mbar_wait(BAR(D_FULL + s), (ph_d >> s) & 1u); ph_d ^= 1u << s;
                     tc_fence_after();
                     if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
                     const uint32_t slot_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
                     if (l == 0) {
-                        // this row's {w*conf, sample slot, first compact sample of the tile, #sample slots}, left by the gather thread
+                        // this row's {w*conf, sample slot, first compact sample of the tile, #sample slots | K-sum passes << 16}
                         const uint4 m = lds128u(slot_base + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4));
-                        wcr[s] = __uint_as_float(m.x); slr[s] = (int)m.y; c0[s] = (int)m.z; nslots[s] = (int)m.w;
+                        if (s == 0) { wcr0 = __uint_as_float(m.x); slr0 = (int)m.y; c00 = (int)m.z; nslots0 = (int)(m.w & 0xffffu); npass0 = (int)(m.w >> 16); }
+                        else { wcr1 = __uint_as_float(m.x); slr1 = (int)m.y; c01 = (int)m.z; nslots1 = (int)(m.w & 0xffffu); npass1 = (int)(m.w >> 16); }
                     }
+                    const float wcr = s == 0 ? wcr0 : wcr1;
+                    const int slr = s == 0 ? slr0 : slr1;
                     const uint32_t acc_addr = tmem_base + (uint32_t)(s * TC_W + h2 * 128) + lane_field;
                     const uint32_t act_row = slot_base + (h2 * 2) * PANEL_A + row * 128;
                     // one 32-column chunk: (bias is part of the GEMM) LeakyReLU in bf16 -> this row's 64 bytes of panel h2*2 + c/2
@@ -237,74 +302,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                         const uint32_t z = sel_base + et * 64;
                         sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
                         epi_bar();
-                        if (h2 == 0 && slr[s] >= 0 && slr[s] < KS_SLOTS) {
-                            const int n = slr[s];
-                            const __nv_bfloat16 wb = __float2bfloat16_rn(wcr[s]);
-                            sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + n * 128 + ((((row & 63) >> 3) ^ (n & 7)) << 4) + (row & 7) * 2,
+                        if (h2 == 0 && slr >= 0 && slr < KS_SLOTS) {
+                            const __nv_bfloat16 wb = __float2bfloat16_rn(wcr);
+                            sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + slr * 128 + ((((row & 63) >> 3) ^ (slr & 7)) << 4) + (row & 7) * 2,
                                   *reinterpret_cast<const uint16_t*>(&wb));
                         }
                     }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(BAR(A_READY + s));
+                    warp_ready(s);
                     if (prof) { const long long t1 = clock64(); if (last) pf_last += t1 - pf_t0; else pf_mid += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
-            // ---- alpha / sigma, and the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F[c0 + slot][feature]
+            // ---- alpha / sigma, and the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F image
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                if (s >= nslot_tiles) continue;
-                const int npass = (nslots[s] + KS_SLOTS - 1) / KS_SLOTS;
+                const int npass = s == 0 ? npass0 : npass1, nslots = s == 0 ? nslots0 : nslots1, c0 = s == 0 ? c00 : c01, slr = s == 0 ? slr0 : slr1;
+                const float wcr = s == 0 ? wcr0 : wcr1;
                 const int f = h2 * 128 + quad * 32 + lane;
                 const uint32_t sel_base = sbase + OFF_SLOT0 + s * SLOT_BYTES + 4 * PANEL_A;
                 for (int pass = 0; pass < npass; pass++) {
                     if (prof) pf_t0 = clock64();
-                    mbar_wait(BAR(D_FULL + s), ph_d[s]); ph_d[s] ^= 1;
+                    mbar_wait(BAR(D_FULL + s), (ph_d >> s) & 1u); ph_d ^= 1u << s;
                     tc_fence_after();
                     if (pass == 0 && h2 == 0) {
                         // sigma of a sample = sum over its rows of w*conf*act(alpha); alpha came out of the alpha_branch MMA
                         const float a = __uint_as_float(tc_ld1(tmem_base + (uint32_t)(s * TC_W + ALPHA_COL) + lane_field)) + ba;
                         const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
-                        sig_sh[row] = (p.dbg & 24) ? 0.f : act * wcr[s];
-                        slot_sh[row] = slr[s];
+                        sig_sh[row] = (p.dbg & 24) ? 0.f : act * wcr;
+                        slot_sh[row] = slr;
                         sig_bar();
-                        const int me = slr[s];
-                        if (me >= 0 && (row == 0 || slot_sh[row - 1] != me)) {
+                        if (slr >= 0 && (row == 0 || slot_sh[row - 1] != slr)) {
                             float sum = sig_sh[row];
-                            for (int q = row + 1; q < TC_ROWS && slot_sh[q] == me; q++) sum += sig_sh[q];
-                            p.sigma[c0[s] + me] = sum;
+                            for (int q = row + 1; q < TC_ROWS && slot_sh[q] == slr; q++) sum += sig_sh[q];
+                            p.sigma[c0 + slr] = sum;
                         }
                         sig_bar();
                     }
-                    const int ns = min(KS_SLOTS, nslots[s] - pass * KS_SLOTS);
-                    const int cbase = c0[s] + pass * KS_SLOTS;
-                    const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_SLOTS) + lane_field;
+                    const int ns = min(KS_SLOTS, nslots - pass * KS_SLOTS);
+                    const int cbase = c0 + pass * KS_SLOTS;
+                    // this CTA's samples are columns [rank*56, rank*56+56) of each feature half's [128 x 112] block
+                    const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_N + rank * KS_SLOTS) + lane_field;
 #pragma unroll 1
-                    for (int j = 0; j < KS_SLOTS / 32; j++) {
+                    for (int j = 0; j < 2; j++) {
                         if (32 * j >= ns) break;
                         uint32_t v[32];
-                        tc_ld32(d_addr + 32 * j, v);
+                        tc_ld32(d_addr + 32 * j, v);                                  // j = 1 reads 8 columns past the 56 (in bounds, unused)
                         if (!(p.dbg & 16)) {
 #pragma unroll
                             for (int i = 0; i < 32; i++)
                                 if (32 * j + i < ns) *(__nv_bfloat16*)(p.F + f_image_off(cbase + 32 * j + i, f)) = __float2bfloat16_rn(__uint_as_float(v[i]));
                         }
                     }
-                    tc_fence_before();
                     if (pass + 1 < npass) {
-                        // next 64 sample slots: rebuild Sel (the MMA of this pass has completed, nobody reads it now)
+                        // next 56 sample slots: rebuild Sel (the MMA of this pass has completed, nobody reads it now)
                         const uint32_t z = sel_base + et * 64;
                         sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
                         epi_bar();
-                        const int n = slr[s] - (pass + 1) * KS_SLOTS;
+                        const int n = slr - (pass + 1) * KS_SLOTS;
                         if (h2 == 0 && n >= 0 && n < KS_SLOTS) {
-                            const __nv_bfloat16 wb = __float2bfloat16_rn(wcr[s]);
+                            const __nv_bfloat16 wb = __float2bfloat16_rn(wcr);
                             sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + n * 128 + ((((row & 63) >> 3) ^ (n & 7)) << 4) + (row & 7) * 2,
                                   *reinterpret_cast<const uint16_t*>(&wb));
                         }
-                        fence_proxy_async();
                     }
-                    mbar_arrive(BAR(A_READY + s));
+                    warp_ready(s);
                     if (prof) { const long long t1 = clock64(); pf_drain += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
@@ -325,13 +385,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
         uint32_t tcount = 0;
         const uint32_t x0 = sbase + OFF_SLOT0 + s * SLOT_BYTES;
         const uint32_t one_one = pack_bf16(1.0f, 1.0f);
-        for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
-            const int tile = 2 * pc + s;
-            if (tile >= ntiles) continue;
+        const uint32_t x_full = LEADER_BAR(X_FULL + s);
+        for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
+            const int tile = 4 * cyc + 2 * s + (int)rank, ptile = tile ^ 1;          // ptile: the peer CTA's tile in the same slot
             tcount++;
             if (prof) gf_t0 = clock64();
             // ---- everything that does not need the slot: indices, point data, PE(dists), [colour | dir-view | dir.view], in registers
-            const int2 ta = p.tile_tab[tile], tb = p.tile_tab[tile + 1];
+            int2 ta = make_int2(0, 0), tb = make_int2(0, 0);
+            if (tile < ntiles) { ta = p.tile_tab[tile]; tb = p.tile_tab[tile + 1]; }
+            int pslots = 0;
+            if (ptile < ntiles) pslots = p.tile_tab[ptile + 1].y - p.tile_tab[ptile].y;
+            const int nsl = tb.y - ta.y;
+            const int npass = max(1, (max(nsl, pslots) + KS_SLOTS - 1) / KS_SLOTS);   // the pair runs the same number of K-sum passes
             const bool live = row < tb.x - ta.x && !(p.dbg & 4);
             uint32_t pe[32], e7p[4] = {0u, 0u, 0u, 0u};
             float wcv = 0.f; int slot = -1;
@@ -390,68 +455,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
 #pragma unroll
                 for (int i = 0; i < (4 * 64 + E7_COL0 + 16) / 8; i++) sts128(x0 + sw_off(row, 8 * i), 0u, 0u, 0u, 0u);
             }
-            sts128(x0 + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4), __float_as_uint(wcv), (uint32_t)slot, (uint32_t)ta.y, (uint32_t)(tb.y - ta.y));
+            sts128(x0 + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4), __float_as_uint(wcv), (uint32_t)slot, (uint32_t)ta.y,
+                   (uint32_t)nsl | ((uint32_t)npass << 16));
             cp_async_wait_all();
             fence_proxy_async();
-            mbar_arrive(BAR(X_FULL + s));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(x_full);
             if (prof) { const long long t1 = clock64(); gf_write += t1 - gf_t0; gf_t0 = t1; }
         }
         if (prof && blockIdx.x == 0 && lane == 0)
             printf("gather warp %d: tiles %u prepare %lld wait-slot %lld copy %lld (cycles/tile)\n", warp, tcount, gf_load / max(tcount, 1u),
                    gf_wait / max(tcount, 1u), gf_write / max(tcount, 1u));
     } else if (warp == TC_PRODUCER_WARP) {
-        // =========================================================== PRODUCER: weight panels through the ring, once per (layer, slot)
+        // =========================================================== PRODUCER: this CTA's half of every weight panel, once per (layer, slot)
         if (lane == 0) {
-            uint32_t ph_empty[B_STAGES];
-            for (int s = 0; s < B_STAGES; s++) ph_empty[s] = 1;
+            uint32_t ph_empty = (1u << B_STAGES) - 1u;
             uint32_t n = 0;
             auto push = [&](const uint8_t* srcp, uint32_t bytes) {
-                const int st = n % B_STAGES;
-                mbar_wait(BAR(W_EMPTY + st), ph_empty[st]); ph_empty[st] ^= 1;
+                const uint32_t st = n % B_STAGES;
+                mbar_wait(BAR(W_EMPTY + st), (ph_empty >> st) & 1u); ph_empty ^= 1u << st;
                 n++;
                 if (p.dbg & 1) { mbar_arrive(BAR(W_FULL + st)); return; }
                 mbar_expect_tx(BAR(W_FULL + st), bytes);
-                bulk_g2s(sbase + OFF_WRING + st * PANEL_B, srcp, bytes, BAR(W_FULL + st));
+                bulk_g2s(sbase + OFF_WRING + st * PANEL_BH, srcp, bytes, BAR(W_FULL + st));
             };
-            for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
-                const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
+            for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
                 for (int l = 0; l < p.n_layers; l++)
-                    for (int s = 0; s < nslot; s++) {
-                        for (int pi = p.first_panel[l]; pi < p.first_panel[l + 1]; pi++) push(p.wpack + (size_t)pi * PANEL_B, PANEL_B);
-                        if (p.bpack[l]) push(p.bpack[l], BIAS_PANEL_B);
+                    for (int s = 0; s < 2; s++) {
+                        for (int pi = p.first_panel[l]; pi < p.first_panel[l + 1]; pi++) push(p.wpack + (size_t)pi * PANEL_B + rank * PANEL_BH, PANEL_BH);
+                        if (p.bpack[l]) push(p.bpack[l] + rank * (BIAS_PANEL_B / 2), BIAS_PANEL_B / 2);
                     }
-                for (int s = 0; s < nslot; s++) push(p.apack, ALPHA_PANEL_B);
+                for (int s = 0; s < 2; s++) push(p.apack + rank * (ALPHA_PANEL_B / 2), ALPHA_PANEL_B / 2);
             }
         }
+    } else if (!leader) {
+        // =========================================================== peer CTA: forward "my half of stage st has landed" to the leader
+        if (lane == 0) {
+            uint32_t ph_full = 0, n = 0;
+            const uint32_t peer_w0 = LEADER_BAR(PEER_W);
+            int per_cycle = 2;                                           // alpha panels
+            for (int l = 0; l < p.n_layers; l++) per_cycle += 2 * (p.first_panel[l + 1] - p.first_panel[l] + (p.bpack[l] ? 1 : 0));
+            for (int cyc = cl0; cyc < ncycles; cyc += ncl)
+                for (int i = 0; i < per_cycle; i++, n++) {
+                    const uint32_t st = n % B_STAGES;
+                    mbar_wait(BAR(W_FULL + st), (ph_full >> st) & 1u); ph_full ^= 1u << st;
+                    mbar_arrive_cluster(peer_w0 + 8u * st);
+                }
+        }
     } else {
-        // =========================================================== MMA issuer: the whole warp walks the (warp-uniform) schedule, one
-        // elected lane issues each tcgen05 instruction -- keeps descriptors and addresses on the uniform datapath
+        // =========================================================== leader CTA: MMA issuer for the pair.  The whole warp walks the
+        // (warp-uniform) schedule, one elected lane issues each tcgen05 instruction
         {
-            uint32_t ph_full = 0, ph_x = 0, ph_a = 3;                       // phase bits, one per stage / slot
+            uint32_t ph_full = 0, ph_peer = 0, ph_x = 0, ph_a = 3;          // phase bits, one per stage / slot
             uint32_t n = 0;
             auto next_stage = [&]() -> uint32_t {
                 const uint32_t st = n % B_STAGES;
                 mbar_wait(BAR(W_FULL + st), (ph_full >> st) & 1u); ph_full ^= 1u << st;
+                mbar_wait_cluster(BAR(PEER_W + st), (ph_peer >> st) & 1u); ph_peer ^= 1u << st;
                 tc_fence_after();
                 return st;
             };
             auto release_stage = [&](uint32_t st) {
-                if (elect_one()) tc_commit(BAR(W_EMPTY + st));
+                if (elect_one()) tc_commit2(BAR(W_EMPTY + st));
                 n++;
             };
-            for (int pc = blockIdx.x; pc < npairs; pc += gridDim.x) {
-                const int nslot = (2 * pc + 1 < ntiles) ? 2 : 1;
-                int npass0 = (p.tile_tab[2 * pc + 1].y - p.tile_tab[2 * pc].y + KS_SLOTS - 1) / KS_SLOTS, npass1 = 0;
-                if (nslot == 2) npass1 = (p.tile_tab[2 * pc + 2].y - p.tile_tab[2 * pc + 1].y + KS_SLOTS - 1) / KS_SLOTS;
+            for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
+                int npass[2];
+                for (int s = 0; s < 2; s++) {
+                    int m = 0;
+                    for (int r = 0; r < 2; r++) {
+                        const int tile = 4 * cyc + 2 * s + r;
+                        if (tile < ntiles) m = max(m, p.tile_tab[tile + 1].y - p.tile_tab[tile].y);
+                    }
+                    npass[s] = max(1, (m + KS_SLOTS - 1) / KS_SLOTS);
+                }
                 for (int l = 0; l < p.n_layers; l++) {
                     const int np = p.first_panel[l + 1] - p.first_panel[l];
                     const int kind = p.kind[l];
                     const bool own_bias_step = p.bpack[l] != nullptr;
-                    for (int s = 0; s < nslot; s++) {
+                    for (int s = 0; s < 2; s++) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
                         const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
-                        mbar_wait(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
-                        if (kind == LAYER_FROM_X0) { mbar_wait(BAR(X_FULL + s), (ph_x >> s) & 1u); ph_x ^= 1u << s; }
+                        mbar_wait_cluster(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
+                        if (kind == LAYER_FROM_X0) { mbar_wait_cluster(BAR(X_FULL + s), (ph_x >> s) & 1u); ph_x ^= 1u << s; }
                         tc_fence_after();
                         uint32_t acc = 0;
                         for (int kp = 0; kp < np; kp++) {
@@ -462,9 +548,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                                 else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view | 1 | 1] of block3.0
                             }
                             const uint32_t st = next_stage();
-                            uint64_t ad = umma_desc(a_addr), bd = umma_desc(sbase + OFF_WRING + st * PANEL_B);
+                            uint64_t ad = umma_desc(a_addr), bd = umma_desc(sbase + OFF_WRING + st * PANEL_BH);
                             for (int k = 0; k < ksteps; k++) {
-                                if (elect_one()) tc_mma(d_tmem, ad, bd, IDESC_LAYER, acc);
+                                if (elect_one()) tc_mma2(d_tmem, ad, bd, IDESC_LAYER, acc);
                                 acc = 1; ad += 2; bd += 2;                                               // next K-step: +32 bytes
                             }
                             release_stage(st);
@@ -473,29 +559,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                             // bias: one more K-step, A = the operand columns that hold (.., 1, 1, 0, 0), B = the compact bias panel
                             const uint32_t st = next_stage();
                             if (elect_one())
-                                tc_mma(d_tmem, umma_desc(a_base + 4 * PANEL_A + ONES_KSTEP * 32), umma_desc_nosw(sbase + OFF_WRING + st * PANEL_B), IDESC_LAYER, 1u);
+                                tc_mma2(d_tmem, umma_desc(a_base + 4 * PANEL_A + ONES_KSTEP * 32), umma_desc_nosw(sbase + OFF_WRING + st * PANEL_BH), IDESC_LAYER, 1u);
                             release_stage(st);
                         }
-                        if (elect_one()) tc_commit(BAR(D_FULL + s));
+                        if (elect_one()) tc_commit2(BAR(D_FULL + s));
                     }
                 }
-                // alpha = H x wa^T (N = 16, column 0), then the K-weighted sums
-                // F^T[256 features (two M = 128 halves)][64 sample slots] = H^T x Sel^T, K = the tile's 128 rows
-                for (int s = 0; s < nslot; s++) {
+                // alpha = H x wa^T (N = 16, column 0), then the K-weighted sums of both CTAs in one MMA per feature half:
+                // F^T[128 features per CTA][112 = 56 leader + 56 peer sample slots] = H^T x Sel^T, K = the tile's 128 rows;
+                // each CTA supplies its own selection matrix as its half of B and reads back only its own 56 columns.
+                for (int s = 0; s < 2; s++) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
                     const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
                     const uint32_t sel = a_base + 4 * PANEL_A;
-                    const int npass = s == 0 ? npass0 : npass1;
-                    for (int pass = 0; pass < npass; pass++) {
-                        mbar_wait(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
+                    for (int pass = 0; pass < npass[s]; pass++) {
+                        mbar_wait_cluster(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
                         tc_fence_after();
                         if (pass == 0) {
                             const uint32_t st = next_stage();
-                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_B;
+                            const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_BH;
                             for (int kp = 0; kp < 4; kp++) {
-                                uint64_t ad = umma_desc(a_base + kp * PANEL_A), bd = umma_desc(b_addr + kp * (ALPHA_N * 128));
+                                uint64_t ad = umma_desc(a_base + kp * PANEL_A), bd = umma_desc(b_addr + kp * (ALPHA_N / 2 * 128));
                                 for (int k = 0; k < 4; k++) {
-                                    if (elect_one()) tc_mma(d_tmem + ALPHA_COL, ad, bd, IDESC_ALPHA, (kp | k) != 0);
+                                    if (elect_one()) tc_mma2(d_tmem + ALPHA_COL, ad, bd, IDESC_ALPHA, (kp | k) != 0);
                                     ad += 2; bd += 2;
                                 }
                             }
@@ -505,19 +591,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __gri
                             uint64_t ad = umma_desc_mn(a_base + (2 * half) * PANEL_A);
                             for (int ks = 0; ks < TC_ROWS / 16; ks++) {
                                 if (elect_one())
-                                    tc_mma(d_tmem + (uint32_t)(half * KS_SLOTS), ad, umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
+                                    tc_mma2(d_tmem + (uint32_t)(half * KS_N), ad, umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
                                 ad += 2048 >> 4;                                                         // next 16 rows of the tile
                             }
                         }
-                        if (elect_one()) tc_commit(BAR(D_FULL + s));
+                        if (elect_one()) tc_commit2(BAR(D_FULL + s));
                     }
-                    if (elect_one()) tc_commit(BAR(BUF_FREE + s));
+                    if (elect_one()) tc_commit2(BAR(BUF_FREE + s));
                 }
             }
         }
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == TC_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    cluster_sync();                                                 // the leader's MMAs read the peer's shared memory and write its TMEM
+    if (warp == TC_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 // ================================================================================================ colour branch
@@ -961,7 +1049,9 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
             cp.bias[c] = biases[l];
         }
     }
-    launch(tc_pack_weight_kernel, cdiv((int64_t)4 * ALPHA_N * 8, 256), 256, 0, st, weights[P.alpha_layer], ALPHA_N, 1, TC_W, 4, (const float*)nullptr, ws.apack);
+    // alpha panel: per CTA of the pair four K panels of 8 rows; rank 0's row 0 is the weight vector, everything else zero
+    SGN_CUDA(cudaMemsetAsync(ws.apack, 0, ALPHA_PANEL_B, st));
+    launch(tc_pack_weight_kernel, cdiv((int64_t)4 * 8 * 8, 256), 256, 0, st, weights[P.alpha_layer], 8, 1, TC_W, 4, (const float*)nullptr, ws.apack);
     launch(tc_point_rows_kernel, cdiv(tables->N, 8), 256, 0, st, tables->embedding, tables->N, ws.ptab);
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
@@ -1001,8 +1091,10 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         tp.tuple_src = ws.tuple_src; tp.sample_cidx = ws.sample_cidx;
         tp.loc_pers = loc_pers; tp.wc = ws.wc;
         tp.F = ws.F; tp.sigma = ws.sigma;
-        const int max_pairs = (tp.ntiles_cap + 1) / 2;
-        launch(agg_tuple_tc_kernel, max_pairs < n_sm ? max_pairs : n_sm, TC_THREADS, TC_SMEM, st, tp);
+        // clusters of two CTAs (a TPC's SM pair); every cluster takes four tiles per cycle
+        const int max_clusters = (tp.ntiles_cap + 3) / 4;
+        const int n_clusters = max_clusters < n_sm / 2 ? max_clusters : n_sm / 2;
+        launch(agg_tuple_tc_kernel, 2 * n_clusters, TC_THREADS, TC_SMEM, st, tp);
 
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
         cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.F; cp.sigma = ws.sigma;
