@@ -46,7 +46,7 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
         const float cf = in.tab.conf ? fminf(fmaxf(in.tab.conf[p], 0.0001f), 1.0f) : 1.0f;
         const float wn = w[k] / den;
         wc[s * K + k] = wn * cf;
-        weight_n[s * K + k] = wn;
+        if (weight_n) weight_n[s * K + k] = wn;
         if (weight_out) weight_out[s * K + k] = wn;
         if (conf_out) conf_out[s * K + k] = cf;
     }

@@ -43,7 +43,7 @@ constexpr int PANEL_BH = PANEL_B / 2;     // 16 KB: this CTA's half (128 of the 
 constexpr int SLOT_PANELS = 5, SLOT_BYTES = SLOT_PANELS * PANEL_A, B_STAGES = 4;
 constexpr int E7_COL0 = 32;               // inside panel 4: cols [32,48) hold [colour | dir-view | dir.view | 1 | 1 | 0..]
 constexpr int ONES_KSTEP = 1;             // K-step of panel 4 that holds operand cols 272..287, i.e. the two 1.0 columns at 12, 13
-constexpr int META_CHUNK = 6;             // 16-byte chunk of a row of panel 4 that carries {w*conf, sample slot, first compact sample, #slots}
+constexpr int META_CHUNK = 6;             // 16-byte chunks 6, 7 of a row of panel 4: {w*conf, sample slot, first padded sample, #slots | passes << 16}, {tuple index}
 constexpr int KS_SLOTS = 56;              // sample slots per CTA and K-sum pass (Sel^T = 2 K-panels x 56 x 128 B, inside panel 4)
 constexpr int KS_N = 2 * KS_SLOTS;        // the pair's K-sum MMA: columns [0,56) = leader CTA's samples, [56,112) = peer CTA's
 constexpr int BIAS_PANEL_B = TC_W * 32;   // 8 KB: compact (unswizzled) [256 x 16] bias K-step (4 KB per CTA)
@@ -53,13 +53,12 @@ constexpr int ALPHA_COL = 2 * KS_N;       // accumulator columns [224, 240) of t
 
 constexpr int OFF_SLOT0 = 0;
 constexpr int OFF_WRING = 2 * SLOT_BYTES;                       // 163840
-constexpr int OFF_SIG = OFF_WRING + B_STAGES * PANEL_BH;        // 229376: [128] w*conf*act(alpha) per row
-constexpr int OFF_SLOTID = OFF_SIG + TC_ROWS * 4;               // [128] sample slot of the row (-1: dead row)
-constexpr int OFF_BAR = OFF_SLOTID + TC_ROWS * 4;
+constexpr int OFF_BAR = OFF_WRING + B_STAGES * PANEL_BH;        // 229376
 constexpr int N_BARS = 3 * B_STAGES + 8;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
-constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 16, TC_MMA_WARP = 17, TC_THREADS = 18 * 32;
+constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 16, TC_MMA_WARP = 17, TC_THREADS = 20 * 32;   // warps 18, 19 idle (whole warpgroups for setmaxnreg)
+constexpr int REGS_EPI = 136, REGS_GATHER = 80, REGS_MISC = 40;      // 8*136 + 8*80 + 4*40 <= 20 * 96 (the launch allocation per warp-lane)
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
@@ -73,6 +72,7 @@ struct TcParams {
     int K, SR;
     const int32_t* ntiles_ptr; int ntiles_cap;
     const int2* tile_tab;                  // [ntiles + 1] {first tuple, first compact sample} of every tile, then the totals
+    const int32_t* cpad0;                  // [ntiles + 1] first PADDED sample index of every tile (each tile's samples padded to a multiple of 8)
     const int32_t* tuple_src; const int32_t* sample_cidx;
     const float* loc_pers; const float* wc;
     const uint8_t* ptab;                   // [N][224] bf16 per-point rows
@@ -84,17 +84,20 @@ struct TcParams {
     int first_panel[TC_MAX_LAYERS + 1];
     const float* ba;
     float slope; int act_super;
-    uint8_t* F; float* sigma;              // outputs per compact sample: F (bf16, colour-kernel operand image, see f_image_off), sigma [S]
+    uint8_t* F; float* sigrow;             // outputs: F per padded sample (bf16, colour-kernel operand image, see f_image_off), w*conf*act(alpha) per tuple
     int dbg;                               // SGN_TC_DEBUG bitmask (timing experiments only; results invalid when != 0)
 };
 
-// K-weighted feature sums F[c][f] are stored as the colour kernel's first-layer A operand: per 128 compact samples four
-// 16 KB panels (64 features each) in the 128B-swizzled K-major shared-memory image, so that kernel loads them with plain bulk copies.
+// K-weighted feature sums are stored as the colour kernel's first-layer A operand, MN-major (the sample index is the contiguous
+// dimension, which is how they leave the K-sum MMA: one thread = one feature, consecutive registers = consecutive samples).
+// Per 128 padded samples: four 16 KB stages of 64 features; a stage = 2 sample atoms (64 samples) x 8 feature groups x 8 features x
+// 128 bytes, 16-byte chunks XOR-swizzled with the feature index (canonical SWIZZLE_128B MN-major, LBO 8 KB, SBO 1 KB), so the
+// colour kernel loads a stage with one bulk copy.  cp8 must be a multiple of 8: returns the offset of 8 consecutive samples (16 B).
 constexpr int F_TILE_BYTES = 4 * TC_PANEL_BYTES;
-__device__ __forceinline__ size_t f_image_off(int c, int f)
+__device__ __forceinline__ size_t f_image_off8(int cp8, int f)
 {
-    const int r = c & 127;
-    return (size_t)(c >> 7) * F_TILE_BYTES + (f >> 6) * TC_PANEL_BYTES + r * 128 + ((((f & 63) >> 3) ^ (r & 7)) << 4) + (f & 7) * 2;
+    return (size_t)(cp8 >> 7) * F_TILE_BYTES + (f >> 6) * TC_PANEL_BYTES + ((cp8 >> 6) & 1) * 8192 + ((f >> 3) & 7) * 1024 + (f & 7) * 128 +
+           ((((cp8 & 63) >> 3) ^ (f & 7)) << 4);
 }
 
 // A operand read MN-major (M = 64-element atoms 16 KB apart (LBO), K = 8-row groups 1 KB apart (SBO)), 128-byte swizzle
@@ -163,7 +166,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void sig_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128u(uint32_t addr)
 {
     uint4 v;
@@ -189,6 +191,7 @@ __device__ __forceinline__ uint32_t leaky_pack(uint32_t a, uint32_t b, __nv_bflo
 // tiles; only the MMAs are shared: the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2, M = 256 = its 128 rows +
 // the peer's 128 rows, and each CTA streams and holds only its half of every weight panel (N split) -- half the shared-memory
 // operand traffic and half the L2 weight traffic per SM.  Per pair-cycle a cluster works on four tiles: (slot 0|1) x (rank 0|1).
+template <bool kDbg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_tuple_tc_kernel(const __grid_constant__ TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -198,8 +201,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
 
-    float* sig_sh = (float*)(smem + OFF_SIG);
-    int32_t* slot_sh = (int32_t*)(smem + OFF_SLOTID);
     const uint32_t bar0 = sbase + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
     // W_FULL / W_EMPTY / D_FULL / BUF_FREE: one per CTA.  PEER_W (the peer's weight stage has landed), X_FULL, A_READY: the
@@ -229,6 +230,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
     cluster_sync();                                                 // both CTAs' barriers are initialised before anyone arrives remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // hand the registers to the warps that need them (whole warpgroups: epilogue 0-7, gather 8-15, producer / MMA / idle 16-19)
+    if (warp < TC_EPI_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+    else if (warp < TC_PRODUCER_WARP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MISC));
 
     if (warp < TC_EPI_WARPS) {
         // =========================================================== EPILOGUE: warp = (column half h2, TMEM lane quadrant)
@@ -240,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
         const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
         const float ba = p.ba[0];
         long long pf_wait = 0, pf_mid = 0, pf_last = 0, pf_drain = 0, pf_t0 = 0;
-        const bool prof = (p.dbg & 32) != 0;
+        const bool prof = kDbg && (kDbg && (p.dbg & 32)) != 0;
         uint32_t tcount = 0;
         const uint32_t a_ready0 = LEADER_BAR(A_READY);
         // this warp's part of "slot s is ready for the next MMA": every lane's writes are fenced, then one arrival for the warp
@@ -252,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
         };
 
         for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
-            int nslots0 = 0, nslots1 = 0, npass0 = 1, npass1 = 1, c00 = 0, c01 = 0, slr0 = -1, slr1 = -1;
+            int nslots0 = 0, nslots1 = 0, npass0 = 1, npass1 = 1, c00 = 0, c01 = 0, slr0 = -1, slr1 = -1, j0 = 0, j1 = 0;
             float wcr0 = 0.f, wcr1 = 0.f;
             tcount += 2;
             for (int l = 0; l < p.n_layers; l++) {
@@ -267,8 +272,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     if (l == 0) {
                         // this row's {w*conf, sample slot, first compact sample of the tile, #sample slots | K-sum passes << 16}
                         const uint4 m = lds128u(slot_base + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4));
-                        if (s == 0) { wcr0 = __uint_as_float(m.x); slr0 = (int)m.y; c00 = (int)m.z; nslots0 = (int)(m.w & 0xffffu); npass0 = (int)(m.w >> 16); }
-                        else { wcr1 = __uint_as_float(m.x); slr1 = (int)m.y; c01 = (int)m.z; nslots1 = (int)(m.w & 0xffffu); npass1 = (int)(m.w >> 16); }
+                        const int j = (int)lds128u(slot_base + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4)).x;
+                        if (s == 0) { wcr0 = __uint_as_float(m.x); slr0 = (int)m.y; c00 = (int)m.z; nslots0 = (int)(m.w & 0xffffu); npass0 = (int)(m.w >> 16); j0 = j; }
+                        else { wcr1 = __uint_as_float(m.x); slr1 = (int)m.y; c01 = (int)m.z; nslots1 = (int)(m.w & 0xffffu); npass1 = (int)(m.w >> 16); j1 = j; }
                     }
                     const float wcr = s == 0 ? wcr0 : wcr1;
                     const int slr = s == 0 ? slr0 : slr1;
@@ -276,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     const uint32_t act_row = slot_base + (h2 * 2) * PANEL_A + row * 128;
                     // one 32-column chunk: (bias is part of the GEMM) LeakyReLU in bf16 -> this row's 64 bytes of panel h2*2 + c/2
                     auto chunk = [&](int c, const uint32_t(&vv)[32]) {
-                        if (p.dbg & 8) return;
+                        if (kDbg && (p.dbg & 8)) return;
                         const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
@@ -323,33 +329,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     if (prof) pf_t0 = clock64();
                     mbar_wait(BAR(D_FULL + s), (ph_d >> s) & 1u); ph_d ^= 1u << s;
                     tc_fence_after();
-                    if (pass == 0 && h2 == 0) {
-                        // sigma of a sample = sum over its rows of w*conf*act(alpha); alpha came out of the alpha_branch MMA
+                    if (pass == 0 && h2 == 0) {                                            // warp-uniform: the TMEM load is .sync.aligned
+                        // this tuple's term of sigma = sum_k w*conf*act(alpha_k); alpha came out of the alpha_branch MMA, the colour
+                        // kernel adds up the (consecutive) terms of a sample
                         const float a = __uint_as_float(tc_ld1(tmem_base + (uint32_t)(s * TC_W + ALPHA_COL) + lane_field)) + ba;
                         const float act = p.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f);
-                        sig_sh[row] = (p.dbg & 24) ? 0.f : act * wcr;
-                        slot_sh[row] = slr;
-                        sig_bar();
-                        if (slr >= 0 && (row == 0 || slot_sh[row - 1] != slr)) {
-                            float sum = sig_sh[row];
-                            for (int q = row + 1; q < TC_ROWS && slot_sh[q] == slr; q++) sum += sig_sh[q];
-                            p.sigma[c0 + slr] = sum;
-                        }
-                        sig_bar();
+                        if (slr >= 0) p.sigrow[s == 0 ? j0 : j1] = (kDbg && (p.dbg & 24)) ? 0.f : act * wcr;
                     }
-                    const int ns = min(KS_SLOTS, nslots - pass * KS_SLOTS);
-                    const int cbase = c0 + pass * KS_SLOTS;
+                    const int ns8 = min(KS_SLOTS, ((nslots + 7) & ~7) - pass * KS_SLOTS);   // padded slots of this pass, a multiple of 8
+                    const int cbase = c0 + pass * KS_SLOTS;                                 // first padded sample index of the pass (multiple of 8)
                     // this CTA's samples are columns [rank*56, rank*56+56) of each feature half's [128 x 112] block
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_N + rank * KS_SLOTS) + lane_field;
 #pragma unroll 1
                     for (int j = 0; j < 2; j++) {
-                        if (32 * j >= ns) break;
+                        if (32 * j >= ns8) break;
                         uint32_t v[32];
                         tc_ld32(d_addr + 32 * j, v);                                  // j = 1 reads 8 columns past the 56 (in bounds, unused)
-                        if (!(p.dbg & 16)) {
+                        if (!(kDbg && (p.dbg & 16))) {
 #pragma unroll
-                            for (int i = 0; i < 32; i++)
-                                if (32 * j + i < ns) *(__nv_bfloat16*)(p.F + f_image_off(cbase + 32 * j + i, f)) = __float2bfloat16_rn(__uint_as_float(v[i]));
+                            for (int g = 0; g < 4; g++)
+                                if (32 * j + 8 * g < ns8) {
+                                    const uint4 o = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                                               pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                                               pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                                               pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                                    *(uint4*)(p.F + f_image_off8(cbase + 32 * j + 8 * g, f)) = o;
+                                }
                         }
                     }
                     if (pass + 1 < npass) {
@@ -381,7 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
         const float r00 = Rm[0], r01 = Rm[1], r02 = Rm[2], r10 = Rm[3], r11 = Rm[4], r12 = Rm[5], r20 = Rm[6], r21 = Rm[7], r22 = Rm[8];
         const float cpx = p.in.campos[0], cpy = p.in.campos[1], cpz = p.in.campos[2];
         long long gf_load = 0, gf_wait = 0, gf_write = 0, gf_t0 = 0;
-        const bool prof = (p.dbg & 32) != 0;
+        const bool prof = kDbg && (kDbg && (p.dbg & 32)) != 0;
         uint32_t tcount = 0;
         const uint32_t x0 = sbase + OFF_SLOT0 + s * SLOT_BYTES;
         const uint32_t one_one = pack_bf16(1.0f, 1.0f);
@@ -392,12 +397,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
             if (prof) gf_t0 = clock64();
             // ---- everything that does not need the slot: indices, point data, PE(dists), [colour | dir-view | dir.view], in registers
             int2 ta = make_int2(0, 0), tb = make_int2(0, 0);
-            if (tile < ntiles) { ta = p.tile_tab[tile]; tb = p.tile_tab[tile + 1]; }
+            int cpad = 0;
+            if (tile < ntiles) { ta = p.tile_tab[tile]; tb = p.tile_tab[tile + 1]; cpad = p.cpad0[tile]; }
             int pslots = 0;
             if (ptile < ntiles) pslots = p.tile_tab[ptile + 1].y - p.tile_tab[ptile].y;
             const int nsl = tb.y - ta.y;
             const int npass = max(1, (max(nsl, pslots) + KS_SLOTS - 1) / KS_SLOTS);   // the pair runs the same number of K-sum passes
-            const bool live = row < tb.x - ta.x && !(p.dbg & 4);
+            const bool live = row < tb.x - ta.x && !(kDbg && (p.dbg & 4));
             uint32_t pe[32], e7p[4] = {0u, 0u, 0u, 0u};
             float wcv = 0.f; int slot = -1;
             const uint8_t* src = p.ptab;
@@ -455,8 +461,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
 #pragma unroll
                 for (int i = 0; i < (4 * 64 + E7_COL0 + 16) / 8; i++) sts128(x0 + sw_off(row, 8 * i), 0u, 0u, 0u, 0u);
             }
-            sts128(x0 + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4), __float_as_uint(wcv), (uint32_t)slot, (uint32_t)ta.y,
+            sts128(x0 + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4), __float_as_uint(wcv), (uint32_t)slot, (uint32_t)cpad,
                    (uint32_t)nsl | ((uint32_t)npass << 16));
+            sts128(x0 + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4), (uint32_t)(ta.x + row), 0u, 0u, 0u);
             cp_async_wait_all();
             fence_proxy_async();
             __syncwarp();
@@ -475,7 +482,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                 const uint32_t st = n % B_STAGES;
                 mbar_wait(BAR(W_EMPTY + st), (ph_empty >> st) & 1u); ph_empty ^= 1u << st;
                 n++;
-                if (p.dbg & 1) { mbar_arrive(BAR(W_FULL + st)); return; }
+                if (kDbg && (p.dbg & 1)) { mbar_arrive(BAR(W_FULL + st)); return; }
                 mbar_expect_tx(BAR(W_FULL + st), bytes);
                 bulk_g2s(sbase + OFF_WRING + st * PANEL_BH, srcp, bytes, BAR(W_FULL + st));
             };
@@ -488,7 +495,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                 for (int s = 0; s < 2; s++) push(p.apack + rank * (ALPHA_PANEL_B / 2), ALPHA_PANEL_B / 2);
             }
         }
-    } else if (!leader) {
+    } else if (warp == TC_MMA_WARP && !leader) {
         // =========================================================== peer CTA: forward "my half of stage st has landed" to the leader
         if (lane == 0) {
             uint32_t ph_full = 0, n = 0;
@@ -502,7 +509,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     mbar_arrive_cluster(peer_w0 + 8u * st);
                 }
         }
-    } else {
+    } else if (warp == TC_MMA_WARP) {
         // =========================================================== leader CTA: MMA issuer for the pair.  The whole warp walks the
         // (warp-uniform) schedule, one elected lane issues each tcgen05 instruction
         {
@@ -631,12 +638,19 @@ constexpr int COFF_TMEMPTR = COFF_BAR + C_NBARS * 8;
 constexpr int C_SMEM = COFF_TMEMPTR + 16 + 1024;
 static_assert(C_SMEM <= 232448, "colour kernel exceeds the 227 KB shared memory limit");
 constexpr uint32_t C_IDESC = tc_idesc(TC_ROWS, CW);
+constexpr uint32_t C_IDESC_F = tc_idesc(TC_ROWS, CW, 1);     // the F stages are MN-major (sample index contiguous)
+// MN-major SWIZZLE_128B A operand inside a 16 KB F stage: the two 64-sample atoms 8 KB apart (LBO), 8-feature groups 1 KB apart (SBO)
+__device__ __forceinline__ uint64_t umma_desc_fstage(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
 
 struct ColParams {
-    const int32_t* S_ptr; int S_max;
-    const int32_t* csample;            // compact sample -> sample
-    const uint8_t* F;                  // K-weighted feature sums per compact sample, bf16 operand image (f_image_off)
-    const float* sigma;                // [S]
+    const int32_t* S_ptr; int S_max;   // number of PADDED samples (every tuple tile's samples padded to a multiple of 8)
+    const int32_t* csample;            // padded sample -> sample, -1 for padding
+    const uint8_t* F;                  // K-weighted feature sums per padded sample, bf16 MN-major operand image (f_image_off8)
+    const float* sigrow;               // w*conf*act(alpha) per tuple; sigma of a sample = sum over its nvalid consecutive tuples
+    const int32_t* tuple_start; const int32_t* nvalid;
     const float* raydir; int SR;
     const uint8_t* wpack;              // packed hidden-layer weights, C_PANEL each, layer after layer
     int n_hidden;                      // colour layers followed by an activation (1..3)
@@ -736,11 +750,15 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 }
                 tc_fence_before();
                 mbar_arrive(BAR(D_EMPTY + db));
-                if (last && c < Sv && !(p.dbg & 256)) {
+                const int sidx = (last && c < Sv) ? p.csample[c] : -1;
+                if (sidx >= 0 && !(p.dbg & 256)) {
                     const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
                                 s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
                     const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
-                    ((float4*)p.decoded)[p.csample[c]] = make_float4(p.sigma[c], s0 * m - o, s1 * m - o, s2 * m - o);
+                    float sg = 0.f;
+                    const int j0 = p.tuple_start[sidx], nv = p.nvalid[sidx];
+                    for (int q = 0; q < nv; q++) sg += p.sigrow[j0 + q];
+                    ((float4*)p.decoded)[sidx] = make_float4(sg, s0 * m - o, s1 * m - o, s2 * m - o);
                 }
             }
         }
@@ -776,8 +794,9 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                     float vals[32];
 #pragma unroll
                     for (int i = 0; i < 32; i++) vals[i] = 0.f;
-                    if (c0 + r < Sv && !(p.dbg & 64)) {
-                        const int64_t ray = p.csample[c0 + r] / p.SR;
+                    const int sidx_r = (c0 + r < Sv && !(p.dbg & 64)) ? p.csample[c0 + r] : -1;
+                    if (sidx_r >= 0) {
+                        const int64_t ray = sidx_r / p.SR;
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             if (i < 3 * p.fv) {
@@ -827,7 +846,9 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                             const uint32_t a_addr = sbase + COFF_RING + s * C_PANEL, b_addr = sbase + COFF_W + kp * C_PANEL;
                             const int ksteps = kp < 4 ? 4 : 2;
                             for (int k = 0; k < ksteps; k++) {
-                                tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), C_IDESC, acc);
+                                // F stages: MN-major A, one K-step = 16 features = two 1 KB feature groups; the view panel is K-major
+                                if (kp < 4) tc_mma(d_tmem, umma_desc_fstage(a_addr + k * 2048), umma_desc(b_addr + k * 32), C_IDESC_F, acc);
+                                else tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), C_IDESC, acc);
                                 acc = 1;
                             }
                             tc_commit(BAR(R_EMPTY + s));
@@ -893,6 +914,26 @@ __global__ void tc_tile_kernel(const int32_t* __restrict__ S_ptr, int S_max, con
     }
 }
 
+// Padded sample index space: every tile's samples are padded to a multiple of 8 so that the K-sum drain stores whole 16-byte groups.
+__global__ void tc_tile_pad_kernel(const int32_t* __restrict__ ntiles_ptr, int ncap, const int2* __restrict__ tile_tab, int32_t* __restrict__ padslots)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ncap) return;
+    const int nt = min(*ntiles_ptr, ncap);
+    padslots[t] = t < nt ? ((tile_tab[t + 1].y - tile_tab[t].y + 7) & ~7) : 0;
+}
+// padded sample -> sample (the buffer is preset to -1)
+__global__ void tc_csample_pad_kernel(const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample, const int32_t* __restrict__ tuple_start,
+                                      int TW, const int2* __restrict__ tile_tab, const int32_t* __restrict__ cpad0, int32_t* __restrict__ csample_pad)
+{
+    const int Sv = min(*S_ptr, S_max);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Sv) return;
+    const int sidx = csample[c];
+    const int t = tuple_start[sidx] / TW;
+    csample_pad[cpad0[t] + (c - tile_tab[t].y)] = sidx;
+}
+
 // torch Linear weight [Nvalid, K_in] fp32 -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (Nrows x 128 bytes each).
 // With `bias`, columns K_in and K_in + 1 carry the bias split into two bf16 (hi + lo): the matching operand columns hold 1.0.
 __global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, int Nvalid, int Kin, int npanels, const float* __restrict__ bias,
@@ -930,16 +971,24 @@ __global__ void tc_pack_bias_kernel(const float* __restrict__ bias, uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-constexpr int64_t TC_CHUNK = 65536;       // rays per pass: bounds the worst-case (every slot valid) workspace
+constexpr int64_t TC_CHUNK = 1 << 19;     // rays per pass: bounds the worst-case (every slot valid) workspace (~21 KB per ray) and int32 indexing
 
 struct TcWs {
-    int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles;
+    int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles, *padslots, *cpad0, *csample_pad, *tpartials;
     int2* tile_tab;
-    float *loc_pers, *weight_n, *wc, *sigma;
+    float *loc_pers, *wc, *sigrow;
     uint8_t *wpack, *cpack, *ptab, *bpack, *apack, *F;
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
+// rays per pass: as few equal passes as keep each one under TC_CHUNK rays
+static inline int64_t tc_chunk_rays(int64_t R)
+{
+    const char* e = getenv("SGN_TC_CHUNK");                  // tests force small passes through this
+    const int64_t cap = e && atoll(e) > 0 ? atoll(e) : TC_CHUNK;
+    const int64_t n = (R + cap - 1) / cap;
+    return n <= 1 ? R : (R + n - 1) / n;
+}
 
 static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
 {
@@ -950,9 +999,14 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1); ws->csample = A.take<int32_t>(S + 1);
     ws->ntiles = A.take<int32_t>(4);
-    ws->tile_tab = A.take<int2>(T / tile_width(K) + 3);
-    ws->loc_pers = A.take<float>(S * 3); ws->weight_n = A.take<float>(T); ws->wc = A.take<float>(T);
-    ws->F = A.take<uint8_t>((S / TC_ROWS + 2) * F_TILE_BYTES); ws->sigma = A.take<float>(S + 1);
+    const size_t ncap = T / tile_width(K) + 1;            // upper bound of the number of tiles
+    const size_t spad = S + 7 * ncap + 8;                  // upper bound of the padded sample count
+    ws->tile_tab = A.take<int2>(ncap + 2);
+    ws->padslots = A.take<int32_t>(ncap + 2); ws->cpad0 = A.take<int32_t>(ncap + 2);
+    ws->tpartials = A.take<int32_t>(scan_partials_count((int64_t)ncap + 1));
+    ws->csample_pad = A.take<int32_t>(spad);
+    ws->loc_pers = A.take<float>(S * 3); ws->wc = A.take<float>(T);
+    ws->F = A.take<uint8_t>((spad / TC_ROWS + 2) * F_TILE_BYTES); ws->sigrow = A.take<float>(T + 1);
     size_t panels = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
@@ -989,7 +1043,7 @@ int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, i
     int rc = tc_supported(P, K);
     if (rc) return rc;
     TcWs ws;
-    *bytes = tc_carve(P, N, R < TC_CHUNK ? R : TC_CHUNK, SR, K, nullptr, 0, &ws);
+    *bytes = tc_carve(P, N, tc_chunk_rays(R), SR, K, nullptr, 0, &ws);
     return SGN_OK;
 }
 
@@ -1001,7 +1055,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     int rc = tc_supported(P, K);
     if (rc) return rc;
     const AggDims& d = P.dims;
-    const int64_t chunk = R < TC_CHUNK ? R : TC_CHUNK;
+    const int64_t chunk = tc_chunk_rays(R);
     TcWs ws;
     const size_t need = tc_carve(P, tables->N, chunk, SR, K, workspace, workspace_bytes, &ws);
     if (need > workspace_bytes || ((uintptr_t)workspace & 255)) {
@@ -1010,7 +1064,8 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     }
     static bool attr_set = false;
     if (!attr_set) {
-        SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
         attr_set = true;
     }
@@ -1076,7 +1131,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         float* dec = decoded + r0 * SR * 4;
         float* loc_pers = loc_pers_out ? loc_pers_out + r0 * SR * 3 : ws.loc_pers;
         SGN_CUDA(cudaMemsetAsync(dec, 0, sizeof(float) * 4 * (size_t)S, st));
-        launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, ws.weight_n, weight_out ? weight_out + r0 * SR * K : nullptr,
+        launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, (float*)nullptr, weight_out ? weight_out + r0 * SR * K : nullptr,
                conf_out ? conf_out + r0 * SR * K : nullptr, ray_valid + r0 * SR, ws.nvalid, ws.svalid);
         if ((rc = exclusive_scan_i32(ws.nvalid, ws.tuple_start, S, ws.partials, st))) return rc;
         if ((rc = exclusive_scan_i32(ws.svalid, ws.sample_cidx, S, ws.partials, st))) return rc;
@@ -1084,22 +1139,30 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         const int32_t* S_ptr = ws.sample_cidx + S;
         launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
         launch(tc_tile_kernel, cdiv(S, 256), 256, 0, st, S_ptr, Sm, T_ptr, ws.csample, ws.tuple_start, TW, ws.tile_tab, ws.ntiles);
+        const int ncap = Tm / TW + 1;
+        const int spad = Sm + 7 * ncap + 8;
+        launch(tc_tile_pad_kernel, cdiv(ncap + 1, 256), 256, 0, st, ws.ntiles, ncap, ws.tile_tab, ws.padslots);
+        if ((rc = exclusive_scan_i32(ws.padslots, ws.cpad0, ncap + 1, ws.tpartials, st))) return rc;
+        SGN_CUDA(cudaMemsetAsync(ws.csample_pad, 0xFF, sizeof(int32_t) * (size_t)spad, st));
+        launch(tc_csample_pad_kernel, cdiv(S, 256), 256, 0, st, S_ptr, Sm, ws.csample, ws.tuple_start, TW, ws.tile_tab, ws.cpad0, ws.csample_pad);
 
         tp.in = in;
-        tp.ntiles_ptr = ws.ntiles; tp.ntiles_cap = Tm / TW + 1;
-        tp.tile_tab = ws.tile_tab;
+        tp.ntiles_ptr = ws.ntiles; tp.ntiles_cap = ncap;
+        tp.tile_tab = ws.tile_tab; tp.cpad0 = ws.cpad0;
         tp.tuple_src = ws.tuple_src; tp.sample_cidx = ws.sample_cidx;
         tp.loc_pers = loc_pers; tp.wc = ws.wc;
-        tp.F = ws.F; tp.sigma = ws.sigma;
+        tp.F = ws.F; tp.sigrow = ws.sigrow;
         // clusters of two CTAs (a TPC's SM pair); every cluster takes four tiles per cycle
         const int max_clusters = (tp.ntiles_cap + 3) / 4;
         const int n_clusters = max_clusters < n_sm / 2 ? max_clusters : n_sm / 2;
-        launch(agg_tuple_tc_kernel, 2 * n_clusters, TC_THREADS, TC_SMEM, st, tp);
+        if (tp.dbg) launch(agg_tuple_tc_kernel<true>, 2 * n_clusters, TC_THREADS, TC_SMEM, st, tp);
+        else launch(agg_tuple_tc_kernel<false>, 2 * n_clusters, TC_THREADS, TC_SMEM, st, tp);
 
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
-        cp.S_ptr = S_ptr; cp.S_max = Sm; cp.csample = ws.csample; cp.F = ws.F; cp.sigma = ws.sigma;
+        cp.S_ptr = ws.cpad0 + (ncap + 1); cp.S_max = spad; cp.csample = ws.csample_pad; cp.F = ws.F; cp.sigrow = ws.sigrow;
+        cp.tuple_start = ws.tuple_start; cp.nvalid = ws.nvalid;
         cp.raydir = in.raydir; cp.decoded = dec;
-        const int max_ctiles = cdiv(Sm, TC_ROWS);
+        const int max_ctiles = cdiv(spad, TC_ROWS);
         launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, 288, C_SMEM, st, cp);
         SGN_LAUNCH_CHECK();
     }

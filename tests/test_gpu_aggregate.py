@@ -197,3 +197,46 @@ def test_bf16_tensor_core_path_vs_fp32(R, SR):
     sig_err = ((out[0][..., 0] - ref[0][..., 0]).abs() / ref[0][..., 0].abs().clamp(min=1.0))
     print(f"bf16 vs fp32: max |d rgb| = {d_rgb:.3e}, max rel |d sigma| = {float(sig_err.max()):.3e}")
     assert d_rgb <= 1e-2 and float(sig_err.max()) <= 2e-2
+
+
+def test_bf16_edge_cases(monkeypatch):
+    """bf16 path: ragged tiles -- many one-neighbour samples (more than 56 sample slots per 128-row tile, i.e. several K-sum
+    passes), an all-empty input, a single valid tuple, and ray chunking (SGN_TC_CHUNK) must not change the result."""
+    cfg = rr.agg_config()
+    N, R, SR, K = 4000, 257, 24, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=77)
+    g = torch.Generator().manual_seed(3)
+    keep = torch.rand(R, SR, generator=g) < 0.7                 # most samples keep exactly one neighbour -> ~120 slots per tile
+    pidx = pidx.clone()
+    first = torch.randint(0, N, (R, SR), generator=g).to(torch.int32)
+    one = torch.full((R, SR, K), -1, dtype=torch.int32)
+    one[..., 3] = first
+    pidx = torch.where(keep[..., None], one, pidx)
+    P = rr.init_params(cfg, seed=4, bias_scale=0.1)
+    _, W, B = param_lists(P, cfg)
+    tb = (tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(), None)
+    cam = (raydir.cuda(), campos.cuda(), rot.cuda())
+
+    def run(pi, lw, precision):
+        with torch.no_grad():
+            o = ops.aggregate(cfg_to_c(cfg), W, B, *tb, pi.cuda(), lw.cuda(), cam[0][:pi.shape[0]], cam[1], cam[2], precision=precision)
+        torch.cuda.synchronize()
+        return o
+    ref = run(pidx, loc_w, ops.PRECISION_FP32)
+    out = run(pidx, loc_w, ops.PRECISION_BF16)
+    assert torch.equal(out[1], ref[1])
+    assert float((out[0][..., 1:] - ref[0][..., 1:]).abs().max()) <= 1e-2
+    assert float(((out[0][..., 0] - ref[0][..., 0]).abs() / ref[0][..., 0].abs().clamp(min=1.0)).max()) <= 2e-2
+    monkeypatch.setenv("SGN_TC_CHUNK", "64")                    # 5 passes of 52 rays instead of one
+    chunked = run(pidx, loc_w, ops.PRECISION_BF16)
+    monkeypatch.delenv("SGN_TC_CHUNK")
+    torch.testing.assert_close(chunked[0], out[0], rtol=0, atol=2e-3)   # tiles are cut differently: K-sum order inside the MMA changes
+    assert torch.equal(chunked[1], out[1])
+    empty = torch.full((7, SR, K), -1, dtype=torch.int32)
+    o = run(empty, loc_w[:7], ops.PRECISION_BF16)
+    assert float(o[0].abs().max()) == 0 and int(o[1].sum()) == 0
+    single = empty.clone()
+    single[4, 11, 6] = 123
+    o = run(single, loc_w[:7], ops.PRECISION_BF16)
+    r = run(single, loc_w[:7], ops.PRECISION_FP32)
+    assert int(o[1].sum()) == 1 and float((o[0] - r[0]).abs().max()) <= 2e-2
