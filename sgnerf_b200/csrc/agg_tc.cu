@@ -515,10 +515,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
         {
             uint32_t ph_full = 0, ph_peer = 0, ph_x = 0, ph_a = 3;          // phase bits, one per stage / slot
             uint32_t n = 0;
+            const bool prof = kDbg && (p.dbg & 32) != 0;
+            long long mf_w = 0, mf_pw = 0, mf_a = 0, mf_x = 0, mf_ks = 0, mf_t0 = 0, mf_start = prof ? clock64() : 0;
             auto next_stage = [&]() -> uint32_t {
                 const uint32_t st = n % B_STAGES;
+                if (prof) mf_t0 = clock64();
                 mbar_wait(BAR(W_FULL + st), (ph_full >> st) & 1u); ph_full ^= 1u << st;
+                if (prof) { const long long t1 = clock64(); mf_w += t1 - mf_t0; mf_t0 = t1; }
                 mbar_wait_cluster(BAR(PEER_W + st), (ph_peer >> st) & 1u); ph_peer ^= 1u << st;
+                if (prof) mf_pw += clock64() - mf_t0;
                 tc_fence_after();
                 return st;
             };
@@ -543,8 +548,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     for (int s = 0; s < 2; s++) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(s * TC_W);
                         const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
+                        if (prof) mf_t0 = clock64();
                         mbar_wait_cluster(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
+                        if (prof) { const long long t1 = clock64(); mf_a += t1 - mf_t0; mf_t0 = t1; }
                         if (kind == LAYER_FROM_X0) { mbar_wait_cluster(BAR(X_FULL + s), (ph_x >> s) & 1u); ph_x ^= 1u << s; }
+                        if (prof) mf_x += clock64() - mf_t0;
                         tc_fence_after();
                         uint32_t acc = 0;
                         for (int kp = 0; kp < np; kp++) {
@@ -555,11 +563,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                                 else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view | 1 | 1] of block3.0
                             }
                             const uint32_t st = next_stage();
-                            uint64_t ad = umma_desc(a_addr), bd = umma_desc(sbase + OFF_WRING + st * PANEL_BH);
-                            for (int k = 0; k < ksteps; k++) {
-                                if (elect_one()) tc_mma2(d_tmem, ad, bd, IDESC_LAYER, acc);
-                                acc = 1; ad += 2; bd += 2;                                               // next K-step: +32 bytes
+                            const uint64_t ad = umma_desc(a_addr), bd = umma_desc(sbase + OFF_WRING + st * PANEL_BH);
+                            if (elect_one()) {                                                           // one lane issues the panel's K-steps back to back
+                                tc_mma2(d_tmem, ad, bd, IDESC_LAYER, acc);
+                                if (ksteps > 1) tc_mma2(d_tmem, ad + 2, bd + 2, IDESC_LAYER, 1u);        // next K-step: +32 bytes
+                                if (ksteps > 2) {
+                                    tc_mma2(d_tmem, ad + 4, bd + 4, IDESC_LAYER, 1u);
+                                    tc_mma2(d_tmem, ad + 6, bd + 6, IDESC_LAYER, 1u);
+                                }
                             }
+                            acc = 1;
                             release_stage(st);
                         }
                         if (own_bias_step) {
@@ -580,32 +593,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     const uint32_t a_base = sbase + OFF_SLOT0 + s * SLOT_BYTES;
                     const uint32_t sel = a_base + 4 * PANEL_A;
                     for (int pass = 0; pass < npass[s]; pass++) {
+                        if (prof) mf_t0 = clock64();
                         mbar_wait_cluster(BAR(A_READY + s), (ph_a >> s) & 1u); ph_a ^= 1u << s;
+                        if (prof) mf_ks += clock64() - mf_t0;
                         tc_fence_after();
                         if (pass == 0) {
                             const uint32_t st = next_stage();
                             const uint32_t b_addr = sbase + OFF_WRING + st * PANEL_BH;
-                            for (int kp = 0; kp < 4; kp++) {
-                                uint64_t ad = umma_desc(a_base + kp * PANEL_A), bd = umma_desc(b_addr + kp * (ALPHA_N / 2 * 128));
-                                for (int k = 0; k < 4; k++) {
-                                    if (elect_one()) tc_mma2(d_tmem + ALPHA_COL, ad, bd, IDESC_ALPHA, (kp | k) != 0);
-                                    ad += 2; bd += 2;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int kp = 0; kp < 4; kp++) {
+                                    const uint64_t ad = umma_desc(a_base + kp * PANEL_A), bd = umma_desc(b_addr + kp * (ALPHA_N / 2 * 128));
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) tc_mma2(d_tmem + ALPHA_COL, ad + 2 * k, bd + 2 * k, IDESC_ALPHA, (kp | k) != 0);
                                 }
                             }
                             release_stage(st);
                         }
-                        for (int half = 0; half < 2; half++) {
-                            uint64_t ad = umma_desc_mn(a_base + (2 * half) * PANEL_A);
-                            for (int ks = 0; ks < TC_ROWS / 16; ks++) {
-                                if (elect_one())
-                                    tc_mma2(d_tmem + (uint32_t)(half * KS_N), ad, umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
-                                ad += 2048 >> 4;                                                         // next 16 rows of the tile
+                        if (elect_one()) {
+#pragma unroll
+                            for (int half = 0; half < 2; half++) {
+                                const uint64_t ad = umma_desc_mn(a_base + (2 * half) * PANEL_A);
+#pragma unroll
+                                for (int ks = 0; ks < TC_ROWS / 16; ks++)                                // +16 rows of the tile per K-step
+                                    tc_mma2(d_tmem + (uint32_t)(half * KS_N), ad + ks * (2048 >> 4),
+                                            umma_desc(sel + (ks >> 2) * (KS_SLOTS * 128) + (ks & 3) * 32), IDESC_KSUM, ks > 0);
                             }
+                            tc_commit2(BAR(D_FULL + s));
                         }
-                        if (elect_one()) tc_commit2(BAR(D_FULL + s));
                     }
                     if (elect_one()) tc_commit2(BAR(BUF_FREE + s));
                 }
+            }
+            if (prof && blockIdx.x == 0 && lane == 0) {
+                const long long cyc = max((ncycles - cl0 + ncl - 1) / ncl, 1);
+                printf("mma issuer: %lld cycles/pair-cycle; waiting: own weights %lld, peer weights %lld, epilogue (layers) %lld, gather %lld, epilogue (K-sum) %lld\n",
+                       (clock64() - mf_start) / cyc, mf_w / cyc, mf_pw / cyc, mf_a / cyc, mf_x / cyc, mf_ks / cyc);
             }
         }
     }
