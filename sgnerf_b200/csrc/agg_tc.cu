@@ -58,7 +58,7 @@ constexpr int N_BARS = 3 * B_STAGES + 8;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
 constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 16, TC_MMA_WARP = 17, TC_THREADS = 20 * 32;   // warps 18, 19 idle (whole warpgroups for setmaxnreg)
-constexpr int REGS_EPI = 136, REGS_GATHER = 80, REGS_MISC = 40;      // 8*136 + 8*80 + 4*40 <= 20 * 96 (the launch allocation per warp-lane)
+constexpr int REGS_EPI = 128, REGS_GATHER = 80, REGS_MISC = 64;      // 8*128 + 8*80 + 4*64 <= 20 * 96 (the launch allocation per warp-lane)
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
