@@ -674,10 +674,9 @@ struct ColParams {
     const uint8_t* F;                  // K-weighted feature sums per padded sample, bf16 MN-major operand image (f_image_off8)
     const float* sigrow;               // w*conf*act(alpha) per tuple; sigma of a sample = sum over its nvalid consecutive tuples
     const int32_t* tuple_start; const int32_t* nvalid;
-    const float* raydir; int SR;
+    const uint8_t* vtab; int SR;       // per ray 32 bf16: view-direction encoding (see tc_viewdir_rows_kernel)
     const uint8_t* wpack;              // packed hidden-layer weights, C_PANEL each, layer after layer
     int n_hidden;                      // colour layers followed by an activation (1..3)
-    int fv;                            // num_viewdir_freqs
     const float* bias[C_MAX_HIDDEN];
     const float* wl; const float* bl;  // last Linear [3,128], [3]
     float slope; int act_super;
@@ -727,6 +726,13 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
         uint32_t lcount = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t c = (int64_t)tile * TC_ROWS + row;
+            // per-sample scalars first: their dependent loads run while the tensor pipe works on the first layer
+            const int sidx = (c < Sv && !(p.dbg & 256)) ? p.csample[c] : -1;
+            float sg = 0.f;
+            if (sidx >= 0) {
+                const int j0 = p.tuple_start[sidx], nv = p.nvalid[sidx];
+                for (int q = 0; q < nv; q++) sg += p.sigrow[j0 + q];
+            }
             for (int l = 0; l < p.n_hidden; l++, lcount++) {
                 const int db = lcount & 1;
                 const bool last = (l == p.n_hidden - 1);
@@ -773,14 +779,10 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 }
                 tc_fence_before();
                 mbar_arrive(BAR(D_EMPTY + db));
-                const int sidx = (last && c < Sv) ? p.csample[c] : -1;
-                if (sidx >= 0 && !(p.dbg & 256)) {
+                if (last && sidx >= 0) {
                     const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
                                 s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
                     const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
-                    float sg = 0.f;
-                    const int j0 = p.tuple_start[sidx], nv = p.nvalid[sidx];
-                    for (int q = 0; q < nv; q++) sg += p.sigrow[j0 + q];
                     ((float4*)p.decoded)[sidx] = make_float4(sg, s0 * m - o, s1 * m - o, s2 * m - o);
                 }
             }
@@ -802,8 +804,9 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 const int s = n % C_RING;
                 const uint32_t base = sbase + COFF_RING + s * C_PANEL;
                 if (kp < 4) {
+                    // every loader thread follows every phase of the stage (a parity wait is only unambiguous one phase ahead)
+                    mbar_wait(BAR(R_EMPTY + s), ph_empty[s]);
                     if (lt == 0) {
-                        mbar_wait(BAR(R_EMPTY + s), ph_empty[s]);
                         if (p.dbg & 128) mbar_arrive(BAR(R_FULL + s));
                         else {
                             mbar_expect_tx(BAR(R_FULL + s), C_PANEL);
@@ -812,33 +815,19 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                     }
                     ph_empty[s] ^= 1;
                 } else {
-                    // view-direction encoding (ori=True, first three stripped): sin(v_d 2^f) d-major, then the cosines; cols [6 fv, 32) = 0
+                    // view-direction encoding of the sample's ray: 32 bf16 (cols [6 fv, 32) = 0) precomputed per ray
                     const int r = lt;
-                    float vals[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) vals[i] = 0.f;
+                    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0, v3 = v0;
                     const int sidx_r = (c0 + r < Sv && !(p.dbg & 64)) ? p.csample[c0 + r] : -1;
                     if (sidx_r >= 0) {
-                        const int64_t ray = sidx_r / p.SR;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            if (i < 3 * p.fv) {
-                                const int dd = i / p.fv, f = i - dd * p.fv;
-                                float sn, cs;
-                                sincosf(p.raydir[3 * ray + dd] * exp2f((float)f), &sn, &cs);
-#pragma unroll
-                                for (int j = 0; j < 32; j++) {
-                                    if (j == i) vals[j] = sn;
-                                    if (j == i + 3 * p.fv) vals[j] = cs;
-                                }
-                            }
-                        }
+                        const uint4* src = (const uint4*)(p.vtab + (size_t)(sidx_r / p.SR) * 64);
+                        v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2); v3 = __ldg(src + 3);
                     }
                     mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        sts128(base + r * 128 + ((q ^ (r & 7)) << 4), pack_bf16(vals[8 * q], vals[8 * q + 1]), pack_bf16(vals[8 * q + 2], vals[8 * q + 3]),
-                               pack_bf16(vals[8 * q + 4], vals[8 * q + 5]), pack_bf16(vals[8 * q + 6], vals[8 * q + 7]));
+                    sts128(base + r * 128 + ((0 ^ (r & 7)) << 4), v0.x, v0.y, v0.z, v0.w);
+                    sts128(base + r * 128 + ((1 ^ (r & 7)) << 4), v1.x, v1.y, v1.z, v1.w);
+                    sts128(base + r * 128 + ((2 ^ (r & 7)) << 4), v2.x, v2.y, v2.z, v2.w);
+                    sts128(base + r * 128 + ((3 ^ (r & 7)) << 4), v3.x, v3.y, v3.z, v3.w);
                     fence_proxy_async();
                     asm volatile("bar.sync 3, 128;" ::: "memory");
                     if (lt == 0) mbar_arrive(BAR(R_FULL + s));
@@ -917,6 +906,25 @@ __global__ void __launch_bounds__(256) tc_point_rows_kernel(const float* __restr
         const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
         sn = s2; cs_ = c2;
     }
+}
+
+// Per-ray view-direction encoding (ori=True with the first three stripped, point_aggregators.py:579-585): 32 bf16 per ray,
+// [sin(v_d 2^f) d-major (3 fv) | cos(..) (3 fv) | 0...]; the colour kernel's fifth operand panel is a copy of these rows.
+__global__ void tc_viewdir_rows_kernel(const float* __restrict__ raydir, int64_t R, int fv, uint8_t* __restrict__ vtab)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * 32) return;
+    const int64_t ray = i >> 5;
+    const int j = (int)(i & 31);
+    float v = 0.f;
+    if (j < 6 * fv) {
+        const int jj = j < 3 * fv ? j : j - 3 * fv;
+        const int dd = jj / fv, f = jj - dd * fv;
+        float sn, cs;
+        sincosf(raydir[3 * ray + dd] * exp2f((float)f), &sn, &cs);
+        v = j < 3 * fv ? sn : cs;
+    }
+    ((__nv_bfloat16*)vtab)[i] = __float2bfloat16_rn(v);
 }
 
 // Tile table: tile t owns the compact samples whose first tuple index lies in [t*TW, (t+1)*TW).  One thread per compact sample.
@@ -1000,7 +1008,7 @@ struct TcWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles, *padslots, *cpad0, *csample_pad, *tpartials;
     int2* tile_tab;
     float *loc_pers, *wc, *sigrow;
-    uint8_t *wpack, *cpack, *ptab, *bpack, *apack, *F;
+    uint8_t *wpack, *cpack, *ptab, *bpack, *apack, *F, *vtab;
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
@@ -1036,6 +1044,7 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     ws->cpack = A.take<uint8_t>((size_t)C_W_PANELS * C_PANEL);
     ws->bpack = A.take<uint8_t>((size_t)TC_MAX_LAYERS * BIAS_PANEL_B);
     ws->apack = A.take<uint8_t>(ALPHA_PANEL_B);
+    ws->vtab = A.take<uint8_t>((size_t)Rc * 64);
     ws->ptab = A.take<uint8_t>((size_t)N * TC_PT_BYTES);
     return A.off;
 }
@@ -1139,7 +1148,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     tp.K = K; tp.SR = SR;
     { const char* e = getenv("SGN_TC_DEBUG"); tp.dbg = e ? atoi(e) : 0; }
     cp.dbg = tp.dbg;
-    cp.wpack = ws.cpack; cp.n_hidden = P.n_color_hidden; cp.fv = d.FV;
+    cp.wpack = ws.cpack; cp.n_hidden = P.n_color_hidden;
     cp.wl = weights[P.n_layers - 1]; cp.bl = biases[P.n_layers - 1];
     cp.slope = d.slope; cp.act_super = d.act_super; cp.SR = SR;
     const int TW = tile_width(K);
@@ -1184,7 +1193,8 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
         cp.S_ptr = ws.cpad0 + (ncap + 1); cp.S_max = spad; cp.csample = ws.csample_pad; cp.F = ws.F; cp.sigrow = ws.sigrow;
         cp.tuple_start = ws.tuple_start; cp.nvalid = ws.nvalid;
-        cp.raydir = in.raydir; cp.decoded = dec;
+        launch(tc_viewdir_rows_kernel, cdiv(Rc * 32, 256), 256, 0, st, in.raydir, Rc, d.FV, ws.vtab);
+        cp.vtab = ws.vtab; cp.decoded = dec;
         const int max_ctiles = cdiv(spad, TC_ROWS);
         launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, 288, C_SMEM, st, cp);
         SGN_LAUNCH_CHECK();
