@@ -173,6 +173,12 @@ int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const fl
                      float* const* d_weights, float* const* d_biases, const SgnPointGrads* d_tables,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement aid (bench.py's roofline): when enabled, the bf16 path brackets its dominant kernel, agg_tuple_tc_kernel, with
+ * CUDA events on the launching stream (this serialises the host with the previous call's kernel; leave it off otherwise).
+ * sgn_agg_kernel_timing_read returns the summed duration and the number of timed launches since it was enabled. */
+int sgn_agg_kernel_timing(int enable);
+int sgn_agg_kernel_timing_read(float* total_ms, int* launches);
+
 /* ------------------------------------------------------------------------------------------------
  * Compositing.  Replaces ray_march / alpha_ray_march (diff_ray_marching.py:509-573) with
  * render_func = radiance and blend_func = alpha (blend = 0) or alpha2 (blend = 1)

@@ -1070,6 +1070,38 @@ static int tc_supported(const AggPlan& P, int K)
 
 using namespace sgn;
 
+// Optional timing of the dominant kernel (agg_tuple_tc_kernel) with CUDA events on the launching stream, for bench.py's roofline.
+static bool g_tc_timing = false;
+static cudaEvent_t g_tc_ev[2] = {nullptr, nullptr};
+static float g_tc_ms_sum = 0.f;
+static int g_tc_ms_n = 0, g_tc_pending = 0;
+
+static void tc_timing_collect()
+{
+    if (g_tc_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_tc_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, g_tc_ev[0], g_tc_ev[1]) == cudaSuccess) { g_tc_ms_sum += ms; g_tc_ms_n++; }
+        g_tc_pending = 0;
+    }
+}
+
+extern "C" int sgn_agg_kernel_timing(int enable)
+{
+    tc_timing_collect();
+    g_tc_timing = enable != 0;
+    g_tc_ms_sum = 0.f; g_tc_ms_n = 0;
+    if (g_tc_timing && !g_tc_ev[0]) { SGN_CUDA(cudaEventCreate(&g_tc_ev[0])); SGN_CUDA(cudaEventCreate(&g_tc_ev[1])); }
+    return SGN_OK;
+}
+
+extern "C" int sgn_agg_kernel_timing_read(float* total_ms, int* launches)
+{
+    tc_timing_collect();
+    if (total_ms) *total_ms = g_tc_ms_sum;
+    if (launches) *launches = g_tc_ms_n;
+    return SGN_OK;
+}
+
 int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes)
 {
     int rc = tc_supported(P, K);
@@ -1187,8 +1219,10 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         // clusters of two CTAs (a TPC's SM pair); every cluster takes four tiles per cycle
         const int max_clusters = (tp.ntiles_cap + 3) / 4;
         const int n_clusters = max_clusters < n_sm / 2 ? max_clusters : n_sm / 2;
+        if (g_tc_timing) { tc_timing_collect(); cudaEventRecord(g_tc_ev[0], st); }
         if (tp.dbg) launch(agg_tuple_tc_kernel<true>, 2 * n_clusters, TC_THREADS, TC_SMEM, st, tp);
         else launch(agg_tuple_tc_kernel<false>, 2 * n_clusters, TC_THREADS, TC_SMEM, st, tp);
+        if (g_tc_timing) { cudaEventRecord(g_tc_ev[1], st); g_tc_pending = 1; }
 
         // per-sample colour MLP + rgb + (sigma, r, g, b) store
         cp.S_ptr = ws.cpad0 + (ncap + 1); cp.S_max = spad; cp.csample = ws.csample_pad; cp.F = ws.F; cp.sigrow = ws.sigrow;
