@@ -33,17 +33,18 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_W = 256;                 // layer width == accumulator columns
 constexpr int TC_C = 32, TC_F = 3, TC_FD = 5;
 constexpr int TC_PT_COLS = TC_C * (1 + 2 * TC_F);              // 224 per-point columns: emb | PE(emb)
-constexpr int TC_PT_BYTES = TC_PT_COLS * 2;                    // 448
-constexpr int TC_K0 = TC_PT_COLS + 2 * TC_FD * 6;              // 284; cols 284, 285 of the operand hold 1.0 (bias columns)
-static_assert(TC_K0 + 2 <= 4 * 64 + 32, "the two bias columns must fit in the first layer K padding");
+// block1.0 has 284 inputs: 224 per point (hoisted, see tc_point_l0_kernel) + 60 per tuple
+constexpr int TC_KD = 2 * TC_FD * 6;                           // 60 PE(dists) columns: the per-tuple K of the first layer, + 2 bias columns (1.0)
+constexpr int X0_PANEL = 3;                                    // panel of the slot that holds [PE(dists) | 1 | 1 | 0 | 0] during the first layer
+static_assert(TC_KD + 2 <= 64, "PE(dists) and the two bias columns must fit in one K panel");
 constexpr int TC_MAX_LAYERS = 6;
 constexpr int PANEL_A = TC_PANEL_BYTES;   // 16 KB: 128 rows x 64 bf16
 constexpr int PANEL_B = TC_W * 128;       // 32 KB: 256 rows x 64 bf16
 constexpr int PANEL_BH = PANEL_B / 2;     // 16 KB: this CTA's half (128 of the 256 output columns) of a weight panel
 constexpr int SLOT_PANELS = 5, SLOT_BYTES = SLOT_PANELS * PANEL_A, B_STAGES = 4;
 constexpr int E7_COL0 = 32;               // inside panel 4: cols [32,48) hold [colour | dir-view | dir.view | 1 | 1 | 0..]
-constexpr int ONES_KSTEP = 1;             // K-step of panel 4 that holds operand cols 272..287, i.e. the two 1.0 columns at 12, 13
-constexpr int META_CHUNK = 6;             // 16-byte chunks 6, 7 of a row of panel 4: {w*conf, sample slot, first padded sample, #slots | passes << 16}, {tuple index}
+constexpr int ONES_KSTEP = 1;             // K-step of panel 4 (cols 16..31) that is zero except for 1.0 at its columns 12, 13 (bias K-step operand)
+constexpr int META_CHUNK = 6;             // 16-byte chunks 6, 7 of a row of panel 4: {w*conf, sample slot, first padded sample, #slots | passes << 16}, {tuple index, point index}
 constexpr int KS_SLOTS = 56;              // sample slots per CTA and K-sum pass (Sel^T = 2 K-panels x 56 x 128 B, inside panel 4)
 constexpr int KS_N = 2 * KS_SLOTS;        // the pair's K-sum MMA: columns [0,56) = leader CTA's samples, [56,112) = peer CTA's
 constexpr int BIAS_PANEL_B = TC_W * 32;   // 8 KB: compact (unswizzled) [256 x 16] bias K-step (4 KB per CTA)
@@ -75,7 +76,7 @@ struct TcParams {
     const int32_t* cpad0;                  // [ntiles + 1] first PADDED sample index of every tile (each tile's samples padded to a multiple of 8)
     const int32_t* tuple_src; const int32_t* sample_cidx;
     const float* loc_pers; const float* wc;
-    const uint8_t* ptab;                   // [N][224] bf16 per-point rows
+    const uint8_t* p0tab;                  // [N][256] bf16: point part of the first layer (tc_point_l0_kernel)
     const uint8_t* wpack;                  // pre-swizzled bf16 weight panels, all layers back to back
     const uint8_t* bpack[TC_MAX_LAYERS];   // compact bias K-step of the layer, or NULL when the bias rides in a weight panel
     const uint8_t* apack;                  // alpha_branch panel
@@ -152,17 +153,12 @@ __device__ __forceinline__ void tc_commit2(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t r;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(r));
     return r != 0;
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -259,12 +255,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
         for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
             int nslots0 = 0, nslots1 = 0, npass0 = 1, npass1 = 1, c00 = 0, c01 = 0, slr0 = -1, slr1 = -1, j0 = 0, j1 = 0;
             float wcr0 = 0.f, wcr1 = 0.f;
+            const uint4* p0row = (const uint4*)p.p0tab + h2 * 16;
             tcount += 2;
             for (int l = 0; l < p.n_layers; l++) {
                 const bool last = (l == p.n_layers - 1);
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     if (prof) pf_t0 = clock64();
+                    uint4 pa[4], pb[4];
                     mbar_wait(BAR(D_FULL + s), (ph_d >> s) & 1u); ph_d ^= 1u << s;
                     tc_fence_after();
                     if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
@@ -272,7 +270,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     if (l == 0) {
                         // this row's {w*conf, sample slot, first compact sample of the tile, #sample slots | K-sum passes << 16}
                         const uint4 m = lds128u(slot_base + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4));
-                        const int j = (int)lds128u(slot_base + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4)).x;
+                        const uint4 m2 = lds128u(slot_base + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4));
+                        const int j = (int)m2.x;
+                        // this row's 128 columns of P0[pt] (bf16), fetched two 32-column chunks ahead of their use
+                        p0row = (const uint4*)(p.p0tab + (size_t)m2.y * (TC_W * 2)) + h2 * 16;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { pa[q] = __ldg(p0row + q); pb[q] = __ldg(p0row + 4 + q); }
                         if (s == 0) { wcr0 = __uint_as_float(m.x); slr0 = (int)m.y; c00 = (int)m.z; nslots0 = (int)(m.w & 0xffffu); npass0 = (int)(m.w >> 16); j0 = j; }
                         else { wcr1 = __uint_as_float(m.x); slr1 = (int)m.y; c01 = (int)m.z; nslots1 = (int)(m.w & 0xffffu); npass1 = (int)(m.w >> 16); j1 = j; }
                     }
@@ -292,15 +295,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                         }
                     };
                     uint32_t v0[32], v1[32];
-                    tc_ld32_nowait(acc_addr, v0);
+                    if (l == 0) {
+                        // first layer: add the point part P0[pt] (bf16) to the accumulator before the activation
+                        // x = acc + P0 in fp32 (P0 unpacked from bf16), then LeakyReLU in bf16 as in the other layers
+                        auto chunk0 = [&](int c, const uint32_t(&vv)[32], const uint4(&pq)[4]) {
+                            const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t w[4] = {pq[q].x, pq[q].y, pq[q].z, pq[q].w};
+                                uint32_t o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++)
+                                    o[e] = leaky_pack(__float_as_uint(__uint_as_float(vv[8 * q + 2 * e]) + __uint_as_float(w[e] << 16)),
+                                                      __float_as_uint(__uint_as_float(vv[8 * q + 2 * e + 1]) + __uint_as_float(w[e] & 0xffff0000u)), slope2);
+                                const int ch = (c & 1) * 4 + q;
+                                sts128(rowbase + ((ch ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+                            }
+                        };
+                        tc_ld32_nowait(acc_addr, v0);
 #pragma unroll 1
-                    for (int cp = 0; cp < 2; cp++) {
-                        tc_wait_ld(v0);
-                        tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                        chunk(2 * cp, v0);
-                        tc_wait_ld(v1);
-                        if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
-                        chunk(2 * cp + 1, v1);
+                        for (int cp = 0; cp < 2; cp++) {
+                            tc_wait_ld(v0);
+                            tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
+                            chunk0(2 * cp, v0, pa);
+                            if (cp == 0) {
+#pragma unroll
+                                for (int q = 0; q < 4; q++) pa[q] = __ldg(p0row + 8 + q);
+                            }
+                            tc_wait_ld(v1);
+                            if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
+                            chunk0(2 * cp + 1, v1, pb);
+                            if (cp == 0) {
+#pragma unroll
+                                for (int q = 0; q < 4; q++) pb[q] = __ldg(p0row + 12 + q);
+                            }
+                        }
+                    } else {
+                        tc_ld32_nowait(acc_addr, v0);
+#pragma unroll 1
+                        for (int cp = 0; cp < 2; cp++) {
+                            tc_wait_ld(v0);
+                            tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
+                            chunk(2 * cp, v0);
+                            tc_wait_ld(v1);
+                            if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
+                            chunk(2 * cp + 1, v1);
+                        }
                     }
                     if (last) {
                         // H is in the panels; selection matrix of K-sum pass 0 next to it: Sel[sample slot][row] = w*conf (bf16)
@@ -405,14 +445,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
             const int npass = max(1, (max(nsl, pslots) + KS_SLOTS - 1) / KS_SLOTS);   // the pair runs the same number of K-sum passes
             const bool live = row < tb.x - ta.x && !(kDbg && (p.dbg & 4));
             uint32_t pe[32], e7p[4] = {0u, 0u, 0u, 0u};
-            float wcv = 0.f; int slot = -1;
-            const uint8_t* src = p.ptab;
+            float wcv = 0.f; int slot = -1; int ptv = 0;
             if (live) {
                 const int flat = p.tuple_src[ta.x + row];
                 const int64_t sm = flat / p.K;
                 const int64_t r = sm / p.SR;
                 const int64_t pt = p.in.pidx[flat];
-                src = p.ptab + (size_t)pt * TC_PT_BYTES;
+                ptv = (int)pt;
+                const uint8_t* src = p.p0tab + (size_t)pt * (TC_W * 2);          // the epilogue reads this row: bring it into L2 now
                 prefetch_l2(src); prefetch_l2(src + 128); prefetch_l2(src + 256); prefetch_l2(src + 384);
                 wcv = p.wc[flat];
                 slot = p.sample_cidx[sm] - ta.y;
@@ -442,29 +482,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                         sn = s2; cs_ = c2;
                     }
                 }
-                pe[30] = one_one; pe[31] = 0u;                                   // cols 284, 285 = 1 (bias columns), 286, 287 = 0
+                pe[30] = one_one; pe[31] = 0u;                                   // cols 60, 61 = 1 (bias columns), 62, 63 = 0
             }
             if (prof) { const long long t1 = clock64(); gf_load += t1 - gf_t0; gf_t0 = t1; }
             mbar_wait(BAR(BUF_FREE + s), ph_free); ph_free ^= 1;
             if (prof) { const long long t1 = clock64(); gf_wait += t1 - gf_t0; gf_t0 = t1; }
-            if (live) {
-                // cols [0,224): the point's precomputed row, 28 x 16 bytes; cols [224,288): PE(dists) + bias columns; [288,304): E7 | 1 | 1
+            // first-layer operand of the row, panel 3: [PE(dists) (60) | 1 | 1 | 0 | 0]; dead rows are all zero (what is left in the
+            // panel from the previous tile must not reach the MMAs).  Panel 4: K-step 1 = (0 x12, 1, 1, 0, 0) for the bias K-steps,
+            // K-step 2 = [colour | dir-view | dir.view | 1 | 1 | 0..] for block3.0, chunks 6, 7 = per-row metadata for the epilogue.
+            const uint32_t xrow = x0 + X0_PANEL * PANEL_A + row * 128, prow = x0 + 4 * PANEL_A + row * 128;
 #pragma unroll
-                for (int i = 0; i < TC_PT_BYTES / 16; i++) cp_async16(x0 + sw_off(row, 8 * i), src + 16 * i);
-#pragma unroll
-                for (int q = 0; q < 8; q++) sts128(x0 + sw_off(row, TC_PT_COLS + 8 * q), pe[4 * q], pe[4 * q + 1], pe[4 * q + 2], pe[4 * q + 3]);
-                const int col = 4 * 64 + E7_COL0;
-                sts128(x0 + sw_off(row, col), e7p[0], e7p[1], e7p[2], e7p[3]);
-                sts128(x0 + sw_off(row, col + 8), pack_bf16(1.0f, 0.f), 0u, 0u, 0u);
-            } else {
-                // dead row: all-zero operand (what is left in the slot from the previous tile must not reach the MMAs)
-#pragma unroll
-                for (int i = 0; i < (4 * 64 + E7_COL0 + 16) / 8; i++) sts128(x0 + sw_off(row, 8 * i), 0u, 0u, 0u, 0u);
+            for (int q = 0; q < 8; q++) {
+                if (live) sts128(xrow + ((q ^ (row & 7)) << 4), pe[4 * q], pe[4 * q + 1], pe[4 * q + 2], pe[4 * q + 3]);
+                else sts128(xrow + ((q ^ (row & 7)) << 4), 0u, 0u, 0u, 0u);
             }
+            sts128(prow + ((2 ^ (row & 7)) << 4), 0u, 0u, 0u, 0u);
+            sts128(prow + ((3 ^ (row & 7)) << 4), 0u, 0u, live ? one_one : 0u, 0u);
+            sts128(prow + ((4 ^ (row & 7)) << 4), e7p[0], e7p[1], e7p[2], e7p[3]);
+            sts128(prow + ((5 ^ (row & 7)) << 4), live ? pack_bf16(1.0f, 0.f) : 0u, 0u, 0u, 0u);
             sts128(x0 + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4), __float_as_uint(wcv), (uint32_t)slot, (uint32_t)cpad,
                    (uint32_t)nsl | ((uint32_t)npass << 16));
-            sts128(x0 + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4), (uint32_t)(ta.x + row), 0u, 0u, 0u);
-            cp_async_wait_all();
+            sts128(x0 + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4), (uint32_t)(ta.x + row), (uint32_t)ptv, 0u, 0u);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(x_full);
@@ -558,10 +596,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                         for (int kp = 0; kp < np; kp++) {
                             uint32_t a_addr = a_base + kp * PANEL_A;
                             int ksteps = 4;
-                            if (kp == 4) {
-                                if (kind == LAYER_FROM_X0) ksteps = 2;                                   // cols 256..287
-                                else { a_addr += E7_COL0 * 2; ksteps = 1; }                             // [colour | dir-view | dir.view | 1 | 1] of block3.0
-                            }
+                            if (kind == LAYER_FROM_X0) a_addr = a_base + X0_PANEL * PANEL_A;            // [PE(dists) | 1 | 1 | 0 | 0], one panel
+                            else if (kp == 4) { a_addr += E7_COL0 * 2; ksteps = 1; }                    // [colour | dir-view | dir.view | 1 | 1] of block3.0
                             const uint32_t st = next_stage();
                             const uint64_t ad = umma_desc(a_addr), bd = umma_desc(sbase + OFF_WRING + st * PANEL_BH);
                             if (elect_one()) {                                                           // one lane issues the panel's K-steps back to back
@@ -887,25 +923,107 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// Per-point operand rows: ptab[p] = bf16 [emb (32) | sin, cos of emb_c * 2^f, (c, f) major (192)] -- exactly the first 224
-// columns of the reference's `feat` (point_aggregators.py:603-611).  One warp per point, lane = channel.
-__global__ void __launch_bounds__(256) tc_point_rows_kernel(const float* __restrict__ emb, int64_t N, uint8_t* __restrict__ ptab)
+// Point part of the first per-neighbour layer, hoisted out of the per-tuple work: block1.0 is linear in its input
+// [emb | PE(emb) | PE(dists)], and the first 224 columns depend on the POINT only, so
+//     P0[pt] = W0[:, 0:224] . [emb_pt | sin, cos of emb_pt,c * 2^f]        (fp32 accumulate, stored bf16, [N][256])
+// is computed once per call for every point (N rows) instead of once per tuple (13x more rows at C1); the per-tuple kernel
+// adds it to its K = 64 GEMM over PE(dists) in the first epilogue.  One CTA per SM, tile = 128 points, the four weight panels
+// (cols 0..255 of W0; the operand's cols 224..255 are zero) resident in shared memory, tcgen05.mma 128x256x16, cta_group::1.
+constexpr int P0_OFF_W = 0, P0_OFF_A = 4 * PANEL_B, P0_OFF_BAR = P0_OFF_A + 4 * PANEL_A, P0_SMEM = P0_OFF_BAR + 64 + 1024;
+__global__ void __launch_bounds__(128, 1) tc_point_l0_kernel(const float* __restrict__ emb, int64_t N, const uint8_t* __restrict__ wpack0,
+                                                              uint8_t* __restrict__ p0tab)
 {
-    const int64_t pnt = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pnt >= N) return;
-    const int c = threadIdx.x & 31;
-    const float e = emb[pnt * TC_C + c];
-    uint8_t* row = ptab + (size_t)pnt * TC_PT_BYTES;
-    *(__nv_bfloat16*)(row + 2 * c) = __float2bfloat16_rn(e);
-    float sn, cs_;
-    __sincosf(e, &sn, &cs_);
-    uint32_t* pe = (uint32_t*)(row + 2 * TC_C + 4 * TC_F * c);
-#pragma unroll
-    for (int f = 0; f < TC_F; f++) {
-        pe[f] = pack_bf16(sn, cs_);
-        const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
-        sn = s2; cs_ = c2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t bar_w = sbase + P0_OFF_BAR, bar_d = bar_w + 8;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(smem + P0_OFF_BAR + 16);
+    if (tid == 0) {
+        mbar_init(bar_w, 1); mbar_init(bar_d, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, 4 * PANEL_B);
+        for (int i = 0; i < 4; i++) bulk_g2s(sbase + P0_OFF_W + i * PANEL_B, wpack0 + (size_t)i * PANEL_B, PANEL_B, bar_w);
+    }
+    const int64_t ntile = (N + TC_ROWS - 1) / TC_ROWS;
+    uint32_t ph_d = 0;
+    const uint32_t x0 = sbase + P0_OFF_A;
+    const int row = tid;
+    for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const int64_t pt = tile * TC_ROWS + row;
+        // ---- operand row: [emb | sin, cos of emb_c 2^f (c, f major) | 0 (cols 224..255)]
+        float e[TC_C];
+        if (pt < N) {
+#pragma unroll
+            for (int i = 0; i < TC_C / 4; i++) {
+                const float4 v = __ldg((const float4*)(emb + pt * TC_C) + i);
+                e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TC_C; i++) e[i] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            sts128(x0 + sw_off(row, 8 * q), pack_bf16(e[8 * q], e[8 * q + 1]), pack_bf16(e[8 * q + 2], e[8 * q + 3]),
+                   pack_bf16(e[8 * q + 4], e[8 * q + 5]), pack_bf16(e[8 * q + 6], e[8 * q + 7]));
+#pragma unroll
+        for (int c = 0; c < TC_C; c++) {
+            float sn, cs_;
+            __sincosf(e[c], &sn, &cs_);
+#pragma unroll
+            for (int f = 0; f < TC_F; f++) {
+                sts32(x0 + sw_off(row, TC_C + 2 * (c * TC_F + f)), pack_bf16(sn, cs_));
+                const float s2 = 2.0f * sn * cs_, c2 = 1.0f - 2.0f * sn * sn;
+                sn = s2; cs_ = c2;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) sts128(x0 + sw_off(row, TC_PT_COLS + 8 * q), 0u, 0u, 0u, 0u);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(bar_w, 0);                               // weights resident (completes once; later waits return at once)
+            tc_fence_after();
+            for (int kp = 0; kp < 4; kp++)
+                for (int k = 0; k < 4; k++)
+                    tc_mma(tmem_base, umma_desc(x0 + kp * PANEL_A + k * 32), umma_desc(sbase + P0_OFF_W + kp * PANEL_B + k * 32), tc_idesc(TC_ROWS, TC_W),
+                           (kp | k) != 0);
+            tc_commit(bar_d);
+        }
+        mbar_wait(bar_d, ph_d); ph_d ^= 1;
+        tc_fence_after();
+        // ---- epilogue: 256 fp32 accumulators of this point -> bf16 row
+        uint8_t* dst = p0tab + (size_t)pt * (TC_W * 2);
+#pragma unroll 1
+        for (int ch = 0; ch < TC_W / 32; ch++) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+            if (pt < N) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *(uint4*)(dst + ch * 64 + q * 16) = make_uint4(pack_bf16(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])),
+                                                                   pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                                                                   pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                                                                   pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                       // accumulator and operand tile are free again
+        tc_fence_after();
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
 // Per-ray view-direction encoding (ori=True with the first three stripped, point_aggregators.py:579-585): 32 bf16 per ray,
@@ -965,9 +1083,9 @@ __global__ void tc_csample_pad_kernel(const int32_t* __restrict__ S_ptr, int S_m
     csample_pad[cpad0[t] + (c - tile_tab[t].y)] = sidx;
 }
 
-// torch Linear weight [Nvalid, K_in] fp32 -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (Nrows x 128 bytes each).
+// torch Linear weight [Nvalid, K_in] fp32 (row stride ldw) -> bf16 panels of 64 K-columns in the 128B-swizzled smem image (Nrows x 128 bytes each).
 // With `bias`, columns K_in and K_in + 1 carry the bias split into two bf16 (hi + lo): the matching operand columns hold 1.0.
-__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, int Nvalid, int Kin, int npanels, const float* __restrict__ bias,
+__global__ void tc_pack_weight_kernel(const float* __restrict__ W, int ldw, int Nrows, int Nvalid, int Kin, int npanels, const float* __restrict__ bias,
                                       uint8_t* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk (8 bf16)
@@ -979,7 +1097,7 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ W, int Nrows, in
         const int k = pnl * 64 + ch * 8 + e;
         float x = 0.f;
         if (n < Nvalid) {
-            if (k < Kin) x = W[(size_t)n * Kin + k];
+            if (k < Kin) x = W[(size_t)n * ldw + k];
             else if (bias && k == Kin) x = __bfloat162float(__float2bfloat16_rn(bias[n]));
             else if (bias && k == Kin + 1) x = bias[n] - __bfloat162float(__float2bfloat16_rn(bias[n]));
         }
@@ -1008,7 +1126,7 @@ struct TcWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles, *padslots, *cpad0, *csample_pad, *tpartials;
     int2* tile_tab;
     float *loc_pers, *wc, *sigrow;
-    uint8_t *wpack, *cpack, *ptab, *bpack, *apack, *F, *vtab;
+    uint8_t *wpack, *cpack, *p0tab, *p0pack, *bpack, *apack, *F, *vtab;
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
@@ -1039,13 +1157,14 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     ws->loc_pers = A.take<float>(S * 3); ws->wc = A.take<float>(T);
     ws->F = A.take<uint8_t>((spad / TC_ROWS + 2) * F_TILE_BYTES); ws->sigrow = A.take<float>(T + 1);
     size_t panels = 0;
-    for (int t = 0; t < P.n_tuple_layers; t++) panels += (size_t)(P.layers[t].in + 63) / 64;
+    for (int t = 0; t < P.n_tuple_layers; t++) panels += t == 0 ? 1 : (size_t)(P.layers[t].in + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
     ws->cpack = A.take<uint8_t>((size_t)C_W_PANELS * C_PANEL);
     ws->bpack = A.take<uint8_t>((size_t)TC_MAX_LAYERS * BIAS_PANEL_B);
     ws->apack = A.take<uint8_t>(ALPHA_PANEL_B);
     ws->vtab = A.take<uint8_t>((size_t)Rc * 64);
-    ws->ptab = A.take<uint8_t>((size_t)N * TC_PT_BYTES);
+    ws->p0pack = A.take<uint8_t>((size_t)4 * PANEL_B);
+    ws->p0tab = A.take<uint8_t>((size_t)(N + TC_ROWS) * (TC_W * 2));
     return A.off;
 }
 
@@ -1131,6 +1250,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
+        SGN_CUDA(cudaFuncSetAttribute(tc_point_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
         attr_set = true;
     }
     int dev = 0, n_sm = 148;
@@ -1143,12 +1263,21 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     tp.first_panel[0] = 0;
     for (int t = 0; t < P.n_tuple_layers; t++) {
         const LayerInfo& L = P.layers[t];
-        const int np = (L.in + 63) / 64;
         tp.kind[t] = t == 0 ? LAYER_FROM_X0 : (L.extra == EXTRA_COLORDIR ? LAYER_FROM_ACT_E7 : LAYER_FROM_ACT);
         // the bias rides in the weight panel where the operand has spare columns (first layer, colour/dir layer), else in its own K-step
         const bool folded = tp.kind[t] != LAYER_FROM_ACT;
-        launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], TC_W, TC_W, L.in, np, folded ? biases[t] : (const float*)nullptr,
-               ws.wpack + (size_t)tp.first_panel[t] * PANEL_B);
+        uint8_t* dst = ws.wpack + (size_t)tp.first_panel[t] * PANEL_B;
+        int np;
+        if (t == 0) {
+            // first layer: the per-tuple part only, W0[:, 224:284] + bias -> one panel; the point part W0[:, 0:224] feeds tc_point_l0_kernel
+            np = 1;
+            launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t] + TC_PT_COLS, L.in, TC_W, TC_W, TC_KD, np, biases[t], dst);
+            launch(tc_pack_weight_kernel, cdiv((int64_t)4 * TC_W * 8, 256), 256, 0, st, weights[t], L.in, TC_W, TC_W, TC_PT_COLS, 4, (const float*)nullptr, ws.p0pack);
+        } else {
+            np = (L.in + 63) / 64;
+            launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], L.in, TC_W, TC_W, L.in, np,
+                   folded ? biases[t] : (const float*)nullptr, dst);
+        }
         tp.first_panel[t + 1] = tp.first_panel[t] + np;
         tp.bpack[t] = nullptr;
         if (!folded) {
@@ -1162,7 +1291,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         for (int c = 0; c < P.n_color_hidden; c++) {
             const int l = P.color_layer0 + c;
             const int np = c == 0 ? C_K0_PANELS : 2;
-            launch(tc_pack_weight_kernel, cdiv((int64_t)np * CW * 8, 256), 256, 0, st, weights[l], CW, CW, P.layers[l].in, np, (const float*)nullptr,
+            launch(tc_pack_weight_kernel, cdiv((int64_t)np * CW * 8, 256), 256, 0, st, weights[l], P.layers[l].in, CW, CW, P.layers[l].in, np, (const float*)nullptr,
                    ws.cpack + (size_t)pnl * C_PANEL);
             pnl += np;
             cp.bias[c] = biases[l];
@@ -1170,11 +1299,14 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     }
     // alpha panel: per CTA of the pair four K panels of 8 rows; rank 0's row 0 is the weight vector, everything else zero
     SGN_CUDA(cudaMemsetAsync(ws.apack, 0, ALPHA_PANEL_B, st));
-    launch(tc_pack_weight_kernel, cdiv((int64_t)4 * 8 * 8, 256), 256, 0, st, weights[P.alpha_layer], 8, 1, TC_W, 4, (const float*)nullptr, ws.apack);
-    launch(tc_point_rows_kernel, cdiv(tables->N, 8), 256, 0, st, tables->embedding, tables->N, ws.ptab);
+    launch(tc_pack_weight_kernel, cdiv((int64_t)4 * 8 * 8, 256), 256, 0, st, weights[P.alpha_layer], TC_W, 8, 1, TC_W, 4, (const float*)nullptr, ws.apack);
+    {
+        const int64_t ptiles = (tables->N + TC_ROWS - 1) / TC_ROWS;
+        launch(tc_point_l0_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->embedding, tables->N, ws.p0pack, ws.p0tab);
+    }
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
-    tp.wpack = ws.wpack; tp.ptab = ws.ptab;
+    tp.wpack = ws.wpack; tp.p0tab = ws.p0tab;
     tp.apack = ws.apack; tp.ba = biases[P.alpha_layer];
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;
