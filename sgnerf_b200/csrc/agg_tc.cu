@@ -681,7 +681,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
 // swizzled panel image, so four bulk copies (TMA) per tile bring them into a 2-stage ring (the next tile is prefetched into
 // L2 meanwhile); the fifth panel, the view-direction encoding, is computed by the loader warps.  The 128-wide activations live in place in two panels; the last Linear (128 -> 3), the
 // sigmoid and the (sigma, r, g, b) store are fused into the last epilogue.
-//   warps 0-3 epilogue | warps 4-7 loaders | warp 8 MMA issuer (and the one-off weight load)
+//   warps 0-7 epilogue (two column halves) | warps 8-11 loaders | warp 12 MMA issuer (and the one-off weight load)
 constexpr int CW = 128;                                   // colour hidden width
 constexpr int C_PANEL = CW * 128;                         // 16 KB: 128 rows x 64 bf16 (A and B panels alike)
 constexpr int C_K0_PANELS = 5, C_RING = 2, C_MAX_HIDDEN = 3;
@@ -691,7 +691,9 @@ constexpr int COFF_RING = COFF_W + C_W_PANELS * C_PANEL;
 constexpr int COFF_ACT = COFF_RING + C_RING * C_PANEL;
 constexpr int COFF_BIAS = COFF_ACT + 2 * C_PANEL;                           // [3][128] hidden biases
 constexpr int COFF_WL = COFF_BIAS + C_MAX_HIDDEN * CW * 4;                  // [3][128] last Linear + its bias [4]
-constexpr int COFF_BAR = COFF_WL + 3 * CW * 4 + 16;
+constexpr int COFF_PART = COFF_WL + 3 * CW * 4 + 16;                        // [128][4] rgb partial sums of the upper column half
+constexpr int COFF_BAR = COFF_PART + TC_ROWS * 16;
+constexpr int C_MMA_WARP = 12, C_THREADS = 13 * 32;                          // warps 0-7 epilogue | 8-11 loaders | 12 MMA issuer
 constexpr int C_NBARS = 1 + 2 * C_RING + 2 + 4;
 constexpr int COFF_TMEMPTR = COFF_BAR + C_NBARS * 8;
 constexpr int C_SMEM = COFF_TMEMPTR + 16 + 1024;
@@ -720,7 +722,7 @@ struct ColParams {
     int dbg;
 };
 
-__global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_constant__ ColParams p)
+__global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid_constant__ ColParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -740,13 +742,13 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
     if (tid == 0) {
         mbar_init(BAR(W_FULL), 1);
         for (int s = 0; s < C_RING; s++) { mbar_init(BAR(R_FULL + s), 1); mbar_init(BAR(R_EMPTY + s), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 128); }
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < p.n_hidden * CW; i += blockDim.x) s_bias[i] = p.bias[i / CW][i % CW];
     for (int i = tid; i < 3 * CW; i += blockDim.x) s_wl[i] = p.wl[i];
     if (tid < 3) s_wl[3 * CW + tid] = p.bl[tid];
-    if (warp == 8) {
+    if (warp == C_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -755,15 +757,18 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp < 4) {
-        // =========================================================== EPILOGUE
-        const int row = tid;
+    if (warp < 8) {
+        // =========================================================== EPILOGUE: warp = (column half, TMEM lane quadrant); half h owns
+        // columns [64h, 64h+64) = activation panel h
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        float* s_part = (float*)(smem + COFF_PART);            // [128][4] partial rgb sums of the upper column half
         uint32_t ph_dfull[2] = {0, 0};
         uint32_t lcount = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t c = (int64_t)tile * TC_ROWS + row;
             // per-sample scalars first: their dependent loads run while the tensor pipe works on the first layer
-            const int sidx = (c < Sv && !(p.dbg & 256)) ? p.csample[c] : -1;
+            const int sidx = (half == 0 && c < Sv && !(p.dbg & 256)) ? p.csample[c] : -1;
             float sg = 0.f;
             if (sidx >= 0) {
                 const int j0 = p.tuple_start[sidx], nv = p.nvalid[sidx];
@@ -777,9 +782,9 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 tc_fence_after();
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll 1
-                for (int ch = 0; ch < CW / 32; ch++) {
+                for (int ch = 2 * half; ch < 2 * half + 2; ch++) {
                     uint32_t v[32];
-                    tc_ld32(tmem_base + (uint32_t)(db * CW + ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+                    tc_ld32(tmem_base + (uint32_t)(db * CW + ch * 32) + ((uint32_t)(quad * 32) << 16), v);
                     float h[32];
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -815,7 +820,14 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 }
                 tc_fence_before();
                 mbar_arrive(BAR(D_EMPTY + db));
-                if (last && sidx >= 0) {
+                if (last) {
+                    // the two column halves of a row meet in shared memory
+                    if (half == 1) { s_part[4 * row] = o0; s_part[4 * row + 1] = o1; s_part[4 * row + 2] = o2; }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (half == 0) { o0 += s_part[4 * row]; o1 += s_part[4 * row + 1]; o2 += s_part[4 * row + 2]; }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                }
+                if (last && half == 0 && sidx >= 0) {
                     const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
                                 s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
                     const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
@@ -823,9 +835,9 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < C_MMA_WARP) {
         // =========================================================== LOADERS: F panels by bulk copy, view-direction panel computed
-        const int lt = tid - 128;
+        const int lt = tid - 256;
         uint32_t ph_empty[C_RING];
         for (int s = 0; s < C_RING; s++) ph_empty[s] = 1;
         uint32_t n = 0;
@@ -919,7 +931,7 @@ __global__ void __launch_bounds__(288, 1) agg_color_tc_kernel(const __grid_const
         }
     }
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    if (warp == C_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
@@ -1362,7 +1374,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         launch(tc_viewdir_rows_kernel, cdiv(Rc * 32, 256), 256, 0, st, in.raydir, Rc, d.FV, ws.vtab);
         cp.vtab = ws.vtab; cp.decoded = dec;
         const int max_ctiles = cdiv(spad, TC_ROWS);
-        launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, 288, C_SMEM, st, cp);
+        launch(agg_color_tc_kernel, max_ctiles < n_sm ? max_ctiles : n_sm, C_THREADS, C_SMEM, st, cp);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;
