@@ -159,6 +159,12 @@ __device__ __forceinline__ bool elect_one()
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(r));
     return r != 0;
 }
+// 32-byte global load (whole sector per lane): two consecutive uint4
+__device__ __forceinline__ void ldg256(const uint4* ptr, uint4& a, uint4& b)
+{
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(ptr));
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -275,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                         // this row's 128 columns of P0[pt] (bf16), fetched two 32-column chunks ahead of their use
                         p0row = (const uint4*)(p.p0tab + (size_t)m2.y * (TC_W * 2)) + h2 * 16;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) { pa[q] = __ldg(p0row + q); pb[q] = __ldg(p0row + 4 + q); }
+                        for (int q = 0; q < 4; q += 2) { ldg256(p0row + q, pa[q], pa[q + 1]); ldg256(p0row + 4 + q, pb[q], pb[q + 1]); }
                         if (s == 0) { wcr0 = __uint_as_float(m.x); slr0 = (int)m.y; c00 = (int)m.z; nslots0 = (int)(m.w & 0xffffu); npass0 = (int)(m.w >> 16); j0 = j; }
                         else { wcr1 = __uint_as_float(m.x); slr1 = (int)m.y; c01 = (int)m.z; nslots1 = (int)(m.w & 0xffffu); npass1 = (int)(m.w >> 16); j1 = j; }
                     }
@@ -320,14 +326,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                             chunk0(2 * cp, v0, pa);
                             if (cp == 0) {
 #pragma unroll
-                                for (int q = 0; q < 4; q++) pa[q] = __ldg(p0row + 8 + q);
+                                for (int q = 0; q < 4; q += 2) ldg256(p0row + 8 + q, pa[q], pa[q + 1]);
                             }
                             tc_wait_ld(v1);
                             if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
                             chunk0(2 * cp + 1, v1, pb);
                             if (cp == 0) {
 #pragma unroll
-                                for (int q = 0; q < 4; q++) pb[q] = __ldg(p0row + 12 + q);
+                                for (int q = 0; q < 4; q += 2) ldg256(p0row + 12 + q, pb[q], pb[q + 1]);
                             }
                         }
                     } else {
