@@ -50,6 +50,7 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
     const float dx = raydir[3 * r], dy = raydir[3 * r + 1], dz = raydir[3 * r + 2];
     const float* tr = t_per_ray ? t + r * D : t;
     const int label = ray_label ? ray_label[r] : 0;
+    const float rvx = 1.0f / g.vx, rvy = 1.0f / g.vy, rvz = 1.0f / g.vz;
     int cnt = 0;
     for (int base = 0; base < D && cnt < SR; base += 32) {
         const int d = base + lane;
@@ -61,7 +62,7 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
             px = __fadd_rn(cx, __fmul_rn(dx, tv));
             py = __fadd_rn(cy, __fmul_rn(dy, tv));
             pz = __fadd_rn(cz, __fmul_rn(dz, tv));
-            const int vx = vox_coord(px, g.ox, g.vx), vy = vox_coord(py, g.oy, g.vy), vz = vox_coord(pz, g.oz, g.vz);
+            const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
             if (vx >= 0 && vx < g.dx && vy >= 0 && vy < g.dy && vz >= 0 && vz < g.dz) {
                 const int64_t c = ((int64_t)vx * g.dy + vy) * g.dz + vz;
                 occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
@@ -87,6 +88,8 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
     if (lane == 0) ray_mask[r] = 0;
 }
 
+constexpr int KNN_RAYS = 64;      // rays per block: their occupied samples are compacted in shared memory so that all lanes work
+
 template <int KT, bool SEMANTIC>
 __global__ void __launch_bounds__(128)
 knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, const float* __restrict__ sample_loc_w,
@@ -94,8 +97,29 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
            const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
            int8_t* __restrict__ ray_mask)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R * SR) return;
+    extern __shared__ int32_t s_list[];                       // [KNN_RAYS * SR] sample indices (relative to the block's first slot)
+    __shared__ int s_count;
+    const int64_t slot0 = (int64_t)blockIdx.x * KNN_RAYS * SR;
+    const int nslot = (int)min((int64_t)KNN_RAYS * SR, R * SR - slot0);
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    // pass 1: unoccupied slots get their empty neighbour lists right away, occupied ones are queued (any order: results go by index)
+    for (int i = threadIdx.x; i < ((nslot + 31) & ~31); i += blockDim.x) {
+        const bool occ = i < nslot && __ldg(sample_mask + slot0 + i) > 0;
+        const unsigned b = __ballot_sync(0xffffffffu, occ);
+        int base = 0;
+        if (lane_id() == 0 && b) base = atomicAdd(&s_count, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (occ) s_list[base + __popc(b & ((1u << lane_id()) - 1u))] = i;
+        else if (i < nslot) {
+            int32_t* o = sample_pidx + (slot0 + i) * K;
+            for (int k = 0; k < K; k++) o[k] = -1;
+        }
+    }
+    __syncthreads();
+    const int nq = s_count;
+    for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+    const int64_t idx = slot0 + s_list[qi];
     const int64_t r = idx / SR;
     int32_t out[KT];
     float buf[KT];
@@ -167,6 +191,7 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
             if (i < K) o[i] = out[i];
     }
     if (kid > 0) ray_mask[r] = 1;  // every writer stores the same value
+    }
 }
 
 }  // namespace sgn
@@ -195,20 +220,21 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     launch(march_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
                                                                    sample_mask, semantic ? sample_label : nullptr, ray_mask);
     const int nlayer = (kernel_size0 + 1) / 2;
-    const int nb = cdiv(R * SR, 128);
+    const int nb = cdiv(R, KNN_RAYS);
+    const size_t ksm = (size_t)KNN_RAYS * SR * sizeof(int32_t);
     if (K == 8) {
         if (semantic)
-            launch(knn_kernel<8, true>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+            launch(knn_kernel<8, true>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
                                                      pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
         else
-            launch(knn_kernel<8, false>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
+            launch(knn_kernel<8, false>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
                                                       seconds_query, sample_pidx, ray_mask);
     } else {
         if (semantic)
-            launch(knn_kernel<SGN_MAX_K, true>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+            launch(knn_kernel<SGN_MAX_K, true>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
                                                              pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
         else
-            launch(knn_kernel<SGN_MAX_K, false>, nb, 128, 0, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
+            launch(knn_kernel<SGN_MAX_K, false>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
                                                               nullptr, seconds_query, sample_pidx, ray_mask);
     }
     SGN_LAUNCH_CHECK();
