@@ -33,7 +33,7 @@ constexpr int TC_ROWS = 128;
 constexpr int TC_W = 256;                 // layer width == accumulator columns
 constexpr int TC_C = 32, TC_F = 3, TC_FD = 5;
 constexpr int TC_PT_COLS = TC_C * (1 + 2 * TC_F);              // 224 per-point columns: emb | PE(emb)
-// block1.0 has 284 inputs: 224 per point (hoisted, see tc_point_l0_kernel) + 60 per tuple
+// block1.0 has 284 inputs: 224 per point (hoisted, see tc_point_gemm_kernel) + 60 per tuple
 constexpr int TC_KD = 2 * TC_FD * 6;                           // 60 PE(dists) columns: the per-tuple K of the first layer, + 2 bias columns (1.0)
 constexpr int X0_PANEL = 3;                                    // panel of the slot that holds [PE(dists) | 1 | 1 | 0 | 0] during the first layer
 static_assert(TC_KD + 2 <= 64, "PE(dists) and the two bias columns must fit in one K panel");
@@ -76,7 +76,8 @@ struct TcParams {
     const int32_t* cpad0;                  // [ntiles + 1] first PADDED sample index of every tile (each tile's samples padded to a multiple of 8)
     const int32_t* tuple_src; const int32_t* sample_cidx;
     const float* loc_pers; const float* wc;
-    const uint8_t* p0tab;                  // [N][256] bf16: point part of the first layer (tc_point_l0_kernel)
+    const uint8_t* padd[TC_MAX_LAYERS];    // per layer: [N][256] bf16 added to the accumulator in the epilogue (point-only part of the
+                                           // layer's input, hoisted into tc_point_gemm_kernel), or NULL: layer 0 (emb | PE(emb)), block2_bpnet.0 (label)
     const uint8_t* wpack;                  // pre-swizzled bf16 weight panels, all layers back to back
     const uint8_t* bpack[TC_MAX_LAYERS];   // compact bias K-step of the layer, or NULL when the bias rides in a weight panel
     const uint8_t* apack;                  // alpha_branch panel
@@ -261,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
         for (int cyc = cl0; cyc < ncycles; cyc += ncl) {
             int nslots0 = 0, nslots1 = 0, npass0 = 1, npass1 = 1, c00 = 0, c01 = 0, slr0 = -1, slr1 = -1, j0 = 0, j1 = 0;
             float wcr0 = 0.f, wcr1 = 0.f;
-            const uint4* p0row = (const uint4*)p.p0tab + h2 * 16;
+            int pt0 = 0, pt1 = 0;                                     // point of this row, per slot
             tcount += 2;
             for (int l = 0; l < p.n_layers; l++) {
                 const bool last = (l == p.n_layers - 1);
@@ -278,10 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                         const uint4 m = lds128u(slot_base + 4 * PANEL_A + row * 128 + ((META_CHUNK ^ (row & 7)) << 4));
                         const uint4 m2 = lds128u(slot_base + 4 * PANEL_A + row * 128 + (((META_CHUNK + 1) ^ (row & 7)) << 4));
                         const int j = (int)m2.x;
-                        // this row's 128 columns of P0[pt] (bf16), fetched two 32-column chunks ahead of their use
-                        p0row = (const uint4*)(p.p0tab + (size_t)m2.y * (TC_W * 2)) + h2 * 16;
-#pragma unroll
-                        for (int q = 0; q < 4; q += 2) { ldg256(p0row + q, pa[q], pa[q + 1]); ldg256(p0row + 4 + q, pb[q], pb[q + 1]); }
+                        if (s == 0) pt0 = (int)m2.y; else pt1 = (int)m2.y;
                         if (s == 0) { wcr0 = __uint_as_float(m.x); slr0 = (int)m.y; c00 = (int)m.z; nslots0 = (int)(m.w & 0xffffu); npass0 = (int)(m.w >> 16); j0 = j; }
                         else { wcr1 = __uint_as_float(m.x); slr1 = (int)m.y; c01 = (int)m.z; nslots1 = (int)(m.w & 0xffffu); npass1 = (int)(m.w >> 16); j1 = j; }
                     }
@@ -301,8 +299,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                         }
                     };
                     uint32_t v0[32], v1[32];
-                    if (l == 0) {
-                        // first layer: add the point part P0[pt] (bf16) to the accumulator before the activation
+                    if (p.padd[l]) {
+                        // this row's 128 columns of the layer's point table (bf16), fetched two 32-column chunks ahead of their use
+                        const uint4* p0row = (const uint4*)(p.padd[l] + (size_t)(s == 0 ? pt0 : pt1) * (TC_W * 2)) + h2 * 16;
+#pragma unroll
+                        for (int q = 0; q < 4; q += 2) { ldg256(p0row + q, pa[q], pa[q + 1]); ldg256(p0row + 4 + q, pb[q], pb[q + 1]); }
+                        // add the point part (bf16) to the accumulator before the activation
                         // x = acc + P0 in fp32 (P0 unpacked from bf16), then LeakyReLU in bf16 as in the other layers
                         auto chunk0 = [&](int c, const uint32_t(&vv)[32], const uint4(&pq)[4]) {
                             const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
@@ -458,8 +460,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                 const int64_t r = sm / p.SR;
                 const int64_t pt = p.in.pidx[flat];
                 ptv = (int)pt;
-                const uint8_t* src = p.p0tab + (size_t)pt * (TC_W * 2);          // the epilogue reads this row: bring it into L2 now
-                prefetch_l2(src); prefetch_l2(src + 128); prefetch_l2(src + 256); prefetch_l2(src + 384);
+                for (int l = 0; l < p.n_layers; l++)                             // the epilogues read these rows: bring them into L2 now
+                    if (p.padd[l]) {
+                        const uint8_t* src = p.padd[l] + (size_t)pt * (TC_W * 2);
+                        prefetch_l2(src); prefetch_l2(src + 128); prefetch_l2(src + 256); prefetch_l2(src + 384);
+                    }
                 wcv = p.wc[flat];
                 slot = p.sample_cidx[sm] - ta.y;
                 float dist[6];
@@ -948,8 +953,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
 // adds it to its K = 64 GEMM over PE(dists) in the first epilogue.  One CTA per SM, tile = 128 points, the four weight panels
 // (cols 0..255 of W0; the operand's cols 224..255 are zero) resident in shared memory, tcgen05.mma 128x256x16, cta_group::1.
 constexpr int P0_OFF_W = 0, P0_OFF_A = 4 * PANEL_B, P0_OFF_BAR = P0_OFF_A + 4 * PANEL_A, P0_SMEM = P0_OFF_BAR + 64 + 1024;
-__global__ void __launch_bounds__(128, 1) tc_point_l0_kernel(const float* __restrict__ emb, int64_t N, const uint8_t* __restrict__ wpack0,
-                                                              uint8_t* __restrict__ p0tab)
+// raw_cols == 0: operand = [emb | PE(emb)] of the 32-channel embedding (224 columns, 4 panels); raw_cols > 0: operand = the table's
+// raw_cols columns as they are (label embedding for block2_bpnet.0), ceil(raw_cols / 64) panels.
+__global__ void __launch_bounds__(128, 1) tc_point_gemm_kernel(const float* __restrict__ emb, int raw_cols, int64_t N, const uint8_t* __restrict__ wpack0,
+                                                                uint8_t* __restrict__ p0tab)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -969,9 +976,10 @@ __global__ void __launch_bounds__(128, 1) tc_point_l0_kernel(const float* __rest
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    const int npan = raw_cols > 0 ? (raw_cols + 63) / 64 : 4;
     if (tid == 0) {
-        mbar_expect_tx(bar_w, 4 * PANEL_B);
-        for (int i = 0; i < 4; i++) bulk_g2s(sbase + P0_OFF_W + i * PANEL_B, wpack0 + (size_t)i * PANEL_B, PANEL_B, bar_w);
+        mbar_expect_tx(bar_w, (uint32_t)npan * PANEL_B);
+        for (int i = 0; i < npan; i++) bulk_g2s(sbase + P0_OFF_W + i * PANEL_B, wpack0 + (size_t)i * PANEL_B, PANEL_B, bar_w);
     }
     const int64_t ntile = (N + TC_ROWS - 1) / TC_ROWS;
     uint32_t ph_d = 0;
@@ -979,6 +987,15 @@ __global__ void __launch_bounds__(128, 1) tc_point_l0_kernel(const float* __rest
     const int row = tid;
     for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const int64_t pt = tile * TC_ROWS + row;
+        if (raw_cols > 0) {
+            // ---- operand row: the table's columns as they are, zero padded to whole panels
+            for (int q = 0; q < npan * 8; q++) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = (pt < N && 8 * q + i < raw_cols) ? __ldg(emb + pt * raw_cols + 8 * q + i) : 0.f;
+                sts128(x0 + sw_off(row, 8 * q), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+        } else {
         // ---- operand row: [emb | sin, cos of emb_c 2^f (c, f major) | 0 (cols 224..255)]
         float e[TC_C];
         if (pt < N) {
@@ -1008,12 +1025,13 @@ __global__ void __launch_bounds__(128, 1) tc_point_l0_kernel(const float* __rest
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) sts128(x0 + sw_off(row, TC_PT_COLS + 8 * q), 0u, 0u, 0u, 0u);
+        }
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             mbar_wait(bar_w, 0);                               // weights resident (completes once; later waits return at once)
             tc_fence_after();
-            for (int kp = 0; kp < 4; kp++)
+            for (int kp = 0; kp < npan; kp++)
                 for (int k = 0; k < 4; k++)
                     tc_mma(tmem_base, umma_desc(x0 + kp * PANEL_A + k * 32), umma_desc(sbase + P0_OFF_W + kp * PANEL_B + k * 32), tc_idesc(TC_ROWS, TC_W),
                            (kp | k) != 0);
@@ -1144,7 +1162,7 @@ struct TcWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample, *ntiles, *padslots, *cpad0, *csample_pad, *tpartials;
     int2* tile_tab;
     float *loc_pers, *wc, *sigrow;
-    uint8_t *wpack, *cpack, *p0tab, *p0pack, *bpack, *apack, *F, *vtab;
+    uint8_t *wpack, *cpack, *p0tab, *p0pack, *pltab, *plpack, *bpack, *apack, *F, *vtab;
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
@@ -1159,6 +1177,7 @@ static inline int64_t tc_chunk_rays(int64_t R)
 
 static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, void* base, size_t cap, TcWs* ws)
 {
+    const AggDims& d = P.dims;
     Arena A(base, cap);
     const size_t S = (size_t)Rc * SR, T = S * K;
     ws->nvalid = A.take<int32_t>(S + 1); ws->svalid = A.take<int32_t>(S + 1);
@@ -1175,14 +1194,17 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     ws->loc_pers = A.take<float>(S * 3); ws->wc = A.take<float>(T);
     ws->F = A.take<uint8_t>((spad / TC_ROWS + 2) * F_TILE_BYTES); ws->sigrow = A.take<float>(T + 1);
     size_t panels = 0;
-    for (int t = 0; t < P.n_tuple_layers; t++) panels += t == 0 ? 1 : (size_t)(P.layers[t].in + 63) / 64;
+    for (int t = 0; t < P.n_tuple_layers; t++)
+        panels += t == 0 ? 1 : (size_t)((P.layers[t].extra == EXTRA_LABEL ? TC_W : P.layers[t].in) + 63) / 64;
     ws->wpack = A.take<uint8_t>(panels * PANEL_B);
     ws->cpack = A.take<uint8_t>((size_t)C_W_PANELS * C_PANEL);
     ws->bpack = A.take<uint8_t>((size_t)TC_MAX_LAYERS * BIAS_PANEL_B);
     ws->apack = A.take<uint8_t>(ALPHA_PANEL_B);
     ws->vtab = A.take<uint8_t>((size_t)Rc * 64);
     ws->p0pack = A.take<uint8_t>((size_t)4 * PANEL_B);
+    ws->plpack = A.take<uint8_t>((size_t)4 * PANEL_B);
     ws->p0tab = A.take<uint8_t>((size_t)(N + TC_ROWS) * (TC_W * 2));
+    ws->pltab = A.take<uint8_t>(d.LD > 0 ? (size_t)(N + TC_ROWS) * (TC_W * 2) : 256);
     return A.off;
 }
 
@@ -1192,14 +1214,15 @@ static int tc_supported(const AggPlan& P, int K)
     SGN_CHECK_ARG(d.C == TC_C && d.F == TC_F && d.FD == TC_FD && d.W == TC_W,
                   "bf16 tensor-core path is built for feat_dim=32, num_feat_freqs=3, dist_xyz_freq=5, width=256 (got %d,%d,%d,%d); use SGN_PRECISION_FP32",
                   d.C, d.F, d.FD, d.W);
-    SGN_CHECK_ARG(d.LD == 0, "bf16 tensor-core path does not take the label embedding yet (label_dim=%d); use SGN_PRECISION_FP32", d.LD);
+    SGN_CHECK_ARG(d.LD >= 0 && d.LD <= 256, "bf16 tensor-core path: label_dim must be at most 256 (got %d)", d.LD);
     SGN_CHECK_ARG(P.n_tuple_layers <= TC_MAX_LAYERS, "bf16 tensor-core path: at most %d per-neighbour layers", TC_MAX_LAYERS);
     SGN_CHECK_ARG(P.n_color_hidden >= 1 && P.n_color_hidden <= C_MAX_HIDDEN && d.WC == CW && d.FV <= 5,
                   "bf16 tensor-core path: colour branch must have 2..%d layers of width %d and num_viewdir_freqs <= 5; use SGN_PRECISION_FP32",
                   C_MAX_HIDDEN + 1, CW);
     SGN_CHECK_ARG(K <= 32, "bf16 tensor-core path: K <= 32");
     for (int t = 0; t < P.n_tuple_layers; t++)
-        SGN_CHECK_ARG(P.layers[t].extra != EXTRA_LABEL, "bf16 tensor-core path: label input unsupported");
+        SGN_CHECK_ARG(P.layers[t].extra != EXTRA_LABEL || (t > 0 && P.layers[t].in == TC_W + d.LD),
+                      "bf16 tensor-core path: the label embedding must enter a hidden layer next to the %d running features", TC_W);
     return SGN_OK;
 }
 
@@ -1268,7 +1291,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
-        SGN_CUDA(cudaFuncSetAttribute(tc_point_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+        SGN_CUDA(cudaFuncSetAttribute(tc_point_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
         attr_set = true;
     }
     int dev = 0, n_sm = 148;
@@ -1287,10 +1310,18 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         uint8_t* dst = ws.wpack + (size_t)tp.first_panel[t] * PANEL_B;
         int np;
         if (t == 0) {
-            // first layer: the per-tuple part only, W0[:, 224:284] + bias -> one panel; the point part W0[:, 0:224] feeds tc_point_l0_kernel
+            // first layer: the per-tuple part only, W0[:, 224:284] + bias -> one panel; the point part W0[:, 0:224] feeds tc_point_gemm_kernel
             np = 1;
             launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t] + TC_PT_COLS, L.in, TC_W, TC_W, TC_KD, np, biases[t], dst);
             launch(tc_pack_weight_kernel, cdiv((int64_t)4 * TC_W * 8, 256), 256, 0, st, weights[t], L.in, TC_W, TC_W, TC_PT_COLS, 4, (const float*)nullptr, ws.p0pack);
+        } else if (L.extra == EXTRA_LABEL) {
+            // block2_bpnet.0: the running features' part W[:, 0:256] stays per tuple; the label part W[:, 256:256+LD] depends on the point
+            // only and becomes a second per-point table added in this layer's epilogue
+            np = TC_W / 64;
+            launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], L.in, TC_W, TC_W, TC_W, np, (const float*)nullptr, dst);
+            const int lp = (d.LD + 63) / 64;
+            launch(tc_pack_weight_kernel, cdiv((int64_t)lp * TC_W * 8, 256), 256, 0, st, weights[t] + TC_W, L.in, TC_W, TC_W, d.LD, lp, (const float*)nullptr, ws.plpack);
+            tp.padd[t] = ws.pltab;
         } else {
             np = (L.in + 63) / 64;
             launch(tc_pack_weight_kernel, cdiv((int64_t)np * TC_W * 8, 256), 256, 0, st, weights[t], L.in, TC_W, TC_W, L.in, np,
@@ -1320,11 +1351,13 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     launch(tc_pack_weight_kernel, cdiv((int64_t)4 * 8 * 8, 256), 256, 0, st, weights[P.alpha_layer], TC_W, 8, 1, TC_W, 4, (const float*)nullptr, ws.apack);
     {
         const int64_t ptiles = (tables->N + TC_ROWS - 1) / TC_ROWS;
-        launch(tc_point_l0_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->embedding, tables->N, ws.p0pack, ws.p0tab);
+        launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->embedding, 0, tables->N, ws.p0pack, ws.p0tab);
+        if (d.LD > 0)
+            launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->label_emb, d.LD, tables->N, ws.plpack, ws.pltab);
     }
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
-    tp.wpack = ws.wpack; tp.p0tab = ws.p0tab;
+    tp.wpack = ws.wpack; tp.padd[0] = ws.p0tab;
     tp.apack = ws.apack; tp.ba = biases[P.alpha_layer];
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;

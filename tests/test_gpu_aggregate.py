@@ -174,18 +174,19 @@ def test_inference_chunking_and_empty():
         assert float(out[0].abs().max()) == 0 and int(out[1].sum()) == 0
 
 
-@pytest.mark.parametrize("R,SR", [(3, 24), (300, 24), (41, 80)])
-def test_bf16_tensor_core_path_vs_fp32(R, SR):
+@pytest.mark.parametrize("R,SR,semantic", [(3, 24, False), (300, 24, False), (41, 80, False), (300, 24, True)])
+def test_bf16_tensor_core_path_vs_fp32(R, SR, semantic):
     """bf16 tcgen05 path (forward only) against the fp32 strict path on the same inputs.
     Stated bf16 tolerance (operands rounded to bf16, fp32 accumulate): |d rgb| <= 1e-2, |d sigma| <= 2e-2 * max(1, |sigma|);
-    validity masks, weights and conf coefficients are computed in fp32 on both paths and must be identical."""
-    cfg = rr.agg_config()
+    validity masks, weights and conf coefficients are computed in fp32 on both paths and must be identical.
+    semantic = the block2_bpnet configuration with the 96-d label embedding (its point-only part is a second hoisted table)."""
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
     N, K = 5000, 8
     tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=21 + R)
     P = rr.init_params(cfg, seed=3, bias_scale=0.1)
     _, W, B = param_lists(P, cfg)
-    args = (tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(), None,
-            pidx.cuda(), loc_w.cuda(), raydir.cuda(), campos.cuda(), rot.cuda())
+    args = (tables.xyz.cuda(), tables.embedding.cuda(), tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(),
+            tables.label_embedding.cuda() if semantic else None, pidx.cuda(), loc_w.cuda(), raydir.cuda(), campos.cuda(), rot.cuda())
     with torch.no_grad():
         ref = ops.aggregate(cfg_to_c(cfg), W, B, *args, precision=ops.PRECISION_FP32)
         out = ops.aggregate(cfg_to_c(cfg), W, B, *args, precision=ops.PRECISION_BF16)
