@@ -163,6 +163,20 @@ int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights /*[host]*/
                     int save_for_backward, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
                     float* conf_coef, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Inference cache of the bf16 path.  The first per-neighbour layer (and block2_bpnet.0) is linear in its input and most of that input
+ * depends on the point only, so its point part is one table per point (bf16 [N,256]) -- a function of the embedding tables and the layer
+ * weights alone.  Like the occupancy grid it can be built once per (point cloud, weights) version and passed to every frame's
+ * sgn_agg_forward_cached; with point_cache = NULL (what sgn_agg_forward does) the tables are rebuilt inside the call's workspace.
+ * The caller must rebuild the cache whenever embeddings or aggregator weights change. */
+int sgn_agg_point_cache_bytes(const SgnAggCfg* cfg, int64_t N, size_t* bytes);
+int sgn_agg_point_cache_build(const SgnAggCfg* cfg, const float* const* weights /*[host]*/, const SgnPointTables* tables, void* cache,
+                              size_t cache_bytes, void* stream);
+int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights /*[host]*/, const float* const* biases /*[host]*/,
+                           const SgnPointTables* tables, const int32_t* pidx, const float* loc_w, const float* raydir,
+                           const float* campos, const float* camrotc2w, int64_t R, int SR, int K, int precision,
+                           int save_for_backward, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
+                           float* conf_coef, void* workspace, size_t workspace_bytes, const void* point_cache, void* stream);
+
 /* Backward of sgn_agg_forward (autograd of the reference path).  Needs the workspace
  * of a forward call made with save_for_backward = 1 and the same arguments.  d_weights/d_biases are
  * [host] arrays of device pointers (accumulated, +=); d_conf_coef may be NULL. */

@@ -57,6 +57,11 @@ SIGNATURES = {
     "sgn_agg_forward": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                 c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
                                 c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void]),
+    "sgn_agg_forward_cached": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
+                                       c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
+                                       c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void, c_void]),
+    "sgn_agg_point_cache_bytes": (c_int, [C.POINTER(SgnAggCfg), c_i64, C.POINTER(c_size)]),
+    "sgn_agg_point_cache_build": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(SgnPointTables), c_void, c_size, c_void]),
     "sgn_agg_backward": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                  c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_void, c_void,
                                  C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointGrads), c_void, c_size, c_void]),

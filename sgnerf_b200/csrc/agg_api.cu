@@ -25,7 +25,9 @@ static bool tc_use_v1() { const char* e = getenv("SGN_TC_V"); return e && e[0] =
 int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                        const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                        int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
-                       void* workspace, size_t workspace_bytes, cudaStream_t st);
+                       void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st);
+int sgn_agg_tc_point_cache_bytes(const AggPlan& P, int64_t N, size_t* bytes);
+int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, const SgnPointTables* tables, void* cache, size_t cache_bytes, cudaStream_t st);
 
 static int check_common(const SgnAggCfg* cfg, AggPlan* P, int64_t R, int SR, int K)
 {
@@ -56,10 +58,11 @@ extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t N, int64_t 
     return sgn_agg_tc_workspace_bytes(P, N, R, SR, K, bytes);
 }
 
-extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                                const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                                int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,
-                               float* loc_pers, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes, void* stream)
+                               float* loc_pers, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes, const void* point_cache,
+                                      void* stream)
 {
     AggPlan P;
     int rc = check_common(cfg, &P, R, SR, K);
@@ -77,7 +80,36 @@ extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights
         return sgn_agg_tc_v1_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
                                      weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
     return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
-                              weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
+                              weight, conf_coef, workspace, workspace_bytes, tc_use_v1() ? nullptr : point_cache, (cudaStream_t)stream);
+}
+
+extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                               const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                               int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,
+                               float* loc_pers, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return sgn_agg_forward_cached(cfg, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, precision, save_for_backward,
+                                  decoded, ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int sgn_agg_point_cache_bytes(const SgnAggCfg* cfg, int64_t N, size_t* bytes)
+{
+    AggPlan P;
+    int rc = make_plan(cfg, &P);
+    if (rc) return rc;
+    SGN_CHECK_ARG(bytes != nullptr && N >= 0, "sgn_agg_point_cache_bytes: bad argument");
+    return sgn_agg_tc_point_cache_bytes(P, N, bytes);
+}
+
+extern "C" int sgn_agg_point_cache_build(const SgnAggCfg* cfg, const float* const* weights, const SgnPointTables* tables, void* cache,
+                                         size_t cache_bytes, void* stream)
+{
+    AggPlan P;
+    int rc = make_plan(cfg, &P);
+    if (rc) return rc;
+    SGN_CHECK_ARG(weights && tables && cache && tables->embedding, "sgn_agg_point_cache_build: NULL argument");
+    SGN_CHECK_ARG(P.dims.LD == 0 || tables->label_emb, "sgn_agg_point_cache_build: label embedding table missing");
+    return sgn_agg_tc_point_cache_build(P, weights, tables, cache, cache_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,

@@ -1230,6 +1230,48 @@ static int tc_supported(const AggPlan& P, int K)
 
 using namespace sgn;
 
+// Point cache layout: [packed W0[:, :224] (4 panels) | packed label weights (4 panels) | P0 table | label table]
+static inline size_t pc_off_p0() { return (size_t)8 * PANEL_B; }
+static inline size_t pc_off_pl(int64_t N) { return pc_off_p0() + align_up((size_t)(N + TC_ROWS) * (TC_W * 2)); }
+
+int sgn_agg_tc_point_cache_bytes(const AggPlan& P, int64_t N, size_t* bytes)
+{
+    int rc = tc_supported(P, 1);
+    if (rc) return rc;
+    *bytes = pc_off_pl(N) + (P.dims.LD > 0 ? align_up((size_t)(N + TC_ROWS) * (TC_W * 2)) : 256);
+    return SGN_OK;
+}
+
+int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, const SgnPointTables* tables, void* cache, size_t cache_bytes, cudaStream_t st)
+{
+    size_t need = 0;
+    int rc = sgn_agg_tc_point_cache_bytes(P, tables->N, &need);
+    if (rc) return rc;
+    if (need > cache_bytes || ((uintptr_t)cache & 255)) {
+        set_error("sgn_agg_point_cache_build: cache too small or misaligned (need %zu bytes, got %zu)", need, cache_bytes);
+        return SGN_E_WORKSPACE;
+    }
+    SGN_CUDA(cudaFuncSetAttribute(tc_point_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    uint8_t* base = (uint8_t*)cache;
+    uint8_t *p0pack = base, *plpack = base + 4 * PANEL_B;
+    const int64_t ptiles = (tables->N + TC_ROWS - 1) / TC_ROWS;
+    const int grid = (int)(ptiles < n_sm ? ptiles : n_sm);
+    launch(tc_pack_weight_kernel, cdiv((int64_t)4 * TC_W * 8, 256), 256, 0, st, weights[0], P.layers[0].in, TC_W, TC_W, TC_PT_COLS, 4, (const float*)nullptr, p0pack);
+    launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->embedding, 0, tables->N, p0pack, base + pc_off_p0());
+    for (int t = 1; t < P.n_tuple_layers; t++)
+        if (P.layers[t].extra == EXTRA_LABEL) {
+            const int lp = (P.dims.LD + 63) / 64;
+            launch(tc_pack_weight_kernel, cdiv((int64_t)lp * TC_W * 8, 256), 256, 0, st, weights[t] + TC_W, P.layers[t].in, TC_W, TC_W, P.dims.LD, lp,
+                   (const float*)nullptr, plpack);
+            launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->label_emb, P.dims.LD, tables->N, plpack, base + pc_off_pl(tables->N));
+        }
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
 // Optional timing of the dominant kernel (agg_tuple_tc_kernel) with CUDA events on the launching stream, for bench.py's roofline.
 static bool g_tc_timing = false;
 static cudaEvent_t g_tc_ev[2] = {nullptr, nullptr};
@@ -1274,7 +1316,7 @@ int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, i
 int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                        const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                        int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* weight_out, float* conf_out,
-                       void* workspace, size_t workspace_bytes, cudaStream_t st)
+                       void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st)
 {
     int rc = tc_supported(P, K);
     if (rc) return rc;
@@ -1349,15 +1391,23 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     // alpha panel: per CTA of the pair four K panels of 8 rows; rank 0's row 0 is the weight vector, everything else zero
     SGN_CUDA(cudaMemsetAsync(ws.apack, 0, ALPHA_PANEL_B, st));
     launch(tc_pack_weight_kernel, cdiv((int64_t)4 * 8 * 8, 256), 256, 0, st, weights[P.alpha_layer], TC_W, 8, 1, TC_W, 4, (const float*)nullptr, ws.apack);
-    {
+    // the per-point tables: from the caller's cache (inference on a static cloud with fixed weights), else computed now
+    const uint8_t* p0tab = ws.p0tab;
+    const uint8_t* pltab = ws.pltab;
+    if (point_cache) {
+        p0tab = (const uint8_t*)point_cache + pc_off_p0();
+        pltab = (const uint8_t*)point_cache + pc_off_pl(tables->N);
+    } else {
         const int64_t ptiles = (tables->N + TC_ROWS - 1) / TC_ROWS;
         launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->embedding, 0, tables->N, ws.p0pack, ws.p0tab);
         if (d.LD > 0)
             launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->label_emb, d.LD, tables->N, ws.plpack, ws.pltab);
     }
+    for (int t = 1; t < P.n_tuple_layers; t++)
+        if (tp.padd[t]) tp.padd[t] = pltab;
     SGN_LAUNCH_CHECK();
     tp.n_layers = P.n_tuple_layers;
-    tp.wpack = ws.wpack; tp.padd[0] = ws.p0tab;
+    tp.wpack = ws.wpack; tp.padd[0] = p0tab;
     tp.apack = ws.apack; tp.ba = biases[P.alpha_layer];
     tp.slope = d.slope; tp.act_super = d.act_super;
     tp.K = K; tp.SR = SR;

@@ -281,9 +281,10 @@ class _Aggregate(torch.autograd.Function):
         weight = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
         conf_coef = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
         tb = _tables(xyz, embedding, color, dirs, conf, label_emb)
-        _lib.call("sgn_agg_forward", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w),
+        cache = meta.point_cache if (precision == PRECISION_BF16 and not need_grad) else None
+        _lib.call("sgn_agg_forward_cached", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w),
                   _ptr(raydir), _ptr(campos), _ptr(camrot), R, SR, K, precision, int(need_grad), _ptr(decoded), _ptr(ray_valid),
-                  _ptr(loc_pers), _ptr(weight), _ptr(conf_coef), _ptr(ws), ws.numel() * 4, _stream())
+                  _ptr(loc_pers), _ptr(weight), _ptr(conf_coef), _ptr(ws), ws.numel() * 4, _ptr(cache), _stream())
         if need_grad:
             ctx.meta, ctx.ws, ctx.nl = meta, ws, nl
             ctx.save_for_backward(embedding, color, dirs, conf, *wb)
@@ -321,8 +322,27 @@ class _Aggregate(torch.autograd.Function):
         return (None, d_emb, d_col, d_dir, d_conf, *d_w, *d_b)
 
 
+def build_point_cache(cfg, weights, embedding, label_emb=None):
+    """Inference cache of the bf16 path (sgn_agg_point_cache_build): the point-only part of block1.0 (and block2_bpnet.0) per point.
+    Valid until the embeddings or the aggregator weights change; pass it to aggregate(point_cache=...)."""
+    f32 = torch.float32
+    embedding = _dev(embedding.reshape(-1, embedding.shape[-1]), f32, "embedding")
+    N = embedding.shape[0]
+    label_emb = _dev(label_emb.reshape(N, -1), f32, "label_emb") if label_emb is not None else None
+    ws_ = [_dev(w, f32, "weight") for w in weights]
+    nbytes = C.c_size_t()
+    _lib.call("sgn_agg_point_cache_bytes", C.byref(cfg), N, C.byref(nbytes))
+    cache = _workspace(nbytes.value, embedding.device)
+    tb = SgnPointTables()
+    tb.embedding = embedding.data_ptr()
+    tb.label_emb = label_emb.data_ptr() if label_emb is not None else None
+    tb.N = N
+    _lib.call("sgn_agg_point_cache_build", C.byref(cfg), _ptr_array(ws_), C.byref(tb), _ptr(cache), cache.numel() * 4, _stream())
+    return cache
+
+
 def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb, pidx, loc_w, raydir, campos, camrotc2w,
-              precision=PRECISION_FP32, want_aux=True):
+              precision=PRECISION_FP32, want_aux=True, point_cache=None):
     """Fused gather + aggregation MLPs (sgn_agg_forward / sgn_agg_backward).
 
     Tables: xyz [N,3], embedding [N,C], color [N,3], dirs [N,3], conf [N] (or None), label_emb [N,E] (or None).
@@ -333,7 +353,7 @@ def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb
                            pidx=_dev(pidx, torch.int32, "pidx"), loc_w=_dev(loc_w, f32, "loc_w"),
                            raydir=_dev(raydir.reshape(-1, 3), f32, "raydir"), campos=_dev(campos.reshape(3), f32, "campos"),
                            camrot=_dev(camrotc2w.reshape(3, 3), f32, "camrotc2w"), precision=int(precision), want_aux=bool(want_aux),
-                           grad_enabled=torch.is_grad_enabled())
+                           grad_enabled=torch.is_grad_enabled(), point_cache=point_cache)
     N = meta.xyz.shape[0]
     embedding = _dev(embedding.reshape(N, -1), f32, "embedding")
     color = _dev(color.reshape(N, 3), f32, "color")

@@ -55,12 +55,24 @@ class RenderScene:
         self.agg_cfg, self.qopt, self.device = agg_cfg, qopt, device
         self._grid = None
         self._hp = None
+        self._point_cache = None
 
     def invalidate_grid(self):
         """Call after the point cloud changed (grow / prune / set_points)."""
         if self._grid is not None:
             self._grid.close()
         self._grid, self._hp = None, None
+        self._point_cache = None
+
+    def invalidate_point_cache(self):
+        """Call after the embeddings (or the label embeddings) or the aggregator weights changed."""
+        self._point_cache = None
+
+    def point_cache(self):
+        """Per-point first-layer tables of the bf16 path, built once per (cloud, weights) version like the grid."""
+        if self._point_cache is None:
+            self._point_cache = ops.build_point_cache(self.agg_cfg, self.weights, self.embedding, self.label_emb)
+        return self._point_cache
 
     def grid(self, seconds=(0, 0)):
         if self._grid is None:
@@ -71,7 +83,8 @@ class RenderScene:
         return self._grid, self._hp
 
 
-def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision=ops.PRECISION_FP32, t=None, want_aux=False):
+def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision=ops.PRECISION_FP32, t=None, want_aux=False,
+                use_point_cache=True):
     """Render R rays (device tensors).  Returns a namespace with ray_color [R,3] (misses = bg), ray_mask int8 [R],
     opacity [R,SR], bg_transmission [R] and, with want_aux, the intermediate tensors."""
     q = scene.qopt
@@ -81,7 +94,8 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
     pidx, loc_w, smask, rmask = ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2)
     decoded, ray_valid, loc_pers, weight, conf_coef = ops.aggregate(
         scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf,
-        scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux)
+        scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux,
+        point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None)
     rd = ops.ray_dist(loc_pers, ray_valid, hp.vsize[2], 1)
     ray_color, opacity, acc, bw, bgt = ops.composite(decoded, rd, ray_valid, bg_color, blend=0)
     ops.fill_invalid(rmask, bg_color, ray_color, opacity, bgt)

@@ -241,3 +241,28 @@ def test_bf16_edge_cases(monkeypatch):
     o = run(single, loc_w[:7], ops.PRECISION_BF16)
     r = run(single, loc_w[:7], ops.PRECISION_FP32)
     assert int(o[1].sum()) == 1 and float((o[0] - r[0]).abs().max()) <= 2e-2
+
+
+@pytest.mark.parametrize("semantic", [False, True])
+def test_bf16_point_cache(semantic):
+    """The cached per-point tables (sgn_agg_point_cache_build + sgn_agg_forward_cached) give bit-identical results to rebuilding
+    them inside the call, and a stale cache is the caller's responsibility (changing the embedding without rebuilding differs)."""
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
+    N, R, SR, K = 3000, 64, 24, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=5)
+    P = rr.init_params(cfg, seed=6, bias_scale=0.1)
+    _, W, B = param_lists(P, cfg)
+    emb = tables.embedding.cuda()
+    lab = tables.label_embedding.cuda() if semantic else None
+    args = (tables.xyz.cuda(), emb, tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(), lab, pidx.cuda(), loc_w.cuda(), raydir.cuda(),
+            campos.cuda(), rot.cuda())
+    with torch.no_grad():
+        cache = ops.build_point_cache(cfg_to_c(cfg), W, emb, lab)
+        a = ops.aggregate(cfg_to_c(cfg), W, B, *args, precision=ops.PRECISION_BF16)
+        b = ops.aggregate(cfg_to_c(cfg), W, B, *args, precision=ops.PRECISION_BF16, point_cache=cache)
+        emb2 = emb + 0.25
+        c = ops.aggregate(cfg_to_c(cfg), W, B, args[0], emb2, *args[2:], precision=ops.PRECISION_BF16, point_cache=cache)
+        d = ops.aggregate(cfg_to_c(cfg), W, B, args[0], emb2, *args[2:], precision=ops.PRECISION_BF16)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0])
+    assert torch.equal(c[0], b[0]) and not torch.equal(d[0], b[0])
