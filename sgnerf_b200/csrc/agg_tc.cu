@@ -1166,11 +1166,14 @@ struct TcWs {
 };
 
 static inline int tile_width(int K) { return TC_ROWS - (K - 1); }
-// rays per pass: as few equal passes as keep each one under TC_CHUNK rays
-static inline int64_t tc_chunk_rays(int64_t R)
+// rays per pass: as few equal passes as keep each one under TC_CHUNK rays and 2^27 (sample, neighbour) slots (the worst-case workspace
+// is ~110 bytes per slot: 14 GB)
+static inline int64_t tc_chunk_rays(int64_t R, int SR, int K)
 {
     const char* e = getenv("SGN_TC_CHUNK");                  // tests force small passes through this
-    const int64_t cap = e && atoll(e) > 0 ? atoll(e) : TC_CHUNK;
+    int64_t cap = e && atoll(e) > 0 ? atoll(e) : TC_CHUNK;
+    const int64_t by_slots = ((int64_t)1 << 27) / ((int64_t)SR * K);
+    if (!(e && atoll(e) > 0) && by_slots < cap) cap = by_slots > 1 ? by_slots : 1;
     const int64_t n = (R + cap - 1) / cap;
     return n <= 1 ? R : (R + n - 1) / n;
 }
@@ -1309,7 +1312,7 @@ int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, i
     int rc = tc_supported(P, K);
     if (rc) return rc;
     TcWs ws;
-    *bytes = tc_carve(P, N, tc_chunk_rays(R), SR, K, nullptr, 0, &ws);
+    *bytes = tc_carve(P, N, tc_chunk_rays(R, SR, K), SR, K, nullptr, 0, &ws);
     return SGN_OK;
 }
 
@@ -1321,7 +1324,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
     int rc = tc_supported(P, K);
     if (rc) return rc;
     const AggDims& d = P.dims;
-    const int64_t chunk = tc_chunk_rays(R);
+    const int64_t chunk = tc_chunk_rays(R, SR, K);
     TcWs ws;
     const size_t need = tc_carve(P, tables->N, chunk, SR, K, workspace, workspace_bytes, &ws);
     if (need > workspace_bytes || ((uintptr_t)workspace & 255)) {

@@ -88,19 +88,19 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
     if (lane == 0) ray_mask[r] = 0;
 }
 
-constexpr int KNN_RAYS = 64;      // rays per block: their occupied samples are compacted in shared memory so that all lanes work
+constexpr int KNN_SLOTS = 1536;   // sample slots per block (64 rays at SR = 24): their occupied samples are compacted in shared memory so that all lanes work
 
 template <int KT, bool SEMANTIC>
 __global__ void __launch_bounds__(128)
 knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, const float* __restrict__ sample_loc_w,
            const int32_t* __restrict__ sample_mask, const int32_t* __restrict__ sample_label, const int32_t* __restrict__ pt_label,
            const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
-           int8_t* __restrict__ ray_mask)
+           int8_t* __restrict__ ray_mask, int rays_per_block)
 {
-    extern __shared__ int32_t s_list[];                       // [KNN_RAYS * SR] sample indices (relative to the block's first slot)
+    extern __shared__ int32_t s_list[];                       // [rays_per_block * SR] sample indices (relative to the block's first slot)
     __shared__ int s_count;
-    const int64_t slot0 = (int64_t)blockIdx.x * KNN_RAYS * SR;
-    const int nslot = (int)min((int64_t)KNN_RAYS * SR, R * SR - slot0);
+    const int64_t slot0 = (int64_t)blockIdx.x * rays_per_block * SR;
+    const int nslot = (int)min((int64_t)rays_per_block * SR, R * SR - slot0);
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
     // pass 1: unoccupied slots get their empty neighbour lists right away, occupied ones are queued (any order: results go by index)
@@ -204,7 +204,7 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
                          int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, void* stream)
 {
     SGN_CHECK_ARG(G != nullptr, "sgn_query: grid is NULL");
-    SGN_CHECK_ARG(R >= 0 && D > 0 && SR > 0, "sgn_query: bad R/D/SR");
+    SGN_CHECK_ARG(R >= 0 && D > 0 && SR > 0 && SR <= 4096, "sgn_query: bad R/D/SR (SR at most 4096)");
     SGN_CHECK_ARG(K > 0 && K <= SGN_MAX_K, "sgn_query: K=%d out of range (1..%d)", K, SGN_MAX_K);
     SGN_CHECK_ARG(sample_pidx && sample_loc_w && sample_mask && ray_mask, "sgn_query: NULL output");
     const bool semantic = ray_label != nullptr;
@@ -220,22 +220,23 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     launch(march_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
                                                                    sample_mask, semantic ? sample_label : nullptr, ray_mask);
     const int nlayer = (kernel_size0 + 1) / 2;
-    const int nb = cdiv(R, KNN_RAYS);
-    const size_t ksm = (size_t)KNN_RAYS * SR * sizeof(int32_t);
+    const int rpb = KNN_SLOTS / SR > 0 ? KNN_SLOTS / SR : 1;      // rays per block (SR <= 1024 keeps the list under 4 KB ... 6 KB)
+    const int nb = cdiv(R, rpb);
+    const size_t ksm = (size_t)rpb * SR * sizeof(int32_t);
     if (K == 8) {
         if (semantic)
             launch(knn_kernel<8, true>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
-                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
+                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb);
         else
             launch(knn_kernel<8, false>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
-                                                      seconds_query, sample_pidx, ray_mask);
+                                                      seconds_query, sample_pidx, ray_mask, rpb);
     } else {
         if (semantic)
             launch(knn_kernel<SGN_MAX_K, true>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
-                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask);
+                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb);
         else
             launch(knn_kernel<SGN_MAX_K, false>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
-                                                              nullptr, seconds_query, sample_pidx, ray_mask);
+                                                              nullptr, seconds_query, sample_pidx, ray_mask, rpb);
     }
     SGN_LAUNCH_CHECK();
     return SGN_OK;

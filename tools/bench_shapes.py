@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Other shapes of BASELINE.json's config list on ONE GPU (shape checks, not the headline bench):
+
+    C3  NeRF-Synthetic-shape: 3M points, 800x800 full frame, SR=200 (P=9, vsize .004)          -- python tools/bench_shapes.py c3
+    C4  large scene: 10M points, 1296x968 raw ScanNet resolution, SR=24, one grid rebuild      -- python tools/bench_shapes.py c4
+
+Each renders the frame with the bf16 tensor-core path (timed), and checks a 2048-ray subset against the fp32 strict path
+(|d rgb| <= 1e-2) and against itself when rendered alone (ray independence / chunking).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    from sgnerf_b200 import ops, pipeline, synth
+    dev = "cuda:0"
+    if which == "c3":
+        n, room, w, h, qo = 3_000_000, (3.0, 3.0, 3.0), 800, 800, dict(vsize=(0.004,) * 3, P=9, SR=200)
+    else:
+        n, room, w, h, qo = 10_000_000, (20.0, 20.0, 4.0), 1296, 968, dict(SR=24)
+    s = synth.scene_room(n, room=room, width=w, height=h, seed=1234)
+    tabs = synth.make_point_tables(n, 32, 0, seed=0)
+    shapes = synth.mlp_layer_shapes()
+    P = synth.make_mlp_params(shapes, seed=0)
+    names = [k for k, _, _ in shapes]
+    scene = pipeline.RenderScene(s.xyz, tabs.embedding, tabs.color, tabs.dir, tabs.conf, [P[k + ".weight"] for k in names],
+                                 [P[k + ".bias"] for k in names], ops.agg_cfg(), pipeline.query_options(**qo), device=dev)
+    campos, rot = torch.from_numpy(s.campos).to(dev), torch.from_numpy(s.camrotc2w).to(dev)
+    raydir = torch.from_numpy(s.raydir).to(dev)
+    bg = torch.ones(3, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        a, b = ev(), ev()
+        a.record(); scene.grid(); scene.point_cache(); b.record(); torch.cuda.synchronize()
+        build_ms = a.elapsed_time(b)
+        for _ in range(2):
+            out = pipeline.render_rays(scene, campos, rot, raydir, s.near, s.far, bg, precision=ops.PRECISION_BF16, want_aux=True)
+        T_v = int((out.pidx >= 0).sum()); hit = int(out.ray_mask.sum())
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(3):
+            o2 = pipeline.render_rays(scene, campos, rot, raydir, s.near, s.far, bg, precision=ops.PRECISION_BF16)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        sel = torch.from_numpy(np.random.default_rng(0).choice(raydir.shape[0], 2048, replace=False)).to(dev).sort()[0]
+        sub16 = pipeline.render_rays(scene, campos, rot, raydir[sel], s.near, s.far, bg, precision=ops.PRECISION_BF16)
+        sub32 = pipeline.render_rays(scene, campos, rot, raydir[sel], s.near, s.far, bg, precision=ops.PRECISION_FP32)
+        torch.cuda.synchronize()
+        d_self = float((sub16.ray_color - o2.ray_color[sel]).abs().max())
+        d_fp32 = float((sub16.ray_color - sub32.ray_color).abs().max())
+    print(json.dumps({"config": which, "points": n, "rays": int(raydir.shape[0]), "SR": scene.qopt.SR, "rays_hit": hit, "valid_tuples": T_v,
+                      "grid_and_point_cache_build_ms": build_ms, "ms_per_frame": ms, "rays_per_s": raydir.shape[0] / (ms * 1e-3),
+                      "max_abs_rgb_subset_vs_full_frame": d_self, "max_abs_rgb_bf16_vs_fp32": d_fp32}))
+    assert d_self <= 2e-3 and d_fp32 <= 1e-2
+
+
+if __name__ == "__main__":
+    main()
