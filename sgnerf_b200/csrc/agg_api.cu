@@ -15,20 +15,6 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
                           int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
                           float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes);
-// first-generation tensor-core kernel, selected with SGN_TC_V=1 (A/B runs only)
-int sgn_agg_tc_v1_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, size_t* bytes);
-int sgn_agg_tc_v1_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
-                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                          int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
-                          void* workspace, size_t workspace_bytes, cudaStream_t st);
-static bool tc_use_v1() { const char* e = getenv("SGN_TC_V"); return e && e[0] == '1'; }
-int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
-                       const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
-                       void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st);
-int sgn_agg_tc_point_cache_bytes(const AggPlan& P, int64_t N, size_t* bytes);
-int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, const SgnPointTables* tables, void* cache, size_t cache_bytes, cudaStream_t st);
-
 static int check_common(const SgnAggCfg* cfg, AggPlan* P, int64_t R, int SR, int K)
 {
     int rc = make_plan(cfg, P);
@@ -48,13 +34,6 @@ extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t N, int64_t 
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
     SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
     SGN_CHECK_ARG(N >= 0, "sgn_agg_workspace_bytes: bad N");
-    if (tc_use_v1()) {
-        size_t b1 = 0, b2 = 0;
-        if ((rc = sgn_agg_tc_v1_workspace_bytes(P, R, SR, K, &b1))) return rc;
-        if ((rc = sgn_agg_tc_workspace_bytes(P, N, R, SR, K, &b2))) return rc;
-        *bytes = b1 > b2 ? b1 : b2;
-        return SGN_OK;
-    }
     return sgn_agg_tc_workspace_bytes(P, N, R, SR, K, bytes);
 }
 
@@ -76,11 +55,8 @@ extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* 
                                     ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
     SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
-    if (tc_use_v1())
-        return sgn_agg_tc_v1_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
-                                     weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
     return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
-                              weight, conf_coef, workspace, workspace_bytes, tc_use_v1() ? nullptr : point_cache, (cudaStream_t)stream);
+                              weight, conf_coef, workspace, workspace_bytes, point_cache, (cudaStream_t)stream);
 }
 
 extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
