@@ -15,6 +15,13 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
                           int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
                           float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes);
+int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                       const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
+                       void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st);
+int sgn_agg_tc_point_cache_bytes(const AggPlan& P, int64_t N, size_t* bytes);
+int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, const SgnPointTables* tables, void* cache, size_t cache_bytes, cudaStream_t st);
+
 static int check_common(const SgnAggCfg* cfg, AggPlan* P, int64_t R, int SR, int K)
 {
     int rc = make_plan(cfg, P);
