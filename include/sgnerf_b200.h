@@ -147,7 +147,9 @@ int sgn_agg_num_layers(const SgnAggCfg* cfg);
 int sgn_agg_layer_shape(const SgnAggCfg* cfg, int layer, int* in_features, int* out_features);
 
 #define SGN_PRECISION_FP32 0   /* fp32 SIMT, strict parity mode                                   */
-#define SGN_PRECISION_BF16 1   /* bf16 tcgen05/TMEM tensor-core tiles, fp32 accumulate            */
+#define SGN_PRECISION_BF16 1   /* bf16 tcgen05/TMEM tensor-core tiles, fp32 accumulate (forward only) */
+#define SGN_PRECISION_TF32 2   /* layer-wise path of FP32 with its GEMMs on tcgen05 kind::tf32 (fp32 storage and accumulation;
+                                  the arithmetic of the reference's cuBLAS default, torch 1.10 allow_tf32) -- forward + backward */
 
 /* save_for_backward != 0 keeps the per-layer activations in the workspace for sgn_agg_backward.
  * N = number of points in the tables (the bf16 path keeps one 448-byte operand row per point in the workspace). */
@@ -186,6 +188,13 @@ int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const fl
                      const float* d_decoded /*[R,SR,4]*/, const float* d_conf_coef /*[R,SR,K]*/,
                      float* const* d_weights, float* const* d_biases, const SgnPointGrads* d_tables,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* The same with the arithmetic of the GEMMs chosen: SGN_PRECISION_FP32 (what sgn_agg_backward does) or SGN_PRECISION_TF32. */
+int sgn_agg_backward_prec(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases,
+                          const SgnPointTables* tables, const int32_t* pidx, const float* loc_w, const float* raydir,
+                          const float* campos, const float* camrotc2w, int64_t R, int SR, int K, int precision,
+                          const float* d_decoded /*[R,SR,4]*/, const float* d_conf_coef /*[R,SR,K]*/,
+                          float* const* d_weights, float* const* d_biases, const SgnPointGrads* d_tables,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement aid (bench.py's roofline): when enabled, the bf16 path brackets its dominant kernel, agg_tuple_tc_kernel, with
  * CUDA events on the launching stream (this serialises the host with the previous call's kernel; leave it off otherwise).

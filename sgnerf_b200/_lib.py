@@ -65,6 +65,9 @@ SIGNATURES = {
     "sgn_agg_backward": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                  c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_void, c_void,
                                  C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointGrads), c_void, c_size, c_void]),
+    "sgn_agg_backward_prec": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
+                                      c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_void, c_void,
+                                      C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointGrads), c_void, c_size, c_void]),
     "sgn_agg_kernel_timing": (c_int, [c_int]),
     "sgn_agg_kernel_timing_read": (c_int, [C.POINTER(c_f32), C.POINTER(c_int)]),
     "sgn_ray_dist": (c_int, [c_void, c_void, c_f32, c_int, c_i64, c_int, c_void, c_void]),

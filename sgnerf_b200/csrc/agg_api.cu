@@ -9,11 +9,11 @@ int sgn_agg_fp32_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, int
 int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                          int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
-                         float* conf_coef, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                         float* conf_coef, void* workspace, size_t workspace_bytes, bool tc, cudaStream_t st);
 int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                           const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                           int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
-                          float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                          float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, bool tc, cudaStream_t st);
 int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes);
 int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                        const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
@@ -37,9 +37,9 @@ extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t N, int64_t 
     int rc = check_common(cfg, &P, R, SR, K);
     if (rc) return rc;
     SGN_CHECK_ARG(bytes != nullptr, "sgn_agg_workspace_bytes: bytes is NULL");
-    if (precision == SGN_PRECISION_FP32) return sgn_agg_fp32_workspace_bytes(P, R, SR, K, save_for_backward, bytes);
+    if (precision == SGN_PRECISION_FP32 || precision == SGN_PRECISION_TF32) return sgn_agg_fp32_workspace_bytes(P, R, SR, K, save_for_backward, bytes);
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
-    SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
+    SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32 or SGN_PRECISION_TF32");
     SGN_CHECK_ARG(N >= 0, "sgn_agg_workspace_bytes: bad N");
     return sgn_agg_tc_workspace_bytes(P, N, R, SR, K, bytes);
 }
@@ -57,11 +57,12 @@ extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* 
     SGN_CHECK_ARG(tables->xyz && tables->embedding && tables->color && tables->dir, "sgn_agg_forward: xyz/embedding/color/dir tables are required");
     SGN_CHECK_ARG(P.dims.LD == 0 || tables->label_emb, "sgn_agg_forward: label embedding table missing");
     if (R == 0) return SGN_OK;
-    if (precision == SGN_PRECISION_FP32)
+    if (precision == SGN_PRECISION_FP32 || precision == SGN_PRECISION_TF32)
         return sgn_agg_fp32_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, save_for_backward, decoded,
-                                    ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, (cudaStream_t)stream);
+                                    ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, precision == SGN_PRECISION_TF32,
+                                    (cudaStream_t)stream);
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
-    SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32");
+    SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32 or SGN_PRECISION_TF32");
     return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
                               weight, conf_coef, workspace, workspace_bytes, point_cache, (cudaStream_t)stream);
 }
@@ -95,16 +96,27 @@ extern "C" int sgn_agg_point_cache_build(const SgnAggCfg* cfg, const float* cons
     return sgn_agg_tc_point_cache_build(P, weights, tables, cache, cache_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
-                                const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                                int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
-                                float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, void* stream)
+extern "C" int sgn_agg_backward_prec(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                                     const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                                     int64_t R, int SR, int K, int precision, const float* d_decoded, const float* d_conf_coef,
+                                     float* const* d_weights, float* const* d_biases, const SgnPointGrads* d_tables, void* workspace,
+                                     size_t workspace_bytes, void* stream)
 {
     AggPlan P;
     int rc = check_common(cfg, &P, R, SR, K);
     if (rc) return rc;
     SGN_CHECK_ARG(weights && tables && pidx && raydir && d_decoded, "sgn_agg_backward: NULL argument");
+    SGN_CHECK_ARG(precision == SGN_PRECISION_FP32 || precision == SGN_PRECISION_TF32, "sgn_agg_backward: precision must be FP32 or TF32");
     if (R == 0) return SGN_OK;
     return sgn_agg_fp32_backward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, d_decoded, d_conf_coef,
-                                 d_weights, d_biases, d_tables, workspace, workspace_bytes, (cudaStream_t)stream);
+                                 d_weights, d_biases, d_tables, workspace, workspace_bytes, precision == SGN_PRECISION_TF32, (cudaStream_t)stream);
+}
+
+extern "C" int sgn_agg_backward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                                const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                                int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
+                                float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, void* stream)
+{
+    return sgn_agg_backward_prec(cfg, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, SGN_PRECISION_FP32, d_decoded,
+                                 d_conf_coef, d_weights, d_biases, d_tables, workspace, workspace_bytes, stream);
 }

@@ -16,12 +16,41 @@
 // one training uses.
 #include "agg_kernels.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace sgn {
 
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
+
+// out[p, c] += sum_m w_p[m] X[m, c] (w = A[:, p], or 1 when A is NULL): bias gradients and the wgrads of the 1- / 3-output layers
+static int launch_skinny(const float* A, int lda, int np, const float* X, int ld, int ncols, const int32_t* m_ptr, int m_max, float* out, int ldo,
+                         cudaStream_t st)
+{
+    if (!out || m_max <= 0) return SGN_OK;
+    dim3 grid(cdiv(m_max, SKINNY_ROWS), cdiv(ncols, 256));
+    if (np == 1) launch(skinny_tn_kernel<1>, grid, 256, 0, st, A, lda, X, ld, ncols, m_ptr, m_max, out, ldo);
+    else launch(skinny_tn_kernel<3>, grid, 256, 0, st, A, lda, X, ld, ncols, m_ptr, m_max, out, ldo);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+// GEMM dispatch: tc = TF32 tensor-core kernels (gemm_tc.cuh) where the operand shapes allow, fp32 SIMT otherwise.
+// g.colsum (column sums of the result = the bias gradient of the layer below) is fused into the tensor-core epilogue and is a
+// separate pass over C on the SIMT path.
+static int run_gemm_nn(const GemmNN& g, bool tc, cudaStream_t st)
+{
+    if (tc && gemm_tc_nn_ok(g)) return launch_gemm_tc_nn(g, st);
+    int rc = launch_gemm_nn(g, st);
+    if (rc || !g.colsum) return rc;
+    return launch_skinny(nullptr, 0, 1, g.C, g.ldc, g.N, g.m_ptr, g.m_max, g.colsum, 0, st);
+}
+static int run_gemm_tn(const GemmTN& t, bool tc, cudaStream_t st)
+{
+    if (tc && gemm_tc_tn_ok(t)) return launch_gemm_tc_tn(t, st);
+    return launch_gemm_tn(t, st);
+}
 
 static int pack_weights(const AggPlan& P, const float* const* weights, AggWs& ws, cudaStream_t st)
 {
@@ -37,7 +66,7 @@ static int pack_weights(const AggPlan& P, const float* const* weights, AggWs& ws
 // forward for one chunk of rays
 static int agg_forward_chunk(const AggPlan& P, const float* const* weights, const float* const* biases, const AggIn& in, int64_t Rc,
                              int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* weight_out, float* conf_out,
-                             AggWs& ws, bool save, cudaStream_t st)
+                             AggWs& ws, bool save, bool tc, cudaStream_t st)
 {
     const AggDims& d = P.dims;
     const int64_t S = Rc * SR;
@@ -62,10 +91,12 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
         float* out = ws.H[save ? t : (t & 1)];
         GemmNN g = {};
         g.A1 = cur; g.lda1 = cur_ld; g.B1 = ws.Wt[t]; g.ldb1 = L.npad; g.K1 = cur_k;
+        g.Bt1 = ws.Wp[t]; g.ldbt1 = L.kpad;
         if (L.extra == EXTRA_LABEL) { g.A2 = ws.L; g.lda2 = d.LD; g.B2 = ws.Wt[t] + (size_t)cur_k * L.npad; g.ldb2 = L.npad; g.K2 = d.LD; }
         if (L.extra == EXTRA_COLORDIR) { g.A2 = ws.E7; g.lda2 = 8; g.B2 = ws.Wt[t] + (size_t)cur_k * L.npad; g.ldb2 = L.npad; g.K2 = 8; }
+        if (L.extra != EXTRA_NONE) { g.Bt2 = ws.Wp[t] + cur_k; g.ldbt2 = L.kpad; }
         g.C = out; g.ldc = d.W; g.N = d.W; g.m_ptr = T_ptr; g.m_max = Tm; g.bias = biases[t]; g.epi = EPI_BIAS_LEAKY; g.slope = d.slope;
-        if ((rc = launch_gemm_nn(g, st))) return rc;
+        if ((rc = run_gemm_nn(g, tc, st))) return rc;
         cur = out; cur_ld = d.W; cur_k = d.W;
     }
     const float* Hlast = cur;
@@ -82,8 +113,9 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
         float* out = ws.CH[save ? c : (c & 1)];
         GemmNN g = {};
         g.A1 = cur; g.lda1 = cur_ld; g.B1 = ws.Wt[l]; g.ldb1 = L.npad; g.K1 = cur_k;
+        g.Bt1 = ws.Wp[l]; g.ldbt1 = L.kpad;
         g.C = out; g.ldc = d.WC; g.N = d.WC; g.m_ptr = S_ptr; g.m_max = Sm; g.bias = biases[l]; g.epi = EPI_BIAS_LEAKY; g.slope = d.slope;
-        if ((rc = launch_gemm_nn(g, st))) return rc;
+        if ((rc = run_gemm_nn(g, tc, st))) return rc;
         cur = out; cur_ld = d.WC; cur_k = d.WC;
     }
     const int ll = P.n_layers - 1;
@@ -125,7 +157,7 @@ int sgn_agg_fp32_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, int
 int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                          int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
-                         float* conf_coef, void* workspace, size_t workspace_bytes, cudaStream_t st)
+                         float* conf_coef, void* workspace, size_t workspace_bytes, bool tc, cudaStream_t st)
 {
     const int64_t chunk = save ? R : (R < AGG_FP32_CHUNK ? R : AGG_FP32_CHUNK);
     AggWs ws;
@@ -144,7 +176,7 @@ int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const fl
         in.campos = campos; in.camrot = camrotc2w;
         rc = agg_forward_chunk(P, weights, biases, in, Rc, SR, K, decoded + r0 * SR * 4, ray_valid + r0 * SR,
                                loc_pers ? loc_pers + r0 * SR * 3 : nullptr, weight ? weight + r0 * SR * K : nullptr,
-                               conf_coef ? conf_coef + r0 * SR * K : nullptr, ws, save != 0, st);
+                               conf_coef ? conf_coef + r0 * SR * K : nullptr, ws, save != 0, tc, st);
         if (rc) return rc;
     }
     return SGN_OK;
@@ -153,7 +185,7 @@ int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const fl
 int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                           const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                           int64_t R, int SR, int K, const float* d_decoded, const float* d_conf_coef, float* const* d_weights,
-                          float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, cudaStream_t st)
+                          float* const* d_biases, const SgnPointGrads* d_tables, void* workspace, size_t workspace_bytes, bool tc, cudaStream_t st)
 {
     (void)biases; (void)loc_w;
     const AggDims& d = P.dims;
@@ -172,19 +204,18 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     SgnPointGrads g = {};
     if (d_tables) g = *d_tables;
     int rc;
+    auto skinny = [&](const float* A, int lda, int np, const float* X, int ld, int ncols, const int32_t* m_ptr, int m_max, float* out, int ldo) -> int {
+        return launch_skinny(A, lda, np, X, ld, ncols, m_ptr, m_max, out, ldo, st);
+    };
     auto bias_grad = [&](const float* dZ, int ld, int ncols, const int32_t* m_ptr, int m_max, float* out) -> int {
-        if (!out || m_max <= 0) return SGN_OK;
-        const int rpb = 512;
-        dim3 grid(cdiv(m_max, rpb), cdiv(ncols, 128));
-        launch(colsum_kernel, grid, 128, 0, st, dZ, ld, ncols, m_ptr, m_max, rpb, out);
-        SGN_LAUNCH_CHECK();
-        return SGN_OK;
+        return skinny(nullptr, 0, 1, dZ, ld, ncols, m_ptr, m_max, out, 0);
     };
     auto wgrad = [&](const float* dZ, int ldz, int Pn, const float* act, int lda, int Q, float* out, int ldc, const int32_t* m_ptr, int m_max) -> int {
         if (!out) return SGN_OK;
+        if (Pn == 1 || Pn == 3) return skinny(dZ, ldz, Pn, act, lda, Q, m_ptr, m_max, out, ldc);   // alpha_branch.0, color_branch.6
         GemmTN t = {};
         t.A = dZ; t.lda = ldz; t.P = Pn; t.B = act; t.ldb = lda; t.Q = Q; t.C = out; t.ldc = ldc; t.m_ptr = m_ptr; t.m_max = m_max;
-        return launch_gemm_tn(t, st);
+        return run_gemm_tn(t, tc, st);
     };
 
     // ---- colour branch ----
@@ -202,10 +233,12 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     {
         GemmNN q = {};
         q.A1 = ws.d_raw; q.lda1 = 8; q.B1 = ws.Wp[ll]; q.ldb1 = P.layers[ll].kpad; q.K1 = 8;
+        q.Bt1 = ws.Wt[ll]; q.ldbt1 = P.layers[ll].npad;
         const bool to_c0 = P.n_color_hidden == 0;
         q.C = dcur; q.ldc = to_c0 ? d.W : d.WC; q.N = to_c0 ? d.W : d.WC; q.m_ptr = S_ptr; q.m_max = Sm;
         q.epi = to_c0 ? EPI_NONE : EPI_MUL_DLEAKY; q.aux = Clast; q.ldaux = Clast_ld; q.slope = d.slope;
-        if ((rc = launch_gemm_nn(q, st))) return rc;
+        if (!to_c0 && d_biases) q.colsum = d_biases[P.color_layer0 + P.n_color_hidden - 1];     // bias gradient of the layer that produced Clast
+        if ((rc = run_gemm_nn(q, tc, st))) return rc;
         dcur_ld = q.ldc;
     }
     for (int c = P.n_color_hidden - 1; c >= 0; c--) {
@@ -213,14 +246,14 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         const float* a_in = c > 0 ? ws.CH[c - 1] : ws.C0;
         const int a_ld = c > 0 ? d.WC : d.kc0pad, a_k = c > 0 ? d.WC : d.kc0;
         if ((rc = wgrad(dcur, dcur_ld, d.WC, a_in, a_ld, a_k, d_weights ? d_weights[l] : nullptr, P.layers[l].in, S_ptr, Sm))) return rc;
-        if ((rc = bias_grad(dcur, dcur_ld, d.WC, S_ptr, Sm, d_biases ? d_biases[l] : nullptr))) return rc;
         float* dnext = ws.dC[(P.n_color_hidden - c) & 1];
         GemmNN q = {};
         q.A1 = dcur; q.lda1 = dcur_ld; q.B1 = ws.Wp[l]; q.ldb1 = P.layers[l].kpad; q.K1 = d.WC;
+        q.Bt1 = ws.Wt[l]; q.ldbt1 = P.layers[l].npad;
         q.C = dnext; q.m_ptr = S_ptr; q.m_max = Sm; q.slope = d.slope;
-        if (c > 0) { q.ldc = d.WC; q.N = d.WC; q.epi = EPI_MUL_DLEAKY; q.aux = a_in; q.ldaux = a_ld; }
+        if (c > 0) { q.ldc = d.WC; q.N = d.WC; q.epi = EPI_MUL_DLEAKY; q.aux = a_in; q.ldaux = a_ld; q.colsum = d_biases ? d_biases[l - 1] : nullptr; }
         else { q.ldc = d.W; q.N = d.W; q.epi = EPI_NONE; }      // only dF = dC0[:, :W] is needed (view encoding has no gradient)
-        if ((rc = launch_gemm_nn(q, st))) return rc;
+        if ((rc = run_gemm_nn(q, tc, st))) return rc;
         dcur = dnext; dcur_ld = q.ldc;
     }
     const float* dF = dcur;   // [S_v, W]
@@ -251,21 +284,23 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
             if ((rc = wgrad(dZ, d.W, d.W, ws.L, d.LD, d.LD, d_weights[t] + a_k, L.in, T_ptr, Tm))) return rc;
         if (L.extra == EXTRA_COLORDIR && d_weights)
             if ((rc = wgrad(dZ, d.W, d.W, ws.E7, 8, 7, d_weights[t] + a_k, L.in, T_ptr, Tm))) return rc;
-        if ((rc = bias_grad(dZ, d.W, d.W, T_ptr, Tm, d_biases ? d_biases[t] : nullptr))) return rc;
+        if (t == nt - 1 && (rc = bias_grad(dZ, d.W, d.W, T_ptr, Tm, d_biases ? d_biases[t] : nullptr))) return rc;   // lower layers: fused below
         if (L.extra == EXTRA_COLORDIR && (g.color || g.dir)) {
             GemmNN q = {};
             q.A1 = dZ; q.lda1 = d.W; q.B1 = ws.Wp[t] + a_kpad; q.ldb1 = L.kpad; q.K1 = d.W;
+            q.Bt1 = ws.Wt[t] + (size_t)a_kpad * L.npad; q.ldbt1 = L.npad;
             q.C = ws.dE7; q.ldc = 8; q.N = 8; q.m_ptr = T_ptr; q.m_max = Tm; q.epi = EPI_NONE;
-            if ((rc = launch_gemm_nn(q, st))) return rc;
+            if ((rc = run_gemm_nn(q, tc, st))) return rc;
             dE7 = ws.dE7;
         }
         if (t > 0 || g.embedding) {
             float* dnext = t > 0 ? ws.dZ[(nt - t) & 1] : ws.dX0;
             GemmNN q = {};
             q.A1 = dZ; q.lda1 = d.W; q.B1 = ws.Wp[t]; q.ldb1 = L.kpad; q.K1 = d.W;
+            q.Bt1 = ws.Wt[t]; q.ldbt1 = L.npad;
             q.C = dnext; q.ldc = a_kpad; q.N = a_kpad; q.m_ptr = T_ptr; q.m_max = Tm; q.slope = d.slope;
-            if (t > 0) { q.epi = EPI_MUL_DLEAKY; q.aux = a_in; q.ldaux = a_ld; } else { q.epi = EPI_NONE; }
-            if ((rc = launch_gemm_nn(q, st))) return rc;
+            if (t > 0) { q.epi = EPI_MUL_DLEAKY; q.aux = a_in; q.ldaux = a_ld; q.colsum = d_biases ? d_biases[t - 1] : nullptr; } else { q.epi = EPI_NONE; }
+            if ((rc = run_gemm_nn(q, tc, st))) return rc;
             dZ = dnext;
         }
     }

@@ -242,18 +242,64 @@ static __global__ void pack_weight_kernel(const float* __restrict__ W, int N, in
 
 // ---- backward-only kernels ----
 
-// column sums: out[c] += sum_m X[m, c]  (bias gradients)
-static __global__ void __launch_bounds__(128)
-colsum_kernel(const float* __restrict__ X, int ld, int ncols, const int32_t* __restrict__ m_ptr, int m_max, int rows_per_block, float* __restrict__ out)
+// Skinny reductions over the rows: out[p, c] += sum_m w_p[m] X[m, c] for p < NP, with w_p[m] = A[m, p], or 1 when A is NULL
+// (bias gradients = column sums; the wgrads of the 1- and 3-output layers alpha_branch.0 / color_branch.6).
+// Block = 64 column quads x 4 row groups over SKINNY_ROWS rows; four 16-byte loads in flight per thread.
+constexpr int SKINNY_ROWS = 256;
+template <int NP>
+static __global__ void __launch_bounds__(256)
+skinny_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ X, int ld, int ncols, const int32_t* __restrict__ m_ptr, int m_max,
+                 float* __restrict__ out, int ldo)
 {
     const int M = min(*m_ptr, m_max);
-    const int c = blockIdx.y * 128 + threadIdx.x;
-    const int m0 = blockIdx.x * rows_per_block;
-    if (m0 >= M || c >= ncols) return;
-    const int m1 = min(M, m0 + rows_per_block);
-    float acc = 0.f;
-    for (int m = m0; m < m1; m++) acc += X[(size_t)m * ld + c];
-    atomicAdd(out + c, acc);
+    const int m0 = blockIdx.x * SKINNY_ROWS;
+    if (m0 >= M) return;
+    const int m1 = min(M, m0 + SKINNY_ROWS);
+    const int cq = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int c = blockIdx.y * 256 + 4 * cq;
+    const bool vec = (ld & 3) == 0 && c + 4 <= ncols && (((uintptr_t)X) & 15) == 0;
+    float acc[NP][4];
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[p][j] = 0.f;
+    if (c < ncols) {
+#pragma unroll 4
+        for (int m = m0 + rg; m < m1; m += 4) {
+            const float* src = X + (size_t)m * ld + c;
+            float4 x;
+            if (vec) x = *(const float4*)src;
+            else {
+                x.x = src[0];
+                x.y = c + 1 < ncols ? src[1] : 0.f;
+                x.z = c + 2 < ncols ? src[2] : 0.f;
+                x.w = c + 3 < ncols ? src[3] : 0.f;
+            }
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const float w = A ? __ldg(A + (size_t)m * lda + p) : 1.f;
+                acc[p][0] = fmaf(w, x.x, acc[p][0]); acc[p][1] = fmaf(w, x.y, acc[p][1]);
+                acc[p][2] = fmaf(w, x.z, acc[p][2]); acc[p][3] = fmaf(w, x.w, acc[p][3]);
+            }
+        }
+    }
+    __shared__ float red[3][64][NP * 4 + 1];
+    if (rg > 0) {
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) red[rg - 1][cq][p * 4 + j] = acc[p][j];
+    }
+    __syncthreads();
+    if (rg == 0 && c < ncols) {
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float v = acc[p][j] + red[0][cq][p * 4 + j] + red[1][cq][p * 4 + j] + red[2][cq][p * 4 + j];
+                if (c + j < ncols) atomicAdd(out + (size_t)p * ldo + c + j, v);
+            }
+    }
 }
 
 // One warp per compact sample: d_raw[c, 0:3] = d_rgb * scale * sig (1 - sig), padded to 8 columns
@@ -323,12 +369,26 @@ agg_ksum_bwd_kernel(AggIn in, AggDims d, int K, const int32_t* __restrict__ T_pt
 }
 
 // cotangent of the conf_coefficient output (all slots, invalid ones use point 0 like the reference's clamp(pidx,0) gather)
-static __global__ void agg_conf_out_bwd_kernel(const int32_t* __restrict__ pidx, int64_t n, const float* __restrict__ d_conf_coef, float* __restrict__ d_conf)
+static __global__ void __launch_bounds__(256)
+agg_conf_out_bwd_kernel(const int32_t* __restrict__ pidx, int64_t n, const float* __restrict__ d_conf_coef, float* __restrict__ d_conf)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float g = d_conf_coef[i];
-    if (g != 0.f) atomicAdd(d_conf + (pidx[i] < 0 ? 0 : pidx[i]), g);
+    float to0 = 0.f;                       // invalid slots all land on point 0: one atomic per block instead of one per slot
+    if (i < n) {
+        const float g = d_conf_coef[i];
+        const int p = pidx[i];
+        if (p <= 0) to0 = g;
+        else if (g != 0.f) atomicAdd(d_conf + p, g);
+    }
+    to0 = warp_sum(to0);
+    __shared__ float part[8];
+    if (lane_id() == 0) part[threadIdx.x >> 5] = to0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; w++) s += part[w];
+        if (s != 0.f) atomicAdd(d_conf, s);
+    }
 }
 
 // One warp per tuple: scatter-add into the point tables.

@@ -16,11 +16,13 @@ enum Epilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_LEAKY = 2, EPI_MUL_DLEAKY =
 struct GemmNN {
     const float* A1; int lda1; const float* B1; int ldb1; int K1;
     const float* A2; int lda2; const float* B2; int ldb2; int K2;   // optional second operand pair (concat input)
+    const float* Bt1; int ldbt1; const float* Bt2; int ldbt2;       // the same B operands transposed ([N, ldbt], K contiguous): what the tensor-core path reads
     float* C; int ldc; int N;
     const int* m_ptr; int m_max;
     const float* bias;        // [N] for EPI_BIAS*
     const float* aux; int ldaux;  // saved activation for EPI_MUL_DLEAKY: C *= (aux > 0 ? 1 : slope)
     int epi; float slope;
+    float* colsum;            // optional [N]: += column sums of the stored C over the valid rows (bias gradient of the next wgrad); tensor-core path only
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 8, GTHREADS = 256, GPAD = 4;

@@ -1,0 +1,432 @@
+// gemm_tc.cuh -- TF32 tensor-core GEMMs (tcgen05.mma kind::tf32, fp32 accumulators in TMEM) for the layer-wise training path.
+//
+//   gemm_tc_nn : C[M,N] = epi( A1[M,K1] Bt1[N,K1]^T (+ A2[M,K2] Bt2[N,K2]^T) )        forward layers and dgrad
+//   gemm_tc_tn : C[P,Q] += sum_m A[m,p] B[m,q]   (m split over CTAs, red.global.add)   wgrad
+//
+// The reference runs these contractions in cuBLAS through torch.nn.Linear (models/aggregators/point_aggregators.py:111-175);
+// its pinned torch (1.10) has allow_tf32 on, so TF32 operands with fp32 accumulation is the reference's own arithmetic.
+//
+// Operands stay fp32 in HBM (tf32 = the top 19 bits, the tensor core ignores the rest) and go to shared memory with 16-byte
+// cp.async copies whose destination addresses carry the UMMA swizzle:
+//   * nn: A and Bt rows are K-contiguous -> K-major SWIZZLE_128B tiles (row = 128 B = 32 floats, 16-byte chunk ^= row & 7);
+//   * tn: both operands are m-major ([m, p] rows) -> MN-major tiles; for 32-bit types the only MN-major layout of the tensor
+//     core is SWIZZLE_128B_BASE32B (32-byte chunk ^= k-row & 3; MN atoms of 32 floats LBO apart, 4-row k-groups SBO apart).
+// M (valid tuples / samples) is only known on the device: the kernels read it from *m_ptr and are persistent over the tiles
+// (nn) or split the m range evenly over the grid (tn), so the host never synchronises.
+// Warp roles: 0-3 epilogue (TMEM lane quarter = warp), 4-7 cp.async loaders, 8 MMA issuer.
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "tc_ptx.cuh"
+
+namespace sgn {
+
+constexpr int GT_THREADS = 288;
+constexpr int GT_LAG = 2;                     // cp.async groups a loader thread keeps in flight
+
+// ---- PTX helpers specific to these kernels
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// instruction descriptor, kind::tf32: A = B = tf32 (format 2), D = f32; a_mn / b_mn = operand is MN-major
+__host__ __device__ constexpr uint32_t tc_idesc_tf32(int M, int N, int a_mn, int b_mn)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major SWIZZLE_128B_BASE32B operand: MN atoms (32 floats) `lbo` bytes apart, 4-row k-groups 512 B apart (rows packed at 128 B)
+__device__ __forceinline__ uint64_t umma_desc_mn32(uint32_t saddr, uint32_t lbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+// ordered with respect to the surrounding shared-memory stores (tc_ptx.cuh's lds128f is a pure asm the compiler may hoist)
+__device__ __forceinline__ float4 lds128f_v(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------ nn
+struct GemmTcNN {
+    const float* A1; int lda1; const float* Bt1; int ldb1; int K1;     // Bt: [N, ldb], K contiguous
+    const float* A2; int lda2; const float* Bt2; int ldb2; int K2;
+    float* C; int ldc; int N; int BN;                                  // BN = columns per CTA (multiple of 16, <= 256)
+    const int* m_ptr; int m_max;
+    const float* bias; const float* aux; int ldaux; int epi; float slope;
+    float* colsum;                                                     // optional [N]: += column sums of the stored C (valid rows)
+};
+
+constexpr int NN_STAGES = 4;
+constexpr int NN_A_BYTES = 128 * 128, NN_B_BYTES = 256 * 128, NN_STAGE_BYTES = NN_A_BYTES + NN_B_BYTES;
+constexpr int NN_OFF_EPI = NN_STAGES * NN_STAGE_BYTES;            // 4 warps x (32 rows x 128 B) staging
+constexpr int NN_OFF_BAR = NN_OFF_EPI + 4 * 4096;
+constexpr int NN_SMEM = NN_OFF_BAR + 256 + 1024;
+
+static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTcNN p)
+{
+    const int M = min(*p.m_ptr, p.m_max);
+    const int ntile = (M + 127) >> 7;
+    if ((int)blockIdx.x >= ntile) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_full = sbase + NN_OFF_BAR, bar_empty = bar_full + 8 * NN_STAGES, bar_accf = bar_empty + 8 * NN_STAGES, bar_acce = bar_accf + 16;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(smem + NN_OFF_BAR + 8 * (2 * NN_STAGES + 4));
+    if (tid == 0) {
+        for (int s = 0; s < NN_STAGES; s++) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_accf + 8 * a, 1); mbar_init(bar_acce + 8 * a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int n0 = blockIdx.y * p.BN;
+    const int nst1 = (p.K1 + 31) >> 5, nst = nst1 + (p.A2 ? (p.K2 + 31) >> 5 : 0);
+
+    if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ loaders
+        const int lt = tid - 128;
+        const int c = lt & 7, r0 = lt >> 3;                    // 16-byte chunk of a 128-byte row; rows r0, r0 + 16, ...
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+            const int m0 = tile << 7;
+            for (int i = 0; i < nst; i++, it++) {
+                const bool second = i >= nst1;
+                const float* A = second ? p.A2 : p.A1;
+                const float* B = second ? p.Bt2 : p.Bt1;
+                const int lda = second ? p.lda2 : p.lda1, ldb = second ? p.ldb2 : p.ldb1;
+                const int k0 = (second ? i - nst1 : i) << 5;
+                const int kleft = (second ? p.K2 : p.K1) - k0;   // columns of this stage that exist (multiple of 8)
+                const uint32_t s = it % NN_STAGES, ph = (it / NN_STAGES) & 1;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                const uint32_t sa = sbase + s * NN_STAGE_BYTES, sb = sa + NN_A_BYTES;
+                if (4 * c < kleft) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int row = r0 + 16 * j;
+                        if (m0 + row < M) cp_async16(sa + row * 128 + ((c ^ (row & 7)) << 4), A + (size_t)(m0 + row) * lda + k0 + 4 * c, 16);
+                    }
+                    for (int row = r0; row < p.BN; row += 16)
+                        if (n0 + row < p.N) cp_async16(sb + row * 128 + ((c ^ (row & 7)) << 4), B + (size_t)(n0 + row) * ldb + k0 + 4 * c, 16);
+                }
+                cp_async_commit();
+                if (it >= GT_LAG) {
+                    cp_async_wait<GT_LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(bar_full + 8 * ((it - GT_LAG) % NN_STAGES));
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (uint32_t j = it > GT_LAG ? it - GT_LAG : 0; j < it; j++) mbar_arrive(bar_full + 8 * (j % NN_STAGES));
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_tf32(128, p.BN, 0, 0);
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, tl++) {
+                const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+                mbar_wait(bar_acce + 8 * acc, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int i = 0; i < nst; i++, it++) {
+                    const bool second = i >= nst1;
+                    const int kleft = (second ? p.K2 - ((i - nst1) << 5) : p.K1 - (i << 5));
+                    const int ksteps = kleft >= 32 ? 4 : kleft >> 3;
+                    const uint32_t s = it % NN_STAGES, ph = (it / NN_STAGES) & 1;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint64_t ad = umma_desc(sbase + s * NN_STAGE_BYTES), bd = umma_desc(sbase + s * NN_STAGE_BYTES + NN_A_BYTES);
+                    for (int k = 0; k < ksteps; k++) tc_mma_tf32(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (i | k) != 0);
+                    tc_commit(bar_empty + 8 * s);
+                }
+                tc_commit(bar_accf + 8 * acc);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> swizzled staging -> coalesced rows
+        const uint32_t stg = sbase + NN_OFF_EPI + warp * 4096;
+        const int c4 = lane & 7, rsub = lane >> 3;
+        float4 cs[8];                                          // column sums of what this thread stores (chunk ch, columns 4 c4 .. + 3)
+#pragma unroll
+        for (int i = 0; i < 8; i++) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, tl++) {
+            const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            const int m0 = (tile << 7) + warp * 32;
+            mbar_wait(bar_accf + 8 * acc, aph);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) {
+                if (ch * 32 >= p.BN) break;
+                const int nl = ch * 32 + 4 * c4;              // column inside this CTA's BN columns
+                const int n = n0 + nl;
+                const bool ncol = nl < p.BN && n < p.N;
+                // saved activations of this chunk (dLeakyReLU mask): all eight loads in flight before the accumulators are touched
+                float4 ax[8];
+                if (p.epi == EPI_MUL_DLEAKY) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int m = m0 + 4 * i + rsub;
+                        ax[i] = (ncol && m < M) ? __ldg((const float4*)(p.aux + (size_t)m * p.ldaux + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                uint32_t v[32];
+                tc_ld32(tmem_base + acc * 256 + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+                for (int q = 0; q < 8; q++) sts128(stg + lane * 128 + ((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ncol && (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LEAKY)) bb = __ldg((const float4*)(p.bias + n));
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = 4 * i + rsub;
+                    float4 x = lds128f_v(stg + row * 128 + ((c4 ^ (row & 7)) << 4));
+                    const int m = m0 + row;
+                    if (ncol && m < M) {
+                        if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LEAKY) {
+                            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                            if (p.epi == EPI_BIAS_LEAKY) {
+                                x.x = x.x > 0.f ? x.x : x.x * p.slope; x.y = x.y > 0.f ? x.y : x.y * p.slope;
+                                x.z = x.z > 0.f ? x.z : x.z * p.slope; x.w = x.w > 0.f ? x.w : x.w * p.slope;
+                            }
+                        } else if (p.epi == EPI_MUL_DLEAKY) {
+                            const float4 a = ax[i];
+                            x.x *= a.x > 0.f ? 1.f : p.slope; x.y *= a.y > 0.f ? 1.f : p.slope;
+                            x.z *= a.z > 0.f ? 1.f : p.slope; x.w *= a.w > 0.f ? 1.f : p.slope;
+                        }
+                        *(float4*)(p.C + (size_t)m * p.ldc + n) = x;
+                        cs[ch].x += x.x; cs[ch].y += x.y; cs[ch].z += x.z; cs[ch].w += x.w;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_acce + 8 * acc);
+        }
+        if (p.colsum) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) {
+                float4 v = cs[ch];                             // the four row phases (lane >> 3) hold the same columns
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, 8); v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, 8); v.w += __shfl_xor_sync(0xffffffffu, v.w, 8);
+                v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+                v.z += __shfl_xor_sync(0xffffffffu, v.z, 16); v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
+                const int nl = ch * 32 + 4 * c4, n = n0 + nl;
+                if (rsub == 0 && nl < p.BN && n < p.N) red_add_v4(p.colsum + n, v.x, v.y, v.z, v.w);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+static inline bool gemm_tc_nn_ok(const GemmNN& g)
+{
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    if (g.K1 % 8 || (g.lda1 & 3) || (g.ldbt1 & 3) || !al(g.A1) || !al(g.Bt1) || !g.Bt1) return false;
+    if (g.A2 && (g.K2 % 8 || (g.lda2 & 3) || (g.ldbt2 & 3) || !al(g.A2) || !al(g.Bt2) || !g.Bt2)) return false;
+    if ((g.N & 3) || (g.ldc & 3) || !al(g.C)) return false;
+    if (g.epi == EPI_MUL_DLEAKY && ((g.ldaux & 3) || !al(g.aux))) return false;
+    if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_LEAKY) && !al(g.bias)) return false;
+    if (g.colsum && !al(g.colsum)) return false;
+    return true;
+}
+
+static inline int launch_gemm_tc_nn(const GemmNN& g, cudaStream_t st)
+{
+    if (g.m_max <= 0) return SGN_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGN_CUDA(cudaFuncSetAttribute(gemm_tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
+        attr_set = true;
+    }
+    GemmTcNN p = {};
+    p.A1 = g.A1; p.lda1 = g.lda1; p.Bt1 = g.Bt1; p.ldb1 = g.ldbt1; p.K1 = g.K1;
+    p.A2 = g.A2; p.lda2 = g.lda2; p.Bt2 = g.Bt2; p.ldb2 = g.ldbt2; p.K2 = g.K2;
+    p.C = g.C; p.ldc = g.ldc; p.N = g.N; p.m_ptr = g.m_ptr; p.m_max = g.m_max;
+    p.bias = g.bias; p.aux = g.aux; p.ldaux = g.ldaux; p.epi = g.epi; p.slope = g.slope; p.colsum = g.colsum;
+    const int nsplit = cdiv(g.N, 256);
+    p.BN = (cdiv(g.N, nsplit) + 15) / 16 * 16;
+    const int tiles = cdiv(g.m_max, 128);
+    const int gx = tiles < 148 / nsplit ? tiles : 148 / nsplit;
+    launch(gemm_tc_nn_kernel, dim3(gx, nsplit), GT_THREADS, NN_SMEM, st, p);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tn (wgrad)
+struct GemmTcTN {
+    const float* A; int lda; int P;        // dZ  [M, lda], P columns used (multiple of 32, <= 256)
+    const float* B; int ldb; int Q;        // act [M, ldb], Q columns used
+    float* C; int ldc;                     // grad [P, ldc] (+=)
+    const int* m_ptr; int m_max; int BQ;   // BQ = columns of B per CTA (multiple of 16, <= 256)
+};
+
+constexpr int TN_STAGES = 3;
+constexpr int TN_ATOM = 32 * 128;                                  // one MN atom of a stage: 32 m-rows x 128 B
+constexpr int TN_A_BYTES = 8 * TN_ATOM, TN_B_BYTES = 8 * TN_ATOM, TN_STAGE_BYTES = TN_A_BYTES + TN_B_BYTES;
+constexpr int TN_OFF_EPI = TN_STAGES * TN_STAGE_BYTES;             // 4 warps x 32 x 33 floats
+constexpr int TN_EPI_WARP = 32 * 33 * 4;
+constexpr int TN_OFF_BAR = TN_OFF_EPI + 4 * TN_EPI_WARP + 128;
+constexpr int TN_SMEM = TN_OFF_BAR + 256 + 1024;
+
+static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_tn_kernel(GemmTcTN p)
+{
+    const int M = min(*p.m_ptr, p.m_max);
+    const int mpb = ((M + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31;
+    const int mb = blockIdx.x * mpb;
+    if (mb >= M) return;
+    const int me = min(M, mb + mpb);
+    const int nst = (me - mb + 31) >> 5;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_full = sbase + TN_OFF_BAR, bar_empty = bar_full + 8 * TN_STAGES, bar_done = bar_empty + 8 * TN_STAGES;
+    uint32_t* tmem_ptr_smem = (uint32_t*)(smem + TN_OFF_BAR + 8 * (2 * TN_STAGES + 2));
+    if (tid == 0) {
+        for (int s = 0; s < TN_STAGES; s++) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int q0 = blockIdx.y * p.BQ;
+    const int atoms_a = p.P >> 5, atoms_b = (p.BQ + 31) >> 5;
+    const int nhalf = (p.P + 127) >> 7;
+
+    if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ loaders: rows of m, 128-byte segments, BASE32B swizzle
+        const int lt = tid - 128;
+        const int jj = lt & 7, r0 = lt >> 3;                   // 16-byte piece of a 128-byte segment; m-rows r0 and r0 + 16
+        for (int i = 0; i < nst; i++) {
+            const uint32_t s = i % TN_STAGES, ph = (i / TN_STAGES) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            const uint32_t sa = sbase + s * TN_STAGE_BYTES, sb = sa + TN_A_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = r0 + 16 * h;
+                const int m = mb + (i << 5) + row;
+                const bool live = m < me;
+                const uint32_t off = row * 128 + ((((uint32_t)jj >> 1) ^ (row & 3)) << 5) + (jj & 1) * 16;
+                const float* arow = p.A + (size_t)(live ? m : mb) * p.lda + 4 * jj;
+                const float* brow = p.B + (size_t)(live ? m : mb) * p.ldb;
+                for (int a = 0; a < atoms_a; a++) cp_async16(sa + a * TN_ATOM + off, arow + 32 * a, live ? 16u : 0u);
+                for (int b = 0; b < atoms_b; b++) {
+                    const int col = q0 + 32 * b + 4 * jj;
+                    const bool in = live && col + 4 <= p.ldb;
+                    cp_async16(sb + b * TN_ATOM + off, in ? brow + col : p.B, in ? 16u : 0u);
+                }
+            }
+            cp_async_commit();
+            if (i >= GT_LAG) {
+                cp_async_wait<GT_LAG>();
+                fence_proxy_async();
+                mbar_arrive(bar_full + 8 * ((i - GT_LAG) % TN_STAGES));
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int j = nst > GT_LAG ? nst - GT_LAG : 0; j < nst; j++) mbar_arrive(bar_full + 8 * (j % TN_STAGES));
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc_tf32(128, p.BQ, 1, 1);
+            for (int i = 0; i < nst; i++) {
+                const uint32_t s = i % TN_STAGES, ph = (i / TN_STAGES) & 1;
+                mbar_wait(bar_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t sa = sbase + s * TN_STAGE_BYTES, sb = sa + TN_A_BYTES;
+                for (int k = 0; k < 4; k++) {                  // K-step = 8 m-rows = 1 KB further down every atom
+                    const uint64_t bd = umma_desc_mn32(sb + k * 1024, TN_ATOM);
+                    for (int h = 0; h < nhalf; h++)
+                        tc_mma_tf32(tmem_base + h * 256, umma_desc_mn32(sa + h * 4 * TN_ATOM + k * 1024, TN_ATOM), bd, idesc, (i | k) != 0);
+                }
+                tc_commit(bar_empty + 8 * s);
+            }
+            tc_commit(bar_done);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: TMEM -> padded staging -> coalesced reductions
+        const uint32_t stg = sbase + TN_OFF_EPI + warp * TN_EPI_WARP;
+        mbar_wait(bar_done, 0);
+        tc_fence_after();
+        const int qend = min(p.Q, q0 + p.BQ);
+        for (int h = 0; h < nhalf; h++) {
+            const int prow0 = h * 128 + warp * 32;
+            for (int ch = 0; ch * 32 < p.BQ; ch++) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + h * 256 + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) sts32(stg + (lane * 33 + j) * 4, v[j]);
+                __syncwarp();
+                const int q = q0 + ch * 32 + lane;
+                if (q < qend) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; r++) {
+                        const int pp = prow0 + r;
+                        if (pp < p.P) red_add_f32(p.C + (size_t)pp * p.ldc + q, ldsf(stg + (r * 33 + lane) * 4));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+static inline bool gemm_tc_tn_ok(const GemmTN& t)
+{
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    return t.P >= 32 && t.P <= 256 && t.P % 32 == 0 && (t.lda & 3) == 0 && (t.ldb & 3) == 0 && t.lda >= t.P && al(t.A) && al(t.B);
+}
+
+static inline int launch_gemm_tc_tn(const GemmTN& t, cudaStream_t st)
+{
+    if (t.m_max <= 0) return SGN_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SGN_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+        attr_set = true;
+    }
+    GemmTcTN p = {};
+    p.A = t.A; p.lda = t.lda; p.P = t.P; p.B = t.B; p.ldb = t.ldb; p.Q = t.Q; p.C = t.C; p.ldc = t.ldc; p.m_ptr = t.m_ptr; p.m_max = t.m_max;
+    const int nq = cdiv(t.Q, 256);
+    p.BQ = (cdiv(t.Q, nq) + 15) / 16 * 16;
+    int gx = 148 / nq;
+    const int most = cdiv(t.m_max, 32);
+    if (gx > most) gx = most;
+    launch(gemm_tc_tn_kernel, dim3(gx, nq), GT_THREADS, TN_SMEM, st, p);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+}  // namespace sgn

@@ -220,7 +220,11 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     launch(march_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
                                                                    sample_mask, semantic ? sample_label : nullptr, ray_mask);
     const int nlayer = (kernel_size0 + 1) / 2;
-    const int rpb = KNN_SLOTS / SR > 0 ? KNN_SLOTS / SR : 1;      // rays per block (SR <= 1024 keeps the list under 4 KB ... 6 KB)
+    // rays per block: up to KNN_SLOTS sample slots (6 KB list), fewer for small ray counts (a training patch) so that the grid still
+    // covers the 148 SMs several times over, but never fewer slots than the block has threads
+    int rpb = KNN_SLOTS / SR > 0 ? KNN_SLOTS / SR : 1;
+    const int rpb_fill = (int)(R / (148 * 8)), rpb_min = cdiv(128, SR);
+    if (rpb > rpb_fill) rpb = rpb_fill > rpb_min ? rpb_fill : (rpb_min < rpb ? rpb_min : rpb);
     const int nb = cdiv(R, rpb);
     const size_t ksm = (size_t)rpb * SR * sizeof(int32_t);
     if (K == 8) {

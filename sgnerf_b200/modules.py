@@ -351,7 +351,15 @@ class PointAggregator(nn.Module):
         npnts = ctx.neural_points
         lin = self._linears()
         training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        precision = ops.PRECISION_FP32 if (training or _opt(self.opt, "sgn_precision", "auto") == "fp32") else ops.PRECISION_BF16
+        # opt.sgn_precision: "auto" = TF32 tensor-core GEMMs when training (the reference's cuBLAS default at its pinned torch), bf16
+        # tensor-core kernels for inference; "fp32" = strict fp32 SIMT everywhere; "tf32" = the layer-wise TF32 path everywhere
+        mode = _opt(self.opt, "sgn_precision", "auto")
+        if mode == "fp32":
+            precision = ops.PRECISION_FP32
+        elif training or mode == "tf32":
+            precision = ops.PRECISION_TF32
+        else:
+            precision = ops.PRECISION_BF16
         opt = self.opt
         want = not ((_opt(opt, "sparse_loss_weight", 0) <= 0) and ("conf_coefficient" not in _opt(opt, "zero_one_loss_items", "")) and _opt(opt, "prob", 0) == 0)
         label = npnts.bpnet_points_embedding[0] if (self.label_dim > 0 and npnts.bpnet_points_embedding is not None) else None

@@ -14,6 +14,7 @@ from ._lib import SgnAggCfg, SgnGridCfg, SgnPointGrads, SgnPointTables
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_TF32 = 2     # layer-wise path with TF32 tensor-core GEMMs (forward + backward): the training precision
 
 
 def _ptr(t):
@@ -257,6 +258,11 @@ def _tables(xyz, embedding, color, dirs, conf, label_emb):
     return tb
 
 
+# Test hook: run the backward GEMMs in this precision instead of the forward call's (both read the same saved workspace, so a
+# TF32 forward followed by an fp32 and a TF32 backward isolates the rounding of the backward GEMMs from LeakyReLU-kink flips).
+BACKWARD_PRECISION_OVERRIDE = None
+
+
 class _Aggregate(torch.autograd.Function):
     """decoded, ray_valid, loc_pers, weight, conf_coef = f(embedding, color, dir, conf, *weights, *biases)."""
 
@@ -270,8 +276,8 @@ class _Aggregate(torch.autograd.Function):
         R, SR, K = pidx.shape
         dev = pidx.device
         need_grad = meta.grad_enabled and any(ctx.needs_input_grad[1:])    # forward() itself always runs with grad mode off
-        if need_grad and precision != PRECISION_FP32:
-            raise RuntimeError("sgnerf_b200: training runs the fp32 path; the bf16 tensor-core path is forward-only")
+        if need_grad and precision == PRECISION_BF16:
+            raise RuntimeError("sgnerf_b200: training runs the fp32 or tf32 path; the bf16 tensor-core path is forward-only")
         nbytes = C.c_size_t()
         _lib.call("sgn_agg_workspace_bytes", C.byref(cfg), xyz.shape[0], R, SR, K, precision, int(need_grad), C.byref(nbytes))
         ws = _workspace(nbytes.value, dev)
@@ -315,8 +321,9 @@ class _Aggregate(torch.autograd.Function):
         gr.color = d_col.data_ptr() if d_col is not None else None
         gr.dir = d_dir.data_ptr() if d_dir is not None else None
         gr.conf = d_conf.data_ptr() if d_conf is not None else None
-        _lib.call("sgn_agg_backward", C.byref(meta.cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(meta.pidx),
-                  _ptr(meta.loc_w), _ptr(meta.raydir), _ptr(meta.campos), _ptr(meta.camrot), R, SR, K, _ptr(g_decoded),
+        _lib.call("sgn_agg_backward_prec", C.byref(meta.cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(meta.pidx),
+                  _ptr(meta.loc_w), _ptr(meta.raydir), _ptr(meta.campos), _ptr(meta.camrot), R, SR, K,
+                  meta.precision if BACKWARD_PRECISION_OVERRIDE is None else int(BACKWARD_PRECISION_OVERRIDE), _ptr(g_decoded),
                   _ptr(g_conf_c), _ptr_array(d_w), _ptr_array(d_b), C.byref(gr), _ptr(ctx.ws), ctx.ws.numel() * 4, _stream())
         ctx.ws = None
         return (None, d_emb, d_col, d_dir, d_conf, *d_w, *d_b)

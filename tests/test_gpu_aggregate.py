@@ -266,3 +266,59 @@ def test_bf16_point_cache(semantic):
     torch.cuda.synchronize()
     assert torch.equal(a[0], b[0])
     assert torch.equal(c[0], b[0]) and not torch.equal(d[0], b[0])
+
+
+def _tf32_case(R, SR, semantic, prec, bwd_override=None):
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
+    N, K = 5000, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=21 + semantic, prefix_mask=True)
+    P = rr.init_params(cfg, seed=4, bias_scale=0.1)
+    g = torch.Generator().manual_seed(6)
+    cot_d, cot_c = torch.randn(R, SR, 4, generator=g).cuda(), (torch.randn(R, SR, K, generator=g) * 0.1).cuda()
+    names, W, B = param_lists(P, cfg, requires_grad=True)
+    tc = {k: getattr(tables, k).clone().cuda().requires_grad_(True) for k in ("embedding", "color", "dir", "conf")}
+    lab = tables.label_embedding.cuda() if semantic else None
+    dec, valid, _, w, conf = ops.aggregate(cfg_to_c(cfg), W, B, tables.xyz.cuda(), tc["embedding"], tc["color"], tc["dir"], tc["conf"],
+                                           lab, pidx.cuda(), loc_w.cuda(), raydir.cuda(), campos.cuda(), rot.cuda(), precision=prec)
+    ops.BACKWARD_PRECISION_OVERRIDE = bwd_override
+    try:
+        ((dec * cot_d).sum() + (conf * cot_c).sum()).backward()
+    finally:
+        ops.BACKWARD_PRECISION_OVERRIDE = None
+    grads = {k: v.grad for k, v in tc.items()}
+    grads.update({n + ".weight": x.grad for n, x in zip(names, W)})
+    grads.update({n + ".bias": x.grad for n, x in zip(names, B)})
+    return dec.detach(), valid, grads
+
+
+TF32_SHAPES = [(37, 24, False), (37, 24, True), (700, 24, False), (129, 80, True)]
+
+
+@pytest.mark.parametrize("R,SR,semantic", TF32_SHAPES)
+def test_tf32_backward_gemms_on_shared_activations(R, SR, semantic):
+    """The tcgen05 kind::tf32 dgrad / wgrad kernels against the fp32 SIMT ones on the SAME saved activations (TF32 forward, then
+    the backward once per arithmetic): only the rounding of the backward GEMM operands differs (the tensor core truncates fp32 operands to TF32, a bias of up to 2^-10
+    per operand that compounds over the six dgrad layers: observed <= 5e-3).  Relative L2 <= 1e-2 per tensor."""
+    d0, v0, g_tf = _tf32_case(R, SR, semantic, ops.PRECISION_TF32)
+    d1, v1, g_fp = _tf32_case(R, SR, semantic, ops.PRECISION_TF32, bwd_override=ops.PRECISION_FP32)
+    assert torch.equal(d0, d1) and torch.equal(v0, v1)          # the forward is deterministic: both backwards saw the same workspace
+    for k in g_fp:
+        assert rel_l2(g_tf[k], g_fp[k]) < 1e-2, (k, rel_l2(g_tf[k], g_fp[k]))
+
+
+@pytest.mark.parametrize("R,SR,semantic", TF32_SHAPES)
+def test_tf32_training_path_vs_fp32(R, SR, semantic):
+    """SGN_PRECISION_TF32 (tcgen05 kind::tf32 GEMMs, fp32 storage and accumulation -- the arithmetic of the reference's cuBLAS default
+    at its pinned torch 1.10) against the fp32 SIMT path end to end.  Stated TF32 tolerance: |d decoded| <= 1e-2 * max(1, |decoded|).
+    End-to-end gradients differ by more than operand rounding: a pre-activation within ~1e-3 of zero changes sign between the two
+    arithmetics and LeakyReLU(0.01) then scales that element's gradient by 1 instead of 0.01 (about 0.3 % of the elements, i.e.
+    ~5 % relative L2 -- a CPU emulation that truncates the operands of every torch Linear to TF32 shows the same figures), so the
+    end-to-end bound is direction + scale: cosine >= 0.99 and relative L2 <= 0.12; the GEMMs themselves are held to 1e-2 above."""
+    dec_a, valid_a, g_a = _tf32_case(R, SR, semantic, ops.PRECISION_FP32)
+    dec_b, valid_b, g_b = _tf32_case(R, SR, semantic, ops.PRECISION_TF32)
+    assert torch.equal(valid_a, valid_b)
+    assert bool(((dec_a - dec_b).abs() <= 1e-2 * dec_a.abs().clamp(min=1.0)).all()), float((dec_a - dec_b).abs().max())
+    for k in g_a:
+        a, b = g_a[k].double().flatten(), g_b[k].double().flatten()
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.99 and rel_l2(g_b[k], g_a[k]) < 0.12, (k, cos, rel_l2(g_b[k], g_a[k]))
