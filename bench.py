@@ -237,6 +237,7 @@ def run_ours(args):
         e2e_ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
 
+    train = None if args.no_train_step else train_step_leg(s, scene, device, rank, world, dist, bg)
     tmax = torch.tensor([ms_total, e2e_ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -262,7 +263,7 @@ def run_ours(args):
                    "parallelism": f"ray-sharded x{world}, point cloud replicated, no collective on the render path",
                    "semantic_variant": None if sem_ms is None else {"what": "same frame with block2_bpnet + 96-d label embedding (rank 0)", "ms_per_step": sem_ms,
                                                                     "rays_per_s_per_gpu": R / (sem_ms * 1e-3)}},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "train_step": train,
         "e2e": {"value": world * R / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(R * 12 + 48),
                 "d2h_bytes_per_step": int(R * 12)},
         "roofline": {"bound": "tensor", "kernel": rl_kernel, "achieved": achieved,
@@ -280,6 +281,60 @@ def run_ours(args):
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
+    """Config C2 beside the headline (BASELINE.json's metric names both): one training step = 56x56 random pixels per GPU with jittered
+    samples -> query -> aggregation forward + backward (TF32 tensor-core GEMMs, scatter-add into the point tables) -> compositing,
+    masked MSE + zero-one(conf) -> gradient all-reduce over ranks (one flat bucket, NCCL) -> Adam; no host synchronisation, the whole
+    step replayed as one CUDA graph (sgnerf_b200/train.py).  ms = device time per step, max over ranks."""
+    from sgnerf_b200 import ops, pipeline, train
+    info = {"what": f"C2: {patch}x{patch} rays per GPU, fwd + bwd + all-reduce + Adam", "rays_per_step_per_gpu": patch * patch, "dtype": "tf32"}
+    try:
+        sc = pipeline.RenderScene(scene.xyz, scene.embedding.clone(), scene.color.clone(), scene.dirs.clone(), scene.conf.clone(),
+                                  [w.clone() for w in scene.weights], [b.clone() for b in scene.biases], scene.agg_cfg, scene.qopt, device=device)
+        sc._grid, sc._hp = scene._grid, scene._hp                        # same cloud: share the occupancy grid
+        n = patch * patch
+        all_rays = torch.from_numpy(s.raydir).to(device)
+        campos, rot = torch.from_numpy(s.campos).to(device), torch.from_numpy(s.camrotc2w).to(device)
+        gen = torch.Generator(device=device).manual_seed(100 + rank)
+        ms = None
+        for mode in ("cuda graph", "eager"):
+            try:
+                ts = train.TrainStep(sc, n, s.near, s.far, bg, precision=ops.PRECISION_TF32, use_graph=mode == "cuda graph")
+
+                def one():
+                    pix = torch.randint(0, all_rays.shape[0], (n,), device=device, generator=gen)
+                    ts.set_inputs(campos, rot, all_rays[pix], torch.rand(n, 3, device=device, generator=gen), ts.jittered_t(0.3, gen))
+                    ts.step()
+                for _ in range(3):
+                    one()
+                torch.cuda.synchronize()
+                if dist is not None:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                info.update(mode=mode, loss=float(ts.loss), rays_hit_last_step=float(ts.n_hit),
+                            allreduce_bytes_per_step=(sum(p.numel() for p in ts.params) * 4 if world > 1 else 0))
+                break
+            except Exception as e:                                       # e.g. a collective that cannot be captured: launch kernel by kernel
+                info["graph_error"] = repr(e)[:200]
+        sc._grid = None
+        if ms is None:
+            return info
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        info.update(ms=ms, rays_per_s=world * n / (ms * 1e-3), steps=steps)
+    except Exception as e:
+        info["error"] = repr(e)[:300]
+    return info
 
 
 def cpu_reference_step(s, P, cfg, tabs, sel, opt, threads):
@@ -367,6 +422,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2304)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-semantic-variant", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
