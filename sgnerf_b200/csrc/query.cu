@@ -51,6 +51,12 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
     const float* tr = t_per_ray ? t + r * D : t;
     const int label = ray_label ? ray_label[r] : 0;
     const float rvx = 1.0f / g.vx, rvy = 1.0f / g.vy, rvz = 1.0f / g.vz;
+    // conservative box of the grid (one voxel of margin on every side): a position outside it cannot land in a voxel of the grid
+    // whatever the rounding of the exact coordinate computation, so the lane skips that computation
+    const float bx0 = g.ox - g.vx, bx1 = g.ox + (float)(g.dx + 1) * g.vx;
+    const float by0 = g.oy - g.vy, by1 = g.oy + (float)(g.dy + 1) * g.vy;
+    const float bz0 = g.oz - g.vz, bz1 = g.oz + (float)(g.dz + 1) * g.vz;
+    const bool idx32 = (int64_t)g.dx * g.dy * g.dz < (1ll << 31);
     int cnt = 0;
     for (int base = 0; base < D && cnt < SR; base += 32) {
         const int d = base + lane;
@@ -62,10 +68,17 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
             px = __fadd_rn(cx, __fmul_rn(dx, tv));
             py = __fadd_rn(cy, __fmul_rn(dy, tv));
             pz = __fadd_rn(cz, __fmul_rn(dz, tv));
-            const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
-            if (vx >= 0 && vx < g.dx && vy >= 0 && vy < g.dy && vz >= 0 && vz < g.dz) {
-                const int64_t c = ((int64_t)vx * g.dy + vy) * g.dz + vz;
-                occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
+            if (px > bx0 && px < bx1 && py > by0 && py < by1 && pz > bz0 && pz < bz1) {
+                const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
+                if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
+                    if (idx32) {
+                        const uint32_t c = ((uint32_t)vx * (uint32_t)g.dy + (uint32_t)vy) * (uint32_t)g.dz + (uint32_t)vz;
+                        occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
+                    } else {
+                        const int64_t c = ((int64_t)vx * g.dy + vy) * g.dz + vz;
+                        occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
+                    }
+                }
             }
         }
         const unsigned b = __ballot_sync(0xffffffffu, occ);
@@ -89,15 +102,45 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
 }
 
 constexpr int KNN_SLOTS = 1536;   // sample slots per block (64 rays at SR = 24): their occupied samples are compacted in shared memory so that all lanes work
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_MAX_CELLS = 27;  // cell-list entries per thread kept in shared memory (a 3^3 block; larger kernels take the nested-loop path)
 
+// One candidate against the K slots, exactly the reference's rule (:650-676): fill the first K slots in order, then replace the
+// farthest one when the new candidate is strictly nearer and rescan for the new farthest (first index wins ties).
+template <int KT>
+__device__ __forceinline__ void knn_insert(int pidx, float d2, int K, int& kid, int& far_ind, float& far2, int32_t (&out)[KT], float (&buf)[KT])
+{
+    if (kid++ < K) {
+#pragma unroll
+        for (int i = 0; i < KT; i++)
+            if (i == kid - 1) { out[i] = pidx; buf[i] = d2; }
+        if (d2 > far2) { far2 = d2; far_ind = kid - 1; }
+    } else if (d2 < far2) {
+#pragma unroll
+        for (int i = 0; i < KT; i++)
+            if (i == far_ind) { out[i] = pidx; buf[i] = d2; }
+        far2 = d2;
+#pragma unroll
+        for (int i = 0; i < KT; i++)
+            if (i < K && buf[i] > far2) { far2 = buf[i]; far_ind = i; }
+    }
+}
+
+// knn_kernel, two phases per sample so that the lanes of a warp (32 different samples) stay in step:
+//   1. walk the voxels of the block in the reference's order (shell by shell, x outer / z inner) and append the occupied ones --
+//      (first candidate, end, "opens a new shell") -- to a per-thread list in shared memory: a uniform 27-iteration loop;
+//   2. one flat loop over the candidates of that list, one candidate per lane per iteration: a warp runs max-over-lanes of the
+//      candidate counts instead of the sum over voxels of the per-voxel maxima the nested loops cost.
+// The visiting order and the insertion rule are unchanged, so the K slots come out as in the sequential reference.
 template <int KT, bool SEMANTIC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KNN_THREADS, KT == 8 ? 8 : 3)
 knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, const float* __restrict__ sample_loc_w,
            const int32_t* __restrict__ sample_mask, const int32_t* __restrict__ sample_label, const int32_t* __restrict__ pt_label,
            const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
-           int8_t* __restrict__ ray_mask, int rays_per_block)
+           int8_t* __restrict__ ray_mask, int rays_per_block, int flat_ok)
 {
     extern __shared__ int32_t s_list[];                       // [rays_per_block * SR] sample indices (relative to the block's first slot)
+    __shared__ uint32_t s_cells[KNN_MAX_CELLS][KNN_THREADS];  // per-thread list of occupied voxels: begin (24 bits) | count (7 bits) << 24 | new-shell flag (bit 31)
     __shared__ int s_count;
     const int64_t slot0 = (int64_t)blockIdx.x * rays_per_block * SR;
     const int nslot = (int)min((int64_t)rays_per_block * SR, R * SR - slot0);
@@ -118,79 +161,120 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
     }
     __syncthreads();
     const int nq = s_count;
+    const bool flat = nlayer <= 2 && flat_ok;                 // 3^3 block, candidate indices < 2^24, at most 127 candidates per voxel: the list fits
     for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
-    const int64_t idx = slot0 + s_list[qi];
-    const int64_t r = idx / SR;
-    int32_t out[KT];
-    float buf[KT];
+        const int64_t idx = slot0 + s_list[qi];
+        const int64_t r = idx / SR;
+        int32_t out[KT];
+        float buf[KT];
 #pragma unroll
-    for (int i = 0; i < KT; i++) out[i] = -1;
-    int kid = 0;
-    if (__ldg(sample_mask + idx) > 0) {
+        for (int i = 0; i < KT; i++) { out[i] = -1; buf[i] = 0.f; }
+        int kid = 0;
         const float cx = sample_loc_w[3 * idx], cy = sample_loc_w[3 * idx + 1], cz = sample_loc_w[3 * idx + 2];
         const int fx = vox_coord(cx, g.ox, g.vx), fy = vox_coord(cy, g.oy, g.vy), fz = vox_coord(cz, g.oz, g.vz);
         const int center_label = SEMANTIC ? sample_label[idx] : 0;
         int far_ind = 0;
         float far2 = 0.0f;
-        for (int layer = 0; layer < nlayer; layer++) {
-            const int xlo = max(-fx, -layer), xhi = min(g.dx - fx, layer + 1);
-            const int ylo = max(-fy, -layer), yhi = min(g.dy - fy, layer + 1);
-            const int zlo = max(-fz, -layer), zhi = min(g.dz - fz, layer + 1);
-            for (int x = xlo; x < xhi; x++) {
-                for (int y = ylo; y < yhi; y++) {
-                    const int64_t rowbase = ((int64_t)(fx + x) * g.dy + (fy + y)) * g.dz + fz;
-                    const bool inner = max(abs(x), abs(y)) != layer;  // only |z| == layer qualifies on this row
-                    for (int z = zlo; z < zhi; z++) {
-                        if (inner && abs(z) != layer) continue;
-                        const int occ = __ldg(g.cell_slot + rowbase + z);
-                        if (occ < 0) continue;
-                        const int b = __ldg(g.slot_start + occ), e = __ldg(g.slot_start + occ + 1);
-                        for (int q = b; q < e; q++) {
-                            const float4 c = __ldg(g.cand + q);
-                            const int pidx = __float_as_int(c.w);
-                            if (SEMANTIC) {
-                                const int label_v = pt_label[pidx];
-                                const int label_prob = (int)(__int_as_float(pt_label_prob_bits[(int64_t)pidx * 20 + label_v]) * 10.0f);
-                                const bool ok = (center_label == label_v) || (label_v == 0) || (center_label == 0) ||
-                                                ((center_label != label_v) && ((seconds % 10) <= (uint64_t)(int64_t)(1 - label_prob)));
-                                if (!ok) continue;
-                            }
-                            const float xv = __fsub_rn(c.x, cx), yv = __fsub_rn(c.y, cy), zv = __fsub_rn(c.z, cz);
-                            // nvcc contracts the reference's x*x + y*y + z*z to fma(z,z, fma(x,x, y*y))
-                            const float d2 = __fmaf_rn(zv, zv, __fmaf_rn(xv, xv, __fmul_rn(yv, yv)));
-                            if (radius2 == 0.0f || d2 <= radius2) {
-                                if (kid++ < K) {
+        auto candidate = [&](const float4 c) {
+            const int pidx = __float_as_int(c.w);
+            if (SEMANTIC) {
+                const int label_v = pt_label[pidx];
+                const int label_prob = (int)(__int_as_float(pt_label_prob_bits[(int64_t)pidx * 20 + label_v]) * 10.0f);
+                const bool ok = (center_label == label_v) || (label_v == 0) || (center_label == 0) ||
+                                ((center_label != label_v) && ((seconds % 10) <= (uint64_t)(int64_t)(1 - label_prob)));
+                if (!ok) return;
+            }
+            const float xv = __fsub_rn(c.x, cx), yv = __fsub_rn(c.y, cy), zv = __fsub_rn(c.z, cz);
+            // nvcc contracts the reference's x*x + y*y + z*z to fma(z,z, fma(x,x, y*y))
+            const float d2 = __fmaf_rn(zv, zv, __fmaf_rn(xv, xv, __fmul_rn(yv, yv)));
+            if (radius2 == 0.0f || d2 <= radius2) knn_insert<KT>(pidx, d2, K, kid, far_ind, far2, out, buf);
+        };
+        if (flat) {
+            // ---- phase 1: the voxels of the 3^3 block in visiting order -- centre (shell 0), then x outer / y / z inner without the
+            // centre (shell 1; nlayer == 1 stops after the centre).  All voxel reads are issued before any is used, then the
+            // candidate ranges of the occupied ones nine at a time: two or three memory latencies instead of one per voxel.
+            int occ[27];
 #pragma unroll
-                                    for (int i = 0; i < KT; i++)
-                                        if (i == kid - 1) { out[i] = pidx; buf[i] = d2; }
-                                    if (d2 > far2) { far2 = d2; far_ind = kid - 1; }
-                                } else if (d2 < far2) {
+            for (int i = 0; i < 27; i++) {
+                const int l = i == 0 ? 13 : (i - 1 < 13 ? i - 1 : i);
+                const int x = l / 9 - 1, y = (l / 3) % 3 - 1, z = l % 3 - 1;
+                const bool in = (i == 0 || nlayer > 1) && (unsigned)(fx + x) < (unsigned)g.dx && (unsigned)(fy + y) < (unsigned)g.dy &&
+                                (unsigned)(fz + z) < (unsigned)g.dz;
+                occ[i] = in ? __ldg(g.cell_slot + ((int64_t)(fx + x) * g.dy + (fy + y)) * g.dz + (fz + z)) : -1;
+            }
+            int nc = 0;
+            unsigned shell1 = 0x80000000u;
 #pragma unroll
-                                    for (int i = 0; i < KT; i++)
-                                        if (i == far_ind) { out[i] = pidx; buf[i] = d2; }
-                                    far2 = d2;
+            for (int grp = 0; grp < 3; grp++) {
+                int b[9], e[9];
 #pragma unroll
-                                    for (int i = 0; i < KT; i++)
-                                        if (i < K && buf[i] > far2) { far2 = buf[i]; far_ind = i; }
-                                }
-                            }
-                        }
+                for (int j = 0; j < 9; j++) {
+                    const int o = occ[9 * grp + j];
+                    b[j] = o >= 0 ? __ldg(g.slot_start + o) : 0;
+                    e[j] = o >= 0 ? __ldg(g.slot_start + o + 1) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    if (e[j] > b[j]) {
+                        unsigned flag = 0u;
+                        if (9 * grp + j > 0) { flag = shell1; shell1 = 0u; }
+                        s_cells[nc++][threadIdx.x] = (uint32_t)b[j] | ((uint32_t)(e[j] - b[j]) << 24) | flag;
                     }
                 }
             }
-            if (kid >= K) break;
+            // ---- phase 2: the candidates of the list, one per iteration; the next candidate's record is requested before the
+            // current one is processed (its address never depends on the outcome, only whether it is used does)
+            int ci = 0, q = 0, e = 0;
+            bool live = nc > 0;
+            float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) { const uint32_t c0 = s_cells[0][threadIdx.x]; q = (int)(c0 & 0xffffffu); e = q + (int)((c0 >> 24) & 127u); cur = __ldg(g.cand + q); }
+            while (live) {
+                bool nxt_live = true, nxt_shell = false;
+                if (++q == e) {
+                    if (++ci == nc) nxt_live = false;
+                    else {
+                        const uint32_t cn = s_cells[ci][threadIdx.x];
+                        nxt_shell = (cn >> 31) != 0u;
+                        q = (int)(cn & 0xffffffu); e = q + (int)((cn >> 24) & 127u);
+                    }
+                }
+                float4 nxt = cur;
+                if (nxt_live) nxt = __ldg(g.cand + q);
+                candidate(cur);
+                if (nxt_shell && kid >= K) nxt_live = false;          // a new shell starts: the reference stops once K were found (:678)
+                cur = nxt; live = nxt_live;
+            }
+        } else {
+            for (int layer = 0; layer < nlayer; layer++) {
+                const int xlo = max(-fx, -layer), xhi = min(g.dx - fx, layer + 1);
+                const int ylo = max(-fy, -layer), yhi = min(g.dy - fy, layer + 1);
+                const int zlo = max(-fz, -layer), zhi = min(g.dz - fz, layer + 1);
+                for (int x = xlo; x < xhi; x++) {
+                    for (int y = ylo; y < yhi; y++) {
+                        const int64_t rowbase = ((int64_t)(fx + x) * g.dy + (fy + y)) * g.dz + fz;
+                        const bool inner = max(abs(x), abs(y)) != layer;
+                        for (int z = zlo; z < zhi; z++) {
+                            if (inner && abs(z) != layer) continue;
+                            const int occ = __ldg(g.cell_slot + rowbase + z);
+                            if (occ < 0) continue;
+                            const int b = __ldg(g.slot_start + occ), e = __ldg(g.slot_start + occ + 1);
+                            for (int q = b; q < e; q++) candidate(__ldg(g.cand + q));
+                        }
+                    }
+                }
+                if (kid >= K) break;
+            }
         }
-    }
-    int32_t* o = sample_pidx + idx * K;
-    if (KT == 8 && K == 8) {
-        ((int4*)o)[0] = make_int4(out[0], out[1], out[2], out[3]);
-        ((int4*)o)[1] = make_int4(out[4], out[5], out[6], out[7]);
-    } else {
+        int32_t* o = sample_pidx + idx * K;
+        if (KT == 8 && K == 8) {
+            ((int4*)o)[0] = make_int4(out[0], out[1], out[2], out[3]);
+            ((int4*)o)[1] = make_int4(out[4], out[5], out[6], out[7]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < KT; i++)
-            if (i < K) o[i] = out[i];
-    }
-    if (kid > 0) ray_mask[r] = 1;  // every writer stores the same value
+            for (int i = 0; i < KT; i++)
+                if (i < K) o[i] = out[i];
+        }
+        if (kid > 0) ray_mask[r] = 1;  // every writer stores the same value
     }
 }
 
@@ -226,21 +310,22 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     const int rpb_fill = (int)(R / (148 * 8)), rpb_min = cdiv(128, SR);
     if (rpb > rpb_fill) rpb = rpb_fill > rpb_min ? rpb_fill : (rpb_min < rpb ? rpb_min : rpb);
     const int nb = cdiv(R, rpb);
+    const int flat_ok = (G->N < (1ll << 24) && G->cfg.P < 128) ? 1 : 0;
     const size_t ksm = (size_t)rpb * SR * sizeof(int32_t);
     if (K == 8) {
         if (semantic)
-            launch(knn_kernel<8, true>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
-                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb);
+            launch(knn_kernel<8, true>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
         else
-            launch(knn_kernel<8, false>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
-                                                      seconds_query, sample_pidx, ray_mask, rpb);
+            launch(knn_kernel<8, false>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
+                                                      seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
     } else {
         if (semantic)
-            launch(knn_kernel<SGN_MAX_K, true>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
-                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb);
+            launch(knn_kernel<SGN_MAX_K, true>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
+                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
         else
-            launch(knn_kernel<SGN_MAX_K, false>, nb, 128, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
-                                                              nullptr, seconds_query, sample_pidx, ray_mask, rpb);
+            launch(knn_kernel<SGN_MAX_K, false>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
+                                                              nullptr, seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
     }
     SGN_LAUNCH_CHECK();
     return SGN_OK;
