@@ -230,6 +230,14 @@ int sgn_composite_backward(const float* decoded, const float* ray_dist, const ui
 int sgn_fill_invalid(const int8_t* ray_mask, const float* bg /*[3]*/, int64_t R, int SR, float* ray_color /*[R,3]*/,
                      float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/, void* stream);
 
+/* Inference frame tail in one kernel: sgn_ray_dist -> sgn_composite_forward -> sgn_fill_invalid with the same results
+ * (neural_points_volumetric_model.py:569-577, diff_ray_marching.py:509-555, neural_points_volumetric_model.py:158-195) and none
+ * of the intermediate tensors.  ray_mask may be NULL (no fill); ray_color / opacity / bg_transmission may be NULL. */
+int sgn_render_composite(const float* decoded /*[R,SR,4]*/, const float* loc_pers /*[R,SR,3]*/, const uint8_t* ray_valid /*[R,SR]*/,
+                         const int8_t* ray_mask /*[R]*/, float vsize_z, int raydist_mode_unit, const float* bg /*[3]*/, int blend,
+                         int64_t R, int SR, float* ray_color /*[R,3]*/, float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -204,6 +204,75 @@ ray_dist_kernel(const float* __restrict__ loc_pers, const uint8_t* __restrict__ 
     }
 }
 
+// Inference frame tail in one pass: step sizes (ray_dist_kernel) -> compositing (composite_fwd_kernel) -> fill_invalid, per ray,
+// nothing but the outputs written: reads SR*(16 + 12 + 1) + 1 B, writes SR*4 (opacity) + 16 B per ray.  Rays that missed the cloud
+// (ray_mask <= 0) get the background without reading their samples -- the same values the three separate kernels produce.
+template <int BLEND>
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+render_composite_kernel(const float4* __restrict__ decoded, const float* __restrict__ loc_pers, const uint8_t* __restrict__ valid,
+                        const int8_t* __restrict__ ray_mask, float vsize_z, int mode_unit, const float* __restrict__ bg, int64_t R, int SR,
+                        float* __restrict__ ray_color, float* __restrict__ opacity, float* __restrict__ bg_t)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * COMP_WARPS;
+    const float b0 = bg ? bg[0] : 0.f, b1 = bg ? bg[1] : 0.f, b2 = bg ? bg[2] : 0.f;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        if (ray_mask && ray_mask[r] <= 0) {
+            if (opacity)
+                for (int s = lane; s < SR; s += 32) opacity[r * SR + s] = 0.f;
+            if (lane == 0) {
+                if (ray_color) { ray_color[r * 3] = b0; ray_color[r * 3 + 1] = b1; ray_color[r * 3 + 2] = b2; }
+                if (bg_t) bg_t[r] = 1.0f;
+            }
+            continue;
+        }
+        float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, zcarry = -INFINITY;
+        for (int base = 0; base < SR; base += 32) {
+            const int s = base + lane;
+            const bool act = s < SR;
+            const int64_t i = r * SR + s;
+            const float4 f = act ? __ldg(decoded + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float v = (act && __ldg(valid + i)) ? 1.0f : 0.0f;
+            // step size: running maximum of the camera depth, difference to the next sample, voxel size where degenerate
+            const float z = act ? __ldg(loc_pers + i * 3 + 2) : -INFINITY;
+            const float cm = fmaxf(zcarry, warp_incl_max(z));
+            float zn = __shfl_down_sync(0xffffffffu, z, 1);
+            if (lane == 31 && s + 1 < SR) zn = __ldg(loc_pers + (i + 1) * 3 + 2);
+            float d = (s + 1 < SR) ? fmaxf(cm, zn) - cm : vsize_z;
+            bool bad = d < 1e-8f;
+            if (mode_unit > 0) bad = bad || (d > 2.0f * vsize_z);
+            const float m = bad ? 1.0f : 0.0f;
+            d = d * (1.0f - m) + m * vsize_z;
+            const float dist = act ? d * v : 0.f;
+            zcarry = __shfl_sync(0xffffffffu, cm, 31);
+            // compositing
+            const float sigma = f.x * v;
+            const float o = 1.0f - expf(-sigma * dist);
+            const float x = act ? (1.0f - o) + 1e-10f : 1.0f;
+            const float incl = warp_incl_prod(x);
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.0f;
+            const float T = carry * excl;
+            const float w = BLEND == 0 ? o * T : o * T * T;
+            if (act) {
+                if (opacity) opacity[i] = o;
+                cr += f.y * w; cg += f.z * w; cb += f.w * w;
+            }
+            carry *= __shfl_sync(0xffffffffu, incl, 31);
+        }
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+        if (lane == 0) {
+            if (ray_color) {
+                ray_color[r * 3 + 0] = cr + b0 * carry;
+                ray_color[r * 3 + 1] = cg + b1 * carry;
+                ray_color[r * 3 + 2] = cb + b2 * carry;
+            }
+            if (bg_t) bg_t[r] = carry;
+        }
+    }
+}
+
 __global__ void fill_invalid_kernel(const int8_t* __restrict__ ray_mask, const float* __restrict__ bg, int64_t R, int SR,
                                     float* ray_color, float* opacity, float* bg_t)
 {
@@ -268,6 +337,25 @@ extern "C" int sgn_composite_backward(const float* decoded, const float* ray_dis
     else
         launch(composite_bwd_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, ray_dist, valid, bg, R, SR, d_ray_color,
                                                                          d_opacity, d_blend_weight, d_bg_transmission, (float4*)d_decoded);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_render_composite(const float* decoded, const float* loc_pers, const uint8_t* ray_valid, const int8_t* ray_mask, float vsize_z,
+                                    int raydist_mode_unit, const float* bg, int blend, int64_t R, int SR, float* ray_color, float* opacity,
+                                    float* bg_transmission, void* stream)
+{
+    SGN_CHECK_ARG(R >= 0 && SR > 0 && SR <= 32 * COMP_MAX_CHUNKS, "sgn_render_composite: SR=%d out of range", SR);
+    SGN_CHECK_ARG(blend == 0 || blend == 1, "sgn_render_composite: blend must be 0 (alpha) or 1 (alpha2)");
+    SGN_CHECK_ARG(decoded && loc_pers && ray_valid, "sgn_render_composite: NULL input");
+    if (R == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    if (blend == 0)
+        launch(render_composite_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
+                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission);
+    else
+        launch(render_composite_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
+                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

@@ -212,6 +212,23 @@ def composite(decoded, ray_dist_, ray_valid, bg_color=None, blend=0):
     return _Composite.apply(decoded, ray_dist_, valid, bg, int(blend))
 
 
+def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, blend=0, raydist_mode_unit=1):
+    """Inference tail of a frame in one kernel (no autograd): ray_dist -> composite -> fill_invalid.
+    Returns ray_color [R,3], opacity [R,SR], bg_transmission [R] -- the values the three separate calls give."""
+    decoded = _dev(decoded.detach(), torch.float32, "decoded")
+    loc_pers = _dev(loc_pers, torch.float32, "loc_pers")
+    valid = _dev(ray_valid, torch.uint8, "ray_valid")
+    R, SR = decoded.shape[-3], decoded.shape[-2]
+    dev = decoded.device
+    ray_color = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    opacity = torch.empty(R, SR, dtype=torch.float32, device=dev)
+    bgt = torch.empty(R, dtype=torch.float32, device=dev)
+    _lib.call("sgn_render_composite", _ptr(decoded), _ptr(loc_pers), _ptr(valid), _ptr(_dev(ray_mask, torch.int8, "ray_mask")), float(vsize_z),
+              int(raydist_mode_unit), _ptr(_dev(bg_color.reshape(3), torch.float32, "bg")), int(blend), R, SR, _ptr(ray_color), _ptr(opacity),
+              _ptr(bgt), _stream())
+    return ray_color, opacity, bgt
+
+
 def fill_invalid(ray_mask, bg_color, ray_color, opacity=None, bg_transmission=None):
     """In-place fill_invalid for uncompacted rows (models/neural_points_volumetric_model.py:158-195)."""
     R = ray_mask.numel()

@@ -96,6 +96,10 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
         scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf,
         scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux,
         point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None)
+    if not want_aux and not decoded.requires_grad:
+        # inference: step sizes, compositing and fill_invalid in one kernel, no intermediate tensors
+        ray_color, opacity, bgt = ops.render_composite(decoded, loc_pers, ray_valid, rmask, hp.vsize[2], bg_color, blend=0)
+        return SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt)
     rd = ops.ray_dist(loc_pers, ray_valid, hp.vsize[2], 1)
     ray_color, opacity, acc, bw, bgt = ops.composite(decoded, rd, ray_valid, bg_color, blend=0)
     ops.fill_invalid(rmask, bg_color, ray_color, opacity, bgt)

@@ -109,3 +109,27 @@ def test_full_size_properties():
     torch.testing.assert_close(bw.sum(-1) + bgt, torch.ones(R, device="cuda"), rtol=0, atol=1e-5)
     assert float(color.min()) >= 0 and float(color.max()) <= 1 + 1e-5
     assert bool((opacity[~valid] == 0).all())
+
+
+@pytest.mark.parametrize("R,SR", [(1, 1), (57, 24), (40, 33), (9, 200), (640 * 480, 24)])
+@pytest.mark.parametrize("blend", [0, 1])
+def test_fused_frame_tail_equals_three_kernels(R, SR, blend):
+    """sgn_render_composite (ray_dist + composite + fill_invalid in one pass) must give exactly what the three kernels give."""
+    g = torch.Generator(device="cuda").manual_seed(4)
+    dec = torch.rand(R, SR, 4, device="cuda", generator=g)
+    dec[..., 0] *= 80.0
+    loc = torch.rand(R, SR, 3, device="cuda", generator=g)
+    loc[..., 2] = torch.cumsum(torch.rand(R, SR, device="cuda", generator=g) * 0.02, dim=-1)
+    if R > 8:
+        loc[3, SR // 3:, 2] = 0.0                # unused slots at the origin -> non-monotone depth
+        loc[4, SR // 2, 2] = loc[4, SR // 2 - 1, 2]
+    valid = torch.rand(R, SR, device="cuda", generator=g) < 0.5
+    mask = valid.any(-1).to(torch.int8)
+    if R > 8:
+        mask[5] = 0                              # a missed ray whose rows hold junk must still come out as background
+    bg = torch.tensor([1.0, 0.5, 0.25], device="cuda")
+    rd = ops.ray_dist(loc, valid, 0.008, 1)
+    color, opacity, _, _, bgt = ops.composite(dec, rd, valid, bg, blend=blend)
+    ops.fill_invalid(mask, bg, color, opacity, bgt)
+    f_color, f_opacity, f_bgt = ops.render_composite(dec, loc, valid, mask, 0.008, bg, blend=blend)
+    assert torch.equal(f_color, color) and torch.equal(f_opacity, opacity) and torch.equal(f_bgt, bgt)
