@@ -25,6 +25,42 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
         loc_pers[3 * s] = c0 / c2; loc_pers[3 * s + 1] = c1 / c2; loc_pers[3 * s + 2] = c2;
     }
     const int32_t* pi = in.pidx + s * K;
+    if (K == 8 && (((uintptr_t)in.pidx | (uintptr_t)wc | (uintptr_t)weight_n | (uintptr_t)weight_out | (uintptr_t)conf_out) & 15) == 0) {
+        // canonical K: the eight indices as two 16-byte loads, every output row as two 16-byte stores
+        const int4 pa = __ldg((const int4*)pi), pb = __ldg((const int4*)pi + 1);
+        const int p8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        float w8[8], cf8[8];
+        float sum = 0.f;
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int p = p8[k];
+            float wk = 0.f;
+            if (p >= 0) {
+                const float dx = in.tab.xyz[3 * (int64_t)p] - lx, dy = in.tab.xyz[3 * (int64_t)p + 1] - ly, dz = in.tab.xyz[3 * (int64_t)p + 2] - lz;
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+                wk = 1.0f / fmaxf(nrm, 1e-6f);
+                n++;
+            }
+            w8[k] = wk;
+            sum += wk;
+            const int pc = p < 0 ? 0 : p;                  // the reference gathers with clamp(pidx, 0) (neural_points.py:958)
+            cf8[k] = in.tab.conf ? fminf(fmaxf(__ldg(in.tab.conf + pc), 0.0001f), 1.0f) : 1.0f;
+        }
+        const float den = fmaxf(sum, 1e-8f);
+#pragma unroll
+        for (int k = 0; k < 8; k++) w8[k] = w8[k] / den;
+        float4* o = (float4*)(wc + s * 8);
+        o[0] = make_float4(w8[0] * cf8[0], w8[1] * cf8[1], w8[2] * cf8[2], w8[3] * cf8[3]);
+        o[1] = make_float4(w8[4] * cf8[4], w8[5] * cf8[5], w8[6] * cf8[6], w8[7] * cf8[7]);
+        if (weight_n) { o = (float4*)(weight_n + s * 8); o[0] = make_float4(w8[0], w8[1], w8[2], w8[3]); o[1] = make_float4(w8[4], w8[5], w8[6], w8[7]); }
+        if (weight_out) { o = (float4*)(weight_out + s * 8); o[0] = make_float4(w8[0], w8[1], w8[2], w8[3]); o[1] = make_float4(w8[4], w8[5], w8[6], w8[7]); }
+        if (conf_out) { o = (float4*)(conf_out + s * 8); o[0] = make_float4(cf8[0], cf8[1], cf8[2], cf8[3]); o[1] = make_float4(cf8[4], cf8[5], cf8[6], cf8[7]); }
+        ray_valid[s] = n > 0;
+        nvalid[s] = n;
+        svalid[s] = n > 0;
+        return;
+    }
     float w[SGN_MAX_K];
     float sum = 0.f;
     int n = 0;

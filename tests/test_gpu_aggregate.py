@@ -268,8 +268,10 @@ def test_bf16_point_cache(semantic):
     assert torch.equal(c[0], b[0]) and not torch.equal(d[0], b[0])
 
 
-def _tf32_case(R, SR, semantic, prec, bwd_override=None):
+def _tf32_case(R, SR, semantic, prec, bwd_override=None, width=256):
     cfg = rr.semantic_config() if semantic else rr.agg_config()
+    if width != 256:
+        cfg = rr.agg_config(shading_feature_num=width)
     N, K = 5000, 8
     tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=21 + semantic, prefix_mask=True)
     P = rr.init_params(cfg, seed=4, bias_scale=0.1)
@@ -304,6 +306,18 @@ def test_tf32_backward_gemms_on_shared_activations(R, SR, semantic):
     assert torch.equal(d0, d1) and torch.equal(v0, v1)          # the forward is deterministic: both backwards saw the same workspace
     for k in g_fp:
         assert rel_l2(g_tf[k], g_fp[k]) < 1e-2, (k, rel_l2(g_tf[k], g_fp[k]))
+
+
+@pytest.mark.parametrize("width", [64, 128])
+def test_tf32_backward_gemms_narrow_layers(width):
+    """Same check at shading_feature_num 64 / 128 (colour width 32 / 64): partial MMA tiles, one accumulator half in the wgrad."""
+    d0, v0, g_tf = _tf32_case(300, 24, False, ops.PRECISION_TF32, width=width)
+    d1, v1, g_fp = _tf32_case(300, 24, False, ops.PRECISION_TF32, bwd_override=ops.PRECISION_FP32, width=width)
+    assert torch.equal(d0, d1)
+    for k in g_fp:
+        assert rel_l2(g_tf[k], g_fp[k]) < 1e-2, (k, rel_l2(g_tf[k], g_fp[k]))
+    d2, _, _ = _tf32_case(300, 24, False, ops.PRECISION_FP32, width=width)
+    assert bool(((d0 - d2).abs() <= 1e-2 * d2.abs().clamp(min=1.0)).all())
 
 
 @pytest.mark.parametrize("R,SR,semantic", TF32_SHAPES)
