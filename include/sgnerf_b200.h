@@ -238,6 +238,17 @@ int sgn_render_composite(const float* decoded /*[R,SR,4]*/, const float* loc_per
                          int64_t R, int SR, float* ray_color /*[R,3]*/, float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/,
                          void* stream);
 
+/* `prob == 1` outputs of NeuralPointsRayMarching.forward (neural_points_volumetric_model.py:633-656), the inputs of probe_hole / point
+ * growing (run/train_ft.py:425-540): per ray the first sample of largest opacity, its world position, the distance to its nearest
+ * gathered neighbour (all K slots; invalid ones hold point 0 as clamp(pidx, 0) gathers it) and the weight * conf_coefficient sums of
+ * its neighbours' colour / dir / conf / embedding.  Rows are per input ray (uncompacted); rays with ray_mask <= 0 get zeros
+ * (ray_mask may be NULL).  Outputs [R], [R,3], [R], [R,3], [R,3], [R], [R,feat_dim]; any may be NULL. */
+int sgn_probe_outputs(const float* opacity /*[R,SR]*/, const float* sample_loc_w /*[R,SR,3]*/, const int32_t* sample_pidx /*[R,SR,K]*/,
+                      const float* weight /*[R,SR,K]*/, const float* conf_coef /*[R,SR,K]*/, const int8_t* ray_mask /*[R]*/,
+                      const SgnPointTables* tables, int feat_dim, int64_t R, int SR, int K, float* ray_max_shading_opacity,
+                      float* ray_max_sample_loc_w, float* ray_max_far_dist, float* shading_avg_color, float* shading_avg_dir,
+                      float* shading_avg_conf, float* shading_avg_embedding, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,28 @@ def fill_invalid(ray_mask, ray_color, opacity, bg_transmission, bg_color):
     return color, op, is_bg
 
 
+def probe_outputs(opacity, sample_loc_w, weight, conf_coefficient, gn):
+    """`prob == 1` outputs of NeuralPointsRayMarching.forward (models/neural_points_volumetric_model.py:633-656), the inputs of
+    probe_hole / point growing (run/train_ft.py:425-540): per ray, the sample of largest opacity, its world position, the distance
+    to its nearest gathered neighbour (all K slots: invalid ones hold point 0, as clamp(pidx, 0) gathers it) and the
+    weight * conf averages of its neighbours' colour / dir / conf / embedding.  The same torch calls as the reference.
+    opacity [B,R,SR]; sample_loc_w [B,R,SR,3]; weight, conf_coefficient [B,R,SR,K]; gn = gather_neighbors(...)."""
+    out = {}
+    out["ray_max_shading_opacity"], opacity_ind = torch.max(opacity, dim=-1, keepdim=True)
+    opacity_ind = opacity_ind[..., None]
+    out["ray_max_sample_loc_w"] = torch.gather(sample_loc_w, 2, opacity_ind.expand(-1, -1, -1, sample_loc_w.shape[-1])).squeeze(2)
+    w = torch.gather(weight * conf_coefficient, 2, opacity_ind.expand(-1, -1, -1, weight.shape[-1])).squeeze(2)[..., None]
+    opacity_ind = opacity_ind[..., None]
+    g5 = lambda t: torch.gather(t, 2, opacity_ind.expand(-1, -1, -1, t.shape[-2], t.shape[-1])).squeeze(2)
+    xyz_max = g5(gn.xyz)
+    out["ray_max_far_dist"] = torch.min(torch.norm(xyz_max - out["ray_max_sample_loc_w"][..., None, :], dim=-1), axis=-1, keepdim=True)[0]
+    out["shading_avg_color"] = torch.sum(g5(gn.color) * w, dim=-2)
+    out["shading_avg_dir"] = torch.sum(g5(gn.dir) * w, dim=-2)
+    out["shading_avg_conf"] = torch.sum(g5(gn.conf) * w, dim=-2)
+    out["shading_avg_embedding"] = torch.sum(g5(gn.embedding) * w, dim=-2)
+    return out
+
+
 def render_from_query(P, cfg, tables, sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, ray_mask,
                       camrotc2w, campos, vsize, bg_color):
     """NeuralPointsRayMarching.forward, :541-626, from the querier outputs on."""

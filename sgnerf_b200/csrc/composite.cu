@@ -273,6 +273,75 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
     }
 }
 
+// `prob == 1` outputs (models/neural_points_volumetric_model.py:633-656): one warp per ray.  Lanes find the first sample of largest
+// opacity (torch.max returns the first maximal index), then lane k < K reads neighbour k of that sample -- invalid slots read point 0,
+// as the reference's clamp(pidx, 0) gather does -- and the K-wide reductions are warp shuffles.  Rays with ray_mask <= 0 (no row in
+// the reference's compacted tensors) get zeros.
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+probe_kernel(const float* __restrict__ opacity, const float* __restrict__ loc_w, const int32_t* __restrict__ pidx, const float* __restrict__ weight,
+             const float* __restrict__ conf_coef, const int8_t* __restrict__ ray_mask, SgnPointTables tab, int C, int64_t R, int SR, int K,
+             float* __restrict__ max_opacity, float* __restrict__ max_loc_w, float* __restrict__ far_dist, float* __restrict__ avg_color,
+             float* __restrict__ avg_dir, float* __restrict__ avg_conf, float* __restrict__ avg_emb)
+{
+    const int lane = lane_id();
+    const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * COMP_WARPS;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        const bool hit = !ray_mask || ray_mask[r] > 0;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        if (hit)
+            for (int s = lane; s < SR; s += 32) {
+                const float o = opacity[r * SR + s];
+                if (o > best) { best = o; bi = s; }          // strict: keeps the first maximum of this lane's samples
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (!hit || bi >= SR) { best = 0.f; bi = 0; }
+        const int64_t smp = r * SR + bi;
+        const float lx = hit ? loc_w[3 * smp] : 0.f, ly = hit ? loc_w[3 * smp + 1] : 0.f, lz = hit ? loc_w[3 * smp + 2] : 0.f;
+        float w = 0.f, dmin = INFINITY, cr = 0.f, cg = 0.f, cb = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, cf = 0.f;
+        int p = 0;
+        // K <= 32: lane k owns neighbour k
+        if (hit && lane < K) {
+            const int pi = pidx[smp * K + lane];
+            p = pi < 0 ? 0 : pi;
+            w = weight[smp * K + lane] * conf_coef[smp * K + lane];
+            const float ex = tab.xyz[3 * (int64_t)p] - lx, ey = tab.xyz[3 * (int64_t)p + 1] - ly, ez = tab.xyz[3 * (int64_t)p + 2] - lz;
+            dmin = sqrtf(ex * ex + ey * ey + ez * ez);
+            cr = tab.color[3 * (int64_t)p] * w; cg = tab.color[3 * (int64_t)p + 1] * w; cb = tab.color[3 * (int64_t)p + 2] * w;
+            dx = tab.dir[3 * (int64_t)p] * w; dy = tab.dir[3 * (int64_t)p + 1] * w; dz = tab.dir[3 * (int64_t)p + 2] * w;
+            cf = (tab.conf ? tab.conf[p] : 1.0f) * w;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, off));
+        cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+        dx = warp_sum(dx); dy = warp_sum(dy); dz = warp_sum(dz); cf = warp_sum(cf);
+        if (lane == 0) {
+            if (max_opacity) max_opacity[r] = best;
+            if (max_loc_w) { max_loc_w[3 * r] = lx; max_loc_w[3 * r + 1] = ly; max_loc_w[3 * r + 2] = lz; }
+            if (far_dist) far_dist[r] = hit ? dmin : 0.f;
+            if (avg_color) { avg_color[3 * r] = cr; avg_color[3 * r + 1] = cg; avg_color[3 * r + 2] = cb; }
+            if (avg_dir) { avg_dir[3 * r] = dx; avg_dir[3 * r + 1] = dy; avg_dir[3 * r + 2] = dz; }
+            if (avg_conf) avg_conf[r] = cf;
+        }
+        if (avg_emb)
+            for (int c = lane; c < C; c += 32) {           // embedding average: lane = channel, the K weights broadcast one by one
+                float acc = 0.f;
+                for (int k = 0; k < K; k++) {
+                    const float wk = __shfl_sync(0xffffffffu, w, k);
+                    const int pk = __shfl_sync(0xffffffffu, p, k);
+                    acc += hit ? tab.embedding[(int64_t)pk * C + c] * wk : 0.f;
+                }
+                avg_emb[r * C + c] = acc;
+            }
+    }
+}
+
 __global__ void fill_invalid_kernel(const int8_t* __restrict__ ray_mask, const float* __restrict__ bg, int64_t R, int SR,
                                     float* ray_color, float* opacity, float* bg_t)
 {
@@ -356,6 +425,24 @@ extern "C" int sgn_render_composite(const float* decoded, const float* loc_pers,
     else
         launch(render_composite_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
                                                                             raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_probe_outputs(const float* opacity, const float* sample_loc_w, const int32_t* sample_pidx, const float* weight,
+                                 const float* conf_coef, const int8_t* ray_mask, const SgnPointTables* tables, int feat_dim, int64_t R, int SR,
+                                 int K, float* ray_max_shading_opacity, float* ray_max_sample_loc_w, float* ray_max_far_dist,
+                                 float* shading_avg_color, float* shading_avg_dir, float* shading_avg_conf, float* shading_avg_embedding,
+                                 void* stream)
+{
+    SGN_CHECK_ARG(R >= 0 && SR > 0 && K > 0 && K <= 32, "sgn_probe_outputs: bad R/SR/K (K at most 32)");
+    SGN_CHECK_ARG(opacity && sample_loc_w && sample_pidx && weight && conf_coef && tables, "sgn_probe_outputs: NULL input");
+    SGN_CHECK_ARG(tables->xyz && tables->color && tables->dir && (tables->embedding || !shading_avg_embedding), "sgn_probe_outputs: missing table");
+    SGN_CHECK_ARG(feat_dim % 32 == 0 || !shading_avg_embedding, "sgn_probe_outputs: feat_dim must be a multiple of 32");
+    if (R == 0) return SGN_OK;
+    launch(probe_kernel, comp_grid(R), COMP_WARPS * 32, 0, (cudaStream_t)stream, opacity, sample_loc_w, sample_pidx, weight, conf_coef, ray_mask,
+           *tables, feat_dim, R, SR, K, ray_max_shading_opacity, ray_max_sample_loc_w, ray_max_far_dist, shading_avg_color, shading_avg_dir,
+           shading_avg_conf, shading_avg_embedding);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

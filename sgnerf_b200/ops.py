@@ -229,6 +229,33 @@ def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, 
     return ray_color, opacity, bgt
 
 
+def probe_outputs(opacity, sample_loc_w, sample_pidx, weight, conf_coef, ray_mask, xyz, embedding, color, dirs, conf):
+    """The reference's `prob == 1` outputs (sgn_probe_outputs), rows per input ray.  Returns a dict with the reference's key names:
+    ray_max_shading_opacity [R,1], ray_max_sample_loc_w [R,3], ray_max_far_dist [R,1], shading_avg_color [R,3], shading_avg_dir [R,3],
+    shading_avg_conf [R,1], shading_avg_embedding [R,C]."""
+    f32 = torch.float32
+    opacity = _dev(opacity.detach(), f32, "opacity")
+    R, SR = opacity.shape[-2], opacity.shape[-1]
+    pidx = _dev(sample_pidx, torch.int32, "sample_pidx")
+    K = pidx.shape[-1]
+    xyz = _dev(xyz.reshape(-1, 3), f32, "xyz")
+    N = xyz.shape[0]
+    embedding = _dev(embedding.detach().reshape(N, -1), f32, "embedding")
+    C_ = embedding.shape[1]
+    tb = _tables(xyz, embedding, _dev(color.detach().reshape(N, 3), f32, "color"), _dev(dirs.detach().reshape(N, 3), f32, "dirs"),
+                 _dev(conf.detach().reshape(N), f32, "conf") if conf is not None else None, None)
+    dev = opacity.device
+    o = {"ray_max_shading_opacity": torch.empty(R, 1, device=dev), "ray_max_sample_loc_w": torch.empty(R, 3, device=dev),
+         "ray_max_far_dist": torch.empty(R, 1, device=dev), "shading_avg_color": torch.empty(R, 3, device=dev),
+         "shading_avg_dir": torch.empty(R, 3, device=dev), "shading_avg_conf": torch.empty(R, 1, device=dev),
+         "shading_avg_embedding": torch.empty(R, C_, device=dev)}
+    _lib.call("sgn_probe_outputs", _ptr(opacity), _ptr(_dev(sample_loc_w, f32, "sample_loc_w")), _ptr(pidx), _ptr(_dev(weight.detach(), f32, "weight")),
+              _ptr(_dev(conf_coef.detach(), f32, "conf_coef")), _ptr(_dev(ray_mask, torch.int8, "ray_mask") if ray_mask is not None else None),
+              C.byref(tb), C_, R, SR, K, _ptr(o["ray_max_shading_opacity"]), _ptr(o["ray_max_sample_loc_w"]), _ptr(o["ray_max_far_dist"]),
+              _ptr(o["shading_avg_color"]), _ptr(o["shading_avg_dir"]), _ptr(o["shading_avg_conf"]), _ptr(o["shading_avg_embedding"]), _stream())
+    return o
+
+
 def fill_invalid(ray_mask, bg_color, ray_color, opacity=None, bg_transmission=None):
     """In-place fill_invalid for uncompacted rows (models/neural_points_volumetric_model.py:158-195)."""
     R = ray_mask.numel()

@@ -84,9 +84,11 @@ class RenderScene:
 
 
 def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision=ops.PRECISION_FP32, t=None, want_aux=False,
-                use_point_cache=True):
+                use_point_cache=True, probe=False):
     """Render R rays (device tensors).  Returns a namespace with ray_color [R,3] (misses = bg), ray_mask int8 [R],
-    opacity [R,SR], bg_transmission [R] and, with want_aux, the intermediate tensors."""
+    opacity [R,SR], bg_transmission [R] and, with want_aux, the intermediate tensors.  probe=True adds `probe`, the reference's
+    `prob == 1` outputs (ray_max_* / shading_avg_*, neural_points_volumetric_model.py:633-656) that point growing reads."""
+    want_aux = want_aux or probe
     q = scene.qopt
     grid, hp = scene.grid()
     if t is None:
@@ -107,4 +109,7 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
     if want_aux:
         out.__dict__.update(pidx=pidx, loc_w=loc_w, sample_mask=smask, decoded=decoded, ray_valid=ray_valid, loc_pers=loc_pers,
                             weight=weight, conf_coef=conf_coef, ray_dist=rd, blend_weight=bw, acc_transmission=acc)
+    if probe:
+        out.probe = ops.probe_outputs(opacity, loc_w, pidx, weight, conf_coef, rmask, scene.xyz, scene.embedding, scene.color, scene.dirs,
+                                      scene.conf)
     return out

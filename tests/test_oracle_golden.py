@@ -77,3 +77,23 @@ def test_aggregator_forward_backward(golden_dir, name):
         else:
             s = g["sig_gw_" + k]
             np.testing.assert_allclose([float(v.grad.double().sum()), float(v.grad.double().abs().sum())], s, rtol=1e-4, atol=1e-6)
+
+
+def test_probe_outputs_known_answer():
+    """Hand-made case for the `prob == 1` restatement: the first of two equal opacities wins, an invalid slot reads point 0."""
+    from types import SimpleNamespace
+    xyz = torch.tensor([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 2.0, 0.0]])
+    tables = SimpleNamespace(xyz=xyz, embedding=torch.tensor([[[1.0, 1.0], [2.0, 0.0], [0.0, 4.0]]]), color=torch.tensor([[[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]]]),
+                             dir=torch.tensor([[[0.0, 0, 1.0], [0, 1.0, 0], [1.0, 0, 0]]]), conf=torch.tensor([[[0.5], [1.0], [0.25]]]), label_embedding=None)
+    pidx = torch.tensor([[[[1, 2], [2, -1]]]])                       # [1,1,2,2]: sample 1 has one invalid slot
+    gn = rr.gather_neighbors(tables, pidx, torch.eye(3)[None], torch.tensor([[0.0, 0.0, -5.0]]))
+    opacity = torch.tensor([[[0.7, 0.7]]])
+    loc_w = torch.tensor([[[[1.0, 0.0, 1.0], [9.0, 9.0, 9.0]]]])
+    weight = torch.tensor([[[[0.25, 0.75], [1.0, 0.0]]]])
+    conf_c = torch.tensor([[[[1.0, 0.5], [1.0, 1.0]]]])
+    o = rr.probe_outputs(opacity, loc_w, weight, conf_c, gn)
+    assert torch.equal(o["ray_max_sample_loc_w"], torch.tensor([[[1.0, 0.0, 1.0]]]))                    # sample 0, not 1
+    torch.testing.assert_close(o["ray_max_far_dist"], torch.tensor([[[1.0]]]))                          # point 1 at distance 1
+    torch.testing.assert_close(o["shading_avg_color"], torch.tensor([[[0.0, 0.25, 0.375]]]))
+    torch.testing.assert_close(o["shading_avg_conf"], torch.tensor([[[0.25 * 1.0 + 0.375 * 0.25]]]))
+    torch.testing.assert_close(o["shading_avg_embedding"], torch.tensor([[[0.5, 1.5]]]))
