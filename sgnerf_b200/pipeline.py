@@ -83,6 +83,51 @@ class RenderScene:
         return self._grid, self._hp
 
 
+def agg_cfg_from_state_dict(sd, prefix="aggregator."):
+    """Aggregator configuration recovered from the shapes in a reference checkpoint (layer names of point_aggregators.py:318-418)."""
+    has = lambda k: (prefix + k) in sd
+    count = lambda block: sum(1 for i in range(0, 64, 2) if has(f"{block}.{i}.weight"))
+    n1, n2, n3, nc = count("block1"), count("block2_bpnet"), count("block3"), count("color_branch")
+    width = sd[prefix + "block1.0.weight"].shape[0]
+    k0 = sd[prefix + "block1.0.weight"].shape[1]
+    label_dim = (sd[prefix + "block2_bpnet.0.weight"].shape[1] - width) if n2 > 0 else 0
+    kc0 = sd[prefix + "color_branch.0.weight"].shape[1]
+    fv = (kc0 - width) // 6
+    # k0 = C (1 + 2 F) + 12 FD with the canonical C = 32, F = 3 unless the shapes say otherwise
+    feat_dim, F_, FD = 32, 3, 5
+    if feat_dim * (1 + 2 * F_) + 12 * FD != k0:
+        raise ValueError(f"cannot infer (feat_dim, num_feat_freqs, dist_xyz_freq) from block1.0 input width {k0}; pass agg_cfg explicitly")
+    names = [f"block1.{2 * i}" for i in range(n1)] + [f"block2_bpnet.{2 * i}" for i in range(n2)] + [f"block3.{2 * i}" for i in range(n3)] + \
+            ["alpha_branch.0"] + [f"color_branch.{2 * i}" for i in range(nc)]
+    cfg = ops.agg_cfg(feat_dim=feat_dim, num_feat_freqs=F_, dist_xyz_freq=FD, num_viewdir_freqs=fv, width=width, n_block1=n1,
+                      n_block2_bpnet=n2, label_dim=label_dim, n_block3=n3, n_color=nc)
+    return cfg, names
+
+
+def scene_from_checkpoint(checkpoint, qopt=None, device="cuda", label_emb=None, agg_cfg=None):
+    """RenderScene from a reference checkpoint: the state_dict of `net_ray_marching` as base_model.py:125-159 saves it
+    (`*_net_ray_marching.pth`; keys `neural_points.xyz / points_embeding / points_conf / points_dir / points_color`,
+    `aggregator.<block>.<i>.weight|bias`, optionally under a DataParallel `module.` prefix -- SURVEY.md appendix B).
+    `checkpoint` is a path or an already loaded dict.  bpnet_points_embedding is not part of the checkpoint (the reference refreshes
+    it every forward): pass it as label_emb for the semantic configuration."""
+    sd = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, (str, bytes)) else checkpoint
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    cfg, names = agg_cfg_from_state_dict(sd)
+    if agg_cfg is not None:
+        cfg = agg_cfg
+    g = lambda k: sd.get("neural_points." + k)
+    xyz = g("xyz")
+    N = xyz.shape[0]
+    ones = torch.ones(N)
+    conf = g("points_conf")
+    scene = RenderScene(xyz, g("points_embeding").reshape(N, -1), g("points_color").reshape(N, 3) if g("points_color") is not None else torch.zeros(N, 3),
+                        g("points_dir").reshape(N, 3) if g("points_dir") is not None else torch.zeros(N, 3),
+                        conf.reshape(N) if conf is not None else ones, [sd["aggregator." + n + ".weight"] for n in names],
+                        [sd["aggregator." + n + ".bias"] for n in names], cfg, qopt if qopt is not None else query_options(),
+                        label_emb=label_emb, device=device)
+    return scene
+
+
 def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision=ops.PRECISION_FP32, t=None, want_aux=False,
                 use_point_cache=True, probe=False):
     """Render R rays (device tensors).  Returns a namespace with ray_color [R,3] (misses = bg), ray_mask int8 [R],

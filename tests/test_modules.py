@@ -114,7 +114,7 @@ def test_reference_call_sequence_vs_oracle(train):
     ref = rr.render_from_query(P, cfg, tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, torch.from_numpy(s.camrotc2w)[None],
                                torch.from_numpy(s.campos)[None], o_vsize, torch.ones(3))
     sel = o_mask[0] > 0
-    tol = 1e-3 if train else 1e-2          # training runs the fp32 kernels (1e-3 bar); inference the bf16 tensor-core ones (stated 1e-2)
+    tol = 1e-3 if train else 1e-2          # training runs the layer-wise path with TF32 tensor-core GEMMs (observed < 1e-3 here); inference the bf16 kernels (stated 1e-2)
     torch.testing.assert_close(ray_color[0].detach().cpu(), ref.coarse_raycolor[0][sel], rtol=0, atol=tol)
     assert tuple(point_color.shape) == tuple(decoded.shape[:-1]) + (3,) and blend_weight.shape[-1] == 1 and background_transmission.shape[-1] == 1
     torch.testing.assert_close(background_blend_weight, background_transmission)
@@ -131,3 +131,42 @@ def test_reference_call_sequence_vs_oracle(train):
         loss.backward()
         assert npnts.points_embeding.grad is not None and float(npnts.points_embeding.grad.abs().sum()) > 0
         assert agg.block1[0].weight.grad is not None and npnts.xyz.grad is None
+
+
+@pytest.mark.parametrize("semantic", [False, True])
+def test_agg_cfg_from_reference_checkpoint_shapes(semantic):
+    """A reference-shaped state_dict (keys of SURVEY.md appendix B, DataParallel prefix or not) gives back the configuration and the
+    layer order the C ABI expects -- no GPU needed for the shape logic."""
+    from sgnerf_b200 import pipeline
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
+    P = rr.init_params(cfg, seed=0)
+    sd = {"aggregator." + k: v for k, v in P.items()}
+    c, names = pipeline.agg_cfg_from_state_dict(sd)
+    assert names == [n for n, _, _ in rr.layer_shapes(cfg)]
+    assert (c.width, c.n_block1, c.n_block2_bpnet, c.label_dim, c.n_block3, c.n_color, c.num_viewdir_freqs) == \
+           (256, 2, 1 if semantic else 0, 96 if semantic else 0, 2, 4, 4)
+
+
+@pytest.mark.gpu
+def test_scene_from_reference_checkpoint_renders_like_the_modules_state():
+    """state_dict of (neural_points + aggregator) under a DataParallel prefix -> pipeline.scene_from_checkpoint -> same frame as a
+    RenderScene built from the tensors directly."""
+    from sgnerf_b200 import modules, ops, pipeline, synth
+    dev = "cuda"
+    s = synth.scene_c0(n_points=20_000, n_rays=200)
+    tabs = synth.make_point_tables(s.xyz.shape[0], 32, 0, seed=0, conf_spread=0.2)
+    cfg = rr.agg_config()
+    P = rr.init_params(cfg, seed=0, bias_scale=0.05)
+    sd = {"module.aggregator." + k: v for k, v in P.items()}
+    sd.update({"module.neural_points.xyz": torch.from_numpy(s.xyz), "module.neural_points.points_embeding": tabs.embedding,
+               "module.neural_points.points_conf": tabs.conf, "module.neural_points.points_dir": tabs.dir,
+               "module.neural_points.points_color": tabs.color, "module.neural_points.Rw2c": torch.eye(3)})
+    a = pipeline.scene_from_checkpoint(sd, device=dev)
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    b = pipeline.RenderScene(s.xyz, tabs.embedding, tabs.color, tabs.dir, tabs.conf, [P[n + ".weight"] for n in names], [P[n + ".bias"] for n in names],
+                             ops.agg_cfg(), pipeline.query_options(), device=dev)
+    args = (torch.from_numpy(s.campos).to(dev), torch.from_numpy(s.camrotc2w).to(dev), torch.from_numpy(s.raydir).to(dev), s.near, s.far,
+            torch.ones(3, device=dev))
+    with torch.no_grad():
+        ra, rb = pipeline.render_rays(a, *args), pipeline.render_rays(b, *args)
+    assert torch.equal(ra.ray_color, rb.ray_color) and torch.equal(ra.ray_mask, rb.ray_mask) and int(ra.ray_mask.sum()) > 20
