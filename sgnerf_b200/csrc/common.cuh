@@ -82,14 +82,17 @@ __device__ __forceinline__ int vox_coord(float p, float shift, float vsize)
 }
 
 // The same value as vox_coord for the hot loop of the march: multiply by the reciprocal and take the exact division only when the
-// product lands within 2e-3 of an integer (its error is a few ulp of a quotient < 2^13, far below that margin).
+// product lands too close to an integer to be sure.  With Q = a / vsize exactly, q = fl(a * fl(1 / vsize)) is within |Q| 2^-23 of Q and
+// the reference's fl(a / vsize) within |Q| 2^-24, so whenever q is farther than |q| 4e-7 + 1e-6 (> 3x that) from an integer both floor
+// to the same voxel.  At |q| of a few hundred the test fires for ~1e-4 of the positions, so a warp almost never takes the slow path.
 __device__ __forceinline__ int vox_coord_fast(float p, float shift, float vsize, float rvsize)
 {
     const float a = __fsub_rn(p, shift);
     const float q = a * rvsize;
     const float f = floorf(q);
     const float fr = q - f;
-    if (fr < 2e-3f || fr > 1.0f - 2e-3f || !(fabsf(q) < 8192.0f)) return (int)floorf(__fdiv_rn(a, vsize));
+    const float thr = fmaf(fabsf(q), 4e-7f, 1e-6f);
+    if (fr < thr || fr > 1.0f - thr || !(fabsf(q) < 8192.0f)) return (int)floorf(__fdiv_rn(a, vsize));
     return (int)f;
 }
 

@@ -51,11 +51,6 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
     const float* tr = t_per_ray ? t + r * D : t;
     const int label = ray_label ? ray_label[r] : 0;
     const float rvx = 1.0f / g.vx, rvy = 1.0f / g.vy, rvz = 1.0f / g.vz;
-    // conservative box of the grid (one voxel of margin on every side): a position outside it cannot land in a voxel of the grid
-    // whatever the rounding of the exact coordinate computation, so the lane skips that computation
-    const float bx0 = g.ox - g.vx, bx1 = g.ox + (float)(g.dx + 1) * g.vx;
-    const float by0 = g.oy - g.vy, by1 = g.oy + (float)(g.dy + 1) * g.vy;
-    const float bz0 = g.oz - g.vz, bz1 = g.oz + (float)(g.dz + 1) * g.vz;
     const bool idx32 = (int64_t)g.dx * g.dy * g.dz < (1ll << 31);
     int cnt = 0;
     for (int base = 0; base < D && cnt < SR; base += 32) {
@@ -68,7 +63,7 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
             px = __fadd_rn(cx, __fmul_rn(dx, tv));
             py = __fadd_rn(cy, __fmul_rn(dy, tv));
             pz = __fadd_rn(cz, __fmul_rn(dz, tv));
-            if (px > bx0 && px < bx1 && py > by0 && py < by1 && pz > bz0 && pz < bz1) {
+            {
                 const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
                 if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
                     if (idx32) {
