@@ -29,6 +29,23 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
         // canonical K: the eight indices as two 16-byte loads, every output row as two 16-byte stores
         const int4 pa = __ldg((const int4*)pi), pb = __ldg((const int4*)pi + 1);
         const int p8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+        if ((pa.x & pa.y & pa.z & pa.w & pb.x & pb.y & pb.z & pb.w) < 0) {
+            // no neighbour at all (two thirds of the slots of a frame): zero weights; the confidence column still holds point 0's
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* o = (float4*)(wc + s * 8);
+            o[0] = z4; o[1] = z4;
+            if (weight_n) { o = (float4*)(weight_n + s * 8); o[0] = z4; o[1] = z4; }
+            if (weight_out) { o = (float4*)(weight_out + s * 8); o[0] = z4; o[1] = z4; }
+            if (conf_out) {
+                const float c0 = in.tab.conf ? fminf(fmaxf(__ldg(in.tab.conf), 0.0001f), 1.0f) : 1.0f;
+                const float4 c4 = make_float4(c0, c0, c0, c0);
+                o = (float4*)(conf_out + s * 8); o[0] = c4; o[1] = c4;
+            }
+            ray_valid[s] = 0;
+            nvalid[s] = 0;
+            svalid[s] = 0;
+            return;
+        }
         float w8[8], cf8[8];
         float sum = 0.f;
         int n = 0;

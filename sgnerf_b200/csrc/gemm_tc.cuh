@@ -255,10 +255,12 @@ static inline bool gemm_tc_nn_ok(const GemmNN& g)
 static inline int launch_gemm_tc_nn(const GemmNN& g, cudaStream_t st)
 {
     if (g.m_max <= 0) return SGN_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                        // the attribute is per device (one process may drive several)
+    int dev_id = 0;
+    SGN_CUDA(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         SGN_CUDA(cudaFuncSetAttribute(gemm_tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM));
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     GemmTcNN p = {};
     p.A1 = g.A1; p.lda1 = g.lda1; p.Bt1 = g.Bt1; p.ldb1 = g.ldbt1; p.K1 = g.K1;
@@ -412,10 +414,12 @@ static inline bool gemm_tc_tn_ok(const GemmTN& t)
 static inline int launch_gemm_tc_tn(const GemmTN& t, cudaStream_t st)
 {
     if (t.m_max <= 0) return SGN_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                        // the attribute is per device (one process may drive several)
+    int dev_id = 0;
+    SGN_CUDA(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         SGN_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     GemmTcTN p = {};
     p.A = t.A; p.lda = t.lda; p.P = t.P; p.B = t.B; p.ldb = t.ldb; p.Q = t.Q; p.C = t.C; p.ldc = t.ldc; p.m_ptr = t.m_ptr; p.m_max = t.m_max;

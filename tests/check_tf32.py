@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-tensor error report of the TF32 tensor-core training path against the fp32 SIMT path (debug aid for gemm_tc.cuh)."""
+"""Per-tensor error report of the TF32 tensor-core training path against the fp32 SIMT path (debug aid for gemm_tc.cuh; test
+infrastructure: it uses the oracle's parameter initialiser).  python tests/check_tf32.py [semantic]"""
 import os
 import sys
 
