@@ -182,7 +182,23 @@ def run_ours(args):
             b.record(); torch.cuda.synchronize()
             agg_ms.append(a.elapsed_time(b))
         agg_ms = float(np.mean(agg_ms[1:]))
-        del pidx, loc_w, smask, rmask
+        # ---- the HBM-bound stages on their own (SURVEY.md section 8d byte formulas): query (march + knn) and the frame tail
+        def timed_ms(fn, n=max(3, args.steps)):
+            ms = []
+            for _ in range(n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b))
+            return float(np.mean(ms[1:])), r
+        query_ms, _ = timed_ms(lambda: ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2))
+        dec_, val_, lp_, _, _ = ops.aggregate(scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs,
+                                              scene.conf, None, pidx, loc_w, raydir, campos, rot, precision=precision, want_aux=False)
+        tail_ms, _ = timed_ms(lambda: ops.render_composite(dec_, lp_, val_, rmask, hp.vsize[2], bg, blend=0))
+        n_touched = int(torch.unique(pidx[pidx >= 0]).numel())
+        hit_rays = int((rmask > 0).sum())
+        query_bytes = 24 * R + 4 * q.z_depth_dim + R + hit_rays * q.SR * (12 + 4 * q.K) + 12 * n_touched
+        tail_bytes = R * q.SR * (16 + 4 + 1) + R * q.SR * 4 + R * 16
+        del pidx, loc_w, smask, rmask, dec_, val_, lp_
         # ---- grid build (once per cloud version; not part of the static-scene step) ----
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         scene.invalidate_grid(); torch.cuda.synchronize()
@@ -274,6 +290,15 @@ def run_ours(args):
                              "block1.0's 284 input columns are hoisted into a per-point GEMM (tc_point_l0_kernel, inside `stage`)",
                      "stage": {"name": "sgn_agg_forward (prepare + scans + tuple kernel + colour kernel)", "ms": agg_ms,
                                "algorithmic_flops": flops_stage, "achieved": flops_stage / (agg_ms * 1e-3) / 1e12}},
+        # the two HBM-bound stages of the frame, algorithmic bytes of SURVEY.md section 8d over their own CUDA-event time (warm caches)
+        "hbm_stages": {
+            "peak_GBps": peaks["hbm"],
+            "query": {"kernels": "march_kernel + knn_kernel (sgn_query)", "ms": query_ms, "algorithmic_bytes": int(query_bytes),
+                      "achieved_GBps": query_bytes / (query_ms * 1e-3) / 1e9, "frac": query_bytes / (query_ms * 1e-3) / 1e9 / peaks["hbm"],
+                      "note": "bound by instruction issue (march) and dependent L2/HBM reads (knn), not by bytes: see DESIGN.md 4.2"},
+            "frame_tail": {"kernels": "render_composite_kernel (step sizes + compositing + fill_invalid)", "ms": tail_ms,
+                           "algorithmic_bytes": int(tail_bytes), "achieved_GBps": tail_bytes / (tail_ms * 1e-3) / 1e9,
+                           "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm"]}},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
