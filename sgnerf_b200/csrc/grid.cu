@@ -31,6 +31,7 @@ struct SgnGrid {
     int32_t* slot_start;
     float4* cand;
     int32_t* counters;
+    uint32_t* coarse_bits;   // 1 bit per 8^3 voxels: some voxel of the brick, or one next to it, is set in occ_bits (march_kernel's skip test)
 };
 
 namespace sgn {
@@ -206,7 +207,8 @@ __global__ void emit_cand_kernel(int max_o, const float* __restrict__ xyz, const
 }
 
 // K8: occupancy bits on the query_size box around every surviving record (:353-360)
-__global__ void dilate_kernel(GridParams g, const int32_t* __restrict__ counters, const int32_t* __restrict__ slot_coor, uint32_t* occ_bits)
+__global__ void dilate_kernel(GridParams g, const int32_t* __restrict__ counters, const int32_t* __restrict__ slot_coor, uint32_t* occ_bits,
+                              uint32_t* coarse_bits)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     int n_rec = counters[0] < g.max_o ? counters[0] : g.max_o;
@@ -224,6 +226,19 @@ __global__ void dilate_kernel(GridParams g, const int32_t* __restrict__ counters
                 uint32_t bit = 1u << (c & 31);
                 if (!(occ_bits[c >> 5] & bit)) atomicOr(occ_bits + (c >> 5), bit);
             }
+    // coarse mask: every 8^3 brick that holds one of these voxels or a voxel adjacent to one (the one-voxel margin absorbs the rounding
+    // of the approximate coordinate march_kernel tests the brick with)
+    const int cdx = (g.dx + 7) >> 3, cdy = (g.dy + 7) >> 3, cdz = (g.dz + 7) >> 3;
+    const int bx0 = max(0, (x0 - 1) >> 3), bx1 = min(cdx - 1, x1 >> 3);
+    const int by0 = max(0, (y0 - 1) >> 3), by1 = min(cdy - 1, y1 >> 3);
+    const int bz0 = max(0, (z0 - 1) >> 3), bz1 = min(cdz - 1, z1 >> 3);
+    for (int x = bx0; x <= bx1; x++)
+        for (int y = by0; y <= by1; y++)
+            for (int z = bz0; z <= bz1; z++) {
+                const int c = (x * cdy + y) * cdz + z;
+                const uint32_t bit = 1u << (c & 31);
+                if (!(coarse_bits[c >> 5] & bit)) atomicOr(coarse_bits + (c >> 5), bit);
+            }
 }
 
 static GridParams make_params(const SgnGridCfg* c)
@@ -238,10 +253,16 @@ static GridParams make_params(const SgnGridCfg* c)
 }
 
 struct GridLayout {
-    size_t cell_slot, occ_bits, slot_coor, slot_count, slot_start, cand, counters, total;
+    size_t cell_slot, occ_bits, slot_coor, slot_count, slot_start, cand, counters, coarse_bits, total;
 };
 
 static int64_t grid_vol(const SgnGridCfg* c) { return (int64_t)c->dim[0] * c->dim[1] * c->dim[2]; }
+
+static size_t coarse_words(const SgnGridCfg* c)
+{
+    const size_t cvol = (size_t)((c->dim[0] + 7) >> 3) * ((c->dim[1] + 7) >> 3) * ((c->dim[2] + 7) >> 3);
+    return (cvol + 31) / 32;
+}
 
 static GridLayout persistent_layout(int64_t N, const SgnGridCfg* c)
 {
@@ -256,6 +277,7 @@ static GridLayout persistent_layout(int64_t N, const SgnGridCfg* c)
     L.slot_start = take(sizeof(int32_t) * ((size_t)c->max_o + 1));
     L.cand = take(sizeof(float4) * (size_t)(N > 0 ? N : 1));
     L.counters = take(sizeof(int32_t) * 4);
+    L.coarse_bits = take(sizeof(uint32_t) * coarse_words(c));
     L.total = off;
     return L;
 }
@@ -326,6 +348,7 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
     G->slot_start = (int32_t*)(pb + L.slot_start);
     G->cand = (float4*)(pb + L.cand);
     G->counters = (int32_t*)(pb + L.counters);
+    G->coarse_bits = (uint32_t*)(pb + L.coarse_bits);
 
     Arena A(scratch, scratch_bytes);
     int64_t nscan = N > max_o ? N : max_o;
@@ -349,6 +372,7 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
     GRID_CUDA(cudaMemsetAsync(G->slot_coor, 0xFF, sizeof(int32_t) * 3 * (size_t)max_o, st));
     GRID_CUDA(cudaMemsetAsync(G->slot_count, 0, sizeof(int32_t) * (size_t)max_o, st));
     GRID_CUDA(cudaMemsetAsync(G->counters, 0, sizeof(int32_t) * 4, st));
+    GRID_CUDA(cudaMemsetAsync(G->coarse_bits, 0, sizeof(uint32_t) * coarse_words(cfg), st));
     GRID_CUDA(cudaMemsetAsync(record_writer, 0xFF, sizeof(int32_t) * (size_t)max_o, st));
     GRID_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)max_o, st));
 
@@ -365,7 +389,7 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
         launch(slot_canon_kernel, cdiv(max_o, T), T, 0, st, max_o, cfg->P, cfg->seconds_fill, G->slot_count, seg_start, seg, ncap);
         GRID_TRY(exclusive_scan_i32(ncap, G->slot_start, max_o, partials, st));
         launch(emit_cand_kernel, cdiv(max_o, T), T, 0, st, max_o, xyz, seg_start, seg, G->slot_start, G->cand, G->counters);
-        launch(dilate_kernel, cdiv(max_o, T), T, 0, st, g, G->counters, G->slot_coor, G->occ_bits);
+        launch(dilate_kernel, cdiv(max_o, T), T, 0, st, g, G->counters, G->slot_coor, G->occ_bits, G->coarse_bits);
         GRID_CUDA(cudaGetLastError());
     } else {
         GRID_CUDA(cudaMemsetAsync(G->slot_start, 0, sizeof(int32_t) * ((size_t)max_o + 1), st));
@@ -393,6 +417,7 @@ extern "C" int sgn_grid_buffer(const SgnGrid* g, int which, void** ptr, int64_t*
         case 4: *ptr = g->slot_start; *n = (int64_t)g->cfg.max_o + 1; break;
         case 5: *ptr = g->cand; *n = g->N; break;
         case 6: *ptr = g->counters; *n = 4; break;
+        case 7: *ptr = g->coarse_bits; *n = (int64_t)coarse_words(&g->cfg); break;
         default: set_error("sgn_grid_buffer: unknown buffer %d", which); return SGN_E_INVALID;
     }
     return SGN_OK;

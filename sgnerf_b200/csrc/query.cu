@@ -23,6 +23,7 @@ struct SgnGrid {
     int32_t* slot_start;
     float4* cand;
     int32_t* counters;
+    uint32_t* coarse_bits;
 };
 
 namespace sgn {
@@ -34,6 +35,8 @@ struct QueryGrid {
     const uint32_t* occ_bits;
     const int32_t* slot_start;
     const float4* cand;
+    const uint32_t* coarse_bits;   // 8^3-voxel bricks that may hold an occupied voxel (grid.cu:dilate_kernel)
+    int cdx, cdy, cdz;
 };
 
 constexpr int MARCH_WARPS = 8;
@@ -51,29 +54,25 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
     const float* tr = t_per_ray ? t + r * D : t;
     const int label = ray_label ? ray_label[r] : 0;
     const float rvx = 1.0f / g.vx, rvy = 1.0f / g.vy, rvz = 1.0f / g.vz;
-    const bool idx32 = (int64_t)g.dx * g.dy * g.dz < (1ll << 31);
-    int cnt = 0;
-    for (int base = 0; base < D && cnt < SR; base += 32) {
-        const int d = base + lane;
+    const float fdx = (float)g.dx + 0.01f, fdy = (float)g.dy + 0.01f, fdz = (float)g.dz + 0.01f;
+    __shared__ uint16_t s_queue[MARCH_WARPS][64];            // per warp: depth indices that passed the brick test, in ray order
+    uint16_t* queue = s_queue[threadIdx.x >> 5];
+    int cnt = 0, qn = 0;
+    // exact test of up to 32 queued candidates (lane i takes entry i): voxel coordinate as the reference computes it, occupancy bit,
+    // rank among the ray's occupied candidates by ballot + popcount (the reference's torch.cumsum, :843-844), sample store
+    auto drain = [&](int n) {
         bool occ = false;
         float px = 0.f, py = 0.f, pz = 0.f;
-        if (d < D) {
-            const float tv = __ldg(tr + d);
+        if (lane < n) {
+            const float tv = __ldg(tr + queue[lane]);
             // campos + raydir * t with separate fp32 multiply and add, as torch evaluates it
             px = __fadd_rn(cx, __fmul_rn(dx, tv));
             py = __fadd_rn(cy, __fmul_rn(dy, tv));
             pz = __fadd_rn(cz, __fmul_rn(dz, tv));
-            {
-                const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
-                if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
-                    if (idx32) {
-                        const uint32_t c = ((uint32_t)vx * (uint32_t)g.dy + (uint32_t)vy) * (uint32_t)g.dz + (uint32_t)vz;
-                        occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
-                    } else {
-                        const int64_t c = ((int64_t)vx * g.dy + vy) * g.dz + vz;
-                        occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
-                    }
-                }
+            const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
+            if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
+                const uint32_t c = ((uint32_t)vx * (uint32_t)g.dy + (uint32_t)vy) * (uint32_t)g.dz + (uint32_t)vz;   // < 2^31 (grid.cu:check_cfg)
+                occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
             }
         }
         const unsigned b = __ballot_sync(0xffffffffu, occ);
@@ -85,7 +84,38 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
             if (sample_label) sample_label[o] = label;
         }
         cnt += __popc(b);
+    };
+    for (int base = 0; base < D && cnt < SR; base += 32) {
+        const int d = base + lane;
+        bool maybe = false;
+        if (d < D) {
+            // brick test: approximate voxel coordinate (a few 1e-5 off at most), 8^3-voxel brick, one bit.  The mask covers every brick
+            // with an occupied voxel inside or one voxel away, so a candidate that fails it cannot be occupied whatever the rounding;
+            // only the others are queued for the exact test, and the queue keeps them in ray order.
+            const float tv = __ldg(tr + d);
+            const float ax = (__fadd_rn(cx, __fmul_rn(dx, tv)) - g.ox) * rvx, ay = (__fadd_rn(cy, __fmul_rn(dy, tv)) - g.oy) * rvy,
+                        az = (__fadd_rn(cz, __fmul_rn(dz, tv)) - g.oz) * rvz;
+            if (ax > -0.01f && ay > -0.01f && az > -0.01f && ax < fdx && ay < fdy && az < fdz) {
+                const int bx = min((int)(ax * 0.125f), g.cdx - 1), by = min((int)(ay * 0.125f), g.cdy - 1), bz = min((int)(az * 0.125f), g.cdz - 1);
+                const int bc = (bx * g.cdy + by) * g.cdz + bz;
+                maybe = (__ldg(g.coarse_bits + (bc >> 5)) >> (bc & 31)) & 1u;
+            }
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, maybe);
+        if (mb == 0u) continue;
+        if (maybe) queue[qn + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)d;
+        qn += __popc(mb);
+        __syncwarp();
+        if (qn >= 32) {
+            drain(32);
+            const uint16_t carry = queue[32 + lane];             // at most 31 entries stay behind
+            __syncwarp();
+            queue[lane] = carry;
+            qn -= 32;
+            __syncwarp();
+        }
     }
+    if (qn > 0 && cnt < SR) drain(qn);
     cnt = cnt < SR ? cnt : SR;
     for (int s = cnt + lane; s < SR; s += 32) {  // unused slots stay at world (0,0,0), mask 0 (:835, :845)
         const int64_t o = r * SR + s;
@@ -283,7 +313,7 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
                          int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, void* stream)
 {
     SGN_CHECK_ARG(G != nullptr, "sgn_query: grid is NULL");
-    SGN_CHECK_ARG(R >= 0 && D > 0 && SR > 0 && SR <= 4096, "sgn_query: bad R/D/SR (SR at most 4096)");
+    SGN_CHECK_ARG(R >= 0 && D > 0 && D <= 65535 && SR > 0 && SR <= 4096, "sgn_query: bad R/D/SR (D at most 65535, SR at most 4096)");
     SGN_CHECK_ARG(K > 0 && K <= SGN_MAX_K, "sgn_query: K=%d out of range (1..%d)", K, SGN_MAX_K);
     SGN_CHECK_ARG(sample_pidx && sample_loc_w && sample_mask && ray_mask, "sgn_query: NULL output");
     const bool semantic = ray_label != nullptr;
@@ -295,6 +325,7 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     g.vx = G->cfg.vsize[0]; g.vy = G->cfg.vsize[1]; g.vz = G->cfg.vsize[2];
     g.dx = G->cfg.dim[0]; g.dy = G->cfg.dim[1]; g.dz = G->cfg.dim[2];
     g.cell_slot = G->cell_slot; g.occ_bits = G->occ_bits; g.slot_start = G->slot_start; g.cand = G->cand;
+    g.coarse_bits = G->coarse_bits; g.cdx = (g.dx + 7) >> 3; g.cdy = (g.dy + 7) >> 3; g.cdz = (g.dz + 7) >> 3;
 
     launch(march_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
                                                                    sample_mask, semantic ? sample_label : nullptr, ray_mask);
