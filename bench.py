@@ -254,6 +254,7 @@ def run_ours(args):
         clocks = sampler.stop()
 
     train = None if args.no_train_step else train_step_leg(s, scene, device, rank, world, dist, bg)
+    ref_gpu = reference_gpu_leg(s, P, tabs, device) if (world == 1 and rank == 0 and not args.no_reference_gpu) else None
     tmax = torch.tensor([ms_total, e2e_ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -279,7 +280,7 @@ def run_ours(args):
                    "parallelism": f"ray-sharded x{world}, point cloud replicated, no collective on the render path",
                    "semantic_variant": None if sem_ms is None else {"what": "same frame with block2_bpnet + 96-d label embedding (rank 0)", "ms_per_step": sem_ms,
                                                                     "rays_per_s_per_gpu": R / (sem_ms * 1e-3)}},
-        "clocks": clocks, "gpu_launches": int(launches), "train_step": train,
+        "clocks": clocks, "gpu_launches": int(launches), "train_step": train, "reference_gpu": ref_gpu,
         "e2e": {"value": world * R / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(R * 12 + 48),
                 "d2h_bytes_per_step": int(R * 12)},
         "roofline": {"bound": "tensor", "kernel": rl_kernel, "achieved": achieved,
@@ -357,6 +358,74 @@ def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
         info.update(ms=ms, rays_per_s=world * n / (ms * 1e-3), steps=steps)
+    except Exception as e:
+        info["error"] = repr(e)[:300]
+    return info
+
+
+def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
+    """The reference's own path on this B200, beside ours (SURVEY.md section 8d "GPU (one B200)"): its CUDA query kernels compiled
+    unchanged from the reference source (oracle/_ref, launched with the reference's geometry and torch glue by tests/ref_driver.py,
+    grid rebuilt in every call as query_point_indices_worldcoords.py:706-778 does) + the torch restatement of its gathers /
+    aggregator / ray_march (oracle/render_ref.py) on cuda, in 48^2-ray chunks as run/test_ft.py renders a frame.  A bounded sample
+    of chunks of the same C1 frame; wall clock per chunk including the reference's host synchronisations.  fp32 matmuls and, as
+    the reference's pinned torch 1.10 defaults to, TF32 matmuls."""
+    from types import SimpleNamespace
+    info = {"what": f"reference CUDA query kernels (per-call grid rebuild) + torch aggregator/ray_march on cuda, {chunk}-ray chunks"}
+    try:
+        from oracle import query_ref as qr
+        from oracle import render_ref as rr
+        from sgnerf_b200 import ops
+        from tests import ref_driver, util
+        if not ref_driver.available(8):
+            info["unavailable"] = "oracle/_ref/libref_query_K8.so not built (needs /root/reference at build time)"
+            return info
+        L = ref_driver.lib(8)
+        opt, cfg = qr.default_opt(SR=24), rr.agg_config()
+        xyz = torch.from_numpy(s.xyz).to(device)[None]
+        Pd = {k: v.to(device) for k, v in P.items()}
+        tables = SimpleNamespace(xyz=xyz[0], embedding=tabs.embedding.to(device), color=tabs.color.to(device), dir=tabs.dir.to(device),
+                                 conf=tabs.conf.to(device), label_embedding=None)
+        campos, rot = torch.from_numpy(s.campos).to(device)[None], torch.from_numpy(s.camrotc2w).to(device)[None]
+        rays = torch.from_numpy(s.raydir).to(device)
+        t = util.shared_t(s.near, s.far, opt.z_depth_dim).to(device)
+        bg = torch.ones(3, device=device)
+        n_total = rays.shape[0] // chunk
+        picks = [int(i * n_total / n_chunks) for i in range(n_chunks)]
+
+        def one(ci):
+            rd = rays[ci * chunk:(ci + 1) * chunk]
+            hp = ops.grid_hyperparameters(xyz[0], opt.vsize, opt.vscale, opt.kernel_size, opt.ranges, opt.radius_limit_scale)   # :66-92, every call
+            raypos = qr.raypos_from_t(campos, rd[None], t)
+            torch.cuda.synchronize(); q0 = time.perf_counter()
+            pidx, loc_w, mask, _ = ref_driver.query_grid_point_index(L, raypos, xyz, opt, hp)
+            torch.cuda.synchronize(); q1 = time.perf_counter()
+            sel = mask[0] > 0
+            if int(sel.sum()) == 0:
+                return q1 - q0
+            dirs = rd[sel][None, :, None, :].expand(-1, -1, opt.SR, -1).contiguous()
+            loc = rr.w2pers_points(loc_w.reshape(-1, 3), rot, campos).reshape(1, -1, opt.SR, 3)
+            with torch.device(device):
+                rr.render_from_query(Pd, cfg, tables, pidx, loc, loc_w, dirs, mask, rot, campos, np.asarray(opt.vsize, np.float32), bg)
+            return q1 - q0
+
+        with torch.no_grad():
+            for tf32, key in ((False, "fp32"), (True, "tf32")):
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                try:
+                    for ci in picks:                                    # warm-up on the same chunks (cuBLAS heuristics per shape, allocator)
+                        one(ci)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    tq = sum(one(ci) for ci in picks)
+                    torch.cuda.synchronize()
+                    sec = time.perf_counter() - t0
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+                info[key] = {"rays_per_s": n_chunks * chunk / sec, "ms_per_chunk": sec / n_chunks * 1e3, "query_ms_per_chunk": tq / n_chunks * 1e3,
+                             "frame_ms_extrapolated": sec / n_chunks * 1e3 * (rays.shape[0] / chunk)}
+        info["chunks_sampled"] = n_chunks
     except Exception as e:
         info["error"] = repr(e)[:300]
     return info
@@ -448,6 +517,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-semantic-variant", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
