@@ -426,6 +426,47 @@ def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
                 info[key] = {"rays_per_s": n_chunks * chunk / sec, "ms_per_chunk": sec / n_chunks * 1e3, "query_ms_per_chunk": tq / n_chunks * 1e3,
                              "frame_ms_extrapolated": sec / n_chunks * 1e3 * (rays.shape[0] / chunk)}
         info["chunks_sampled"] = n_chunks
+        # ---- C2 beside train_step: 56x56 random rays, reference query kernels + torch autograd through the restatement + dense Adam
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            leaf = lambda x: x.clone().requires_grad_(True)
+            Pt = {k: leaf(v) for k, v in Pd.items()}
+            tt = SimpleNamespace(xyz=xyz[0], embedding=leaf(tables.embedding), color=leaf(tables.color), dir=leaf(tables.dir),
+                                 conf=leaf(tables.conf), label_embedding=None)
+            optim = torch.optim.Adam([{"params": list(Pt.values()), "lr": 5e-4}, {"params": [tt.embedding, tt.color, tt.dir, tt.conf], "lr": 2e-3}])
+            gen = torch.Generator(device=device).manual_seed(7)
+            n = 56 * 56
+
+            def train_one():
+                pix = torch.randint(0, rays.shape[0], (n,), device=device, generator=gen)
+                rd = rays[pix]
+                gt = torch.rand(1, n, 3, device=device, generator=gen)
+                hp = ops.grid_hyperparameters(xyz[0], opt.vsize, opt.vscale, opt.kernel_size, opt.ranges, opt.radius_limit_scale)
+                with torch.no_grad():
+                    pidx, loc_w, mask, _ = ref_driver.query_grid_point_index(L, qr.raypos_from_t(campos, rd[None], t), xyz, opt, hp)
+                sel = mask[0] > 0
+                dirs = rd[sel][None, :, None, :].expand(-1, -1, opt.SR, -1).contiguous()
+                loc = rr.w2pers_points(loc_w.reshape(-1, 3), rot, campos).reshape(1, -1, opt.SR, 3)
+                with torch.device(device):
+                    out = rr.render_from_query(Pt, cfg, tt, pidx, loc, loc_w, dirs, mask, rot, campos, np.asarray(opt.vsize, np.float32), bg)
+                    c = out.conf_coefficient.reshape(-1)
+                    loss = ((out.ray_color - gt[:, sel]) ** 2).mean() + 1e-4 * torch.mean(torch.log(0.1 + c) + torch.log(0.1 + 1.0 - c) + 2.20727)
+                optim.zero_grad(set_to_none=False)
+                loss.backward()
+                optim.step()
+
+            for _ in range(2):
+                train_one()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                train_one()
+            torch.cuda.synchronize()
+            info["train_step_tf32"] = {"ms": (time.perf_counter() - t0) / 5 * 1e3, "rays_per_step": n,
+                                       "what": "reference query kernels + torch autograd through the restatement (TF32 matmuls) + dense Adam"}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
     except Exception as e:
         info["error"] = repr(e)[:300]
     return info
