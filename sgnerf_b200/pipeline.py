@@ -74,6 +74,28 @@ class RenderScene:
             self._point_cache = ops.build_point_cache(self.agg_cfg, self.weights, self.embedding, self.label_emb)
         return self._point_cache
 
+    # ---- point-cloud edits (NeuralPoints.prune / grow_points, models/neural_points/neural_points.py:520-572): the tables are re-made
+    # on the device, the occupancy grid and the per-point tables are rebuilt on next use
+    def prune(self, thresh):
+        """Drop the points whose confidence is below `thresh`.  Returns the number of points kept."""
+        keep = self.conf >= thresh
+        self.xyz, self.embedding, self.color, self.dirs, self.conf = (self.xyz[keep], self.embedding[keep], self.color[keep],
+                                                                     self.dirs[keep], self.conf[keep])
+        if self.label_emb is not None:
+            self.label_emb = self.label_emb[keep]
+        self.invalidate_grid()
+        return int(self.xyz.shape[0])
+
+    def grow(self, add_xyz, add_embedding, add_color, add_dir, add_conf, add_label_emb=None):
+        """Append points (device tensors [M,3], [M,C], [M,3], [M,3], [M])."""
+        cat = lambda a, b: torch.cat([a, b.to(a.device, a.dtype).reshape(-1, *a.shape[1:])], dim=0).contiguous()
+        self.xyz, self.embedding, self.color, self.dirs, self.conf = (cat(self.xyz, add_xyz), cat(self.embedding, add_embedding),
+                                                                     cat(self.color, add_color), cat(self.dirs, add_dir), cat(self.conf, add_conf))
+        if self.label_emb is not None:
+            self.label_emb = cat(self.label_emb, add_label_emb)
+        self.invalidate_grid()
+        return int(self.xyz.shape[0])
+
     def grid(self, seconds=(0, 0)):
         if self._grid is None:
             q = self.qopt

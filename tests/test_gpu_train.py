@@ -54,3 +54,33 @@ def test_graph_replay_matches_eager_steps():
     # may go the other way in the two runs (the scatter-adds are float atomics): compare in the mean, not element by element
     for pa, pb in zip(a.params, b.params):
         assert float((pa.detach() - pb.detach()).abs().mean()) < 2e-4
+
+
+def test_scene_prune_and_grow_rebuild_the_grid():
+    """RenderScene.prune / grow (NeuralPoints.prune / grow_points): the edited cloud renders exactly like a scene built from the same
+    tensors from scratch (grid and per-point tables are rebuilt on next use)."""
+    n_points = 40_000
+    s = synth.scene_room(n_points, room=(3.0, 3.0, 2.0), width=160, height=120, seed=7)
+    tabs = synth.make_point_tables(n_points, 32, 0, seed=0, conf_spread=0.3)
+    cfg = rr.agg_config()
+    P = rr.init_params(cfg, seed=3, bias_scale=0.05)
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    mk = lambda xyz, e, c, d, cf: pipeline.RenderScene(xyz, e, c, d, cf, [P[n + ".weight"].clone() for n in names], [P[n + ".bias"].clone() for n in names],
+                                                       cfg_to_c(cfg), pipeline.query_options(), device="cuda")
+    a = mk(torch.from_numpy(s.xyz), tabs.embedding.reshape(n_points, -1), tabs.color.reshape(n_points, 3), tabs.dir.reshape(n_points, 3),
+           tabs.conf.reshape(n_points))
+    args = (torch.from_numpy(s.campos).cuda(), torch.from_numpy(s.camrotc2w).cuda(), torch.from_numpy(s.raydir).cuda(), s.near, s.far,
+            torch.ones(3, device="cuda"))
+    with torch.no_grad():
+        before = pipeline.render_rays(a, *args, precision=ops.PRECISION_BF16)
+        kept = a.prune(0.9)
+        assert 0 < kept < n_points
+        g = torch.Generator(device="cuda").manual_seed(1)
+        m = 500
+        a.grow(a.xyz[:m] + 0.003, torch.rand(m, 32, device="cuda", generator=g) - 0.5, torch.rand(m, 3, device="cuda", generator=g),
+               torch.nn.functional.normalize(torch.randn(m, 3, device="cuda", generator=g), dim=-1), torch.ones(m, device="cuda"))
+        after = pipeline.render_rays(a, *args, precision=ops.PRECISION_BF16)
+        b = mk(a.xyz.clone(), a.embedding.clone(), a.color.clone(), a.dirs.clone(), a.conf.clone())
+        fresh = pipeline.render_rays(b, *args, precision=ops.PRECISION_BF16)
+    assert torch.equal(after.ray_color, fresh.ray_color) and torch.equal(after.ray_mask, fresh.ray_mask)
+    assert not torch.equal(after.ray_color, before.ray_color)

@@ -55,7 +55,31 @@ def main():
         torch.cuda.synchronize()
         d_self = float((sub16.ray_color - o2.ray_color[sel]).abs().max())
         d_fp32 = float((sub16.ray_color - sub32.ray_color).abs().max())
-    print(json.dumps({"config": which, "points": n, "rays": int(raydir.shape[0]), "SR": scene.qopt.SR, "rays_hit": hit, "valid_tuples": T_v,
+    edit = None
+    if which == "c4":
+        # between steps prune the 2 % lowest-confidence points and grow 1 % new ones; the grid and the per-point
+        # first-layer tables are rebuilt, and all of it is inside the timed step
+        with torch.no_grad():
+            g = torch.Generator(device=dev).manual_seed(5)
+            scene.conf = (0.5 + 0.5 * torch.rand(n, device=dev, generator=g)).contiguous()
+            pipeline.render_rays(scene, campos, rot, raydir, s.near, s.far, bg, precision=ops.PRECISION_BF16)
+            ms_e = []
+            for it in range(3):
+                a, b = ev(), ev()
+                a.record()
+                thr = torch.quantile(scene.conf[:1_000_000], 0.02)           # device-side threshold (a 1M-point sample of the confidences)
+                kept = scene.prune(thr)
+                m = n // 100
+                base = scene.xyz[torch.randint(0, kept, (m,), device=dev, generator=g)]
+                scene.grow(base + 0.004 * torch.randn(m, 3, device=dev, generator=g), torch.rand(m, 32, device=dev, generator=g) - 0.5,
+                           torch.rand(m, 3, device=dev, generator=g), torch.nn.functional.normalize(torch.randn(m, 3, device=dev, generator=g), dim=-1),
+                           torch.ones(m, device=dev))
+                o3 = pipeline.render_rays(scene, campos, rot, raydir, s.near, s.far, bg, precision=ops.PRECISION_BF16)
+                b.record(); torch.cuda.synchronize()
+                ms_e.append(a.elapsed_time(b))
+            edit = {"what": "prune 2 % lowest confidence + grow 1 % + grid rebuild + per-point tables + full frame", "ms_per_step": ms_e,
+                    "points_after": int(scene.xyz.shape[0]), "rays_hit": int(o3.ray_mask.sum())}
+    print(json.dumps({"config": which, "grow_prune_step": edit, "points": n, "rays": int(raydir.shape[0]), "SR": scene.qopt.SR, "rays_hit": hit, "valid_tuples": T_v,
                       "grid_and_point_cache_build_ms": build_ms, "ms_per_frame": ms, "rays_per_s": raydir.shape[0] / (ms * 1e-3),
                       "max_abs_rgb_subset_vs_full_frame": d_self, "max_abs_rgb_bf16_vs_fp32": d_fp32}))
     assert d_self <= 2e-3 and d_fp32 <= 1e-2
