@@ -10,10 +10,11 @@
 //   prepare  per sample : loc_pers, inverse-distance weights, conf clamp, counts
 //   scan     compaction offsets (tuple <- sample,slot ; compact sample <- sample)
 //   gather   per tuple  : X0 = [emb | PE(emb) | PE(dists)], label embedding, [colour | dir - view | dir.view]
-//   layers   SGEMM (gemm_simt.cuh) with fused bias + LeakyReLU, concat inputs as a second operand pair
+//   layers   GEMMs with fused bias + LeakyReLU, concat inputs as a second operand pair: fp32 SIMT (gemm_simt.cuh, SGN_PRECISION_FP32)
+//            or tcgen05 kind::tf32 (gemm_tc.cuh, SGN_PRECISION_TF32: what training uses by default)
 //   alpha    per tuple  : raw sigma ; ksum per sample : sum_k w conf (sigma, h) ; colour MLP ; rgb
-// The tensor-core (bf16, tcgen05) path lives in agg_tc.cu; this file is the numerically strict one and the
-// one training uses.
+// The fused bf16 tcgen05 inference path lives in agg_tc.cu; this file is the layer-wise one (strict fp32 or TF32 GEMMs), the only
+// one with a backward.
 #include "agg_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
