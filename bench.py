@@ -236,43 +236,18 @@ def run_ours(args):
         h_cam = torch.from_numpy(np.concatenate([s.campos, s.camrotc2w.reshape(-1)])).pin_memory()
         h_out = torch.empty(R, 3).pin_memory()
 
-        # Frames are independent, so the copies of neighbouring steps overlap the kernels: inputs go up on a copy stream into one of two
-        # device buffers (step i + 1 uploads while step i renders), the result comes down on a second copy stream.  Every step still
-        # moves its own inputs and its own result inside the timed region.
-        main = torch.cuda.current_stream()
-        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-        bufs = [dict(ray=torch.empty(R, 3, device=device), cam=torch.empty(12, device=device), free=torch.cuda.Event(), ready=torch.cuda.Event())
-                for _ in range(2)]
-        for b in bufs:
-            b["free"].record(main)
-        e2e_i = [0]
-
-        def e2e_step():
-            b = bufs[e2e_i[0] & 1]
-            e2e_i[0] += 1
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(b["free"])                  # the step that last read this buffer has finished with it
-                b["ray"].copy_(h_ray, non_blocking=True)
-                b["cam"].copy_(h_cam, non_blocking=True)
-                b["ready"].record(s_in)
-            main.wait_event(b["ready"])
-            o = pipeline.render_rays(scene, b["cam"][:3], b["cam"][3:].view(3, 3), b["ray"], s.near, s.far, bg, precision=precision)
-            b["free"].record(main)
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
-                h_out.copy_(o.ray_color, non_blocking=True)
-                o.ray_color.record_stream(s_out)
+        # pipeline.HostFrameRenderer: inputs go up on a copy stream into one of two device buffers (step i + 1 uploads while step i renders),
+        # the result comes down on a second copy stream.  Every step still moves its own inputs and its own result inside the timed region.
+        hfr = pipeline.HostFrameRenderer(scene, R, s.near, s.far, bg, precision=precision)
         for _ in range(2):                                  # untimed: first use after the grid rebuild re-establishes the allocator's blocks
-            e2e_step()
-        main.wait_stream(s_out)
+            hfr.render(h_cam, h_ray, h_out)
+        hfr.wait()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            e2e_step()
-        main.wait_stream(s_out)                             # the last result has landed in host memory
+            hfr.render(h_cam, h_ray, h_out)
+        torch.cuda.current_stream().wait_stream(hfr.s_out)  # the last result has landed in host memory
         e1.record()
         barrier()
         e2e_check = float((h_out.to(device) - out.ray_color).abs().max())      # the frame that came back = the resident steps' frame

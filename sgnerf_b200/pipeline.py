@@ -180,3 +180,48 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
         out.probe = ops.probe_outputs(opacity, loc_w, pidx, weight, conf_coef, rmask, scene.xyz, scene.embedding, scene.color, scene.dirs,
                                       scene.conf)
     return out
+
+
+class HostFrameRenderer:
+    """Frames from host memory to host memory (what a viewer or an evaluation loop does, run/test_ft.py:132-237): the camera and the rays
+    of a frame go up from pinned host buffers on a copy stream into one of two device buffers, the frame is rendered on the current
+    stream, and the colours come down on a second copy stream into the caller's pinned buffer.  Frames are independent, so the upload
+    of frame i + 1 and the download of frame i - 1 overlap the kernels of frame i; `wait()` returns when every submitted result has
+    landed.  Nothing here synchronises the host except `wait()`."""
+
+    def __init__(self, scene, n_rays, near, far, bg_color, precision=ops.PRECISION_BF16):
+        dev = scene.xyz.device
+        self.scene, self.near, self.far, self.precision = scene, float(near), float(far), precision
+        self.bg = torch.as_tensor(bg_color, dtype=torch.float32, device=dev).reshape(3)
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.bufs = [dict(ray=torch.empty(n_rays, 3, device=dev), cam=torch.empty(12, device=dev), free=torch.cuda.Event(), ready=torch.cuda.Event())
+                     for _ in range(2)]
+        for b in self.bufs:
+            b["free"].record(torch.cuda.current_stream(dev))
+        self.i = 0
+
+    def render(self, h_cam, h_raydir, h_out):
+        """h_cam: pinned [12] = campos (3) | camrotc2w (9, row-major); h_raydir: pinned [R,3]; h_out: pinned [R,3], written asynchronously."""
+        main = torch.cuda.current_stream(self.bufs[0]["ray"].device)
+        b = self.bufs[self.i & 1]
+        self.i += 1
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(b["free"])                 # the frame that last read this buffer has finished with it
+            b["ray"].copy_(h_raydir, non_blocking=True)
+            b["cam"].copy_(h_cam, non_blocking=True)
+            b["ready"].record(self.s_in)
+        main.wait_event(b["ready"])
+        with torch.no_grad():
+            o = render_rays(self.scene, b["cam"][:3], b["cam"][3:].view(3, 3), b["ray"], self.near, self.far, self.bg, precision=self.precision)
+        b["free"].record(main)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            h_out.copy_(o.ray_color, non_blocking=True)
+            o.ray_color.record_stream(self.s_out)
+        return o
+
+    def wait(self):
+        torch.cuda.current_stream(self.bufs[0]["ray"].device).wait_stream(self.s_out)
+        self.s_out.synchronize()
