@@ -5,7 +5,9 @@
     C4  large scene: 10M points, 1296x968 raw ScanNet resolution, SR=24, one grid rebuild      -- python tools/bench_shapes.py c4
 
 Each renders the frame with the bf16 tensor-core path (timed), and checks a 2048-ray subset against the fp32 strict path
-(|d rgb| <= 1e-2) and against itself when rendered alone (ray independence / chunking).
+(|d rgb| <= 1e-2) and against itself when rendered alone (ray independence / chunking).  Under torchrun (WORLD_SIZE > 1) the ONE frame
+is also rendered ray-sharded over all ranks (tiles of 256 rays round-robin, image assembled with one all-reduce) and compared with the
+single-GPU frame:  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_shapes.py c3
 """
 import json
 import os
@@ -19,8 +21,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    from sgnerf_b200 import dist as sdist
     from sgnerf_b200 import ops, pipeline, synth
-    dev = "cuda:0"
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(dev))
     if which == "c3":
         n, room, w, h, qo = 3_000_000, (3.0, 3.0, 3.0), 800, 800, dict(vsize=(0.004,) * 3, P=9, SR=200)
     else:
@@ -55,8 +62,30 @@ def main():
         torch.cuda.synchronize()
         d_self = float((sub16.ray_color - o2.ray_color[sel]).abs().max())
         d_fp32 = float((sub16.ray_color - sub32.ray_color).abs().max())
+    shard = None
+    if world > 1:
+        # ONE frame over all ranks (BASELINE config "ray-sharded across 8 B200"): every rank renders its tiles of 256 consecutive rays
+        # (dealt round-robin so hit and miss regions spread evenly), the frame is assembled on every rank with one all-reduce of the
+        # [R,3] image (shards are disjoint); point cloud and grid replicated.  ms = max over ranks, device time.
+        with torch.no_grad():
+            idx = sdist.shard_rays(raydir.shape[0], rank, world, tile=256).to(dev)
+            mine = raydir[idx].contiguous()
+            for _ in range(2):
+                part = pipeline.render_rays(scene, campos, rot, mine, s.near, s.far, bg, precision=ops.PRECISION_BF16)
+                frame = sdist.gather_frame(part.ray_color, idx, raydir.shape[0])
+            torch.cuda.synchronize(); torch.distributed.barrier()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(3):
+                part = pipeline.render_rays(scene, campos, rot, mine, s.near, s.far, bg, precision=ops.PRECISION_BF16)
+                frame = sdist.gather_frame(part.ray_color, idx, raydir.shape[0])
+            b.record(); torch.cuda.synchronize()
+            tms = torch.tensor([a.elapsed_time(b) / 3], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+            shard = {"ranks": world, "ms_per_frame": float(tms[0]), "rays_per_s": raydir.shape[0] / (float(tms[0]) * 1e-3),
+                     "speedup_vs_one_gpu": ms / float(tms[0]), "max_abs_vs_single_gpu_frame": float((frame - o2.ray_color).abs().max())}
     edit = None
-    if which == "c4":
+    if which == "c4" and world == 1:
         # between steps prune the 2 % lowest-confidence points and grow 1 % new ones; the grid and the per-point
         # first-layer tables are rebuilt, and all of it is inside the timed step
         with torch.no_grad():
@@ -79,10 +108,14 @@ def main():
                 ms_e.append(a.elapsed_time(b))
             edit = {"what": "prune 2 % lowest confidence + grow 1 % + grid rebuild + per-point tables + full frame", "ms_per_step": ms_e,
                     "points_after": int(scene.xyz.shape[0]), "rays_hit": int(o3.ray_mask.sum())}
-    print(json.dumps({"config": which, "grow_prune_step": edit, "points": n, "rays": int(raydir.shape[0]), "SR": scene.qopt.SR, "rays_hit": hit, "valid_tuples": T_v,
+    if rank == 0:
+      print(json.dumps({"config": which, "grow_prune_step": edit, "sharded_frame": shard, "points": n, "rays": int(raydir.shape[0]), "SR": scene.qopt.SR, "rays_hit": hit, "valid_tuples": T_v,
                       "grid_and_point_cache_build_ms": build_ms, "ms_per_frame": ms, "rays_per_s": raydir.shape[0] / (ms * 1e-3),
                       "max_abs_rgb_subset_vs_full_frame": d_self, "max_abs_rgb_bf16_vs_fp32": d_fp32}))
     assert d_self <= 2e-3 and d_fp32 <= 1e-2
+    assert shard is None or shard["max_abs_vs_single_gpu_frame"] <= 1e-4      # same kernels, different tile packing of the rays
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
