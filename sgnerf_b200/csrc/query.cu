@@ -12,19 +12,8 @@
 // slots come out in the same order as the sequential reference, ties included.  Candidates of a voxel
 // are consecutive float4 (x,y,z,index) records, so the inner loop is one 16-byte load per candidate.
 #include "common.cuh"
+#include "grid.cuh"
 
-struct SgnGrid {
-    SgnGridCfg cfg;
-    int64_t N, vol;
-    int32_t* cell_slot;
-    uint32_t* occ_bits;
-    int32_t* slot_coor;
-    int32_t* slot_count;
-    int32_t* slot_start;
-    float4* cand;
-    int32_t* counters;
-    uint32_t* coarse_bits;
-};
 
 namespace sgn {
 
