@@ -106,7 +106,7 @@ static inline size_t carve_ws(const AggPlan& P, int64_t Rc, int SR, int K, bool 
     ws->svalid = A.take<int32_t>(S + 1);
     ws->tuple_start = A.take<int32_t>(S + 1);
     ws->sample_cidx = A.take<int32_t>(S + 1);
-    ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
+    ws->partials = A.take<int32_t>(2 * scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1);
     ws->csample = A.take<int32_t>(S + 1);
     ws->loc_pers = A.take<float>(S * 3);

@@ -76,8 +76,8 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     SGN_CUDA(cudaMemsetAsync(decoded, 0, sizeof(float) * 4 * (size_t)S, st));
     launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, ws.weight_n, weight_out, conf_out, ray_valid, ws.nvalid, ws.svalid);
     int rc;
-    if ((rc = exclusive_scan_i32(ws.nvalid, ws.tuple_start, S, ws.partials, st))) return rc;
-    if ((rc = exclusive_scan_i32(ws.svalid, ws.sample_cidx, S, ws.partials, st))) return rc;
+    // compaction offsets of the tuples (scan of nvalid) and of the samples with a neighbour (scan of nvalid > 0), one pass
+    if ((rc = exclusive_scan_pair_i32(ws.nvalid, ws.tuple_start, ws.sample_cidx, S, ws.partials, st))) return rc;
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
     launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);

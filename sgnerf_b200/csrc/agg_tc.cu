@@ -1185,7 +1185,7 @@ static size_t tc_carve(const AggPlan& P, int64_t N, int64_t Rc, int SR, int K, v
     const size_t S = (size_t)Rc * SR, T = S * K;
     ws->nvalid = A.take<int32_t>(S + 1); ws->svalid = A.take<int32_t>(S + 1);
     ws->tuple_start = A.take<int32_t>(S + 1); ws->sample_cidx = A.take<int32_t>(S + 1);
-    ws->partials = A.take<int32_t>(scan_partials_count((int64_t)S));
+    ws->partials = A.take<int32_t>(2 * scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1); ws->csample = A.take<int32_t>(S + 1);
     ws->ntiles = A.take<int32_t>(4);
     const size_t ncap = T / tile_width(K) + 1;            // upper bound of the number of tiles
@@ -1433,8 +1433,8 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         SGN_CUDA(cudaMemsetAsync(dec, 0, sizeof(float) * 4 * (size_t)S, st));
         launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, (float*)nullptr, weight_out ? weight_out + r0 * SR * K : nullptr,
                conf_out ? conf_out + r0 * SR * K : nullptr, ray_valid + r0 * SR, ws.nvalid, ws.svalid);
-        if ((rc = exclusive_scan_i32(ws.nvalid, ws.tuple_start, S, ws.partials, st))) return rc;
-        if ((rc = exclusive_scan_i32(ws.svalid, ws.sample_cidx, S, ws.partials, st))) return rc;
+        // compaction offsets of the tuples (scan of nvalid) and of the samples with a neighbour (scan of nvalid > 0), one pass
+        if ((rc = exclusive_scan_pair_i32(ws.nvalid, ws.tuple_start, ws.sample_cidx, S, ws.partials, st))) return rc;
         const int32_t* T_ptr = ws.tuple_start + S;
         const int32_t* S_ptr = ws.sample_cidx + S;
         launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);

@@ -116,6 +116,83 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* part
     return SGN_OK;
 }
 
+// ---- pair scan: out_sum = exclusive scan of in, out_cnt = exclusive scan of (in > 0), one pass over `in` for both.
+// partials holds 2 * (nb + 1) ints: the sums, then the counts.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_pair_reduce_kernel(const int32_t* __restrict__ in, int64_t n, int32_t* partials, int nb)
+{
+    __shared__ int sm[SCAN_THREADS / 32 + 1];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    int s = 0, c = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++)
+        if (base + i < n) { const int v = in[base + i]; s += v; c += v > 0; }
+    int total;
+    block_exclusive_scan(s, &total, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+    block_exclusive_scan(c, &total, sm);
+    if (threadIdx.x == 0) partials[nb + 1 + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_pair_partials_kernel(int32_t* partials, int nb)
+{
+    __shared__ int sm[SCAN_THREADS / 32 + 1];
+    for (int which = 0; which < 2; which++) {
+        int32_t* p = partials + which * (nb + 1);
+        int carry = 0;
+        for (int base = 0; base < nb; base += SCAN_THREADS) {
+            int i = base + threadIdx.x;
+            int v = i < nb ? p[i] : 0;
+            int total;
+            int e = block_exclusive_scan(v, &total, sm);
+            if (i < nb) p[i] = carry + e;
+            carry += total;
+        }
+        if (threadIdx.x == 0) p[nb] = carry;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_pair_apply_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out_sum,
+                                                                        int32_t* __restrict__ out_cnt, int64_t n,
+                                                                        const int32_t* __restrict__ partials, int nb)
+{
+    __shared__ int sm[SCAN_THREADS / 32 + 1];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    int v[SCAN_PER_THREAD];
+    int s = 0, c = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+        c += v[i] > 0;
+    }
+    int total;
+    int es = block_exclusive_scan(s, &total, sm) + partials[blockIdx.x];
+    int ec = block_exclusive_scan(c, &total, sm) + partials[nb + 1 + blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        if (base + i < n) { out_sum[base + i] = es; out_cnt[base + i] = ec; }
+        es += v[i];
+        ec += v[i] > 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out_sum[n] = partials[nb]; out_cnt[n] = partials[2 * nb + 1]; }
+}
+
+int exclusive_scan_pair_i32(const int32_t* in, int32_t* out_sum, int32_t* out_cnt, int64_t n, int32_t* partials, cudaStream_t st)
+{
+    int nb = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    if (nb == 0) {
+        SGN_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(int32_t), st));
+        SGN_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int32_t), st));
+        return SGN_OK;
+    }
+    launch(scan_pair_reduce_kernel, nb, SCAN_THREADS, 0, st, in, n, partials, nb);
+    launch(scan_pair_partials_kernel, 1, SCAN_THREADS, 0, st, partials, nb);
+    launch(scan_pair_apply_kernel, nb, SCAN_THREADS, 0, st, in, out_sum, out_cnt, n, partials, nb);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
 }  // namespace sgn
 
 extern "C" const char* sgn_last_error(void) { return sgn::g_err; }

@@ -54,6 +54,8 @@ struct Arena {
 constexpr int SCAN_TILE = 2048;
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* partials, cudaStream_t st);
 static inline size_t scan_partials_count(int64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE + 1); }
+// The same for two scans of one input in one pass: out_sum = scan of in, out_cnt = scan of (in > 0); partials: 2 * scan_partials_count(n).
+int exclusive_scan_pair_i32(const int32_t* in, int32_t* out_sum, int32_t* out_cnt, int64_t n, int32_t* partials, cudaStream_t st);
 
 // Every kernel launch of the library goes through launch(): it counts launches (sgn_launch_count) so a
 // caller can state how many of OUR kernels ran inside a timed region.
