@@ -78,6 +78,7 @@ class TrainStep:
 
     def step(self):
         """One training step on the inputs last given to set_inputs.  Returns nothing; self.loss / self.n_hit are device scalars."""
+        self.scene.invalidate_point_cache()      # embeddings and weights are about to change: the bf16 path's per-point tables are stale
         if not self.use_graph:
             self._body()
             return
