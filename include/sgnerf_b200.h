@@ -232,11 +232,13 @@ int sgn_fill_invalid(const int8_t* ray_mask, const float* bg /*[3]*/, int64_t R,
 
 /* Inference frame tail in one kernel: sgn_ray_dist -> sgn_composite_forward -> sgn_fill_invalid with the same results
  * (neural_points_volumetric_model.py:569-577, diff_ray_marching.py:509-555, neural_points_volumetric_model.py:158-195) and none
- * of the intermediate tensors.  ray_mask may be NULL (no fill); ray_color / opacity / bg_transmission may be NULL. */
+ * of the intermediate tensors.  ray_mask may be NULL (no fill); ray_color / opacity / bg_transmission / depth may be NULL.
+ * depth [R] = sum_i w_i z_i / (sum_i w_i + 1e-6) with w = opacity * acc_transmission and z the samples' camera depth
+ * (`coarse_depth`, neural_points_volumetric_model.py:620-624); 0 for rays that missed. */
 int sgn_render_composite(const float* decoded /*[R,SR,4]*/, const float* loc_pers /*[R,SR,3]*/, const uint8_t* ray_valid /*[R,SR]*/,
                          const int8_t* ray_mask /*[R]*/, float vsize_z, int raydist_mode_unit, const float* bg /*[3]*/, int blend,
                          int64_t R, int SR, float* ray_color /*[R,3]*/, float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/,
-                         void* stream);
+                         float* depth /*[R]*/, void* stream);
 
 /* `prob == 1` outputs of NeuralPointsRayMarching.forward (neural_points_volumetric_model.py:633-656), the inputs of probe_hole / point
  * growing (run/train_ft.py:425-540): per ray the first sample of largest opacity, its world position, the distance to its nearest

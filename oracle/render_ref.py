@@ -277,7 +277,11 @@ def render_from_query(P, cfg, tables, sample_pidx, sample_loc, sample_loc_w, sam
     ray_dist = ray_dist_from_samples(sample_loc, ray_valid, float(vsize[2]))
     rm = ray_march(ray_dist, ray_valid, decoded, bg_color)
     color, op, is_bg = fill_invalid(ray_mask, rm[0], rm[2], rm[5], bg_color)
-    return SimpleNamespace(coarse_raycolor=color, coarse_point_opacity=op, coarse_is_background=is_bg,
+    # :620-624 (return_depth): avg_depth = sum(w ray_ts) / (sum(w) + 1e-6), w = opacity * acc_transmission.  The reference's
+    # forward never defines `ray_ts` (the branch is dead there); upstream Point-NeRF feeds the samples' camera depth, used here.
+    w_alpha = rm[2] * rm[3]
+    depth = (w_alpha * sample_loc[..., 2]).sum(-1) / (w_alpha.sum(-1) + 1e-6)
+    return SimpleNamespace(coarse_raycolor=color, coarse_point_opacity=op, coarse_is_background=is_bg, coarse_depth=depth,
                            decoded=decoded, ray_valid=ray_valid, weight=weight, conf_coefficient=conf,
                            ray_dist=ray_dist, ray_color=rm[0], opacity=rm[2], acc_transmission=rm[3],
                            blend_weight=rm[4], bg_transmission=rm[5])

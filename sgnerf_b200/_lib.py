@@ -75,7 +75,8 @@ SIGNATURES = {
                                       c_void, c_void, c_void]),
     "sgn_composite_backward": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_int, c_void, c_void, c_void,
                                        c_void, c_void, c_void]),
-    "sgn_render_composite": (c_int, [c_void, c_void, c_void, c_void, c_f32, c_int, c_void, c_int, c_i64, c_int, c_void, c_void, c_void, c_void]),
+    "sgn_render_composite": (c_int, [c_void, c_void, c_void, c_void, c_f32, c_int, c_void, c_int, c_i64, c_int, c_void, c_void, c_void, c_void,
+                                     c_void]),
     "sgn_probe_outputs": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, C.POINTER(SgnPointTables), c_int, c_i64, c_int, c_int,
                                   c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void]),
     "sgn_fill_invalid": (c_int, [c_void, c_void, c_i64, c_int, c_void, c_void, c_void, c_void]),

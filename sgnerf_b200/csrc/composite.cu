@@ -211,7 +211,7 @@ template <int BLEND>
 __global__ void __launch_bounds__(COMP_WARPS * 32)
 render_composite_kernel(const float4* __restrict__ decoded, const float* __restrict__ loc_pers, const uint8_t* __restrict__ valid,
                         const int8_t* __restrict__ ray_mask, float vsize_z, int mode_unit, const float* __restrict__ bg, int64_t R, int SR,
-                        float* __restrict__ ray_color, float* __restrict__ opacity, float* __restrict__ bg_t)
+                        float* __restrict__ ray_color, float* __restrict__ opacity, float* __restrict__ bg_t, float* __restrict__ depth)
 {
     const int lane = lane_id();
     const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
@@ -224,10 +224,11 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
             if (lane == 0) {
                 if (ray_color) { ray_color[r * 3] = b0; ray_color[r * 3 + 1] = b1; ray_color[r * 3 + 2] = b2; }
                 if (bg_t) bg_t[r] = 1.0f;
+                if (depth) depth[r] = 0.f;
             }
             continue;
         }
-        float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, zcarry = -INFINITY;
+        float carry = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, zcarry = -INFINITY, dsum = 0.f, wsum = 0.f;
         for (int base = 0; base < SR; base += 32) {
             const int s = base + lane;
             const bool act = s < SR;
@@ -258,10 +259,12 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
             if (act) {
                 if (opacity) opacity[i] = o;
                 cr += f.y * w; cg += f.z * w; cb += f.w * w;
+                dsum += (o * T) * z; wsum += o * T;           // depth: opacity * acc_transmission weights whatever the blend (:621)
             }
             carry *= __shfl_sync(0xffffffffu, incl, 31);
         }
         cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+        if (depth) { dsum = warp_sum(dsum); wsum = warp_sum(wsum); }
         if (lane == 0) {
             if (ray_color) {
                 ray_color[r * 3 + 0] = cr + b0 * carry;
@@ -269,6 +272,7 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
                 ray_color[r * 3 + 2] = cb + b2 * carry;
             }
             if (bg_t) bg_t[r] = carry;
+            if (depth) depth[r] = dsum / (wsum + 1e-6f);
         }
     }
 }
@@ -412,7 +416,7 @@ extern "C" int sgn_composite_backward(const float* decoded, const float* ray_dis
 
 extern "C" int sgn_render_composite(const float* decoded, const float* loc_pers, const uint8_t* ray_valid, const int8_t* ray_mask, float vsize_z,
                                     int raydist_mode_unit, const float* bg, int blend, int64_t R, int SR, float* ray_color, float* opacity,
-                                    float* bg_transmission, void* stream)
+                                    float* bg_transmission, float* depth, void* stream)
 {
     SGN_CHECK_ARG(R >= 0 && SR > 0 && SR <= 32 * COMP_MAX_CHUNKS, "sgn_render_composite: SR=%d out of range", SR);
     SGN_CHECK_ARG(blend == 0 || blend == 1, "sgn_render_composite: blend must be 0 (alpha) or 1 (alpha2)");
@@ -421,10 +425,10 @@ extern "C" int sgn_render_composite(const float* decoded, const float* loc_pers,
     auto st = (cudaStream_t)stream;
     if (blend == 0)
         launch(render_composite_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
-                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission);
+                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
     else
         launch(render_composite_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
-                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission);
+                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

@@ -214,7 +214,8 @@ def composite(decoded, ray_dist_, ray_valid, bg_color=None, blend=0):
 
 def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, blend=0, raydist_mode_unit=1):
     """Inference tail of a frame in one kernel (no autograd): ray_dist -> composite -> fill_invalid.
-    Returns ray_color [R,3], opacity [R,SR], bg_transmission [R] -- the values the three separate calls give."""
+    Returns ray_color [R,3], opacity [R,SR], bg_transmission [R] -- the values the three separate calls give -- and depth [R]
+    (`coarse_depth`: opacity * transmittance weighted camera depth of the samples, 0 for rays that missed)."""
     decoded = _dev(decoded.detach(), torch.float32, "decoded")
     loc_pers = _dev(loc_pers, torch.float32, "loc_pers")
     valid = _dev(ray_valid, torch.uint8, "ray_valid")
@@ -223,10 +224,11 @@ def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, 
     ray_color = torch.empty(R, 3, dtype=torch.float32, device=dev)
     opacity = torch.empty(R, SR, dtype=torch.float32, device=dev)
     bgt = torch.empty(R, dtype=torch.float32, device=dev)
+    depth = torch.empty(R, dtype=torch.float32, device=dev)
     _lib.call("sgn_render_composite", _ptr(decoded), _ptr(loc_pers), _ptr(valid), _ptr(_dev(ray_mask, torch.int8, "ray_mask")), float(vsize_z),
               int(raydist_mode_unit), _ptr(_dev(bg_color.reshape(3), torch.float32, "bg")), int(blend), R, SR, _ptr(ray_color), _ptr(opacity),
-              _ptr(bgt), _stream())
-    return ray_color, opacity, bgt
+              _ptr(bgt), _ptr(depth), _stream())
+    return ray_color, opacity, bgt, depth
 
 
 def probe_outputs(opacity, sample_loc_w, sample_pidx, weight, conf_coef, ray_mask, xyz, embedding, color, dirs, conf):

@@ -153,7 +153,7 @@ def scene_from_checkpoint(checkpoint, qopt=None, device="cuda", label_emb=None, 
 def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision=ops.PRECISION_FP32, t=None, want_aux=False,
                 use_point_cache=True, probe=False):
     """Render R rays (device tensors).  Returns a namespace with ray_color [R,3] (misses = bg), ray_mask int8 [R],
-    opacity [R,SR], bg_transmission [R] and, with want_aux, the intermediate tensors.  probe=True adds `probe`, the reference's
+    opacity [R,SR], bg_transmission [R], depth [R] (`coarse_depth`, 0 for misses) and, with want_aux, the intermediate tensors.  probe=True adds `probe`, the reference's
     `prob == 1` outputs (ray_max_* / shading_avg_*, neural_points_volumetric_model.py:633-656) that point growing reads."""
     want_aux = want_aux or probe
     q = scene.qopt
@@ -167,12 +167,14 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
         point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None)
     if not want_aux and not decoded.requires_grad:
         # inference: step sizes, compositing and fill_invalid in one kernel, no intermediate tensors
-        ray_color, opacity, bgt = ops.render_composite(decoded, loc_pers, ray_valid, rmask, hp.vsize[2], bg_color, blend=0)
-        return SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt)
+        ray_color, opacity, bgt, depth = ops.render_composite(decoded, loc_pers, ray_valid, rmask, hp.vsize[2], bg_color, blend=0)
+        return SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt, depth=depth)
     rd = ops.ray_dist(loc_pers, ray_valid, hp.vsize[2], 1)
     ray_color, opacity, acc, bw, bgt = ops.composite(decoded, rd, ray_valid, bg_color, blend=0)
     ops.fill_invalid(rmask, bg_color, ray_color, opacity, bgt)
-    out = SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt)
+    w_alpha = (opacity * acc).detach()                     # coarse_depth (neural_points_volumetric_model.py:620-624), after fill_invalid: 0 for misses
+    depth = (w_alpha * loc_pers[..., 2]).sum(-1) / (w_alpha.sum(-1) + 1e-6) * (rmask > 0)
+    out = SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt, depth=depth)
     if want_aux:
         out.__dict__.update(pidx=pidx, loc_w=loc_w, sample_mask=smask, decoded=decoded, ray_valid=ray_valid, loc_pers=loc_pers,
                             weight=weight, conf_coef=conf_coef, ray_dist=rd, blend_weight=bw, acc_transmission=acc)

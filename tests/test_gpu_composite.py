@@ -131,5 +131,10 @@ def test_fused_frame_tail_equals_three_kernels(R, SR, blend):
     rd = ops.ray_dist(loc, valid, 0.008, 1)
     color, opacity, _, _, bgt = ops.composite(dec, rd, valid, bg, blend=blend)
     ops.fill_invalid(mask, bg, color, opacity, bgt)
-    f_color, f_opacity, f_bgt = ops.render_composite(dec, loc, valid, mask, 0.008, bg, blend=blend)
+    color, opacity, acc, _, bgt = ops.composite(dec, rd, valid, bg, blend=blend)
+    w_alpha = opacity * acc
+    want_depth = (w_alpha * loc[..., 2]).sum(-1) / (w_alpha.sum(-1) + 1e-6) * (mask > 0)
+    ops.fill_invalid(mask, bg, color, opacity, bgt)
+    f_color, f_opacity, f_bgt, f_depth = ops.render_composite(dec, loc, valid, mask, 0.008, bg, blend=blend)
     assert torch.equal(f_color, color) and torch.equal(f_opacity, opacity) and torch.equal(f_bgt, bgt)
+    torch.testing.assert_close(f_depth, want_depth, rtol=0, atol=1e-5)
