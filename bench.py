@@ -183,13 +183,17 @@ def run_ours(args):
             agg_ms.append(a.elapsed_time(b))
         agg_ms = float(np.mean(agg_ms[1:]))
         # ---- the HBM-bound stages on their own (SURVEY.md section 8d byte formulas): query (march + knn) and the frame tail
-        def timed_ms(fn, n=max(3, args.steps)):
-            ms = []
+        def timed_ms(fn, n=10):
+            """Device time per call: n calls queued back to back between one pair of events (a single call of a ~100 us stage would
+            time the host-side launch gap, not the kernels)."""
+            r = fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
             for _ in range(n):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); r = fn(); b.record(); torch.cuda.synchronize()
-                ms.append(a.elapsed_time(b))
-            return float(np.mean(ms[1:])), r
+                r = fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / n, r
         query_ms, _ = timed_ms(lambda: ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2))
         dec_, val_, lp_, _, _ = ops.aggregate(scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs,
                                               scene.conf, None, pidx, loc_w, raydir, campos, rot, precision=precision, want_aux=False)
