@@ -77,3 +77,11 @@ def test_cpu_tensors_are_rejected(built_lib):
     from sgnerf_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.composite(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.ones(2, 4, dtype=torch.bool))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/sgnerf_b200.h is the C-ABI contract: it must compile as C99 on its own (no C++ or CUDA types in the signatures) and a C
+    program must link against the shared library with nothing but the header."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "sgnerf_b200.h"\nint main(void) { return sgn_version() >= 100 && sgn_last_error() != 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "use.o")])
