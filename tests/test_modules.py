@@ -170,3 +170,18 @@ def test_scene_from_reference_checkpoint_renders_like_the_modules_state():
     with torch.no_grad():
         ra, rb = pipeline.render_rays(a, *args), pipeline.render_rays(b, *args)
     assert torch.equal(ra.ray_color, rb.ray_color) and torch.equal(ra.ray_mask, rb.ray_mask) and int(ra.ray_mask.sum()) > 20
+
+
+def test_depth_candidates_match_the_oracle_ray_generation():
+    """pipeline.middle_point_ts (host-side torch: the depth candidates the query kernel consumes) is bit for bit the oracle's
+    near_far_linear_ray_generation (diff_ray_marching.py:349-393, itself pinned to the reference by tests/golden/pe_rays.npz)."""
+    from sgnerf_b200 import pipeline
+    for near, far, D in ((0.1, 8.0, 400), (2.0, 6.0, 400), (0.5, 3.0, 97)):
+        _, mid = qr.near_far_linear_ray_generation(torch.zeros(1, 3), torch.zeros(1, 1, 3), D, near, far, jitter=0.0)
+        assert torch.equal(pipeline.middle_point_ts(near, far, D, "cpu"), mid[0, 0])
+    # with jitter: same formula given the same uniform draws
+    g1, g2 = torch.Generator().manual_seed(3), torch.Generator().manual_seed(3)
+    t = pipeline.middle_point_ts(0.1, 8.0, 400, "cpu", jitter=0.3, n_rays=7, generator=g1)
+    rand = torch.rand((1, 7, 400), generator=g2)
+    _, mid = qr.near_far_linear_ray_generation(torch.zeros(1, 3), torch.zeros(1, 7, 3), 400, 0.1, 8.0, jitter=0.3, rand=rand)
+    assert torch.equal(t, mid[0])
