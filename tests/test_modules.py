@@ -185,3 +185,20 @@ def test_depth_candidates_match_the_oracle_ray_generation():
     rand = torch.rand((1, 7, 400), generator=g2)
     _, mid = qr.near_far_linear_ray_generation(torch.zeros(1, 3), torch.zeros(1, 7, 3), 400, 0.1, 8.0, jitter=0.3, rand=rand)
     assert torch.equal(t, mid[0])
+
+
+def test_grid_hyperparameters_match_the_oracle():
+    """ops.grid_hyperparameters (host logic of lighting_fast_querier.get_hyperparameters, :66-92) against the oracle's literal
+    restatement: grid origin / far corner, scaled voxel size, voxel counts and radius, bit for bit, for several clouds and options."""
+    from sgnerf_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    for n, scale, vsize, ranges in ((5000, 3.0, [0.008] * 3, [-10.0] * 3 + [10.0] * 3), (777, 12.0, [0.016, 0.016, 0.008], [-2.0, -3.0, -1.0, 2.5, 3.0, 1.5]),
+                                    (100, 0.3, [0.004] * 3, None)):
+        xyz = (torch.rand(1, n, 3, generator=g) - 0.5) * scale
+        opt = qr.default_opt(vsize=vsize, ranges=ranges, radius_limit_scale=4.0)
+        a = qr.get_hyperparameters(opt, xyz)
+        b = ops.grid_hyperparameters(xyz[0], opt.vsize, opt.vscale, opt.kernel_size, opt.ranges, opt.radius_limit_scale)
+        assert np.array_equal(a.ranges.view(np.int32), b.ranges.view(np.int32))
+        assert np.array_equal(a.scaled_vsize.view(np.int32), b.scaled_vsize.view(np.int32))
+        assert np.array_equal(a.scaled_vdim, b.scaled_vdim)
+        assert np.float32(a.radius2).tobytes() == np.float32(b.radius2).tobytes()
