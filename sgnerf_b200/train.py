@@ -17,6 +17,10 @@ from . import ops, pipeline
 
 
 class TrainStep:
+    """One training iteration as a replayable unit.  set_inputs() copies a batch into static device buffers, step() runs it.
+    With use_graph=True the first step() call runs three ordinary (eager) steps on the current inputs -- they allocate the optimiser
+    state and set kernel attributes, and they are real optimiser steps -- then captures the step and replays the capture from then on."""
+
     def __init__(self, scene, n_rays, near, far, bg_color, lr=5e-4, plr=2e-3, conf_loss_weight=1e-4, precision=ops.PRECISION_TF32,
                  use_graph=True, train_dir=True, group=None):
         """scene: pipeline.RenderScene (its tensors become the trainable leaves).  n_rays: rays per step on this rank (fixed)."""

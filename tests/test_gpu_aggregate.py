@@ -336,3 +336,34 @@ def test_tf32_training_path_vs_fp32(R, SR, semantic):
         a, b = g_a[k].double().flatten(), g_b[k].double().flatten()
         cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
         assert cos > 0.99 and rel_l2(g_b[k], g_a[k]) < 0.12, (k, cos, rel_l2(g_b[k], g_a[k]))
+
+
+@pytest.mark.parametrize("precision", [ops.PRECISION_FP32, ops.PRECISION_TF32])
+def test_training_path_with_no_valid_tuple(precision):
+    """Edge case: no sample has a neighbour (M = 0 for every GEMM, read from the device): forward gives zeros, backward gives zero
+    gradients and nothing hangs or faults -- and a single valid tuple (M = 1, one partial tile) matches between the two arithmetics."""
+    cfg = rr.agg_config()
+    N, R, SR, K = 500, 9, 24, 8
+    tables, pidx, loc_w, raydir, campos, rot = _random_case(cfg, N, R, SR, K, seed=5)
+    P = rr.init_params(cfg, seed=1, bias_scale=0.1)
+
+    def run(pi):
+        names, W, B = param_lists(P, cfg, requires_grad=True)
+        emb = tables.embedding.clone().cuda().requires_grad_(True)
+        dec, valid, _, w, conf = ops.aggregate(cfg_to_c(cfg), W, B, tables.xyz.cuda(), emb, tables.color.cuda(), tables.dir.cuda(), tables.conf.cuda(),
+                                               None, pi.cuda(), loc_w.cuda(), raydir.cuda(), campos.cuda(), rot.cuda(), precision=precision)
+        (dec.sum() + 0.0 * conf.sum()).backward()
+        torch.cuda.synchronize()
+        return dec.detach(), valid, emb.grad, [x.grad for x in W]
+
+    empty = torch.full_like(pidx, -1)
+    dec, valid, g_emb, g_w = run(empty)
+    assert float(dec.abs().max()) == 0.0 and int(valid.sum()) == 0
+    assert float(g_emb.abs().max()) == 0.0 and all(float(g.abs().max()) == 0.0 for g in g_w)
+    one = empty.clone()
+    one[3, 7, 0] = 11
+    dec1, valid1, g_emb1, g_w1 = run(one)
+    assert int(valid1.sum()) == 1 and float(dec1[3, 7].abs().max()) > 0 and float(g_emb1[0, 11].abs().max()) > 0
+    rest = g_emb1.clone()
+    rest[0, 11] = 0.0
+    assert float(rest.abs().max()) == 0.0                                        # only the gathered point receives a gradient
