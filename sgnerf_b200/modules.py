@@ -12,6 +12,7 @@ wcoord_query=1, near_far_linear ray generation, radiance render, alpha/alpha2 bl
 runs in libsgnerf_b200.so -- there is no PyTorch fallback, CPU tensors are rejected.
 """
 import math
+import time
 from types import SimpleNamespace
 
 import numpy as np
@@ -23,6 +24,53 @@ from . import ops, pipeline
 
 def _opt(opt, name, default):
     return getattr(opt, name, default)
+
+
+def _register_flags(parser, table):
+    """Add the reference's command-line flags (name, type, default, nargs) to `parser`; a flag another class already added
+    (argparse raises on duplicates) is left as it is, as happens when both the reference's and these classes are imported."""
+    have = set(parser._option_string_actions)
+    for name, typ, default, nargs in table:
+        if "--" + name in have:
+            continue
+        kw = dict(type=typ, default=default, help=f"{name} (same flag as the reference)")
+        if nargs is not None:
+            kw["nargs"] = nargs
+        parser.add_argument("--" + name, **kw)
+    return parser
+
+
+# Flags of NeuralPoints.modify_commandline_options (models/neural_points/neural_points.py:80-309): same names, types, defaults, nargs.
+# `wcoord_query` is declared int with the STRING default '0' in the reference (argparse converts string defaults through `type`).
+NEURAL_POINTS_FLAGS = (
+    ("semantic_guidance", int, 0, None), ("load_points", int, 1, None), ("point_noise", str, "", None), ("num_point", int, 8192, None),
+    ("construct_res", int, 0, None), ("grid_res", int, 0, None), ("cloud_path", str, "", None), ("shpnt_jitter", str, "passfunc", None),
+    ("point_features_dim", int, 64, None), ("gpu_maxthr", int, 1024, None), ("z_depth_dim", int, 400, None), ("SR", int, 24, None),
+    ("K", int, 32, None), ("max_o", int, None, None), ("P", int, 16, None), ("NN", int, 0, None), ("radius_limit_scale", float, 5.0, None),
+    ("depth_limit_scale", float, 1.3, None), ("default_conf", float, -1.0, None), ("vscale", int, (2, 2, 1), "+"),
+    ("kernel_size", int, (7, 7, 1), "+"), ("query_size", int, (0, 0, 0), "+"), ("xyz_grad", int, 0, None), ("feat_grad", int, 1, None),
+    ("conf_grad", int, 1, None), ("color_grad", int, 1, None), ("bp_embedding_grad", int, 0, None), ("dir_grad", int, 0, None),
+    ("feedforward", int, 0, None), ("inverse", int, 0, None), ("point_conf_mode", str, "0", None), ("point_color_mode", str, "0", None),
+    ("point_dir_mode", str, "0", None), ("vsize", float, (0.005, 0.005, 0.005), "+"), ("wcoord_query", int, "0", None),
+    ("ranges", float, (-100.0, -100.0, -100.0, 100.0, 100.0, 100.0), "+"),
+)
+
+# Flags of PointAggregator.modify_commandline_options (models/aggregators/point_aggregators.py:15-253).
+POINT_AGGREGATOR_FLAGS = (
+    ("feature_init_method", str, "rand", None), ("which_agg_model", str, "viewmlp", None), ("agg_distance_kernel", str, "quadric", None),
+    ("sh_degree", int, 4, None), ("sh_dist_func", str, "sh_quadric", None), ("sh_act", str, "sigmoid", None),
+    ("agg_axis_weight", float, None, "+"), ("agg_dist_pers", int, 1, None), ("apply_pnt_mask", int, 1, None), ("modulator_concat", int, 0, None),
+    ("agg_intrp_order", int, 0, None), ("shading_feature_mlp_layer0", int, 0, None), ("shading_feature_mlp_layer1", int, 2, None),
+    ("shading_feature_mlp_layer2", int, 0, None), ("shading_feature_mlp_layer2_bpnet", int, 0, None), ("shading_feature_mlp_layer3", int, 0, None),
+    ("shading_feature_mlp_layer4", int, 1, None), ("shading_feature_mlp_linear", int, 0, None), ("shading_feature_num", int, 256, None),
+    ("point_hyper_dim", int, 256, None), ("shading_alpha_mlp_layer", int, 1, None), ("shading_color_mlp_layer", int, 1, None),
+    ("shading_color_channel_num", int, 3, None), ("num_feat_freqs", int, 0, None), ("num_hyperfeat_freqs", int, 0, None),
+    ("dist_xyz_freq", int, 2, None), ("dist_xyz_deno", float, 0, None), ("weight_xyz_freq", int, 2, None), ("weight_feat_dim", int, 8, None),
+    ("agg_weight_norm", int, 1, None), ("view_ori", int, 0, None), ("agg_feat_xyz_mode", str, "None", None),
+    ("agg_alpha_xyz_mode", str, "None", None), ("agg_color_xyz_mode", str, "None", None), ("act_type", str, "ReLU", None),
+    ("act_super", int, 1, None), ("predict_semantic", int, 0, None), ("layers_2d", int, 34, None), ("classes", int, 20, None),
+    ("arch_3d", str, "MinkUNet18A", None), ("bpnetweight", str, "../bpnetInitmodel/bpnet_5cm.pth.tar", None),
+)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -42,11 +90,43 @@ class GatheredRows:
         return torch.Size(tuple(self.ctx.pidx.shape) + (C,))
 
     def materialize(self):
-        t = self.table.reshape(-1, self.table.shape[-1])
-        out = ops.gather_rows(t.detach(), self.ctx.pidx.clamp(min=0))
-        if self.cols is not None:
-            out = out[..., self.cols]
-        return out
+        """The dense tensor (sgn_gather_rows); built once per handle, detached as the reference's callers use it (prob outputs)."""
+        if getattr(self, "_dense", None) is None:
+            t = self.table.reshape(-1, self.table.shape[-1])
+            out = ops.gather_rows(t.detach(), self.ctx.pidx.clamp(min=0))
+            if self.cols is not None:
+                out = out[..., self.cols]
+            self._dense = out
+        return self._dense
+
+    # The reference's caller treats these entries as tensors in its `opt.prob == 1` block (torch.gather(sampled_xyz, 2, ...),
+    # sampled_color * weight, .shape[-2] -- neural_points_volumetric_model.py:633-668).  Any torch function that meets a handle
+    # gets the dense tensor; so do indexing and arithmetic.
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        dense = lambda a: a.materialize() if isinstance(a, GatheredRows) else a
+        args = tuple(dense(a) for a in args)
+        kwargs = {k: dense(v) for k, v in (kwargs or {}).items()}
+        return func(*args, **kwargs)
+
+    def __getitem__(self, item):
+        return self.materialize()[item]
+
+    def __getattr__(self, name):                # .dtype, .device, .dim(), .detach(), .squeeze(), ... of the dense tensor
+        if name.startswith("_") or name in ("ctx", "table", "cols"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+
+
+def _dense_binary(op):
+    def f(self, other):
+        return getattr(self.materialize(), op)(other.materialize() if isinstance(other, GatheredRows) else other)
+    return f
+
+
+for _n in ("__mul__", "__rmul__", "__add__", "__radd__", "__sub__", "__rsub__", "__truediv__"):
+    setattr(GatheredRows, _n, _dense_binary(_n))
 
 
 class GatheredPers(GatheredRows):
@@ -88,9 +168,16 @@ class lighting_fast_querier:
             self.invalidate()
             o = self.opt
             self._hp = ops.grid_hyperparameters(xyz, o.vsize, o.vscale, o.kernel_size, _opt(o, "ranges", None), o.radius_limit_scale)
-            self._grid = ops.OccGrid(xyz, self._hp.ranges[:3], self._hp.scaled_vsize, self._hp.scaled_vdim, o.query_size, o.P, o.max_o)
+            # reservoir seeds of the max_o / P overflows: two time.time() reads as in the reference (:715, :751)
+            self._grid = ops.OccGrid(xyz, self._hp.ranges[:3], self._hp.scaled_vsize, self._hp.scaled_vdim, o.query_size, o.P, o.max_o,
+                                     seconds_claim=self._seconds(), seconds_fill=self._seconds())
             self._grid_key = key
         return self._grid, self._hp
+
+    def _seconds(self):
+        """np.uint64(time.time()) of the reference's kernel calls (:715, :751, :916); `opt.sgn_seconds` pins it (tests)."""
+        fixed = _opt(self.opt, "sgn_seconds", None)
+        return int(time.time()) if fixed is None else int(fixed)
 
     @staticmethod
     def w2pers(point_xyz_w, camrotc2w, campos):
@@ -112,8 +199,11 @@ class lighting_fast_querier:
         kw = {}
         if _opt(o, "semantic_guidance", 0) == 1:
             prob = points_label_prob_tensor.reshape(-1, points_label_prob_tensor.shape[-1])
+            # the reference converts the probabilities with .to(torch.int32) (values 0 / 1) and its kernel then reads that tensor
+            # through a `const float*` (:916, :547): the same int32 tensor goes to sgn_query, which reinterprets the bits likewise
+            bits = prob.to(torch.int32)
             kw = dict(ray_label=ray_label_tensor.reshape(-1).to(torch.int32), pt_label=points_label_tensor.reshape(-1).to(torch.int32),
-                      pt_label_prob_bits=prob.view(torch.int32) if prob.is_floating_point() else prob.to(torch.int32))
+                      pt_label_prob_bits=bits, seconds_query=self._seconds())
         pidx, loc_w, smask, rmask = ops.query(grid, cam_pos_tensor.reshape(3), raydir, t, o.SR, o.K, o.kernel_size[0], hp.radius2, **kw)
         return pidx, loc_w, smask, rmask, hp
 
@@ -137,9 +227,9 @@ class lighting_fast_querier:
 class NeuralPoints(nn.Module):
     @staticmethod
     def modify_commandline_options(parser, is_train=True):
-        """The reference's own NeuralPoints.modify_commandline_options registers these flags (neural_points.py:80-310);
-        when this class replaces it the option parser still imports the reference's method, so nothing is added here."""
-        return parser
+        """Registers the flags of the reference's NeuralPoints.modify_commandline_options (neural_points.py:80-309): the reference
+        calls it on the imported class (neural_points_volumetric_model.py:66), so after the import swap this is where they come from."""
+        return _register_flags(parser, NEURAL_POINTS_FLAGS)
 
     def __init__(self, num_channels, size, opt, device, checkpoint=None, feature_init_method='rand', reg_weight=0., feedforward=0):
         super().__init__()
@@ -149,26 +239,53 @@ class NeuralPoints(nn.Module):
         self.points_label = self.points_label_prob = self.bpnet_points_embedding = self.points_feats = None
         self.Rw2c = torch.eye(3, device=device, dtype=torch.float32)
         self.reg_weight = reg_weight
+        # neural_points.py:425: query_size falls back to kernel_size when left at its (0, 0, 0) default
+        if hasattr(opt, "query_size") and hasattr(opt, "kernel_size") and opt.query_size[0] == 0:
+            opt.query_size = opt.kernel_size
         self.querier = lighting_fast_querier(device, opt)
-        if checkpoint:
-            saved = torch.load(checkpoint, map_location=device) if isinstance(checkpoint, str) else checkpoint
-            g = lambda k: saved.get("neural_points." + k)
-            self.xyz = nn.Parameter(g("xyz").to(device))
-            for name in ("points_embeding", "points_conf", "points_dir", "points_color", "eulers"):
-                v = g(name)
-                setattr(self, name, nn.Parameter(v.to(device)) if v is not None else None)
-            if g("Rw2c") is not None:
-                self.Rw2c = nn.Parameter(g("Rw2c").to(device))
-        elif feedforward:
-            self.xyz, self.points_embeding = None, None        # filled by set_points (MVS feed-forward initialisation)
-        else:
-            # feature_init_method == 'rand': U(-.5, .5) (neural_points.py:386); the cloud itself arrives through set_points
-            n = int(size)
-            self.xyz = nn.Parameter(torch.zeros(n, 3, device=device))
-            emb = torch.rand(1, n, num_channels, device=device) - 0.5 if feature_init_method == 'rand' else torch.zeros(1, n, num_channels, device=device)
-            self.points_embeding = nn.Parameter(emb)
-        if self.xyz is not None:
+        self.xyz, self.points_embeding = None, None
+        if _opt(opt, "load_points", 1) == 1 and not feedforward:
+            saved = None
+            if checkpoint:
+                saved = torch.load(checkpoint, map_location=device) if isinstance(checkpoint, str) else checkpoint
+            if saved is not None and "neural_points.xyz" in saved:
+                g = lambda k: saved.get("neural_points." + k)
+                self.xyz = nn.Parameter(g("xyz").to(device))
+                for name in ("points_embeding", "points_conf", "points_dir", "points_color", "eulers"):
+                    v = g(name)
+                    setattr(self, name, nn.Parameter(v.to(device)) if v is not None else None)
+                for name in ("points_feats", "points_label"):        # constants kept in the state_dict (requires_grad False)
+                    v = g(name)
+                    if v is not None:
+                        setattr(self, name, nn.Parameter(v.to(device), requires_grad=False))
+                if g("Rw2c") is not None:
+                    self.Rw2c = nn.Parameter(g("Rw2c").to(device), requires_grad=False)
+            else:
+                # no checkpoint: `size` points whose positions arrive through set_points; features by feature_init_method
+                # (neural_points.py:386-409: rand = U(-.5, .5), zeros, ones, gau_<std>)
+                n = int(size)
+                self.xyz = nn.Parameter(torch.zeros(n, 3, device=device))
+                shape = (1, n, num_channels)
+                if feature_init_method == "rand":
+                    emb = torch.rand(shape, device=device) - 0.5
+                elif feature_init_method == "zeros":
+                    emb = torch.zeros(shape, device=device)
+                elif feature_init_method == "ones":
+                    emb = torch.ones(shape, device=device)
+                elif feature_init_method.startswith("gau"):
+                    emb = torch.normal(mean=torch.zeros(shape, device=device), std=float(feature_init_method.split("_")[1]))
+                else:
+                    raise ValueError(feature_init_method)
+                self.points_embeding = nn.Parameter(emb)
+                self.points_conf = torch.ones_like(self.points_embeding[..., 0:1])
             self.xyz.requires_grad = _opt(opt, "xyz_grad", 0) > 0
+            for name, flag in (("points_embeding", "feat_grad"), ("points_conf", "conf_grad"), ("points_dir", "dir_grad"),
+                               ("points_color", "color_grad")):
+                t = getattr(self, name)
+                if isinstance(t, nn.Parameter):
+                    t.requires_grad = _opt(opt, flag, 1 if flag != "dir_grad" else 0) > 0
+            if self.eulers is not None:
+                self.eulers.requires_grad = False
 
     # ---- point-cloud edits: every one of them moves the tensors, so the querier's grid key changes on its own ----
     def reset_querier(self):
@@ -177,18 +294,30 @@ class NeuralPoints(nn.Module):
 
     def set_points(self, points_xyz, points_feats, points_embeding, points_label=None, points_color=None, points_dir=None,
                    points_conf=None, points_semantic=None, parameter=False, Rw2c=None, eulers=None):
-        wrap = (lambda t, grad=True: nn.Parameter(t, requires_grad=grad)) if parameter else (lambda t, grad=True: t)
+        o = self.opt
+        grad = lambda flag, default: _opt(o, flag, default) > 0
+        wrap = (lambda t, g=True: nn.Parameter(t, requires_grad=g)) if parameter else (lambda t, g=True: t)
         three = lambda t: None if t is None else (t if t.dim() == 3 else t[None, ...])
-        self.xyz = wrap(points_xyz.reshape(-1, 3), _opt(self.opt, "xyz_grad", 0) > 0)
+        if points_embeding.shape[-1] > _opt(o, "point_features_dim", points_embeding.shape[-1]):
+            points_embeding = points_embeding[..., :o.point_features_dim]
+        dc = _opt(o, "default_conf", -1.0)
+        if 0.0 < dc <= 1.0 and points_conf is not None:
+            points_conf = torch.ones_like(points_conf) * dc
+        for name, mode in (("conf", "point_conf_mode"), ("dir", "point_dir_mode"), ("color", "point_color_mode")):
+            if "0" in list(_opt(o, mode, "1")):
+                raise NotImplementedError(f"sgnerf_b200: --{mode} 0 (attribute concatenated into the embedding) is not built; use '1'")
+        for name in ("xyz", "points_feats", "points_label", "points_embeding", "points_conf", "points_dir", "points_color", "eulers", "Rw2c"):
+            self._parameters.pop(name, None)          # a plain tensor may replace what was a Parameter, and back
+        self.xyz = wrap(points_xyz.reshape(-1, 3), grad("xyz_grad", 0))
         self.points_feats = None if points_feats is None else wrap(points_feats, False)
         self.points_label = None if points_label is None else wrap(points_label, False)
-        self.points_embeding = wrap(three(points_embeding))
-        self.points_conf = None if points_conf is None else wrap(three(points_conf))
-        self.points_dir = None if points_dir is None else wrap(three(points_dir))
-        self.points_color = None if points_color is None else wrap(three(points_color))
+        self.points_embeding = wrap(three(points_embeding), grad("feat_grad", 1))
+        self.points_conf = None if points_conf is None else wrap(three(points_conf), grad("conf_grad", 1))
+        self.points_dir = None if points_dir is None else wrap(three(points_dir), grad("dir_grad", 0))
+        self.points_color = None if points_color is None else wrap(three(points_color), grad("color_grad", 1))
         self.eulers = None if eulers is None else wrap(eulers, False)
-        if Rw2c is not None:
-            self.Rw2c = wrap(Rw2c, False)
+        # the reference resets Rw2c to the identity when none is given (neural_points.py:647-651)
+        self.Rw2c = torch.eye(3, device=self.xyz.device, dtype=torch.float32) if Rw2c is None else nn.Parameter(Rw2c, requires_grad=False)
         self.reset_querier()
 
     def editing_set_points(self, points_xyz, points_embeding, points_color=None, points_dir=None, points_conf=None, parameter=False,
@@ -295,7 +424,9 @@ def _init_seq(seq, slope):
 class PointAggregator(nn.Module):
     @staticmethod
     def modify_commandline_options(parser, is_train=True):
-        return parser                      # flags are registered by the reference's own method (point_aggregators.py:15-254)
+        """Registers the flags of the reference's PointAggregator.modify_commandline_options (point_aggregators.py:15-253), called on
+        the imported class at neural_points_volumetric_model.py:67."""
+        return _register_flags(parser, POINT_AGGREGATOR_FLAGS)
 
     def __init__(self, opt):
         super().__init__()
@@ -342,6 +473,21 @@ class PointAggregator(nn.Module):
         seqs = [self.block1] + ([self.block2_bpnet] if hasattr(self, "block2_bpnet") else []) + [self.block3, self.alpha_branch, self.color_branch]
         return [m for s in seqs for m in s if isinstance(m, nn.Linear)]
 
+    def _require_identity_rw2c(self, Rw2c):
+        """The kernels take Rw2c = identity (include/sgnerf_b200.h; what every ScanNet script of the reference passes:
+        data/scannet_ft_dataset.py:124).  The reference rotates view directions, point offsets and point directions by Rw2c^T
+        (point_aggregators.py:563-653): any other matrix, or a per-point one, is refused instead of rendering wrong colours.
+        One device read per Rw2c tensor version."""
+        if Rw2c is None:
+            return
+        if Rw2c.dim() != 2:
+            raise NotImplementedError("sgnerf_b200: per-point Rw2c is not built (uniform identity only)")
+        key = (Rw2c.data_ptr(), Rw2c._version)
+        if getattr(self, "_rw2c_ok", None) != key:
+            if tuple(Rw2c.shape) != (3, 3) or not torch.equal(Rw2c.detach().float().cpu(), torch.eye(3)):
+                raise NotImplementedError("sgnerf_b200: Rw2c must be the 3x3 identity (a rotated point frame is not built)")
+            self._rw2c_ok = key
+
     def forward(self, sampled_color, sampled_label_embedding, sampled_Rw2c, sampled_dir, sampled_conf, sampled_embedding, sampled_xyz_pers,
                 sampled_xyz, sample_pnt_mask, sample_loc, sample_loc_w, sample_ray_dirs, vsize, grid_vox_sz):
         if not isinstance(sampled_embedding, GatheredRows):
@@ -349,6 +495,7 @@ class PointAggregator(nn.Module):
                             "dense gathered tensors are not accepted and there is no PyTorch fallback")
         ctx = sampled_embedding.ctx
         npnts = ctx.neural_points
+        self._require_identity_rw2c(sampled_Rw2c)
         lin = self._linears()
         training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         # opt.sgn_precision: "auto" = TF32 tensor-core GEMMs when training (the reference's cuBLAS default at its pinned torch), bf16

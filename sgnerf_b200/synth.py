@@ -179,3 +179,24 @@ def scene_room(n_points, room=(8.0, 8.0, 3.0), width=640, height=480, seed=1234,
     return SimpleNamespace(xyz=xyz, campos=eye.astype(np.float32), camrotc2w=R.astype(np.float32),
                            raydir=pixel_rays(px, py, K, R), px=px, py=py, near=0.1, far=8.0,
                            width=width, height=height)
+
+
+def scene_c3(n_points=3_000_000, width=800, height=800, seed=1234, pixels=None):
+    """Config C3: NeRF-Synthetic-shaped object cloud in [-1.5,1.5]^3, 800x800 frame, focal 1111, camera on a
+    sphere of radius 4 looking at the origin, near 2 / far 6.  Query options that go with it: vsize .004, P = 9, SR = 200."""
+    xyz = make_object_cloud(n_points, 1.0, 0.001, seed)
+    eye = 4.0 * np.array([0.6, -0.64, 0.48]) / np.linalg.norm([0.6, -0.64, 0.48])
+    R = look_at(eye, np.zeros(3))
+    K = np.array([[1111.0, 0.0, (width - 1) / 2.0], [0.0, 1111.0, (height - 1) / 2.0], [0.0, 0.0, 1.0]])
+    K[0, 0] = K[1, 1] = 1111.0 * width / 800.0
+    px, py = pixels if pixels is not None else full_frame_pixels(width, height)
+    return SimpleNamespace(xyz=xyz, campos=eye.astype(np.float32), camrotc2w=R.astype(np.float32), raydir=pixel_rays(px, py, K, R),
+                           px=px, py=py, near=2.0, far=6.0, width=width, height=height)
+
+
+C3_QUERY = dict(vsize=(0.004, 0.004, 0.004), P=9, SR=200)
+
+
+def scene_c4(n_points=10_000_000, width=1296, height=968, seed=1234, pixels=None):
+    """Config C4: 10M-point room of 20 x 20 x 4 m at raw ScanNet resolution."""
+    return scene_room(n_points, room=(20.0, 20.0, 4.0), width=width, height=height, seed=seed, pixels=pixels)

@@ -66,8 +66,11 @@ def build_occ_vox(L, xyz, opt, hp, seconds=(0, 0)):
                 occ_2_pnts=occ_2_pnts, shift=shift, vsize=vsize, dim_t=dim_t, vol=vol)
 
 
-def query_grid_point_index(L, raypos, xyz, opt, hp, seconds=(0, 0, 0), grid=None):
-    """:782-954 (non-semantic branch).  raypos [1,R,D,3] cuda, xyz [1,N,3] cuda.
+def query_grid_point_index(L, raypos, xyz, opt, hp, seconds=(0, 0, 0), grid=None, raylabel=None, points_label=None,
+                           points_label_prob=None):
+    """:782-954.  raypos [1,R,D,3] cuda, xyz [1,N,3] cuda.  With raylabel (int32 [1,R], one label per ray, repeated over D as :110 does),
+    points_label (int32 [N]) and points_label_prob (int32 [N,20]: what `.to(torch.int32)` of :916 produced) the semantic-guidance
+    kernels run (get_shadingloc_with_semantic + query_neigh_along_ray_layered_semantic_guidance, :853-870 / :910-938).
     Returns sample_pidx [1,R'',SR,K], sample_loc [1,R'',SR,3], ray_mask int8 [1,R], grid dict."""
     dev = xyz.device
     B, R, D = 1, raypos.shape[1], raypos.shape[2]
@@ -85,16 +88,32 @@ def query_grid_point_index(L, raypos, xyz, opt, hp, seconds=(0, 0, 0), grid=None
     if R1 > 0:
         raypos = torch.masked_select(raypos, ray_mask[..., None, None].expand(-1, -1, D, 3)).reshape(B, R1, D, 3)
         raypos_mask = torch.masked_select(raypos_mask, ray_mask[..., None].expand(-1, -1, D)).reshape(B, R1, D)
+        sem = raylabel is not None
+        if sem:
+            raylabel_d = raylabel.reshape(B, R, 1, 1).to(torch.int32).expand(-1, -1, D, 1).contiguous()                    # :110
+            raylabel_d = torch.masked_select(raylabel_d, ray_mask[..., None, None].expand(-1, -1, D, 1)).reshape(B, R1, D, 1)  # :840
         cum = torch.cumsum(raypos_mask, dim=-1).to(torch.int32)
         raypos_mask = (raypos_mask * cum * (cum <= SR)) - 1
         sample_loc_mask = torch.zeros([B, R1, SR], **i32)
-        _chk(L.ref_get_shadingloc(_p(raypos), _p(raypos_mask.contiguous()), B, R1, D, SR, _p(sample_loc), _p(sample_loc_mask), _st()),
-             "get_shadingloc")
         ks = torch.tensor(list(opt.kernel_size), **i32)
-        _chk(L.ref_query_neigh_along_ray_layered(
-            _p(xyz), B, SR, R1, opt.max_o, opt.P, K, g["vol"], C.c_float(float(hp.radius2)), _p(g["shift"]), _p(g["dim_t"]),
-            _p(g["vsize"]), _p(ks), _p(g["occ_numpnts"]), _p(g["occ_2_pnts"]), _p(g["coor_2_occ"]), _p(sample_loc),
-            _p(sample_loc_mask), _p(sample_pidx), C.c_ulong(int(seconds[2])), opt.NN, _st()), "query_neigh_along_ray_layered")
+        if sem:
+            sample_label = torch.zeros([B, R1, SR], **i32)
+            _chk(L.ref_get_shadingloc_with_semantic(_p(raypos), _p(raylabel_d.contiguous()), _p(raypos_mask.contiguous()), B, R1, D, SR,
+                                                    _p(sample_loc), _p(sample_label), _p(sample_loc_mask), _st()), "get_shadingloc_with_semantic")
+            lab = points_label.reshape(-1).to(torch.int32).contiguous()
+            prob = points_label_prob.reshape(-1, 20).to(torch.int32).contiguous()
+            _chk(L.ref_query_neigh_along_ray_layered_semantic_guidance(
+                _p(xyz), _p(lab), _p(prob), B, SR, R1, opt.max_o, opt.P, K, g["vol"], C.c_float(float(hp.radius2)), _p(g["shift"]),
+                _p(g["dim_t"]), _p(g["vsize"]), _p(ks), _p(g["occ_numpnts"]), _p(g["occ_2_pnts"]), _p(g["coor_2_occ"]), _p(sample_loc),
+                _p(sample_loc_mask), _p(sample_label), _p(sample_pidx), C.c_ulong(int(seconds[2])), opt.NN, _st()),
+                "query_neigh_along_ray_layered_semantic_guidance")
+        else:
+            _chk(L.ref_get_shadingloc(_p(raypos), _p(raypos_mask.contiguous()), B, R1, D, SR, _p(sample_loc), _p(sample_loc_mask), _st()),
+                 "get_shadingloc")
+            _chk(L.ref_query_neigh_along_ray_layered(
+                _p(xyz), B, SR, R1, opt.max_o, opt.P, K, g["vol"], C.c_float(float(hp.radius2)), _p(g["shift"]), _p(g["dim_t"]),
+                _p(g["vsize"]), _p(ks), _p(g["occ_numpnts"]), _p(g["occ_2_pnts"]), _p(g["coor_2_occ"]), _p(sample_loc),
+                _p(sample_loc_mask), _p(sample_pidx), C.c_ulong(int(seconds[2])), opt.NN, _st()), "query_neigh_along_ray_layered")
         valid_ray = torch.sum(sample_pidx.view(B, R1, -1) >= 0, dim=-1) > 0
         R2 = int(torch.max(torch.sum(valid_ray.to(torch.int32), dim=-1)).cpu().numpy())
         ray_mask.masked_scatter_(ray_mask, valid_ray)

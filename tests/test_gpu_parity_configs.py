@@ -1,0 +1,116 @@
+"""GPU: exact CUDA-vs-oracle parity AT the benchmark configurations (BASELINE.json configs C1 and C3), on ray subsets the sequential
+oracle finishes in seconds, and the bf16 headline mode held to the ORACLE (not to the repo's own fp32 path).
+
+  * C1: 1M-point room, 640x480 frame, SR 24, K 8, P 26, vsize .008.  The CUDA query runs the FULL frame; the oracle a 9216-ray random
+    subset; rows of the subset must be identical (ray mask, neighbour indices incl. slot order, sample positions bit for bit).
+  * C3: 3M-point object cloud, 800x800, SR 200, P 9, vsize .004, near 2 / far 6: same comparison on a 9216-ray subset.
+  * bf16 tensor-core frame against the oracle render on a 2048-ray C1 subset: |d rgb| <= 1e-3 (observed ~1e-4), PSNR(bf16, oracle) >= 65 dB,
+    and the PSNR against a pseudo ground truth changes by <= 0.02 dB.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import query_ref as qr
+from oracle import render_ref as rr
+from sgnerf_b200 import ops, pipeline, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _subset(s, n, seed=0):
+    sel = np.sort(np.random.default_rng(seed).choice(s.raydir.shape[0], n, replace=False))
+    sub = SimpleNamespace(**vars(s))
+    sub.raydir = np.ascontiguousarray(s.raydir[sel])
+    return sel, sub
+
+
+def _rows_equal(cu_pidx, cu_loc, cu_rmask, orc):
+    o_pidx, _, o_loc_w, _, o_ray_mask, _, _, _ = orc
+    rmask = cu_rmask.cpu().numpy()
+    assert np.array_equal(rmask, o_ray_mask[0].numpy()), "ray_mask differs"
+    hit = rmask > 0
+    assert np.array_equal(cu_pidx.cpu().numpy()[hit], o_pidx[0].numpy()), "sample_pidx differs (slot order included)"
+    assert np.array_equal(cu_loc.cpu().numpy()[hit].view(np.int32), o_loc_w[0].numpy().view(np.int32)), "sample_loc_w differs (bitwise)"
+    return int(hit.sum())
+
+
+@pytest.fixture(scope="module")
+def c1():
+    return synth.scene_room(1_000_000, room=(8.0, 8.0, 3.0), width=640, height=480, seed=1234)
+
+
+def test_c1_full_frame_rows_equal_the_oracle_on_a_9216_ray_subset(c1):
+    opt = qr.default_opt(SR=24)
+    t = util.shared_t(c1.near, c1.far, opt.z_depth_dim)
+    cu = util.cuda_query(c1, opt, t)                                   # all 307200 rays in one call
+    sel, sub = _subset(c1, 9216)
+    orc = util.oracle_query(sub, opt, t)
+    n_hit = _rows_equal(cu.pidx[sel], cu.loc_w[sel], cu.rmask[sel], orc)
+    assert n_hit > 8000
+    assert np.array_equal(cu.hp.ranges, orc[6]) and np.array_equal(cu.hp.scaled_vdim, orc[7].hp.scaled_vdim)
+    util.assert_grid_equal(cu.grid, orc[7].grid)
+
+
+def test_c3_shape_rows_equal_the_oracle_on_a_9216_ray_subset():
+    s = synth.scene_c3()
+    opt = qr.default_opt(**synth.C3_QUERY)
+    assert opt.SR == 200 and opt.P == 9
+    t = util.shared_t(s.near, s.far, opt.z_depth_dim)
+    sel, sub = _subset(s, 9216, seed=1)
+    cu = util.cuda_query(sub, opt, t)
+    orc = util.oracle_query(sub, opt, t)
+    n_hit = _rows_equal(cu.pidx, cu.loc_w, cu.rmask, orc)
+    assert n_hit > 1000
+    util.assert_grid_equal(cu.grid, orc[7].grid)
+    # a sub-subset queried inside a larger call gives the same rows (ray independence at SR = 200)
+    sel2, sub2 = _subset(sub, 1024, seed=2)
+    cu2 = util.cuda_query(sub2, opt, t, grid=(cu.grid, cu.hp))
+    assert torch.equal(cu2.pidx, cu.pidx[sel2]) and torch.equal(cu2.loc_w, cu.loc_w[sel2]) and torch.equal(cu2.rmask, cu.rmask[sel2])
+
+
+def _psnr(a, b):
+    return float(-10.0 * torch.log10(((a - b) ** 2).mean().clamp(min=1e-20)))
+
+
+@pytest.mark.parametrize("semantic", [False, True])
+def test_bf16_frame_vs_oracle_on_a_c1_subset(c1, semantic):
+    dev = "cuda"
+    sel, sub = _subset(c1, 2048, seed=3)
+    opt = qr.default_opt(SR=24)
+    cfg = rr.semantic_config() if semantic else rr.agg_config()
+    P = rr.init_params(cfg, seed=0, bias_scale=0.05)
+    N = c1.xyz.shape[0]
+    tabs = synth.make_point_tables(N, 32, 96 if semantic else 0, seed=0, conf_spread=0.2)
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    acfg = ops.agg_cfg(n_block2_bpnet=1, label_dim=96) if semantic else ops.agg_cfg()
+    scene = pipeline.RenderScene(c1.xyz, tabs.embedding, tabs.color, tabs.dir, tabs.conf, [P[n + ".weight"] for n in names],
+                                 [P[n + ".bias"] for n in names], acfg, pipeline.query_options(SR=24), label_emb=tabs.label_embedding, device=dev)
+    t = util.shared_t(c1.near, c1.far, opt.z_depth_dim)
+    bg = torch.ones(3, device=dev)
+    args = (torch.from_numpy(c1.campos).to(dev), torch.from_numpy(c1.camrotc2w).to(dev), torch.from_numpy(sub.raydir).to(dev), c1.near, c1.far, bg)
+    with torch.no_grad():
+        o16 = pipeline.render_rays(scene, *args, precision=ops.PRECISION_BF16, t=t.to(dev))
+        o32 = pipeline.render_rays(scene, *args, precision=ops.PRECISION_FP32, t=t.to(dev))
+    orc = util.oracle_query(sub, opt, t)
+    o_pidx, o_loc, o_loc_w, o_dirs, o_mask, o_vsize, _, _ = orc
+    tables = SimpleNamespace(xyz=torch.from_numpy(c1.xyz), embedding=tabs.embedding, color=tabs.color, dir=tabs.dir, conf=tabs.conf,
+                             label_embedding=tabs.label_embedding)
+    with torch.no_grad():
+        want = rr.render_from_query(P, cfg, tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, torch.from_numpy(c1.camrotc2w)[None],
+                                    torch.from_numpy(c1.campos)[None], o_vsize, torch.ones(3))
+    ref = want.coarse_raycolor[0]
+    assert np.array_equal(o16.ray_mask.cpu().numpy(), o_mask[0].numpy()) and int(o_mask.sum()) > 1500
+    e32 = float((o32.ray_color.cpu() - ref).abs().max())
+    e16 = float((o16.ray_color.cpu() - ref).abs().max())
+    assert e32 <= 1e-3, e32                               # north_star's fp32 bar (observed ~3e-6)
+    assert e16 <= 1e-3, e16                               # the stated bf16 tensor-core tolerance on rgb (observed ~1e-4)
+    sel_hit = o_mask[0] > 0
+    d16 = (o16.depth.cpu()[sel_hit] - want.coarse_depth[0]).abs().max()
+    assert float(d16) <= 5e-3, float(d16)                 # depth in metres (camera z up to 8 m): bf16 weights on the compositing weights
+    assert _psnr(o16.ray_color.cpu(), ref) >= 65.0
+    gt = (ref + 0.01 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(0))).clamp(0, 1)      # pseudo ground truth, ~40 dB
+    assert abs(_psnr(o16.ray_color.cpu(), gt) - _psnr(ref, gt)) <= 0.02

@@ -90,3 +90,53 @@ def test_reference_kernel_reservoir_matches_oracle_xorwow():
     cnt = g["occ_numpnts"][0].cpu().numpy()
     lists = g["occ_2_pnts"][0].cpu().numpy()
     assert ((lists >= 0).sum(-1) == np.minimum(cnt, opt.P)).all()
+
+
+@pytest.mark.skipif(not ref_driver.available(8), reason="oracle/_ref/libref_query_K8.so not built")
+@pytest.mark.parametrize("sec", [1_700_000_001, 1_700_000_005])          # seconds % 10 = 1 opens the cross-label gate, 5 closes it
+def test_reference_semantic_kernels_vs_oracle_and_cuda(sec):
+    """The semantic-guidance branch (get_shadingloc_with_semantic + query_neigh_along_ray_layered_semantic_guidance, :462-591, host side
+    :853-938) of the reference's own compiled kernels against the oracle's restatement and the CUDA path.  The branch holds a reference
+    quirk the restatement reproduces: the probabilities go through `.to(torch.int32)` (:916) and the kernel reads that tensor through a
+    `const float*` (:547), so `label_prob = int(bits_as_float * 10)`; the int `1 - label_prob` is then compared with the unsigned long
+    `seconds % 10`.  Point probabilities here are (a) what `.to(int32)` of softmax values gives (0, and 1 for an exact 1.0) and (b) raw
+    int32 patterns that read back as 0.35f / 0.05f, which drive `1 - label_prob` negative (= a huge unsigned: always accepted) or to 1."""
+    s = synth.scene_c0(n_points=100_000, n_rays=1024)
+    rng = np.random.default_rng(3)
+    N, R = s.xyz.shape[0], s.raydir.shape[0]
+    opt = qr.default_opt(SR=24, semantic_guidance=1)
+    pt_label = rng.integers(0, 20, N).astype(np.int32)                     # label 0 = "accept always" on either side
+    prob = (rng.random((N, 20)) < 0.1).astype(np.int32)                    # .to(int32) of probabilities: 0, or 1 where p == 1.0
+    wild = rng.random(N) < 0.2
+    prob[wild] = np.where(rng.random((int(wild.sum()), 20)) < 0.5, np.float32(0.35).view(np.int32), np.float32(0.05).view(np.int32))
+    ray_label = rng.integers(0, 20, R).astype(np.int32)
+    t = util.shared_t(s.near, s.far, opt.z_depth_dim)
+    kw = dict(ray_label=ray_label, points_label=pt_label, points_label_prob=prob)
+    orc = util.oracle_query(s, opt, t, seconds=(0, 0, sec), **kw)
+    o_pidx, _, o_loc_w, _, o_ray_mask, _, _, info = orc
+    hp = info.hp
+    L = ref_driver.lib(8)
+    xyz = torch.from_numpy(s.xyz).cuda()[None]
+    raypos = qr.raypos_from_t(torch.from_numpy(s.campos)[None], torch.from_numpy(s.raydir)[None], t).cuda()
+    r_pidx, r_loc, r_mask, g = ref_driver.query_grid_point_index(
+        L, raypos, xyz, opt, hp, seconds=(0, 0, sec), raylabel=torch.from_numpy(ray_label).cuda()[None],
+        points_label=torch.from_numpy(pt_label).cuda(), points_label_prob=torch.from_numpy(prob).cuda())
+    torch.cuda.synchronize()
+    ref_slot0, orc_slot0 = g["occ_2_coor"][0, 0].cpu().numpy(), info.grid.occ_2_coor[0]
+    r_mask_np, o_mask_np = r_mask[0].cpu().numpy(), o_ray_mask[0].numpy()
+    both = (r_mask_np > 0) & (o_mask_np > 0)
+    assert (r_mask_np != o_mask_np).sum() <= 4 and both.sum() > 500
+    ridx, oidx = np.cumsum(r_mask_np > 0) - 1, np.cumsum(o_mask_np > 0) - 1
+    rp, op_ = r_pidx[0].cpu().numpy()[ridx[both]], o_pidx[0].numpy()[oidx[both]]
+    rl, ol = r_loc[0].cpu().numpy()[ridx[both]], o_loc_w[0].numpy()[oidx[both]]
+    assert np.array_equal(rl.view(np.int32), ol.view(np.int32))
+    touched = _near_voxel(ol, hp, ref_slot0) | _near_voxel(ol, hp, orc_slot0)
+    same = (np.sort(rp, -1) == np.sort(op_, -1)).all(-1)
+    assert same[~touched].all(), "semantic-guidance neighbour sets differ from the reference's own kernel"
+    assert (~touched).mean() > 0.95
+    # the gate must matter in this fixture: closed (seconds % 10 = 5) it rejects most cross-label neighbours, open it rejects none
+    plain = util.oracle_query(s, qr.default_opt(SR=24), t)
+    n_plain, n_sem = int((plain[0] >= 0).sum()), int((o_pidx >= 0).sum())
+    assert (n_sem == n_plain) if sec % 10 <= 1 else (0 < n_sem < 0.5 * n_plain)
+    cu = util.cuda_query(s, opt, t, seconds=(0, 0, sec), **kw)
+    util.assert_query_equal(cu, orc)

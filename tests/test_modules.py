@@ -1,6 +1,7 @@
 """Drop-in modules (sgnerf_b200/modules.py): state_dict parity on the CPU; on the GPU the reference's own call sequence
 (NeuralPointsRayMarching.forward, models/neural_points_volumetric_model.py:541-607) through our NeuralPoints / PointAggregator /
 ray_march against the oracle's render of the same scene."""
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -202,3 +203,36 @@ def test_grid_hyperparameters_match_the_oracle():
         assert np.array_equal(a.scaled_vsize.view(np.int32), b.scaled_vsize.view(np.int32))
         assert np.array_equal(a.scaled_vdim, b.scaled_vdim)
         assert np.float32(a.radius2).tobytes() == np.float32(b.radius2).tobytes()
+
+
+def test_commandline_flags_equal_the_reference(golden_dir):
+    """modify_commandline_options of both drop-in classes registers the reference's flags (neural_points.py:80-309,
+    point_aggregators.py:15-253): same names, order, type, default (after argparse's conversion) and nargs -- against
+    tests/golden/reference_flags.json, extracted from the reference's source by tests/golden/make_flags_golden.py.  The reference
+    calls these on the imported classes (neural_points_volumetric_model.py:66-67), so a parser built from them alone must parse a
+    reference training command line."""
+    import argparse
+    import json
+    from sgnerf_b200 import modules
+    gold = json.load(open(os.path.join(golden_dir, "reference_flags.json")))
+    for cls, key in ((modules.NeuralPoints, "NeuralPoints"), (modules.PointAggregator, "PointAggregator")):
+        p = argparse.ArgumentParser()
+        assert cls.modify_commandline_options(p, is_train=True) is p
+        acts = [a for a in p._actions if a.option_strings and a.option_strings[0] != "-h"]
+        assert [a.option_strings[0] for a in acts] == [g["flag"] for g in gold[key]]
+        for a, g in zip(acts, gold[key]):
+            assert a.type.__name__ == g["type"] and a.nargs == g["nargs"], g["flag"]
+            d = tuple(g["default"]) if isinstance(g["default"], list) else g["default"]
+            assert a.default == d and type(a.default) is type(d), g["flag"]
+    # both on one parser, then a command line of the reference's ScanNet scripts (dev_scripts/w_scannet_etf/*.sh)
+    p = argparse.ArgumentParser()
+    modules.NeuralPoints.modify_commandline_options(p)
+    modules.PointAggregator.modify_commandline_options(p)
+    modules.NeuralPoints.modify_commandline_options(p)              # registering twice must not raise
+    o = p.parse_args("--K 8 --SR 24 --P 26 --NN 2 --vsize 0.008 0.008 0.008 --vscale 2 2 2 --kernel_size 3 3 3 --query_size 3 3 3 "
+                     "--radius_limit_scale 4 --max_o 610000 --ranges -10 -10 -10 10 10 10 --wcoord_query 1 --point_features_dim 32 "
+                     "--agg_distance_kernel linear --agg_dist_pers 20 --agg_intrp_order 2 --act_type LeakyReLU --num_feat_freqs 3 "
+                     "--dist_xyz_freq 5 --shading_feature_mlp_layer3 2 --shading_color_mlp_layer 4 --point_conf_mode 1 --point_dir_mode 1 "
+                     "--point_color_mode 1".split())
+    assert o.K == 8 and o.vsize == [0.008] * 3 and o.wcoord_query == 1 and o.max_o == 610000 and o.z_depth_dim == 400
+    assert p.parse_args([]).wcoord_query == 0                        # the reference's string default '0' goes through type=int
