@@ -458,7 +458,7 @@ def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
                 with torch.device(device):
                     out = rr.render_from_query(Pt, cfg, tt, pidx, loc, loc_w, dirs, mask, rot, campos, np.asarray(opt.vsize, np.float32), bg)
                     c = out.conf_coefficient.reshape(-1)
-                    loss = ((out.ray_color - gt[:, sel]) ** 2).mean() + 1e-4 * torch.mean(torch.log(0.1 + c) + torch.log(0.1 + 1.0 - c) + 2.20727)
+                    loss = ((out.ray_color - gt[:, sel]) ** 2).mean() + 1e-6 + 1e-4 * torch.mean(torch.log(c.clamp(1e-3, 1 - 1e-3)) + torch.log(1.0 - c.clamp(1e-3, 1 - 1e-3)))
                 optim.zero_grad(set_to_none=False)
                 loss.backward()
                 optim.step()

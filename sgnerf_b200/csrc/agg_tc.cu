@@ -1331,16 +1331,17 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         set_error("sgn_agg_forward(bf16): workspace too small or misaligned (need %zu bytes, got %zu)", need, workspace_bytes);
         return SGN_E_WORKSPACE;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    // the dynamic shared-memory opt-in is per device: once per device ordinal of this process
+    static bool attr_set[64] = {};
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_tuple_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(agg_color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
         SGN_CUDA(cudaFuncSetAttribute(tc_point_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    int dev = 0, n_sm = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
 
     // per call (weights and embeddings may have been updated by the optimiser): bf16 weight panels in the 128B-swizzled

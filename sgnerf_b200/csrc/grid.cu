@@ -230,6 +230,92 @@ __global__ void dilate_kernel(GridParams g, const int32_t* __restrict__ counters
             }
 }
 
+// K9-K11: the K-NN index.  A voxel is "listed" when it owns a surviving record with at least one candidate (slot 0 never does, :395).
+__device__ __forceinline__ void brick_of(const GridParams& g, int c0, int c1, int c2, int64_t& b, int& bit)
+{
+    b = ((int64_t)(c0 >> 2) * brick4(g.dy) + (c1 >> 2)) * brick4(g.dz) + (c2 >> 2);
+    bit = ((c0 & 3) * 4 + (c1 & 3)) * 4 + (c2 & 3);
+}
+
+__global__ void brick_mark_kernel(GridParams g, const int32_t* __restrict__ counters, const int32_t* __restrict__ slot_coor,
+                                  const int32_t* __restrict__ slot_start, uint4* knn_brick)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_rec = counters[0] < g.max_o ? counters[0] : g.max_o;
+    if (s >= n_rec || slot_coor[3 * s] < 0 || slot_start[s + 1] <= slot_start[s]) return;
+    int64_t b; int bit;
+    brick_of(g, slot_coor[3 * s], slot_coor[3 * s + 1], slot_coor[3 * s + 2], b, bit);
+    atomicOr((unsigned long long*)(knn_brick + b), 1ull << bit);
+}
+
+__global__ void brick_count_kernel(int64_t nb, const uint4* __restrict__ knn_brick, int32_t* cnt)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint4 e = knn_brick[b];
+    cnt[b] = __popc(e.x) + __popc(e.y);
+}
+
+__global__ void brick_base_kernel(int64_t nb, const int32_t* __restrict__ base, uint4* knn_brick)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    knn_brick[b].z = (uint32_t)base[b];
+}
+
+__global__ void brick_list_kernel(GridParams g, const int32_t* __restrict__ counters, const int32_t* __restrict__ slot_coor,
+                                  const int32_t* __restrict__ slot_start, const uint4* __restrict__ knn_brick, int2* knn_list)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_rec = counters[0] < g.max_o ? counters[0] : g.max_o;
+    if (s >= n_rec || slot_coor[3 * s] < 0 || slot_start[s + 1] <= slot_start[s]) return;
+    int64_t b; int bit;
+    brick_of(g, slot_coor[3 * s], slot_coor[3 * s + 1], slot_coor[3 * s + 2], b, bit);
+    const uint4 e = knn_brick[b];
+    const unsigned long long m = ((unsigned long long)e.y << 32) | e.x;
+    const int rank = (int)e.z + __popcll(m & ((1ull << bit) - 1ull));
+    knn_list[rank] = make_int2(slot_start[s], slot_start[s + 1] - slot_start[s]);
+}
+
+// K12-K14: neighbour lists per sample voxel (grid.cuh).
+__global__ void word_popc_kernel(int64_t nwords, const uint32_t* __restrict__ bits, int32_t* cnt)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nwords) cnt[w] = __popc(bits[w]);
+}
+
+template <bool FILL>
+__global__ void nbr_list_kernel(GridParams g, int nby, int nbz, int64_t vol, const uint32_t* __restrict__ occ_bits, const int32_t* __restrict__ occ_rank,
+                                const uint4* __restrict__ knn_brick, const int2* __restrict__ knn_list, int32_t* nbr_cnt_or_off, uint32_t* nbr_ent)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= vol) return;
+    const uint32_t w = occ_bits[c >> 5];
+    if (!((w >> (c & 31)) & 1u)) return;
+    const int rank = occ_rank[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
+    const int fz = (int)(c % g.dz), fy = (int)((c / g.dz) % g.dy), fx = (int)(c / ((int64_t)g.dz * g.dy));
+    int n = 0;
+    uint32_t shell1 = 0x80000000u;
+    uint32_t* out = FILL ? nbr_ent + nbr_cnt_or_off[rank] : nullptr;
+    for (int i = 0; i < 27; i++) {
+        const int l = i == 0 ? 13 : (i - 1 < 13 ? i - 1 : i);       // centre first, then the 26 others with x outer / z inner (:617-627)
+        const int vx = fx + l / 9 - 1, vy = fy + (l / 3) % 3 - 1, vz = fz + l % 3 - 1;
+        if ((unsigned)vx >= (unsigned)g.dx || (unsigned)vy >= (unsigned)g.dy || (unsigned)vz >= (unsigned)g.dz) continue;
+        const uint4 e = knn_brick[((int64_t)(vx >> 2) * nby + (vy >> 2)) * nbz + (vz >> 2)];
+        const int bit = ((vx & 3) * 4 + (vy & 3)) * 4 + (vz & 3);
+        const unsigned long long m = ((unsigned long long)e.y << 32) | e.x;
+        if (!((m >> bit) & 1ull)) continue;
+        if (FILL) {
+            const int2 li = knn_list[(int)e.z + __popcll(m & ((1ull << bit) - 1ull))];
+            uint32_t flag = 0u;
+            if (i > 0) { flag = shell1; shell1 = 0u; }
+            out[n] = (uint32_t)li.x | ((uint32_t)li.y << 24) | flag;
+        }
+        n++;
+    }
+    if (!FILL) nbr_cnt_or_off[rank] = n;
+}
+
 static GridParams make_params(const SgnGridCfg* c)
 {
     GridParams g;
@@ -242,8 +328,20 @@ static GridParams make_params(const SgnGridCfg* c)
 }
 
 struct GridLayout {
-    size_t cell_slot, occ_bits, slot_coor, slot_count, slot_start, cand, counters, coarse_bits, total;
+    size_t cell_slot, occ_bits, slot_coor, slot_count, slot_start, cand, counters, coarse_bits, knn_brick, knn_list, occ_rank, nbr_off, nbr_ent, total;
 };
+
+// upper bounds known before the build: every surviving record dilates to at most q^3 sample voxels and is listed by at most 27 of them
+static int64_t listed_max(int64_t N, const SgnGridCfg* c) { return N < c->max_o ? N : c->max_o; }
+static int64_t sample_voxels_max(int64_t N, const SgnGridCfg* c)
+{
+    const int64_t q = (int64_t)(c->query_size[0] > 0 ? c->query_size[0] : 1) * (c->query_size[1] > 0 ? c->query_size[1] : 1) * (c->query_size[2] > 0 ? c->query_size[2] : 1);
+    const int64_t v = q * listed_max(N, c), vol = (int64_t)c->dim[0] * c->dim[1] * c->dim[2];
+    return v < vol ? v : vol;
+}
+static bool nbr_lists_ok(int64_t N, const SgnGridCfg* c) { return N < (1ll << 24) && c->P < 128; }
+
+static int64_t brick_count(const SgnGridCfg* c) { return (int64_t)brick4(c->dim[0]) * brick4(c->dim[1]) * brick4(c->dim[2]); }
 
 static int64_t grid_vol(const SgnGridCfg* c) { return (int64_t)c->dim[0] * c->dim[1] * c->dim[2]; }
 
@@ -267,6 +365,11 @@ static GridLayout persistent_layout(int64_t N, const SgnGridCfg* c)
     L.cand = take(sizeof(float4) * (size_t)(N > 0 ? N : 1));
     L.counters = take(sizeof(int32_t) * 4);
     L.coarse_bits = take(sizeof(uint32_t) * coarse_words(c));
+    L.knn_brick = take(sizeof(uint4) * (size_t)brick_count(c));
+    L.knn_list = take(sizeof(int2) * ((size_t)c->max_o + 1));
+    L.occ_rank = take(sizeof(int32_t) * (size_t)((vol + 31) / 32 + 1));
+    L.nbr_off = take(nbr_lists_ok(N, c) ? sizeof(int32_t) * (size_t)(sample_voxels_max(N, c) + 1) : 0);
+    L.nbr_ent = take(nbr_lists_ok(N, c) ? sizeof(uint32_t) * (size_t)(27 * listed_max(N, c) + 1) : 0);
     L.total = off;
     return L;
 }
@@ -276,6 +379,14 @@ static size_t scratch_bytes_for(int64_t N, const SgnGridCfg* c)
     size_t off = 0;
     auto take = [&](size_t bytes) { off += align_up(bytes); };
     int64_t nscan = N > c->max_o ? N : c->max_o;
+    if (brick_count(c) > nscan) nscan = brick_count(c);
+    const int64_t nwords = ((int64_t)c->dim[0] * c->dim[1] * c->dim[2] + 31) / 32;
+    if (nwords > nscan) nscan = nwords;
+    if (sample_voxels_max(N, c) > nscan) nscan = sample_voxels_max(N, c);
+    take(sizeof(int32_t) * (size_t)(nwords + 1));          // set bits per occupancy word
+    take(sizeof(int32_t) * (size_t)(sample_voxels_max(N, c) + 1));   // neighbours per sample voxel
+    take(sizeof(int32_t) * (size_t)(brick_count(c) + 1)); // listed voxels per brick
+    take(sizeof(int32_t) * (size_t)(brick_count(c) + 1)); // its exclusive scan
     take(sizeof(int32_t) * (size_t)(N + 1));              // flag
     take(sizeof(int32_t) * (size_t)(N + 1));              // rank
     take(sizeof(int32_t) * scan_partials_count(nscan));    // scan partials
@@ -338,9 +449,25 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
     G->cand = (float4*)(pb + L.cand);
     G->counters = (int32_t*)(pb + L.counters);
     G->coarse_bits = (uint32_t*)(pb + L.coarse_bits);
+    G->knn_brick = (uint4*)(pb + L.knn_brick);
+    G->knn_list = (int2*)(pb + L.knn_list);
+    G->nbx = brick4(cfg->dim[0]); G->nby = brick4(cfg->dim[1]); G->nbz = brick4(cfg->dim[2]);
+    const int64_t nbrick = brick_count(cfg);
 
     Arena A(scratch, scratch_bytes);
+    G->occ_rank = (int32_t*)(pb + L.occ_rank);
+    G->nbr_ok = nbr_lists_ok(N, cfg) ? 1 : 0;
+    G->nbr_off = G->nbr_ok ? (int32_t*)(pb + L.nbr_off) : nullptr;
+    G->nbr_ent = G->nbr_ok ? (uint32_t*)(pb + L.nbr_ent) : nullptr;
     int64_t nscan = N > max_o ? N : max_o;
+    if (nbrick > nscan) nscan = nbrick;
+    const int64_t nwords = (vol + 31) / 32, nsv = sample_voxels_max(N, cfg);
+    if (nwords > nscan) nscan = nwords;
+    if (nsv > nscan) nscan = nsv;
+    int32_t* word_cnt = A.take<int32_t>(nwords + 1);
+    int32_t* nbr_cnt = A.take<int32_t>(nsv + 1);
+    int32_t* brick_cnt = A.take<int32_t>(nbrick + 1);
+    int32_t* brick_base = A.take<int32_t>(nbrick + 1);
     int32_t* flag = A.take<int32_t>(N + 1);
     int32_t* rank = A.take<int32_t>(N + 1);
     int32_t* partials = A.take<int32_t>(scan_partials_count(nscan));
@@ -364,6 +491,7 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
     GRID_CUDA(cudaMemsetAsync(G->coarse_bits, 0, sizeof(uint32_t) * coarse_words(cfg), st));
     GRID_CUDA(cudaMemsetAsync(record_writer, 0xFF, sizeof(int32_t) * (size_t)max_o, st));
     GRID_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)max_o, st));
+    GRID_CUDA(cudaMemsetAsync(G->knn_brick, 0, sizeof(uint4) * (size_t)nbrick, st));
 
     if (actual_n > 0) {
         const int nb = cdiv(actual_n, T);
@@ -379,9 +507,24 @@ extern "C" int sgn_grid_build(const float* xyz, int64_t N, int64_t actual_n, con
         GRID_TRY(exclusive_scan_i32(ncap, G->slot_start, max_o, partials, st));
         launch(emit_cand_kernel, cdiv(max_o, T), T, 0, st, max_o, xyz, seg_start, seg, G->slot_start, G->cand, G->counters);
         launch(dilate_kernel, cdiv(max_o, T), T, 0, st, g, G->counters, G->slot_coor, G->occ_bits, G->coarse_bits);
+        launch(brick_mark_kernel, cdiv(max_o, T), T, 0, st, g, G->counters, G->slot_coor, G->slot_start, G->knn_brick);
+        launch(brick_count_kernel, cdiv(nbrick, T), T, 0, st, nbrick, G->knn_brick, brick_cnt);
+        GRID_TRY(exclusive_scan_i32(brick_cnt, brick_base, nbrick, partials, st));
+        launch(brick_base_kernel, cdiv(nbrick, T), T, 0, st, nbrick, brick_base, G->knn_brick);
+        launch(brick_list_kernel, cdiv(max_o, T), T, 0, st, g, G->counters, G->slot_coor, G->slot_start, G->knn_brick, G->knn_list);
+        launch(word_popc_kernel, cdiv(nwords, T), T, 0, st, nwords, G->occ_bits, word_cnt);
+        GRID_TRY(exclusive_scan_i32(word_cnt, G->occ_rank, nwords, partials, st));
+        if (G->nbr_ok) {
+            GRID_CUDA(cudaMemsetAsync(nbr_cnt, 0, sizeof(int32_t) * (size_t)(nsv + 1), st));
+            launch(nbr_list_kernel<false>, cdiv(vol, T), T, 0, st, g, G->nby, G->nbz, vol, G->occ_bits, G->occ_rank, G->knn_brick, G->knn_list, nbr_cnt, (uint32_t*)nullptr);
+            GRID_TRY(exclusive_scan_i32(nbr_cnt, G->nbr_off, nsv, partials, st));
+            launch(nbr_list_kernel<true>, cdiv(vol, T), T, 0, st, g, G->nby, G->nbz, vol, G->occ_bits, G->occ_rank, G->knn_brick, G->knn_list, G->nbr_off, G->nbr_ent);
+        }
         GRID_CUDA(cudaGetLastError());
     } else {
         GRID_CUDA(cudaMemsetAsync(G->slot_start, 0, sizeof(int32_t) * ((size_t)max_o + 1), st));
+        GRID_CUDA(cudaMemsetAsync(G->occ_rank, 0, sizeof(int32_t) * (size_t)(nwords + 1), st));
+        if (G->nbr_ok) GRID_CUDA(cudaMemsetAsync(G->nbr_off, 0, sizeof(int32_t) * (size_t)(nsv + 1), st));
     }
 #undef GRID_TRY
 #undef GRID_CUDA
@@ -407,6 +550,8 @@ extern "C" int sgn_grid_buffer(const SgnGrid* g, int which, void** ptr, int64_t*
         case 5: *ptr = g->cand; *n = g->N; break;
         case 6: *ptr = g->counters; *n = 4; break;
         case 7: *ptr = g->coarse_bits; *n = (int64_t)coarse_words(&g->cfg); break;
+        case 8: *ptr = g->knn_brick; *n = 4 * brick_count(&g->cfg); break;
+        case 9: *ptr = g->knn_list; *n = 2 * ((int64_t)g->cfg.max_o + 1); break;
         default: set_error("sgn_grid_buffer: unknown buffer %d", which); return SGN_E_INVALID;
     }
     return SGN_OK;

@@ -26,98 +26,173 @@ struct QueryGrid {
     const float4* cand;
     const uint32_t* coarse_bits;   // 8^3-voxel bricks that may hold an occupied voxel (grid.cu:dilate_kernel)
     int cdx, cdy, cdz;
+    const uint4* knn_brick;        // 4^3-voxel bricks: mask of voxels with a candidate list + rank of the first one (grid.cu:brick_*_kernel)
+    const int2* knn_list;          // rank -> (first candidate, count)
+    int nby, nbz;
+    const int32_t* occ_rank;       // neighbour lists per sample voxel (grid.cuh); nbr_off == nullptr when they were not built
+    const int32_t* nbr_off;
+    const uint32_t* nbr_ent;
 };
 
-constexpr int MARCH_WARPS = 8;
+constexpr int MARCH_THREADS = 128;
+constexpr int MARCH_RANGES = 14;   // candidate ranges kept per ray (more are merged into the last one: tests a few extra candidates, never fewer)
 
-__global__ void __launch_bounds__(MARCH_WARPS * 32)
+// march_kernel: empty space is skipped with a 3-D DDA over the 8^3-voxel brick mask, one THREAD per ray: a step per brick (0.128 m at
+// the canonical voxel size) instead of a test per depth candidate (0.02 m).  The walk only produces index ranges [k_lo, k_hi] of the
+// candidates whose depth falls in a run of set bricks; the exact test of those -- voxel coordinate exactly as the reference computes
+// it, occupancy bit, running count (the reference's [R,D] mask + torch.cumsum, :843-844) -- is then done by the whole WARP, ray by ray
+// for its 32 rays, 32 candidates per step in depth order with ballot + popcount ranks, so the first SR occupied candidates land in the
+// same slots.  Why no candidate is lost: the bricks' intervals partition the ray's parameter range and candidate k is assigned to the
+// brick whose interval holds t[k]; that brick contains a point within ~1e-5 m (fp32 rounding of the DDA planes and of campos +
+// raydir * t) of the candidate's position, and grid.cu:dilate_kernel sets every brick holding a voxel equal or ADJACENT to an
+// occupied one, so the brick of an occupied candidate is always set.  Rays of a warp are neighbouring pixels and step through
+// nearly the same bricks.
+__global__ void __launch_bounds__(MARCH_THREADS)
 march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restrict__ raydir, const float* __restrict__ t,
              int t_per_ray, int64_t R, int D, int SR, const int32_t* __restrict__ ray_label, float* __restrict__ sample_loc_w,
              int32_t* __restrict__ sample_mask, int32_t* __restrict__ sample_label, int8_t* __restrict__ ray_mask)
 {
+    __shared__ uint32_t s_rng[MARCH_RANGES][MARCH_THREADS];      // k_lo | k_hi << 16
+    __shared__ uint8_t s_nr[MARCH_THREADS];
     const int lane = lane_id();
-    const int64_t r = (int64_t)blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
-    if (r >= R) return;
+    const int64_t r = (int64_t)blockIdx.x * MARCH_THREADS + threadIdx.x;
     const float cx = campos[0], cy = campos[1], cz = campos[2];
-    const float dx = raydir[3 * r], dy = raydir[3 * r + 1], dz = raydir[3 * r + 2];
-    const float* tr = t_per_ray ? t + r * D : t;
-    const int label = ray_label ? ray_label[r] : 0;
     const float rvx = 1.0f / g.vx, rvy = 1.0f / g.vy, rvz = 1.0f / g.vz;
-    const float fdx = (float)g.dx + 0.01f, fdy = (float)g.dy + 0.01f, fdz = (float)g.dz + 0.01f;
-    __shared__ uint16_t s_queue[MARCH_WARPS][64];            // per warp: depth indices that passed the brick test, in ray order
-    uint16_t* queue = s_queue[threadIdx.x >> 5];
-    int cnt = 0, qn = 0;
-    // exact test of up to 32 queued candidates (lane i takes entry i): voxel coordinate as the reference computes it, occupancy bit,
-    // rank among the ray's occupied candidates by ballot + popcount (the reference's torch.cumsum, :843-844), sample store
-    auto drain = [&](int n) {
-        bool occ = false;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (lane < n) {
-            const float tv = __ldg(tr + queue[lane]);
-            // campos + raydir * t with separate fp32 multiply and add, as torch evaluates it
-            px = __fadd_rn(cx, __fmul_rn(dx, tv));
-            py = __fadd_rn(cy, __fmul_rn(dy, tv));
-            pz = __fadd_rn(cz, __fmul_rn(dz, tv));
-            const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
-            if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
-                const uint32_t c = ((uint32_t)vx * (uint32_t)g.dy + (uint32_t)vy) * (uint32_t)g.dz + (uint32_t)vz;   // < 2^31 (grid.cu:check_cfg)
-                occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
-            }
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, occ);
-        const int rank = cnt + __popc(b & ((1u << lane) - 1u));
-        if (occ && rank < SR) {
-            const int64_t o = r * SR + rank;
-            sample_loc_w[3 * o] = px; sample_loc_w[3 * o + 1] = py; sample_loc_w[3 * o + 2] = pz;
-            sample_mask[o] = 1;
-            if (sample_label) sample_label[o] = label;
-        }
-        cnt += __popc(b);
-    };
-    for (int base = 0; base < D && cnt < SR; base += 32) {
-        const int d = base + lane;
-        bool maybe = false;
-        if (d < D) {
-            // brick test: approximate voxel coordinate (a few 1e-5 off at most), 8^3-voxel brick, one bit.  The mask covers every brick
-            // with an occupied voxel inside or one voxel away, so a candidate that fails it cannot be occupied whatever the rounding;
-            // only the others are queued for the exact test, and the queue keeps them in ray order.
-            const float tv = __ldg(tr + d);
-            const float ax = (__fadd_rn(cx, __fmul_rn(dx, tv)) - g.ox) * rvx, ay = (__fadd_rn(cy, __fmul_rn(dy, tv)) - g.oy) * rvy,
-                        az = (__fadd_rn(cz, __fmul_rn(dz, tv)) - g.oz) * rvz;
-            if (ax > -0.01f && ay > -0.01f && az > -0.01f && ax < fdx && ay < fdy && az < fdz) {
-                const int bx = min((int)(ax * 0.125f), g.cdx - 1), by = min((int)(ay * 0.125f), g.cdy - 1), bz = min((int)(az * 0.125f), g.cdz - 1);
+    // ---- phase A: brick walk of this thread's ray -> candidate ranges
+    int nr = 0;
+    if (r < R) {
+        const float dx = raydir[3 * r], dy = raydir[3 * r + 1], dz = raydir[3 * r + 2];
+        const float* tr = t_per_ray ? t + r * D : t;
+        // brick coordinates along the ray: q(t) = A + B t
+        const float Ax = (cx - g.ox) * rvx * 0.125f, Ay = (cy - g.oy) * rvy * 0.125f, Az = (cz - g.oz) * rvz * 0.125f;
+        const float Bx = dx * rvx * 0.125f, By = dy * rvy * 0.125f, Bz = dz * rvz * 0.125f;
+        const float t_first = __ldg(tr), t_last = __ldg(tr + D - 1);
+        const float inv_dt = D > 1 ? (float)(D - 1) / fmaxf(t_last - t_first, 1e-20f) : 0.f;
+        // clip to the grid box grown by 0.02 brick (2.5 mm): a candidate in a boundary voxel is never clipped away by rounding
+        const float PAD = 0.02f;
+        float t0 = t_first - 1e-3f, t1 = t_last + 1e-3f;
+        auto slab = [&](float A, float B, float hi) {
+            if (fabsf(B) < 1e-12f) { if (A < -PAD || A > hi + PAD) t1 = -1e30f; return; }
+            const float ib = 1.0f / B;
+            float ta = (-PAD - A) * ib, tb = (hi + PAD - A) * ib;
+            if (ta > tb) { const float x = ta; ta = tb; tb = x; }
+            t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+        };
+        slab(Ax, Bx, (float)g.dx * 0.125f); slab(Ay, By, (float)g.dy * 0.125f); slab(Az, Bz, (float)g.dz * 0.125f);
+        if (t1 >= t0) {
+            auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+            int bx = clampi((int)floorf(Ax + Bx * t0), g.cdx - 1), by = clampi((int)floorf(Ay + By * t0), g.cdy - 1),
+                bz = clampi((int)floorf(Az + Bz * t0), g.cdz - 1);
+            const int sx = Bx > 0.f ? 1 : -1, sy = By > 0.f ? 1 : -1, sz = Bz > 0.f ? 1 : -1;
+            const float ibx = fabsf(Bx) < 1e-12f ? 0.f : 1.0f / Bx, iby = fabsf(By) < 1e-12f ? 0.f : 1.0f / By, ibz = fabsf(Bz) < 1e-12f ? 0.f : 1.0f / Bz;
+            // parameter at which the ray leaves brick b along one axis (planes are recomputed, not accumulated: no drift)
+            auto cross = [](int b, int sgn, float A, float ib) { return ib == 0.f ? 3e38f : ((float)(b + (sgn > 0 ? 1 : 0)) - A) * ib; };
+            float tx = cross(bx, sx, Ax, ibx), ty = cross(by, sy, Ay, iby), tz = cross(bz, sz, Az, ibz);
+            int k = 0;
+            // first index with t[k] > tt, never moving backwards: guess from the mean spacing, then exact
+            auto seek = [&](float tt) {
+                int kg = (int)((tt - t_first) * inv_dt) - (t_per_ray ? 12 : 2);
+                if (kg > D) kg = D;
+                const int k0 = k;
+                if (kg > k) k = kg;
+                while (k > k0 && __ldg(tr + k - 1) > tt) k--;
+                while (k < D && __ldg(tr + k) <= tt) k++;
+            };
+            float tcur = t0;
+            // candidates at or before the box entry can only belong to it through rounding: keep them with the first brick
+            { int kg = (int)((t0 - t_first) * inv_dt) - (t_per_ray ? 12 : 2); if (kg > D) kg = D; if (kg > 0) k = kg;
+              while (k > 0 && __ldg(tr + k - 1) >= t0) k--;
+              while (k < D && __ldg(tr + k) < t0) k++; }
+            bool open = false;
+            int lo = 0;
+            auto push = [&](int a, int b2) {
+                if (b2 < a) return;
+                if (nr == MARCH_RANGES) { s_rng[nr - 1][threadIdx.x] = (s_rng[nr - 1][threadIdx.x] & 0xffffu) | ((uint32_t)b2 << 16); return; }
+                s_rng[nr++][threadIdx.x] = (uint32_t)a | ((uint32_t)b2 << 16);
+            };
+            while (k < D && tcur <= t1) {
+                const float tnext = fminf(fminf(tx, ty), tz);
                 const int bc = (bx * g.cdy + by) * g.cdz + bz;
-                maybe = (__ldg(g.coarse_bits + (bc >> 5)) >> (bc & 31)) & 1u;
+                const bool set = (__ldg(g.coarse_bits + (bc >> 5)) >> (bc & 31)) & 1u;
+                if (set && !open) { if (tcur > t0) seek(tcur); lo = k; open = true; }
+                else if (!set && open) { seek(tcur); push(lo, k - 1); open = false; }
+                // step into the next brick
+                bool out_of_box;
+                if (tx <= ty && tx <= tz) { bx += sx; out_of_box = (unsigned)bx >= (unsigned)g.cdx; tx = cross(bx, sx, Ax, ibx); }
+                else if (ty <= tz)        { by += sy; out_of_box = (unsigned)by >= (unsigned)g.cdy; ty = cross(by, sy, Ay, iby); }
+                else                      { bz += sz; out_of_box = (unsigned)bz >= (unsigned)g.cdz; tz = cross(bz, sz, Az, ibz); }
+                tcur = tnext;
+                if (out_of_box) break;
+            }
+            if (open) { seek(fminf(tcur, t1)); push(lo, k - 1); }
+        }
+        ray_mask[r] = 0;
+    }
+    s_nr[threadIdx.x] = (uint8_t)nr;
+    __syncwarp();
+    // ---- phase B: the warp tests the candidates of its 32 rays, ray by ray, 32 candidates at a time in depth order
+    const int64_t r0 = r - lane;
+    const int w0 = threadIdx.x - lane;
+    for (int j = 0; j < 32; j++) {
+        const int64_t rj = r0 + j;
+        if (rj >= R) break;
+        const int n_rng = s_nr[w0 + j];
+        int cnt = 0;
+        if (n_rng > 0) {
+            const float dx = raydir[3 * rj], dy = raydir[3 * rj + 1], dz = raydir[3 * rj + 2];
+            const float* tr = t_per_ray ? t + rj * D : t;
+            const int label = ray_label ? ray_label[rj] : 0;
+            // lane i holds range i; the candidates of all ranges form one sequence, 32 consecutive elements per step
+            const uint32_t mine = lane < n_rng ? s_rng[lane][w0 + j] : 0u;
+            const int my_lo = (int)(mine & 0xffffu), my_len = lane < n_rng ? (int)(mine >> 16) - my_lo + 1 : 0;
+            int inc = my_len;                                  // inclusive prefix of the range lengths
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+            const int total = __shfl_sync(0xffffffffu, inc, MARCH_RANGES - 1 < 31 ? 15 : 31);
+            for (int base = 0; base < total && cnt < SR; base += 32) {
+                const int p = base + lane;
+                int k = -1;
+                for (int i = 0; i < n_rng; i++) {              // range that holds element p (n_rng is the same for the whole warp)
+                    const int end_i = __shfl_sync(0xffffffffu, inc, i);
+                    const uint32_t rg = __shfl_sync(0xffffffffu, mine, i);
+                    if (k < 0 && p < end_i) k = (int)(rg >> 16) - (end_i - 1 - p);
+                }
+                bool occ = false;
+                float px = 0.f, py = 0.f, pz = 0.f;
+                if (k >= 0 && p < total) {
+                    const float tv = __ldg(tr + k);
+                    // campos + raydir * t with separate fp32 multiply and add, as torch evaluates it
+                    px = __fadd_rn(cx, __fmul_rn(dx, tv)); py = __fadd_rn(cy, __fmul_rn(dy, tv)); pz = __fadd_rn(cz, __fmul_rn(dz, tv));
+                    const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
+                    if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
+                        const uint32_t c = ((uint32_t)vx * (uint32_t)g.dy + (uint32_t)vy) * (uint32_t)g.dz + (uint32_t)vz;   // < 2^31 (grid.cu:check_cfg)
+                        occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, occ);
+                const int rank = cnt + __popc(bal & ((1u << lane) - 1u));
+                if (occ && rank < SR) {
+                    const int64_t o = rj * SR + rank;
+                    sample_loc_w[3 * o] = px; sample_loc_w[3 * o + 1] = py; sample_loc_w[3 * o + 2] = pz;
+                    sample_mask[o] = 1;
+                    if (sample_label) sample_label[o] = label;
+                }
+                cnt += __popc(bal);
             }
         }
-        const unsigned mb = __ballot_sync(0xffffffffu, maybe);
-        if (mb == 0u) continue;
-        if (maybe) queue[qn + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)d;
-        qn += __popc(mb);
-        __syncwarp();
-        if (qn >= 32) {
-            drain(32);
-            const uint16_t carry = queue[32 + lane];             // at most 31 entries stay behind
-            __syncwarp();
-            queue[lane] = carry;
-            qn -= 32;
-            __syncwarp();
+        // unused slots stay at world (0,0,0), mask 0 (:835, :845)
+        for (int sl = (cnt < SR ? cnt : SR) + lane; sl < SR; sl += 32) {
+            const int64_t o = rj * SR + sl;
+            sample_loc_w[3 * o] = 0.f; sample_loc_w[3 * o + 1] = 0.f; sample_loc_w[3 * o + 2] = 0.f;
+            sample_mask[o] = 0;
+            if (sample_label) sample_label[o] = 0;
         }
     }
-    if (qn > 0 && cnt < SR) drain(qn);
-    cnt = cnt < SR ? cnt : SR;
-    for (int s = cnt + lane; s < SR; s += 32) {  // unused slots stay at world (0,0,0), mask 0 (:835, :845)
-        const int64_t o = r * SR + s;
-        sample_loc_w[3 * o] = 0.f; sample_loc_w[3 * o + 1] = 0.f; sample_loc_w[3 * o + 2] = 0.f;
-        sample_mask[o] = 0;
-        if (sample_label) sample_label[o] = 0;
-    }
-    if (lane == 0) ray_mask[r] = 0;
 }
 
 constexpr int KNN_SLOTS = 1536;   // sample slots per block (64 rays at SR = 24): their occupied samples are compacted in shared memory so that all lanes work
 constexpr int KNN_THREADS = 128;
-constexpr int KNN_MAX_CELLS = 27;  // cell-list entries per thread kept in shared memory (a 3^3 block; larger kernels take the nested-loop path)
+constexpr int KNN_BINS = 64;      // candidate-count bins of the in-block counting sort
 
 // One candidate against the K slots, exactly the reference's rule (:650-676): fill the first K slots in order, then replace the
 // farthest one when the new candidate is strictly nearer and rescan for the new farthest (first index wins ties).
@@ -153,8 +228,8 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
            const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
            int8_t* __restrict__ ray_mask, int rays_per_block, int flat_ok)
 {
-    extern __shared__ int32_t s_list[];                       // [rays_per_block * SR] sample indices (relative to the block's first slot)
-    __shared__ uint32_t s_cells[KNN_MAX_CELLS][KNN_THREADS];  // per-thread list of occupied voxels: begin (24 bits) | count (7 bits) << 24 | new-shell flag (bit 31)
+    extern __shared__ int32_t s_list[];                       // [slots_cap] sample indices (relative to the block's first slot), then s_off / s_sorted / s_nent / s_key
+    const int slots_cap = (rays_per_block * SR + 3) & ~3;
     __shared__ int s_count;
     const int64_t slot0 = (int64_t)blockIdx.x * rays_per_block * SR;
     const int nslot = (int)min((int64_t)rays_per_block * SR, R * SR - slot0);
@@ -170,13 +245,58 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
         if (occ) s_list[base + __popc(b & ((1u << lane_id()) - 1u))] = i;
         else if (i < nslot) {
             int32_t* o = sample_pidx + (slot0 + i) * K;
-            for (int k = 0; k < K; k++) o[k] = -1;
+            if (KT == 8 && K == 8) { ((int4*)o)[0] = make_int4(-1, -1, -1, -1); ((int4*)o)[1] = make_int4(-1, -1, -1, -1); }
+            else for (int k = 0; k < K; k++) o[k] = -1;
         }
     }
     __syncthreads();
     const int nq = s_count;
-    const bool flat = nlayer <= 2 && flat_ok;                 // 3^3 block, candidate indices < 2^24, at most 127 candidates per voxel: the list fits
-    for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+    const bool flat = nlayer <= 2 && flat_ok;                 // 3^3 (or 1^3) block and prebuilt neighbour lists (candidate indices < 2^24, P < 128)
+    // pass 2 (lists only): the sample's voxel -> its neighbour list (grid.cu:nbr_list_kernel) and the number of candidates it holds; the
+    // queue is then counting-sorted by that number, so that the 32 samples a warp takes together run loops of nearly the same length
+    // (samples are independent and results go by index, so the processing order is free).
+    int32_t* s_off = s_list + slots_cap;                      // first list entry of the queued sample
+    uint16_t* s_sorted = (uint16_t*)(s_off + slots_cap);      // queue positions ordered by candidate count
+    uint8_t* s_nent = (uint8_t*)(s_sorted + slots_cap);       // entries in the list (<= 27)
+    uint8_t* s_key = s_nent + slots_cap;
+    __shared__ int s_hist[KNN_BINS + 1];
+    if (flat) {
+        for (int i = threadIdx.x; i <= KNN_BINS; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+            const int64_t idx = slot0 + s_list[qi];
+            const int fx = vox_coord(sample_loc_w[3 * idx], g.ox, g.vx), fy = vox_coord(sample_loc_w[3 * idx + 1], g.oy, g.vy),
+                      fz = vox_coord(sample_loc_w[3 * idx + 2], g.oz, g.vz);
+            const uint32_t c = ((uint32_t)fx * (uint32_t)g.dy + (uint32_t)fy) * (uint32_t)g.dz + (uint32_t)fz;
+            const uint32_t w = __ldg(g.occ_bits + (c >> 5));
+            const int vr = __ldg(g.occ_rank + (c >> 5)) + __popc(w & ((1u << (c & 31)) - 1u));
+            const int ci = __ldg(g.nbr_off + vr), ce = __ldg(g.nbr_off + vr + 1);
+            int total = 0;
+            for (int j = ci; j < ce; j++) total += (int)((__ldg(g.nbr_ent + j) >> 24) & 127u);
+            const int key = total < KNN_BINS - 1 ? total : KNN_BINS - 1;
+            s_off[qi] = ci; s_nent[qi] = (uint8_t)(ce - ci); s_key[qi] = (uint8_t)key;
+            atomicAdd(&s_hist[key], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                               // exclusive scan of the histogram, largest counts first
+            int carry = 0;
+            for (int b0 = 0; b0 < KNN_BINS; b0 += 32) {
+                const int bin = KNN_BINS - 1 - (b0 + lane_id());
+                const int v = s_hist[bin];
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane_id() >= o) inc += n; }
+                __syncwarp();
+                s_hist[bin] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncthreads();
+        for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) s_sorted[atomicAdd(&s_hist[s_key[qi]], 1)] = (uint16_t)qi;
+        __syncthreads();
+    }
+    for (int pos = threadIdx.x; pos < nq; pos += blockDim.x) {
+        const int qi = flat ? (int)s_sorted[pos] : pos;
         const int64_t idx = slot0 + s_list[qi];
         const int64_t r = idx / SR;
         int32_t out[KT];
@@ -185,7 +305,6 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
         for (int i = 0; i < KT; i++) { out[i] = -1; buf[i] = 0.f; }
         int kid = 0;
         const float cx = sample_loc_w[3 * idx], cy = sample_loc_w[3 * idx + 1], cz = sample_loc_w[3 * idx + 2];
-        const int fx = vox_coord(cx, g.ox, g.vx), fy = vox_coord(cy, g.oy, g.vy), fz = vox_coord(cz, g.oz, g.vz);
         const int center_label = SEMANTIC ? sample_label[idx] : 0;
         int far_ind = 0;
         float far2 = 0.0f;
@@ -204,75 +323,56 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
             if (radius2 == 0.0f || d2 <= radius2) knn_insert<KT>(pidx, d2, K, kid, far_ind, far2, out, buf);
         };
         if (flat) {
-            // ---- phase 1: the voxels of the 3^3 block in visiting order -- centre (shell 0), then x outer / y / z inner without the
-            // centre (shell 1; nlayer == 1 stops after the centre).  All voxel reads are issued before any is used, then the
-            // candidate ranges of the occupied ones nine at a time: two or three memory latencies instead of one per voxel.
-            int occ[27];
-#pragma unroll
-            for (int i = 0; i < 27; i++) {
-                const int l = i == 0 ? 13 : (i - 1 < 13 ? i - 1 : i);
-                const int x = l / 9 - 1, y = (l / 3) % 3 - 1, z = l % 3 - 1;
-                const bool in = (i == 0 || nlayer > 1) && (unsigned)(fx + x) < (unsigned)g.dx && (unsigned)(fy + y) < (unsigned)g.dy &&
-                                (unsigned)(fz + z) < (unsigned)g.dz;
-                occ[i] = in ? __ldg(g.cell_slot + ((int64_t)(fx + x) * g.dy + (fy + y)) * g.dz + (fz + z)) : -1;
-            }
-            int nc = 0;
-            unsigned shell1 = 0x80000000u;
-#pragma unroll
-            for (int grp = 0; grp < 3; grp++) {
-                int b[9], e[9];
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    const int o = occ[9 * grp + j];
-                    b[j] = o >= 0 ? __ldg(g.slot_start + o) : 0;
-                    e[j] = o >= 0 ? __ldg(g.slot_start + o + 1) : 0;
-                }
-#pragma unroll
-                for (int j = 0; j < 9; j++) {
-                    if (e[j] > b[j]) {
-                        unsigned flag = 0u;
-                        if (9 * grp + j > 0) { flag = shell1; shell1 = 0u; }
-                        s_cells[nc++][threadIdx.x] = (uint32_t)b[j] | ((uint32_t)(e[j] - b[j]) << 24) | flag;
-                    }
-                }
-            }
-            // ---- phase 2: the candidates of the list, one per iteration; the next candidate's record is requested before the
-            // current one is processed (its address never depends on the outcome, only whether it is used does)
-            int ci = 0, q = 0, e = 0;
-            bool live = nc > 0;
+            // the prebuilt neighbour list of the sample's voxel: the occupied voxels of the 3^3 block in the reference's visiting order,
+            // one 4-byte entry each (first candidate | count << 24 | "shell 1 starts here" << 31)
+            int ci = s_off[qi];
+            const int ce = ci + (int)s_nent[qi];
+            // one flat loop over the candidates of the list; the next candidate's record (and the next list entry) is requested before
+            // the current one is processed -- its address never depends on the outcome, only whether it is used does
+            int q = 0, e = 0;
+            bool live = ci < ce;
             float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live) { const uint32_t c0 = s_cells[0][threadIdx.x]; q = (int)(c0 & 0xffffffu); e = q + (int)((c0 >> 24) & 127u); cur = __ldg(g.cand + q); }
+            uint32_t nent = 0u;
+            if (live) {
+                const uint32_t c0 = __ldg(g.nbr_ent + ci);
+                q = (int)(c0 & 0xffffffu); e = q + (int)((c0 >> 24) & 127u); cur = __ldg(g.cand + q);
+                if (ci + 1 < ce) nent = __ldg(g.nbr_ent + ci + 1);
+            }
             while (live) {
                 bool nxt_live = true, nxt_shell = false;
                 if (++q == e) {
-                    if (++ci == nc) nxt_live = false;
+                    if (++ci == ce) nxt_live = false;
                     else {
-                        const uint32_t cn = s_cells[ci][threadIdx.x];
-                        nxt_shell = (cn >> 31) != 0u;
-                        q = (int)(cn & 0xffffffu); e = q + (int)((cn >> 24) & 127u);
+                        nxt_shell = (nent >> 31) != 0u;
+                        q = (int)(nent & 0xffffffu); e = q + (int)((nent >> 24) & 127u);
+                        if (ci + 1 < ce) nent = __ldg(g.nbr_ent + ci + 1);
                     }
                 }
                 float4 nxt = cur;
                 if (nxt_live) nxt = __ldg(g.cand + q);
                 candidate(cur);
-                if (nxt_shell && kid >= K) nxt_live = false;          // a new shell starts: the reference stops once K were found (:678)
+                // a new shell starts: the reference stops once K were found (:678); with a 1^3 kernel it never looks past the centre
+                if (nxt_shell && (kid >= K || nlayer < 2)) nxt_live = false;
                 cur = nxt; live = nxt_live;
             }
         } else {
+            const int fx = vox_coord(cx, g.ox, g.vx), fy = vox_coord(cy, g.oy, g.vy), fz = vox_coord(cz, g.oz, g.vz);
             for (int layer = 0; layer < nlayer; layer++) {
                 const int xlo = max(-fx, -layer), xhi = min(g.dx - fx, layer + 1);
                 const int ylo = max(-fy, -layer), yhi = min(g.dy - fy, layer + 1);
                 const int zlo = max(-fz, -layer), zhi = min(g.dz - fz, layer + 1);
                 for (int x = xlo; x < xhi; x++) {
                     for (int y = ylo; y < yhi; y++) {
-                        const int64_t rowbase = ((int64_t)(fx + x) * g.dy + (fy + y)) * g.dz + fz;
                         const bool inner = max(abs(x), abs(y)) != layer;
                         for (int z = zlo; z < zhi; z++) {
                             if (inner && abs(z) != layer) continue;
-                            const int occ = __ldg(g.cell_slot + rowbase + z);
-                            if (occ < 0) continue;
-                            const int b = __ldg(g.slot_start + occ), e = __ldg(g.slot_start + occ + 1);
-                            for (int q = b; q < e; q++) candidate(__ldg(g.cand + q));
+                            const int vx = fx + x, vy = fy + y, vz = fz + z;
+                            const uint4 be = __ldg(g.knn_brick + ((int64_t)(vx >> 2) * g.nby + (vy >> 2)) * g.nbz + (vz >> 2));
+                            const int bit = ((vx & 3) * 4 + (vy & 3)) * 4 + (vz & 3);
+                            const unsigned long long m = ((unsigned long long)be.y << 32) | be.x;
+                            if (!((m >> bit) & 1ull)) continue;
+                            const int2 li = __ldg(g.knn_list + (int)be.z + __popcll(m & ((1ull << bit) - 1ull)));
+                            for (int q = li.x; q < li.x + li.y; q++) candidate(__ldg(g.cand + q));
                         }
                     }
                 }
@@ -315,9 +415,11 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     g.dx = G->cfg.dim[0]; g.dy = G->cfg.dim[1]; g.dz = G->cfg.dim[2];
     g.cell_slot = G->cell_slot; g.occ_bits = G->occ_bits; g.slot_start = G->slot_start; g.cand = G->cand;
     g.coarse_bits = G->coarse_bits; g.cdx = (g.dx + 7) >> 3; g.cdy = (g.dy + 7) >> 3; g.cdz = (g.dz + 7) >> 3;
+    g.knn_brick = G->knn_brick; g.knn_list = G->knn_list; g.nby = G->nby; g.nbz = G->nbz;
+    g.occ_rank = G->occ_rank; g.nbr_off = G->nbr_off; g.nbr_ent = G->nbr_ent;
 
-    launch(march_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
-                                                                   sample_mask, semantic ? sample_label : nullptr, ray_mask);
+    launch(march_kernel, cdiv(R, MARCH_THREADS), MARCH_THREADS, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
+                                                                sample_mask, semantic ? sample_label : nullptr, ray_mask);
     const int nlayer = (kernel_size0 + 1) / 2;
     // rays per block: up to KNN_SLOTS sample slots (6 KB list), fewer for small ray counts (a training patch) so that the grid still
     // covers the 148 SMs several times over, but never fewer slots than the block has threads
@@ -325,8 +427,8 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     const int rpb_fill = (int)(R / (148 * 8)), rpb_min = cdiv(128, SR);
     if (rpb > rpb_fill) rpb = rpb_fill > rpb_min ? rpb_fill : (rpb_min < rpb ? rpb_min : rpb);
     const int nb = cdiv(R, rpb);
-    const int flat_ok = (G->N < (1ll << 24) && G->cfg.P < 128) ? 1 : 0;
-    const size_t ksm = (size_t)rpb * SR * sizeof(int32_t);
+    const int flat_ok = G->nbr_ok;
+    const size_t ksm = (size_t)((rpb * SR + 3) & ~3) * (4 + 4 + 2 + 1 + 1);
     if (K == 8) {
         if (semantic)
             launch(knn_kernel<8, true>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,

@@ -371,7 +371,7 @@ class _Aggregate(torch.autograd.Function):
                   _ptr(meta.loc_w), _ptr(meta.raydir), _ptr(meta.campos), _ptr(meta.camrot), R, SR, K,
                   meta.precision if BACKWARD_PRECISION_OVERRIDE is None else int(BACKWARD_PRECISION_OVERRIDE), _ptr(g_decoded),
                   _ptr(g_conf_c), _ptr_array(d_w), _ptr_array(d_b), C.byref(gr), _ptr(ctx.ws), ctx.ws.numel() * 4, _stream())
-        ctx.ws = None
+        # the saved workspace stays with ctx (a second backward under retain_graph reads it again); autograd frees it with the graph
         return (None, d_emb, d_col, d_dir, d_conf, *d_w, *d_b)
 
 

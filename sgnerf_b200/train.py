@@ -22,10 +22,11 @@ class TrainStep:
     state and set kernel attributes, and they are real optimiser steps -- then captures the step and replays the capture from then on."""
 
     def __init__(self, scene, n_rays, near, far, bg_color, lr=5e-4, plr=2e-3, conf_loss_weight=1e-4, precision=ops.PRECISION_TF32,
-                 use_graph=True, train_dir=True, group=None):
+                 use_graph=True, train_dir=True, group=None, zero_epsilon=1e-3):
         """scene: pipeline.RenderScene (its tensors become the trainable leaves).  n_rays: rays per step on this rank (fixed)."""
         self.scene, self.n_rays, self.near, self.far = scene, int(n_rays), float(near), float(far)
         self.precision, self.conf_w, self.group = precision, float(conf_loss_weight), group
+        self.zero_eps = float(zero_epsilon)             # --zero_epsilon of the reference (base_rendering_model.py:119, default 1e-3)
         dev = scene.xyz.device
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.net_params = [t.requires_grad_(True) for t in scene.weights + scene.biases]
@@ -66,16 +67,23 @@ class TrainStep:
         q = self.scene.qopt
         out = pipeline.render_rays(self.scene, self.campos, self.camrot, self.raydir, self.near, self.far, self.bg,
                                    precision=self.precision, t=self.t, want_aux=True)
+        # the reference's loss (base_rendering_model.py:543-641) on uncompacted rows: colour MSE over the rays that hit the cloud
+        # (`ray_masked_coarse_raycolor`, + 1e-6 per colour item) and the zero-one regulariser mean(log(v) + log(1 - v)),
+        # v = clamp(conf_coefficient, eps, 1 - eps), over the [R'', SR, K] block of the hit rays.  Sums are normalised by the GLOBAL
+        # hit count (all ranks), and gradients are summed over ranks: the multi-GPU step is the single-GPU step on the union of rays.
         hit = (out.ray_mask > 0).float()
-        cnt = hit.sum().clamp(min=1.0)
+        cnt = hit.sum()
+        if self.world > 1:
+            dist.all_reduce(cnt, group=self.group)
+        cnt = cnt.clamp(min=1.0)
         mse = (((out.ray_color - self.gt) ** 2) * hit[:, None]).sum() / (3.0 * cnt)
-        conf = out.conf_coef
-        zo = ((torch.log(0.1 + conf) + torch.log(0.1 + 1.0 - conf) + 2.20727) * hit[:, None, None]).sum() / (cnt * q.SR * q.K)
-        loss = mse + self.conf_w * zo
+        v = out.conf_coef.clamp(self.zero_eps, 1.0 - self.zero_eps)
+        zo = ((torch.log(v) + torch.log(1.0 - v)) * hit[:, None, None]).sum() / (cnt * q.SR * q.K)
+        loss = mse + 1e-6 / self.world + self.conf_w * zo
         self.optim.zero_grad(set_to_none=True)
         loss.backward()
         if self.world > 1:
-            sdist.allreduce_grads(self.params, average=True, group=self.group)
+            sdist.allreduce_grads(self.params, average=False, group=self.group)
         self.optim.step()
         self.loss.copy_(loss.detach())
         self.n_hit.copy_(hit.sum())

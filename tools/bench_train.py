@@ -103,7 +103,7 @@ def main():
             rd = (rd * (1.0 - m) + m * float(vsize[2])) * ray_valid.float()
             ray_color = modules.ray_march(rd, ray_valid, decoded, render, blend, bg)[0]
             sel = ray_mask[0] > 0
-            loss = ((ray_color - gt[:, sel]) ** 2).mean() + 1e-4 * torch.mean(torch.log(0.1 + conf.reshape(-1)) + torch.log(0.1 + 1.0 - conf.reshape(-1)) + 2.20727)
+            loss = ((ray_color - gt[:, sel]) ** 2).mean() + 1e-6 + 1e-4 * torch.mean(torch.log(conf.reshape(-1).clamp(1e-3, 1 - 1e-3)) + torch.log(1.0 - conf.reshape(-1).clamp(1e-3, 1 - 1e-3)))
             optim.zero_grad(set_to_none=False)
             loss.backward()
             ev[1].record()
