@@ -2,8 +2,9 @@
 """bench.py -- rays/s of the SG-NeRF per-ray render hot path (BASELINE.json metric) on N B200s of one node.
 
     python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (default: bf16 tensor-core MLPs if built, else fp32)
-    python bench.py --impl reference --steps 3 --warmup 1     # the reference's algorithm on the host cores (oracle port)
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's own PointAggregator + ray_march (baseline/_ref) on the host cores
     torchrun ... bench.py --gpus N ...                        # one rank per GPU, rays of N frames, no data-path collective
+                                                              # (+ `strong`: ONE C1 / C3 / C4 frame ray-sharded over the N ranks)
 
 A "step" is one full-frame render (query + aggregation + compositing + fill) of the ScanNet-shaped
 config C1 of SURVEY.md section 8(d): 1M neural points, 640x480 = 307200 rays, K=8, SR=24, radius query.
@@ -196,8 +197,8 @@ def run_ours(args):
             return a.elapsed_time(b) / n, r
         query_ms, _ = timed_ms(lambda: ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2))
         dec_, val_, lp_, _, _ = ops.aggregate(scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs,
-                                              scene.conf, None, pidx, loc_w, raydir, campos, rot, precision=precision, want_aux=False)
-        tail_ms, _ = timed_ms(lambda: ops.render_composite(dec_, lp_, val_, rmask, hp.vsize[2], bg, blend=0))
+                                              scene.conf, None, pidx, loc_w, raydir, campos, rot, precision=precision, want_aux=False, depth_only=True)
+        tail_ms, _ = timed_ms(lambda: ops.render_composite(dec_, lp_, val_, rmask, hp.vsize[2], bg, blend=0, depth_array=True))
         n_touched = int(torch.unique(pidx[pidx >= 0]).numel())
         hit_rays = int((rmask > 0).sum())
         query_bytes = 24 * R + 4 * q.z_depth_dim + R + hit_rays * q.SR * (12 + 4 * q.K) + 12 * n_touched
@@ -213,6 +214,14 @@ def run_ours(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); scene.point_cache(); b.record(); torch.cuda.synchronize()
             pc_ms = a.elapsed_time(b)
+        # ---- cold frame: the cloud just changed -- grid and per-point tables rebuilt inside the timed region, then the frame
+        cold = []
+        for _ in range(2):
+            scene.invalidate_grid(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(); b.record(); torch.cuda.synchronize()
+            cold.append(a.elapsed_time(b))
+        cold_ms = min(cold)
         # ---- the semantic variant of C1 (block2_bpnet + 96-d label embedding per point), whole step, reported next to the headline ----
         sem_ms = None
         if precision == ops.PRECISION_BF16 and not args.no_semantic_variant:
@@ -259,7 +268,9 @@ def run_ours(args):
         clocks = sampler.stop()
 
     train = None if args.no_train_step else train_step_leg(s, scene, device, rank, world, dist, bg)
-    ref_gpu = reference_gpu_leg(s, P, tabs, device) if (world == 1 and rank == 0 and not args.no_reference_gpu) else None
+    strong = None if args.no_strong else strong_scaling_leg(device, rank, world, dist, precision, args)
+    # the reference's path on this GPU runs in its own process: this process maps nothing but libsgnerf_b200.so
+    ref_gpu = run_leg("reference_gpu", args) if (world == 1 and rank == 0 and not args.no_reference_gpu) else None
     tmax = torch.tensor([ms_total, e2e_ms], device=device, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -281,11 +292,12 @@ def run_ours(args):
                    "scene": "static: occupancy grid built once per cloud version, per-point first-layer tables (sgn_agg_point_cache_build) once per "
                             "(cloud, weights) version; both build times reported, neither is inside a step",
                    "grid_build_ms": grid_ms, "point_cache_build_ms": pc_ms,
+                   "cold_frame_ms": cold_ms, "cold_frame_what": "one frame with the occupancy grid and the per-point tables rebuilt first (the cloud just changed)",
                    "l2": "no explicit flush: per-step working set (indices 236 MB + positions 88 MB + K-sum image 1.4 GB + per-point rows 448 MB) exceeds the 126 MB L2",
                    "parallelism": f"ray-sharded x{world}, point cloud replicated, no collective on the render path",
                    "semantic_variant": None if sem_ms is None else {"what": "same frame with block2_bpnet + 96-d label embedding (rank 0)", "ms_per_step": sem_ms,
                                                                     "rays_per_s_per_gpu": R / (sem_ms * 1e-3)}},
-        "clocks": clocks, "gpu_launches": int(launches), "train_step": train, "reference_gpu": ref_gpu,
+        "clocks": clocks, "gpu_launches": int(launches), "train_step": train, "strong": strong, "reference_gpu": ref_gpu,
         "e2e": {"value": world * R / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(R * 12 + 48),
                 "d2h_bytes_per_step": int(R * 12),
                 "copies": "pinned host buffers; uploads and the result download run on copy streams and overlap the neighbouring steps' kernels",
@@ -310,7 +322,7 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(sample_rays=4 * args.cpu_sample)
+            line["cpu_baseline"] = run_leg("cpu_baseline", args)
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -370,6 +382,30 @@ def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
     return info
 
 
+def run_leg(name, args):
+    """Run one of the reference legs (oracle / baseline/_ref code) in a child process and return the JSON object it prints: the bench
+    process itself never imports `oracle` or maps its libraries."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--leg", name, "--cpu-sample", str(args.cpu_sample)]
+    try:
+        out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+        lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+        if out.returncode != 0 or not lines:
+            return {"error": f"leg {name} exited {out.returncode}: {out.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
+def reference_gpu_standalone():
+    from sgnerf_b200 import synth
+    device = "cuda:0"
+    torch.cuda.set_device(0)
+    s = synth.scene_room(N_POINTS, room=(8.0, 8.0, 3.0), width=WIDTH, height=HEIGHT, seed=1234)
+    tabs = synth.make_point_tables(N_POINTS, 32, 0, seed=0)
+    P = synth.make_mlp_params(synth.mlp_layer_shapes(), seed=0)
+    return reference_gpu_leg(s, P, tabs, device)
+
+
 def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
     """The reference's own path on this B200, beside ours (SURVEY.md section 8d "GPU (one B200)"): its CUDA query kernels compiled
     unchanged from the reference source (oracle/_ref, launched with the reference's geometry and torch glue by tests/ref_driver.py,
@@ -378,7 +414,7 @@ def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
     of chunks of the same C1 frame; wall clock per chunk including the reference's host synchronisations.  fp32 matmuls and, as
     the reference's pinned torch 1.10 defaults to, TF32 matmuls."""
     from types import SimpleNamespace
-    info = {"what": f"reference CUDA query kernels (per-call grid rebuild) + torch aggregator/ray_march on cuda, {chunk}-ray chunks"}
+    info = {"what": f"reference CUDA query kernels (per-call grid rebuild) + the reference's own PointAggregator / ray_march (baseline/_ref) on cuda, {chunk}-ray chunks"}
     try:
         from oracle import query_ref as qr
         from oracle import render_ref as rr
@@ -391,6 +427,10 @@ def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
         opt, cfg = qr.default_opt(SR=24), rr.agg_config()
         xyz = torch.from_numpy(s.xyz).to(device)[None]
         Pd = {k: v.to(device) for k, v in P.items()}
+        renderer = ReferenceRenderer(Pd, cfg)
+        if renderer.ref is not None:
+            renderer.agg.to(device)
+        info["aggregator"] = renderer.kind + (" (baseline/_ref PointAggregator + ray_march)" if renderer.kind == "reference" else " (oracle restatement: baseline/_ref not staged)")
         tables = SimpleNamespace(xyz=xyz[0], embedding=tabs.embedding.to(device), color=tabs.color.to(device), dir=tabs.dir.to(device),
                                  conf=tabs.conf.to(device), label_embedding=None)
         campos, rot = torch.from_numpy(s.campos).to(device)[None], torch.from_numpy(s.camrotc2w).to(device)[None]
@@ -413,7 +453,7 @@ def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
             dirs = rd[sel][None, :, None, :].expand(-1, -1, opt.SR, -1).contiguous()
             loc = rr.w2pers_points(loc_w.reshape(-1, 3), rot, campos).reshape(1, -1, opt.SR, 3)
             with torch.device(device):
-                rr.render_from_query(Pd, cfg, tables, pidx, loc, loc_w, dirs, mask, rot, campos, np.asarray(opt.vsize, np.float32), bg)
+                renderer(tables, pidx, loc, loc_w, dirs, mask, rot, campos, np.asarray(opt.vsize, np.float32), bg)
             return q1 - q0
 
         with torch.no_grad():
@@ -479,79 +519,235 @@ def reference_gpu_leg(s, P, tabs, device, n_chunks=4, chunk=2304):
     return info
 
 
-def cpu_reference_step(s, P, cfg, tabs, sel, opt, threads):
-    """One bounded sample of the workload on the host cores with the oracle port of the reference algorithm:
-    C query (single thread, sequential) + torch aggregator + ray_march (all host threads)."""
+def reference_classes():
+    """(namespace of the reference's own modules from baseline/_ref, or None): its PointAggregator, ray_march and render / blend functions,
+    unmodified (tests/ref_import.py; the files are staged by baseline/stage_reference.py in the build container)."""
+    try:
+        from tests import ref_import
+        return ref_import.reference_modules() if ref_import.available() else None
+    except Exception:
+        return None
+
+
+def reference_opt(cfg):
+    """The option fields the reference's PointAggregator reads, canonical values."""
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        act_type="LeakyReLU", point_hyper_dim=256, point_features_dim=cfg.point_features_dim, agg_distance_kernel="linear", agg_dist_pers=20,
+        agg_axis_weight=None, num_pos_freqs=10, num_viewdir_freqs=cfg.num_viewdir_freqs, view_ori=0, which_agg_model="viewmlp",
+        dist_xyz_freq=cfg.dist_xyz_freq, agg_feat_xyz_mode="None", weight_feat_dim=8, weight_xyz_freq=2, sh_degree=4,
+        num_feat_freqs=cfg.num_feat_freqs, agg_intrp_order=2, shading_feature_mlp_layer1=cfg.shading_feature_mlp_layer1,
+        shading_feature_num=cfg.shading_feature_num, shading_feature_mlp_layer2=0, shading_feature_mlp_layer2_bpnet=0, predict_semantic=0,
+        shading_feature_mlp_layer3=cfg.shading_feature_mlp_layer3, point_color_mode="1", point_dir_mode="1", point_conf_mode="1",
+        agg_alpha_xyz_mode="None", shading_alpha_mlp_layer=cfg.shading_alpha_mlp_layer, agg_color_xyz_mode="None",
+        shading_color_mlp_layer=cfg.shading_color_mlp_layer, act_super=cfg.act_super, apply_pnt_mask=1, dist_xyz_deno=0.0, agg_weight_norm=1,
+        sparse_loss_weight=0.0, zero_one_loss_items=["conf_coefficient"], prob=0, shading_color_channel_num=3)
+
+
+class ReferenceRenderer:
+    """The reference's per-ray path after the query, on whatever device its tensors live on: index_select gathers as
+    NeuralPoints.forward does them (neural_points.py:956-972, restated: that class needs PyCUDA to import), then the reference's OWN
+    PointAggregator.forward and ray_march (imported from baseline/_ref), the caller's step-size glue (neural_points_volumetric_model.py:569-577)
+    and fill_invalid.  Falls back to the oracle restatement of the aggregator when baseline/_ref is not staged (kind = "port")."""
+
+    def __init__(self, P, cfg):
+        from oracle import render_ref as rr
+        self.rr, self.P, self.cfg = rr, P, cfg
+        self.ref = reference_classes()
+        self.kind = "reference" if self.ref is not None else "port"
+        if self.ref is not None:
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):          # the reference's constructor prints; stdout carries the JSON line only
+                self.agg = self.ref.PointAggregator(reference_opt(cfg))
+            self.agg.load_state_dict(P)
+            self.agg.requires_grad_(False)
+            self.render_func = self.ref.find_render_function("radiance")
+            self.blend_func = self.ref.find_blend_function("alpha")
+
+    def __call__(self, tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, rot, campos, vsize, bg):
+        rr = self.rr
+        if self.ref is None:
+            return rr.render_from_query(self.P, self.cfg, tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, rot, campos, vsize, bg).coarse_raycolor
+        g = rr.gather_neighbors(tables, o_pidx, rot, campos)
+        decoded, ray_valid, weight, conf = self.agg(g.color, None, torch.eye(3), g.dir, g.conf, g.embedding, g.xyz_pers, g.xyz, g.pnt_mask, o_loc,
+                                                    o_loc_w, o_dirs, np.asarray(vsize, dtype=np.float32), 0)
+        ray_dist = rr.ray_dist_from_samples(o_loc, ray_valid, float(vsize[2]))
+        rm = self.ref.ray_march(ray_dist, ray_valid, decoded, self.render_func, self.blend_func, bg[None, :])
+        color, _, _ = rr.fill_invalid(o_mask, rm[0], rm[2], rm[5], bg)
+        return color
+
+
+def cpu_reference_step(s, renderer, tabs, sel, opt, threads):
+    """One bounded sample of the workload on the host cores: sequential C query restatement (the reference's query kernels are CUDA-only)
+    + the reference's PointAggregator + ray_march on all host threads."""
     from types import SimpleNamespace
     from oracle import query_ref as qr
-    from oracle import render_ref as rr
     torch.set_num_threads(threads)
-    sub = SimpleNamespace(**vars(s))
-    sub.raydir = s.raydir[sel]
     xyz = torch.from_numpy(s.xyz)[None]
     t0 = time.perf_counter()
     o_pidx, o_loc, o_loc_w, o_dirs, o_mask, vsize, _, info = qr.query_points(
-        opt, xyz, s.near, s.far, torch.from_numpy(sub.raydir)[None], torch.from_numpy(s.campos)[None],
-        torch.from_numpy(s.camrotc2w)[None])
+        opt, xyz, s.near, s.far, torch.from_numpy(s.raydir[sel])[None], torch.from_numpy(s.campos)[None], torch.from_numpy(s.camrotc2w)[None])
     t1 = time.perf_counter()
     tables = SimpleNamespace(xyz=torch.from_numpy(s.xyz), embedding=tabs.embedding, color=tabs.color, dir=tabs.dir, conf=tabs.conf,
                              label_embedding=None)
     with torch.no_grad():
-        rr.render_from_query(P, cfg, tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, torch.from_numpy(s.camrotc2w)[None],
-                             torch.from_numpy(s.campos)[None], vsize, torch.ones(3))
+        renderer(tables, o_pidx, o_loc, o_loc_w, o_dirs, o_mask, torch.from_numpy(s.camrotc2w)[None], torch.from_numpy(s.campos)[None], vsize, torch.ones(3))
     t2 = time.perf_counter()
     return t1 - t0, t2 - t1
 
 
-def cpu_setup():
+def cpu_setup(c0=False):
     from oracle import query_ref as qr
     from oracle import render_ref as rr
     from sgnerf_b200 import synth
-    s = synth.scene_room(N_POINTS, room=(8.0, 8.0, 3.0), width=WIDTH, height=HEIGHT, seed=1234)
-    tabs = synth.make_point_tables(N_POINTS, 32, 0, seed=0)
-    shapes = synth.mlp_layer_shapes()
-    P = synth.make_mlp_params(shapes, seed=0)
-    return s, P, rr.agg_config(), tabs, qr.default_opt(SR=24)
+    if c0:        # BASELINE.json configs[0]: 100k-point cloud, 1024 rays, SR = 80
+        s, n, opt = synth.scene_c0(100_000, 1024), 100_000, qr.default_opt(SR=80)
+    else:
+        s, n, opt = synth.scene_room(N_POINTS, room=(8.0, 8.0, 3.0), width=WIDTH, height=HEIGHT, seed=1234), N_POINTS, qr.default_opt(SR=24)
+    tabs = synth.make_point_tables(n, 32, 0, seed=0)
+    P = synth.make_mlp_params(synth.mlp_layer_shapes(), seed=0)
+    return s, ReferenceRenderer(P, rr.agg_config()), tabs, opt
 
 
 def cpu_baseline(sample_rays=2304):
-    s, P, cfg, tabs, opt = cpu_setup()
+    s, renderer, tabs, opt = cpu_setup()
     threads = os.cpu_count() or 1
     rng = np.random.default_rng(0)
     sel = np.sort(rng.choice(s.raydir.shape[0], sample_rays, replace=False))
-    tq, tr = cpu_reference_step(s, P, cfg, tabs, sel, opt, threads)
-    return {"value": sample_rays / tr, "unit": "rays/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_rays} random rays of the same 640x480 frame (one reference-sized chunk of 48^2): torch aggregator + ray_march "
+    cpu_reference_step(s, renderer, tabs, sel[:256], opt, threads)                  # warm-up (allocator, thread pool)
+    tq, tr = cpu_reference_step(s, renderer, tabs, sel, opt, threads)
+    # BASELINE.json's own CPU case (configs[0]): 1024 rays, 100k points, SR = 80, forward of the aggregator + ray_march
+    s0, r0, tabs0, opt0 = cpu_setup(c0=True)
+    all0 = np.arange(s0.raydir.shape[0])
+    cpu_reference_step(s0, r0, tabs0, all0[:128], opt0, threads)
+    best = min(cpu_reference_step(s0, r0, tabs0, all0, opt0, threads)[1] for _ in range(3))
+    return {"value": sample_rays / tr, "unit": "rays/s", "cores": threads, "kind": renderer.kind,
+            "sample": f"{sample_rays} random rays of the same 640x480 C1 frame: index_select gathers + the reference's PointAggregator + ray_march "
                       f"forward on {threads} host threads = {tr:.2f} s; the sequential C query restatement incl. its per-call grid rebuild took "
-                      f"{tq:.2f} s more (1 thread) and is not in `value`", "query_s": tq, "render_s": tr}
+                      f"{tq:.2f} s more (1 thread) and is not in `value`", "query_s": tq, "render_s": tr,
+            "c0": {"what": "BASELINE.json configs[0]: 1024 rays, 100k-point cloud, K=8, SR=80, fp32 forward of the reference PointAggregator + ray_march, "
+                           "query indices from the oracle; best of 3", "rays_per_s": 1024 / best, "seconds": best}}
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm for this path on the host cores (oracle port; the reference's
-    query kernels are CUDA-only and its Python modules cannot travel to the GPU box)."""
+    """--impl reference: the reference's path on the host cores -- its own PointAggregator + ray_march (baseline/_ref) after the sequential C
+    restatement of its CUDA-only query -- on bounded samples of the same C1 frame."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    s, P, cfg, tabs, opt = cpu_setup()
+    s, renderer, tabs, opt = cpu_setup()
     threads = os.cpu_count() or 1
     rng = np.random.default_rng(0)
     n = args.cpu_sample
     times = []
     for i in range(args.warmup + args.steps):
         sel = np.sort(rng.choice(s.raydir.shape[0], n, replace=False))
-        tq, tr = cpu_reference_step(s, P, cfg, tabs, sel, opt, threads)
+        tq, tr = cpu_reference_step(s, renderer, tabs, sel, opt, threads)
         if i >= args.warmup:
             times.append(tq + tr)
     sec = float(np.mean(times))
     v = n / sec
     sample = (f"each step = {n} random rays of the 640x480 frame (one reference chunk of 48^2 rays): sequential C query restatement "
-              f"incl. per-call grid rebuild + torch aggregator + ray_march on {threads} host threads")
+              f"incl. per-call grid rebuild + the reference's PointAggregator + ray_march on {threads} host threads")
     print(json.dumps({
         "impl": "reference", "metric": "rays/sec (full-frame render)", "value": v, "unit": "rays/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "rays_per_step": n},
-        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "rays_per_gpu": n, "rays_per_step": n},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": threads, "kind": renderer.kind, "sample": sample},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def strong_scaling_leg(device, rank, world, dist, precision, args):
+    """ONE frame over the N ranks (BASELINE.json configs 2, 4, 5 read as strong scaling): tiles of 256 consecutive rays dealt round-robin
+    (sgnerf_b200.dist.shard_rays), point cloud + grid + per-point tables replicated, the [R,3] image assembled on every rank with one
+    all-gather.  C1 (1M points, 640x480), C3 (3M points, 800x800, SR 200, P 9, vsize .004) and C4 (10M points, 1296x968) with its point
+    edits between frames (prune 2 % + grow 1 %, decided identically on every rank; grid and per-point tables rebuilt inside the step).
+    ms = device time per frame, max over ranks; at N = 1 the same code gives the single-GPU time of the configuration."""
+    from sgnerf_b200 import dist as sdist
+    from sgnerf_b200 import ops, pipeline, synth
+    out = {"what": f"one frame ray-sharded over {world} GPU(s), tiles of 256 rays round-robin, all-gather of the image"}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    bg = torch.ones(3, device=device)
+    shapes = synth.mlp_layer_shapes()
+    P = synth.make_mlp_params(shapes, seed=0)
+    names = [k for k, _, _ in shapes]
+
+    def tmax(ms):
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def frame_fn(scene, s):
+        campos, rot = torch.from_numpy(s.campos).to(device), torch.from_numpy(s.camrotc2w).to(device)
+        R = s.raydir.shape[0]
+        idx = sdist.shard_rays(R, rank, world, tile=256)
+        mine = torch.from_numpy(s.raydir)[idx].to(device).contiguous()
+        idx_d = idx.to(device)
+
+        def one():
+            part = pipeline.render_rays(scene, campos, rot, mine, s.near, s.far, bg, precision=precision)
+            return sdist.gather_frame(part.ray_color, idx_d, R, tile=256), part
+        return one, R
+
+    def measure(one, n=3, warm=2):
+        for _ in range(warm):
+            one()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(n):
+            r = one()
+        b.record(); torch.cuda.synchronize()
+        return tmax(a.elapsed_time(b) / n), r
+
+    with torch.no_grad():
+        for name, mk, n_pts, qo in (("c1", lambda: synth.scene_room(N_POINTS, room=(8.0, 8.0, 3.0), width=WIDTH, height=HEIGHT, seed=1234), N_POINTS, dict(SR=24)),
+                                    ("c3", lambda: synth.scene_c3(), 3_000_000, dict(synth.C3_QUERY)),
+                                    ("c4", lambda: synth.scene_c4(), 10_000_000, dict(SR=24))):
+            if name in args.skip_strong:
+                continue
+            try:
+                s = mk()
+                tabs = synth.make_point_tables(n_pts, 32, 0, seed=0, conf_spread=0.5 if name == "c4" else 0.0)
+                scene = pipeline.RenderScene(s.xyz, tabs.embedding, tabs.color, tabs.dir, tabs.conf, [P[k + ".weight"] for k in names],
+                                             [P[k + ".bias"] for k in names], ops.agg_cfg(), pipeline.query_options(**qo), device=device)
+                one, R = frame_fn(scene, s)
+                ms, (frame, part) = measure(one)
+                info = {"points": n_pts, "rays": R, "SR": scene.qopt.SR, "ms_per_frame": ms, "rays_per_s": R / (ms * 1e-3),
+                        "rays_hit_this_rank": int(part.ray_mask.sum()), "frame_checksum": float(frame.double().sum())}
+                if name == "c4":
+                    # SURVEY.md 8d, C4: between frames prune the 2 % lowest-confidence points and grow 1 % new ones (same decision on every
+                    # rank: same seed, replicated tables); grid + per-point tables rebuilt; all of it inside the timed step
+                    g = torch.Generator(device=device).manual_seed(5)
+                    steps = []
+                    for it in range(3):
+                        torch.cuda.synchronize()
+                        if dist is not None:
+                            dist.barrier()
+                        a, b = ev(), ev()
+                        a.record()
+                        n_now = scene.xyz.shape[0]
+                        thr = torch.quantile(scene.conf[:1_000_000], 0.02)
+                        kept = scene.prune(thr)
+                        m = n_now // 100
+                        base = scene.xyz[torch.randint(0, kept, (m,), device=device, generator=g)]
+                        scene.grow(base + 0.004 * torch.randn(m, 3, device=device, generator=g), torch.rand(m, 32, device=device, generator=g) - 0.5,
+                                   torch.rand(m, 3, device=device, generator=g), torch.nn.functional.normalize(torch.randn(m, 3, device=device, generator=g), dim=-1),
+                                   0.5 + torch.rand(m, device=device, generator=g))
+                        one()
+                        b.record(); torch.cuda.synchronize()
+                        steps.append(tmax(a.elapsed_time(b)))
+                    info["edit_step"] = {"what": "prune 2 % lowest confidence + grow 1 % + grid + per-point tables + the sharded frame", "ms_per_step": steps,
+                                         "points_after": int(scene.xyz.shape[0])}
+                out[name] = info
+                del scene, tabs, s, one, frame, part
+                torch.cuda.empty_cache()
+            except Exception as e:
+                out[name] = {"error": repr(e)[:300]}
+    return out
 
 
 def main():
@@ -566,7 +762,17 @@ def main():
     ap.add_argument("--no-semantic-variant", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the one-frame-over-N-ranks leg (C1 / C3 / C4)")
+    ap.add_argument("--skip-strong", default="", help="comma list of c1,c3,c4 to leave out of the strong-scaling leg")
+    ap.add_argument("--leg", default=None, choices=["cpu_baseline", "reference_gpu"], help="(internal) run one reference leg and print its JSON")
     args = ap.parse_args()
+    args.skip_strong = [x for x in args.skip_strong.split(",") if x]
+    if args.leg == "cpu_baseline":
+        print(json.dumps(cpu_baseline(sample_rays=4 * args.cpu_sample)))
+        return
+    if args.leg == "reference_gpu":
+        print(json.dumps(reference_gpu_standalone()))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

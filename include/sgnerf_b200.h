@@ -75,7 +75,9 @@ int sgn_grid_destroy(SgnGrid* g);
  *   0 cell_slot [X*Y*Z] (= coor_2_occ), 1 occ_bits uint32[ceil(X*Y*Z/32)] (= coor_occ as a bitmask),
  *   2 slot_coor [max_o*3] (= occ_2_coor), 3 slot_count [max_o] (= occ_numpnts, uncapped),
  *   4 slot_start [max_o+1] (offset of the slot's list in cand), 5 cand float4[(x,y,z,bits(pidx))],
- *   6 counters [4]: {n_claimed (= occ_idx), n_candidates, 0, 0}.                                  */
+ *   6 counters [4]: {n_claimed (= occ_idx), n_candidates, 0, 0}, 7 brick mask of the march (1 bit per 8^3 voxels),
+ *   8 knn_brick uint32[4 per 4^3-voxel brick] = (mask lo, mask hi, rank of the first listed voxel, 0),
+ *   9 knn_list int32[2 per listed voxel] = (first candidate, count).                               */
 int sgn_grid_buffer(const SgnGrid* g, int which, void** ptr, int64_t* n_elements);
 
 /* ------------------------------------------------------------------------------------------------
@@ -179,6 +181,14 @@ int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights /*[
                            int save_for_backward, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
                            float* conf_coef, void* workspace, size_t workspace_bytes, const void* point_cache, void* stream);
 
+/* The frame variant: sgn_agg_forward_cached plus loc_depth [R,SR] (or NULL) = the camera depth of every sample (loc_pers[..., 2]) as a
+ * dense array -- the only part of loc_pers the frame tail (sgn_render_composite_depth) reads; loc_pers itself may then be NULL. */
+int sgn_agg_forward_frame(const SgnAggCfg* cfg, const float* const* weights /*[host]*/, const float* const* biases /*[host]*/,
+                          const SgnPointTables* tables, const int32_t* pidx, const float* loc_w, const float* raydir,
+                          const float* campos, const float* camrotc2w, int64_t R, int SR, int K, int precision,
+                          int save_for_backward, float* decoded, uint8_t* ray_valid, float* loc_pers, float* loc_depth, float* weight,
+                          float* conf_coef, void* workspace, size_t workspace_bytes, const void* point_cache, void* stream);
+
 /* Backward of sgn_agg_forward (autograd of the reference path).  Needs the workspace
  * of a forward call made with save_for_backward = 1 and the same arguments.  d_weights/d_biases are
  * [host] arrays of device pointers (accumulated, +=); d_conf_coef may be NULL. */
@@ -239,6 +249,13 @@ int sgn_render_composite(const float* decoded /*[R,SR,4]*/, const float* loc_per
                          const int8_t* ray_mask /*[R]*/, float vsize_z, int raydist_mode_unit, const float* bg /*[3]*/, int blend,
                          int64_t R, int SR, float* ray_color /*[R,3]*/, float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/,
                          float* depth /*[R]*/, void* stream);
+
+/* The same from the dense depth array of sgn_agg_forward_frame (loc_depth [R,SR] = loc_pers[..., 2]): identical results, a third of the
+ * position bytes. */
+int sgn_render_composite_depth(const float* decoded /*[R,SR,4]*/, const float* loc_depth /*[R,SR]*/, const uint8_t* ray_valid /*[R,SR]*/,
+                               const int8_t* ray_mask /*[R]*/, float vsize_z, int raydist_mode_unit, const float* bg /*[3]*/, int blend,
+                               int64_t R, int SR, float* ray_color /*[R,3]*/, float* opacity /*[R,SR]*/, float* bg_transmission /*[R]*/,
+                               float* depth /*[R]*/, void* stream);
 
 /* `prob == 1` outputs of NeuralPointsRayMarching.forward (neural_points_volumetric_model.py:633-656), the inputs of probe_hole / point
  * growing (run/train_ft.py:425-540): per ray the first sample of largest opacity, its world position, the distance to its nearest

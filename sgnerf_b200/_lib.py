@@ -60,6 +60,9 @@ SIGNATURES = {
     "sgn_agg_forward_cached": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                        c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
                                        c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void, c_void]),
+    "sgn_agg_forward_frame": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
+                                      c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
+                                      c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void, c_void]),
     "sgn_agg_point_cache_bytes": (c_int, [C.POINTER(SgnAggCfg), c_i64, C.POINTER(c_size)]),
     "sgn_agg_point_cache_build": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(SgnPointTables), c_void, c_size, c_void]),
     "sgn_agg_backward": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
@@ -77,6 +80,8 @@ SIGNATURES = {
                                        c_void, c_void, c_void]),
     "sgn_render_composite": (c_int, [c_void, c_void, c_void, c_void, c_f32, c_int, c_void, c_int, c_i64, c_int, c_void, c_void, c_void, c_void,
                                      c_void]),
+    "sgn_render_composite_depth": (c_int, [c_void, c_void, c_void, c_void, c_f32, c_int, c_void, c_int, c_i64, c_int, c_void, c_void, c_void,
+                                           c_void, c_void]),
     "sgn_probe_outputs": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, C.POINTER(SgnPointTables), c_int, c_i64, c_int, c_int,
                                   c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void]),
     "sgn_fill_invalid": (c_int, [c_void, c_void, c_i64, c_int, c_void, c_void, c_void, c_void]),

@@ -8,7 +8,7 @@ using namespace sgn;
 int sgn_agg_fp32_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, int save, size_t* bytes);
 int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                         int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
+                         int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* loc_depth, float* weight,
                          float* conf_coef, void* workspace, size_t workspace_bytes, bool tc, cudaStream_t st);
 int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                           const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
@@ -17,7 +17,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
 int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, int K, size_t* bytes);
 int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                        const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight, float* conf_coef,
+                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers, float* loc_depth, float* weight, float* conf_coef,
                        void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st);
 int sgn_agg_tc_point_cache_bytes(const AggPlan& P, int64_t N, size_t* bytes);
 int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, const SgnPointTables* tables, void* cache, size_t cache_bytes, cudaStream_t st);
@@ -44,11 +44,11 @@ extern "C" int sgn_agg_workspace_bytes(const SgnAggCfg* cfg, int64_t N, int64_t 
     return sgn_agg_tc_workspace_bytes(P, N, R, SR, K, bytes);
 }
 
-extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
-                               const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                               int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,
-                               float* loc_pers, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes, const void* point_cache,
-                                      void* stream)
+extern "C" int sgn_agg_forward_frame(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                                     const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                                     int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,
+                                     float* loc_pers, float* loc_depth, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes,
+                                     const void* point_cache, void* stream)
 {
     AggPlan P;
     int rc = check_common(cfg, &P, R, SR, K);
@@ -59,12 +59,22 @@ extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* 
     if (R == 0) return SGN_OK;
     if (precision == SGN_PRECISION_FP32 || precision == SGN_PRECISION_TF32)
         return sgn_agg_fp32_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, save_for_backward, decoded,
-                                    ray_valid, loc_pers, weight, conf_coef, workspace, workspace_bytes, precision == SGN_PRECISION_TF32,
+                                    ray_valid, loc_pers, loc_depth, weight, conf_coef, workspace, workspace_bytes, precision == SGN_PRECISION_TF32,
                                     (cudaStream_t)stream);
     SGN_CHECK_ARG(precision == SGN_PRECISION_BF16, "aggregator: unknown precision %d", precision);
     SGN_CHECK_ARG(!save_for_backward, "aggregator: the bf16 tensor-core path is forward-only; train with SGN_PRECISION_FP32 or SGN_PRECISION_TF32");
-    return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers,
+    return sgn_agg_tc_forward(P, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, decoded, ray_valid, loc_pers, loc_depth,
                               weight, conf_coef, workspace, workspace_bytes, point_cache, (cudaStream_t)stream);
+}
+
+extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                               const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
+                               int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,
+                               float* loc_pers, float* weight, float* conf_coef, void* workspace, size_t workspace_bytes, const void* point_cache,
+                                      void* stream)
+{
+    return sgn_agg_forward_frame(cfg, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, precision, save_for_backward,
+                                 decoded, ray_valid, loc_pers, nullptr, weight, conf_coef, workspace, workspace_bytes, point_cache, stream);
 }
 
 extern "C" int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,

@@ -66,7 +66,7 @@ static int pack_weights(const AggPlan& P, const float* const* weights, AggWs& ws
 
 // forward for one chunk of rays
 static int agg_forward_chunk(const AggPlan& P, const float* const* weights, const float* const* biases, const AggIn& in, int64_t Rc,
-                             int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* weight_out, float* conf_out,
+                             int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* loc_depth, float* weight_out, float* conf_out,
                              AggWs& ws, bool save, bool tc, cudaStream_t st)
 {
     const AggDims& d = P.dims;
@@ -74,7 +74,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     const int Tm = (int)(S * K), Sm = (int)S;
     float* loc_pers = loc_pers_out ? loc_pers_out : ws.loc_pers;
     SGN_CUDA(cudaMemsetAsync(decoded, 0, sizeof(float) * 4 * (size_t)S, st));
-    launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, ws.weight_n, weight_out, conf_out, ray_valid, ws.nvalid, ws.svalid);
+    launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, loc_depth, ws.wc, ws.weight_n, weight_out, conf_out, ray_valid, ws.nvalid, ws.svalid);
     int rc;
     // compaction offsets of the tuples (scan of nvalid) and of the samples with a neighbour (scan of nvalid > 0), one pass
     if ((rc = exclusive_scan_pair_i32(ws.nvalid, ws.tuple_start, ws.sample_cidx, S, ws.partials, st))) return rc;
@@ -157,7 +157,7 @@ int sgn_agg_fp32_workspace_bytes(const AggPlan& P, int64_t R, int SR, int K, int
 
 int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                          const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                         int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* weight,
+                         int64_t R, int SR, int K, int save, float* decoded, uint8_t* ray_valid, float* loc_pers, float* loc_depth, float* weight,
                          float* conf_coef, void* workspace, size_t workspace_bytes, bool tc, cudaStream_t st)
 {
     const int64_t chunk = save ? R : (R < AGG_FP32_CHUNK ? R : AGG_FP32_CHUNK);
@@ -176,7 +176,7 @@ int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const fl
         in.pidx = pidx + r0 * SR * K; in.loc_w = loc_w + r0 * SR * 3; in.raydir = raydir + r0 * 3;
         in.campos = campos; in.camrot = camrotc2w;
         rc = agg_forward_chunk(P, weights, biases, in, Rc, SR, K, decoded + r0 * SR * 4, ray_valid + r0 * SR,
-                               loc_pers ? loc_pers + r0 * SR * 3 : nullptr, weight ? weight + r0 * SR * K : nullptr,
+                               loc_pers ? loc_pers + r0 * SR * 3 : nullptr, loc_depth ? loc_depth + r0 * SR : nullptr, weight ? weight + r0 * SR * K : nullptr,
                                conf_coef ? conf_coef + r0 * SR * K : nullptr, ws, save != 0, tc, st);
         if (rc) return rc;
     }

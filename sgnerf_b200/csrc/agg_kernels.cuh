@@ -9,7 +9,7 @@ namespace sgn {
 // ------------------------------------------------------------------------------------------------
 
 // One thread per sample.  point_aggregators.py:885, :917-925 (dists), :494-502 + :946-947 (weights), :953 (conf).
-static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __restrict__ loc_pers, float* __restrict__ wc,
+static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __restrict__ loc_pers, float* __restrict__ loc_depth, float* __restrict__ wc,
                                    float* __restrict__ weight_n, float* __restrict__ weight_out, float* __restrict__ conf_out, uint8_t* __restrict__ ray_valid,
                                    int32_t* __restrict__ nvalid, int32_t* __restrict__ svalid)
 {
@@ -23,6 +23,7 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
         const float c1 = sx * Rm[1] + sy * Rm[4] + sz * Rm[7];
         const float c2 = sx * Rm[2] + sy * Rm[5] + sz * Rm[8];
         loc_pers[3 * s] = c0 / c2; loc_pers[3 * s + 1] = c1 / c2; loc_pers[3 * s + 2] = c2;
+        if (loc_depth) loc_depth[s] = c2;          // the camera depth again as a dense array: what the frame tail reads (4 B instead of a 12-B-stride gather)
     }
     const int32_t* pi = in.pidx + s * K;
     if (K == 8 && (((uintptr_t)in.pidx | (uintptr_t)wc | (uintptr_t)weight_n | (uintptr_t)weight_out | (uintptr_t)conf_out) & 15) == 0) {

@@ -1318,7 +1318,7 @@ int sgn_agg_tc_workspace_bytes(const AggPlan& P, int64_t N, int64_t R, int SR, i
 
 int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                        const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
-                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* weight_out, float* conf_out,
+                       int64_t R, int SR, int K, float* decoded, uint8_t* ray_valid, float* loc_pers_out, float* loc_depth, float* weight_out, float* conf_out,
                        void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st)
 {
     int rc = tc_supported(P, K);
@@ -1432,7 +1432,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         float* dec = decoded + r0 * SR * 4;
         float* loc_pers = loc_pers_out ? loc_pers_out + r0 * SR * 3 : ws.loc_pers;
         SGN_CUDA(cudaMemsetAsync(dec, 0, sizeof(float) * 4 * (size_t)S, st));
-        launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, ws.wc, (float*)nullptr, weight_out ? weight_out + r0 * SR * K : nullptr,
+        launch(agg_prepare_kernel, cdiv(S, 128), 128, 0, st, in, S, K, loc_pers, loc_depth ? loc_depth + r0 * SR : nullptr, ws.wc, (float*)nullptr, weight_out ? weight_out + r0 * SR * K : nullptr,
                conf_out ? conf_out + r0 * SR * K : nullptr, ray_valid + r0 * SR, ws.nvalid, ws.svalid);
         // compaction offsets of the tuples (scan of nvalid) and of the samples with a neighbour (scan of nvalid > 0), one pass
         if ((rc = exclusive_scan_pair_i32(ws.nvalid, ws.tuple_start, ws.sample_cidx, S, ws.partials, st))) return rc;

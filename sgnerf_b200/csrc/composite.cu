@@ -209,7 +209,7 @@ ray_dist_kernel(const float* __restrict__ loc_pers, const uint8_t* __restrict__ 
 // (ray_mask <= 0) get the background without reading their samples -- the same values the three separate kernels produce.
 template <int BLEND>
 __global__ void __launch_bounds__(COMP_WARPS * 32)
-render_composite_kernel(const float4* __restrict__ decoded, const float* __restrict__ loc_pers, const uint8_t* __restrict__ valid,
+render_composite_kernel(const float4* __restrict__ decoded, const float* __restrict__ zsrc, int zstride, const uint8_t* __restrict__ valid,
                         const int8_t* __restrict__ ray_mask, float vsize_z, int mode_unit, const float* __restrict__ bg, int64_t R, int SR,
                         float* __restrict__ ray_color, float* __restrict__ opacity, float* __restrict__ bg_t, float* __restrict__ depth)
 {
@@ -237,10 +237,11 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
             // a sample without neighbours has sigma * valid = 0, hence weight 0: its 16 bytes are not read (two thirds of a frame's slots)
             const float4 f = v > 0.f ? __ldg(decoded + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             // step size: running maximum of the camera depth, difference to the next sample, voxel size where degenerate
-            const float z = act ? __ldg(loc_pers + i * 3 + 2) : -INFINITY;
+            // camera depth of the sample: zsrc = loc_pers + 2 with stride 3, or the dense [R,SR] depth array with stride 1
+            const float z = act ? __ldg(zsrc + i * zstride) : -INFINITY;
             const float cm = fmaxf(zcarry, warp_incl_max(z));
             float zn = __shfl_down_sync(0xffffffffu, z, 1);
-            if (lane == 31 && s + 1 < SR) zn = __ldg(loc_pers + (i + 1) * 3 + 2);
+            if (lane == 31 && s + 1 < SR) zn = __ldg(zsrc + (i + 1) * zstride);
             float d = (s + 1 < SR) ? fmaxf(cm, zn) - cm : vsize_z;
             bool bad = d < 1e-8f;
             if (mode_unit > 0) bad = bad || (d > 2.0f * vsize_z);
@@ -415,23 +416,39 @@ extern "C" int sgn_composite_backward(const float* decoded, const float* ray_dis
     return SGN_OK;
 }
 
+static int render_composite_impl(const float* decoded, const float* zsrc, int zstride, const uint8_t* ray_valid, const int8_t* ray_mask, float vsize_z,
+                                 int raydist_mode_unit, const float* bg, int blend, int64_t R, int SR, float* ray_color, float* opacity,
+                                 float* bg_transmission, float* depth, void* stream)
+{
+    SGN_CHECK_ARG(R >= 0 && SR > 0 && SR <= 32 * COMP_MAX_CHUNKS, "sgn_render_composite: SR=%d out of range", SR);
+    SGN_CHECK_ARG(blend == 0 || blend == 1, "sgn_render_composite: blend must be 0 (alpha) or 1 (alpha2)");
+    SGN_CHECK_ARG(decoded && zsrc && ray_valid, "sgn_render_composite: NULL input");
+    if (R == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    if (blend == 0)
+        launch(render_composite_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, zsrc, zstride, ray_valid, ray_mask, vsize_z,
+                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
+    else
+        launch(render_composite_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, zsrc, zstride, ray_valid, ray_mask, vsize_z,
+                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
 extern "C" int sgn_render_composite(const float* decoded, const float* loc_pers, const uint8_t* ray_valid, const int8_t* ray_mask, float vsize_z,
                                     int raydist_mode_unit, const float* bg, int blend, int64_t R, int SR, float* ray_color, float* opacity,
                                     float* bg_transmission, float* depth, void* stream)
 {
-    SGN_CHECK_ARG(R >= 0 && SR > 0 && SR <= 32 * COMP_MAX_CHUNKS, "sgn_render_composite: SR=%d out of range", SR);
-    SGN_CHECK_ARG(blend == 0 || blend == 1, "sgn_render_composite: blend must be 0 (alpha) or 1 (alpha2)");
-    SGN_CHECK_ARG(decoded && loc_pers && ray_valid, "sgn_render_composite: NULL input");
-    if (R == 0) return SGN_OK;
-    auto st = (cudaStream_t)stream;
-    if (blend == 0)
-        launch(render_composite_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
-                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
-    else
-        launch(render_composite_kernel<1>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, loc_pers, ray_valid, ray_mask, vsize_z,
-                                                                            raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
-    SGN_LAUNCH_CHECK();
-    return SGN_OK;
+    return render_composite_impl(decoded, loc_pers ? loc_pers + 2 : nullptr, 3, ray_valid, ray_mask, vsize_z, raydist_mode_unit, bg, blend, R, SR,
+                                 ray_color, opacity, bg_transmission, depth, stream);
+}
+
+extern "C" int sgn_render_composite_depth(const float* decoded, const float* loc_depth, const uint8_t* ray_valid, const int8_t* ray_mask, float vsize_z,
+                                          int raydist_mode_unit, const float* bg, int blend, int64_t R, int SR, float* ray_color, float* opacity,
+                                          float* bg_transmission, float* depth, void* stream)
+{
+    return render_composite_impl(decoded, loc_depth, 1, ray_valid, ray_mask, vsize_z, raydist_mode_unit, bg, blend, R, SR, ray_color, opacity,
+                                 bg_transmission, depth, stream);
 }
 
 extern "C" int sgn_probe_outputs(const float* opacity, const float* sample_loc_w, const int32_t* sample_pidx, const float* weight,

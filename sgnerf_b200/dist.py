@@ -20,14 +20,43 @@ def shard_rays(n_rays, rank, world, tile=256):
     return idx[idx < n_rays]
 
 
-def gather_frame(local_rgb, idx, n_rays, group=None):
-    """Assemble the full frame on every rank from the per-rank ray shards (inference convenience; 12 bytes per ray)."""
+_FRAME_PERM = {}
+
+
+def _frame_layout(n_rays, world, tile):
+    """(rays of the largest shard, for every ray its position in the rank-major concatenation of the padded shards)."""
+    key = (int(n_rays), int(world), int(tile))
+    if key not in _FRAME_PERM:
+        shards = [shard_rays(n_rays, r, world, tile) for r in range(world)]
+        per = max(int(s.numel()) for s in shards)
+        perm = torch.empty(n_rays, dtype=torch.long)
+        for r, s in enumerate(shards):
+            perm[s] = r * per + torch.arange(s.numel())
+        _FRAME_PERM[key] = (per, perm)
+    return _FRAME_PERM[key]
+
+
+def gather_frame(local_rgb, idx, n_rays, group=None, tile=256):
+    """Assemble the full frame on every rank from the per-rank ray shards of shard_rays(n_rays, rank, world, tile): ONE all-gather of
+    the (padded) shards -- every byte crosses the links once, 12 bytes per ray -- then one indexed copy into frame order.
+    `idx` is this rank's shard_rays(...) (kept for the single-process case and for checking)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    out = torch.zeros(n_rays, local_rgb.shape[-1], dtype=local_rgb.dtype, device=local_rgb.device)
-    out[idx.to(local_rgb.device)] = local_rgb
-    if world > 1:
-        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)       # shards are disjoint, so the sum is the concatenation
-    return out
+    if world <= 1:
+        out = torch.empty(n_rays, local_rgb.shape[-1], dtype=local_rgb.dtype, device=local_rgb.device)
+        out[idx.to(local_rgb.device)] = local_rgb
+        return out
+    per, perm = _frame_layout(n_rays, world, tile)
+    C_ = local_rgb.shape[-1]
+    mine = local_rgb
+    if mine.shape[0] != per:                                  # the last tiles may leave a shard a few rays short: pad to the common size
+        mine = torch.zeros(per, C_, dtype=local_rgb.dtype, device=local_rgb.device)
+        mine[:local_rgb.shape[0]] = local_rgb
+    allr = torch.empty(world * per, C_, dtype=local_rgb.dtype, device=local_rgb.device)
+    dist.all_gather_into_tensor(allr, mine.contiguous(), group=group)
+    key = ("perm_dev", n_rays, world, tile, str(local_rgb.device))
+    if key not in _FRAME_PERM:
+        _FRAME_PERM[key] = perm.to(local_rgb.device)
+    return allr[_FRAME_PERM[key]]
 
 
 def allreduce_grads(params, average=True, group=None):

@@ -212,8 +212,9 @@ def composite(decoded, ray_dist_, ray_valid, bg_color=None, blend=0):
     return _Composite.apply(decoded, ray_dist_, valid, bg, int(blend))
 
 
-def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, blend=0, raydist_mode_unit=1):
-    """Inference tail of a frame in one kernel (no autograd): ray_dist -> composite -> fill_invalid.
+def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, blend=0, raydist_mode_unit=1, depth_array=False):
+    """Inference tail of a frame in one kernel (no autograd): ray_dist -> composite -> fill_invalid.  loc_pers is [R,SR,3], or with
+    depth_array=True the dense camera-depth array [R,SR] of aggregate(depth_only=True) (sgn_render_composite_depth).
     Returns ray_color [R,3], opacity [R,SR], bg_transmission [R] -- the values the three separate calls give -- and depth [R]
     (`coarse_depth`: opacity * transmittance weighted camera depth of the samples, 0 for rays that missed)."""
     decoded = _dev(decoded.detach(), torch.float32, "decoded")
@@ -225,7 +226,8 @@ def render_composite(decoded, loc_pers, ray_valid, ray_mask, vsize_z, bg_color, 
     opacity = torch.empty(R, SR, dtype=torch.float32, device=dev)
     bgt = torch.empty(R, dtype=torch.float32, device=dev)
     depth = torch.empty(R, dtype=torch.float32, device=dev)
-    _lib.call("sgn_render_composite", _ptr(decoded), _ptr(loc_pers), _ptr(valid), _ptr(_dev(ray_mask, torch.int8, "ray_mask")), float(vsize_z),
+    _lib.call("sgn_render_composite_depth" if depth_array else "sgn_render_composite", _ptr(decoded), _ptr(loc_pers), _ptr(valid),
+              _ptr(_dev(ray_mask, torch.int8, "ray_mask")), float(vsize_z),
               int(raydist_mode_unit), _ptr(_dev(bg_color.reshape(3), torch.float32, "bg")), int(blend), R, SR, _ptr(ray_color), _ptr(opacity),
               _ptr(bgt), _ptr(depth), _stream())
     return ray_color, opacity, bgt, depth
@@ -329,14 +331,19 @@ class _Aggregate(torch.autograd.Function):
         ws = _workspace(nbytes.value, dev)
         decoded = torch.empty(R, SR, 4, dtype=torch.float32, device=dev)
         ray_valid = torch.empty(R, SR, dtype=torch.uint8, device=dev)
-        loc_pers = torch.empty(R, SR, 3, dtype=torch.float32, device=dev)
+        # frame mode (inference tail): the samples' camera depth as a dense [R,SR] array instead of the [R,SR,3] perspective positions
+        depth_only = bool(getattr(meta, "depth_only", False)) and not need_grad
+        loc_pers = None if depth_only else torch.empty(R, SR, 3, dtype=torch.float32, device=dev)
+        loc_depth = torch.empty(R, SR, dtype=torch.float32, device=dev) if depth_only else None
         weight = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
         conf_coef = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
         tb = _tables(xyz, embedding, color, dirs, conf, label_emb)
         cache = meta.point_cache if (precision == PRECISION_BF16 and not need_grad) else None
-        _lib.call("sgn_agg_forward_cached", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w),
+        _lib.call("sgn_agg_forward_frame", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w),
                   _ptr(raydir), _ptr(campos), _ptr(camrot), R, SR, K, precision, int(need_grad), _ptr(decoded), _ptr(ray_valid),
-                  _ptr(loc_pers), _ptr(weight), _ptr(conf_coef), _ptr(ws), ws.numel() * 4, _ptr(cache), _stream())
+                  _ptr(loc_pers), _ptr(loc_depth), _ptr(weight), _ptr(conf_coef), _ptr(ws), ws.numel() * 4, _ptr(cache), _stream())
+        if depth_only:
+            loc_pers = loc_depth
         if need_grad:
             ctx.meta, ctx.ws, ctx.nl = meta, ws, nl
             ctx.save_for_backward(embedding, color, dirs, conf, *wb)
@@ -395,18 +402,20 @@ def build_point_cache(cfg, weights, embedding, label_emb=None):
 
 
 def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb, pidx, loc_w, raydir, campos, camrotc2w,
-              precision=PRECISION_FP32, want_aux=True, point_cache=None):
+              precision=PRECISION_FP32, want_aux=True, point_cache=None, depth_only=False):
     """Fused gather + aggregation MLPs (sgn_agg_forward / sgn_agg_backward).
 
     Tables: xyz [N,3], embedding [N,C], color [N,3], dirs [N,3], conf [N] (or None), label_emb [N,E] (or None).
     Query outputs: pidx int32 [R,SR,K], loc_w [R,SR,3]; raydir [R,3]; campos [3]; camrotc2w [3,3].
-    Returns decoded [R,SR,4], ray_valid uint8 [R,SR], loc_pers [R,SR,3], weight [R,SR,K], conf_coef [R,SR,K]."""
+    Returns decoded [R,SR,4], ray_valid uint8 [R,SR], loc_pers [R,SR,3], weight [R,SR,K], conf_coef [R,SR,K].
+    depth_only=True (inference, no autograd): the third result is the samples' camera depth [R,SR] (= loc_pers[..., 2]) for
+    render_composite(depth_array=True) instead of the full perspective positions (sgn_agg_forward_frame)."""
     f32 = torch.float32
     meta = SimpleNamespace(cfg=cfg, xyz=_dev(xyz.reshape(-1, 3), f32, "xyz"), label_emb=_dev(label_emb, f32, "label_emb"),
                            pidx=_dev(pidx, torch.int32, "pidx"), loc_w=_dev(loc_w, f32, "loc_w"),
                            raydir=_dev(raydir.reshape(-1, 3), f32, "raydir"), campos=_dev(campos.reshape(3), f32, "campos"),
                            camrot=_dev(camrotc2w.reshape(3, 3), f32, "camrotc2w"), precision=int(precision), want_aux=bool(want_aux),
-                           grad_enabled=torch.is_grad_enabled(), point_cache=point_cache)
+                           grad_enabled=torch.is_grad_enabled(), point_cache=point_cache, depth_only=depth_only)
     N = meta.xyz.shape[0]
     embedding = _dev(embedding.reshape(N, -1), f32, "embedding")
     color = _dev(color.reshape(N, 3), f32, "color")

@@ -56,6 +56,14 @@ class RenderScene:
         self._grid = None
         self._hp = None
         self._point_cache = None
+        self._ts = {}
+
+    def depth_candidates(self, near, far):
+        """middle_point_ts without jitter (the test-time candidates, identical for every ray and frame): computed once per (near, far)."""
+        key = (float(near), float(far), int(self.qopt.z_depth_dim))
+        if key not in self._ts:
+            self._ts[key] = middle_point_ts(key[0], key[1], key[2], self.xyz.device)
+        return self._ts[key]
 
     def invalidate_grid(self):
         """Call after the point cloud changed (grow / prune / set_points)."""
@@ -159,15 +167,17 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
     q = scene.qopt
     grid, hp = scene.grid()
     if t is None:
-        t = middle_point_ts(near, far, q.z_depth_dim, raydir.device)
+        t = scene.depth_candidates(near, far)
     pidx, loc_w, smask, rmask = ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2)
+    inference = not want_aux and not (torch.is_grad_enabled() and any(t.requires_grad for t in scene.weights + [scene.embedding, scene.color]))
     decoded, ray_valid, loc_pers, weight, conf_coef = ops.aggregate(
         scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf,
         scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux,
-        point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None)
-    if not want_aux and not decoded.requires_grad:
-        # inference: step sizes, compositing and fill_invalid in one kernel, no intermediate tensors
-        ray_color, opacity, bgt, depth = ops.render_composite(decoded, loc_pers, ray_valid, rmask, hp.vsize[2], bg_color, blend=0)
+        point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None, depth_only=inference)
+    if inference and not decoded.requires_grad:
+        # inference: step sizes, compositing and fill_invalid in one kernel, no intermediate tensors; the aggregator hands over the
+        # samples' camera depth as a dense array (the tail reads 4 bytes per sample instead of gathering z out of 12-byte rows)
+        ray_color, opacity, bgt, depth = ops.render_composite(decoded, loc_pers, ray_valid, rmask, hp.vsize[2], bg_color, blend=0, depth_array=True)
         return SimpleNamespace(ray_color=ray_color, ray_mask=rmask, opacity=opacity, bg_transmission=bgt, depth=depth)
     rd = ops.ray_dist(loc_pers, ray_valid, hp.vsize[2], 1)
     ray_color, opacity, acc, bw, bgt = ops.composite(decoded, rd, ray_valid, bg_color, blend=0)

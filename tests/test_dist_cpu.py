@@ -45,7 +45,7 @@ def _worker(rank, world, port, q):
     # frame assembly from ray shards
     n = 1000
     idx = shard_rays(n, rank, world, 64)
-    full = gather_frame(idx[:, None].float().repeat(1, 3), idx, n)
+    full = gather_frame(idx[:, None].float().repeat(1, 3), idx, n, tile=64)
     ok = ok and torch.equal(full[:, 0], torch.arange(n).float())
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
