@@ -268,6 +268,31 @@ int sgn_probe_outputs(const float* opacity /*[R,SR]*/, const float* sample_loc_w
                       float* ray_max_sample_loc_w, float* ray_max_far_dist, float* shading_avg_color, float* shading_avg_dir,
                       float* shading_avg_conf, float* shading_avg_embedding, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step glue.  Replaces BaseRenderingModel.compute_losses for the canonical loss items
+ * (models/base_rendering_model.py:543-641: `ray_masked_coarse_raycolor` colour MSE over the rays that hit the cloud + 1e-6, and the
+ * zero-one regulariser mean(log v + log(1 - v)), v = clamp(conf_coefficient, zero_epsilon, 1 - zero_epsilon)) together with its
+ * autograd backward, on UNCOMPACTED rows (ray_mask marks the hits), and torch.optim.Adam on the point tables
+ * (models/mvs_points_volumetric_model.py:99-109).
+ * ---------------------------------------------------------------------------------------------- */
+/* *count += number of rays with ray_mask > 0 (device scalar; all-reduce it over ranks before the next call when ranks share a step). */
+int sgn_loss_hit_count(const int8_t* ray_mask /*[R]*/, int64_t R, float* count, void* stream);
+/* loss = color_weight * sum_hit |ray_color - gt|^2 / (3 n) + conf_weight * sum_hit (log v + log(1 - v)) / (n SR K) + const_term with
+ * n = max(*hit_count, 1); *loss is overwritten; d_ray_color [R,3] and d_conf_coef [R,SR,K] (either may be NULL) receive d loss / d input
+ * (zero for rays that missed and where the clamp is active).  conf_coef may be NULL (no regulariser). */
+int sgn_loss_forward_backward(const float* ray_color /*[R,3]*/, const float* gt /*[R,3]*/, const int8_t* ray_mask /*[R]*/,
+                              const float* conf_coef /*[R,SR,K]*/, int64_t R, int SR, int K, const float* hit_count, float color_weight,
+                              float conf_weight, float zero_eps, float const_term, float* loss, float* d_ray_color, float* d_conf_coef,
+                              void* stream);
+/* *step += 1 (the optimiser's step counter lives on the device so that a captured step needs no host value). */
+int sgn_adam_step_count(float* step, void* stream);
+/* One Adam update (betas, eps, no weight decay, bias correction with t = *step, torch.optim.Adam's arithmetic) of the rows of a [N,C]
+ * table whose gradient is non-zero now or was at any earlier step (`active` [N] bytes, maintained by the call; NULL = all rows): rows
+ * that never received a gradient have zero moments and are exactly where dense Adam leaves them.  grad is multiplied by grad_scale
+ * first; zero_grad != 0 clears the gradient rows it consumed (the accumulator then never needs a dense memset). */
+int sgn_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint8_t* active, int64_t N, int C, float lr, float beta1,
+                  float beta2, float eps, const float* step, float grad_scale, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,11 @@ SIGNATURES = {
     "sgn_probe_outputs": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, C.POINTER(SgnPointTables), c_int, c_i64, c_int, c_int,
                                   c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void]),
     "sgn_fill_invalid": (c_int, [c_void, c_void, c_i64, c_int, c_void, c_void, c_void, c_void]),
+    "sgn_loss_hit_count": (c_int, [c_void, c_i64, c_void, c_void]),
+    "sgn_loss_forward_backward": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_void, c_f32, c_f32, c_f32, c_f32, c_void, c_void,
+                                          c_void, c_void]),
+    "sgn_adam_step_count": (c_int, [c_void, c_void]),
+    "sgn_adam_rows": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),
 }
 
 _lib = None

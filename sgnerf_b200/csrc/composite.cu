@@ -217,8 +217,26 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
     const int64_t warp0 = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * COMP_WARPS;
     const float b0 = bg ? bg[0] : 0.f, b1 = bg ? bg[1] : 0.f, b2 = bg ? bg[2] : 0.f;
+    // The per-ray chain mask -> valid -> decoded is three dependent memory latencies; the first two (and the depth) of the NEXT ray are
+    // requested before the current ray is processed, so a warp waits for one latency per ray, not three.
+    const bool pipelined = SR <= 32;
+    int8_t m_next = 1;
+    uint8_t v_next = 0;
+    float z_next = -INFINITY;
+    if (pipelined && warp0 < R) {
+        m_next = ray_mask ? ray_mask[warp0] : (int8_t)1;
+        if (lane < SR) { v_next = __ldg(valid + warp0 * SR + lane); z_next = __ldg(zsrc + (warp0 * SR + lane) * zstride); }
+    }
     for (int64_t r = warp0; r < R; r += nwarps) {
-        if (ray_mask && ray_mask[r] <= 0) {
+        const int8_t m_cur = pipelined ? m_next : (ray_mask ? ray_mask[r] : (int8_t)1);
+        const uint8_t v_cur = v_next;
+        const float z_cur = z_next;
+        if (pipelined && r + nwarps < R) {
+            const int64_t rn = r + nwarps;
+            m_next = ray_mask ? ray_mask[rn] : (int8_t)1;
+            if (lane < SR) { v_next = __ldg(valid + rn * SR + lane); z_next = __ldg(zsrc + (rn * SR + lane) * zstride); }
+        }
+        if (m_cur <= 0) {
             if (opacity)
                 for (int s = lane; s < SR; s += 32) opacity[r * SR + s] = 0.f;
             if (lane == 0) {
@@ -233,12 +251,12 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
             const int s = base + lane;
             const bool act = s < SR;
             const int64_t i = r * SR + s;
-            const float v = (act && __ldg(valid + i)) ? 1.0f : 0.0f;
+            const float v = (act && (pipelined ? v_cur : __ldg(valid + i))) ? 1.0f : 0.0f;
             // a sample without neighbours has sigma * valid = 0, hence weight 0: its 16 bytes are not read (two thirds of a frame's slots)
             const float4 f = v > 0.f ? __ldg(decoded + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             // step size: running maximum of the camera depth, difference to the next sample, voxel size where degenerate
             // camera depth of the sample: zsrc = loc_pers + 2 with stride 3, or the dense [R,SR] depth array with stride 1
-            const float z = act ? __ldg(zsrc + i * zstride) : -INFINITY;
+            const float z = act ? (pipelined ? z_cur : __ldg(zsrc + i * zstride)) : -INFINITY;
             const float cm = fmaxf(zcarry, warp_incl_max(z));
             float zn = __shfl_down_sync(0xffffffffu, z, 1);
             if (lane == 31 && s + 1 < SR) zn = __ldg(zsrc + (i + 1) * zstride);

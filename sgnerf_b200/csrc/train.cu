@@ -1,0 +1,164 @@
+// train.cu -- the pieces of a training iteration around the aggregator / compositing backward: the reference's loss with its gradient
+// in one pass, and Adam over the rows of the point tables that ever received a gradient.
+//
+// Reference: models/base_rendering_model.py:543-641 (compute_losses: `ray_masked_coarse_raycolor` colour MSE + 1e-6 per item, zero-one
+// regulariser on conf_coefficient with --zero_epsilon), models/mvs_points_volumetric_model.py:67-109 (two torch.optim.Adam instances,
+// betas (0.9, 0.999), no weight decay: MLP weights at --lr, point tables at --plr).
+#include "common.cuh"
+
+namespace sgn {
+
+constexpr int LOSS_THREADS = 256;
+
+// number of rays that hit the cloud (the reference's masked_select row count), accumulated into *count
+__global__ void loss_hit_count_kernel(const int8_t* __restrict__ ray_mask, int64_t R, float* count)
+{
+    int c = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) c += ray_mask[r] > 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int s[LOSS_THREADS / 32];
+    if (lane_id() == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < LOSS_THREADS / 32; i++) t += s[i];
+        if (t) atomicAdd(count, (float)t);
+    }
+}
+
+// loss = color_w * sum_hit |c - gt|^2 / (3 n) + conf_w * sum_hit (log v + log(1 - v)) / (n SR K) + const_term,  v = clamp(conf, eps, 1 - eps),
+// n = max(*hit_count, 1) (the GLOBAL hit count when ranks share a step).  One pass: the loss terms are reduced per block and added to
+// *loss (which the caller zeroes... the first block adds const_term), the gradients w.r.t. ray_color and conf_coefficient are written
+// for every row (zero for rays that missed; zero where the clamp is active, as torch.clamp's backward gives).
+__global__ void loss_fwd_bwd_kernel(const float* __restrict__ ray_color, const float* __restrict__ gt, const int8_t* __restrict__ ray_mask,
+                                    const float* __restrict__ conf, int64_t R, int SRK, const float* __restrict__ hit_count, float color_w,
+                                    float conf_w, float eps, float const_term, float* loss, float* __restrict__ d_color, float* __restrict__ d_conf)
+{
+    const float n = fmaxf(*hit_count, 1.0f);
+    const float kc = color_w / (3.0f * n), kz = conf_w / (n * (float)SRK);
+    float acc = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < R * 3; i += stride) {
+        const bool hit = ray_mask[i / 3] > 0;
+        const float d = hit ? ray_color[i] - gt[i] : 0.f;
+        acc += kc * d * d;
+        if (d_color) d_color[i] = 2.0f * kc * d;
+    }
+    if (conf) {
+        const int64_t total = R * SRK;
+        for (int64_t i = i0; i < total; i += stride) {
+            const bool hit = ray_mask[i / SRK] > 0;
+            float g = 0.f;
+            if (hit) {
+                const float c = conf[i];
+                const float v = fminf(fmaxf(c, eps), 1.0f - eps);
+                acc += kz * (logf(v) + logf(1.0f - v));
+                if (c >= eps && c <= 1.0f - eps) g = kz * (1.0f / v - 1.0f / (1.0f - v));
+            }
+            if (d_conf) d_conf[i] = g;
+        }
+    }
+    acc = warp_sum(acc);
+    __shared__ float s[LOSS_THREADS / 32];
+    if (lane_id() == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = blockIdx.x == 0 ? const_term : 0.f;
+        for (int i = 0; i < LOSS_THREADS / 32; i++) t += s[i];
+        atomicAdd(loss, t);
+    }
+}
+
+// Adam (torch.optim.Adam arithmetic: m = b1 m + (1 - b1) g, v = b2 v + (1 - b2) g^2, p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps))
+// over the rows of a [N, C] table.  One thread per row.  `active` (may be NULL = every row) remembers the rows that ever received a
+// non-zero gradient: a row that never did has m = v = 0 and dense Adam leaves it where it is, so skipping it gives the same table;
+// a row that did keeps being updated every step (its moments decay), exactly like the dense optimiser.  zero_grad != 0 clears the
+// gradient rows that were non-zero, so the [N, C] accumulator never needs a dense memset.
+template <int VEC>
+__global__ void adam_rows_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m1, float* __restrict__ m2,
+                                 uint8_t* __restrict__ active, int64_t N, int C, float lr, float b1, float b2, float eps, const float* __restrict__ step,
+                                 float grad_scale, int zero_grad)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    float* g = grad + row * C;
+    bool nz = false;
+    if (VEC == 4) {
+        for (int c = 0; c < C; c += 4) { const float4 x = *(const float4*)(g + c); nz = nz || x.x != 0.f || x.y != 0.f || x.z != 0.f || x.w != 0.f; }
+    } else {
+        for (int c = 0; c < C; c++) nz = nz || g[c] != 0.f;
+    }
+    if (active) {
+        if (nz) active[row] = 1;
+        else if (!active[row]) return;
+    }
+    const float t = *step;
+    const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
+    const float step_size = lr / bc1;
+    float *p = param + row * C, *a = m1 + row * C, *b = m2 + row * C;
+    for (int c = 0; c < C; c++) {
+        const float gc = g[c] * grad_scale;
+        const float m = b1 * a[c] + (1.0f - b1) * gc;
+        const float v = b2 * b[c] + (1.0f - b2) * gc * gc;
+        a[c] = m; b[c] = v;
+        p[c] -= step_size * (m / (sqrtf(v) / bc2s + eps));
+        if (zero_grad && nz) g[c] = 0.f;
+    }
+}
+
+__global__ void step_increment_kernel(float* step) { *step += 1.0f; }
+
+}  // namespace sgn
+
+using namespace sgn;
+
+extern "C" int sgn_loss_hit_count(const int8_t* ray_mask, int64_t R, float* count, void* stream)
+{
+    SGN_CHECK_ARG(ray_mask && count && R >= 0, "sgn_loss_hit_count: bad argument");
+    if (R == 0) return SGN_OK;
+    int nb = cdiv(R, LOSS_THREADS);
+    if (nb > 148 * 8) nb = 148 * 8;
+    launch(loss_hit_count_kernel, nb, LOSS_THREADS, 0, (cudaStream_t)stream, ray_mask, R, count);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_loss_forward_backward(const float* ray_color, const float* gt, const int8_t* ray_mask, const float* conf_coef, int64_t R, int SR,
+                                         int K, const float* hit_count, float color_weight, float conf_weight, float zero_eps, float const_term,
+                                         float* loss, float* d_ray_color, float* d_conf_coef, void* stream)
+{
+    SGN_CHECK_ARG(ray_color && gt && ray_mask && hit_count && loss && R >= 0 && SR > 0 && K > 0, "sgn_loss_forward_backward: bad argument");
+    SGN_CHECK_ARG(zero_eps > 0.f && zero_eps < 0.5f, "sgn_loss_forward_backward: zero_eps must lie in (0, 0.5)");
+    auto st = (cudaStream_t)stream;
+    SGN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    const int64_t work = conf_coef ? R * SR * K : R * 3;
+    int nb = cdiv(work > 0 ? work : 1, LOSS_THREADS);
+    if (nb > 148 * 16) nb = 148 * 16;
+    launch(loss_fwd_bwd_kernel, nb, LOSS_THREADS, 0, st, ray_color, gt, ray_mask, conf_coef, R, SR * K, hit_count, color_weight, conf_weight, zero_eps,
+           const_term, loss, d_ray_color, d_conf_coef);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_adam_step_count(float* step, void* stream)
+{
+    SGN_CHECK_ARG(step != nullptr, "sgn_adam_step_count: NULL");
+    launch(step_increment_kernel, 1, 1, 0, (cudaStream_t)stream, step);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint8_t* active, int64_t N, int C, float lr, float beta1,
+                             float beta2, float eps, const float* step, float grad_scale, int zero_grad, void* stream)
+{
+    SGN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && step && N >= 0 && C > 0, "sgn_adam_rows: bad argument");
+    if (N == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    const bool vec = (C % 4 == 0) && (((uintptr_t)grad & 15) == 0);
+    if (vec)
+        launch(adam_rows_kernel<4>, cdiv(N, 128), 128, 0, st, param, grad, exp_avg, exp_avg_sq, active, N, C, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
+    else
+        launch(adam_rows_kernel<1>, cdiv(N, 128), 128, 0, st, param, grad, exp_avg, exp_avg_sq, active, N, C, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}

@@ -382,6 +382,89 @@ class _Aggregate(torch.autograd.Function):
         return (None, d_emb, d_col, d_dir, d_conf, *d_w, *d_b)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# training step without autograd (sgnerf_b200/train.py): the same entry points, called in order, gradients into caller-owned buffers
+# ---------------------------------------------------------------------------------------------------------
+def aggregate_train_forward(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision):
+    """sgn_agg_forward with save_for_backward = 1.  All tensors are contiguous fp32 CUDA tensors already (no checks: hot loop).
+    Returns (decoded, ray_valid, loc_pers, weight, conf_coef, workspace, tables)."""
+    R, SR, K = pidx.shape
+    dev = pidx.device
+    nbytes = C.c_size_t()
+    _lib.call("sgn_agg_workspace_bytes", C.byref(cfg), xyz.shape[0], R, SR, K, precision, 1, C.byref(nbytes))
+    ws = _workspace(nbytes.value, dev)
+    decoded = torch.empty(R, SR, 4, dtype=torch.float32, device=dev)
+    ray_valid = torch.empty(R, SR, dtype=torch.uint8, device=dev)
+    loc_pers = torch.empty(R, SR, 3, dtype=torch.float32, device=dev)
+    weight = torch.empty(R, SR, K, dtype=torch.float32, device=dev)
+    conf_coef = torch.empty(R, SR, K, dtype=torch.float32, device=dev)
+    tb = _tables(xyz, embedding, color, dirs, conf, label_emb)
+    _lib.call("sgn_agg_forward", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w), _ptr(raydir),
+              _ptr(campos), _ptr(camrotc2w), R, SR, K, precision, 1, _ptr(decoded), _ptr(ray_valid), _ptr(loc_pers), _ptr(weight), _ptr(conf_coef),
+              _ptr(ws), ws.numel() * 4, _stream())
+    return decoded, ray_valid, loc_pers, weight, conf_coef, ws, tb
+
+
+def aggregate_train_backward(cfg, weights, biases, tb, pidx, loc_w, raydir, campos, camrotc2w, precision, d_decoded, d_conf_coef, d_weights, d_biases,
+                             d_emb, d_color, d_dir, d_conf, ws):
+    """sgn_agg_backward_prec: gradients are ACCUMULATED (+=) into d_weights / d_biases (lists, entries may be None) and the point-table
+    accumulators d_emb / d_color / d_dir / d_conf (any may be None)."""
+    R, SR, K = pidx.shape
+    gr = SgnPointGrads()
+    gr.embedding = d_emb.data_ptr() if d_emb is not None else None
+    gr.color = d_color.data_ptr() if d_color is not None else None
+    gr.dir = d_dir.data_ptr() if d_dir is not None else None
+    gr.conf = d_conf.data_ptr() if d_conf is not None else None
+    _lib.call("sgn_agg_backward_prec", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w), _ptr(raydir),
+              _ptr(campos), _ptr(camrotc2w), R, SR, K, precision, _ptr(d_decoded), _ptr(d_conf_coef), _ptr_array(d_weights), _ptr_array(d_biases),
+              C.byref(gr), _ptr(ws), ws.numel() * 4, _stream())
+
+
+def composite_forward_raw(decoded, ray_dist_, valid_u8, bg, blend=0):
+    """sgn_composite_forward, ray colour only (no autograd)."""
+    R, SR = decoded.shape[0], decoded.shape[1]
+    ray_color = torch.empty(R, 3, dtype=torch.float32, device=decoded.device)
+    _lib.call("sgn_composite_forward", _ptr(decoded), _ptr(ray_dist_), _ptr(valid_u8), _ptr(bg), blend, R, SR, _ptr(ray_color), None, None, None, None,
+              _stream())
+    return ray_color
+
+
+def composite_backward_raw(decoded, ray_dist_, valid_u8, bg, d_ray_color, blend=0):
+    R, SR = decoded.shape[0], decoded.shape[1]
+    d_dec = torch.empty_like(decoded)
+    _lib.call("sgn_composite_backward", _ptr(decoded), _ptr(ray_dist_), _ptr(valid_u8), _ptr(bg), blend, R, SR, _ptr(d_ray_color), None, None, None,
+              _ptr(d_dec), _stream())
+    return d_dec
+
+
+def loss_hit_count(ray_mask, count):
+    _lib.call("sgn_loss_hit_count", _ptr(ray_mask), ray_mask.numel(), _ptr(count), _stream())
+
+
+def loss_forward_backward(ray_color, gt, ray_mask, conf_coef, hit_count, loss, color_weight=1.0, conf_weight=1e-4, zero_eps=1e-3, const_term=1e-6):
+    """The reference's loss (base_rendering_model.py:543-641) and its gradients in one pass (sgn_loss_forward_backward).
+    Returns (d_ray_color [R,3], d_conf_coef [R,SR,K] or None); `loss` (device scalar) is overwritten."""
+    R = ray_color.shape[0]
+    d_color = torch.empty_like(ray_color)
+    SR, K = (conf_coef.shape[1], conf_coef.shape[2]) if conf_coef is not None else (1, 1)
+    d_conf = torch.empty_like(conf_coef) if conf_coef is not None else None
+    _lib.call("sgn_loss_forward_backward", _ptr(ray_color), _ptr(gt), _ptr(ray_mask), _ptr(conf_coef), R, SR, K, _ptr(hit_count), float(color_weight),
+              float(conf_weight), float(zero_eps), float(const_term), _ptr(loss), _ptr(d_color), _ptr(d_conf), _stream())
+    return d_color, d_conf
+
+
+def adam_rows(param, grad, exp_avg, exp_avg_sq, active, step, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, zero_grad=True):
+    """sgn_adam_rows on a [N,C] (or [N]) table; `step` is the device step counter (already incremented for this step)."""
+    N = param.shape[0]
+    Cc = param.numel() // max(N, 1)
+    _lib.call("sgn_adam_rows", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), _ptr(active), N, Cc, float(lr), float(betas[0]), float(betas[1]),
+              float(eps), _ptr(step), float(grad_scale), int(zero_grad), _stream())
+
+
+def adam_step_count(step):
+    _lib.call("sgn_adam_step_count", _ptr(step), _stream())
+
+
 def build_point_cache(cfg, weights, embedding, label_emb=None):
     """Inference cache of the bf16 path (sgn_agg_point_cache_build): the point-only part of block1.0 (and block2_bpnet.0) per point.
     Valid until the embeddings or the aggregator weights change; pass it to aggregate(point_cache=...)."""

@@ -1,13 +1,28 @@
 """Training step of the render path without host synchronisation, captured in a CUDA graph.
 
 What it replaces: one iteration of the reference's loop -- NeuralPointsRayMarching.forward on a random-pixel patch, the colour
-MSE over the rays that hit the cloud + the zero-one regulariser on conf_coefficient (models/base_rendering_model.py:543-607,
-`zero_one_loss_items=conf_coefficient`, weight 1e-4), backward, Adam on the aggregator MLP (lr) and the point tables (plr)
-(models/mvs_points_volumetric_model.py:67-109).  The reference compacts the hit rays on the host (`.cpu()` syncs at
+MSE over the rays that hit the cloud + the zero-one regulariser on conf_coefficient (models/base_rendering_model.py:543-641,
+`zero_one_loss_items=conf_coefficient`, weight 1e-4, --zero_epsilon 1e-3), backward, Adam on the aggregator MLP (lr) and the point
+tables (plr) (models/mvs_points_volumetric_model.py:67-109).  The reference compacts the hit rays on the host (`.cpu()` syncs at
 query_point_indices_worldcoords.py:834/:946); here rows stay uncompacted and the loss is masked, so nothing in the step depends on
-a device value and the whole step -- query, aggregation forward (TF32 tensor-core GEMMs), compositing, loss, backward with the
-scatter-add into the point tables, gradient all-reduce, Adam -- is one graph launch.  With world_size > 1 the gradients of all
-parameters are summed over ranks in one flat bucket (NCCL) inside the same graph; every rank applies the identical Adam step.
+a device value and the whole step is one graph launch.
+
+TrainStep calls the library's entry points in order -- no autograd graph is built:
+
+    sgn_query -> sgn_agg_forward (save) -> sgn_ray_dist -> sgn_composite_forward -> sgn_loss_hit_count [-> all-reduce of the count]
+    -> sgn_loss_forward_backward (loss + d ray_color + d conf_coefficient in one pass) -> sgn_composite_backward -> sgn_agg_backward
+    (TF32 tensor-core GEMMs, scatter-add into the point-table gradient accumulators) [-> ONE in-place all-reduce of the flat gradient
+    bucket] -> Adam: fused torch Adam on the ~30 MLP tensors, sgn_adam_rows on the point tables.
+
+All gradients live in one flat fp32 bucket (MLP gradients first, then the point tables') whose slices are the accumulators the backward
+adds into, so the multi-GPU exchange is a single NCCL all-reduce of that buffer in place -- no flatten / divide / un-flatten copies:
+the loss of every rank is normalised by the GLOBAL hit count, so the sum over ranks IS the gradient of the single-GPU step on the
+union of the rays.  sgn_adam_rows updates only the rows that ever received a gradient (identical to dense Adam: the other rows have zero
+moments) and clears the gradient rows it consumed, so neither a dense Adam pass over the N-row tables nor a dense memset of their
+gradients happens per step.
+
+AutogradTrainStep is the same iteration written with torch.autograd over the ops' autograd Functions and torch.optim.Adam on every
+parameter (the first implementation; kept as the cross-check of TrainStep in tests/test_gpu_train.py).
 """
 import torch
 import torch.distributed as dist
@@ -16,26 +31,14 @@ from . import dist as sdist
 from . import ops, pipeline
 
 
-class TrainStep:
-    """One training iteration as a replayable unit.  set_inputs() copies a batch into static device buffers, step() runs it.
-    With use_graph=True the first step() call runs three ordinary (eager) steps on the current inputs -- they allocate the optimiser
-    state and set kernel attributes, and they are real optimiser steps -- then captures the step and replays the capture from then on."""
-
-    def __init__(self, scene, n_rays, near, far, bg_color, lr=5e-4, plr=2e-3, conf_loss_weight=1e-4, precision=ops.PRECISION_TF32,
-                 use_graph=True, train_dir=True, group=None, zero_epsilon=1e-3):
-        """scene: pipeline.RenderScene (its tensors become the trainable leaves).  n_rays: rays per step on this rank (fixed)."""
+class _StepBase:
+    def __init__(self, scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon):
         self.scene, self.n_rays, self.near, self.far = scene, int(n_rays), float(near), float(far)
         self.precision, self.conf_w, self.group = precision, float(conf_loss_weight), group
         self.zero_eps = float(zero_epsilon)             # --zero_epsilon of the reference (base_rendering_model.py:119, default 1e-3)
+        self.lr, self.plr = float(lr), float(plr)
         dev = scene.xyz.device
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.net_params = [t.requires_grad_(True) for t in scene.weights + scene.biases]
-        self.pt_params = [scene.embedding, scene.color] + ([scene.dirs] if train_dir else []) + ([scene.conf] if scene.conf is not None else [])
-        for t in self.pt_params:
-            t.requires_grad_(True)
-        self.params = self.net_params + self.pt_params
-        self.optim = torch.optim.Adam([{"params": self.net_params, "lr": lr}, {"params": self.pt_params, "lr": plr}],
-                                      capturable=bool(use_graph), fused=True)
         q = scene.qopt
         # static inputs of the graph: the caller fills them (set_inputs) before every step
         self.raydir = torch.zeros(self.n_rays, 3, device=dev)
@@ -47,9 +50,9 @@ class TrainStep:
         self.loss = torch.zeros((), device=dev)
         self.n_hit = torch.zeros((), device=dev)
         self.use_graph, self._graph = bool(use_graph), None
+        self.train_dir = bool(train_dir)
         scene.grid()                                   # host-side grid parameters + build, once per cloud version
 
-    # ------------------------------------------------------------------------------------------------
     def set_inputs(self, campos, camrotc2w, raydir, gt, t):
         """Device or host tensors; copied into the graph's static buffers (stream-ordered, no synchronisation)."""
         self.campos.copy_(campos.reshape(3), non_blocking=True)
@@ -62,31 +65,6 @@ class TrainStep:
         """Per-ray depth candidates with the reference's training jitter (diff_ray_marching.py:370-386)."""
         return pipeline.middle_point_ts(self.near, self.far, self.scene.qopt.z_depth_dim, self.raydir.device, jitter=jitter,
                                         n_rays=self.n_rays, generator=generator)
-
-    def _body(self):
-        q = self.scene.qopt
-        out = pipeline.render_rays(self.scene, self.campos, self.camrot, self.raydir, self.near, self.far, self.bg,
-                                   precision=self.precision, t=self.t, want_aux=True)
-        # the reference's loss (base_rendering_model.py:543-641) on uncompacted rows: colour MSE over the rays that hit the cloud
-        # (`ray_masked_coarse_raycolor`, + 1e-6 per colour item) and the zero-one regulariser mean(log(v) + log(1 - v)),
-        # v = clamp(conf_coefficient, eps, 1 - eps), over the [R'', SR, K] block of the hit rays.  Sums are normalised by the GLOBAL
-        # hit count (all ranks), and gradients are summed over ranks: the multi-GPU step is the single-GPU step on the union of rays.
-        hit = (out.ray_mask > 0).float()
-        cnt = hit.sum()
-        if self.world > 1:
-            dist.all_reduce(cnt, group=self.group)
-        cnt = cnt.clamp(min=1.0)
-        mse = (((out.ray_color - self.gt) ** 2) * hit[:, None]).sum() / (3.0 * cnt)
-        v = out.conf_coef.clamp(self.zero_eps, 1.0 - self.zero_eps)
-        zo = ((torch.log(v) + torch.log(1.0 - v)) * hit[:, None, None]).sum() / (cnt * q.SR * q.K)
-        loss = mse + 1e-6 / self.world + self.conf_w * zo
-        self.optim.zero_grad(set_to_none=True)
-        loss.backward()
-        if self.world > 1:
-            sdist.allreduce_grads(self.params, average=False, group=self.group)
-        self.optim.step()
-        self.loss.copy_(loss.detach())
-        self.n_hit.copy_(hit.sum())
 
     def step(self):
         """One training step on the inputs last given to set_inputs.  Returns nothing; self.loss / self.n_hit are device scalars."""
@@ -106,3 +84,113 @@ class TrainStep:
             with torch.cuda.graph(self._graph):
                 self._body()
         self._graph.replay()
+
+
+class TrainStep(_StepBase):
+    """One training iteration as a replayable unit.  set_inputs() copies a batch into static device buffers, step() runs it.
+    With use_graph=True the first step() call runs three ordinary (eager) steps on the current inputs -- they allocate the optimiser
+    state and set kernel attributes, and they are real optimiser steps -- then captures the step and replays the capture from then on."""
+
+    def __init__(self, scene, n_rays, near, far, bg_color, lr=5e-4, plr=2e-3, conf_loss_weight=1e-4, precision=ops.PRECISION_TF32,
+                 use_graph=True, train_dir=True, group=None, zero_epsilon=1e-3):
+        """scene: pipeline.RenderScene (its tensors are updated in place).  n_rays: rays per step on this rank (fixed)."""
+        super().__init__(scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon)
+        if precision == ops.PRECISION_BF16:
+            raise ValueError("TrainStep runs the fp32 or tf32 path; the bf16 tensor-core path is forward-only")
+        dev = scene.xyz.device
+        self.net_params = scene.weights + scene.biases
+        pts = [("embedding", scene.embedding), ("color", scene.color)] + ([("dirs", scene.dirs)] if train_dir else []) + \
+              ([("conf", scene.conf)] if scene.conf is not None else [])
+        self.pt_names = [n for n, _ in pts]
+        self.pt_params = [t for _, t in pts]
+        self.params = self.net_params + self.pt_params
+        for t in self.params:
+            t.requires_grad_(False)
+        # one flat gradient bucket; every parameter's gradient accumulator is a slice of it
+        sizes = [p.numel() for p in self.params]
+        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.grads, off = [], 0
+        for p, n in zip(self.params, sizes):
+            self.grads.append(self.flat_grad[off:off + n].view_as(p))
+            off += n
+        self.n_net = sum(p.numel() for p in self.net_params)
+        nl = len(scene.weights)
+        self.d_w, self.d_b = self.grads[:nl], self.grads[nl:2 * nl]
+        self.pt_grads = dict(zip(self.pt_names, self.grads[2 * nl:]))
+        # MLP: torch's fused Adam on gradient views; point tables: sgn_adam_rows with its own moments, step counter and active-row flags
+        for p, g in zip(self.net_params, self.grads[:2 * nl]):
+            p.grad = g
+        self.optim = torch.optim.Adam([{"params": self.net_params, "lr": lr}], capturable=bool(use_graph), fused=True)
+        self.pt_m = [torch.zeros_like(p) for p in self.pt_params]
+        self.pt_v = [torch.zeros_like(p) for p in self.pt_params]
+        self.pt_active = [torch.zeros(p.shape[0], dtype=torch.uint8, device=dev) for p in self.pt_params]
+        self.pt_step = torch.zeros((), dtype=torch.float32, device=dev)
+        self._cnt = torch.zeros((), dtype=torch.float32, device=dev)
+
+    @torch.no_grad()
+    def _body(self):
+        sc, q = self.scene, self.scene.qopt
+        grid, hp = sc.grid()
+        pidx, loc_w, _, rmask = ops.query(grid, self.campos, self.raydir, self.t, q.SR, q.K, q.kernel_size[0], hp.radius2)
+        dec, valid, loc_pers, _, conf, ws, tb = ops.aggregate_train_forward(
+            sc.agg_cfg, sc.weights, sc.biases, sc.xyz, sc.embedding, sc.color, sc.dirs, sc.conf, sc.label_emb, pidx, loc_w, self.raydir,
+            self.campos, self.camrot, self.precision)
+        rd = ops.ray_dist(loc_pers, valid, hp.vsize[2], 1)
+        ray_color = ops.composite_forward_raw(dec, rd, valid, self.bg)
+        # global number of rays that hit the cloud: the normalisation of both loss terms
+        self._cnt.zero_()
+        ops.loss_hit_count(rmask, self._cnt)
+        self.n_hit.copy_(self._cnt)
+        if self.world > 1:
+            dist.all_reduce(self._cnt, group=self.group)
+        d_color, d_conf = ops.loss_forward_backward(ray_color, self.gt, rmask, conf, self._cnt, self.loss, 1.0, self.conf_w, self.zero_eps,
+                                                    1e-6 / self.world)
+        d_dec = ops.composite_backward_raw(dec, rd, valid, self.bg, d_color)
+        self.flat_grad[:self.n_net].zero_()             # MLP accumulators (1.7 MB); the point-table rows are cleared by sgn_adam_rows
+        g = self.pt_grads
+        ops.aggregate_train_backward(sc.agg_cfg, sc.weights, sc.biases, tb, pidx, loc_w, self.raydir, self.campos, self.camrot, self.precision,
+                                     d_dec, d_conf, self.d_w, self.d_b, g.get("embedding"), g.get("color"), g.get("dirs"), g.get("conf"), ws)
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, group=self.group)          # in place, SUM: losses are normalised by the global hit count
+        self.optim.step()
+        ops.adam_step_count(self.pt_step)
+        for p, gr, m, v, act in zip(self.pt_params, self.grads[len(self.net_params):], self.pt_m, self.pt_v, self.pt_active):
+            ops.adam_rows(p, gr, m, v, act, self.pt_step, self.plr)
+
+
+class AutogradTrainStep(_StepBase):
+    """The same iteration through torch.autograd (ops._Aggregate / ops._Composite) and torch.optim.Adam on every parameter, dense
+    gradients; the multi-GPU exchange flattens the gradients into a bucket and back (dist.allreduce_grads)."""
+
+    def __init__(self, scene, n_rays, near, far, bg_color, lr=5e-4, plr=2e-3, conf_loss_weight=1e-4, precision=ops.PRECISION_TF32,
+                 use_graph=True, train_dir=True, group=None, zero_epsilon=1e-3):
+        super().__init__(scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon)
+        self.net_params = [t.requires_grad_(True) for t in scene.weights + scene.biases]
+        self.pt_params = [scene.embedding, scene.color] + ([scene.dirs] if train_dir else []) + ([scene.conf] if scene.conf is not None else [])
+        for t in self.pt_params:
+            t.requires_grad_(True)
+        self.params = self.net_params + self.pt_params
+        self.optim = torch.optim.Adam([{"params": self.net_params, "lr": lr}, {"params": self.pt_params, "lr": plr}],
+                                      capturable=bool(use_graph), fused=True)
+
+    def _body(self):
+        q = self.scene.qopt
+        out = pipeline.render_rays(self.scene, self.campos, self.camrot, self.raydir, self.near, self.far, self.bg,
+                                   precision=self.precision, t=self.t, want_aux=True)
+        # the reference's loss (base_rendering_model.py:543-641) on uncompacted rows, normalised by the GLOBAL hit count
+        hit = (out.ray_mask > 0).float()
+        cnt = hit.sum()
+        self.n_hit.copy_(cnt)
+        if self.world > 1:
+            dist.all_reduce(cnt, group=self.group)
+        cnt = cnt.clamp(min=1.0)
+        mse = (((out.ray_color - self.gt) ** 2) * hit[:, None]).sum() / (3.0 * cnt)
+        v = out.conf_coef.clamp(self.zero_eps, 1.0 - self.zero_eps)
+        zo = ((torch.log(v) + torch.log(1.0 - v)) * hit[:, None, None]).sum() / (cnt * q.SR * q.K)
+        loss = mse + 1e-6 / self.world + self.conf_w * zo
+        self.optim.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.world > 1:
+            sdist.allreduce_grads(self.params, average=False, group=self.group)
+        self.optim.step()
+        self.loss.copy_(loss.detach())

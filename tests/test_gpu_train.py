@@ -150,3 +150,88 @@ def test_full_path_rgb_and_depth_vs_oracle(precision, tol):
     torch.testing.assert_close(out.depth.cpu()[sel], ref.coarse_depth[0], rtol=0, atol=tol)
     assert float(out.depth.cpu()[~sel].abs().max()) == 0.0 if bool((~sel).any()) else True
     torch.testing.assert_close(aux.depth, out.depth, rtol=0, atol=1e-5)
+
+
+def test_loss_kernel_matches_the_reference_formula_and_its_autograd():
+    """sgn_loss_forward_backward against torch: colour MSE over the hit rays + 1e-6 + w * mean(log v + log(1 - v)), v = clamp(conf, eps, 1 - eps)
+    over the [R'', SR, K] block of the hit rays (base_rendering_model.py:543-641), and torch.autograd's gradients of it (zero where the
+    clamp is active, zero for the rays that missed)."""
+    g = torch.Generator().manual_seed(0)
+    R, SR, K = 777, 24, 8
+    color = torch.rand(R, 3, generator=g)
+    gt = torch.rand(R, 3, generator=g)
+    mask = (torch.rand(R, generator=g) < 0.7).to(torch.int8)
+    conf = (torch.rand(R, SR, K, generator=g) * 1.2 - 0.1).clamp(1e-4, 1.0)       # values on both sides of [eps, 1 - eps]
+    conf[0, 0, :4] = torch.tensor([1e-3, 1.0 - 1e-3, 5e-4, 1.0])
+    c_ref, f_ref = color.clone().requires_grad_(True), conf.clone().requires_grad_(True)
+    sel = mask > 0
+    eps, w = 1e-3, 1e-4
+    v = torch.clamp(f_ref[sel], eps, 1 - eps)
+    want = torch.nn.functional.mse_loss(c_ref[sel], gt[sel]) + 1e-6 + w * torch.mean(torch.log(v) + torch.log(1 - v))
+    want.backward()
+    cnt = torch.zeros((), device="cuda")
+    ops.loss_hit_count(mask.cuda(), cnt)
+    assert float(cnt) == float(sel.sum())
+    loss = torch.zeros((), device="cuda")
+    d_color, d_conf = ops.loss_forward_backward(color.cuda(), gt.cuda(), mask.cuda(), conf.cuda(), cnt, loss, 1.0, w, eps, 1e-6)
+    assert abs(float(loss) - float(want)) <= 1e-6 * max(1.0, abs(float(want)))
+    torch.testing.assert_close(d_color.cpu(), c_ref.grad, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(d_conf.cpu(), f_ref.grad, rtol=1e-4, atol=1e-10)
+    assert float(d_color.cpu()[~sel].abs().sum()) == 0.0 and float(d_conf.cpu()[~sel].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("C", [32, 3, 1])
+def test_adam_rows_equals_dense_torch_adam(C):
+    """sgn_adam_rows over several steps with gradients that touch different row subsets (and leave most rows untouched) against
+    torch.optim.Adam on the dense table: same parameters (a row that never received a gradient is not visited and does not move; a row
+    that did keeps being updated by its decaying moments), gradient rows cleared."""
+    g = torch.Generator().manual_seed(1)
+    N = 5000
+    shape = (N, C) if C > 1 else (N,)
+    p0 = torch.randn(*shape, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=2e-3)
+    p = p0.clone().cuda()
+    grad, m, v = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    active = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    step = torch.zeros((), device="cuda")
+    for it in range(6):
+        rows = torch.randperm(N, generator=g)[:300 + 50 * it]
+        gd = torch.zeros(*shape)
+        gd[rows] = torch.randn(*((rows.numel(), C) if C > 1 else (rows.numel(),)), generator=g) * (10.0 ** (it - 3))
+        ref.grad = gd.clone()
+        opt.step()
+        grad.copy_(gd.cuda())
+        ops.adam_step_count(step)
+        ops.adam_rows(p, grad, m, v, active, step, 2e-3)
+        assert float(grad.abs().sum()) == 0.0                  # consumed rows are cleared
+    torch.testing.assert_close(p.cpu(), ref.detach(), rtol=2e-5, atol=2e-6)
+    untouched = active.cpu() == 0
+    assert 0.2 < float(untouched.float().mean()) < 0.9 and torch.equal(p.cpu()[untouched], p0[untouched])
+
+
+def test_direct_step_matches_the_autograd_step():
+    """train.TrainStep (library entry points called in order, fused loss kernel, row Adam, flat gradient bucket) against
+    train.AutogradTrainStep (torch.autograd over the same kernels, torch loss, dense torch Adam) from the same state on the same batch:
+    same hit count, same loss trajectory, same parameters up to the rounding of the float atomics."""
+    def build(cls):
+        ts = _make(ops.PRECISION_TF32, use_graph=False)
+        if cls is train.TrainStep:
+            return ts
+        sc = ts.scene
+        fresh = _make(ops.PRECISION_TF32, use_graph=False)      # same seeds -> same scene / batch; rebuild it as the autograd step
+        b = train.AutogradTrainStep(fresh.scene, fresh.n_rays, fresh.near, fresh.far, torch.ones(3), precision=ops.PRECISION_TF32, use_graph=False)
+        b.set_inputs(fresh.campos, fresh.camrot, fresh.raydir, fresh.gt, fresh.t)
+        return b
+    a, b = build(train.TrainStep), build(train.AutogradTrainStep)
+    la, lb = [], []
+    for _ in range(5):
+        a.step(); b.step()
+        la.append(float(a.loss)); lb.append(float(b.loss))
+    assert float(a.n_hit) == float(b.n_hit) > 50
+    assert np.allclose(la, lb, rtol=2e-3, atol=1e-6), (la, lb)
+    for pa, pb in zip(a.params, b.params):
+        assert float((pa.detach() - pb.detach()).abs().mean()) < 2e-4
+    # rows no ray ever touched did not move and were never visited
+    emb_active = a.pt_active[0].bool()
+    assert 0 < int(emb_active.sum()) < emb_active.numel()
