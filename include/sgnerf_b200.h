@@ -102,6 +102,10 @@ int sgn_query(const SgnGrid* g, const float* campos /*[3]*/, const float* raydir
               uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w, int32_t* sample_mask,
               int32_t* sample_label, int8_t* ray_mask, void* stream);
 
+/* Tuning / test aid: sgn_query has two march kernels with identical results -- a thread-per-ray brick walk (frames) and a
+ * warp-per-ray kernel (small ray counts, e.g. a training patch); mode 0 picks by ray count, 1 / 2 force one of them. */
+int sgn_query_march_mode(int mode);
+
 /* Strict-compat materialisation of NeuralPoints.forward's gathered tensors
  * (neural_points.py:956-972): out[j, :] = table[max(pidx[j],0), :] for n_rows index entries. */
 int sgn_gather_rows(const float* table /*[N,C]*/, int C, const int32_t* pidx, int64_t n_rows, float* out, void* stream);
@@ -292,6 +296,12 @@ int sgn_adam_step_count(float* step, void* stream);
  * first; zero_grad != 0 clears the gradient rows it consumed (the accumulator then never needs a dense memset). */
 int sgn_adam_rows(float* param, float* grad, float* exp_avg, float* exp_avg_sq, uint8_t* active, int64_t N, int C, float lr, float beta1,
                   float beta2, float eps, const float* step, float grad_scale, int zero_grad, void* stream);
+
+/* The same for up to 8 tables [N, C_k] (C_k <= 32) that share their rows -- the point tables -- in one pass: a row is active when any
+ * table has a non-zero gradient in it.  params / grads / exp_avg / exp_avg_sq and C are [host] arrays of n_tables entries. */
+int sgn_adam_rows_multi(int n_tables, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                        const int32_t* C /*[host]*/, uint8_t* active, int64_t N, float lr, float beta1, float beta2, float eps,
+                        const float* step, float grad_scale, int zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,7 @@ SIGNATURES = {
     "sgn_grid_buffer": (c_int, [c_void, c_int, C.POINTER(c_void), C.POINTER(c_i64)]),
     "sgn_query": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_int, c_int, c_int, c_int, c_f32,
                           c_void, c_void, c_void, c_u64, c_void, c_void, c_void, c_void, c_void, c_void]),
+    "sgn_query_march_mode": (c_int, [c_int]),
     "sgn_gather_rows": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void]),
     "sgn_agg_num_layers": (c_int, [C.POINTER(SgnAggCfg)]),
     "sgn_agg_layer_shape": (c_int, [C.POINTER(SgnAggCfg), c_int, C.POINTER(c_int), C.POINTER(c_int)]),
@@ -89,6 +90,8 @@ SIGNATURES = {
     "sgn_loss_forward_backward": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_void, c_f32, c_f32, c_f32, c_f32, c_void, c_void,
                                           c_void, c_void]),
     "sgn_adam_step_count": (c_int, [c_void, c_void]),
+    "sgn_adam_rows_multi": (c_int, [c_int, C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(C.c_int32), c_void,
+                                    c_i64, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),
     "sgn_adam_rows": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),
 }
 

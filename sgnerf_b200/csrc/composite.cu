@@ -297,6 +297,89 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
     }
 }
 
+// The same frame tail with one THREAD per ray (SR <= 64): the warp-per-ray kernel above spends ~320 warp instructions per ray on its
+// scans and reductions (it is bound by instruction issue at 0.12 ms per 640x480 frame); a thread that walks its ray's samples in order
+// needs ~25 instructions per sample.  A block owns 128 consecutive rays and stages their rows through shared memory with coalesced
+// accesses: camera depth + validity of all samples, the decoded (sigma, r, g, b) rows eight samples at a time (only the samples that
+// have neighbours are fetched), the opacities on the way out.  Transmittance is the running product in sample order.
+constexpr int ROWS_RAYS = 128, ROWS_CHUNK = 8;
+
+template <int BLEND>
+__global__ void __launch_bounds__(ROWS_RAYS)
+render_composite_rows_kernel(const float4* __restrict__ decoded, const float* __restrict__ zsrc, int zstride, const uint8_t* __restrict__ valid,
+                             const int8_t* __restrict__ ray_mask, float vsize_z, int mode_unit, const float* __restrict__ bg, int64_t R, int SR,
+                             float* __restrict__ ray_color, float* __restrict__ opacity, float* __restrict__ bg_t, float* __restrict__ depth)
+{
+    extern __shared__ float4 s_rows[];                                     // [128][CHUNK + 1] decoded rows (padded: conflict-free 16-byte reads)
+    float* s_z = (float*)(s_rows + ROWS_RAYS * (ROWS_CHUNK + 1));          // [128][SR + 1] camera depth, overwritten by the opacity
+    uint8_t* s_v = (uint8_t*)(s_z + ROWS_RAYS * (SR + 1));                 // [128][SR]
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * ROWS_RAYS;
+    const int nr = (int)min((int64_t)ROWS_RAYS, R - r0);
+    const int zs = SR + 1;
+    // stage depth and validity of the block's rays (consecutive rays are consecutive in memory)
+    for (int i = tid; i < nr * SR; i += ROWS_RAYS) {
+        const int ray = i / SR, sm = i - ray * SR;
+        s_z[ray * zs + sm] = __ldg(zsrc + (r0 * SR + i) * zstride);
+        s_v[ray * SR + sm] = __ldg(valid + r0 * SR + i);
+    }
+    const int64_t r = r0 + tid;
+    const bool live = tid < nr;
+    const bool hit = live && (!ray_mask || ray_mask[r] > 0);
+    const float b0 = bg ? bg[0] : 0.f, b1 = bg ? bg[1] : 0.f, b2 = bg ? bg[2] : 0.f;
+    float T = 1.0f, cr = 0.f, cg = 0.f, cb = 0.f, zmax = -INFINITY, dsum = 0.f, wsum = 0.f;
+    __syncthreads();
+    for (int c0 = 0; c0 < SR; c0 += ROWS_CHUNK) {
+        const int cn = min(ROWS_CHUNK, SR - c0);
+        // decoded rows of this chunk: thread i takes (ray i / cn, sample i % cn): a warp covers whole 16 * cn-byte runs
+        for (int i = tid; i < nr * cn; i += ROWS_RAYS) {
+            const int ray = i / cn, j = i - ray * cn;
+            if (s_v[ray * SR + c0 + j]) s_rows[ray * (ROWS_CHUNK + 1) + j] = __ldg(decoded + (r0 + ray) * SR + c0 + j);
+        }
+        __syncthreads();
+        if (live) {
+            for (int j = 0; j < cn; j++) {
+                const int sm = c0 + j;
+                const float v = s_v[tid * SR + sm] ? 1.0f : 0.0f;
+                const float z = s_z[tid * zs + sm];
+                // step size: running maximum of the camera depth, difference to the next sample, voxel size where degenerate
+                const float cm = fmaxf(zmax, z);
+                float d = (sm + 1 < SR) ? fmaxf(cm, s_z[tid * zs + sm + 1]) - cm : vsize_z;
+                bool bad = d < 1e-8f;
+                if (mode_unit > 0) bad = bad || (d > 2.0f * vsize_z);
+                const float m = bad ? 1.0f : 0.0f;
+                d = d * (1.0f - m) + m * vsize_z;
+                zmax = cm;
+                float o = 0.f;
+                if (hit) {
+                    const float4 f = v > 0.f ? s_rows[tid * (ROWS_CHUNK + 1) + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    o = 1.0f - expf(-(f.x * v) * (d * v));
+                    const float w = BLEND == 0 ? o * T : o * T * T;
+                    cr += f.y * w; cg += f.z * w; cb += f.w * w;
+                    dsum += (o * T) * z; wsum += o * T;
+                    T *= (1.0f - o) + 1e-10f;
+                }
+                s_z[tid * zs + sm] = o;                                      // the depth of this sample is not needed again
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        if (ray_color) {
+            ray_color[r * 3 + 0] = hit ? cr + b0 * T : b0;
+            ray_color[r * 3 + 1] = hit ? cg + b1 * T : b1;
+            ray_color[r * 3 + 2] = hit ? cb + b2 * T : b2;
+        }
+        if (bg_t) bg_t[r] = hit ? T : 1.0f;
+        if (depth) depth[r] = hit ? dsum / (wsum + 1e-6f) : 0.f;
+    }
+    if (opacity)
+        for (int i = tid; i < nr * SR; i += ROWS_RAYS) {
+            const int ray = i / SR, sm = i - ray * SR;
+            opacity[r0 * SR + i] = s_z[ray * zs + sm];
+        }
+}
+
 // `prob == 1` outputs (models/neural_points_volumetric_model.py:633-656): one warp per ray.  Lanes find the first sample of largest
 // opacity (torch.max returns the first maximal index), then lane k < K reads neighbour k of that sample -- invalid slots read point 0,
 // as the reference's clamp(pidx, 0) gather does -- and the K-wide reductions are warp shuffles.  Rays with ray_mask <= 0 (no row in
@@ -443,6 +526,17 @@ static int render_composite_impl(const float* decoded, const float* zsrc, int zs
     SGN_CHECK_ARG(decoded && zsrc && ray_valid, "sgn_render_composite: NULL input");
     if (R == 0) return SGN_OK;
     auto st = (cudaStream_t)stream;
+    if (SR <= 64) {
+        const size_t sm = sizeof(float4) * ROWS_RAYS * (ROWS_CHUNK + 1) + sizeof(float) * ROWS_RAYS * (SR + 1) + (size_t)ROWS_RAYS * SR;
+        if (blend == 0)
+            launch(render_composite_rows_kernel<0>, cdiv(R, ROWS_RAYS), ROWS_RAYS, sm, st, (const float4*)decoded, zsrc, zstride, ray_valid, ray_mask,
+                   vsize_z, raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
+        else
+            launch(render_composite_rows_kernel<1>, cdiv(R, ROWS_RAYS), ROWS_RAYS, sm, st, (const float4*)decoded, zsrc, zstride, ray_valid, ray_mask,
+                   vsize_z, raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);
+        SGN_LAUNCH_CHECK();
+        return SGN_OK;
+    }
     if (blend == 0)
         launch(render_composite_kernel<0>, comp_grid(R), COMP_WARPS * 32, 0, st, (const float4*)decoded, zsrc, zstride, ray_valid, ray_mask, vsize_z,
                                                                             raydist_mode_unit, bg, R, SR, ray_color, opacity, bg_transmission, depth);

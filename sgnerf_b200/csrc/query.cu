@@ -35,6 +35,7 @@ struct QueryGrid {
 };
 
 constexpr int MARCH_THREADS = 128;
+constexpr int64_t MARCH_WARP_BELOW = 131072;   // fewer rays than this: one warp per ray (march_warp_kernel)
 constexpr int MARCH_RANGES = 14;   // candidate ranges kept per ray (more are merged into the last one: tests a few extra candidates, never fewer)
 
 // march_kernel: empty space is skipped with a 3-D DDA over the 8^3-voxel brick mask, one THREAD per ray: a step per brick (0.128 m at
@@ -188,6 +189,97 @@ march_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restr
             if (sample_label) sample_label[o] = 0;
         }
     }
+}
+
+constexpr int MARCH_WARPS = 8;
+
+// march_warp_kernel: one WARP per ray, used for small ray counts (a training patch), where one thread per ray would leave the GPU
+// empty: lanes test 32 consecutive depth candidates against the brick mask, the survivors are queued in ray order and exact-tested
+// 32 at a time (same arithmetic, same ranks as march_kernel).
+
+__global__ void __launch_bounds__(MARCH_WARPS * 32)
+march_warp_kernel(QueryGrid g, const float* __restrict__ campos, const float* __restrict__ raydir, const float* __restrict__ t,
+             int t_per_ray, int64_t R, int D, int SR, const int32_t* __restrict__ ray_label, float* __restrict__ sample_loc_w,
+             int32_t* __restrict__ sample_mask, int32_t* __restrict__ sample_label, int8_t* __restrict__ ray_mask)
+{
+    const int lane = lane_id();
+    const int64_t r = (int64_t)blockIdx.x * MARCH_WARPS + (threadIdx.x >> 5);
+    if (r >= R) return;
+    const float cx = campos[0], cy = campos[1], cz = campos[2];
+    const float dx = raydir[3 * r], dy = raydir[3 * r + 1], dz = raydir[3 * r + 2];
+    const float* tr = t_per_ray ? t + r * D : t;
+    const int label = ray_label ? ray_label[r] : 0;
+    const float rvx = 1.0f / g.vx, rvy = 1.0f / g.vy, rvz = 1.0f / g.vz;
+    const float fdx = (float)g.dx + 0.01f, fdy = (float)g.dy + 0.01f, fdz = (float)g.dz + 0.01f;
+    __shared__ uint16_t s_queue[MARCH_WARPS][64];            // per warp: depth indices that passed the brick test, in ray order
+    uint16_t* queue = s_queue[threadIdx.x >> 5];
+    int cnt = 0, qn = 0;
+    // exact test of up to 32 queued candidates (lane i takes entry i): voxel coordinate as the reference computes it, occupancy bit,
+    // rank among the ray's occupied candidates by ballot + popcount (the reference's torch.cumsum, :843-844), sample store
+    auto drain = [&](int n) {
+        bool occ = false;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (lane < n) {
+            const float tv = __ldg(tr + queue[lane]);
+            // campos + raydir * t with separate fp32 multiply and add, as torch evaluates it
+            px = __fadd_rn(cx, __fmul_rn(dx, tv));
+            py = __fadd_rn(cy, __fmul_rn(dy, tv));
+            pz = __fadd_rn(cz, __fmul_rn(dz, tv));
+            const int vx = vox_coord_fast(px, g.ox, g.vx, rvx), vy = vox_coord_fast(py, g.oy, g.vy, rvy), vz = vox_coord_fast(pz, g.oz, g.vz, rvz);
+            if ((unsigned)vx < (unsigned)g.dx && (unsigned)vy < (unsigned)g.dy && (unsigned)vz < (unsigned)g.dz) {
+                const uint32_t c = ((uint32_t)vx * (uint32_t)g.dy + (uint32_t)vy) * (uint32_t)g.dz + (uint32_t)vz;   // < 2^31 (grid.cu:check_cfg)
+                occ = (__ldg(g.occ_bits + (c >> 5)) >> (c & 31)) & 1u;
+            }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, occ);
+        const int rank = cnt + __popc(b & ((1u << lane) - 1u));
+        if (occ && rank < SR) {
+            const int64_t o = r * SR + rank;
+            sample_loc_w[3 * o] = px; sample_loc_w[3 * o + 1] = py; sample_loc_w[3 * o + 2] = pz;
+            sample_mask[o] = 1;
+            if (sample_label) sample_label[o] = label;
+        }
+        cnt += __popc(b);
+    };
+    for (int base = 0; base < D && cnt < SR; base += 32) {
+        const int d = base + lane;
+        bool maybe = false;
+        if (d < D) {
+            // brick test: approximate voxel coordinate (a few 1e-5 off at most), 8^3-voxel brick, one bit.  The mask covers every brick
+            // with an occupied voxel inside or one voxel away, so a candidate that fails it cannot be occupied whatever the rounding;
+            // only the others are queued for the exact test, and the queue keeps them in ray order.
+            const float tv = __ldg(tr + d);
+            const float ax = (__fadd_rn(cx, __fmul_rn(dx, tv)) - g.ox) * rvx, ay = (__fadd_rn(cy, __fmul_rn(dy, tv)) - g.oy) * rvy,
+                        az = (__fadd_rn(cz, __fmul_rn(dz, tv)) - g.oz) * rvz;
+            if (ax > -0.01f && ay > -0.01f && az > -0.01f && ax < fdx && ay < fdy && az < fdz) {
+                const int bx = min((int)(ax * 0.125f), g.cdx - 1), by = min((int)(ay * 0.125f), g.cdy - 1), bz = min((int)(az * 0.125f), g.cdz - 1);
+                const int bc = (bx * g.cdy + by) * g.cdz + bz;
+                maybe = (__ldg(g.coarse_bits + (bc >> 5)) >> (bc & 31)) & 1u;
+            }
+        }
+        const unsigned mb = __ballot_sync(0xffffffffu, maybe);
+        if (mb == 0u) continue;
+        if (maybe) queue[qn + __popc(mb & ((1u << lane) - 1u))] = (uint16_t)d;
+        qn += __popc(mb);
+        __syncwarp();
+        if (qn >= 32) {
+            drain(32);
+            const uint16_t carry = queue[32 + lane];             // at most 31 entries stay behind
+            __syncwarp();
+            queue[lane] = carry;
+            qn -= 32;
+            __syncwarp();
+        }
+    }
+    if (qn > 0 && cnt < SR) drain(qn);
+    cnt = cnt < SR ? cnt : SR;
+    for (int s = cnt + lane; s < SR; s += 32) {  // unused slots stay at world (0,0,0), mask 0 (:835, :845)
+        const int64_t o = r * SR + s;
+        sample_loc_w[3 * o] = 0.f; sample_loc_w[3 * o + 1] = 0.f; sample_loc_w[3 * o + 2] = 0.f;
+        sample_mask[o] = 0;
+        if (sample_label) sample_label[o] = 0;
+    }
+    if (lane == 0) ray_mask[r] = 0;
 }
 
 constexpr int KNN_SLOTS = 1536;   // sample slots per block (64 rays at SR = 24): their occupied samples are compacted in shared memory so that all lanes work
@@ -396,6 +488,15 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
 
 using namespace sgn;
 
+static int g_march_mode = 0;   // 0: by ray count, 1: always the thread-per-ray brick walk, 2: always the warp-per-ray kernel
+
+extern "C" int sgn_query_march_mode(int mode)
+{
+    SGN_CHECK_ARG(mode >= 0 && mode <= 2, "sgn_query_march_mode: mode must be 0 (auto), 1 (brick walk) or 2 (warp per ray)");
+    g_march_mode = mode;
+    return SGN_OK;
+}
+
 extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* raydir, const float* t, int t_per_ray, int64_t R, int D,
                          int SR, int K, int kernel_size0, float radius2, const int32_t* ray_label, const int32_t* pt_label,
                          const int32_t* pt_label_prob_bits, uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w,
@@ -418,8 +519,13 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     g.knn_brick = G->knn_brick; g.knn_list = G->knn_list; g.nby = G->nby; g.nbz = G->nbz;
     g.occ_rank = G->occ_rank; g.nbr_off = G->nbr_off; g.nbr_ent = G->nbr_ent;
 
-    launch(march_kernel, cdiv(R, MARCH_THREADS), MARCH_THREADS, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
-                                                                sample_mask, semantic ? sample_label : nullptr, ray_mask);
+    // thread-per-ray brick walk for frames; warp-per-ray for small ray counts (its latency is ~10x lower when the GPU is not full)
+    if (g_march_mode == 1 || (g_march_mode == 0 && R >= MARCH_WARP_BELOW))
+        launch(march_kernel, cdiv(R, MARCH_THREADS), MARCH_THREADS, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
+                                                                    sample_mask, semantic ? sample_label : nullptr, ray_mask);
+    else
+        launch(march_warp_kernel, cdiv(R, MARCH_WARPS), MARCH_WARPS * 32, 0, st, g, campos, raydir, t, t_per_ray, R, D, SR, ray_label, sample_loc_w,
+                                                                            sample_mask, semantic ? sample_label : nullptr, ray_mask);
     const int nlayer = (kernel_size0 + 1) / 2;
     // rays per block: up to KNN_SLOTS sample slots (6 KB list), fewer for small ray counts (a training patch) so that the grid still
     // covers the 148 SMs several times over, but never fewer slots than the block has threads

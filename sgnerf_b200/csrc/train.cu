@@ -106,6 +106,72 @@ __global__ void adam_rows_kernel(float* __restrict__ param, float* __restrict__ 
     }
 }
 
+// The same for several tables that share their rows (the point tables: embedding [N,32], colour [N,3], dir [N,3], conf [N]) in ONE pass:
+// eight lanes per row, lane l owns the elements [4 l, 4 l + 4) of every table (16-byte accesses on the wide table: a warp covers four
+// consecutive rows = 512 contiguous bytes), the row is active when any element of any table has a non-zero gradient.
+constexpr int ADAM_MAX_TABLES = 8;
+struct AdamTables {
+    float* param[ADAM_MAX_TABLES]; float* grad[ADAM_MAX_TABLES]; float* m1[ADAM_MAX_TABLES]; float* m2[ADAM_MAX_TABLES];
+    int C[ADAM_MAX_TABLES];
+    int n;
+};
+
+__global__ void adam_rows_multi_kernel(AdamTables T, uint8_t* __restrict__ active, int64_t N, float lr, float b1, float b2, float eps,
+                                       const float* __restrict__ step, float grad_scale, int zero_grad)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gid >> 3;
+    const int l = (int)(gid & 7);
+    const unsigned group = 0xffu << (lane_id() & 24);
+    const bool inb = row < N;
+    bool nz = false;
+    float4 gv[ADAM_MAX_TABLES];
+#pragma unroll
+    for (int k = 0; k < ADAM_MAX_TABLES; k++) {
+        gv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < T.n && inb) {
+            const int C = T.C[k], e0 = 4 * l;
+            const float* g = T.grad[k] + row * C;
+            if (e0 + 4 <= C && (C & 3) == 0) gv[k] = *(const float4*)(g + e0);
+            else {
+                if (e0 < C) gv[k].x = g[e0];
+                if (e0 + 1 < C) gv[k].y = g[e0 + 1];
+                if (e0 + 2 < C) gv[k].z = g[e0 + 2];
+                if (e0 + 3 < C) gv[k].w = g[e0 + 3];
+            }
+            nz = nz || gv[k].x != 0.f || gv[k].y != 0.f || gv[k].z != 0.f || gv[k].w != 0.f;
+        }
+    }
+    const bool row_nz = (__ballot_sync(0xffffffffu, nz) & group) != 0u;
+    if (!inb) return;
+    if (active) {
+        if (row_nz) { if (l == 0) active[row] = 1; }
+        else if (!active[row]) return;
+    }
+    const float t = *step;
+    const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
+    const float step_size = lr / bc1;
+#pragma unroll
+    for (int k = 0; k < ADAM_MAX_TABLES; k++) {
+        if (k >= T.n) break;
+        const int C = T.C[k], e0 = 4 * l;
+        if (e0 >= C) continue;
+        float *p = T.param[k] + row * C, *a = T.m1[k] + row * C, *b = T.m2[k] + row * C, *g = T.grad[k] + row * C;
+        const float gg[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = e0 + i;
+            if (c >= C) break;
+            const float gc = gg[i] * grad_scale;
+            const float m = b1 * a[c] + (1.0f - b1) * gc;
+            const float v = b2 * b[c] + (1.0f - b2) * gc * gc;
+            a[c] = m; b[c] = v;
+            p[c] -= step_size * (m / (sqrtf(v) / bc2s + eps));
+            if (zero_grad && row_nz) g[c] = 0.f;
+        }
+    }
+}
+
 __global__ void step_increment_kernel(float* step) { *step += 1.0f; }
 
 }  // namespace sgn
@@ -159,6 +225,24 @@ extern "C" int sgn_adam_rows(float* param, float* grad, float* exp_avg, float* e
         launch(adam_rows_kernel<4>, cdiv(N, 128), 128, 0, st, param, grad, exp_avg, exp_avg_sq, active, N, C, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
     else
         launch(adam_rows_kernel<1>, cdiv(N, 128), 128, 0, st, param, grad, exp_avg, exp_avg_sq, active, N, C, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_adam_rows_multi(int n_tables, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                                   const int32_t* C, uint8_t* active, int64_t N, float lr, float beta1, float beta2, float eps, const float* step,
+                                   float grad_scale, int zero_grad, void* stream)
+{
+    SGN_CHECK_ARG(n_tables > 0 && n_tables <= ADAM_MAX_TABLES && params && grads && exp_avg && exp_avg_sq && C && step && N >= 0,
+                  "sgn_adam_rows_multi: bad argument (at most %d tables)", ADAM_MAX_TABLES);
+    AdamTables T = {};
+    T.n = n_tables;
+    for (int k = 0; k < n_tables; k++) {
+        SGN_CHECK_ARG(C[k] > 0 && C[k] <= 32 && params[k] && grads[k] && exp_avg[k] && exp_avg_sq[k], "sgn_adam_rows_multi: table %d: NULL or more than 32 columns", k);
+        T.param[k] = params[k]; T.grad[k] = grads[k]; T.m1[k] = exp_avg[k]; T.m2[k] = exp_avg_sq[k]; T.C[k] = C[k];
+    }
+    if (N == 0) return SGN_OK;
+    launch(adam_rows_multi_kernel, cdiv(N * 8, 256), 256, 0, (cudaStream_t)stream, T, active, N, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

@@ -461,6 +461,14 @@ def adam_rows(param, grad, exp_avg, exp_avg_sq, active, step, lr, betas=(0.9, 0.
               float(eps), _ptr(step), float(grad_scale), int(zero_grad), _stream())
 
 
+def adam_rows_multi(params, grads, exp_avgs, exp_avg_sqs, active, step, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, zero_grad=True):
+    """sgn_adam_rows_multi: several [N, C_k] tables that share their rows (the point tables) in one pass, one `active` flag per row."""
+    N = params[0].shape[0]
+    Cs = (C.c_int32 * len(params))(*[p.numel() // max(N, 1) for p in params])
+    _lib.call("sgn_adam_rows_multi", len(params), _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs), _ptr_array(exp_avg_sqs), Cs, _ptr(active), N,
+              float(lr), float(betas[0]), float(betas[1]), float(eps), _ptr(step), float(grad_scale), int(zero_grad), _stream())
+
+
 def adam_step_count(step):
     _lib.call("sgn_adam_step_count", _ptr(step), _stream())
 

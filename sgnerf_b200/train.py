@@ -107,13 +107,15 @@ class TrainStep(_StepBase):
         for t in self.params:
             t.requires_grad_(False)
         # one flat gradient bucket; every parameter's gradient accumulator is a slice of it
+        # (every slice starts on a 256-byte boundary: the kernels use 16-byte accesses on the table rows)
         sizes = [p.numel() for p in self.params]
-        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        self.grads, off = [], 0
-        for p, n in zip(self.params, sizes):
-            self.grads.append(self.flat_grad[off:off + n].view_as(p))
-            off += n
-        self.n_net = sum(p.numel() for p in self.net_params)
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 63) // 64 * 64
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = [self.flat_grad[o:o + n].view_as(p) for p, n, o in zip(self.params, sizes, offs)]
+        self.n_net = offs[len(self.net_params)]           # the MLP gradients occupy flat_grad[:n_net]
         nl = len(scene.weights)
         self.d_w, self.d_b = self.grads[:nl], self.grads[nl:2 * nl]
         self.pt_grads = dict(zip(self.pt_names, self.grads[2 * nl:]))
@@ -123,7 +125,7 @@ class TrainStep(_StepBase):
         self.optim = torch.optim.Adam([{"params": self.net_params, "lr": lr}], capturable=bool(use_graph), fused=True)
         self.pt_m = [torch.zeros_like(p) for p in self.pt_params]
         self.pt_v = [torch.zeros_like(p) for p in self.pt_params]
-        self.pt_active = [torch.zeros(p.shape[0], dtype=torch.uint8, device=dev) for p in self.pt_params]
+        self.pt_active = torch.zeros(scene.xyz.shape[0], dtype=torch.uint8, device=dev)     # rows that ever received a gradient
         self.pt_step = torch.zeros((), dtype=torch.float32, device=dev)
         self._cnt = torch.zeros((), dtype=torch.float32, device=dev)
 
@@ -154,8 +156,7 @@ class TrainStep(_StepBase):
             dist.all_reduce(self.flat_grad, group=self.group)          # in place, SUM: losses are normalised by the global hit count
         self.optim.step()
         ops.adam_step_count(self.pt_step)
-        for p, gr, m, v, act in zip(self.pt_params, self.grads[len(self.net_params):], self.pt_m, self.pt_v, self.pt_active):
-            ops.adam_rows(p, gr, m, v, act, self.pt_step, self.plr)
+        ops.adam_rows_multi(self.pt_params, self.grads[len(self.net_params):], self.pt_m, self.pt_v, self.pt_active, self.pt_step, self.plr)
 
 
 class AutogradTrainStep(_StepBase):

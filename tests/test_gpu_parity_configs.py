@@ -21,6 +21,15 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 2], ids=["brick-walk", "warp-per-ray"])
+def march_kernel_choice(request):
+    """Every query test runs with each of sgn_query's two march kernels forced (they must give identical results)."""
+    from sgnerf_b200 import _lib
+    _lib.call("sgn_query_march_mode", request.param)
+    yield
+    _lib.call("sgn_query_march_mode", 0)
+
+
 def _subset(s, n, seed=0):
     sel = np.sort(np.random.default_rng(seed).choice(s.raydir.shape[0], n, replace=False))
     sub = SimpleNamespace(**vars(s))

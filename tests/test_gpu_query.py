@@ -11,6 +11,15 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[1, 2], ids=["brick-walk", "warp-per-ray"])
+def march_kernel_choice(request):
+    """Every query test runs with each of sgn_query's two march kernels forced (they must give identical results)."""
+    from sgnerf_b200 import _lib
+    _lib.call("sgn_query_march_mode", request.param)
+    yield
+    _lib.call("sgn_query_march_mode", 0)
+
+
 @pytest.fixture(scope="module")
 def scene_c0():
     return synth.scene_c0(n_points=100_000, n_rays=1024)

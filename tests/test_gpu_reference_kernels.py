@@ -16,6 +16,15 @@ from sgnerf_b200 import synth
 from tests import ref_driver, util
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=[1, 2], ids=["brick-walk", "warp-per-ray"])
+def march_kernel_choice(request):
+    """Every query test runs with each of sgn_query's two march kernels forced (they must give identical results)."""
+    from sgnerf_b200 import _lib
+    _lib.call("sgn_query_march_mode", request.param)
+    yield
+    _lib.call("sgn_query_march_mode", 0)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

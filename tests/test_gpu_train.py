@@ -233,5 +233,36 @@ def test_direct_step_matches_the_autograd_step():
     for pa, pb in zip(a.params, b.params):
         assert float((pa.detach() - pb.detach()).abs().mean()) < 2e-4
     # rows no ray ever touched did not move and were never visited
-    emb_active = a.pt_active[0].bool()
+    emb_active = a.pt_active.bool()
     assert 0 < int(emb_active.sum()) < emb_active.numel()
+
+
+def test_adam_rows_multi_equals_dense_torch_adam():
+    """sgn_adam_rows_multi on the four point tables at once ([N,32], [N,3], [N,3], [N]) against torch.optim.Adam on the dense tables:
+    a row is updated when ANY table has (or ever had) a gradient in it; tables without a gradient in that row move by their moments
+    only, exactly as dense Adam moves them."""
+    g = torch.Generator().manual_seed(2)
+    N, Cs = 3001, [32, 3, 3, 1]
+    shapes = [(N, c) if c > 1 else (N,) for c in Cs]
+    p0 = [torch.randn(*s, generator=g) for s in shapes]
+    refs = [p.clone().requires_grad_(True) for p in p0]
+    opt = torch.optim.Adam(refs, lr=2e-3)
+    ps = [p.clone().cuda() for p in p0]
+    grads, ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    active = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    step = torch.zeros((), device="cuda")
+    for it in range(5):
+        for k, (s, c) in enumerate(zip(shapes, Cs)):
+            rows = torch.randperm(N, generator=g)[:150 + 40 * it + 10 * k]           # different rows per table
+            gd = torch.zeros(*s)
+            gd[rows] = torch.randn(*((rows.numel(), c) if c > 1 else (rows.numel(),)), generator=g)
+            refs[k].grad = gd.clone()
+            grads[k].copy_(gd.cuda())
+        opt.step()
+        ops.adam_step_count(step)
+        ops.adam_rows_multi(ps, grads, ms, vs, active, step, 2e-3)
+        assert all(float(x.abs().sum()) == 0.0 for x in grads)
+    for p, r in zip(ps, refs):
+        torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-5, atol=2e-6)
+    un = active.cpu() == 0
+    assert 0.1 < float(un.float().mean()) < 0.9 and all(torch.equal(p.cpu()[un], q[un]) for p, q in zip(ps, p0))
