@@ -58,8 +58,11 @@ constexpr int OFF_BAR = OFF_WRING + B_STAGES * PANEL_BH;        // 229376
 constexpr int N_BARS = 3 * B_STAGES + 8;
 constexpr int OFF_TMEMPTR = OFF_BAR + N_BARS * 8;
 constexpr int TC_SMEM = OFF_TMEMPTR + 16 + 1024;                // + slack for the 1024 B alignment of the base
-constexpr int TC_EPI_WARPS = 8, TC_GATHER_WARP0 = 8, TC_PRODUCER_WARP = 16, TC_MMA_WARP = 17, TC_THREADS = 20 * 32;   // warps 18, 19 idle (whole warpgroups for setmaxnreg)
-constexpr int REGS_EPI = 128, REGS_GATHER = 80, REGS_MISC = 64;      // 8*128 + 8*80 + 4*64 <= 20 * 96 (the launch allocation per warp-lane)
+// 16 epilogue warps (four per TMEM lane quadrant, one 64-column activation panel each) | 8 gather warps | producer, MMA issuer, 2 idle
+// (whole warpgroups for setmaxnreg).  The epilogue is bound by the latency of its TMEM loads and shared-memory stores, not by issue
+// slots: twice the warps on half the columns each halve the time a layer's epilogue takes, which is what the other slot's MMAs hide.
+constexpr int TC_EPI_WARPS = 16, TC_GATHER_WARP0 = 16, TC_PRODUCER_WARP = 24, TC_MMA_WARP = 25, TC_THREADS = 28 * 32;
+constexpr int REGS_EPI = 72, REGS_GATHER = 80, REGS_MISC = 56;       // 16*72 + 8*80 + 4*56 = 2016 = 28 * 72 (the launch allocation per warp-lane)
 static_assert(TC_SMEM <= 232448, "exceeds the 227 KB shared memory limit");
 
 enum { LAYER_FROM_X0 = 0, LAYER_FROM_ACT = 1, LAYER_FROM_ACT_E7 = 2 };
@@ -168,7 +171,23 @@ __device__ __forceinline__ void ldg256(const uint4* ptr, uint4& a, uint4& b)
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sts16(uint32_t addr, uint16_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }     // all epilogue warps
+// 16-column TMEM load of this warp's 32 lanes, and its wait (the destination registers are in/out operands of the wait so that no use
+// of them can be scheduled above it)
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld16(uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
 __device__ __forceinline__ uint4 lds128u(uint32_t addr)
 {
     uint4 v;
@@ -233,16 +252,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
     cluster_sync();                                                 // both CTAs' barriers are initialised before anyone arrives remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    // hand the registers to the warps that need them (whole warpgroups: epilogue 0-7, gather 8-15, producer / MMA / idle 16-19)
-    if (warp < TC_EPI_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
-    else if (warp < TC_PRODUCER_WARP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MISC));
+    // hand the registers to the warps that need them (whole warpgroups: epilogue 0-15 keep the launch allocation of 72, the four
+    // producer / MMA / idle warps 24-27 give theirs up first, then the gather warps 16-23 take 80)
+    if (warp >= TC_PRODUCER_WARP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_MISC));
+    else if (warp >= TC_GATHER_WARP0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_GATHER));
 
     if (warp < TC_EPI_WARPS) {
-        // =========================================================== EPILOGUE: warp = (column half h2, TMEM lane quadrant)
-        const int quad = warp & 3, h2 = warp >> 2;
+        // =========================================================== EPILOGUE: warp = (64-column panel q4, TMEM lane quadrant)
+        const int quad = warp & 3, q4 = warp >> 2;
         const int row = quad * 32 + lane;
-        const int et = tid;                                      // 0..255
+        const int et = tid;                                      // 0..511
         uint32_t ph_d = 0;
         const uint32_t lane_field = (uint32_t)(quad * 32) << 16;
         const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
@@ -269,7 +288,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     if (prof) pf_t0 = clock64();
-                    uint4 pa[4], pb[4];
                     mbar_wait(BAR(D_FULL + s), (ph_d >> s) & 1u); ph_d ^= 1u << s;
                     tc_fence_after();
                     if (prof) { const long long t1 = clock64(); pf_wait += t1 - pf_t0; pf_t0 = t1; }
@@ -285,78 +303,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     }
                     const float wcr = s == 0 ? wcr0 : wcr1;
                     const int slr = s == 0 ? slr0 : slr1;
-                    const uint32_t acc_addr = tmem_base + (uint32_t)(s * TC_W + h2 * 128) + lane_field;
-                    const uint32_t act_row = slot_base + (h2 * 2) * PANEL_A + row * 128;
-                    // one 32-column chunk: (bias is part of the GEMM) LeakyReLU in bf16 -> this row's 64 bytes of panel h2*2 + c/2
-                    auto chunk = [&](int c, const uint32_t(&vv)[32]) {
-                        if (kDbg && (p.dbg & 8)) return;
-                        const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int ch = (c & 1) * 4 + q;
-                            sts128(rowbase + ((ch ^ (row & 7)) << 4), leaky_pack(vv[8 * q], vv[8 * q + 1], slope2), leaky_pack(vv[8 * q + 2], vv[8 * q + 3], slope2),
-                                   leaky_pack(vv[8 * q + 4], vv[8 * q + 5], slope2), leaky_pack(vv[8 * q + 6], vv[8 * q + 7], slope2));
-                        }
-                    };
-                    uint32_t v0[32], v1[32];
+                    // this warp's 64 accumulator columns = activation panel q4, this thread's row of it (128 bytes)
+                    const uint32_t acc_addr = tmem_base + (uint32_t)(s * TC_W + q4 * 64) + lane_field;
+                    const uint32_t act_row = slot_base + q4 * PANEL_A + row * 128;
+                    uint32_t v0[16], v1[16];
                     if (p.padd[l]) {
-                        // this row's 128 columns of the layer's point table (bf16), fetched two 32-column chunks ahead of their use
-                        const uint4* p0row = (const uint4*)(p.padd[l] + (size_t)(s == 0 ? pt0 : pt1) * (TC_W * 2)) + h2 * 16;
+                        // the layer's point table (bf16 [N][256]) is added to the accumulator before the activation: this row's 64 columns
+                        // = 128 bytes, fetched in two halves, each ahead of its use; x = acc + P0 in fp32, then LeakyReLU in bf16
+                        const uint4* p0row = (const uint4*)(p.padd[l] + (size_t)(s == 0 ? pt0 : pt1) * (TC_W * 2)) + q4 * 8;
+                        uint4 pa[4];
+                        ldg256(p0row, pa[0], pa[1]); ldg256(p0row + 2, pa[2], pa[3]);
+                        auto chunk0 = [&](int c, const uint32_t(&vv)[16], const uint4& pq0, const uint4& pq1) {
 #pragma unroll
-                        for (int q = 0; q < 4; q += 2) { ldg256(p0row + q, pa[q], pa[q + 1]); ldg256(p0row + 4 + q, pb[q], pb[q + 1]); }
-                        // add the point part (bf16) to the accumulator before the activation
-                        // x = acc + P0 in fp32 (P0 unpacked from bf16), then LeakyReLU in bf16 as in the other layers
-                        auto chunk0 = [&](int c, const uint32_t(&vv)[32], const uint4(&pq)[4]) {
-                            const uint32_t rowbase = act_row + (c >> 1) * PANEL_A;
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const uint32_t w[4] = {pq[q].x, pq[q].y, pq[q].z, pq[q].w};
+                            for (int q = 0; q < 2; q++) {
+                                const uint4 pq = q == 0 ? pq0 : pq1;
+                                const uint32_t w[4] = {pq.x, pq.y, pq.z, pq.w};
                                 uint32_t o[4];
 #pragma unroll
                                 for (int e = 0; e < 4; e++)
                                     o[e] = leaky_pack(__float_as_uint(__uint_as_float(vv[8 * q + 2 * e]) + __uint_as_float(w[e] << 16)),
                                                       __float_as_uint(__uint_as_float(vv[8 * q + 2 * e + 1]) + __uint_as_float(w[e] & 0xffff0000u)), slope2);
-                                const int ch = (c & 1) * 4 + q;
-                                sts128(rowbase + ((ch ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+                                sts128(act_row + (((2 * c + q) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
                             }
                         };
-                        tc_ld32_nowait(acc_addr, v0);
-#pragma unroll 1
-                        for (int cp = 0; cp < 2; cp++) {
-                            tc_wait_ld(v0);
-                            tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                            chunk0(2 * cp, v0, pa);
-                            if (cp == 0) {
-#pragma unroll
-                                for (int q = 0; q < 4; q += 2) ldg256(p0row + 8 + q, pa[q], pa[q + 1]);
-                            }
-                            tc_wait_ld(v1);
-                            if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
-                            chunk0(2 * cp + 1, v1, pb);
-                            if (cp == 0) {
-#pragma unroll
-                                for (int q = 0; q < 4; q += 2) ldg256(p0row + 12 + q, pb[q], pb[q + 1]);
-                            }
-                        }
+                        tc_ld16_nowait(acc_addr, v0);
+                        tc_wait_ld16(v0);
+                        tc_ld16_nowait(acc_addr + 16u, v1);
+                        chunk0(0, v0, pa[0], pa[1]);
+                        tc_wait_ld16(v1);
+                        tc_ld16_nowait(acc_addr + 32u, v0);
+                        chunk0(1, v1, pa[2], pa[3]);
+                        ldg256(p0row + 4, pa[0], pa[1]); ldg256(p0row + 6, pa[2], pa[3]);
+                        tc_wait_ld16(v0);
+                        tc_ld16_nowait(acc_addr + 48u, v1);
+                        chunk0(2, v0, pa[0], pa[1]);
+                        tc_wait_ld16(v1);
+                        chunk0(3, v1, pa[2], pa[3]);
                     } else {
-                        tc_ld32_nowait(acc_addr, v0);
-#pragma unroll 1
-                        for (int cp = 0; cp < 2; cp++) {
-                            tc_wait_ld(v0);
-                            tc_ld32_nowait(acc_addr + (uint32_t)(cp * 64 + 32), v1);
-                            chunk(2 * cp, v0);
-                            tc_wait_ld(v1);
-                            if (cp == 0) tc_ld32_nowait(acc_addr + 64u, v0);
-                            chunk(2 * cp + 1, v1);
-                        }
+                        // one 16-column chunk: (bias is part of the GEMM) LeakyReLU in bf16 -> 32 bytes of this row
+                        auto chunk = [&](int c, const uint32_t(&vv)[16]) {
+                            if (kDbg && (p.dbg & 8)) return;
+#pragma unroll
+                            for (int q = 0; q < 2; q++)
+                                sts128(act_row + (((2 * c + q) ^ (row & 7)) << 4), leaky_pack(vv[8 * q], vv[8 * q + 1], slope2),
+                                       leaky_pack(vv[8 * q + 2], vv[8 * q + 3], slope2), leaky_pack(vv[8 * q + 4], vv[8 * q + 5], slope2),
+                                       leaky_pack(vv[8 * q + 6], vv[8 * q + 7], slope2));
+                        };
+                        tc_ld16_nowait(acc_addr, v0);
+                        tc_wait_ld16(v0);
+                        tc_ld16_nowait(acc_addr + 16u, v1);
+                        chunk(0, v0);
+                        tc_wait_ld16(v1);
+                        tc_ld16_nowait(acc_addr + 32u, v0);
+                        chunk(1, v1);
+                        tc_wait_ld16(v0);
+                        tc_ld16_nowait(acc_addr + 48u, v1);
+                        chunk(2, v0);
+                        tc_wait_ld16(v1);
+                        chunk(3, v1);
                     }
                     if (last) {
                         // H is in the panels; selection matrix of K-sum pass 0 next to it: Sel[sample slot][row] = w*conf (bf16)
                         const uint32_t sel_base = slot_base + 4 * PANEL_A;
-                        const uint32_t z = sel_base + et * 64;
-                        sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
+                        const uint32_t z = sel_base + et * 32;
+                        sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u);
                         epi_bar();
-                        if (h2 == 0 && slr >= 0 && slr < KS_SLOTS) {
+                        if (q4 == 0 && slr >= 0 && slr < KS_SLOTS) {
                             const __nv_bfloat16 wb = __float2bfloat16_rn(wcr);
                             sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + slr * 128 + ((((row & 63) >> 3) ^ (slr & 7)) << 4) + (row & 7) * 2,
                                   *reinterpret_cast<const uint16_t*>(&wb));
@@ -366,18 +378,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     if (prof) { const long long t1 = clock64(); if (last) pf_last += t1 - pf_t0; else pf_mid += t1 - pf_t0; pf_t0 = t1; }
                 }
             }
-            // ---- alpha / sigma, and the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F image
+            // ---- alpha / sigma, and the K-sums: F^T[feature = TMEM lane][sample slot = column] -> F image.  Warp (q4, quad): feature half
+            // h2 = q4 >> 1, features h2*128 + quad*32 + lane, and the 32-column half jh = q4 & 1 of this CTA's (up to) 56 sample slots
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const int npass = s == 0 ? npass0 : npass1, nslots = s == 0 ? nslots0 : nslots1, c0 = s == 0 ? c00 : c01, slr = s == 0 ? slr0 : slr1;
                 const float wcr = s == 0 ? wcr0 : wcr1;
+                const int h2 = q4 >> 1, jh = q4 & 1;
                 const int f = h2 * 128 + quad * 32 + lane;
                 const uint32_t sel_base = sbase + OFF_SLOT0 + s * SLOT_BYTES + 4 * PANEL_A;
                 for (int pass = 0; pass < npass; pass++) {
                     if (prof) pf_t0 = clock64();
                     mbar_wait(BAR(D_FULL + s), (ph_d >> s) & 1u); ph_d ^= 1u << s;
                     tc_fence_after();
-                    if (pass == 0 && h2 == 0) {                                            // warp-uniform: the TMEM load is .sync.aligned
+                    if (pass == 0 && q4 == 0) {                                            // warp-uniform: the TMEM load is .sync.aligned
                         // this tuple's term of sigma = sum_k w*conf*act(alpha_k); alpha came out of the alpha_branch MMA, the colour
                         // kernel adds up the (consecutive) terms of a sample
                         const float a = __uint_as_float(tc_ld1(tmem_base + (uint32_t)(s * TC_W + ALPHA_COL) + lane_field)) + ba;
@@ -388,30 +402,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
                     const int cbase = c0 + pass * KS_SLOTS;                                 // first padded sample index of the pass (multiple of 8)
                     // this CTA's samples are columns [rank*56, rank*56+56) of each feature half's [128 x 112] block
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * TC_W + h2 * KS_N + rank * KS_SLOTS) + lane_field;
-#pragma unroll 1
-                    for (int j = 0; j < 2; j++) {
-                        if (32 * j >= ns8) break;
-                        uint32_t v[32];
-                        tc_ld32(d_addr + 32 * j, v);                                  // j = 1 reads 8 columns past the 56 (in bounds, unused)
-                        if (!(kDbg && (p.dbg & 16))) {
+                    if (32 * jh < ns8) {                                                    // (warp-uniform)
 #pragma unroll
-                            for (int g = 0; g < 4; g++)
-                                if (32 * j + 8 * g < ns8) {
-                                    const uint4 o = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
-                                                               pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                                                               pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                                                               pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                                    *(uint4*)(p.F + f_image_off8(cbase + 32 * j + 8 * g, f)) = o;
-                                }
+                        for (int hh = 0; hh < 2; hh++) {
+                            if (32 * jh + 16 * hh >= ns8) break;
+                            uint32_t v[16];
+                            tc_ld16_nowait(d_addr + 32 * jh + 16 * hh, v);               // jh = 1, hh = 1 reads 8 columns past the 56 (in bounds, unused)
+                            tc_wait_ld16(v);
+                            if (!(kDbg && (p.dbg & 16))) {
+#pragma unroll
+                                for (int g = 0; g < 2; g++)
+                                    if (32 * jh + 16 * hh + 8 * g < ns8) {
+                                        const uint4 o = make_uint4(pack_bf16(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                                                                   pack_bf16(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                                                   pack_bf16(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                                                   pack_bf16(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                                        *(uint4*)(p.F + f_image_off8(cbase + 32 * jh + 16 * hh + 8 * g, f)) = o;
+                                    }
+                            }
                         }
                     }
                     if (pass + 1 < npass) {
                         // next 56 sample slots: rebuild Sel (the MMA of this pass has completed, nobody reads it now)
-                        const uint32_t z = sel_base + et * 64;
-                        sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u); sts128(z + 32, 0u, 0u, 0u, 0u); sts128(z + 48, 0u, 0u, 0u, 0u);
+                        const uint32_t z = sel_base + et * 32;
+                        sts128(z, 0u, 0u, 0u, 0u); sts128(z + 16, 0u, 0u, 0u, 0u);
                         epi_bar();
                         const int n = slr - (pass + 1) * KS_SLOTS;
-                        if (h2 == 0 && n >= 0 && n < KS_SLOTS) {
+                        if (q4 == 0 && n >= 0 && n < KS_SLOTS) {
                             const __nv_bfloat16 wb = __float2bfloat16_rn(wcr);
                             sts16(sel_base + (row >> 6) * (KS_SLOTS * 128) + n * 128 + ((((row & 63) >> 3) ^ (n & 7)) << 4) + (row & 7) * 2,
                                   *reinterpret_cast<const uint16_t*>(&wb));

@@ -297,7 +297,7 @@ render_composite_kernel(const float4* __restrict__ decoded, const float* __restr
     }
 }
 
-// The same frame tail with one THREAD per ray (SR <= 64): the warp-per-ray kernel above spends ~320 warp instructions per ray on its
+// The same frame tail with one THREAD per ray (SR <= 40): the warp-per-ray kernel above spends ~320 warp instructions per ray on its
 // scans and reductions (it is bound by instruction issue at 0.12 ms per 640x480 frame); a thread that walks its ray's samples in order
 // needs ~25 instructions per sample.  A block owns 128 consecutive rays and stages their rows through shared memory with coalesced
 // accesses: camera depth + validity of all samples, the decoded (sigma, r, g, b) rows eight samples at a time (only the samples that
@@ -526,7 +526,7 @@ static int render_composite_impl(const float* decoded, const float* zsrc, int zs
     SGN_CHECK_ARG(decoded && zsrc && ray_valid, "sgn_render_composite: NULL input");
     if (R == 0) return SGN_OK;
     auto st = (cudaStream_t)stream;
-    if (SR <= 64) {
+    if (SR <= 40) {                                        // its shared memory stays under the 48 KB a kernel gets without opting in
         const size_t sm = sizeof(float4) * ROWS_RAYS * (ROWS_CHUNK + 1) + sizeof(float) * ROWS_RAYS * (SR + 1) + (size_t)ROWS_RAYS * SR;
         if (blend == 0)
             launch(render_composite_rows_kernel<0>, cdiv(R, ROWS_RAYS), ROWS_RAYS, sm, st, (const float4*)decoded, zsrc, zstride, ray_valid, ray_mask,

@@ -116,7 +116,7 @@ def test_full_size_properties():
 def test_fused_frame_tail_equals_three_kernels(R, SR, blend):
     """sgn_render_composite (ray_dist + composite + fill_invalid in one pass) against the three kernels: the same step sizes and opacities
     bit for bit; colour and background transmittance to rounding (the fused kernel multiplies the transmittance in sample order for
-    SR <= 64, the separate kernel by a warp scan)."""
+    SR <= 40, the separate kernel by a warp scan)."""
     g = torch.Generator(device="cuda").manual_seed(4)
     dec = torch.rand(R, SR, 4, device="cuda", generator=g)
     dec[..., 0] *= 80.0
