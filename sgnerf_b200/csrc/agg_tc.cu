@@ -709,7 +709,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) agg_t
 // swizzled panel image, so four bulk copies (TMA) per tile bring them into a 2-stage ring (the next tile is prefetched into
 // L2 meanwhile); the fifth panel, the view-direction encoding, is computed by the loader warps.  The 128-wide activations live in place in two panels; the last Linear (128 -> 3), the
 // sigmoid and the (sigma, r, g, b) store are fused into the last epilogue.
-//   warps 0-7 epilogue (two column halves) | warps 8-11 loaders | warp 12 MMA issuer (and the one-off weight load)
+//   warps 0-15 epilogue (four column quarters x four TMEM lane quadrants) | warps 16-19 loaders | warp 20 MMA issuer (and the one-off weight load)
 constexpr int CW = 128;                                   // colour hidden width
 constexpr int C_PANEL = CW * 128;                         // 16 KB: 128 rows x 64 bf16 (A and B panels alike)
 constexpr int C_K0_PANELS = 5, C_RING = 2, C_MAX_HIDDEN = 3;
@@ -719,10 +719,12 @@ constexpr int COFF_RING = COFF_W + C_W_PANELS * C_PANEL;
 constexpr int COFF_ACT = COFF_RING + C_RING * C_PANEL;
 constexpr int COFF_BIAS = COFF_ACT + 2 * C_PANEL;                           // [3][128] hidden biases
 constexpr int COFF_WL = COFF_BIAS + C_MAX_HIDDEN * CW * 4;                  // [3][128] last Linear + its bias [4]
-constexpr int COFF_PART = COFF_WL + 3 * CW * 4 + 16;                        // [128][4] rgb partial sums of the upper column half
-constexpr int COFF_BAR = COFF_PART + TC_ROWS * 16;
-constexpr int C_MMA_WARP = 12, C_THREADS = 13 * 32;                          // warps 0-7 epilogue | 8-11 loaders | 12 MMA issuer
-constexpr int C_NBARS = 1 + 2 * C_RING + 2 + 4;
+constexpr int COFF_PART = COFF_WL + 3 * CW * 4 + 16;                        // [3 upper column quarters][128][4] rgb partial sums
+constexpr int COFF_SIG = COFF_PART + 3 * TC_ROWS * 16;                      // [2 tile parities][128] {sample index, sigma}: gathered by the loader warps
+constexpr int COFF_BAR = COFF_SIG + 2 * TC_ROWS * 8;
+constexpr int C_EPI_WARPS = 16, C_LOADER_WARP0 = 16, C_MMA_WARP = 20, C_THREADS = 21 * 32;   // warps 0-15 epilogue | 16-19 loaders | 20 MMA issuer
+constexpr int C_STAGES = 4;                                // first-layer operand stages: the two activation panels, then the two ring panels
+constexpr int C_NBARS = 1 + 2 * C_STAGES + 2 + 4;
 constexpr int COFF_TMEMPTR = COFF_BAR + C_NBARS * 8;
 constexpr int C_SMEM = COFF_TMEMPTR + 16 + 1024;
 static_assert(C_SMEM <= 232448, "colour kernel exceeds the 227 KB shared memory limit");
@@ -750,15 +752,35 @@ struct ColParams {
     int dbg;
 };
 
+// SGN_TC_DEBUG & 4096: a wait that gives up after ~2 s, says where it was and traps (deadlock diagnosis)
+__device__ __noinline__ void mbar_wait_or_report(uint32_t bar, uint32_t parity, int tag, int tile, int extra)
+{
+    for (int it = 0; it < 2000; it++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (ok) return;
+    }
+    printf("STUCK block %d thread %d tag %d tile %d extra %d parity %u\n", blockIdx.x, threadIdx.x, tag, tile, extra, parity);
+    __trap();
+}
+
 __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid_constant__ ColParams p)
 {
+#define CWAIT(tag, bar, par) do { if (p.dbg & 4096) mbar_wait_or_report(bar, par, tag, (int)blockIdx.x, 0); else mbar_wait(bar, par); } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = sbase + COFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * i; };
-    const int W_FULL = 0, R_FULL = 1, R_EMPTY = R_FULL + C_RING, A_FULL = R_EMPTY + C_RING, D_FULL = A_FULL + 2, D_EMPTY = D_FULL + 2;
+    const int W_FULL = 0, R_FULL = 1, R_EMPTY = R_FULL + C_STAGES, A_FULL = R_EMPTY + C_STAGES, D_FULL = A_FULL + 2, D_EMPTY = D_FULL + 2;
+    // The five first-layer operand panels of a tile (four F panels + the view-direction panel) go through FOUR stages: the tile's two
+    // activation panels (free from the moment the previous tile's last layer has been multiplied until this tile's first epilogue
+    // writes them) and the two ring panels, the first ring panel a second time for the view directions.  All four F panels of a tile
+    // can therefore be in flight before its first MMA is due (with a two-stage ring the issuer waited ~2500 cycles per tile for them).
+    auto stage_of = [](int kp) { return kp < 4 ? kp : 2; };
+    auto stage_addr = [&](int st) { return sbase + (uint32_t)(st < 2 ? COFF_ACT + st * C_PANEL : COFF_RING + (st - 2) * C_PANEL); };
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + COFF_TMEMPTR);
     float* s_bias = (float*)(smem + COFF_BIAS);
     float* s_wl = (float*)(smem + COFF_WL);
@@ -769,8 +791,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
 
     if (tid == 0) {
         mbar_init(BAR(W_FULL), 1);
-        for (int s = 0; s < C_RING; s++) { mbar_init(BAR(R_FULL + s), 1); mbar_init(BAR(R_EMPTY + s), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(BAR(A_FULL + i), 128); mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), 256); }
+        for (int s = 0; s < C_STAGES; s++) { mbar_init(BAR(R_FULL + s), 1); mbar_init(BAR(R_EMPTY + s), 1); }
+        // one arrival per WARP (its lanes fence, synchronise, lane 0 arrives): hundreds of per-thread arrivals on one barrier serialise
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(A_FULL + i), C_EPI_WARPS / 2); mbar_init(BAR(D_FULL + i), 1); mbar_init(BAR(D_EMPTY + i), C_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < p.n_hidden * CW; i += blockDim.x) s_bias[i] = p.bias[i / CW][i % CW];
@@ -785,103 +808,129 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp < 8) {
-        // =========================================================== EPILOGUE: warp = (column half, TMEM lane quadrant); half h owns
-        // columns [64h, 64h+64) = activation panel h
-        const int quad = warp & 3, half = warp >> 2;
+    if (warp < C_EPI_WARPS) {
+        // =========================================================== EPILOGUE: warp = (column quarter cq, TMEM lane quadrant): 32 accumulator
+        // columns = half of activation panel cq / 2.  Sixteen warps: the per-layer chain TMEM -> registers -> bias, LeakyReLU -> shared
+        // memory is what the issuer waits for between the layers of a tile; four warps per scheduler hide each other's latencies.
+        const int quad = warp & 3, cq = warp >> 2;
         const int row = quad * 32 + lane;
-        float* s_part = (float*)(smem + COFF_PART);            // [128][4] partial rgb sums of the upper column half
+        float* s_part = (float*)(smem + COFF_PART);            // [3][128][4] partial rgb sums of column quarters 1..3
         uint32_t ph_dfull[2] = {0, 0};
-        uint32_t lcount = 0;
+        uint32_t lcount = 0, tcnt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t c = (int64_t)tile * TC_ROWS + row;
-            // per-sample scalars first: their dependent loads run while the tensor pipe works on the first layer
-            const int sidx = (half == 0 && c < Sv && !(p.dbg & 256)) ? p.csample[c] : -1;
-            float sg = 0.f;
-            if (sidx >= 0) {
-                const int j0 = p.tuple_start[sidx], nv = p.nvalid[sidx];
-                for (int q = 0; q < nv; q++) sg += p.sigrow[j0 + q];
-            }
+            // (the sample index and sigma of this row come from the loader warps through shared memory: their chain of dependent global
+            // loads -- compact sample -> first tuple, count -> the tuples' sigma terms -- must not sit in front of the first epilogue)
+            const int2* s_sig = (const int2*)(smem + COFF_SIG) + (tcnt & 1) * TC_ROWS;
+            tcnt++;
             for (int l = 0; l < p.n_hidden; l++, lcount++) {
                 const int db = lcount & 1;
                 const bool last = (l == p.n_hidden - 1);
-                mbar_wait(BAR(D_FULL + db), ph_dfull[db]);
+                CWAIT(1, BAR(D_FULL + db), ph_dfull[db]);
                 ph_dfull[db] ^= 1;
                 tc_fence_after();
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-                for (int ch = 2 * half; ch < 2 * half + 2; ch++) {
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + (uint32_t)(db * CW + ch * 32) + ((uint32_t)(quad * 32) << 16), v);
-                    float h[32];
+                // the accumulator is handed back to the issuer as soon as this warp's columns are in registers, before the activation math
+                uint32_t v[32];
+                tc_ld32_nowait(tmem_base + (uint32_t)(db * CW + cq * 32) + ((uint32_t)(quad * 32) << 16), v);
+                tc_wait_ld(v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(D_EMPTY + db));
+                float h[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bb = *(const float4*)(s_bias + l * CW + cq * 32 + i);
+                    float x0 = __uint_as_float(v[i]) + bb.x, x1 = __uint_as_float(v[i + 1]) + bb.y;
+                    float x2 = __uint_as_float(v[i + 2]) + bb.z, x3 = __uint_as_float(v[i + 3]) + bb.w;
+                    h[i] = fmaxf(x0, x0 * p.slope); h[i + 1] = fmaxf(x1, x1 * p.slope);
+                    h[i + 2] = fmaxf(x2, x2 * p.slope); h[i + 3] = fmaxf(x3, x3 * p.slope);
+                }
+                if (!last) {
+                    const uint32_t rowbase = sbase + COFF_ACT + (cq >> 1) * C_PANEL + row * 128;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int k = (cq & 1) * 4 + q;
+                        sts128(rowbase + ((k ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                               pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(A_FULL + (cq >> 1)));     // 2 quarters x 4 lane quadrants = 8 warps arrive per panel
+                } else {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 bb = *(const float4*)(s_bias + l * CW + ch * 32 + i);
-                        float x0 = __uint_as_float(v[i]) + bb.x, x1 = __uint_as_float(v[i + 1]) + bb.y;
-                        float x2 = __uint_as_float(v[i + 2]) + bb.z, x3 = __uint_as_float(v[i + 3]) + bb.w;
-                        h[i] = fmaxf(x0, x0 * p.slope); h[i + 1] = fmaxf(x1, x1 * p.slope);
-                        h[i + 2] = fmaxf(x2, x2 * p.slope); h[i + 3] = fmaxf(x3, x3 * p.slope);
+                        const float4 w0 = *(const float4*)(s_wl + cq * 32 + i);
+                        const float4 w1 = *(const float4*)(s_wl + CW + cq * 32 + i);
+                        const float4 w2 = *(const float4*)(s_wl + 2 * CW + cq * 32 + i);
+                        o0 = fmaf(h[i], w0.x, o0); o0 = fmaf(h[i + 1], w0.y, o0); o0 = fmaf(h[i + 2], w0.z, o0); o0 = fmaf(h[i + 3], w0.w, o0);
+                        o1 = fmaf(h[i], w1.x, o1); o1 = fmaf(h[i + 1], w1.y, o1); o1 = fmaf(h[i + 2], w1.z, o1); o1 = fmaf(h[i + 3], w1.w, o1);
+                        o2 = fmaf(h[i], w2.x, o2); o2 = fmaf(h[i + 1], w2.y, o2); o2 = fmaf(h[i + 2], w2.z, o2); o2 = fmaf(h[i + 3], w2.w, o2);
                     }
-                    if (!last) {
-                        const uint32_t rowbase = sbase + COFF_ACT + (ch >> 1) * C_PANEL + row * 128;
+                    // the four column quarters of a row meet in shared memory
+                    if (cq > 0) { float* d = s_part + ((cq - 1) * TC_ROWS + row) * 4; d[0] = o0; d[1] = o1; d[2] = o2; }
+                    asm volatile("bar.sync 2, 512;" ::: "memory");
+                    if (cq == 0) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int k = (ch & 1) * 4 + q;
-                            sts128(rowbase + ((k ^ (row & 7)) << 4), pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
-                                   pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
-                        }
-                        if (ch & 1) {
-                            fence_proxy_async();
-                            mbar_arrive(BAR(A_FULL + (ch >> 1)));
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 w0 = *(const float4*)(s_wl + ch * 32 + i);
-                            const float4 w1 = *(const float4*)(s_wl + CW + ch * 32 + i);
-                            const float4 w2 = *(const float4*)(s_wl + 2 * CW + ch * 32 + i);
-                            o0 = fmaf(h[i], w0.x, o0); o0 = fmaf(h[i + 1], w0.y, o0); o0 = fmaf(h[i + 2], w0.z, o0); o0 = fmaf(h[i + 3], w0.w, o0);
-                            o1 = fmaf(h[i], w1.x, o1); o1 = fmaf(h[i + 1], w1.y, o1); o1 = fmaf(h[i + 2], w1.z, o1); o1 = fmaf(h[i + 3], w1.w, o1);
-                            o2 = fmaf(h[i], w2.x, o2); o2 = fmaf(h[i + 1], w2.y, o2); o2 = fmaf(h[i + 2], w2.z, o2); o2 = fmaf(h[i + 3], w2.w, o2);
-                        }
+                        for (int qq = 0; qq < 3; qq++) { const float* d = s_part + (qq * TC_ROWS + row) * 4; o0 += d[0]; o1 += d[1]; o2 += d[2]; }
                     }
-                }
-                tc_fence_before();
-                mbar_arrive(BAR(D_EMPTY + db));
-                if (last) {
-                    // the two column halves of a row meet in shared memory
-                    if (half == 1) { s_part[4 * row] = o0; s_part[4 * row + 1] = o1; s_part[4 * row + 2] = o2; }
-                    asm volatile("bar.sync 2, 256;" ::: "memory");
-                    if (half == 0) { o0 += s_part[4 * row]; o1 += s_part[4 * row + 1]; o2 += s_part[4 * row + 2]; }
-                    asm volatile("bar.sync 2, 256;" ::: "memory");
-                }
-                if (last && half == 0 && sidx >= 0) {
-                    const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
-                                s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
-                    const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
-                    ((float4*)p.decoded)[sidx] = make_float4(sg, s0 * m - o, s1 * m - o, s2 * m - o);
+                    asm volatile("bar.sync 2, 512;" ::: "memory");
+                    const int2 ss = cq == 0 ? s_sig[row] : make_int2(-1, 0);
+                    const int sidx = ss.x;
+                    const float sg = __int_as_float(ss.y);
+                    if (cq == 0 && sidx >= 0) {
+                        const float s0 = 1.0f / (1.0f + __expf(-(o0 + s_wl[3 * CW]))), s1 = 1.0f / (1.0f + __expf(-(o1 + s_wl[3 * CW + 1]))),
+                                    s2 = 1.0f / (1.0f + __expf(-(o2 + s_wl[3 * CW + 2])));
+                        const float m = p.act_super ? 1.002f : 1.0f, o = p.act_super ? 0.001f : 0.0f;
+                        ((float4*)p.decoded)[sidx] = make_float4(sg, s0 * m - o, s1 * m - o, s2 * m - o);
+                    }
                 }
             }
         }
     } else if (warp < C_MMA_WARP) {
         // =========================================================== LOADERS: F panels by bulk copy, view-direction panel computed
-        const int lt = tid - 256;
-        uint32_t ph_empty[C_RING];
-        for (int s = 0; s < C_RING; s++) ph_empty[s] = 1;
-        uint32_t n = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t c0 = (int64_t)tile * TC_ROWS;
+        const int lt = tid - C_LOADER_WARP0 * 32;
+        uint32_t ph_empty[C_STAGES];
+        for (int s = 0; s < C_STAGES; s++) ph_empty[s] = 1;
+        uint32_t ltile = 0;
+        // This row's view-direction encoding (32 bf16 of its ray, cols [6 fv, 32) = 0), sample index and sigma (= sum of its tuples' terms:
+        // agg_tuple_tc_kernel stored w * conf * act(alpha) per tuple) are gathered here, by the loader warps, after the tile's F panels have
+        // been requested: the chain of dependent global loads (compact sample -> ray / first tuple, count -> terms) must not sit in front
+        // of the epilogue warps' first layer (it did: the issuer waited ~5000 cycles per tile for activations).
+        const int r = lt;
+        uint4 v0, v1, v2, v3;
+        int sidx_r;
+        float sg;
+        auto gather = [&](int tile) {
+            v0 = make_uint4(0u, 0u, 0u, 0u); v1 = v0; v2 = v0; v3 = v0;
+            sg = 0.f;
+            const int64_t c = (int64_t)tile * TC_ROWS + r;
+            sidx_r = (tile < ntiles && c < Sv && !(p.dbg & 64)) ? p.csample[c] : -1;
+            if (sidx_r >= 0) {
+                const uint4* src = (const uint4*)(p.vtab + (size_t)(sidx_r / p.SR) * 64);
+                v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2); v3 = __ldg(src + 3);
+                const int j0 = p.tuple_start[sidx_r], nv = p.nvalid[sidx_r];
+                for (int q = 0; q < nv; q++) sg += p.sigrow[j0 + q];
+            }
+        };
+        // SGN_TC_DEBUG & 1024 gathers one tile AHEAD instead (hides the latency completely, 8.8k instead of 11k cycles per tile) -- it
+        // deadlocks after a few launches for a reason not yet found, so the default gathers in place
+        const bool ahead = (p.dbg & 1024) != 0;
+        if (ahead) gather(blockIdx.x);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ltile++) {
             if (lt == 0 && tile + (int)gridDim.x < ntiles) {
                 const uint8_t* nxt = p.F + (size_t)(tile + gridDim.x) * F_TILE_BYTES;
                 for (int i = 0; i < 4; i++)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + i * C_PANEL), "r"((uint32_t)C_PANEL) : "memory");
             }
-            for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
-                const int s = n % C_RING;
-                const uint32_t base = sbase + COFF_RING + s * C_PANEL;
+            // load order: the ring panels first (free since the previous tile's first layer: F2, F3 travel during its later layers), then
+            // the activation panels (free once its last layer has been multiplied), then the view-direction panel
+            for (int oi = 0; oi < C_K0_PANELS; oi++) {
+                const int kp = oi < 2 ? oi + 2 : (oi < 4 ? oi - 2 : 4);
+                const int s = stage_of(kp);
+                const uint32_t base = stage_addr(s);
                 if (kp < 4) {
                     // every loader thread follows every phase of the stage (a parity wait is only unambiguous one phase ahead)
-                    mbar_wait(BAR(R_EMPTY + s), ph_empty[s]);
+                    CWAIT(2, BAR(R_EMPTY + s), ph_empty[s]);
                     if (lt == 0) {
                         if (p.dbg & 128) mbar_arrive(BAR(R_FULL + s));
                         else {
@@ -891,47 +940,51 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
                     }
                     ph_empty[s] ^= 1;
                 } else {
-                    // view-direction encoding of the sample's ray: 32 bf16 (cols [6 fv, 32) = 0) precomputed per ray
-                    const int r = lt;
-                    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0, v3 = v0;
-                    const int sidx_r = (c0 + r < Sv && !(p.dbg & 64)) ? p.csample[c0 + r] : -1;
-                    if (sidx_r >= 0) {
-                        const uint4* src = (const uint4*)(p.vtab + (size_t)(sidx_r / p.SR) * 64);
-                        v0 = __ldg(src); v1 = __ldg(src + 1); v2 = __ldg(src + 2); v3 = __ldg(src + 3);
-                    }
-                    mbar_wait(BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
+                    if (!ahead) gather(tile);
+                    CWAIT(3, BAR(R_EMPTY + s), ph_empty[s]); ph_empty[s] ^= 1;
+                    ((int2*)(smem + COFF_SIG))[(ltile & 1) * TC_ROWS + r] = make_int2((p.dbg & 256) ? -1 : sidx_r, __float_as_int(sg));
                     sts128(base + r * 128 + ((0 ^ (r & 7)) << 4), v0.x, v0.y, v0.z, v0.w);
                     sts128(base + r * 128 + ((1 ^ (r & 7)) << 4), v1.x, v1.y, v1.z, v1.w);
                     sts128(base + r * 128 + ((2 ^ (r & 7)) << 4), v2.x, v2.y, v2.z, v2.w);
                     sts128(base + r * 128 + ((3 ^ (r & 7)) << 4), v3.x, v3.y, v3.z, v3.w);
                     fence_proxy_async();
-                    asm volatile("bar.sync 3, 128;" ::: "memory");
+                    __syncwarp();
+                    asm volatile("barrier.sync 3, 128;" ::: "memory");
                     if (lt == 0) mbar_arrive(BAR(R_FULL + s));
                 }
             }
+            if (ahead) gather(tile + (int)gridDim.x);            // next tile's row data, while this tile is in the tensor pipe
         }
     } else {
         // =========================================================== MMA issuer (+ one-off resident weight load)
         if (lane == 0) {
             mbar_expect_tx(BAR(W_FULL), (uint32_t)n_wpanels * C_PANEL);
             for (int i = 0; i < n_wpanels; i++) bulk_g2s(sbase + COFF_W + i * C_PANEL, p.wpack + (size_t)i * C_PANEL, C_PANEL, BAR(W_FULL));
-            mbar_wait(BAR(W_FULL), 0);
-            uint32_t ph_full[C_RING];
-            for (int s = 0; s < C_RING; s++) ph_full[s] = 0;
+            CWAIT(4, BAR(W_FULL), 0);
+            uint32_t ph_full[C_STAGES];
+            for (int s = 0; s < C_STAGES; s++) ph_full[s] = 0;
             uint32_t ph_afull[2] = {0, 0}, ph_dempty[2] = {1, 1};
-            uint32_t n = 0, lcount = 0;
+            uint32_t lcount = 0;
+            const bool prof = (p.dbg & 32) != 0;                  // SGN_TC_DEBUG=32: where the issuer waits (cycles per tile)
+            long long w_ring = 0, w_act = 0, w_acc = 0, t0 = 0, t_start = prof ? clock64() : 0;
+            int ntl = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                ntl++;
                 for (int l = 0; l < p.n_hidden; l++, lcount++) {
                     const int db = lcount & 1;
                     const uint32_t d_tmem = tmem_base + (uint32_t)(db * CW);
-                    mbar_wait(BAR(D_EMPTY + db), ph_dempty[db]); ph_dempty[db] ^= 1;
+                    if (prof) t0 = clock64();
+                    CWAIT(5, BAR(D_EMPTY + db), ph_dempty[db]); ph_dempty[db] ^= 1;
+                    if (prof) w_acc += clock64() - t0;
                     uint32_t acc = 0;
                     if (l == 0) {
-                        for (int kp = 0; kp < C_K0_PANELS; kp++, n++) {
-                            const int s = n % C_RING;
-                            mbar_wait(BAR(R_FULL + s), ph_full[s]); ph_full[s] ^= 1;
+                        for (int kp = 0; kp < C_K0_PANELS; kp++) {
+                            const int s = stage_of(kp);
+                            if (prof) t0 = clock64();
+                            CWAIT(6, BAR(R_FULL + s), ph_full[s]); ph_full[s] ^= 1;
+                            if (prof) w_ring += clock64() - t0;
                             tc_fence_after();
-                            const uint32_t a_addr = sbase + COFF_RING + s * C_PANEL, b_addr = sbase + COFF_W + kp * C_PANEL;
+                            const uint32_t a_addr = stage_addr(s), b_addr = sbase + COFF_W + kp * C_PANEL;
                             const int ksteps = kp < 4 ? 4 : 2;
                             for (int k = 0; k < ksteps; k++) {
                                 // F stages: MN-major A, one K-step = 16 features = two 1 KB feature groups; the view panel is K-major
@@ -939,11 +992,13 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
                                 else tc_mma(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), C_IDESC, acc);
                                 acc = 1;
                             }
-                            tc_commit(BAR(R_EMPTY + s));
+                            if (s >= 2) tc_commit(BAR(R_EMPTY + s));           // a ring panel is free once its MMAs have read it
                         }
                     } else {
                         for (int kp = 0; kp < 2; kp++) {
-                            mbar_wait(BAR(A_FULL + kp), ph_afull[kp]); ph_afull[kp] ^= 1;
+                            if (prof) t0 = clock64();
+                            CWAIT(7, BAR(A_FULL + kp), ph_afull[kp]); ph_afull[kp] ^= 1;
+                            if (prof) w_act += clock64() - t0;
                             tc_fence_after();
                             const uint32_t a_addr = sbase + COFF_ACT + kp * C_PANEL;
                             const uint32_t b_addr = sbase + COFF_W + (C_K0_PANELS + 2 * (l - 1) + kp) * C_PANEL;
@@ -954,14 +1009,23 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
                         }
                     }
                     tc_commit(BAR(D_FULL + db));
+                    if (l == p.n_hidden - 1) {
+                        // the activation panels are free for the next tile's first two F panels once this tile's last layer has been multiplied
+                        tc_commit(BAR(R_EMPTY + 0));
+                        tc_commit(BAR(R_EMPTY + 1));
+                    }
                 }
             }
+            if (prof && blockIdx.x == 0)
+                printf("colour mma issuer: %lld cycles/tile (%d tiles); waiting: F ring %lld, activations (epilogue) %lld, accumulator free %lld\n",
+                       (clock64() - t_start) / max(ntl, 1), ntl, w_ring / max(ntl, 1), w_act / max(ntl, 1), w_acc / max(ntl, 1));
         }
     }
     __syncthreads();
     if (warp == C_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
+#undef CWAIT
 // ------------------------------------------------------------------------------------------------ small kernels
 // Point part of the first per-neighbour layer, hoisted out of the per-tuple work: block1.0 is linear in its input
 // [emb | PE(emb) | PE(dists)], and the first 224 columns depend on the POINT only, so
