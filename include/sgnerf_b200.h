@@ -70,6 +70,12 @@ int sgn_grid_workspace_bytes(int64_t N, const SgnGridCfg* cfg, size_t* persisten
 int sgn_grid_build(const float* xyz /*[N,3]*/, int64_t N, int64_t actual_n, const SgnGridCfg* cfg,
                    void* persistent, size_t persistent_bytes, void* scratch, size_t scratch_bytes,
                    SgnGrid** out, void* stream);
+/* The same with options.  SGN_GRID_NO_NEIGHBOUR_LISTS: skip the per-voxel neighbour lists of the K-NN kernel (about two thirds of the
+ * build time; the kernel then walks the compact brick index itself, a little slower per frame) -- for clouds that are edited between
+ * frames, where the grid is rebuilt more often than it is queried. */
+#define SGN_GRID_NO_NEIGHBOUR_LISTS 1
+int sgn_grid_build_flags(const float* xyz /*[N,3]*/, int64_t N, int64_t actual_n, const SgnGridCfg* cfg, void* persistent,
+                         size_t persistent_bytes, void* scratch, size_t scratch_bytes, int flags, SgnGrid** out, void* stream);
 int sgn_grid_destroy(SgnGrid* g);
 /* Device pointers of the built structures, for tests and tooling (all int32 unless noted):
  *   0 cell_slot [X*Y*Z] (= coor_2_occ), 1 occ_bits uint32[ceil(X*Y*Z/32)] (= coor_occ as a bitmask),
@@ -179,6 +185,11 @@ int sgn_agg_forward(const SgnAggCfg* cfg, const float* const* weights /*[host]*/
 int sgn_agg_point_cache_bytes(const SgnAggCfg* cfg, int64_t N, size_t* bytes);
 int sgn_agg_point_cache_build(const SgnAggCfg* cfg, const float* const* weights /*[host]*/, const SgnPointTables* tables, void* cache,
                               size_t cache_bytes, void* stream);
+/* Incremental update after point edits: the cache rows of the n_rows points listed in `rows` (device int32; entries outside [0, N) are
+ * skipped) are recomputed from the current embedding tables with the weights the cache was built with (they are kept, packed, inside
+ * the cache).  The tables must have the same N as at build time. */
+int sgn_agg_point_cache_update(const SgnAggCfg* cfg, const SgnPointTables* tables, void* cache, size_t cache_bytes, const int32_t* rows,
+                               int64_t n_rows, void* stream);
 int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights /*[host]*/, const float* const* biases /*[host]*/,
                            const SgnPointTables* tables, const int32_t* pidx, const float* loc_w, const float* raydir,
                            const float* campos, const float* camrotc2w, int64_t R, int SR, int K, int precision,
@@ -271,6 +282,24 @@ int sgn_probe_outputs(const float* opacity /*[R,SR]*/, const float* sample_loc_w
                       const SgnPointTables* tables, int feat_dim, int64_t R, int SR, int K, float* ray_max_shading_opacity,
                       float* ray_max_sample_loc_w, float* ray_max_far_dist, float* shading_avg_color, float* shading_avg_dir,
                       float* shading_avg_conf, float* shading_avg_embedding, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxel-grid helpers next to the render path.
+ * ---------------------------------------------------------------------------------------------- */
+/* Point-cloud initialisation, construct_vox_points_closest (models/mvs/mvs_utils.py:536-561; run/train_ft.py:141, :715): one point per
+ * occupied voxel of the grid floor((xyz - space_min) / vox_size).  Voxels come out in the lexicographic order of their coordinates
+ * (what torch.unique(dim=0) returns): centroid [V,3] = mean of the voxel's points, grid_idx int32 [V,3], min_idx int64 [V] = index of the
+ * point closest to the centroid (first one on ties), *count = V (device).  Outputs must hold N entries.  space_min / vox_size are
+ * [host] float[3]. */
+int sgn_voxel_downsample_bytes(int64_t N, size_t* bytes);
+int sgn_voxel_downsample(const float* xyz /*[N,3]*/, int64_t N, const float* space_min /*[host]*/, const float* vox_size /*[host]*/,
+                         int vox_res, void* workspace, size_t workspace_bytes, float* centroid, int32_t* grid_idx, int64_t* min_idx,
+                         int32_t* count, void* stream);
+/* NeuralPoints.query_vox_grid (models/neural_points/neural_points.py:814-826, the NN < 0 query): out int64 [n_samples, 8] = indices of
+ * the 8 corners of the grid cell each sample falls in (full_grid_idx int32 [(grid_res+1)^3], -1 = no grid point), all -1 unless the
+ * cell lies inside the grid and its 8 corners exist.  space_min is a [host] float[3]. */
+int sgn_query_vox_grid(const float* sample_loc_w /*[n_samples,3]*/, int64_t n_samples, const int32_t* full_grid_idx, int grid_res,
+                       const float* space_min /*[host]*/, float grid_vox_sz, int64_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Training step glue.  Replaces BaseRenderingModel.compute_losses for the canonical loss items

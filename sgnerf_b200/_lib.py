@@ -46,6 +46,8 @@ SIGNATURES = {
     "sgn_grid_workspace_bytes": (c_int, [c_i64, C.POINTER(SgnGridCfg), C.POINTER(c_size), C.POINTER(c_size)]),
     "sgn_grid_build": (c_int, [c_void, c_i64, c_i64, C.POINTER(SgnGridCfg), c_void, c_size, c_void, c_size,
                                C.POINTER(c_void), c_void]),
+    "sgn_grid_build_flags": (c_int, [c_void, c_i64, c_i64, C.POINTER(SgnGridCfg), c_void, c_size, c_void, c_size, c_int,
+                                     C.POINTER(c_void), c_void]),
     "sgn_grid_destroy": (c_int, [c_void]),
     "sgn_grid_buffer": (c_int, [c_void, c_int, C.POINTER(c_void), C.POINTER(c_i64)]),
     "sgn_query": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_int, c_int, c_int, c_int, c_f32,
@@ -66,6 +68,7 @@ SIGNATURES = {
                                       c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void, c_void]),
     "sgn_agg_point_cache_bytes": (c_int, [C.POINTER(SgnAggCfg), c_i64, C.POINTER(c_size)]),
     "sgn_agg_point_cache_build": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(SgnPointTables), c_void, c_size, c_void]),
+    "sgn_agg_point_cache_update": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(SgnPointTables), c_void, c_size, c_void, c_i64, c_void]),
     "sgn_agg_backward": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                  c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_void, c_void,
                                  C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointGrads), c_void, c_size, c_void]),
@@ -86,6 +89,9 @@ SIGNATURES = {
     "sgn_probe_outputs": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, C.POINTER(SgnPointTables), c_int, c_i64, c_int, c_int,
                                   c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void]),
     "sgn_fill_invalid": (c_int, [c_void, c_void, c_i64, c_int, c_void, c_void, c_void, c_void]),
+    "sgn_voxel_downsample_bytes": (c_int, [c_i64, C.POINTER(c_size)]),
+    "sgn_voxel_downsample": (c_int, [c_void, c_i64, C.POINTER(c_f32), C.POINTER(c_f32), c_int, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
+    "sgn_query_vox_grid": (c_int, [c_void, c_i64, c_void, c_int, C.POINTER(c_f32), c_f32, c_void, c_void]),
     "sgn_loss_hit_count": (c_int, [c_void, c_i64, c_void, c_void]),
     "sgn_loss_forward_backward": (c_int, [c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_void, c_f32, c_f32, c_f32, c_f32, c_void, c_void,
                                           c_void, c_void]),

@@ -21,6 +21,8 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
                        void* workspace, size_t workspace_bytes, const void* point_cache, cudaStream_t st);
 int sgn_agg_tc_point_cache_bytes(const AggPlan& P, int64_t N, size_t* bytes);
 int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, const SgnPointTables* tables, void* cache, size_t cache_bytes, cudaStream_t st);
+int sgn_agg_tc_point_cache_update(const AggPlan& P, const SgnPointTables* tables, void* cache, size_t cache_bytes, const int32_t* rows, int64_t n_rows,
+                                  cudaStream_t st);
 
 static int check_common(const SgnAggCfg* cfg, AggPlan* P, int64_t R, int SR, int K)
 {
@@ -104,6 +106,17 @@ extern "C" int sgn_agg_point_cache_build(const SgnAggCfg* cfg, const float* cons
     SGN_CHECK_ARG(weights && tables && cache && tables->embedding, "sgn_agg_point_cache_build: NULL argument");
     SGN_CHECK_ARG(P.dims.LD == 0 || tables->label_emb, "sgn_agg_point_cache_build: label embedding table missing");
     return sgn_agg_tc_point_cache_build(P, weights, tables, cache, cache_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int sgn_agg_point_cache_update(const SgnAggCfg* cfg, const SgnPointTables* tables, void* cache, size_t cache_bytes, const int32_t* rows,
+                                          int64_t n_rows, void* stream)
+{
+    AggPlan P;
+    int rc = make_plan(cfg, &P);
+    if (rc) return rc;
+    SGN_CHECK_ARG(tables && cache && tables->embedding && (rows || n_rows == 0) && n_rows >= 0, "sgn_agg_point_cache_update: bad argument");
+    SGN_CHECK_ARG(P.dims.LD == 0 || tables->label_emb, "sgn_agg_point_cache_update: label embedding table missing");
+    return sgn_agg_tc_point_cache_update(P, tables, cache, cache_bytes, rows, n_rows, (cudaStream_t)stream);
 }
 
 extern "C" int sgn_agg_backward_prec(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,

@@ -1036,8 +1036,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) agg_color_tc_kernel(const __grid
 constexpr int P0_OFF_W = 0, P0_OFF_A = 4 * PANEL_B, P0_OFF_BAR = P0_OFF_A + 4 * PANEL_A, P0_SMEM = P0_OFF_BAR + 64 + 1024;
 // raw_cols == 0: operand = [emb | PE(emb)] of the 32-channel embedding (224 columns, 4 panels); raw_cols > 0: operand = the table's
 // raw_cols columns as they are (label embedding for block2_bpnet.0), ceil(raw_cols / 64) panels.
+// rows != NULL: only the n_rows points listed there (an incremental update after point edits), tile = 128 list entries.
 __global__ void __launch_bounds__(128, 1) tc_point_gemm_kernel(const float* __restrict__ emb, int raw_cols, int64_t N, const uint8_t* __restrict__ wpack0,
-                                                                uint8_t* __restrict__ p0tab)
+                                                                uint8_t* __restrict__ p0tab, const int32_t* __restrict__ rows, int64_t n_rows)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1062,12 +1063,16 @@ __global__ void __launch_bounds__(128, 1) tc_point_gemm_kernel(const float* __re
         mbar_expect_tx(bar_w, (uint32_t)npan * PANEL_B);
         for (int i = 0; i < npan; i++) bulk_g2s(sbase + P0_OFF_W + i * PANEL_B, wpack0 + (size_t)i * PANEL_B, PANEL_B, bar_w);
     }
-    const int64_t ntile = (N + TC_ROWS - 1) / TC_ROWS;
+    const int64_t n_work = rows ? n_rows : N;
+    const int64_t ntile = (n_work + TC_ROWS - 1) / TC_ROWS;
     uint32_t ph_d = 0;
     const uint32_t x0 = sbase + P0_OFF_A;
     const int row = tid;
     for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-        const int64_t pt = tile * TC_ROWS + row;
+        const int64_t wi = tile * TC_ROWS + row;
+        // the point of this row; out-of-range rows (tile padding, bad list entries) compute on zeros and store nothing
+        int64_t pt = rows ? (wi < n_rows ? (int64_t)rows[wi] : N) : wi;
+        if (pt < 0) pt = N;
         if (raw_cols > 0) {
             // ---- operand row: the table's columns as they are, zero padded to whole panels
             for (int q = 0; q < npan * 8; q++) {
@@ -1344,14 +1349,42 @@ int sgn_agg_tc_point_cache_build(const AggPlan& P, const float* const* weights, 
     const int64_t ptiles = (tables->N + TC_ROWS - 1) / TC_ROWS;
     const int grid = (int)(ptiles < n_sm ? ptiles : n_sm);
     launch(tc_pack_weight_kernel, cdiv((int64_t)4 * TC_W * 8, 256), 256, 0, st, weights[0], P.layers[0].in, TC_W, TC_W, TC_PT_COLS, 4, (const float*)nullptr, p0pack);
-    launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->embedding, 0, tables->N, p0pack, base + pc_off_p0());
+    launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->embedding, 0, tables->N, p0pack, base + pc_off_p0(), (const int32_t*)nullptr, (int64_t)0);
     for (int t = 1; t < P.n_tuple_layers; t++)
         if (P.layers[t].extra == EXTRA_LABEL) {
             const int lp = (P.dims.LD + 63) / 64;
             launch(tc_pack_weight_kernel, cdiv((int64_t)lp * TC_W * 8, 256), 256, 0, st, weights[t] + TC_W, P.layers[t].in, TC_W, TC_W, P.dims.LD, lp,
                    (const float*)nullptr, plpack);
-            launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->label_emb, P.dims.LD, tables->N, plpack, base + pc_off_pl(tables->N));
+            launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->label_emb, P.dims.LD, tables->N, plpack, base + pc_off_pl(tables->N),
+                   (const int32_t*)nullptr, (int64_t)0);
         }
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+// Rows of an existing cache recomputed for the listed points only (their embeddings changed: point edits); weights as at build time.
+int sgn_agg_tc_point_cache_update(const AggPlan& P, const SgnPointTables* tables, void* cache, size_t cache_bytes, const int32_t* rows, int64_t n_rows,
+                                  cudaStream_t st)
+{
+    size_t need = 0;
+    int rc = sgn_agg_tc_point_cache_bytes(P, tables->N, &need);
+    if (rc) return rc;
+    if (need > cache_bytes || ((uintptr_t)cache & 255)) {
+        set_error("sgn_agg_point_cache_update: cache too small or misaligned (need %zu bytes, got %zu)", need, cache_bytes);
+        return SGN_E_WORKSPACE;
+    }
+    if (n_rows <= 0) return SGN_OK;
+    SGN_CUDA(cudaFuncSetAttribute(tc_point_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    uint8_t* base = (uint8_t*)cache;
+    const int64_t ptiles = (n_rows + TC_ROWS - 1) / TC_ROWS;
+    const int grid = (int)(ptiles < n_sm ? ptiles : n_sm);
+    launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->embedding, 0, tables->N, base, base + pc_off_p0(), rows, n_rows);
+    for (int t = 1; t < P.n_tuple_layers; t++)
+        if (P.layers[t].extra == EXTRA_LABEL)
+            launch(tc_point_gemm_kernel, grid, 128, P0_SMEM, st, tables->label_emb, P.dims.LD, tables->N, base + 4 * PANEL_B, base + pc_off_pl(tables->N), rows, n_rows);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
@@ -1484,9 +1517,9 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         pltab = (const uint8_t*)point_cache + pc_off_pl(tables->N);
     } else {
         const int64_t ptiles = (tables->N + TC_ROWS - 1) / TC_ROWS;
-        launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->embedding, 0, tables->N, ws.p0pack, ws.p0tab);
+        launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->embedding, 0, tables->N, ws.p0pack, ws.p0tab, (const int32_t*)nullptr, (int64_t)0);
         if (d.LD > 0)
-            launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->label_emb, d.LD, tables->N, ws.plpack, ws.pltab);
+            launch(tc_point_gemm_kernel, (int)(ptiles < n_sm ? ptiles : n_sm), 128, P0_SMEM, st, tables->label_emb, d.LD, tables->N, ws.plpack, ws.pltab, (const int32_t*)nullptr, (int64_t)0);
     }
     for (int t = 1; t < P.n_tuple_layers; t++)
         if (tp.padd[t]) tp.padd[t] = pltab;

@@ -356,6 +356,28 @@ class NeuralPoints(nn.Module):
             self.points_label = torch.cat([self.points_label, add_label], dim=0)
         self.reset_querier()
 
+    def construct_grid_points(self, xyz):
+        """neural_points.py:685-712: a regular grid of grid_res^3 cells over the cloud's bounding cube (x 1.1); the grid points of every
+        construction voxel (construct_res^3) that holds a point become the neural points, `full_grid_idx` maps a grid coordinate to its
+        point (or -1).  Init-time host logic (torch); the per-sample lookup is sgn_query_vox_grid.  Returns (xyz, sparse_grid_idx,
+        full_grid_idx) and keeps space_min / grid_vox_sz / full_grid_idx for forward()."""
+        o = self.opt
+        xyz_min, xyz_max = torch.min(xyz, dim=-2)[0], torch.max(xyz, dim=-2)[0]
+        self.space_edge = torch.max(xyz_max - xyz_min) * 1.1
+        mid = (xyz_max + xyz_min) / 2
+        self.space_min, self.space_max = mid - self.space_edge / 2, mid + self.space_edge / 2
+        self.construct_vox_sz = self.space_edge / o.construct_res
+        self.grid_vox_sz = self.space_edge / o.grid_res
+        vox = torch.unique(torch.floor((xyz - self.space_min[None]) / self.construct_vox_sz[None]).to(torch.int16), dim=0)
+        ratio = int(o.grid_res / o.construct_res)
+        g = torch.arange(0, ratio + 1, device=vox.device, dtype=vox.dtype)
+        cell = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), dim=-1).view(1, -1, 3)
+        sparse = torch.unique((vox[:, None, :] * ratio + cell).view(-1, 3), dim=0).to(torch.int64)
+        full = torch.full([o.grid_res + 1] * 3, -1, device=xyz.device, dtype=torch.int32)
+        full[sparse[:, 0], sparse[:, 1], sparse[:, 2]] = torch.arange(0, sparse.shape[0], device=xyz.device, dtype=torch.int32)
+        self.full_grid_idx = full
+        return self.space_min[None] + sparse * self.grid_vox_sz, sparse, full
+
     def getPointsData(self):
         return self.xyz.data.cpu().numpy().copy(), None if self.points_feats is None else self.points_feats.data.cpu().numpy().copy()
 
@@ -375,8 +397,10 @@ class NeuralPoints(nn.Module):
         camrotc2w, campos = inputs["camrotc2w"], inputs["campos"]
         near, far = float(torch.min(inputs["near"])), float(torch.max(inputs["far"]))
         raydir = inputs["raydir"]
-        if _opt(self.opt, "NN", 2) < 0:
-            raise NotImplementedError("sgnerf_b200: query_vox_grid (NN < 0) is not built")
+        vox_query = _opt(self.opt, "NN", 2) < 0
+        if vox_query and getattr(self, "full_grid_idx", None) is None:
+            raise RuntimeError("sgnerf_b200: --NN < 0 queries the construction grid: call construct_grid_points(xyz) first "
+                               "(the reference builds it in its constructor when --construct_res > 0, neural_points.py:344)")
         semantic = _opt(self.opt, "semantic_guidance", 0) == 1 or _opt(self.opt, "predict_semantic", 0) == 1
         kw = {}
         if _opt(self.opt, "semantic_guidance", 0) == 1:
@@ -386,6 +410,11 @@ class NeuralPoints(nn.Module):
         sel = rmask > 0                                          # host sync, as in the reference (:946); the fused frame path avoids it
         sample_pidx = pidx_u[sel][None].contiguous()
         sample_loc_w = loc_w_u[sel][None].contiguous()
+        if vox_query:
+            # neural_points.py:799-803: the 8 corners of the construction-grid cell of every sample replace the K-NN result
+            sample_pidx = ops.query_vox_grid(sample_loc_w, self.full_grid_idx, self.space_min, float(self.grid_vox_sz),
+                                             self.opt.grid_res).to(torch.int32) if sample_pidx.shape[1] > 0 else \
+                torch.zeros(1, 0, self.opt.SR, 8, device=sample_pidx.device, dtype=torch.int32)
         rd = raydir.reshape(-1, 3)[sel]
         sample_ray_dirs = rd[None, :, None, :].expand(-1, -1, self.opt.SR, -1).contiguous()
         sample_loc = lighting_fast_querier.w2pers(sample_loc_w, camrotc2w, campos)

@@ -42,7 +42,7 @@ def _workspace(nbytes, device):
 # ---------------------------------------------------------------------------------------------------------
 # occupancy grid
 # ---------------------------------------------------------------------------------------------------------
-def grid_hyperparameters(xyz, vsize, vscale, kernel_size, ranges, radius_limit_scale):
+def grid_hyperparameters(xyz, vsize, vscale, kernel_size, ranges, radius_limit_scale, alive=None):
     """Host-side grid parameters exactly as lighting_fast_querier.get_hyperparameters derives them
     (reference models/neural_points/query_point_indices_worldcoords.py:66-92): fp32 min/max of the cloud,
     clamp to `ranges`, pad by scaled_vsize*kernel/2 (a float64 product rounded to fp32), ceil of a float64
@@ -50,8 +50,13 @@ def grid_hyperparameters(xyz, vsize, vscale, kernel_size, ranges, radius_limit_s
     vsize64 = np.asarray(vsize, dtype=np.float64)
     vscale_i = np.asarray(vscale, dtype=np.int32)
     scaled_vsize = (vsize64 * vscale_i).astype(np.float32)
-    mn = xyz.reshape(-1, 3).min(dim=0)[0].float()
-    mx = xyz.reshape(-1, 3).max(dim=0)[0].float()
+    pts = xyz.reshape(-1, 3)
+    if alive is None:
+        mn, mx = pts.min(dim=0)[0].float(), pts.max(dim=0)[0].float()
+    else:        # rows of pruned points (holes kept for index stability, RenderScene.edit) do not count
+        a = alive.reshape(-1, 1)
+        mn = torch.where(a, pts, torch.full_like(pts, float("inf"))).min(dim=0)[0].float()
+        mx = torch.where(a, pts, torch.full_like(pts, float("-inf"))).max(dim=0)[0].float()
     if ranges is not None:
         r = torch.as_tensor(np.asarray(ranges, dtype=np.float64), dtype=torch.float32, device=xyz.device)
         mn = torch.maximum(mn, r[:3])
@@ -72,7 +77,7 @@ class OccGrid:
     """Device-resident occupancy grid (sgn_grid_build).  Build once per point-cloud version."""
 
     def __init__(self, xyz, origin, scaled_vsize, dim, query_size, P, max_o, seconds_claim=0, seconds_fill=0,
-                 actual_n=None):
+                 actual_n=None, neighbour_lists=True):
         self.xyz = _dev(xyz.reshape(-1, 3), torch.float32, "xyz")
         N = self.xyz.shape[0]
         cfg = SgnGridCfg()
@@ -87,9 +92,9 @@ class OccGrid:
         self._persistent = _workspace(pb.value, self.xyz.device)
         scratch = _workspace(sb.value, self.xyz.device)
         handle = C.c_void_p()
-        _lib.call("sgn_grid_build", _ptr(self.xyz), N, N if actual_n is None else int(actual_n), C.byref(cfg),
+        _lib.call("sgn_grid_build_flags", _ptr(self.xyz), N, N if actual_n is None else int(actual_n), C.byref(cfg),
                   _ptr(self._persistent), self._persistent.numel() * 4, _ptr(scratch), scratch.numel() * 4,
-                  C.byref(handle), _stream())
+                  0 if neighbour_lists else 1, C.byref(handle), _stream())
         self._handle = handle
         self._scratch = scratch  # stream-ordered: keep alive until the build kernels have run
         self.N, self.P, self.max_o = N, int(P), int(max_o)
@@ -155,6 +160,44 @@ def gather_rows(table, pidx):
     Cc = table.shape[-1]
     out = torch.empty(pidx.shape + (Cc,), dtype=torch.float32, device=table.device)
     _lib.call("sgn_gather_rows", _ptr(table), Cc, _ptr(pidx), pidx.numel(), _ptr(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# voxel-grid helpers
+# ---------------------------------------------------------------------------------------------------------
+def voxel_downsample(xyz_val, vox_res):
+    """construct_vox_points_closest (models/mvs/mvs_utils.py:536-561, the call of run/train_ft.py:141 / :715): the host glue (bounds,
+    voxel size) with the reference's torch ops, the grouping / centroids / closest points by sgn_voxel_downsample.
+    Returns (xyz_centroid [V,3], sparse_grid_idx int32 [V,3], min_idx int64 [V])."""
+    xyz = _dev(xyz_val.reshape(-1, 3), torch.float32, "xyz")
+    N = xyz.shape[0]
+    xyz_min, xyz_max = torch.min(xyz, dim=-2)[0], torch.max(xyz, dim=-2)[0]
+    space_edge = torch.max(xyz_max - xyz_min) * 1.05
+    space_min = (xyz_max + xyz_min) / 2 - space_edge / 2
+    vox_sz = space_edge / vox_res
+    mn = (C.c_float * 3)(*[float(v) for v in space_min.cpu()])
+    sz = (C.c_float * 3)(*([float(vox_sz.cpu())] * 3))
+    nbytes = C.c_size_t()
+    _lib.call("sgn_voxel_downsample_bytes", N, C.byref(nbytes))
+    ws = _workspace(nbytes.value, xyz.device)
+    centroid = torch.empty(N, 3, dtype=torch.float32, device=xyz.device)
+    grid_idx = torch.empty(N, 3, dtype=torch.int32, device=xyz.device)
+    min_idx = torch.empty(N, dtype=torch.int64, device=xyz.device)
+    count = torch.zeros(1, dtype=torch.int32, device=xyz.device)
+    _lib.call("sgn_voxel_downsample", _ptr(xyz), N, mn, sz, int(vox_res), _ptr(ws), ws.numel() * 4, _ptr(centroid), _ptr(grid_idx), _ptr(min_idx),
+              _ptr(count), _stream())
+    V = int(count.item())
+    return centroid[:V], grid_idx[:V], min_idx[:V]
+
+
+def query_vox_grid(sample_loc_w, full_grid_idx, space_min, grid_vox_sz, grid_res):
+    """NeuralPoints.query_vox_grid (neural_points.py:814-826): sample_loc_w [...,3] -> int64 [...,8] corner indices (sgn_query_vox_grid)."""
+    loc = _dev(sample_loc_w, torch.float32, "sample_loc_w")
+    grid = _dev(full_grid_idx, torch.int32, "full_grid_idx")
+    out = torch.empty(loc.shape[:-1] + (8,), dtype=torch.int64, device=loc.device)
+    mn = (C.c_float * 3)(*[float(v) for v in torch.as_tensor(space_min).cpu().reshape(3)])
+    _lib.call("sgn_query_vox_grid", _ptr(loc), loc.numel() // 3, _ptr(grid), int(grid_res), mn, float(grid_vox_sz), _ptr(out), _stream())
     return out
 
 
@@ -490,6 +533,21 @@ def build_point_cache(cfg, weights, embedding, label_emb=None):
     tb.N = N
     _lib.call("sgn_agg_point_cache_build", C.byref(cfg), _ptr_array(ws_), C.byref(tb), _ptr(cache), cache.numel() * 4, _stream())
     return cache
+
+
+def update_point_cache(cfg, cache, embedding, rows, label_emb=None):
+    """sgn_agg_point_cache_update: recompute the cache rows of the points listed in `rows` (int32 device tensor) after their embeddings
+    changed (point edits); the layer weights are the ones the cache was built with."""
+    f32 = torch.float32
+    embedding = _dev(embedding.reshape(-1, embedding.shape[-1]), f32, "embedding")
+    N = embedding.shape[0]
+    tb = SgnPointTables()
+    tb.embedding = embedding.data_ptr()
+    label_emb = _dev(label_emb.reshape(N, -1), f32, "label_emb") if label_emb is not None else None
+    tb.label_emb = label_emb.data_ptr() if label_emb is not None else None
+    tb.N = N
+    rows = _dev(rows.reshape(-1), torch.int32, "rows")
+    _lib.call("sgn_agg_point_cache_update", C.byref(cfg), C.byref(tb), _ptr(cache), cache.numel() * 4, _ptr(rows), rows.numel(), _stream())
 
 
 def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb, pidx, loc_w, raydir, campos, camrotc2w,

@@ -57,6 +57,8 @@ class RenderScene:
         self._hp = None
         self._point_cache = None
         self._ts = {}
+        self.alive = None                  # bool [N] once edit() has made holes (pruned rows kept so that point indices stay stable)
+        self.dynamic = False               # True: the cloud is edited between frames -- grids are built without the K-NN neighbour lists
 
     def depth_candidates(self, near, far):
         """middle_point_ts without jitter (the test-time candidates, identical for every ray and frame): computed once per (near, far)."""
@@ -104,12 +106,62 @@ class RenderScene:
         self.invalidate_grid()
         return int(self.xyz.shape[0])
 
+    HOLE = 1.0e30      # position of a pruned row: outside every grid, so the point can never be claimed, listed or found again
+
+    def edit(self, prune_thresh=None, add=None):
+        """Point edits WITHOUT renumbering (the fast path of prune / grow between training steps).
+        prune_thresh: the points whose confidence is below it become holes -- their rows stay, their positions move to HOLE.
+        add = (xyz [M,3], embedding [M,C], color [M,3], dir [M,3], conf [M][, label_emb [M,E]]): the new points fill holes first (lowest
+        index first) and are appended when there are none left.
+        Indices of surviving points do not change, so the per-point first-layer tables (point_cache) are recomputed for the written
+        rows only; the occupancy grid is rebuilt on next use (sgn_grid_build: ~1.5 ms for 10 M points).  The state after edit() is what
+        a fresh RenderScene built from the same tensors gives, bit for bit.  Returns the rows the new points went to (int64)."""
+        dev = self.xyz.device
+        N = self.xyz.shape[0]
+        if self.alive is None:
+            self.alive = torch.ones(N, dtype=torch.bool, device=dev)
+        if prune_thresh is not None:
+            dead = self.alive & (self.conf < prune_thresh)
+            self.alive &= ~dead
+            self.xyz.masked_fill_(dead[:, None], self.HOLE)
+        rows = torch.zeros(0, dtype=torch.int64, device=dev)
+        if add is not None:
+            a_xyz, a_emb, a_col, a_dir, a_conf = [torch.as_tensor(t, dtype=torch.float32, device=dev) for t in add[:5]]
+            a_lab = torch.as_tensor(add[5], dtype=torch.float32, device=dev) if len(add) > 5 and add[5] is not None else None
+            M = a_xyz.shape[0]
+            free = torch.nonzero(~self.alive).reshape(-1)[:M]               # (one host synchronisation: the number of holes)
+            n_fill = int(free.numel())
+            if n_fill < M:                                                   # not enough holes: the tables grow
+                k = M - n_fill
+                grow = lambda t, new: torch.cat([t, new.reshape(k, *t.shape[1:])], dim=0).contiguous()
+                self.xyz, self.embedding, self.color, self.dirs = (grow(self.xyz, a_xyz[n_fill:]), grow(self.embedding, a_emb[n_fill:]),
+                                                                   grow(self.color, a_col[n_fill:]), grow(self.dirs, a_dir[n_fill:]))
+                self.conf = grow(self.conf, a_conf[n_fill:])
+                if self.label_emb is not None:
+                    self.label_emb = grow(self.label_emb, a_lab[n_fill:])
+                self.alive = torch.cat([self.alive, torch.ones(k, dtype=torch.bool, device=dev)])
+                self._point_cache = None                                     # its size is tied to N
+            if n_fill:
+                self.xyz.index_copy_(0, free, a_xyz[:n_fill]); self.embedding.index_copy_(0, free, a_emb[:n_fill].reshape(n_fill, -1))
+                self.color.index_copy_(0, free, a_col[:n_fill]); self.dirs.index_copy_(0, free, a_dir[:n_fill])
+                self.conf.index_copy_(0, free, a_conf[:n_fill].reshape(-1))
+                if self.label_emb is not None:
+                    self.label_emb.index_copy_(0, free, a_lab[:n_fill])
+                self.alive[free] = True
+                if self._point_cache is not None:
+                    ops.update_point_cache(self.agg_cfg, self._point_cache, self.embedding, free.to(torch.int32), self.label_emb)
+            rows = torch.cat([free, torch.arange(N, N + M - n_fill, device=dev)])
+        if self._grid is not None:
+            self._grid.close()
+        self._grid, self._hp = None, None                                    # rebuilt on next use; the point cache stays
+        return rows
+
     def grid(self, seconds=(0, 0)):
         if self._grid is None:
             q = self.qopt
-            self._hp = ops.grid_hyperparameters(self.xyz, q.vsize, q.vscale, q.kernel_size, q.ranges, q.radius_limit_scale)
+            self._hp = ops.grid_hyperparameters(self.xyz, q.vsize, q.vscale, q.kernel_size, q.ranges, q.radius_limit_scale, alive=self.alive)
             self._grid = ops.OccGrid(self.xyz, self._hp.ranges[:3], self._hp.scaled_vsize, self._hp.scaled_vdim, q.query_size,
-                                     q.P, q.max_o, seconds_claim=seconds[0], seconds_fill=seconds[1])
+                                     q.P, q.max_o, seconds_claim=seconds[0], seconds_fill=seconds[1], neighbour_lists=not self.dynamic)
         return self._grid, self._hp
 
 

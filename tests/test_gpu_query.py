@@ -210,3 +210,19 @@ def test_full_size_march_against_torch_bruteforce():
                     assert bool((((coarse[bc >> 5].long() >> (bc & 31)) & 1) > 0).all())
         if b >= 3:
             break
+
+
+def test_grid_without_neighbour_lists_gives_the_same_query(scene_c0):
+    """SGN_GRID_NO_NEIGHBOUR_LISTS (grids of clouds that are edited between frames): the K-NN kernel walks the brick index itself instead
+    of the prebuilt per-voxel lists -- identical outputs, slot order included, also under both overflows."""
+    from sgnerf_b200 import ops
+    for opt, seconds in ((qr.default_opt(SR=24), (0, 0, 0)), (qr.default_opt(SR=24, P=2, max_o=3000, vsize=[0.02, 0.02, 0.02]), (11, 22, 0))):
+        t = util.shared_t(scene_c0.near, scene_c0.far, opt.z_depth_dim)
+        a = util.cuda_query(scene_c0, opt, t, seconds=seconds)
+        xyz = torch.from_numpy(scene_c0.xyz).cuda()
+        hp = a.hp
+        g2 = ops.OccGrid(xyz, hp.ranges[:3], hp.scaled_vsize, hp.scaled_vdim, opt.query_size, opt.P, opt.max_o, seconds_claim=seconds[0],
+                         seconds_fill=seconds[1], neighbour_lists=False)
+        b = util.cuda_query(scene_c0, opt, t, seconds=seconds, grid=(g2, hp))
+        assert torch.equal(a.pidx, b.pidx) and torch.equal(a.loc_w, b.loc_w) and torch.equal(a.rmask, b.rmask) and torch.equal(a.smask, b.smask)
+        assert int(a.rmask.sum()) > 100

@@ -266,3 +266,44 @@ def test_adam_rows_multi_equals_dense_torch_adam():
         torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-5, atol=2e-6)
     un = active.cpu() == 0
     assert 0.1 < float(un.float().mean()) < 0.9 and all(torch.equal(p.cpu()[un], q[un]) for p, q in zip(ps, p0))
+
+
+def test_scene_edit_with_stable_indices_equals_a_fresh_scene():
+    """RenderScene.edit (prune -> holes, grow -> fill holes / append, per-point tables updated for the written rows only, grid rebuilt):
+    after two rounds of edits the scene renders bit for bit like a scene built from scratch from the same tensors, the rows of the
+    surviving points never moved, and the per-point cache equals a freshly built one."""
+    n_points = 40_000
+    s = synth.scene_room(n_points, room=(3.0, 3.0, 2.0), width=160, height=120, seed=7)
+    tabs = synth.make_point_tables(n_points, 32, 0, seed=0, conf_spread=0.3)
+    cfg = rr.agg_config()
+    P = rr.init_params(cfg, seed=3, bias_scale=0.05)
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    mk = lambda xyz, e, c, d, cf: pipeline.RenderScene(xyz, e, c, d, cf, [P[n + ".weight"].clone() for n in names], [P[n + ".bias"].clone() for n in names],
+                                                       cfg_to_c(cfg), pipeline.query_options(), device="cuda")
+    a = mk(torch.from_numpy(s.xyz), tabs.embedding.reshape(n_points, -1), tabs.color.reshape(n_points, 3), tabs.dir.reshape(n_points, 3),
+           tabs.conf.reshape(n_points))
+    args = (torch.from_numpy(s.campos).cuda(), torch.from_numpy(s.camrotc2w).cuda(), torch.from_numpy(s.raydir).cuda(), s.near, s.far,
+            torch.ones(3, device="cuda"))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    with torch.no_grad():
+        before = pipeline.render_rays(a, *args, precision=ops.PRECISION_BF16)           # builds grid + point cache
+        emb0 = a.embedding.clone()
+        for rnd, (thr, m) in enumerate(((0.8, 300), (0.85, 15000))):                       # round 2 grows more than it prunes: appends
+            new = (a.xyz[a.alive if a.alive is not None else slice(None)][:m] + 0.003, torch.rand(m, 32, device="cuda", generator=g) - 0.5,
+                   torch.rand(m, 3, device="cuda", generator=g), torch.nn.functional.normalize(torch.randn(m, 3, device="cuda", generator=g), dim=-1),
+                   0.9 + 0.1 * torch.rand(m, device="cuda", generator=g))
+            rows = a.edit(prune_thresh=thr, add=new)
+            assert rows.numel() == m and torch.equal(a.embedding[rows], new[1])
+            after = pipeline.render_rays(a, *args, precision=ops.PRECISION_BF16)
+            b = mk(a.xyz.clone(), a.embedding.clone(), a.color.clone(), a.dirs.clone(), a.conf.clone())
+            b.alive = a.alive.clone()
+            fresh = pipeline.render_rays(b, *args, precision=ops.PRECISION_BF16)
+            assert torch.equal(after.ray_color, fresh.ray_color) and torch.equal(after.ray_mask, fresh.ray_mask)
+            uncached = pipeline.render_rays(a, *args, precision=ops.PRECISION_BF16, use_point_cache=False)
+            assert torch.equal(after.ray_color, uncached.ray_color), "incrementally updated per-point tables differ from tables rebuilt in the call"
+        survivors = a.alive[:n_points].clone()
+        survivors[rows[rows < n_points]] = False
+        survivors &= (a.embedding[:n_points] == emb0).all(-1)
+        assert int(survivors.sum()) > 0.5 * n_points                                      # most rows never moved
+        assert a.xyz.shape[0] > n_points and not torch.equal(after.ray_color, before.ray_color)
+        assert int((~a.alive).sum()) == 0 or float(a.xyz[~a.alive].min()) == pipeline.RenderScene.HOLE
