@@ -690,7 +690,7 @@ def strong_scaling_leg(device, rank, world, dist, precision, args):
             return sdist.gather_frame(part.ray_color, idx_d, R, tile=256), part
         return one, R
 
-    def measure(one, n=3, warm=2):
+    def measure(one, n=3, warm=4):          # (the allocator needs a few frames of a new shape to settle: the 2nd frame still takes 3x)
         for _ in range(warm):
             one()
         torch.cuda.synchronize()

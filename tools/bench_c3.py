@@ -21,7 +21,13 @@ def main():
                                  [P[k + ".bias"] for k in names], ops.agg_cfg(), pipeline.query_options(**synth.C3_QUERY), device=dev)
     campos, rot = torch.from_numpy(s.campos).to(dev), torch.from_numpy(s.camrotc2w).to(dev)
     n = int(s.raydir.shape[0] * frac)
-    raydir = torch.from_numpy(s.raydir)[:n].to(dev)
+    if len(sys.argv) > 2:        # emulate rank 0 of `world` ranks: tiles of 256 rays dealt round-robin
+        from sgnerf_b200 import dist as sdist
+        idx = sdist.shard_rays(s.raydir.shape[0], 0, int(sys.argv[2]), tile=256)
+        raydir = torch.from_numpy(s.raydir)[idx].to(dev).contiguous()
+        n = raydir.shape[0]
+    else:
+        raydir = torch.from_numpy(s.raydir)[:n].to(dev)
     bg = torch.ones(3, device=dev)
     with torch.no_grad():
         for _ in range(2):
