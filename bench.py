@@ -38,8 +38,10 @@ def load_peaks():
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (agg_tuple_tc_kernel), per launch, from the committed
-    ncu --set full summary (profiles/r1d_ncu_full_all_kernels.txt)."""
-    path = os.path.join(ROOT, "profiles", "r1d_ncu_full_all_kernels.txt")
+    ncu --set full summary (profiles/r2_ncu_full_frame_kernels.txt, else round 1's profiles/r1d_ncu_full_all_kernels.txt)."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_frame_kernels.txt")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1d_ncu_full_all_kernels.txt")
     if not os.path.exists(path):
         return None
     tot, scale, inside = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}, False
@@ -315,8 +317,8 @@ def run_ours(args):
             "peak_GBps": peaks["hbm"],
             "query": {"kernels": "march_kernel + knn_kernel (sgn_query)", "ms": query_ms, "algorithmic_bytes": int(query_bytes),
                       "achieved_GBps": query_bytes / (query_ms * 1e-3) / 1e9, "frac": query_bytes / (query_ms * 1e-3) / 1e9 / peaks["hbm"],
-                      "note": "bound by instruction issue (march) and dependent L2/HBM reads (knn), not by bytes: see DESIGN.md 4.2"},
-            "frame_tail": {"kernels": "render_composite_kernel (step sizes + compositing + fill_invalid)", "ms": tail_ms,
+                      "note": "per-ray brick DDA + warp-parallel exact tests (march), prebuilt per-voxel neighbour lists + work-sorted samples (knn); both bound by instruction issue and L2 latency, not by bytes: DESIGN.md 4.2"},
+            "frame_tail": {"kernels": "render_composite_rows_kernel (step sizes + compositing + fill_invalid + depth, one thread per ray, dense depth array)", "ms": tail_ms,
                            "algorithmic_bytes": int(tail_bytes), "achieved_GBps": tail_bytes / (tail_ms * 1e-3) / 1e9,
                            "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / peaks["hbm"]}},
     }
