@@ -346,28 +346,40 @@ def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
         campos, rot = torch.from_numpy(s.campos).to(device), torch.from_numpy(s.camrotc2w).to(device)
         gen = torch.Generator(device=device).manual_seed(100 + rank)
         ms = None
+        def run(ts_, steps_):
+            def one():
+                pix = torch.randint(0, all_rays.shape[0], (n,), device=device, generator=gen)
+                ts_.set_inputs(campos, rot, all_rays[pix], torch.rand(n, 3, device=device, generator=gen), ts_.jittered_t(0.3, gen))
+                ts_.step()
+            for _ in range(3):
+                one()
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps_):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps_
+
         for mode in ("cuda graph", "eager"):
             try:
                 ts = train.TrainStep(sc, n, s.near, s.far, bg, precision=ops.PRECISION_TF32, use_graph=mode == "cuda graph")
-
-                def one():
-                    pix = torch.randint(0, all_rays.shape[0], (n,), device=device, generator=gen)
-                    ts.set_inputs(campos, rot, all_rays[pix], torch.rand(n, 3, device=device, generator=gen), ts.jittered_t(0.3, gen))
-                    ts.step()
-                for _ in range(3):
-                    one()
-                torch.cuda.synchronize()
-                if dist is not None:
-                    dist.barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(steps):
-                    one()
-                e1.record()
-                torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / steps
+                ms = run(ts, steps)
                 info.update(mode=mode, loss=float(ts.loss), rays_hit_last_step=float(ts.n_hit),
-                            allreduce_bytes_per_step=(sum(p.numel() for p in ts.params) * 4 if world > 1 else 0))
+                            allreduce_bytes_per_step=(int(ts.flat_grad.numel()) * 4 if world > 1 else 0))
+                if world > 1:
+                    # the same step without the exchange, in the same run on every rank: what the all-reduce costs at this N
+                    sc2 = pipeline.RenderScene(scene.xyz, scene.embedding.clone(), scene.color.clone(), scene.dirs.clone(), scene.conf.clone(),
+                                               [w.clone() for w in scene.weights], [b.clone() for b in scene.biases], scene.agg_cfg, scene.qopt, device=device)
+                    sc2._grid, sc2._hp = scene._grid, scene._hp
+                    ms_local = run(train.TrainStep(sc2, n, s.near, s.far, bg, precision=ops.PRECISION_TF32, use_graph=mode == "cuda graph", local_only=True), steps)
+                    sc2._grid = None
+                    tl = torch.tensor([ms_local], device=device, dtype=torch.float64)
+                    dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+                    info["ms_without_exchange"] = float(tl[0])
                 break
             except Exception as e:                                       # e.g. a collective that cannot be captured: launch kernel by kernel
                 info["graph_error"] = repr(e)[:200]
@@ -379,6 +391,8 @@ def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
         info.update(ms=ms, rays_per_s=world * n / (ms * 1e-3), steps=steps)
+        if "ms_without_exchange" in info:
+            info["step_vs_step_without_exchange"] = ms / info["ms_without_exchange"]
     except Exception as e:
         info["error"] = repr(e)[:300]
     return info

@@ -284,6 +284,33 @@ int sgn_probe_outputs(const float* opacity /*[R,SR]*/, const float* sample_loc_w
                       float* shading_avg_conf, float* shading_avg_embedding, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Perspective-frustum querier (--wcoord_query 0).  Replaces get_occ_vox / near_vox_full / insert_vox_points /
+ * query_neigh_along_ray_layered (NN > 0) / query_rand_along_ray (NN <= 0) and the torch glue of query_grid_point_index
+ * (models/neural_points/query_point_indices.py:263-782) for all R rays of one camera in one call, uncompacted: row r of the outputs
+ * belongs to input ray r (the reference keeps the rays with ray_mask > 0, :688).  The grid is in the camera's perspective coordinates
+ * and is rebuilt per call.  Not reproduced: the reference's int8 overflow (> 127 selected voxels in one pixel column, :696) and a max_o
+ * smaller than a column's selected-voxel count (lists are built for every voxel that holds a point).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float shift[3];          /* ranges[:3]                                                         (:604) */
+    float vsize[3];          /* scaled_vsize = vsize * vscale                                      (:66)  */
+    int32_t dim[3];          /* scaled_vdim                                                        (:65)  */
+    int32_t vscale[3];
+    int32_t kernel_size[3];
+    int32_t query_size[3];
+    float ray_vsize[3];      /* scaled_vsize / vscale                                              (:711) */
+    int32_t P, SR, K, NN, inverse;
+    float radius2, depth2;   /* radius_limit^2, depth_limit^2                                      (:749-750) */
+    uint64_t seconds_insert; /* time.time() at :713 (P-cap reservoir, seed = index + seconds)              */
+    uint64_t seconds_query;  /* time.time() at :737 (query_rand_along_ray)                                  */
+} SgnPersCfg;
+int sgn_pers_query_bytes(int64_t N, int64_t R, const SgnPersCfg* cfg, size_t* bytes);
+/* xyz_pers [N,3] = (x/z, y/z, z) of every point (NeuralPoints.w2pers); pixel_idx int32 [R,2].
+ * Outputs: sample_pidx int32 [R,SR,K] (-1 = empty), sample_loc f32 [R,SR,3] (perspective coordinates, :452-463), ray_mask int8 [R]. */
+int sgn_pers_query(const float* xyz_pers, int64_t N, const int32_t* pixel_idx, int64_t R, const SgnPersCfg* cfg, void* workspace,
+                   size_t workspace_bytes, int32_t* sample_pidx, float* sample_loc, int8_t* ray_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Voxel-grid helpers next to the render path.
  * ---------------------------------------------------------------------------------------------- */
 /* Point-cloud initialisation, construct_vox_points_closest (models/mvs/mvs_utils.py:536-561; run/train_ft.py:141, :715): one point per

@@ -20,15 +20,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 REF_ROOT = os.environ.get("SGN_REFERENCE_ROOT", "/root/reference")
 REF_FILE = os.path.join(REF_ROOT, "models", "neural_points", "query_point_indices_worldcoords.py")
+# the perspective-frustum querier (--wcoord_query 0): the same recipe over query_point_indices.py:130-600 and ref_launcher_pers.inc
+REF_FILE_PERS = os.path.join(REF_ROOT, "models", "neural_points", "query_point_indices.py")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
-def so_path(K=8):
-    return os.path.join(OUT, f"libref_query_K{K}.so")
+def so_path(K=8, pers=False):
+    return os.path.join(OUT, f"libref_query{'_pers' if pers else ''}_K{K}.so")
 
 
-def extract_source(K):
-    text = open(REF_FILE, encoding="utf-8").read()
+def extract_source(K, pers=False):
+    text = open(REF_FILE_PERS if pers else REF_FILE, encoding="utf-8").read()
     start = text.index("SourceModule(")
     end = text.index('""", no_extern_c=True)', start)
     body = text[start:end]
@@ -40,20 +42,21 @@ def extract_source(K):
     return body
 
 
-def build(K=8, force=False, keep_sass=False):
+def build(K=8, force=False, keep_sass=False, pers=False):
     """Returns the .so path, or None when the reference tree is not present and nothing was prebuilt."""
-    target = so_path(K)
-    if not os.path.exists(REF_FILE):
+    target = so_path(K, pers)
+    ref_file = REF_FILE_PERS if pers else REF_FILE
+    if not os.path.exists(ref_file):
         return target if os.path.exists(target) else None
-    launcher = os.path.join(HERE, "ref_launcher.inc")
+    launcher = os.path.join(HERE, "ref_launcher_pers.inc" if pers else "ref_launcher.inc")
     if (not force and os.path.exists(target)
-            and os.path.getmtime(target) >= max(os.path.getmtime(REF_FILE), os.path.getmtime(launcher))):
+            and os.path.getmtime(target) >= max(os.path.getmtime(ref_file), os.path.getmtime(launcher))):
         return target
     os.makedirs(OUT, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
         cu = os.path.join(tmp, "ref_query.cu")
         with open(cu, "w", encoding="utf-8") as f:
-            f.write(extract_source(K))
+            f.write(extract_source(K, pers))
             f.write("\n")
             f.write(open(launcher).read())
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-shared", "-Xcompiler", "-fPIC",
@@ -61,10 +64,11 @@ def build(K=8, force=False, keep_sass=False):
         subprocess.check_call(cmd)
         if keep_sass:
             sass = subprocess.check_output(["cuobjdump", "-sass", target]).decode()
-            open(os.path.join(OUT, f"ref_query_K{K}.sass"), "w").write(sass)
+            open(os.path.join(OUT, f"ref_query{'_pers' if pers else ''}_K{K}.sass"), "w").write(sass)
     return target
 
 
 if __name__ == "__main__":
-    p = build(int(sys.argv[1]) if len(sys.argv) > 1 else 8, force=True, keep_sass=True)
-    print(p)
+    k = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    print(build(k, force=True, keep_sass=True))
+    print(build(k, force=True, keep_sass=True, pers=True))

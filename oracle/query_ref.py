@@ -32,10 +32,10 @@ _lib = None
 
 def build(force=False):
     """gcc the C restatement.  -ffp-contract=off: FMAs are explicit in the source."""
-    src = os.path.join(_HERE, "query_ref.c")
+    srcs = [os.path.join(_HERE, "query_ref.c"), os.path.join(_HERE, "query_pers_ref.c")]
     os.makedirs(_BUILD, exist_ok=True)
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", _SO] + srcs + ["-lm"])
     return _SO
 
 

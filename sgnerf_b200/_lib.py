@@ -22,6 +22,12 @@ class SgnGridCfg(C.Structure):
                 ("P", C.c_int32), ("max_o", C.c_int32), ("seconds_claim", c_u64), ("seconds_fill", c_u64)]
 
 
+class SgnPersCfg(C.Structure):
+    _fields_ = [("shift", c_f32 * 3), ("vsize", c_f32 * 3), ("dim", C.c_int32 * 3), ("vscale", C.c_int32 * 3), ("kernel_size", C.c_int32 * 3),
+                ("query_size", C.c_int32 * 3), ("ray_vsize", c_f32 * 3), ("P", C.c_int32), ("SR", C.c_int32), ("K", C.c_int32), ("NN", C.c_int32),
+                ("inverse", C.c_int32), ("radius2", c_f32), ("depth2", c_f32), ("seconds_insert", c_u64), ("seconds_query", c_u64)]
+
+
 class SgnAggCfg(C.Structure):
     _fields_ = [("feat_dim", C.c_int32), ("num_feat_freqs", C.c_int32), ("dist_xyz_freq", C.c_int32),
                 ("num_viewdir_freqs", C.c_int32), ("width", C.c_int32), ("n_block1", C.c_int32),
@@ -89,6 +95,8 @@ SIGNATURES = {
     "sgn_probe_outputs": (c_int, [c_void, c_void, c_void, c_void, c_void, c_void, C.POINTER(SgnPointTables), c_int, c_i64, c_int, c_int,
                                   c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_void]),
     "sgn_fill_invalid": (c_int, [c_void, c_void, c_i64, c_int, c_void, c_void, c_void, c_void]),
+    "sgn_pers_query_bytes": (c_int, [c_i64, c_i64, C.POINTER(SgnPersCfg), C.POINTER(c_size)]),
+    "sgn_pers_query": (c_int, [c_void, c_i64, c_void, c_i64, C.POINTER(SgnPersCfg), c_void, c_size, c_void, c_void, c_void, c_void]),
     "sgn_voxel_downsample_bytes": (c_int, [c_i64, C.POINTER(c_size)]),
     "sgn_voxel_downsample": (c_int, [c_void, c_i64, C.POINTER(c_f32), C.POINTER(c_f32), c_int, c_void, c_size, c_void, c_void, c_void, c_void, c_void]),
     "sgn_query_vox_grid": (c_int, [c_void, c_i64, c_void, c_int, C.POINTER(c_f32), c_f32, c_void, c_void]),

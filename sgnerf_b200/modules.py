@@ -149,8 +149,6 @@ class lighting_fast_querier:
     def __init__(self, device, opt):
         self.device, self.opt = device, opt
         self._grid, self._grid_key, self._hp = None, None, None
-        if _opt(opt, "wcoord_query", 1) <= 0:
-            raise NotImplementedError("sgnerf_b200: only the world-coordinate querier (--wcoord_query 1) is built")
         if _opt(opt, "inverse", 0) > 0:
             raise NotImplementedError("sgnerf_b200: --inverse ray generation is not built")
 
@@ -221,6 +219,76 @@ class lighting_fast_querier:
         return (sample_pidx, sample_loc, sample_loc_w, sample_ray_dirs, rmask[None], np.asarray(hp.vsize, dtype=np.float32), hp.ranges)
 
 
+class lighting_fast_querier_p:
+    """Perspective-frustum querier (--wcoord_query 0): lighting_fast_querier of models/neural_points/query_point_indices.py:28-128.
+    The grid lives in the camera's perspective coordinates, so every call rebuilds it -- for all rays of the call at once
+    (ops.pers_query -> sgn_pers_query).  Like the reference's, query_points takes no semantic arguments (:76)."""
+
+    def __init__(self, device, opt):
+        self.device, self.opt = device, opt
+        self.inverse = _opt(opt, "inverse", 0)
+
+    def clean_up(self):
+        pass
+
+    def invalidate(self):
+        pass
+
+    _seconds = lighting_fast_querier._seconds
+
+    def get_hyperparameters(self, h, w, intrinsic, near_depth, far_depth):
+        o = self.opt
+        return ops.pers_hyperparameters(h, w, intrinsic, near_depth, far_depth, o.z_depth_dim, o.vscale, o.radius_limit_scale,
+                                        o.depth_limit_scale, self.inverse)
+
+    @staticmethod
+    def pers2w(point_xyz_pers, camrotc2w, campos):
+        """:95-107 -- also the (normalised) ray direction of every sample."""
+        xyz_c = torch.stack([point_xyz_pers[..., 0] * point_xyz_pers[..., 2], point_xyz_pers[..., 1] * point_xyz_pers[..., 2],
+                             point_xyz_pers[..., 2]], dim=-1)
+        xyz_w_shift = torch.sum(xyz_c[..., None, :] * camrotc2w, dim=-1)
+        ray_dirs = xyz_w_shift / (torch.linalg.norm(xyz_w_shift, dim=-1, keepdims=True) + 1e-7)
+        return xyz_w_shift + campos[:, None, :], ray_dirs
+
+    @staticmethod
+    def gaussian(input, vsize):                                            # :109-113
+        B, R, SR, _ = input.shape
+        jitters = torch.normal(mean=torch.zeros([B, R, SR], dtype=torch.float32, device=input.device),
+                               std=torch.full([B, R, SR], vsize[2] / 4, dtype=torch.float32, device=input.device))
+        input[..., 2] = input[..., 2] + torch.clamp(jitters, min=-vsize[2] / 2, max=vsize[2] / 2)
+        return input
+
+    @staticmethod
+    def uniform(input, vsize):                                             # :115-119
+        B, R, SR, _ = input.shape
+        jitters = torch.rand([B, R, SR], dtype=torch.float32, device=input.device) - 0.5
+        input[..., 2] = input[..., 2] + jitters * vsize[2]
+        return input
+
+    @staticmethod
+    def passfunc(input, vsize):                                            # :121-122
+        return input
+
+    def query_uncompacted(self, pixel_idx_tensor, point_xyz_pers_tensor, h, w, intrinsic, near_depth, far_depth):
+        """Rows per input ray, no host synchronisation: sample_pidx [R,SR,K], sample_loc (perspective) [R,SR,3], ray_mask int8 [R], hp."""
+        o = self.opt
+        hp = self.get_hyperparameters(int(h), int(w), np.asarray(intrinsic), np.asarray(near_depth).item(), np.asarray(far_depth).item())
+        pidx, loc, mask = ops.pers_query(point_xyz_pers_tensor.reshape(-1, 3), pixel_idx_tensor.reshape(-1, 2), hp, o.kernel_size, o.query_size,
+                                         o.SR, o.K, o.P, NN=o.NN, inverse=self.inverse, seconds=(self._seconds(), self._seconds()))
+        return pidx, loc, mask, hp
+
+    def query_points(self, pixel_idx_tensor, point_xyz_pers_tensor, point_xyz_w_tensor, actual_numpoints_tensor, h, w, intrinsic,
+                     near_depth, far_depth, ray_dirs_tensor, cam_pos_tensor, cam_rot_tensor):
+        pidx, loc, mask, hp = self.query_uncompacted(pixel_idx_tensor, point_xyz_pers_tensor, h, w, intrinsic, near_depth, far_depth)
+        sel = mask > 0                                            # the reference keeps the rays whose pixel column is occupied (:688)
+        sample_pidx, sample_loc = pidx[sel][None], loc[sel][None]
+        if _opt(self.opt, "is_train", 0):
+            sample_loc = getattr(self, _opt(self.opt, "shpnt_jitter", "passfunc"))(sample_loc, hp.vsize)
+        B, R = 1, sample_loc.shape[1]
+        loc_w, dirs = self.pers2w(sample_loc.reshape(1, -1, 3), cam_rot_tensor, cam_pos_tensor)
+        return (sample_pidx, sample_loc, loc_w.reshape(B, R, self.opt.SR, 3), dirs.reshape(B, R, self.opt.SR, 3), mask[None], hp.vsize, hp.ranges)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # NeuralPoints
 # ---------------------------------------------------------------------------------------------------------
@@ -242,7 +310,9 @@ class NeuralPoints(nn.Module):
         # neural_points.py:425: query_size falls back to kernel_size when left at its (0, 0, 0) default
         if hasattr(opt, "query_size") and hasattr(opt, "kernel_size") and opt.query_size[0] == 0:
             opt.query_size = opt.kernel_size
-        self.querier = lighting_fast_querier(device, opt)
+        # neural_points.py:426-427
+        self.lighting_fast_querier = lighting_fast_querier if _opt(opt, "wcoord_query", 1) > 0 else lighting_fast_querier_p
+        self.querier = self.lighting_fast_querier(device, opt)
         self.xyz, self.points_embeding = None, None
         if _opt(opt, "load_points", 1) == 1 and not feedforward:
             saved = None
@@ -406,18 +476,34 @@ class NeuralPoints(nn.Module):
         if _opt(self.opt, "semantic_guidance", 0) == 1:
             kw = dict(points_label_tensor=self.points_label, points_label_prob_tensor=self.points_label_prob,
                       ray_label_tensor=inputs["pixel_label"])
-        pidx_u, loc_w_u, _, rmask, hp = self.querier.query_uncompacted(self.xyz, near, far, raydir, campos, **kw)
-        sel = rmask > 0                                          # host sync, as in the reference (:946); the fused frame path avoids it
-        sample_pidx = pidx_u[sel][None].contiguous()
-        sample_loc_w = loc_w_u[sel][None].contiguous()
+        pers = isinstance(self.querier, lighting_fast_querier_p)
+        if pers:
+            # neural_points.py:760-792 with the perspective querier: per-sample ray directions from pers2w, sample_loc straight from the kernel
+            xyz_pers = self.w2pers(self.xyz, camrotc2w, campos)
+            sample_pidx, sample_loc_p, sample_loc_w, sample_ray_dirs_p, rmask1, vsize_p, _ = self.querier.query_points(
+                inputs["pixel_idx"].to(torch.int32), xyz_pers, self.xyz[None, ...], None, int(torch.max(inputs["h"])), int(torch.max(inputs["w"])),
+                inputs["intrinsic"].cpu().numpy()[0], near, far, raydir, campos, camrotc2w, **kw)
+            rmask, sel = rmask1[0], rmask1[0] > 0
+            sample_pidx, sample_loc_w = sample_pidx.contiguous(), sample_loc_w.contiguous()
+            hp = SimpleNamespace(vsize=vsize_p)
+        else:
+            pidx_u, loc_w_u, _, rmask, hp = self.querier.query_uncompacted(self.xyz, near, far, raydir, campos, **kw)
+            sel = rmask > 0                                      # host sync, as in the reference (:946); the fused frame path avoids it
+            sample_pidx = pidx_u[sel][None].contiguous()
+            sample_loc_w = loc_w_u[sel][None].contiguous()
         if vox_query:
             # neural_points.py:799-803: the 8 corners of the construction-grid cell of every sample replace the K-NN result
             sample_pidx = ops.query_vox_grid(sample_loc_w, self.full_grid_idx, self.space_min, float(self.grid_vox_sz),
                                              self.opt.grid_res).to(torch.int32) if sample_pidx.shape[1] > 0 else \
                 torch.zeros(1, 0, self.opt.SR, 8, device=sample_pidx.device, dtype=torch.int32)
-        rd = raydir.reshape(-1, 3)[sel]
-        sample_ray_dirs = rd[None, :, None, :].expand(-1, -1, self.opt.SR, -1).contiguous()
-        sample_loc = lighting_fast_querier.w2pers(sample_loc_w, camrotc2w, campos)
+        if pers:
+            # all samples of a ray sit on the line through its sub-pixel centre: one direction per ray for the fused aggregator
+            sample_ray_dirs, sample_loc = sample_ray_dirs_p, sample_loc_p
+            rd = sample_ray_dirs_p[0, :, 0, :]
+        else:
+            rd = raydir.reshape(-1, 3)[sel]
+            sample_ray_dirs = rd[None, :, None, :].expand(-1, -1, self.opt.SR, -1).contiguous()
+            sample_loc = lighting_fast_querier.w2pers(sample_loc_w, camrotc2w, campos)
         ctx = SimpleNamespace(neural_points=self, pidx=sample_pidx, loc_w=sample_loc_w, raydir=rd.contiguous(), campos=campos.reshape(3),
                               camrotc2w=camrotc2w.reshape(3, 3), vsize=hp.vsize)
         xyz_tab = self.xyz[None, ...]

@@ -201,6 +201,57 @@ def query_vox_grid(sample_loc_w, full_grid_idx, space_min, grid_vox_sz, grid_res
     return out
 
 
+def pers_hyperparameters(h, w, intrinsic, near_depth, far_depth, z_depth_dim, vscale, radius_limit_scale, depth_limit_scale, inverse=0):
+    """lighting_fast_querier.get_hyperparameters of the perspective querier (models/neural_points/query_point_indices.py:48-73): host numpy
+    arithmetic in the reference's order and dtypes (float32 arrays built from python / float64 scalars)."""
+    from types import SimpleNamespace
+    intrinsic = np.asarray(intrinsic)
+    x_rl, x_rh = -intrinsic[0, 2] / intrinsic[0, 0], (w - intrinsic[0, 2]) / intrinsic[0, 0]
+    y_rl, y_rh = -intrinsic[1, 2] / intrinsic[1, 1], (h - intrinsic[1, 2]) / intrinsic[1, 1]
+    z_r = (far_depth - near_depth) if inverse == 0 else (1.0 / near_depth - 1.0 / far_depth)
+    if inverse == 0:
+        ranges = np.array([x_rl, y_rl, near_depth, x_rh, y_rh, far_depth], dtype=np.float32)
+    else:
+        ranges = np.array([x_rl, y_rl, 1.0 / far_depth, x_rh, y_rh, 1.0 / near_depth], dtype=np.float32)
+    vdim = np.array([w, h, z_depth_dim], dtype=np.int32)
+    vsize = np.array([(x_rh - x_rl) / vdim[0], (y_rh - y_rl) / vdim[1], z_r / vdim[2]], dtype=np.float32)
+    vscale = np.array(vscale, dtype=np.int32)
+    scaled_vdim = np.ceil(vdim / vscale).astype(np.int32)
+    scaled_vsize = (vsize * vscale).astype(np.float32)
+    radius_limit = np.float32(radius_limit_scale * max(vsize[0], vsize[1]))
+    depth_limit = np.float32(depth_limit_scale * vsize[2])
+    return SimpleNamespace(radius_limit=radius_limit, depth_limit=depth_limit, ranges=ranges, vsize=vsize, vdim=vdim, scaled_vsize=scaled_vsize,
+                           scaled_vdim=scaled_vdim, vscale=vscale, ray_vsize=(scaled_vsize / vscale).astype(np.float32),          # :711
+                           radius2=np.float32(radius_limit ** 2), depth2=np.float32(depth_limit ** 2))                            # :749-750
+
+
+def pers_query(xyz_pers, pixel_idx, hp, kernel_size, query_size, SR, K, P, NN=2, inverse=0, seconds=(0, 0)):
+    """query_grid_point_index of the perspective querier (query_point_indices.py:600-782) for all rays of one camera, rows per input ray.
+    xyz_pers f32 [N,3] perspective coordinates, pixel_idx int [R,2].  Returns sample_pidx int32 [R,SR,K], sample_loc f32 [R,SR,3] (perspective),
+    ray_mask int8 [R]."""
+    xyz = _dev(xyz_pers.reshape(-1, 3), torch.float32, "xyz_pers")
+    pix = _dev(pixel_idx.reshape(-1, 2).to(torch.int32), torch.int32, "pixel_idx")
+    N, R = xyz.shape[0], pix.shape[0]
+    cfg = _lib.SgnPersCfg()
+    for name, src in (("shift", hp.ranges[:3]), ("vsize", hp.scaled_vsize), ("ray_vsize", hp.ray_vsize)):
+        for i in range(3):
+            getattr(cfg, name)[i] = float(src[i])
+    for name, src in (("dim", hp.scaled_vdim), ("vscale", hp.vscale), ("kernel_size", kernel_size), ("query_size", query_size)):
+        for i in range(3):
+            getattr(cfg, name)[i] = int(src[i])
+    cfg.P, cfg.SR, cfg.K, cfg.NN, cfg.inverse = int(P), int(SR), int(K), int(NN), int(inverse)
+    cfg.radius2, cfg.depth2 = float(hp.radius2), float(hp.depth2)
+    cfg.seconds_insert, cfg.seconds_query = int(seconds[0]), int(seconds[1])
+    nbytes = C.c_size_t()
+    _lib.call("sgn_pers_query_bytes", N, R, C.byref(cfg), C.byref(nbytes))
+    ws = _workspace(nbytes.value, xyz.device)
+    pidx = torch.empty((R, SR, K), dtype=torch.int32, device=xyz.device)
+    loc = torch.empty((R, SR, 3), dtype=torch.float32, device=xyz.device)
+    mask = torch.empty((R,), dtype=torch.int8, device=xyz.device)
+    _lib.call("sgn_pers_query", _ptr(xyz), N, _ptr(pix), R, C.byref(cfg), _ptr(ws), nbytes.value, _ptr(pidx), _ptr(loc), _ptr(mask), _stream())
+    return pidx, loc, mask
+
+
 # ---------------------------------------------------------------------------------------------------------
 # compositing
 # ---------------------------------------------------------------------------------------------------------

@@ -32,13 +32,14 @@ from . import ops, pipeline
 
 
 class _StepBase:
-    def __init__(self, scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon):
+    def __init__(self, scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon,
+                 local_only=False):
         self.scene, self.n_rays, self.near, self.far = scene, int(n_rays), float(near), float(far)
         self.precision, self.conf_w, self.group = precision, float(conf_loss_weight), group
         self.zero_eps = float(zero_epsilon)             # --zero_epsilon of the reference (base_rendering_model.py:119, default 1e-3)
         self.lr, self.plr = float(lr), float(plr)
         dev = scene.xyz.device
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (dist.is_initialized() and not local_only) else 1     # local_only: no exchange (timing aid)
         q = scene.qopt
         # static inputs of the graph: the caller fills them (set_inputs) before every step
         self.raydir = torch.zeros(self.n_rays, 3, device=dev)
@@ -92,9 +93,10 @@ class TrainStep(_StepBase):
     state and set kernel attributes, and they are real optimiser steps -- then captures the step and replays the capture from then on."""
 
     def __init__(self, scene, n_rays, near, far, bg_color, lr=5e-4, plr=2e-3, conf_loss_weight=1e-4, precision=ops.PRECISION_TF32,
-                 use_graph=True, train_dir=True, group=None, zero_epsilon=1e-3):
+                 use_graph=True, train_dir=True, group=None, zero_epsilon=1e-3, local_only=False):
         """scene: pipeline.RenderScene (its tensors are updated in place).  n_rays: rays per step on this rank (fixed)."""
-        super().__init__(scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon)
+        super().__init__(scene, n_rays, near, far, bg_color, lr, plr, conf_loss_weight, precision, use_graph, train_dir, group, zero_epsilon,
+                         local_only=local_only)
         if precision == ops.PRECISION_BF16:
             raise ValueError("TrainStep runs the fp32 or tf32 path; the bf16 tensor-core path is forward-only")
         dev = scene.xyz.device

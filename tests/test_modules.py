@@ -55,7 +55,10 @@ def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         modules.PointAggregator(make_opt(agg_distance_kernel="quadric"))
     with pytest.raises(NotImplementedError):
-        modules.lighting_fast_querier("cpu", make_opt(wcoord_query=0))
+        modules.lighting_fast_querier("cpu", make_opt(inverse=1))
+    # --wcoord_query picks the querier class, as at neural_points.py:426
+    assert modules.NeuralPoints(32, 0, make_opt(wcoord_query=0, load_points=0), "cpu").lighting_fast_querier is modules.lighting_fast_querier_p
+    assert modules.NeuralPoints(32, 0, make_opt(wcoord_query=1, load_points=0), "cpu").lighting_fast_querier is modules.lighting_fast_querier
     agg = modules.PointAggregator(make_opt())
     with pytest.raises(TypeError):            # dense tensors are not accepted: no PyTorch fallback
         agg(*([torch.zeros(1)] * 14))
