@@ -73,7 +73,8 @@ int orc_pers_query(const float* xyz, int N, const int* pixel_idx, int R, const f
                 }
     }
     /* ---- near_vox_full, P:313-365: per ray its column's mask; the first ray of a column lists its first SR occupied depths and selects
-     * (loc = 1) the point voxels in the kernel_size box around each of them ---- */
+     * (loc = 1) the point voxels in the query_size box around each of them (the launch at P:656-676 hands query_size_gpu to the
+     * kernel's `kernel_size` parameter) ---- */
     for (int r = 0; r < R; r++) {
         int vx = pixel_idx[2 * r] / vscale[0], vy = pixel_idx[2 * r + 1] / vscale[1];
         int64_t col = (int64_t)vx * Y + vy;
@@ -85,9 +86,9 @@ int orc_pers_query(const float* xyz, int N, const int* pixel_idx, int R, const f
         for (int d = nid; d <= fid; d++) {
             if (!coor_occ[col * Z + d]) continue;
             coorz[col * SR + counter] = (short)d;
-            for (int x = imax(0, vx - kernel_size[0] / 2); x < imin(X, vx + (kernel_size[0] + 1) / 2); x++)
-                for (int y = imax(0, vy - kernel_size[1] / 2); y < imin(Y, vy + (kernel_size[1] + 1) / 2); y++)
-                    for (int zz = imax(0, d - kernel_size[2] / 2); zz < imin(Z, d + (kernel_size[2] + 1) / 2); zz++) {
+            for (int x = imax(0, vx - query_size[0] / 2); x < imin(X, vx + (query_size[0] + 1) / 2); x++)
+                for (int y = imax(0, vy - query_size[1] / 2); y < imin(Y, vy + (query_size[1] + 1) / 2); y++)
+                    for (int zz = imax(0, d - query_size[2] / 2); zz < imin(Z, d + (query_size[2] + 1) / 2); zz++) {
                         int64_t cj = ((int64_t)x * Y + y) * Z + zz;
                         if (loc[cj] < 0) loc[cj] = 1;
                     }

@@ -9,9 +9,12 @@
 // (P:313-365); (3) per voxel the list of its points -- with the coordinates TRUNCATED, not floored, at insertion (P:381-386), first P in
 // point order, then the reservoir of P:399-405; (4) per sample the K nearest points of the kernel_size block by the layered walk of
 // P:493-590 (or the random pick of P:411-490 for NN <= 0).  The reference builds lists only for the voxels "selected" by the pixel
-// columns of the call (P:345-355, :695-696); every voxel a sample's walk can visit is selected by that sample's own column, so building
-// the lists of ALL point voxels gives the same neighbours.  Not reproduced (and excluded by the oracle, oracle/query_pers_ref.c): the int8
-// overflow of P:696 and a max_o smaller than a column's selected-voxel count.
+// columns of the call: the point voxels inside the QUERY_size box of a listed sample (P:345-355 -- the launch at :656-676 hands
+// query_size to that kernel -- and :695-696).  When the walk of (4) stays inside the query_size box, every voxel it can visit is selected
+// by the sample's own column and the lists of ALL point voxels give the same neighbours; otherwise (kernel_size larger than query_size:
+// the result then depends on which other rays are in the call) a selection pass marks the voxels exactly as the reference does.
+// Not reproduced (and excluded by the oracle, oracle/query_pers_ref.c): the int8 overflow of P:696 and a max_o smaller than a column's
+// selected-voxel count.
 //
 // B200 design: points are sorted by voxel with a stable radix sort (lists in point order without atomics), voxel -> list through a dense
 // int2 volume (15 M voxels at 640x480 / vscale 2 / D 400: 123 MB, rebuilt per camera), occupancy as a bit volume whose pixel columns are
@@ -141,6 +144,25 @@ __global__ void pers_sample_kernel(PersParams g, const int32_t* __restrict__ pix
     }
 }
 
+// P:345-355: the point voxels inside the query_size box of every listed sample become "selected".  One thread per (ray, sample).
+__global__ void pers_select_kernel(PersParams g, const int32_t* __restrict__ pixel_idx, int64_t R, const int32_t* __restrict__ coorz,
+                                   const uint32_t* __restrict__ pt_bits, uint32_t* sel_bits)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * g.SR) return;
+    const int d = coorz[idx];
+    if (d < 0) return;
+    const int64_t r = idx / g.SR;
+    const int vx = pixel_idx[2 * r] / g.scx, vy = pixel_idx[2 * r + 1] / g.scy;
+    for (int x = max(0, vx - g.qx / 2); x < min(g.X, vx + (g.qx + 1) / 2); x++)
+        for (int y = max(0, vy - g.qy / 2); y < min(g.Y, vy + (g.qy + 1) / 2); y++)
+            for (int z = max(0, d - g.qz / 2); z < min(g.Z, d + (g.qz + 1) / 2); z++) {
+                const int64_t c = pers_cell(g, x, y, z);
+                const uint32_t bit = 1u << (c & 31);
+                if ((pt_bits[c >> 5] & bit) && !(sel_bits[c >> 5] & bit)) atomicOr(sel_bits + (c >> 5), bit);
+            }
+}
+
 // P:493-590 (NN > 0) / P:411-490: one thread per (ray, sample)
 template <int KT>
 __global__ void pers_knn_kernel(PersParams g, const float* __restrict__ xyz, const int32_t* __restrict__ pixel_idx, int64_t R, const int32_t* __restrict__ coorz,
@@ -257,7 +279,7 @@ extern "C" int sgn_pers_query_bytes(int64_t N, int64_t R, const SgnPersCfg* cfg,
     SGN_CHECK_ARG(bytes != nullptr, "sgn_pers_query_bytes: bytes is NULL");
     const int64_t vol = (int64_t)cfg->dim[0] * cfg->dim[1] * cfg->dim[2], nwords = (vol + 31) / 32;
     const size_t n = (size_t)(N > 0 ? N : 1), r = (size_t)(R > 0 ? R : 1);
-    *bytes = align_up(pers_sort_bytes(N)) + 2 * align_up(4 * n) + 2 * align_up(4 * n) + 2 * align_up(4 * (size_t)nwords) + align_up(8 * (size_t)vol) +
+    *bytes = align_up(pers_sort_bytes(N)) + 2 * align_up(4 * n) + 2 * align_up(4 * n) + 3 * align_up(4 * (size_t)nwords) + align_up(8 * (size_t)vol) +
              align_up(4 * r * cfg->SR) + 2 * align_up(4 * (r + 1)) + align_up(4 * scan_partials_count(R));
     return SGN_OK;
 }
@@ -267,11 +289,11 @@ extern "C" int sgn_pers_query(const float* xyz_pers, int64_t N, const int32_t* p
 {
     int rc = pers_check(N, R, cfg);
     if (rc) return rc;
-    SGN_CHECK_ARG(xyz_pers && pixel_idx && sample_pidx && sample_loc && ray_mask, "sgn_pers_query: NULL argument");
+    if (R == 0) return SGN_OK;
+    SGN_CHECK_ARG((xyz_pers || N == 0) && pixel_idx && sample_pidx && sample_loc && ray_mask, "sgn_pers_query: NULL argument");
     size_t need;
     sgn_pers_query_bytes(N, R, cfg, &need);
     if (workspace_bytes < need || ((uintptr_t)workspace & 255)) { set_error("sgn_pers_query: workspace too small or misaligned (need %zu bytes)", need); return SGN_E_WORKSPACE; }
-    if (R == 0) return SGN_OK;
     auto st = (cudaStream_t)stream;
     PersParams g;
     g.sx = cfg->shift[0]; g.sy = cfg->shift[1]; g.sz = cfg->shift[2]; g.vx = cfg->vsize[0]; g.vy = cfg->vsize[1]; g.vz = cfg->vsize[2];
@@ -281,11 +303,11 @@ extern "C" int sgn_pers_query(const float* xyz_pers, int64_t N, const int32_t* p
     g.P = cfg->P; g.SR = cfg->SR; g.K = cfg->K; g.NN = cfg->NN; g.inverse = cfg->inverse; g.radius2 = cfg->radius2; g.depth2 = cfg->depth2;
     const int64_t vol = (int64_t)g.X * g.Y * g.Z, nwords = (vol + 31) / 32;
     Arena A(workspace, workspace_bytes);
-    const size_t sb = pers_sort_bytes(N);
+    size_t sb = pers_sort_bytes(N);
     void* sort_tmp = A.take<char>(sb);
     uint32_t* keys = A.take<uint32_t>(N > 0 ? N : 1); uint32_t* keys2 = A.take<uint32_t>(N > 0 ? N : 1);
     int32_t* vals = A.take<int32_t>(N > 0 ? N : 1); int32_t* vals2 = A.take<int32_t>(N > 0 ? N : 1);
-    uint32_t* pt_bits = A.take<uint32_t>(nwords); uint32_t* occ_bits = A.take<uint32_t>(nwords);
+    uint32_t* pt_bits = A.take<uint32_t>(nwords); uint32_t* occ_bits = A.take<uint32_t>(nwords); uint32_t* sel_bits = A.take<uint32_t>(nwords);
     int2* cell_list = A.take<int2>(vol);
     int32_t* coorz = A.take<int32_t>(R * cfg->SR);
     int32_t* flag = A.take<int32_t>(R + 1); int32_t* ray_rank = A.take<int32_t>(R + 1);
@@ -294,15 +316,30 @@ extern "C" int sgn_pers_query(const float* xyz_pers, int64_t N, const int32_t* p
     SGN_CUDA(cudaMemsetAsync(occ_bits, 0, 4 * (size_t)nwords, st));
     SGN_CUDA(cudaMemsetAsync(cell_list, 0, 8 * (size_t)vol, st));
     const int T = 256;
+    // does the neighbour walk stay inside the query_size box of its sample?  (box of size s: offsets -s/2 .. (s+1)/2-1)
+    bool inside = true;
+    for (int a = 0; a < 3; a++) {
+        const int ks = cfg->NN > 0 ? cfg->kernel_size[a == 2 ? 2 : 0] : cfg->kernel_size[a], qs = cfg->query_size[a];
+        const int lo = cfg->NN > 0 ? (ks + 1) / 2 - 1 : ks / 2, hi = (ks + 1) / 2 - 1;
+        inside = inside && lo <= qs / 2 && hi <= (qs + 1) / 2 - 1;
+    }
     if (N > 0) {
         launch(pers_point_kernel, cdiv(N, T), T, 0, st, xyz_pers, N, g, pt_bits);
         launch(pers_dilate_kernel, cdiv(nwords, T), T, 0, st, g, nwords, pt_bits, occ_bits);
-        launch(pers_key_kernel, cdiv(N, T), T, 0, st, xyz_pers, N, g, pt_bits, keys, vals);
-        ++g_launch_count;
-        SGN_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, const_cast<size_t&>(sb), keys, keys2, vals, vals2, (int)N, 0, 32, st));
-        launch(pers_list_kernel, cdiv(N, T), T, 0, st, keys2, vals2, N, g, cfg->seconds_insert, cell_list);
     }
     launch(pers_sample_kernel, cdiv(R, 128), 128, 0, st, g, pixel_idx, R, occ_bits, coorz, sample_loc, ray_mask);
+    const uint32_t* list_bits = pt_bits;
+    if (!inside && N > 0) {
+        SGN_CUDA(cudaMemsetAsync(sel_bits, 0, 4 * (size_t)nwords, st));
+        launch(pers_select_kernel, cdiv(R * cfg->SR, T), T, 0, st, g, pixel_idx, R, coorz, pt_bits, sel_bits);
+        list_bits = sel_bits;
+    }
+    if (N > 0) {
+        launch(pers_key_kernel, cdiv(N, T), T, 0, st, xyz_pers, N, g, list_bits, keys, vals);
+        ++g_launch_count;
+        SGN_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sb, keys, keys2, vals, vals2, (int)N, 0, 32, st));
+        launch(pers_list_kernel, cdiv(N, T), T, 0, st, keys2, vals2, N, g, cfg->seconds_insert, cell_list);
+    }
     launch(pers_ray_rank_kernel, cdiv(R, T), T, 0, st, ray_mask, R, flag);
     rc = exclusive_scan_i32(flag, ray_rank, R, partials, st);
     if (rc) return rc;

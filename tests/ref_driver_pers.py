@@ -38,6 +38,7 @@ def _chk(rc, what):
 def query_grid_point_index(L, pixel_idx, xyz_pers, opt, hp, seconds=(0, 0), max_o=None):
     """pixel_idx int32 [1,R,2] cuda, xyz_pers f32 [1,N,3] cuda.  Returns the reference's four outputs (compacted to the masked-in rays)."""
     dev = xyz_pers.device
+    xyz_pers = xyz_pers.reshape(1, -1, 3)
     B, N = 1, xyz_pers.shape[1]
     dim = [int(v) for v in hp.scaled_vdim]
     pixel_size, vol = dim[0] * dim[1], dim[0] * dim[1] * dim[2]

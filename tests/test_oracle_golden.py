@@ -127,3 +127,26 @@ def test_query_oracle_against_reference_kernel_vectors(golden_dir):
     touched = near(g["ref_slot0"]) | near(info.grid.occ_2_coor[0])
     same = (np.sort(op_, -1) == g["ref_pidx_sorted"]).all(-1)
     assert same[~touched].all() and (~touched).mean() > 0.95
+
+
+def test_perspective_query_oracle_against_reference_kernel_vectors(golden_dir):
+    """oracle/query_pers_ref.c against outputs of the REFERENCE's OWN perspective kernels (query_point_indices.py:263-590, compiled unchanged
+    into oracle/_ref/libref_query_pers_K8.so and run on a B200 by tests/test_gpu_pers_query.py, case "wide"): ray mask, sample positions
+    bit for bit, neighbours as per-sample sorted sets (the reference's list order follows its atomics)."""
+    import os
+    from oracle import query_pers_ref as qp
+    from sgnerf_b200 import synth
+    from tests import util
+    from tests.test_gpu_pers_query import CASES
+    g = np.load(os.path.join(golden_dir, "pers_reference_kernels_c0.npz"))
+    s = util.pers_scene(int(g["n_points"]), int(g["n_rays"]))
+    opt = qp.default_opt(max_o=127, P=int(g["P"]), **CASES["wide"])
+    hp = qp.get_hyperparameters(opt, s.height, s.width, synth.SCANNET_INTRINSIC, s.near, s.far)
+    o_pidx, o_loc, o_mask = qp.query_uncompacted(opt, hp, s.pixel_idx, s.xyz_pers)
+    assert np.array_equal(o_mask, g["ref_ray_mask"])
+    sel = o_mask > 0
+    rows = g["ray_rows"]
+    assert np.array_equal(o_loc[sel][rows].view(np.int32), g["ref_loc"].view(np.int32))
+    same = (np.sort(o_pidx[sel][rows], -1) == g["ref_pidx_sorted"]).all(-1)
+    assert (g["ref_pidx_sorted"] >= 0).sum() > 1000
+    assert (~same).mean() < 1e-3

@@ -89,3 +89,20 @@ def assert_grid_equal(grid, g):
     # per-slot lists, order included
     flat_ref = np.concatenate([g.occ_2_pnts[s, :ncap[s]] for s in np.nonzero(ncap)[0]]) if ncap.sum() else np.zeros(0, np.int32)
     assert np.array_equal(cand_idx[:start[-1]], flat_ref), "occ_2_pnts differs"
+
+
+def pers_scene(n_points, n_rays, seed=1234, full_patch=False):
+    """Scene C0 for the perspective querier: pixel indices and the points in the camera's perspective coordinates.  w2pers
+    (neural_points.py:838-850) is restated with float32 numpy ELEMENTWISE operations in a fixed order, so the fixture is bit-identical on
+    every machine (the golden vectors of the reference's kernels are re-checked on CPU against it)."""
+    from sgnerf_b200 import synth
+    s = synth.scene_c0(n_points=n_points, n_rays=n_rays, seed=seed)
+    if full_patch:                                                   # a dense 64 x 48 pixel patch: several rays share one frustum column
+        px, py = np.meshgrid(np.arange(200, 264), np.arange(150, 198))
+        s.px, s.py = px.reshape(-1).astype(np.float32), py.reshape(-1).astype(np.float32)
+    d = (s.xyz - s.campos[None]).astype(np.float32)
+    R = s.camrotc2w.astype(np.float32)
+    cam = [d[:, 0] * R[0, j] + d[:, 1] * R[1, j] + d[:, 2] * R[2, j] for j in range(3)]          # shift @ R  (xyz_c = R^T shift)
+    s.xyz_pers = torch.from_numpy(np.ascontiguousarray(np.stack([cam[0] / cam[2], cam[1] / cam[2], cam[2]], -1).astype(np.float32)))
+    s.pixel_idx = torch.from_numpy(np.stack([s.px, s.py], -1).astype(np.int32))
+    return s
