@@ -359,6 +359,17 @@ int sgn_adam_rows_multi(int n_tables, float* const* params, float* const* grads,
                         const int32_t* C /*[host]*/, uint8_t* active, int64_t N, float lr, float beta1, float beta2, float eps,
                         const float* step, float grad_scale, int zero_grad, void* stream);
 
+/* The same update driven by a list of the active rows, for steps that touch a small part of the cloud (a 56x56 patch touches ~5 % of 1M
+ * points): nothing is read for the other rows.  sgn_adam_mark_rows sets touched[r] = 1 for every r >= 0 of `rows` (the step's
+ * sample_pidx: a superset of the rows that receive a gradient); with several ranks `touched` is summed with the gradients.
+ * sgn_adam_rows_list then (1) clears `touched`, appends the touched rows that have a non-zero gradient and were not active yet to
+ * active_list (int32 [N]) / active_count (int32 [1], device) and sets their `active` flag, (2) updates the listed rows exactly as
+ * sgn_adam_rows_multi does.  Same results as sgn_adam_rows_multi (and as dense Adam) bit for bit. */
+int sgn_adam_mark_rows(const int32_t* rows, int64_t n, float* touched, void* stream);
+int sgn_adam_rows_list(int n_tables, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                       const int32_t* C /*[host]*/, uint8_t* active, int32_t* active_list, int32_t* active_count, float* touched, int64_t N,
+                       float lr, float beta1, float beta2, float eps, const float* step, float grad_scale, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,6 +106,9 @@ SIGNATURES = {
     "sgn_adam_step_count": (c_int, [c_void, c_void]),
     "sgn_adam_rows_multi": (c_int, [c_int, C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(C.c_int32), c_void,
                                     c_i64, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),
+    "sgn_adam_mark_rows": (c_int, [c_void, c_i64, c_void, c_void]),
+    "sgn_adam_rows_list": (c_int, [c_int, C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(C.c_int32), c_void, c_void,
+                                   c_void, c_void, c_i64, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),
     "sgn_adam_rows": (c_int, [c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),
 }
 

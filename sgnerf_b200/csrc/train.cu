@@ -174,6 +174,68 @@ __global__ void adam_rows_multi_kernel(AdamTables T, uint8_t* __restrict__ activ
 
 __global__ void step_increment_kernel(float* step) { *step += 1.0f; }
 
+// ---- the same update driven by a LIST of the active rows (rows that ever received a non-zero gradient) --------------------------------
+// A step touches ~5 % of a 1M-point cloud; reading every row's gradient to find them costs more than the update itself.  The rows a step
+// can touch are known from the query (sample_pidx >= 0): mark_rows_kernel flags them, adam_append_kernel moves newly active ones into
+// the list, adam_list_kernel updates the listed rows.  `touched` is a float array so that, with several ranks, it can ride in the same
+// all-reduce as the gradients (sum > 0 = touched on some rank).
+__global__ void mark_rows_kernel(const int32_t* __restrict__ pidx, int64_t n, float* __restrict__ touched)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = pidx[i];
+    if (p >= 0) touched[p] = 1.0f;
+}
+
+__global__ void adam_append_kernel(AdamTables T, uint8_t* __restrict__ active, int32_t* __restrict__ list, int32_t* count, float* __restrict__ touched, int64_t N)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N || touched[row] == 0.f) return;
+    touched[row] = 0.f;
+    if (active[row]) return;
+    bool nz = false;
+    for (int k = 0; k < T.n; k++) {
+        const float* g = T.grad[k] + row * T.C[k];
+        for (int c = 0; c < T.C[k]; c++) nz = nz || g[c] != 0.f;
+    }
+    if (!nz) return;
+    active[row] = 1;
+    list[atomicAdd(count, 1)] = (int32_t)row;
+}
+
+__global__ void adam_list_kernel(AdamTables T, const int32_t* __restrict__ list, const int32_t* __restrict__ count, float lr, float b1, float b2, float eps,
+                                 const float* __restrict__ step, float grad_scale, int zero_grad)
+{
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gid >> 3) >= *count) return;
+    const int64_t row = list[gid >> 3];
+    const int l = (int)(gid & 7);
+    const float t = *step;
+    const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
+    const float step_size = lr / bc1;
+#pragma unroll
+    for (int k = 0; k < ADAM_MAX_TABLES; k++) {
+        if (k >= T.n) break;
+        const int C = T.C[k];
+        // rows of 4 floats or fewer belong to one lane; a different lane per table so that the small tables do not all land on lane 0
+        const int e0 = C <= 4 ? (l == (k & 7) ? 0 : C) : 4 * l;
+        if (e0 >= C) continue;
+        float *p = T.param[k] + row * C, *a = T.m1[k] + row * C, *b = T.m2[k] + row * C, *g = T.grad[k] + row * C;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = e0 + i;
+            if (c >= C) break;
+            const float g0 = g[c];
+            const float gc = g0 * grad_scale;
+            const float m = b1 * a[c] + (1.0f - b1) * gc;
+            const float v = b2 * b[c] + (1.0f - b2) * gc * gc;
+            a[c] = m; b[c] = v;
+            p[c] -= step_size * (m / (sqrtf(v) / bc2s + eps));
+            if (zero_grad && g0 != 0.f) g[c] = 0.f;
+        }
+    }
+}
+
 }  // namespace sgn
 
 using namespace sgn;
@@ -243,6 +305,45 @@ extern "C" int sgn_adam_rows_multi(int n_tables, float* const* params, float* co
     }
     if (N == 0) return SGN_OK;
     launch(adam_rows_multi_kernel, cdiv(N * 8, 256), 256, 0, (cudaStream_t)stream, T, active, N, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+static int adam_tables(const char* what, AdamTables& T, int n_tables, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                       const int32_t* C)
+{
+    SGN_CHECK_ARG(n_tables > 0 && n_tables <= ADAM_MAX_TABLES && params && grads && exp_avg && exp_avg_sq && C, "%s: bad argument (at most %d tables)", what,
+                  ADAM_MAX_TABLES);
+    T.n = n_tables;
+    for (int k = 0; k < n_tables; k++) {
+        SGN_CHECK_ARG(C[k] > 0 && C[k] <= 32 && params[k] && grads[k] && exp_avg[k] && exp_avg_sq[k], "%s: table %d: NULL or more than 32 columns", what, k);
+        T.param[k] = params[k]; T.grad[k] = grads[k]; T.m1[k] = exp_avg[k]; T.m2[k] = exp_avg_sq[k]; T.C[k] = C[k];
+    }
+    return SGN_OK;
+}
+
+extern "C" int sgn_adam_mark_rows(const int32_t* rows, int64_t n, float* touched, void* stream)
+{
+    SGN_CHECK_ARG(n >= 0 && (n == 0 || (rows && touched)), "sgn_adam_mark_rows: bad argument");
+    if (n == 0) return SGN_OK;
+    launch(mark_rows_kernel, cdiv(n, 256), 256, 0, (cudaStream_t)stream, rows, n, touched);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_adam_rows_list(int n_tables, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq, const int32_t* C,
+                                  uint8_t* active, int32_t* active_list, int32_t* active_count, float* touched, int64_t N, float lr, float beta1, float beta2,
+                                  float eps, const float* step, float grad_scale, int zero_grad, void* stream)
+{
+    AdamTables T = {};
+    int rc = adam_tables("sgn_adam_rows_list", T, n_tables, params, grads, exp_avg, exp_avg_sq, C);
+    if (rc) return rc;
+    SGN_CHECK_ARG(active && active_list && active_count && touched && step && N >= 0 && N < (1ll << 31), "sgn_adam_rows_list: bad argument");
+    if (N == 0) return SGN_OK;
+    auto st = (cudaStream_t)stream;
+    launch(adam_append_kernel, cdiv(N, 256), 256, 0, st, T, active, active_list, active_count, touched, N);
+    // the grid covers the case "every row active"; blocks past the list's end leave at once (the count lives on the device: no host round trip)
+    launch(adam_list_kernel, cdiv(N * 8, 256), 256, 0, st, T, active_list, active_count, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

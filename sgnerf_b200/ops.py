@@ -563,6 +563,22 @@ def adam_rows_multi(params, grads, exp_avgs, exp_avg_sqs, active, step, lr, beta
               float(lr), float(betas[0]), float(betas[1]), float(eps), _ptr(step), float(grad_scale), int(zero_grad), _stream())
 
 
+def adam_mark_rows(rows, touched):
+    """sgn_adam_mark_rows: touched[r] = 1 for every r >= 0 of the int32 tensor `rows`."""
+    rows = _dev(rows, torch.int32, "rows")
+    _lib.call("sgn_adam_mark_rows", _ptr(rows), rows.numel(), _ptr(touched), _stream())
+
+
+def adam_rows_list(params, grads, exp_avgs, exp_avg_sqs, active, active_list, active_count, touched, step, lr, betas=(0.9, 0.999), eps=1e-8,
+                   grad_scale=1.0, zero_grad=True):
+    """sgn_adam_rows_list: adam_rows_multi driven by the list of active rows (nothing is read for rows that never received a gradient)."""
+    N = params[0].shape[0]
+    Cs = (C.c_int32 * len(params))(*[p.numel() // max(N, 1) for p in params])
+    _lib.call("sgn_adam_rows_list", len(params), _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs), _ptr_array(exp_avg_sqs), Cs, _ptr(active),
+              _ptr(active_list), _ptr(active_count), _ptr(touched), N, float(lr), float(betas[0]), float(betas[1]), float(eps), _ptr(step),
+              float(grad_scale), int(zero_grad), _stream())
+
+
 def adam_step_count(step):
     _lib.call("sgn_adam_step_count", _ptr(step), _stream())
 

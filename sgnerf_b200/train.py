@@ -115,8 +115,11 @@ class TrainStep(_StepBase):
         for n in sizes:
             offs.append(off)
             off += (n + 63) // 64 * 64
-        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        n_rows = scene.xyz.shape[0]
+        self.flat_grad = torch.zeros(off + n_rows, dtype=torch.float32, device=dev)
         self.grads = [self.flat_grad[o:o + n].view_as(p) for p, n, o in zip(self.params, sizes, offs)]
+        # rows this step may touch (1.0 where sample_pidx points): rides at the end of the bucket so the all-reduce unions it over the ranks
+        self.pt_touched = self.flat_grad[off:off + n_rows]
         self.n_net = offs[len(self.net_params)]           # the MLP gradients occupy flat_grad[:n_net]
         nl = len(scene.weights)
         self.d_w, self.d_b = self.grads[:nl], self.grads[nl:2 * nl]
@@ -128,6 +131,8 @@ class TrainStep(_StepBase):
         self.pt_m = [torch.zeros_like(p) for p in self.pt_params]
         self.pt_v = [torch.zeros_like(p) for p in self.pt_params]
         self.pt_active = torch.zeros(scene.xyz.shape[0], dtype=torch.uint8, device=dev)     # rows that ever received a gradient
+        self.pt_active_list = torch.zeros(scene.xyz.shape[0], dtype=torch.int32, device=dev)    # ... as a list, in order of first appearance
+        self.pt_active_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pt_step = torch.zeros((), dtype=torch.float32, device=dev)
         self._cnt = torch.zeros((), dtype=torch.float32, device=dev)
 
@@ -136,6 +141,7 @@ class TrainStep(_StepBase):
         sc, q = self.scene, self.scene.qopt
         grid, hp = sc.grid()
         pidx, loc_w, _, rmask = ops.query(grid, self.campos, self.raydir, self.t, q.SR, q.K, q.kernel_size[0], hp.radius2)
+        ops.adam_mark_rows(pidx, self.pt_touched)
         dec, valid, loc_pers, _, conf, ws, tb = ops.aggregate_train_forward(
             sc.agg_cfg, sc.weights, sc.biases, sc.xyz, sc.embedding, sc.color, sc.dirs, sc.conf, sc.label_emb, pidx, loc_w, self.raydir,
             self.campos, self.camrot, self.precision)
@@ -158,7 +164,8 @@ class TrainStep(_StepBase):
             dist.all_reduce(self.flat_grad, group=self.group)          # in place, SUM: losses are normalised by the global hit count
         self.optim.step()
         ops.adam_step_count(self.pt_step)
-        ops.adam_rows_multi(self.pt_params, self.grads[len(self.net_params):], self.pt_m, self.pt_v, self.pt_active, self.pt_step, self.plr)
+        ops.adam_rows_list(self.pt_params, self.grads[len(self.net_params):], self.pt_m, self.pt_v, self.pt_active, self.pt_active_list,
+                           self.pt_active_count, self.pt_touched, self.pt_step, self.plr)
 
 
 class AutogradTrainStep(_StepBase):

@@ -268,6 +268,43 @@ def test_adam_rows_multi_equals_dense_torch_adam():
     assert 0.1 < float(un.float().mean()) < 0.9 and all(torch.equal(p.cpu()[un], q[un]) for p, q in zip(ps, p0))
 
 
+def test_adam_rows_list_is_bit_identical_to_adam_rows_multi():
+    """sgn_adam_rows_list (marked rows -> list of active rows -> update of the listed rows only) against sgn_adam_rows_multi (every row's
+    gradient read): parameters, both moments, the gradients' clearing and the active flags are equal bit for bit over 6 steps; rows marked
+    without a gradient (sample_pidx is a superset of the rows that receive one) stay inactive."""
+    g = torch.Generator().manual_seed(5)
+    N, Cs = 5003, [32, 3, 3, 1]
+    shapes = [(N, c) if c > 1 else (N,) for c in Cs]
+    p0 = [torch.randn(*s, generator=g).cuda() for s in shapes]
+    A = dict(p=[p.clone() for p in p0], g=[torch.zeros_like(p) for p in p0], m=[torch.zeros_like(p) for p in p0], v=[torch.zeros_like(p) for p in p0],
+             active=torch.zeros(N, dtype=torch.uint8, device="cuda"), step=torch.zeros((), device="cuda"))
+    B = dict(p=[p.clone() for p in p0], g=[torch.zeros_like(p) for p in p0], m=[torch.zeros_like(p) for p in p0], v=[torch.zeros_like(p) for p in p0],
+             active=torch.zeros(N, dtype=torch.uint8, device="cuda"), step=torch.zeros((), device="cuda"),
+             lst=torch.zeros(N, dtype=torch.int32, device="cuda"), cnt=torch.zeros(1, dtype=torch.int32, device="cuda"), touched=torch.zeros(N, device="cuda"))
+    for it in range(6):
+        rows = torch.randperm(N, generator=g)[:300 + 50 * it]
+        extra = torch.randperm(N, generator=g)[:200]                                   # marked, but no gradient arrives
+        for k, (s, c) in enumerate(zip(shapes, Cs)):
+            gd = torch.zeros(*s)
+            sub = rows[: rows.numel() - 20 * k]
+            gd[sub] = torch.randn(*((sub.numel(), c) if c > 1 else (sub.numel(),)), generator=g)
+            A["g"][k].copy_(gd.cuda())
+            B["g"][k].copy_(gd.cuda())
+        pidx = torch.cat([rows, extra, torch.full((64,), -1, dtype=torch.int64)]).to(torch.int32).cuda().reshape(-1, 2)
+        ops.adam_step_count(A["step"])
+        ops.adam_rows_multi(A["p"], A["g"], A["m"], A["v"], A["active"], A["step"], 2e-3)
+        ops.adam_mark_rows(pidx, B["touched"])
+        ops.adam_step_count(B["step"])
+        ops.adam_rows_list(B["p"], B["g"], B["m"], B["v"], B["active"], B["lst"], B["cnt"], B["touched"], B["step"], 2e-3)
+        for key in ("p", "g", "m", "v"):
+            for a, b in zip(A[key], B[key]):
+                assert torch.equal(a, b), (it, key)
+        assert torch.equal(A["active"], B["active"]) and int(B["cnt"]) == int(B["active"].sum()) and float(B["touched"].abs().sum()) == 0.0
+        lst = B["lst"][: int(B["cnt"])].cpu().numpy()
+        assert len(set(lst.tolist())) == lst.size and bool(B["active"].cpu().numpy()[lst].all())
+    assert 0.1 < float(B["active"].float().mean()) < 0.9
+
+
 def test_scene_edit_with_stable_indices_equals_a_fresh_scene():
     """RenderScene.edit (prune -> holes, grow -> fill holes / append, per-point tables updated for the written rows only, grid rebuilt):
     after two rounds of edits the scene renders bit for bit like a scene built from scratch from the same tensors, the rows of the
