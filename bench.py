@@ -333,8 +333,8 @@ def run_ours(args):
 def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
     """Config C2 beside the headline (BASELINE.json's metric names both): one training step = 56x56 random pixels per GPU with jittered
     samples -> query -> aggregation forward + backward (TF32 tensor-core GEMMs, scatter-add into the point tables) -> compositing,
-    masked MSE + zero-one(conf) -> gradient all-reduce over ranks (one flat bucket, NCCL) -> Adam; no host synchronisation, the whole
-    step replayed as one CUDA graph (sgnerf_b200/train.py).  ms = device time per step, max over ranks."""
+    masked MSE + zero-one(conf) -> gradient all-reduce over ranks (NCCL; MLP gradients + the touched point rows) -> Adam on the active rows;
+    one CUDA graph per step on one GPU (no host synchronisation), two around the exchange on several (sgnerf_b200/train.py).  ms = device time per step, max over ranks."""
     from sgnerf_b200 import ops, pipeline, train
     info = {"what": f"C2: {patch}x{patch} rays per GPU, fwd + bwd + all-reduce + Adam", "rays_per_step_per_gpu": patch * patch, "dtype": "tf32"}
     try:
@@ -369,7 +369,11 @@ def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
                 ts = train.TrainStep(sc, n, s.near, s.far, bg, precision=ops.PRECISION_TF32, use_graph=mode == "cuda graph")
                 ms = run(ts, steps)
                 info.update(mode=mode, loss=float(ts.loss), rays_hit_last_step=float(ts.n_hit),
-                            allreduce_bytes_per_step=(int(ts.flat_grad.numel()) * 4 if world > 1 else 0))
+                            allreduce_bytes_per_step=int(ts.exchange_floats) * 4, dense_bucket_bytes=int(ts.flat_grad.numel()) * 4)
+                if world > 1:
+                    info["exchange"] = ("MLP gradients + the point-table gradient rows some rank touched this step (sgn_rows_union / sgn_rows_pack), one "
+                                        "all-reduce sized by a host read of the row count that overlaps forward + backward: three CUDA graphs per "
+                                        "step") if ts.sparse else "dense bucket"
                 if world > 1:
                     # the same step without the exchange, in the same run on every rank: what the all-reduce costs at this N
                     sc2 = pipeline.RenderScene(scene.xyz, scene.embedding.clone(), scene.color.clone(), scene.dirs.clone(), scene.conf.clone(),

@@ -370,6 +370,16 @@ int sgn_adam_rows_list(int n_tables, float* const* params, float* const* grads, 
                        const int32_t* C /*[host]*/, uint8_t* active, int32_t* active_list, int32_t* active_count, float* touched, int64_t N,
                        float lr, float beta1, float beta2, float eps, const float* step, float grad_scale, int zero_grad, void* stream);
 
+/* Exchange of the touched rows only (data-parallel training, replaces the dense all-reduce of the point tables' gradients -- the flatten /
+ * all-reduce / un-flatten of torch DDP in the reference's multi-GPU scripts).  With `touched` already summed over the ranks,
+ * sgn_rows_union writes the ascending list of rows with touched != 0 and their number (int32 [1], device) -- identical on every rank;
+ * sgn_rows_pack copies those rows of n_tables tables [N, C_k] into packed [count, stride] (unpack = 0) or back (unpack = 1).
+ * The caller all-reduces packed[:count * stride]. */
+int sgn_rows_union_bytes(int64_t N, size_t* bytes);
+int sgn_rows_union(const float* touched, int64_t N, int32_t* list, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+int sgn_rows_pack(int n_tables, float* const* tables, const int32_t* C /*[host]*/, const int32_t* list, const int32_t* count, int64_t N,
+                  float* packed, int stride, int unpack, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,11 @@
 // Reference: models/base_rendering_model.py:543-641 (compute_losses: `ray_masked_coarse_raycolor` colour MSE + 1e-6 per item, zero-one
 // regulariser on conf_coefficient with --zero_epsilon), models/mvs_points_volumetric_model.py:67-109 (two torch.optim.Adam instances,
 // betas (0.9, 0.999), no weight decay: MLP weights at --lr, point tables at --plr).
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sgn {
@@ -206,13 +211,14 @@ __global__ void adam_append_kernel(AdamTables T, uint8_t* __restrict__ active, i
 __global__ void adam_list_kernel(AdamTables T, const int32_t* __restrict__ list, const int32_t* __restrict__ count, float lr, float b1, float b2, float eps,
                                  const float* __restrict__ step, float grad_scale, int zero_grad)
 {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((gid >> 3) >= *count) return;
-    const int64_t row = list[gid >> 3];
-    const int l = (int)(gid & 7);
+    // a fixed grid walks the list (its length lives on the device; a grid sized for "every row active" would spend its time on empty blocks)
+    const int l = (int)(threadIdx.x & 7);
     const float t = *step;
     const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
     const float step_size = lr / bc1;
+    const int64_t n = *count;
+    for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; idx < n; idx += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int64_t row = list[idx];
 #pragma unroll
     for (int k = 0; k < ADAM_MAX_TABLES; k++) {
         if (k >= T.n) break;
@@ -233,6 +239,7 @@ __global__ void adam_list_kernel(AdamTables T, const int32_t* __restrict__ list,
             p[c] -= step_size * (m / (sqrtf(v) / bc2s + eps));
             if (zero_grad && g0 != 0.f) g[c] = 0.f;
         }
+    }
     }
 }
 
@@ -309,6 +316,87 @@ extern "C" int sgn_adam_rows_multi(int n_tables, float* const* params, float* co
     return SGN_OK;
 }
 
+// ---- exchange of the touched rows only (several ranks) --------------------------------------------------------------------------------
+// After `touched` has been summed over the ranks every rank derives the same ordered list of rows some rank touched, packs its own
+// gradient rows of that list into a dense [count, stride] block (zeros for rows only other ranks touched), the block is all-reduced
+// (count * stride floats instead of N * stride), and unpacked back into the table-shaped accumulators.
+namespace sgn {
+struct MarkedRow {
+    const float* touched;
+    __device__ __forceinline__ bool operator()(int32_t i) const { return touched[i] != 0.f; }
+};
+
+template <bool UNPACK>
+__global__ void rows_pack_kernel(AdamTables T, const int32_t* __restrict__ list, const int32_t* __restrict__ count, float* __restrict__ packed, int stride)
+{
+    const int l = (int)(threadIdx.x & 7);
+    const int64_t n = *count;
+    for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; idx < n; idx += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+        const int64_t row = list[idx];
+        float* dst = packed + idx * stride;
+        int col = 0;
+#pragma unroll
+        for (int k = 0; k < ADAM_MAX_TABLES; k++) {
+            if (k >= T.n) break;
+            const int C = T.C[k];
+            const int e0 = C <= 4 ? (l == (k & 7) ? 0 : C) : 4 * l;
+            float* g = T.grad[k] + row * C;
+            for (int c = e0; c < min(C, e0 + 4); c++) {
+                if (UNPACK) g[c] = dst[col + c];
+                else dst[col + c] = g[c];
+            }
+            col += C;
+        }
+    }
+}
+}  // namespace sgn
+
+static size_t rows_select_bytes(int64_t N)
+{
+    size_t b = 0;
+    cub::DeviceSelect::If(nullptr, b, cub::CountingInputIterator<int32_t>(0), (int32_t*)nullptr, (int32_t*)nullptr, (int)N, MarkedRow{nullptr});
+    return b;
+}
+
+extern "C" int sgn_rows_union_bytes(int64_t N, size_t* bytes)
+{
+    SGN_CHECK_ARG(N >= 0 && N < (1ll << 31) && bytes, "sgn_rows_union_bytes: bad argument");
+    *bytes = align_up(rows_select_bytes(N));
+    return SGN_OK;
+}
+
+extern "C" int sgn_rows_union(const float* touched, int64_t N, int32_t* list, int32_t* count, void* workspace, size_t workspace_bytes, void* stream)
+{
+    SGN_CHECK_ARG(touched && list && count && N > 0 && N < (1ll << 31), "sgn_rows_union: bad argument");
+    size_t need = rows_select_bytes(N);
+    if (workspace_bytes < need || ((uintptr_t)workspace & 255)) { set_error("sgn_rows_union: workspace too small or misaligned (need %zu bytes)", need); return SGN_E_WORKSPACE; }
+    // one-pass stream compaction (decoupled look-back): ascending row numbers, the same list on every rank
+    ++g_launch_count;
+    SGN_CUDA(cub::DeviceSelect::If(workspace, need, cub::CountingInputIterator<int32_t>(0), list, count, (int)N, MarkedRow{touched}, (cudaStream_t)stream));
+    return SGN_OK;
+}
+
+extern "C" int sgn_rows_pack(int n_tables, float* const* tables, const int32_t* C, const int32_t* list, const int32_t* count, int64_t N, float* packed,
+                             int stride, int unpack, void* stream)
+{
+    SGN_CHECK_ARG(n_tables > 0 && n_tables <= ADAM_MAX_TABLES && tables && C && list && count && packed && N >= 0, "sgn_rows_pack: bad argument");
+    AdamTables T = {};
+    T.n = n_tables;
+    int cols = 0;
+    for (int k = 0; k < n_tables; k++) {
+        SGN_CHECK_ARG(C[k] > 0 && C[k] <= 32 && tables[k], "sgn_rows_pack: table %d: NULL or more than 32 columns", k);
+        T.grad[k] = tables[k]; T.C[k] = C[k];
+        cols += C[k];
+    }
+    SGN_CHECK_ARG(stride >= cols, "sgn_rows_pack: stride %d < %d columns", stride, cols);
+    if (N == 0) return SGN_OK;
+    const int nb = (int)std::min<int64_t>(cdiv(N * 8, 256), 148 * 8);
+    if (unpack) launch(rows_pack_kernel<true>, nb, 256, 0, (cudaStream_t)stream, T, list, count, packed, stride);
+    else launch(rows_pack_kernel<false>, nb, 256, 0, (cudaStream_t)stream, T, list, count, packed, stride);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
 static int adam_tables(const char* what, AdamTables& T, int n_tables, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                        const int32_t* C)
 {
@@ -342,8 +430,8 @@ extern "C" int sgn_adam_rows_list(int n_tables, float* const* params, float* con
     if (N == 0) return SGN_OK;
     auto st = (cudaStream_t)stream;
     launch(adam_append_kernel, cdiv(N, 256), 256, 0, st, T, active, active_list, active_count, touched, N);
-    // the grid covers the case "every row active"; blocks past the list's end leave at once (the count lives on the device: no host round trip)
-    launch(adam_list_kernel, cdiv(N * 8, 256), 256, 0, st, T, active_list, active_count, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
+    launch(adam_list_kernel, (int)std::min<int64_t>(cdiv(N * 8, 256), 148 * 8), 256, 0, st, T, active_list, active_count, lr, beta1, beta2, eps, step, grad_scale,
+           zero_grad);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

@@ -579,6 +579,22 @@ def adam_rows_list(params, grads, exp_avgs, exp_avg_sqs, active, active_list, ac
               float(grad_scale), int(zero_grad), _stream())
 
 
+def rows_union(touched, row_list, count):
+    """sgn_rows_union: ascending list of the rows with touched != 0 into row_list (int32 [N]), their number into count (int32 [1])."""
+    N = touched.numel()
+    nbytes = C.c_size_t()
+    _lib.call("sgn_rows_union_bytes", N, C.byref(nbytes))
+    ws = _workspace(nbytes.value, touched.device)
+    _lib.call("sgn_rows_union", _ptr(touched), N, _ptr(row_list), _ptr(count), _ptr(ws), nbytes.value, _stream())
+
+
+def rows_pack(tables, row_list, count, packed, stride, unpack=False):
+    """sgn_rows_pack: rows `row_list[:count]` of the tables [N, C_k] <-> packed [count, stride]."""
+    N = tables[0].shape[0]
+    Cs = (C.c_int32 * len(tables))(*[t.numel() // max(N, 1) for t in tables])
+    _lib.call("sgn_rows_pack", len(tables), _ptr_array(tables), Cs, _ptr(row_list), _ptr(count), N, _ptr(packed), int(stride), int(unpack), _stream())
+
+
 def adam_step_count(step):
     _lib.call("sgn_adam_step_count", _ptr(step), _stream())
 

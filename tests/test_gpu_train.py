@@ -14,7 +14,7 @@ from tests.test_gpu_aggregate import cfg_to_c
 pytestmark = pytest.mark.gpu
 
 
-def _make(precision, use_graph, n_rays=512, n_points=60_000):
+def _make(precision, use_graph, n_rays=512, n_points=60_000, **kw):
     s = synth.scene_room(n_points, room=(3.0, 3.0, 2.0), width=160, height=120, seed=7)
     tabs = synth.make_point_tables(n_points, 32, 0, seed=0)
     cfg = rr.agg_config()
@@ -23,7 +23,7 @@ def _make(precision, use_graph, n_rays=512, n_points=60_000):
     scene = pipeline.RenderScene(torch.from_numpy(s.xyz), tabs.embedding.reshape(n_points, -1), tabs.color.reshape(n_points, 3),
                                  tabs.dir.reshape(n_points, 3), tabs.conf.reshape(n_points), [P[n + ".weight"].clone() for n in names],
                                  [P[n + ".bias"].clone() for n in names], cfg_to_c(cfg), pipeline.query_options(), device="cuda")
-    ts = train.TrainStep(scene, n_rays, s.near, s.far, torch.ones(3), precision=precision, use_graph=use_graph)
+    ts = train.TrainStep(scene, n_rays, s.near, s.far, torch.ones(3), precision=precision, use_graph=use_graph, **kw)
     g = torch.Generator().manual_seed(1)
     pix = torch.randint(0, s.raydir.shape[0], (n_rays,), generator=g)
     gt = torch.rand(n_rays, 3, generator=g)
@@ -303,6 +303,51 @@ def test_adam_rows_list_is_bit_identical_to_adam_rows_multi():
         lst = B["lst"][: int(B["cnt"])].cpu().numpy()
         assert len(set(lst.tolist())) == lst.size and bool(B["active"].cpu().numpy()[lst].all())
     assert 0.1 < float(B["active"].float().mean()) < 0.9
+
+
+def test_rows_union_pack_unpack_round_trip():
+    """sgn_rows_union / sgn_rows_pack (the touched-row gradient exchange): the list is the ascending set of rows with touched != 0, packing
+    copies exactly those rows of every table, unpacking puts them back; other rows are never written."""
+    g = torch.Generator().manual_seed(9)
+    N, Cs = 7001, [32, 3, 3, 1]
+    tabs = [torch.randn(N, c, generator=g).cuda() if c > 1 else torch.randn(N, generator=g).cuda() for c in Cs]
+    touched = torch.zeros(N, device="cuda")
+    rows = torch.randperm(N, generator=g)[:913].cuda()
+    touched[rows] = torch.randint(1, 5, (913,), generator=g).float().cuda()           # sums over ranks: any positive value
+    lst, cnt = torch.full((N,), -7, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.rows_union(touched, lst, cnt)
+    assert int(cnt) == 913 and torch.equal(lst[:913].long(), torch.sort(rows)[0]) and bool((lst[913:] == -7).all())
+    stride = 40
+    packed = torch.full((N, stride), float("nan"), device="cuda")
+    ops.rows_pack(tabs, lst, cnt, packed, stride)
+    want = torch.cat([t.reshape(N, -1) for t in tabs], dim=1)[lst[:913].long()]
+    assert torch.equal(packed[:913, :39], want) and bool(torch.isnan(packed[913:]).all())
+    back = [torch.zeros_like(t) for t in tabs]
+    packed[:913, :39] *= 2.0
+    ops.rows_pack(back, lst, cnt, packed, stride, unpack=True)
+    mask = touched != 0
+    for b, t in zip(back, tabs):
+        assert torch.equal(b[mask], 2.0 * t[mask]) and float(b[~mask].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sparse_exchange_step_equals_the_dense_step(use_graph):
+    """TrainStep with the touched-row exchange forced on a single rank (union -> pack -> [all-reduce] -> unpack around the host read of
+    the row count, two CUDA graphs) trains like the plain step: same loss trajectory, same parameters up to the float atomics' rounding."""
+    a = _make(ops.PRECISION_TF32, use_graph=use_graph)
+    b = _make(ops.PRECISION_TF32, use_graph=use_graph, sparse_exchange="force")
+    assert b.sparse and not a.sparse
+    la, lb = [], []
+    for _ in range(6):
+        a.step(); b.step()
+        torch.cuda.synchronize()
+        la.append(float(a.loss)); lb.append(float(b.loss))
+    assert np.allclose(la, lb, rtol=2e-3, atol=1e-6), (la, lb)
+    for pa, pb in zip(a.params, b.params):
+        assert float((pa.detach() - pb.detach()).abs().mean()) < 2e-4
+    assert torch.equal(a.pt_active, b.pt_active)
+    n = int(b.x_count_host[0])
+    assert 0 < n < b.scene.xyz.shape[0] // 2 and b.exchange_floats == b.n_net + n * b.x_stride
 
 
 def test_scene_edit_with_stable_indices_equals_a_fresh_scene():
