@@ -13,10 +13,13 @@
 //     core is SWIZZLE_128B_BASE32B (32-byte chunk ^= k-row & 3; MN atoms of 32 floats LBO apart, 4-row k-groups SBO apart).
 // M (valid tuples / samples) is only known on the device: the kernels read it from *m_ptr and are persistent over the tiles
 // (nn) or split the m range evenly over the grid (tn), so the host never synchronises.
-// Warp roles: 0-3 epilogue (TMEM lane quarter = warp), 4-7 cp.async loaders, 8 MMA issuer.
+// Warp roles, tn: 0-3 epilogue (TMEM lane quarter = warp), 4-7 cp.async loaders, 8 MMA issuer.
+// nn: operands arrive by TMA tile loads (one producer thread, warp 9), warps 0-7 are the epilogue (two per lane quarter), warp 8 issues the MMAs.
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include <cuda.h>                 // CUtensorMap and its enums; cuTensorMapEncodeTiled itself is fetched through cudaGetDriverEntryPoint
+
 #include "tc_ptx.cuh"
 
 namespace sgn {
@@ -56,8 +59,45 @@ __device__ __forceinline__ float4 lds128f_v(uint32_t addr)
 }
 __device__ __forceinline__ void red_add_f32(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
 
+// 2-D TMA tile load (cp.async.bulk.tensor): box {32 floats, rows} at element (k0, row0) of the tensor behind `map`, SWIZZLE_128B, bytes
+// reported to `bar`; out-of-range elements arrive as zeros
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int k0, int row0, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(k0), "r"(row0), "r"(bar) : "memory");
+}
+
+// Row-major fp32 matrix [rows, cols] with leading dimension ld (floats) as a tensor map whose box is 32 columns x box_rows rows
+static inline int make_tmap_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return SGN_E_CUDA;
+        }
+        fn = (EncodeFn)ptr;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %lld] matrix, ld %lld, box rows %d", (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows);
+        return SGN_E_CUDA;
+    }
+    return SGN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ nn
 struct GemmTcNN {
+    alignas(64) CUtensorMap mA1, mB1, mA2, mB2;                        // boxes: A {32, 128}, Bt {32, BN}
     const float* A1; int lda1; const float* Bt1; int ldb1; int K1;     // Bt: [N, ldb], K contiguous
     const float* A2; int lda2; const float* Bt2; int ldb2; int K2;
     float* C; int ldc; int N; int BN;                                  // BN = columns per CTA (multiple of 16, <= 256)
@@ -68,11 +108,12 @@ struct GemmTcNN {
 
 constexpr int NN_STAGES = 4;
 constexpr int NN_A_BYTES = 128 * 128, NN_B_BYTES = 256 * 128, NN_STAGE_BYTES = NN_A_BYTES + NN_B_BYTES;
-constexpr int NN_OFF_EPI = NN_STAGES * NN_STAGE_BYTES;            // 4 warps x (32 rows x 128 B) staging
-constexpr int NN_OFF_BAR = NN_OFF_EPI + 4 * 4096;
+constexpr int NN_THREADS = 10 * 32;                               // warps 0-7: epilogue (two per TMEM lane quarter), 8 MMA issuer, 9 TMA producer
+constexpr int NN_OFF_EPI = NN_STAGES * NN_STAGE_BYTES;            // 8 warps x (32 rows x 128 B) staging
+constexpr int NN_OFF_BAR = NN_OFF_EPI + 8 * 4096;
 constexpr int NN_SMEM = NN_OFF_BAR + 256 + 1024;
 
-static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTcNN p)
+static __global__ void __launch_bounds__(NN_THREADS, 1) gemm_tc_nn_kernel(const __grid_constant__ GemmTcNN p)
 {
     const int M = min(*p.m_ptr, p.m_max);
     const int ntile = (M + 127) >> 7;
@@ -84,8 +125,8 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTc
     const uint32_t bar_full = sbase + NN_OFF_BAR, bar_empty = bar_full + 8 * NN_STAGES, bar_accf = bar_empty + 8 * NN_STAGES, bar_acce = bar_accf + 16;
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + NN_OFF_BAR + 8 * (2 * NN_STAGES + 4));
     if (tid == 0) {
-        for (int s = 0; s < NN_STAGES; s++) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(bar_accf + 8 * a, 1); mbar_init(bar_acce + 8 * a, 128); }
+        for (int s = 0; s < NN_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_accf + 8 * a, 1); mbar_init(bar_acce + 8 * a, 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -100,43 +141,25 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTc
     const int n0 = blockIdx.y * p.BN;
     const int nst1 = (p.K1 + 31) >> 5, nst = nst1 + (p.A2 ? (p.K2 + 31) >> 5 : 0);
 
-    if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ loaders
-        const int lt = tid - 128;
-        const int c = lt & 7, r0 = lt >> 3;                    // 16-byte chunk of a 128-byte row; rows r0, r0 + 16, ...
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-            const int m0 = tile << 7;
-            for (int i = 0; i < nst; i++, it++) {
-                const bool second = i >= nst1;
-                const float* A = second ? p.A2 : p.A1;
-                const float* B = second ? p.Bt2 : p.Bt1;
-                const int lda = second ? p.lda2 : p.lda1, ldb = second ? p.ldb2 : p.ldb1;
-                const int k0 = (second ? i - nst1 : i) << 5;
-                const int kleft = (second ? p.K2 : p.K1) - k0;   // columns of this stage that exist (multiple of 8)
-                const uint32_t s = it % NN_STAGES, ph = (it / NN_STAGES) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint32_t sa = sbase + s * NN_STAGE_BYTES, sb = sa + NN_A_BYTES;
-                if (4 * c < kleft) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const int row = r0 + 16 * j;
-                        if (m0 + row < M) cp_async16(sa + row * 128 + ((c ^ (row & 7)) << 4), A + (size_t)(m0 + row) * lda + k0 + 4 * c, 16);
-                    }
-                    for (int row = r0; row < p.BN; row += 16)
-                        if (n0 + row < p.N) cp_async16(sb + row * 128 + ((c ^ (row & 7)) << 4), B + (size_t)(n0 + row) * ldb + k0 + 4 * c, 16);
-                }
-                cp_async_commit();
-                if (it >= GT_LAG) {
-                    cp_async_wait<GT_LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(bar_full + 8 * ((it - GT_LAG) % NN_STAGES));
+    if (warp == 9) {
+        // ------------------------------------------------------------------ producer: two TMA tile loads per stage (A rows, weight rows)
+        if (lane == 0) {
+            uint32_t it = 0;
+            const uint32_t stage_bytes = NN_A_BYTES + (uint32_t)p.BN * 128u;
+            for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+                const int m0 = tile << 7;
+                for (int i = 0; i < nst; i++, it++) {
+                    const bool second = i >= nst1;
+                    const int k0 = (second ? i - nst1 : i) << 5;
+                    const uint32_t s = it % NN_STAGES, ph = (it / NN_STAGES) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t sa = sbase + s * NN_STAGE_BYTES, sb = sa + NN_A_BYTES;
+                    mbar_expect_tx(bar_full + 8 * s, stage_bytes);
+                    tma_load_2d(sa, second ? &p.mA2 : &p.mA1, k0, m0, bar_full + 8 * s);
+                    tma_load_2d(sb, second ? &p.mB2 : &p.mB1, k0, n0, bar_full + 8 * s);
                 }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (uint32_t j = it > GT_LAG ? it - GT_LAG : 0; j < it; j++) mbar_arrive(bar_full + 8 * (j % NN_STAGES));
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
@@ -163,7 +186,9 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTc
         }
     } else {
         // ------------------------------------------------------------------ epilogue: TMEM -> swizzled staging -> coalesced rows
-        const uint32_t stg = sbase + NN_OFF_EPI + warp * 4096;
+        // two warps per TMEM lane quarter (a warp reaches the 32 lanes of quarter warp % 4): the first takes column chunks 0-3, the second 4-7
+        const int quarter = warp & 3, half = warp >> 2;
+        const uint32_t stg = sbase + NN_OFF_EPI + (quarter + 4 * half) * 4096;
         const int c4 = lane & 7, rsub = lane >> 3;
         float4 cs[8];                                          // column sums of what this thread stores (chunk ch, columns 4 c4 .. + 3)
 #pragma unroll
@@ -171,11 +196,12 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTc
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, tl++) {
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
-            const int m0 = (tile << 7) + warp * 32;
+            const int m0 = (tile << 7) + quarter * 32;
             mbar_wait(bar_accf + 8 * acc, aph);
             tc_fence_after();
 #pragma unroll
             for (int ch = 0; ch < 8; ch++) {
+                if ((ch >> 2) != half) continue;
                 if (ch * 32 >= p.BN) break;
                 const int nl = ch * 32 + 4 * c4;              // column inside this CTA's BN columns
                 const int n = n0 + nl;
@@ -190,7 +216,7 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_nn_kernel(GemmTc
                     }
                 }
                 uint32_t v[32];
-                tc_ld32(tmem_base + acc * 256 + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+                tc_ld32(tmem_base + acc * 256 + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), v);
 #pragma unroll
                 for (int q = 0; q < 8; q++) sts128(stg + lane * 128 + ((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
@@ -269,9 +295,14 @@ static inline int launch_gemm_tc_nn(const GemmNN& g, cudaStream_t st)
     p.bias = g.bias; p.aux = g.aux; p.ldaux = g.ldaux; p.epi = g.epi; p.slope = g.slope; p.colsum = g.colsum;
     const int nsplit = cdiv(g.N, 256);
     p.BN = (cdiv(g.N, nsplit) + 15) / 16 * 16;
+    int rc = make_tmap_f32(&p.mA1, g.A1, g.m_max, g.K1, g.lda1, 128);
+    if (!rc) rc = make_tmap_f32(&p.mB1, g.Bt1, g.N, g.K1, g.ldbt1, p.BN);
+    if (!rc && g.A2) rc = make_tmap_f32(&p.mA2, g.A2, g.m_max, g.K2, g.lda2, 128);
+    if (!rc && g.A2) rc = make_tmap_f32(&p.mB2, g.Bt2, g.N, g.K2, g.ldbt2, p.BN);
+    if (rc) return rc;
     const int tiles = cdiv(g.m_max, 128);
     const int gx = tiles < 148 / nsplit ? tiles : 148 / nsplit;
-    launch(gemm_tc_nn_kernel, dim3(gx, nsplit), GT_THREADS, NN_SMEM, st, p);
+    launch(gemm_tc_nn_kernel, dim3(gx, nsplit), NN_THREADS, NN_SMEM, st, p);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
