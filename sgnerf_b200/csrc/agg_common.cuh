@@ -9,6 +9,8 @@ constexpr int64_t AGG_FP32_CHUNK = 4096;  // rays per pass of the fp32 inference
 
 enum ExtraInput { EXTRA_NONE = 0, EXTRA_LABEL = 1, EXTRA_COLORDIR = 2 };
 
+constexpr int AGG_MAX_W = 512;        // widest MLP (shading_feature_num) the warp-per-row kernels keep per-lane partial sums for
+
 struct LayerInfo {
     int in, out;      // torch Linear shape [out, in]
     int kpad, npad;   // padded to multiples of 8
@@ -41,7 +43,7 @@ static inline int make_plan(const SgnAggCfg* c, AggPlan* P)
     SGN_CHECK_ARG(c != nullptr, "aggregator: cfg is NULL");
     SGN_CHECK_ARG(c->feat_dim > 0 && c->feat_dim % 4 == 0, "aggregator: feat_dim must be a positive multiple of 4");
     SGN_CHECK_ARG(c->num_feat_freqs >= 0 && c->dist_xyz_freq > 0 && c->num_viewdir_freqs > 0, "aggregator: bad frequency counts");
-    SGN_CHECK_ARG(c->width >= 16 && c->width % 16 == 0, "aggregator: width must be a multiple of 16");
+    SGN_CHECK_ARG(c->width >= 16 && c->width % 16 == 0 && c->width <= AGG_MAX_W, "aggregator: width must be a multiple of 16, at most %d", AGG_MAX_W);
     SGN_CHECK_ARG(c->n_block1 >= 1 && c->n_block3 >= 1, "aggregator: block1 and block3 need at least one layer (canonical branch)");
     SGN_CHECK_ARG(c->n_block2_bpnet >= 0 && c->n_color >= 1, "aggregator: bad layer counts");
     SGN_CHECK_ARG(c->label_dim % 8 == 0 && c->label_dim >= 0, "aggregator: label_dim must be a multiple of 8");

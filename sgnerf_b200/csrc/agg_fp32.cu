@@ -15,6 +15,8 @@
 //   alpha    per tuple  : raw sigma ; ksum per sample : sum_k w conf (sigma, h) ; colour MLP ; rgb
 // The fused bf16 tcgen05 inference path lives in agg_tc.cu; this file is the layer-wise one (strict fp32 or TF32 GEMMs), the only
 // one with a backward.
+#include <algorithm>
+
 #include "agg_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -40,6 +42,9 @@ static int launch_skinny(const float* A, int lda, int np, const float* X, int ld
 // GEMM dispatch: tc = TF32 tensor-core kernels (gemm_tc.cuh) where the operand shapes allow, fp32 SIMT otherwise.
 // g.colsum (column sums of the result = the bias gradient of the layer below) is fused into the tensor-core epilogue and is a
 // separate pass over C on the SIMT path.
+// grid of the warp-per-item kernels (8 warps per block): they stride over the items, whose number is only known on the device
+static inline int item_grid(int64_t max_items) { return (int)std::min<int64_t>(cdiv(max_items, 8), 148 * 8); }
+
 static int run_gemm_nn(const GemmNN& g, bool tc, cudaStream_t st)
 {
     if (tc && gemm_tc_nn_ok(g)) return launch_gemm_tc_nn(g, st);
@@ -81,7 +86,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
     launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
-    launch(agg_gather_kernel, cdiv(Tm, 8), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
+    launch(agg_gather_kernel, item_grid(Tm), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
     SGN_LAUNCH_CHECK();
 
     // per-tuple layers
@@ -102,8 +107,8 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     }
     const float* Hlast = cur;
     const int la = P.alpha_layer;
-    launch(agg_alpha_kernel, cdiv(Tm, 8), 256, 0, st, Hlast, d.W, weights[la], biases[la], T_ptr, Tm, ws.araw);
-    launch(agg_ksum_kernel, cdiv(Sm, 8), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, ws.araw, ws.C0, ws.sigma);
+    launch(agg_alpha_kernel, item_grid(Tm), 256, 0, st, Hlast, d.W, weights[la], biases[la], T_ptr, Tm, ws.araw);
+    launch(agg_ksum_kernel, item_grid(Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, ws.araw, ws.C0, ws.sigma);
     SGN_LAUNCH_CHECK();
 
     // colour MLP
@@ -120,7 +125,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
         cur = out; cur_ld = d.WC; cur_k = d.WC;
     }
     const int ll = P.n_layers - 1;
-    launch(agg_rgb_kernel, cdiv(Sm, 8), 256, 0, st, d, S_ptr, Sm, ws.csample, cur, cur_ld, weights[ll], biases[ll], ws.sigma, decoded, ws.sig);
+    launch(agg_rgb_kernel, item_grid(Sm), 256, 0, st, d, S_ptr, Sm, ws.csample, cur, cur_ld, weights[ll], biases[ll], ws.sigma, decoded, ws.sig);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }
@@ -264,15 +269,20 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     const float* Hlast = ws.H[nt - 1];
     const int la = P.alpha_layer;
     float* dZ = ws.dZ[0];
-    launch(agg_ksum_bwd_kernel, cdiv(Tm, 8), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast, ws.araw,
-                                                    weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf);
+    // also: weight + bias gradient of the alpha head and the bias gradient of the last tuple layer (reductions over the same rows)
+    if (d.W <= 256)
+        launch(agg_ksum_bwd_kernel<8>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast, ws.araw,
+               weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf, d_weights ? d_weights[la] : nullptr, d_biases ? d_biases[la] : nullptr,
+               d_biases ? d_biases[nt - 1] : nullptr);
+    else
+        launch(agg_ksum_bwd_kernel<AGG_MAX_W / 32>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast,
+               ws.araw, weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf, d_weights ? d_weights[la] : nullptr, d_biases ? d_biases[la] : nullptr,
+               d_biases ? d_biases[nt - 1] : nullptr);
     SGN_LAUNCH_CHECK();
     if (d_conf_coef && g.conf) {
         launch(agg_conf_out_bwd_kernel, cdiv(S * K, 256), 256, 0, st, pidx, S * K, d_conf_coef, g.conf);
         SGN_LAUNCH_CHECK();
     }
-    if ((rc = wgrad(ws.d_araw, 1, 1, Hlast, d.W, d.W, d_weights ? d_weights[la] : nullptr, d.W, T_ptr, Tm))) return rc;
-    if ((rc = bias_grad(ws.d_araw, 1, 1, T_ptr, Tm, d_biases ? d_biases[la] : nullptr))) return rc;
 
     // ---- per-tuple layers, last to first ----
     const float* dE7 = nullptr;
@@ -285,7 +295,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
             if ((rc = wgrad(dZ, d.W, d.W, ws.L, d.LD, d.LD, d_weights[t] + a_k, L.in, T_ptr, Tm))) return rc;
         if (L.extra == EXTRA_COLORDIR && d_weights)
             if ((rc = wgrad(dZ, d.W, d.W, ws.E7, 8, 7, d_weights[t] + a_k, L.in, T_ptr, Tm))) return rc;
-        if (t == nt - 1 && (rc = bias_grad(dZ, d.W, d.W, T_ptr, Tm, d_biases ? d_biases[t] : nullptr))) return rc;   // lower layers: fused below
+        // bias gradients: the last layer's comes out of agg_ksum_bwd_kernel, the lower layers' out of the dgrad epilogues below (colsum)
         if (L.extra == EXTRA_COLORDIR && (g.color || g.dir)) {
             GemmNN q = {};
             q.A1 = dZ; q.lda1 = d.W; q.B1 = ws.Wp[t] + a_kpad; q.ldb1 = L.kpad; q.K1 = d.W;
@@ -306,7 +316,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         }
     }
     if (g.embedding || g.color || g.dir) {
-        launch(agg_scatter_kernel, cdiv(Tm, 8), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
+        launch(agg_scatter_kernel, item_grid(Tm), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;

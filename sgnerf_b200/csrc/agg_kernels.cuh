@@ -132,8 +132,8 @@ agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict_
 {
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int flat = tuple_src[j];
     const int64_t s = flat / K;
     const int64_t r = s / SR;
@@ -191,6 +191,7 @@ agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict_
         else if (lane == 6) v = dx * vx + dy * vy + dz * vz;
         E7[j * 8 + lane] = v;
     }
+    }
 }
 
 // One warp per tuple: raw alpha = h . wa + ba   (alpha_branch, a single Linear)
@@ -200,12 +201,13 @@ agg_alpha_kernel(const float* __restrict__ H, int W, const float* __restrict__ w
 {
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     float acc = 0.f;
     for (int c = lane; c < W; c += 32) acc = fmaf(H[j * W + c], __ldg(wa + c), acc);
     acc = warp_sum(acc);
     if (lane == 0) araw[j] = acc + ba[0];
+    }
 }
 
 static __device__ __forceinline__ float softplus1(float x)  // torch.nn.Softplus(beta=1, threshold=20)
@@ -222,8 +224,8 @@ agg_ksum_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ 
 {
     const int lane = lane_id();
     const int Sv = min(*S_ptr, S_max);
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= Sv) return;
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < Sv; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int64_t s = csample[c];
     const int j0 = tuple_start[s], n = nvalid[s];
     const int W = d.W;
@@ -254,6 +256,7 @@ agg_ksum_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ 
     }
     for (int col = W + 6 * FV + lane; col < d.kc0pad; col += 32) row[col] = 0.f;
     if (lane == 0) sigma[c] = sg;
+    }
 }
 
 // One warp per compact sample: rgb = sigmoid(c . Wlast^T + b) (*1.002 - 0.001), decoded[s] = (sigma, rgb)
@@ -264,8 +267,8 @@ agg_rgb_kernel(AggDims d, const int32_t* __restrict__ S_ptr, int S_max, const in
 {
     const int lane = lane_id();
     const int Sv = min(*S_ptr, S_max);
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= Sv) return;
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < Sv; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int col = lane; col < Wc; col += 32) {
         const float x = Cin[c * Wc + col];
@@ -280,6 +283,7 @@ agg_rgb_kernel(AggDims d, const int32_t* __restrict__ S_ptr, int S_max, const in
         const int64_t s = csample[c];
         ((float4*)decoded)[s] = make_float4(sigma[c], s0 * m - o, s1 * m - o, s2 * m - o);
         if (sig_out) ((float4*)sig_out)[c] = make_float4(s0, s1, s2, 0.f);
+    }
     }
 }
 
@@ -376,17 +380,26 @@ agg_rgb_bwd_kernel(AggDims d, const int32_t* __restrict__ S_ptr, int S_max, cons
 
 // One warp per tuple: backward of ksum + alpha.  Writes dZ = dH (.) leaky'(H) for the last tuple layer,
 // d_araw[j], and accumulates d_conf (straight-through clamp: d conf_coef / d conf = 1).
-static __global__ void __launch_bounds__(256)
+// The three reductions over the tuples that read the same rows are folded in (they were separate passes over H and dZ): the weight and
+// bias gradient of the alpha head (d_wa[col] += da h[col], d_ba += da) and the bias gradient of the last tuple layer (d_blast = column
+// sums of dZ); partial sums per lane over the tuples its warp walks, per block through shared memory, then one red.add per column per block.
+template <int NC>                                  // columns per lane: W <= 32 * NC
+static __global__ void __launch_bounds__(256, 4)
 agg_ksum_bwd_kernel(AggIn in, AggDims d, int K, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
                     const int32_t* __restrict__ sample_cidx, const float* __restrict__ wc, const float* __restrict__ weight_n,
                     const float* __restrict__ H, const float* __restrict__ araw, const float* __restrict__ wa,
                     const float* __restrict__ dC0, int lddc0, const float* __restrict__ d_decoded, float* __restrict__ dZ,
-                    float* __restrict__ d_araw, float* __restrict__ d_conf)
+                    float* __restrict__ d_araw, float* __restrict__ d_conf, float* __restrict__ d_wa, float* __restrict__ d_ba,
+                    float* __restrict__ d_blast)
 {
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
+    // partial sums of the three reductions: a lane keeps those of its own columns over all the tuples its warp walks
+    float g_wa[NC], g_bl[NC], g_ba = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; i++) { g_wa[i] = 0.f; g_bl[i] = 0.f; }
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int flat = tuple_src[j];
     const int64_t s = flat / K;
     const int64_t c = sample_cidx[s];
@@ -405,19 +418,51 @@ agg_ksum_bwd_kernel(AggIn in, AggDims d, int K, const int32_t* __restrict__ T_pt
     const float da = w * dsig * dact;
     const int W = d.W;
     float dot = 0.f;
-    for (int col = lane; col < W; col += 32) {
-        const float h = H[j * W + col];
-        const float df = dC0[c * lddc0 + col];
-        dot = fmaf(h, df, dot);
-        const float dh = w * df + da * __ldg(wa + col);
-        dZ[j * W + col] = dh * (h > 0.f ? 1.0f : d.slope);
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        const int col = lane + 32 * i;
+        if (col < W) {
+            const float h = H[j * W + col];
+            const float df = dC0[c * lddc0 + col];
+            dot = fmaf(h, df, dot);
+            const float dh = w * df + da * __ldg(wa + col);
+            const float dz = dh * (h > 0.f ? 1.0f : d.slope);
+            dZ[j * W + col] = dz;
+            g_wa[i] = fmaf(da, h, g_wa[i]);
+            g_bl[i] += dz;
+        }
     }
     dot = warp_sum(dot);
     if (lane == 0) {
         d_araw[j] = da;
+        g_ba += da;
         if (d_conf) {
             const float d_wc = act * dsig + dot;
             atomicAdd(d_conf + in.pidx[flat], weight_n[flat] * d_wc);
+        }
+    }
+    }
+    if (!d_wa && !d_ba && !d_blast) return;
+    // block: sum the warps' partials column by column (two passes over one buffer), then one red.add per column per block
+    __shared__ float part[8][32 * NC + 1];
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int pass = 0; pass < 2; pass++) {
+        float* out = pass == 0 ? d_wa : d_blast;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NC; i++) part[wid][lane + 32 * i] = pass == 0 ? g_wa[i] : g_bl[i];
+        if (pass == 0 && lane == 0) part[wid][32 * NC] = g_ba;
+        __syncthreads();
+        if (out)
+            for (int col = threadIdx.x; col < d.W; col += blockDim.x) {
+                float a = 0.f;
+                for (int w2 = 0; w2 < nw; w2++) a += part[w2][col];
+                if (a != 0.f) atomicAdd(out + col, a);
+            }
+        if (pass == 0 && threadIdx.x == 0 && d_ba) {
+            float a = 0.f;
+            for (int w2 = 0; w2 < nw; w2++) a += part[w2][32 * NC];
+            if (a != 0.f) atomicAdd(d_ba, a);
         }
     }
 }
@@ -454,8 +499,8 @@ agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict
 {
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
-    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (j >= T) return;
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     const int flat = tuple_src[j];
     const int64_t p = in.pidx[flat];
     const int C = d.C, F = d.F;
@@ -479,6 +524,7 @@ agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict
             const int64_t r = (flat / K) / SR;
             atomicAdd(g.dir + 3 * p + (lane - 3), e[lane] + in.raydir[3 * r + (lane - 3)] * e[6]);
         }
+    }
     }
 }
 
