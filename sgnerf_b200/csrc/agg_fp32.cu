@@ -60,10 +60,19 @@ static int run_gemm_tn(const GemmTN& t, bool tc, cudaStream_t st)
 
 static int pack_weights(const AggPlan& P, const float* const* weights, AggWs& ws, cudaStream_t st)
 {
-    for (int l = 0; l < P.n_layers; l++) {
-        const LayerInfo& L = P.layers[l];
-        const int n = L.npad * L.kpad;
-        launch(pack_weight_kernel, cdiv(n, 256), 256, 0, st, weights[l], L.out, L.in, L.npad, L.kpad, ws.Wt[l], ws.Wp[l]);
+    if (P.n_layers <= 16) {
+        PackJobs J = {};
+        for (int l = 0; l < P.n_layers; l++) {
+            const LayerInfo& L = P.layers[l];
+            J.W[l] = weights[l]; J.Wt[l] = ws.Wt[l]; J.Wp[l] = ws.Wp[l]; J.N[l] = L.out; J.Kin[l] = L.in; J.Npad[l] = L.npad; J.Kpad[l] = L.kpad;
+        }
+        launch(pack_weights_kernel, dim3(64, P.n_layers), 256, 0, st, J);
+    } else {
+        for (int l = 0; l < P.n_layers; l++) {
+            const LayerInfo& L = P.layers[l];
+            const int n = L.npad * L.kpad;
+            launch(pack_weight_kernel, cdiv(n, 256), 256, 0, st, weights[l], L.out, L.in, L.npad, L.kpad, ws.Wt[l], ws.Wp[l]);
+        }
     }
     SGN_LAUNCH_CHECK();
     return SGN_OK;
@@ -86,7 +95,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
     launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
-    launch(agg_gather_kernel, item_grid(Tm), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
+    launch(agg_gather_kernel, item_grid(Tm), 256, (size_t)8 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
     SGN_LAUNCH_CHECK();
 
     // per-tuple layers
@@ -316,7 +325,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         }
     }
     if (g.embedding || g.color || g.dir) {
-        launch(agg_scatter_kernel, item_grid(Tm), 256, 0, st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
+        launch(agg_scatter_kernel, item_grid(Tm), 256, (size_t)16 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;

@@ -130,6 +130,8 @@ static __global__ void __launch_bounds__(256)
 agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
                   const float* __restrict__ loc_pers, float* __restrict__ X0, float* __restrict__ L, float* __restrict__ E7)
 {
+    extern __shared__ float4 rowbuf4[];                // 8 warps x k0pad floats (dynamic)
+    float* rowbuf = (float*)rowbuf4;
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
     // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
@@ -138,17 +140,21 @@ agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict_
     const int64_t s = flat / K;
     const int64_t r = s / SR;
     const int64_t p = in.pidx[flat];
-    float* x = X0 + j * d.k0pad;
+    // the row is put together in shared memory (its sin / cos columns interleave with a stride of 2 F floats) and leaves as whole float4s
+    float* x = rowbuf + (threadIdx.x >> 5) * d.k0pad;
     const int C = d.C, F = d.F, FD = d.FD;
     for (int c = lane; c < C; c += 32) {
         const float e = __ldg(in.tab.embedding + p * C + c);
         x[c] = e;
-        float fr = 1.0f;
+        // sin / cos of e 2^f: one sincosf, then the double-angle recurrence (|error| grows ~2x per octave from 1 ulp: < 1e-6 at F <= 5)
+        float sn, cs;
+        sincosf(e, &sn, &cs);
         for (int f = 0; f < F; f++) {
-            const float a = e * fr;
-            x[C + 2 * (c * F + f)] = sinf(a);
-            x[C + 2 * (c * F + f) + 1] = cosf(a);
-            fr *= 2.0f;
+            x[C + 2 * (c * F + f)] = sn;
+            x[C + 2 * (c * F + f) + 1] = cs;
+            const float s2 = 2.0f * sn * cs;
+            cs = fmaf(-2.0f * sn, sn, 1.0f);
+            sn = s2;
         }
     }
     const int base = C + 2 * C * F;
@@ -168,15 +174,24 @@ agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict_
             const float lxp = loc_pers[3 * s], lyp = loc_pers[3 * s + 1], lzp = loc_pers[3 * s + 2];
             dist = lane == 3 ? xp * zp - lxp * lzp : (lane == 4 ? yp * zp - lyp * lzp : zp - lzp);
         }
-        float fr = 1.0f;
+        float sn, cs;
+        sincosf(dist, &sn, &cs);
         for (int f = 0; f < FD; f++) {
-            const float a = dist * fr;
-            x[base + 2 * (lane * FD + f)] = sinf(a);
-            x[base + 2 * (lane * FD + f) + 1] = cosf(a);
-            fr *= 2.0f;
+            x[base + 2 * (lane * FD + f)] = sn;
+            x[base + 2 * (lane * FD + f) + 1] = cs;
+            const float s2 = 2.0f * sn * cs;
+            cs = fmaf(-2.0f * sn, sn, 1.0f);
+            sn = s2;
         }
     }
     for (int c = d.k0 + lane; c < d.k0pad; c += 32) x[c] = 0.f;
+    __syncwarp();
+    {
+        float4* dst = (float4*)(X0 + j * d.k0pad);
+        const float4* src = (const float4*)x;
+        for (int i = lane; i < (d.k0pad >> 2); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
     if (L) {
         for (int c = lane; c < d.LD; c += 32) L[j * d.LD + c] = __ldg(in.tab.label_emb + p * d.LD + c);
     }
@@ -296,6 +311,24 @@ static __global__ void pack_weight_kernel(const float* __restrict__ W, int N, in
     const float v = (n < N && k < Kin) ? W[(size_t)n * Kin + k] : 0.f;
     Wp[(size_t)n * Kpad + k] = v;
     Wt[(size_t)k * Npad + n] = v;
+}
+
+// All layers in one launch: blockIdx.y = layer.
+struct PackJobs {
+    const float* W[16]; float* Wt[16]; float* Wp[16];
+    int N[16], Kin[16], Npad[16], Kpad[16];
+};
+static __global__ void pack_weights_kernel(PackJobs J)
+{
+    const int l = blockIdx.y;
+    const int Npad = J.Npad[l], Kpad = J.Kpad[l], N = J.N[l], Kin = J.Kin[l];
+    const float* __restrict__ W = J.W[l];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad * Kpad; i += gridDim.x * blockDim.x) {
+        const int n = i / Kpad, k = i - n * Kpad;
+        const float v = (n < N && k < Kin) ? W[(size_t)n * Kin + k] : 0.f;
+        J.Wp[l][(size_t)n * Kpad + k] = v;
+        J.Wt[l][(size_t)k * Npad + n] = v;
+    }
 }
 
 // ---- backward-only kernels ----
@@ -497,6 +530,8 @@ static __global__ void __launch_bounds__(256)
 agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
                    const float* __restrict__ X0, const float* __restrict__ dX0, const float* __restrict__ dE7, SgnPointGrads g)
 {
+    extern __shared__ float4 rowbuf4[];                // 8 warps x 2 x k0pad floats (dynamic)
+    float* rowbuf = (float*)rowbuf4;
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
     // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
@@ -505,8 +540,15 @@ agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict
     const int64_t p = in.pidx[flat];
     const int C = d.C, F = d.F;
     if (g.embedding) {
-        const float* x = X0 + j * d.k0pad;
-        const float* dx = dX0 + j * d.k0pad;
+        // both rows arrive as whole float4s; the sin / cos columns are then read from shared memory
+        float* x = rowbuf + (threadIdx.x >> 5) * 2 * d.k0pad;
+        float* dx = x + d.k0pad;
+        {
+            const float4* sx = (const float4*)(X0 + j * d.k0pad);
+            const float4* sd = (const float4*)(dX0 + j * d.k0pad);
+            for (int i = lane; i < (d.k0pad >> 2); i += 32) { ((float4*)x)[i] = sx[i]; ((float4*)dx)[i] = sd[i]; }
+        }
+        __syncwarp();
         for (int c = lane; c < C; c += 32) {
             float acc = dx[c], fr = 1.0f;
             for (int f = 0; f < F; f++) {
@@ -516,6 +558,7 @@ agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict
             }
             atomicAdd(g.embedding + p * C + c, acc);
         }
+        __syncwarp();
     }
     if (dE7) {
         const float* e = dE7 + j * 8;
