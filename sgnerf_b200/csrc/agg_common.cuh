@@ -92,6 +92,8 @@ struct AggWs {
     float *loc_pers, *weight_n, *wc;
     float *X0, *L, *E7, *araw, *C0, *sigma, *sig;
     float* H[AGG_MAX_LAYERS];
+    uint32_t* HM[AGG_MAX_LAYERS];   // sign bits of H[t] / CH[c] (training, tensor-core path): what the dgrad epilogues read instead of the activations
+    uint32_t* CM[AGG_MAX_LAYERS];
     float* CH[AGG_MAX_LAYERS];
     float* Wt[AGG_MAX_LAYERS];
     float* Wp[AGG_MAX_LAYERS];
@@ -129,6 +131,8 @@ static inline size_t carve_ws(const AggPlan& P, int64_t Rc, int SR, int K, bool 
         ws->Wp[l] = A.take<float>((size_t)P.layers[l].kpad * P.layers[l].npad);
     }
     if (save) {
+        for (int i = 0; i < nH; i++) ws->HM[i] = A.take<uint32_t>(T * (size_t)((d.W + 31) / 32));
+        for (int i = 0; i < nC; i++) ws->CM[i] = A.take<uint32_t>(S * (size_t)((d.WC + 31) / 32));
         ws->dZ[0] = A.take<float>(T * d.W);
         ws->dZ[1] = A.take<float>(T * d.W);
         ws->dX0 = A.take<float>(T * d.k0pad);

@@ -23,6 +23,9 @@ struct GemmNN {
     const float* aux; int ldaux;  // saved activation for EPI_MUL_DLEAKY: C *= (aux > 0 ? 1 : slope)
     int epi; float slope;
     float* colsum;            // optional [N]: += column sums of the stored C over the valid rows (bias gradient of the next wgrad); tensor-core path only
+    // sign bits of the stored C, one 32-bit word per 32 columns ([M, ldmask] words): written by EPI_BIAS_LEAKY (mask_out), read instead of `aux`
+    // by EPI_MUL_DLEAKY (mask_in) -- 1/32 of the bytes of the activation itself.  Tensor-core path only; N must be a multiple of 32.
+    uint32_t* mask_out; const uint32_t* mask_in; int ldmask;
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 8, GTHREADS = 256, GPAD = 4;

@@ -57,6 +57,12 @@ __device__ __forceinline__ float4 lds128f_v(uint32_t addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ float lds_f32_v(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
 
 // 2-D TMA tile load (cp.async.bulk.tensor): box {32 floats, rows} at element (k0, row0) of the tensor behind `map`, SWIZZLE_128B, bytes
@@ -97,13 +103,14 @@ static inline int make_tmap_f32(CUtensorMap* map, const float* base, int64_t row
 
 // ------------------------------------------------------------------------------------------------ nn
 struct GemmTcNN {
-    alignas(64) CUtensorMap mA1, mB1, mA2, mB2;                        // boxes: A {32, 128}, Bt {32, BN}
+    alignas(64) CUtensorMap mA1, mB1, mA2, mB2, mC;                    // boxes: A {32, 128}, Bt {32, BN}, C {32, 32} (stores)
     const float* A1; int lda1; const float* Bt1; int ldb1; int K1;     // Bt: [N, ldb], K contiguous
     const float* A2; int lda2; const float* Bt2; int ldb2; int K2;
     float* C; int ldc; int N; int BN;                                  // BN = columns per CTA (multiple of 16, <= 256)
     const int* m_ptr; int m_max;
     const float* bias; const float* aux; int ldaux; int epi; float slope;
     float* colsum;                                                     // optional [N]: += column sums of the stored C (valid rows)
+    uint32_t* mask_out; const uint32_t* mask_in; int ldmask;           // sign bits of C (see GemmNN)
 };
 
 constexpr int NN_STAGES = 4;
@@ -185,79 +192,97 @@ static __global__ void __launch_bounds__(NN_THREADS, 1) gemm_tc_nn_kernel(const 
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: TMEM -> swizzled staging -> coalesced rows
+        // ------------------------------------------------------------------ epilogue: TMEM -> registers (one row per lane) -> swizzled staging
+        // -> TMA tile store.  A lane owns row `lane` of its warp's 32 x 32 chunk: bias / LeakyReLU / the dLeakyReLU factor are applied in
+        // registers, the row's 32 sign bits are one word (written for the forward layers, read by the dgrad ones), column sums (bias
+        // gradients) are taken from the staged tile.  Rows past *m_ptr (but inside m_max) are stored too: nothing reads them.
         // two warps per TMEM lane quarter (a warp reaches the 32 lanes of quarter warp % 4): the first takes column chunks 0-3, the second 4-7
         const int quarter = warp & 3, half = warp >> 2;
         const uint32_t stg = sbase + NN_OFF_EPI + (quarter + 4 * half) * 4096;
-        const int c4 = lane & 7, rsub = lane >> 3;
-        float4 cs[8];                                          // column sums of what this thread stores (chunk ch, columns 4 c4 .. + 3)
-#pragma unroll
-        for (int i = 0; i < 8; i++) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};                    // column sums: chunk 4 * half + i, column `lane`
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x, tl++) {
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
             const int m0 = (tile << 7) + quarter * 32;
+            const int m = m0 + lane;
             mbar_wait(bar_accf + 8 * acc, aph);
             tc_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < 8; ch++) {
-                if ((ch >> 2) != half) continue;
+            for (int i = 0; i < 4; i++) {
+                const int ch = 4 * half + i;
                 if (ch * 32 >= p.BN) break;
-                const int nl = ch * 32 + 4 * c4;              // column inside this CTA's BN columns
-                const int n = n0 + nl;
-                const bool ncol = nl < p.BN && n < p.N;
-                // saved activations of this chunk (dLeakyReLU mask): all eight loads in flight before the accumulators are touched
-                float4 ax[8];
-                if (p.epi == EPI_MUL_DLEAKY) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int m = m0 + 4 * i + rsub;
-                        ax[i] = (ncol && m < M) ? __ldg((const float4*)(p.aux + (size_t)m * p.ldaux + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
+                const int nc0 = n0 + ch * 32;                  // first column of the chunk
+                if (nc0 >= p.N) break;
+                uint32_t mword = 0u;
+                if (p.epi == EPI_MUL_DLEAKY && p.mask_in && m < M) mword = __ldg(p.mask_in + (size_t)m * p.ldmask + (nc0 >> 5));
                 uint32_t v[32];
                 tc_ld32(tmem_base + acc * 256 + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), v);
+                float x[32];
 #pragma unroll
-                for (int q = 0; q < 8; q++) sts128(stg + lane * 128 + ((q ^ (lane & 7)) << 4), v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                __syncwarp();
-                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ncol && (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LEAKY)) bb = __ldg((const float4*)(p.bias + n));
+                for (int c = 0; c < 32; c++) x[c] = __uint_as_float(v[c]);
+                if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LEAKY) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int row = 4 * i + rsub;
-                    float4 x = lds128f_v(stg + row * 128 + ((c4 ^ (row & 7)) << 4));
-                    const int m = m0 + row;
-                    if (ncol && m < M) {
-                        if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_LEAKY) {
-                            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                            if (p.epi == EPI_BIAS_LEAKY) {
-                                x.x = x.x > 0.f ? x.x : x.x * p.slope; x.y = x.y > 0.f ? x.y : x.y * p.slope;
-                                x.z = x.z > 0.f ? x.z : x.z * p.slope; x.w = x.w > 0.f ? x.w : x.w * p.slope;
-                            }
-                        } else if (p.epi == EPI_MUL_DLEAKY) {
-                            const float4 a = ax[i];
-                            x.x *= a.x > 0.f ? 1.f : p.slope; x.y *= a.y > 0.f ? 1.f : p.slope;
-                            x.z *= a.z > 0.f ? 1.f : p.slope; x.w *= a.w > 0.f ? 1.f : p.slope;
+                    for (int q = 0; q < 8; q++) {
+                        if (nc0 + 4 * q < p.N) {
+                            const float4 bb = __ldg((const float4*)(p.bias + nc0 + 4 * q));
+                            x[4 * q] += bb.x; x[4 * q + 1] += bb.y; x[4 * q + 2] += bb.z; x[4 * q + 3] += bb.w;
                         }
-                        *(float4*)(p.C + (size_t)m * p.ldc + n) = x;
-                        cs[ch].x += x.x; cs[ch].y += x.y; cs[ch].z += x.z; cs[ch].w += x.w;
+                    }
+                    if (p.epi == EPI_BIAS_LEAKY) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) x[c] = x[c] > 0.f ? x[c] : x[c] * p.slope;
+                    }
+                } else if (p.epi == EPI_MUL_DLEAKY) {
+                    if (p.mask_in) {
+#pragma unroll
+                        for (int c = 0; c < 32; c++) x[c] *= ((mword >> c) & 1u) ? 1.f : p.slope;
+                    } else if (m < M) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (nc0 + 4 * q < p.N) {
+                                const float4 a = __ldg((const float4*)(p.aux + (size_t)m * p.ldaux + nc0 + 4 * q));
+                                x[4 * q] *= a.x > 0.f ? 1.f : p.slope; x[4 * q + 1] *= a.y > 0.f ? 1.f : p.slope;
+                                x[4 * q + 2] *= a.z > 0.f ? 1.f : p.slope; x[4 * q + 3] *= a.w > 0.f ? 1.f : p.slope;
+                            }
+                        }
                     }
                 }
+                if (p.mask_out && m < M) {
+                    uint32_t word = 0u;
+#pragma unroll
+                    for (int c = 0; c < 32; c++) word |= (x[c] > 0.f ? 1u : 0u) << c;
+                    p.mask_out[(size_t)m * p.ldmask + (nc0 >> 5)] = word;
+                }
+                // the staging tile is free once the previous chunk's TMA store has read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    sts128(stg + lane * 128 + ((q ^ (lane & 7)) << 4), __float_as_uint(x[4 * q]), __float_as_uint(x[4 * q + 1]), __float_as_uint(x[4 * q + 2]),
+                           __float_as_uint(x[4 * q + 3]));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&p.mC), "r"(nc0), "r"(m0), "r"(stg) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (p.colsum) {
+                    // column `lane` of the staged tile over its valid rows (a row of the tile is 128 contiguous bytes: no bank conflicts)
+                    const int rows = min(32, M - m0);
+                    float a = 0.f;
+                    for (int r = 0; r < rows; r++) a += lds_f32_v(stg + r * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)r & 7)) << 4) + ((uint32_t)lane & 3) * 4);
+                    cs[i] += a;
+                }
             }
             tc_fence_before();
             mbar_arrive(bar_acce + 8 * acc);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.colsum) {
 #pragma unroll
-            for (int ch = 0; ch < 8; ch++) {
-                float4 v = cs[ch];                             // the four row phases (lane >> 3) hold the same columns
-                v.x += __shfl_xor_sync(0xffffffffu, v.x, 8); v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
-                v.z += __shfl_xor_sync(0xffffffffu, v.z, 8); v.w += __shfl_xor_sync(0xffffffffu, v.w, 8);
-                v.x += __shfl_xor_sync(0xffffffffu, v.x, 16); v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
-                v.z += __shfl_xor_sync(0xffffffffu, v.z, 16); v.w += __shfl_xor_sync(0xffffffffu, v.w, 16);
-                const int nl = ch * 32 + 4 * c4, n = n0 + nl;
-                if (rsub == 0 && nl < p.BN && n < p.N) red_add_v4(p.colsum + n, v.x, v.y, v.z, v.w);
+            for (int i = 0; i < 4; i++) {
+                const int n = n0 + (4 * half + i) * 32 + lane;
+                if ((4 * half + i) * 32 < p.BN && n < p.N && cs[i] != 0.f) red_add_f32(p.colsum + n, cs[i]);
             }
         }
     }
@@ -275,6 +300,7 @@ static inline bool gemm_tc_nn_ok(const GemmNN& g)
     if (g.epi == EPI_MUL_DLEAKY && ((g.ldaux & 3) || !al(g.aux))) return false;
     if ((g.epi == EPI_BIAS || g.epi == EPI_BIAS_LEAKY) && !al(g.bias)) return false;
     if (g.colsum && !al(g.colsum)) return false;
+    if ((g.mask_out || g.mask_in) && (g.N & 31)) return false;
     return true;
 }
 
@@ -293,12 +319,15 @@ static inline int launch_gemm_tc_nn(const GemmNN& g, cudaStream_t st)
     p.A2 = g.A2; p.lda2 = g.lda2; p.Bt2 = g.Bt2; p.ldb2 = g.ldbt2; p.K2 = g.K2;
     p.C = g.C; p.ldc = g.ldc; p.N = g.N; p.m_ptr = g.m_ptr; p.m_max = g.m_max;
     p.bias = g.bias; p.aux = g.aux; p.ldaux = g.ldaux; p.epi = g.epi; p.slope = g.slope; p.colsum = g.colsum;
+    p.mask_out = g.mask_out; p.mask_in = g.mask_in; p.ldmask = g.ldmask;
     const int nsplit = cdiv(g.N, 256);
-    p.BN = (cdiv(g.N, nsplit) + 15) / 16 * 16;
+    // columns per CTA: the epilogue stores whole 32-column chunks (TMA clips at N), so a split must fall on a multiple of 32
+    p.BN = nsplit > 1 ? (cdiv(g.N, nsplit) + 31) / 32 * 32 : (g.N + 15) / 16 * 16;
     int rc = make_tmap_f32(&p.mA1, g.A1, g.m_max, g.K1, g.lda1, 128);
     if (!rc) rc = make_tmap_f32(&p.mB1, g.Bt1, g.N, g.K1, g.ldbt1, p.BN);
     if (!rc && g.A2) rc = make_tmap_f32(&p.mA2, g.A2, g.m_max, g.K2, g.lda2, 128);
     if (!rc && g.A2) rc = make_tmap_f32(&p.mB2, g.Bt2, g.N, g.K2, g.ldbt2, p.BN);
+    if (!rc) rc = make_tmap_f32(&p.mC, g.C, g.m_max, g.N, g.ldc, 32);
     if (rc) return rc;
     const int tiles = cdiv(g.m_max, 128);
     const int gx = tiles < 148 / nsplit ? tiles : 148 / nsplit;
