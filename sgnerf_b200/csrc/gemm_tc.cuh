@@ -74,7 +74,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 }
 
 // Row-major fp32 matrix [rows, cols] with leading dimension ld (floats) as a tensor map whose box is 32 columns x box_rows rows
-static inline int make_tmap_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows)
+static inline int make_tmap_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                                CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -93,7 +94,7 @@ static inline int make_tmap_f32(CUtensorMap* map, const float* base, int64_t row
     const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %lld] matrix, ld %lld, box rows %d", (int)r, (long long)rows, (long long)cols, (long long)ld, box_rows);
         return SGN_E_CUDA;
@@ -338,10 +339,12 @@ static inline int launch_gemm_tc_nn(const GemmNN& g, cudaStream_t st)
 
 // ------------------------------------------------------------------------------------------------ tn (wgrad)
 struct GemmTcTN {
+    alignas(64) CUtensorMap mA, mB;        // boxes {32 columns, 32 m-rows}, SWIZZLE_128B_ATOM_32B: one box = one MN atom of a stage
     const float* A; int lda; int P;        // dZ  [M, lda], P columns used (multiple of 32, <= 256)
     const float* B; int ldb; int Q;        // act [M, ldb], Q columns used
     float* C; int ldc;                     // grad [P, ldc] (+=)
     const int* m_ptr; int m_max; int BQ;   // BQ = columns of B per CTA (multiple of 16, <= 256)
+    int vec;                               // gradient rows are 16-byte aligned: the epilogue reduces with red.global.add.v4.f32
 };
 
 constexpr int TN_STAGES = 3;
@@ -350,9 +353,9 @@ constexpr int TN_A_BYTES = 8 * TN_ATOM, TN_B_BYTES = 8 * TN_ATOM, TN_STAGE_BYTES
 constexpr int TN_OFF_EPI = TN_STAGES * TN_STAGE_BYTES;             // 4 warps x 32 x 33 floats
 constexpr int TN_EPI_WARP = 32 * 33 * 4;
 constexpr int TN_OFF_BAR = TN_OFF_EPI + 4 * TN_EPI_WARP + 128;
-constexpr int TN_SMEM = TN_OFF_BAR + 256 + 1024;
+constexpr int TN_SMEM = TN_OFF_BAR + 256 + 1024;     // barriers: full[3], empty[3], done, tail, the TMEM address
 
-static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_tn_kernel(GemmTcTN p)
+static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_tn_kernel(const __grid_constant__ GemmTcTN p)
 {
     const int M = min(*p.m_ptr, p.m_max);
     const int mpb = ((M + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31;
@@ -364,11 +367,12 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_tn_kernel(GemmTc
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_full = sbase + TN_OFF_BAR, bar_empty = bar_full + 8 * TN_STAGES, bar_done = bar_empty + 8 * TN_STAGES;
+    const uint32_t bar_full = sbase + TN_OFF_BAR, bar_empty = bar_full + 8 * TN_STAGES, bar_done = bar_empty + 8 * TN_STAGES, bar_tail = bar_done + 8;
     uint32_t* tmem_ptr_smem = (uint32_t*)(smem + TN_OFF_BAR + 8 * (2 * TN_STAGES + 2));
     if (tid == 0) {
-        for (int s = 0; s < TN_STAGES; s++) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < TN_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_done, 1);
+        mbar_init(bar_tail, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -385,38 +389,35 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_tn_kernel(GemmTc
     const int nhalf = (p.P + 127) >> 7;
 
     if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ loaders: rows of m, 128-byte segments, BASE32B swizzle
-        const int lt = tid - 128;
-        const int jj = lt & 7, r0 = lt >> 3;                   // 16-byte piece of a 128-byte segment; m-rows r0 and r0 + 16
-        for (int i = 0; i < nst; i++) {
-            const uint32_t s = i % TN_STAGES, ph = (i / TN_STAGES) & 1;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);
-            const uint32_t sa = sbase + s * TN_STAGE_BYTES, sb = sa + TN_A_BYTES;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int row = r0 + 16 * h;
-                const int m = mb + (i << 5) + row;
-                const bool live = m < me;
-                const uint32_t off = row * 128 + ((((uint32_t)jj >> 1) ^ (row & 3)) << 5) + (jj & 1) * 16;
-                const float* arow = p.A + (size_t)(live ? m : mb) * p.lda + 4 * jj;
-                const float* brow = p.B + (size_t)(live ? m : mb) * p.ldb;
-                for (int a = 0; a < atoms_a; a++) cp_async16(sa + a * TN_ATOM + off, arow + 32 * a, live ? 16u : 0u);
-                for (int b = 0; b < atoms_b; b++) {
-                    const int col = q0 + 32 * b + 4 * jj;
-                    const bool in = live && col + 4 <= p.ldb;
-                    cp_async16(sb + b * TN_ATOM + off, in ? brow + col : p.B, in ? 16u : 0u);
+        // ------------------------------------------------------------------ producer (warp 4): one TMA box per MN atom (32 columns x 32 m-rows,
+        // 128-byte rows, 32-byte chunk ^= row & 3: the tensor core's MN-major layout for 32-bit operands).  The CTA's last stage may reach past
+        // its m range (the row count lives on the device, the tensor map only knows m_max): its extra rows are zeroed in shared memory.
+        if (warp == 4) {
+            const uint32_t stage_bytes = (uint32_t)(atoms_a + atoms_b) * TN_ATOM;
+            for (int i = 0; i < nst; i++) {
+                const uint32_t s = i % TN_STAGES, ph = (i / TN_STAGES) & 1;
+                const uint32_t sa = sbase + s * TN_STAGE_BYTES, sb = sa + TN_A_BYTES;
+                const int m0 = mb + (i << 5);
+                const int live = min(32, me - m0);
+                const uint32_t bar = live == 32 ? bar_full + 8 * s : bar_tail;
+                if (lane == 0) {
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    mbar_expect_tx(bar, stage_bytes);
+                    for (int a = 0; a < atoms_a; a++) tma_load_2d(sa + a * TN_ATOM, &p.mA, 32 * a, m0, bar);
+                    for (int b = 0; b < atoms_b; b++) tma_load_2d(sb + b * TN_ATOM, &p.mB, q0 + 32 * b, m0, bar);
+                }
+                if (live < 32) {
+                    mbar_wait(bar_tail, 0);
+                    for (int at = 0; at < atoms_a + atoms_b; at++) {
+                        const uint32_t base = at < atoms_a ? sa + at * TN_ATOM : sb + (at - atoms_a) * TN_ATOM;
+                        for (int idx = lane; idx < (32 - live) * 8; idx += 32) sts128(base + (live + (idx >> 3)) * 128 + (idx & 7) * 16, 0u, 0u, 0u, 0u);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full + 8 * s);
                 }
             }
-            cp_async_commit();
-            if (i >= GT_LAG) {
-                cp_async_wait<GT_LAG>();
-                fence_proxy_async();
-                mbar_arrive(bar_full + 8 * ((i - GT_LAG) % TN_STAGES));
-            }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (int j = nst > GT_LAG ? nst - GT_LAG : 0; j < nst; j++) mbar_arrive(bar_full + 8 * (j % TN_STAGES));
     } else if (warp == 8) {
         if (lane == 0) {
             const uint32_t idesc = tc_idesc_tf32(128, p.BQ, 1, 1);
@@ -435,29 +436,59 @@ static __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tc_tn_kernel(GemmTc
             tc_commit(bar_done);
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: TMEM -> padded staging -> coalesced reductions
-        const uint32_t stg = sbase + TN_OFF_EPI + warp * TN_EPI_WARP;
-        mbar_wait(bar_done, 0);
-        tc_fence_after();
-        const int qend = min(p.Q, q0 + p.BQ);
-        for (int h = 0; h < nhalf; h++) {
-            const int prow0 = h * 128 + warp * 32;
-            for (int ch = 0; ch * 32 < p.BQ; ch++) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + h * 256 + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
-#pragma unroll
-                for (int j = 0; j < 32; j++) sts32(stg + (lane * 33 + j) * 4, v[j]);
-                __syncwarp();
-                const int q = q0 + ch * 32 + lane;
-                if (q < qend) {
-#pragma unroll 8
-                    for (int r = 0; r < 32; r++) {
-                        const int pp = prow0 + r;
-                        if (pp < p.P) red_add_f32(p.C + (size_t)pp * p.ldc + q, ldsf(stg + (r * 33 + lane) * 4));
+        if (p.vec) {
+            // ------------------------------------------------------------------ epilogue: TMEM -> registers -> vector reductions.  A lane holds 32
+            // consecutive columns of one gradient row: eight red.global.add.v4.f32 (a quarter of the L2 atomic operations of scalar reds; every CTA
+            // of the grid adds into the same [P, Q] block, so the atomic units are what this phase waits for)
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+            const int qend = min(p.Q, q0 + p.BQ);
+            for (int h = 0; h < nhalf; h++) {
+                const int pp = h * 128 + warp * 32 + lane;
+                for (int ch = 0; ch * 32 < p.BQ; ch++) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + h * 256 + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+                    if (pp < p.P) {
+                        float* row = p.C + (size_t)pp * p.ldc;
+    #pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int q = q0 + ch * 32 + 4 * j;
+                            if (q + 3 < qend && (((uintptr_t)(row + q)) & 15) == 0)
+                                red_add_v4(row + q, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            else
+                                for (int e = 0; e < 4; e++)
+                                    if (q + e < qend) red_add_f32(row + q + e, __uint_as_float(v[4 * j + e]));
+                        }
                     }
                 }
-                __syncwarp();
             }
+    
+        } else {
+            // ------------------------------------------------------------------ epilogue: TMEM -> padded staging -> coalesced reductions
+            const uint32_t stg = sbase + TN_OFF_EPI + warp * TN_EPI_WARP;
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+            const int qend = min(p.Q, q0 + p.BQ);
+            for (int h = 0; h < nhalf; h++) {
+                const int prow0 = h * 128 + warp * 32;
+                for (int ch = 0; ch * 32 < p.BQ; ch++) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + h * 256 + (uint32_t)(ch * 32) + ((uint32_t)(warp * 32) << 16), v);
+    #pragma unroll
+                    for (int j = 0; j < 32; j++) sts32(stg + (lane * 33 + j) * 4, v[j]);
+                    __syncwarp();
+                    const int q = q0 + ch * 32 + lane;
+                    if (q < qend) {
+    #pragma unroll 8
+                        for (int r = 0; r < 32; r++) {
+                            const int pp = prow0 + r;
+                            if (pp < p.P) red_add_f32(p.C + (size_t)pp * p.ldc + q, ldsf(stg + (r * 33 + lane) * 4));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+    
         }
     }
     tc_fence_before();
@@ -485,6 +516,10 @@ static inline int launch_gemm_tc_tn(const GemmTN& t, cudaStream_t st)
     p.A = t.A; p.lda = t.lda; p.P = t.P; p.B = t.B; p.ldb = t.ldb; p.Q = t.Q; p.C = t.C; p.ldc = t.ldc; p.m_ptr = t.m_ptr; p.m_max = t.m_max;
     const int nq = cdiv(t.Q, 256);
     p.BQ = (cdiv(t.Q, nq) + 15) / 16 * 16;
+    p.vec = (t.ldc & 3) == 0 && ((uintptr_t)t.C & 15) == 0;
+    int rc = make_tmap_f32(&p.mA, t.A, t.m_max, t.P, t.lda, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (!rc) rc = make_tmap_f32(&p.mB, t.B, t.m_max, t.ldb, t.ldb, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
     int gx = 148 / nq;
     const int most = cdiv(t.m_max, 32);
     if (gx > most) gx = most;
