@@ -89,6 +89,7 @@ struct AggIn {
 // fp32-path workspace.  Sized for the worst case (every slot valid) so nothing depends on device counts.
 struct AggWs {
     int32_t *nvalid, *svalid, *tuple_start, *sample_cidx, *partials, *tuple_src, *csample;
+    int32_t *tuple_pt, *tuple_cs;   // per compact tuple: its point, its compact sample
     float *loc_pers, *weight_n, *wc;
     float *X0, *L, *E7, *araw, *C0, *sigma, *sig;
     float* H[AGG_MAX_LAYERS];
@@ -112,6 +113,8 @@ static inline size_t carve_ws(const AggPlan& P, int64_t Rc, int SR, int K, bool 
     ws->sample_cidx = A.take<int32_t>(S + 1);
     ws->partials = A.take<int32_t>(2 * scan_partials_count((int64_t)S));
     ws->tuple_src = A.take<int32_t>(T + 1);
+    ws->tuple_pt = A.take<int32_t>(T + 1);
+    ws->tuple_cs = A.take<int32_t>(T + 1);
     ws->csample = A.take<int32_t>(S + 1);
     ws->loc_pers = A.take<float>(S * 3);
     ws->weight_n = A.take<float>(T);

@@ -119,8 +119,8 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     if ((rc = exclusive_scan_pair_i32(ws.nvalid, ws.tuple_start, ws.sample_cidx, S, ws.partials, st))) return rc;
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
-    launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
-    launch(agg_gather_kernel, item_grid(Tm), 256, (size_t)8 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
+    launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample, ws.tuple_pt, ws.tuple_cs);
+    launch(agg_gather_kernel, item_grid(Tm), 256, (size_t)8 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.tuple_pt, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
     SGN_LAUNCH_CHECK();
 
     // per-tuple layers
@@ -311,11 +311,11 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     float* dZ = ws.dZ[0];
     // also: weight + bias gradient of the alpha head and the bias gradient of the last tuple layer (reductions over the same rows)
     if (d.W <= 256)
-        launch(agg_ksum_bwd_kernel<8>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast, ws.araw,
+        launch(agg_ksum_bwd_kernel<8>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.tuple_cs, ws.wc, ws.weight_n, Hlast, ws.araw,
                weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf, d_weights ? d_weights[la] : nullptr, d_biases ? d_biases[la] : nullptr,
                d_biases ? d_biases[nt - 1] : nullptr);
     else
-        launch(agg_ksum_bwd_kernel<AGG_MAX_W / 32>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.sample_cidx, ws.wc, ws.weight_n, Hlast,
+        launch(agg_ksum_bwd_kernel<AGG_MAX_W / 32>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.tuple_cs, ws.wc, ws.weight_n, Hlast,
                ws.araw, weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf, d_weights ? d_weights[la] : nullptr, d_biases ? d_biases[la] : nullptr,
                d_biases ? d_biases[nt - 1] : nullptr);
     SGN_LAUNCH_CHECK();
@@ -359,7 +359,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         }
     }
     if (g.embedding || g.color || g.dir) {
-        launch(agg_scatter_kernel, item_grid(Tm), 256, (size_t)16 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.X0, ws.dX0, dE7, g);
+        launch(agg_scatter_kernel, item_grid(Tm), 256, (size_t)16 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.tuple_pt, ws.X0, ws.dX0, dE7, g);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;

@@ -112,15 +112,24 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
 // One thread per sample: tuple j -> (sample, slot), compact sample c -> sample.
 static __global__ void agg_index_kernel(const int32_t* __restrict__ pidx, int64_t S, int K, const int32_t* __restrict__ tuple_start,
                                  const int32_t* __restrict__ sample_cidx, const int32_t* __restrict__ nvalid,
-                                 int32_t* __restrict__ tuple_src, int32_t* __restrict__ csample)
+                                 int32_t* __restrict__ tuple_src, int32_t* __restrict__ csample, int32_t* __restrict__ tuple_pt = nullptr,
+                                 int32_t* __restrict__ tuple_cs = nullptr)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     if (nvalid[s] == 0) return;
-    csample[sample_cidx[s]] = (int32_t)s;
+    const int c = sample_cidx[s];
+    csample[c] = (int32_t)s;
     int j = tuple_start[s];
-    for (int k = 0; k < K; k++)
-        if (pidx[s * K + k] >= 0) tuple_src[j++] = (int32_t)(s * K + k);
+    for (int k = 0; k < K; k++) {
+        const int p = pidx[s * K + k];
+        if (p >= 0) {
+            tuple_src[j] = (int32_t)(s * K + k);
+            // the training kernels walk the tuples warp by warp: point and compact sample per tuple save them two dependent loads each
+            if (tuple_pt) { tuple_pt[j] = p; tuple_cs[j] = c; }
+            j++;
+        }
+    }
 }
 
 // One warp per tuple.  X0 layout = reference `feat` (:603-611):
@@ -128,18 +137,24 @@ static __global__ void agg_index_kernel(const int32_t* __restrict__ pidx, int64_
 // E7 = [colour(3) | dir - viewdir (3) | dir . viewdir | 0]  (:639-652).
 static __global__ void __launch_bounds__(256)
 agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
-                  const float* __restrict__ loc_pers, float* __restrict__ X0, float* __restrict__ L, float* __restrict__ E7)
+                  const int32_t* __restrict__ tuple_pt, const float* __restrict__ loc_pers, float* __restrict__ X0, float* __restrict__ L, float* __restrict__ E7)
 {
     extern __shared__ float4 rowbuf4[];                // 8 warps x k0pad floats (dynamic)
     float* rowbuf = (float*)rowbuf4;
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
-    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    const int flat = tuple_src[j];
+    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks.
+    // The next tuple's indices are fetched while the current one is worked on (the loop is a chain of dependent loads otherwise).
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int flat_n = 0, p_n = 0;
+    if (j < T) { flat_n = tuple_src[j]; p_n = tuple_pt[j]; }
+    for (; j < T; j += stride) {
+    const int flat = flat_n;
+    const int64_t p = p_n;
+    if (j + stride < T) { flat_n = tuple_src[j + stride]; p_n = tuple_pt[j + stride]; }
     const int64_t s = flat / K;
     const int64_t r = s / SR;
-    const int64_t p = in.pidx[flat];
     // the row is put together in shared memory (its sin / cos columns interleave with a stride of 2 F floats) and leaves as whole float4s
     float* x = rowbuf + (threadIdx.x >> 5) * d.k0pad;
     const int C = d.C, F = d.F, FD = d.FD;
@@ -419,7 +434,7 @@ agg_rgb_bwd_kernel(AggDims d, const int32_t* __restrict__ S_ptr, int S_max, cons
 template <int NC>                                  // columns per lane: W <= 32 * NC
 static __global__ void __launch_bounds__(256, 4)
 agg_ksum_bwd_kernel(AggIn in, AggDims d, int K, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
-                    const int32_t* __restrict__ sample_cidx, const float* __restrict__ wc, const float* __restrict__ weight_n,
+                    const int32_t* __restrict__ tuple_cs, const float* __restrict__ wc, const float* __restrict__ weight_n,
                     const float* __restrict__ H, const float* __restrict__ araw, const float* __restrict__ wa,
                     const float* __restrict__ dC0, int lddc0, const float* __restrict__ d_decoded, float* __restrict__ dZ,
                     float* __restrict__ d_araw, float* __restrict__ d_conf, float* __restrict__ d_wa, float* __restrict__ d_ba,
@@ -431,11 +446,16 @@ agg_ksum_bwd_kernel(AggIn in, AggDims d, int K, const int32_t* __restrict__ T_pt
     float g_wa[NC], g_bl[NC], g_ba = 0.f;
 #pragma unroll
     for (int i = 0; i < NC; i++) { g_wa[i] = 0.f; g_bl[i] = 0.f; }
-    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    const int flat = tuple_src[j];
+    // a fixed grid strides over the items (see agg_gather_kernel); the next tuple's indices are fetched ahead
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int flat_n = 0, c_n = 0;
+    if (j < T) { flat_n = tuple_src[j]; c_n = tuple_cs[j]; }
+    for (; j < T; j += stride) {
+    const int flat = flat_n;
+    const int64_t c = c_n;
+    if (j + stride < T) { flat_n = tuple_src[j + stride]; c_n = tuple_cs[j + stride]; }
     const int64_t s = flat / K;
-    const int64_t c = sample_cidx[s];
     const float w = wc[flat];
     const float dsig = d_decoded[4 * s];
     const float a = araw[j];
@@ -528,16 +548,21 @@ agg_conf_out_bwd_kernel(const int32_t* __restrict__ pidx, int64_t n, const float
 //   d colour = dE7[0:3] ; d dir = dE7[3:6] + viewdir * dE7[6]
 static __global__ void __launch_bounds__(256)
 agg_scatter_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ T_ptr, int T_max, const int32_t* __restrict__ tuple_src,
-                   const float* __restrict__ X0, const float* __restrict__ dX0, const float* __restrict__ dE7, SgnPointGrads g)
+                   const int32_t* __restrict__ tuple_pt, const float* __restrict__ X0, const float* __restrict__ dX0, const float* __restrict__ dE7, SgnPointGrads g)
 {
     extern __shared__ float4 rowbuf4[];                // 8 warps x 2 x k0pad floats (dynamic)
     float* rowbuf = (float*)rowbuf4;
     const int lane = lane_id();
     const int T = min(*T_ptr, T_max);
-    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    const int flat = tuple_src[j];
-    const int64_t p = in.pidx[flat];
+    // a fixed grid strides over the items (see agg_gather_kernel); the next tuple's indices are fetched ahead
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int flat_n = 0, p_n = 0;
+    if (j < T) { flat_n = tuple_src[j]; p_n = tuple_pt[j]; }
+    for (; j < T; j += stride) {
+    const int flat = flat_n;
+    const int64_t p = p_n;
+    if (j + stride < T) { flat_n = tuple_src[j + stride]; p_n = tuple_pt[j + stride]; }
     const int C = d.C, F = d.F;
     if (g.embedding) {
         // both rows arrive as whole float4s; the sin / cos columns are then read from shared memory

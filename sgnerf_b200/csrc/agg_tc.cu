@@ -1552,7 +1552,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         if ((rc = exclusive_scan_pair_i32(ws.nvalid, ws.tuple_start, ws.sample_cidx, S, ws.partials, st))) return rc;
         const int32_t* T_ptr = ws.tuple_start + S;
         const int32_t* S_ptr = ws.sample_cidx + S;
-        launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample);
+        launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample, (int32_t*)nullptr, (int32_t*)nullptr);
         launch(tc_tile_kernel, cdiv(S, 256), 256, 0, st, S_ptr, Sm, T_ptr, ws.csample, ws.tuple_start, TW, ws.tile_tab, ws.ntiles);
         const int ncap = Tm / TW + 1;
         const int spad = Sm + 7 * ncap + 8;
