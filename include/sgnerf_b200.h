@@ -359,6 +359,12 @@ int sgn_adam_rows_multi(int n_tables, float* const* params, float* const* grads,
                         const int32_t* C /*[host]*/, uint8_t* active, int64_t N, float lr, float beta1, float beta2, float eps,
                         const float* step, float grad_scale, int zero_grad, void* stream);
 
+/* Dense Adam over n_tensors small tensors (the MLP's weights and biases) in one launch; same arithmetic as sgn_adam_rows with every
+ * element active.  params / grads / exp_avg / exp_avg_sq / numel are [host] arrays. */
+int sgn_adam_dense_multi(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                         const int64_t* numel /*[host]*/, float lr, float beta1, float beta2, float eps, const float* step, float grad_scale,
+                         int zero_grad, void* stream);
+
 /* The same update driven by a list of the active rows, for steps that touch a small part of the cloud (a 56x56 patch touches ~5 % of 1M
  * points): nothing is read for the other rows.  sgn_adam_mark_rows sets touched[r] = 1 for every r >= 0 of `rows` (the step's
  * sample_pidx: a superset of the rows that receive a gradient); with several ranks `touched` is summed with the gradients.

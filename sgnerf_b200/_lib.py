@@ -109,6 +109,8 @@ SIGNATURES = {
     "sgn_rows_union_bytes": (c_int, [c_i64, C.POINTER(c_size)]),
     "sgn_rows_union": (c_int, [c_void, c_i64, c_void, c_void, c_void, c_size, c_void]),
     "sgn_rows_pack": (c_int, [c_int, C.POINTER(c_void), C.POINTER(C.c_int32), c_void, c_void, c_i64, c_void, c_int, c_int, c_void]),
+    "sgn_adam_dense_multi": (c_int, [c_int, C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_i64), c_f32, c_f32, c_f32,
+                                     c_f32, c_void, c_f32, c_int, c_void]),
     "sgn_adam_mark_rows": (c_int, [c_void, c_i64, c_void, c_void]),
     "sgn_adam_rows_list": (c_int, [c_int, C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(C.c_int32), c_void, c_void,
                                    c_void, c_void, c_i64, c_f32, c_f32, c_f32, c_f32, c_void, c_f32, c_int, c_void]),

@@ -351,7 +351,7 @@ static __global__ void pack_weights_kernel(PackJobs J)
 // Skinny reductions over the rows: out[p, c] += sum_m w_p[m] X[m, c] for p < NP, with w_p[m] = A[m, p], or 1 when A is NULL
 // (bias gradients = column sums; the wgrads of the 1- and 3-output layers alpha_branch.0 / color_branch.6).
 // Block = 64 column quads x 4 row groups over SKINNY_ROWS rows; four 16-byte loads in flight per thread.
-constexpr int SKINNY_ROWS = 256;
+constexpr int SKINNY_ROWS = 64;                    // rows per block: the remaining users reduce over the samples (tens of thousands of rows), so many small blocks
 template <int NP>
 static __global__ void __launch_bounds__(256)
 skinny_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ X, int ld, int ncols, const int32_t* __restrict__ m_ptr, int m_max,

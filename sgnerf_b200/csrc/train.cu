@@ -179,6 +179,30 @@ __global__ void adam_rows_multi_kernel(AdamTables T, uint8_t* __restrict__ activ
 
 __global__ void step_increment_kernel(float* step) { *step += 1.0f; }
 
+// ---- dense Adam over many small tensors in one launch (the ~30 MLP weights and biases): blockIdx.y = tensor -----------------------------
+constexpr int ADAM_MAX_TENSORS = 64;
+struct AdamTensors {
+    float* param[ADAM_MAX_TENSORS]; float* grad[ADAM_MAX_TENSORS]; float* m1[ADAM_MAX_TENSORS]; float* m2[ADAM_MAX_TENSORS];
+    int64_t n[ADAM_MAX_TENSORS];
+};
+
+__global__ void adam_dense_multi_kernel(AdamTensors T, float lr, float b1, float b2, float eps, const float* __restrict__ step, float grad_scale, int zero_grad)
+{
+    const int k = blockIdx.y;
+    const float t = *step;
+    const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
+    const float step_size = lr / bc1;
+    float *p = T.param[k], *g = T.grad[k], *a = T.m1[k], *b = T.m2[k];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T.n[k]; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gc = g[i] * grad_scale;
+        const float m = b1 * a[i] + (1.0f - b1) * gc;
+        const float v = b2 * b[i] + (1.0f - b2) * gc * gc;
+        a[i] = m; b[i] = v;
+        p[i] -= step_size * (m / (sqrtf(v) / bc2s + eps));
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+
 // ---- the same update driven by a LIST of the active rows (rows that ever received a non-zero gradient) --------------------------------
 // A step touches ~5 % of a 1M-point cloud; reading every row's gradient to find them costs more than the update itself.  The rows a step
 // can touch are known from the query (sample_pidx >= 0): mark_rows_kernel flags them, adam_append_kernel moves newly active ones into
@@ -432,6 +456,29 @@ extern "C" int sgn_adam_rows_list(int n_tables, float* const* params, float* con
     launch(adam_append_kernel, cdiv(N, 256), 256, 0, st, T, active, active_list, active_count, touched, N);
     launch(adam_list_kernel, (int)std::min<int64_t>(cdiv(N * 8, 256), 148 * 8), 256, 0, st, T, active_list, active_count, lr, beta1, beta2, eps, step, grad_scale,
            zero_grad);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+}
+
+extern "C" int sgn_adam_dense_multi(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                                    const int64_t* numel, float lr, float beta1, float beta2, float eps, const float* step, float grad_scale, int zero_grad,
+                                    void* stream)
+{
+    SGN_CHECK_ARG(n_tensors >= 0 && params && grads && exp_avg && exp_avg_sq && numel && step, "sgn_adam_dense_multi: bad argument");
+    for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX_TENSORS) {
+        AdamTensors T = {};
+        const int n = std::min(ADAM_MAX_TENSORS, n_tensors - t0);
+        int64_t most = 0;
+        for (int k = 0; k < n; k++) {
+            SGN_CHECK_ARG(numel[t0 + k] >= 0 && (numel[t0 + k] == 0 || (params[t0 + k] && grads[t0 + k] && exp_avg[t0 + k] && exp_avg_sq[t0 + k])),
+                          "sgn_adam_dense_multi: tensor %d: NULL pointer", t0 + k);
+            T.param[k] = params[t0 + k]; T.grad[k] = grads[t0 + k]; T.m1[k] = exp_avg[t0 + k]; T.m2[k] = exp_avg_sq[t0 + k]; T.n[k] = numel[t0 + k];
+            most = std::max(most, numel[t0 + k]);
+        }
+        if (most == 0) continue;
+        const int gx = (int)std::min<int64_t>(cdiv(most, 256), 32);
+        launch(adam_dense_multi_kernel, dim3(gx, n), 256, 0, (cudaStream_t)stream, T, lr, beta1, beta2, eps, step, grad_scale, zero_grad);
+    }
     SGN_LAUNCH_CHECK();
     return SGN_OK;
 }

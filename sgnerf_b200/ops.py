@@ -563,6 +563,13 @@ def adam_rows_multi(params, grads, exp_avgs, exp_avg_sqs, active, step, lr, beta
               float(lr), float(betas[0]), float(betas[1]), float(eps), _ptr(step), float(grad_scale), int(zero_grad), _stream())
 
 
+def adam_dense_multi(params, grads, exp_avgs, exp_avg_sqs, step, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, zero_grad=False):
+    """sgn_adam_dense_multi: torch.optim.Adam's update on a list of small dense tensors (the MLP) in one launch."""
+    n = (C.c_int64 * len(params))(*[p.numel() for p in params])
+    _lib.call("sgn_adam_dense_multi", len(params), _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avgs), _ptr_array(exp_avg_sqs), n, float(lr),
+              float(betas[0]), float(betas[1]), float(eps), _ptr(step), float(grad_scale), int(zero_grad), _stream())
+
+
 def adam_mark_rows(rows, touched):
     """sgn_adam_mark_rows: touched[r] = 1 for every r >= 0 of the int32 tensor `rows`."""
     rows = _dev(rows, torch.int32, "rows")

@@ -12,7 +12,7 @@ TrainStep calls the library's entry points in order -- no autograd graph is buil
     sgn_query -> sgn_agg_forward (save) -> sgn_ray_dist -> sgn_composite_forward -> sgn_loss_hit_count [-> all-reduce of the count]
     -> sgn_loss_forward_backward (loss + d ray_color + d conf_coefficient in one pass) -> sgn_composite_backward -> sgn_agg_backward
     (TF32 tensor-core GEMMs, scatter-add into the point-table gradient accumulators) [-> ONE in-place all-reduce of the flat gradient
-    bucket] -> Adam: fused torch Adam on the ~30 MLP tensors, sgn_adam_rows on the point tables.
+    bucket] -> Adam: sgn_adam_dense_multi on the ~30 MLP tensors, sgn_adam_rows_list on the point tables.
 
 All gradients live in one flat fp32 bucket (MLP gradients first, then the point tables') whose slices are the accumulators the backward
 adds into, so the multi-GPU exchange is a single NCCL all-reduce of that buffer in place -- no flatten / divide / un-flatten copies:
@@ -147,10 +147,10 @@ class TrainStep(_StepBase):
         nl = len(scene.weights)
         self.d_w, self.d_b = self.grads[:nl], self.grads[nl:2 * nl]
         self.pt_grads = dict(zip(self.pt_names, self.grads[2 * nl:]))
-        # MLP: torch's fused Adam on gradient views; point tables: sgn_adam_rows with its own moments, step counter and active-row flags
-        for p, g in zip(self.net_params, self.grads[:2 * nl]):
-            p.grad = g
-        self.optim = torch.optim.Adam([{"params": self.net_params, "lr": lr}], capturable=bool(use_graph), fused=True)
+        # MLP: sgn_adam_dense_multi (all ~30 tensors in one launch; it also clears the accumulators it consumed); point tables:
+        # sgn_adam_rows_list with its own moments and active-row list; one step counter for both
+        self.net_m = [torch.zeros_like(p) for p in self.net_params]
+        self.net_v = [torch.zeros_like(p) for p in self.net_params]
         self.pt_m = [torch.zeros_like(p) for p in self.pt_params]
         self.pt_v = [torch.zeros_like(p) for p in self.pt_params]
         self.pt_active = torch.zeros(scene.xyz.shape[0], dtype=torch.uint8, device=dev)     # rows that ever received a gradient
@@ -244,7 +244,7 @@ class TrainStep(_StepBase):
         d_color, d_conf = ops.loss_forward_backward(ray_color, self.gt, rmask, conf, self._cnt, self.loss, 1.0, self.conf_w, self.zero_eps,
                                                     1e-6 / self.world)
         d_dec = ops.composite_backward_raw(dec, rd, valid, self.bg, d_color)
-        (self.xbuf if self.sparse else self.flat_grad)[:self.n_net].zero_()   # MLP accumulators (1.7 MB); the point-table rows are cleared by sgn_adam_rows_list
+        # every gradient accumulator is zero here: the Adam kernels clear what they consume
         g = self.pt_grads
         ops.aggregate_train_backward(sc.agg_cfg, sc.weights, sc.biases, tb, pidx, loc_w, self.raydir, self.campos, self.camrot, self.precision,
                                      d_dec, d_conf, self.d_w, self.d_b, g.get("embedding"), g.get("color"), g.get("dirs"), g.get("conf"), ws)
@@ -257,8 +257,8 @@ class TrainStep(_StepBase):
     def _phase_b(self):
         if self.sparse:
             ops.rows_pack(self.grads[len(self.net_params):], self.x_list, self.x_count, self.x_rows, self.x_stride, unpack=True)
-        self.optim.step()
         ops.adam_step_count(self.pt_step)
+        ops.adam_dense_multi(self.net_params, self.grads[:len(self.net_params)], self.net_m, self.net_v, self.pt_step, self.lr, zero_grad=True)
         ops.adam_rows_list(self.pt_params, self.grads[len(self.net_params):], self.pt_m, self.pt_v, self.pt_active, self.pt_active_list,
                            self.pt_active_count, self.pt_touched, self.pt_step, self.plr)
 

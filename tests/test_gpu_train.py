@@ -389,3 +389,26 @@ def test_scene_edit_with_stable_indices_equals_a_fresh_scene():
         assert int(survivors.sum()) > 0.5 * n_points                                      # most rows never moved
         assert a.xyz.shape[0] > n_points and not torch.equal(after.ray_color, before.ray_color)
         assert int((~a.alive).sum()) == 0 or float(a.xyz[~a.alive].min()) == pipeline.RenderScene.HOLE
+
+
+def test_adam_dense_multi_equals_torch_adam():
+    """sgn_adam_dense_multi (the MLP's tensors in one launch) against torch.optim.Adam, 5 steps, tensors of 1 .. 70k elements."""
+    g = torch.Generator().manual_seed(11)
+    shapes = [(256, 284), (256,), (1, 256), (1,), (128, 280), (3, 128), (3,)]
+    p0 = [torch.randn(*s, generator=g) for s in shapes]
+    refs = [p.clone().requires_grad_(True) for p in p0]
+    opt = torch.optim.Adam(refs, lr=5e-4)
+    ps = [p.clone().cuda() for p in p0]
+    grads, ms, vs = [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]
+    step = torch.zeros((), device="cuda")
+    for it in range(5):
+        for k, s in enumerate(shapes):
+            gd = torch.randn(*s, generator=g) * (0.1 + it)
+            refs[k].grad = gd.clone()
+            grads[k].copy_(gd.cuda())
+        opt.step()
+        ops.adam_step_count(step)
+        ops.adam_dense_multi(ps, grads, ms, vs, step, 5e-4, zero_grad=True)
+        assert all(float(x.abs().sum()) == 0.0 for x in grads)
+    for p, r in zip(ps, refs):
+        torch.testing.assert_close(p.cpu(), r.detach(), rtol=2e-5, atol=2e-6)
