@@ -68,16 +68,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int32_t
 __global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(int32_t* partials, int nb)
 {
     __shared__ int sm[SCAN_THREADS / 32 + 1];
-    int carry = 0;
-    for (int base = 0; base < nb; base += SCAN_THREADS) {
-        int i = base + threadIdx.x;
-        int v = i < nb ? partials[i] : 0;
-        int total;
-        int e = block_exclusive_scan(v, &total, sm);
-        if (i < nb) partials[i] = carry + e;
-        carry += total;
-    }
-    if (threadIdx.x == 0) partials[nb] = carry;
+    // a thread owns a run of consecutive partials: one block scan in all (a scan per SCAN_THREADS partials cost 25 us at 3600 of them)
+    const int per = (nb + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int lo = min(nb, (int)threadIdx.x * per), hi = min(nb, lo + per);
+    int s = 0;
+    for (int i = lo; i < hi; i++) s += partials[i];
+    int total;
+    int e = block_exclusive_scan(s, &total, sm);
+    for (int i = lo; i < hi; i++) { const int v = partials[i]; partials[i] = e; e += v; }
+    if (threadIdx.x == 0) partials[nb] = total;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
@@ -138,16 +137,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_pair_partials_kernel(int32_
     __shared__ int sm[SCAN_THREADS / 32 + 1];
     for (int which = 0; which < 2; which++) {
         int32_t* p = partials + which * (nb + 1);
-        int carry = 0;
-        for (int base = 0; base < nb; base += SCAN_THREADS) {
-            int i = base + threadIdx.x;
-            int v = i < nb ? p[i] : 0;
-            int total;
-            int e = block_exclusive_scan(v, &total, sm);
-            if (i < nb) p[i] = carry + e;
-            carry += total;
-        }
-        if (threadIdx.x == 0) p[nb] = carry;
+        const int per = (nb + SCAN_THREADS - 1) / SCAN_THREADS;
+        const int lo = min(nb, (int)threadIdx.x * per), hi = min(nb, lo + per);
+        int s = 0;
+        for (int i = lo; i < hi; i++) s += p[i];
+        int total;
+        int e = block_exclusive_scan(s, &total, sm);
+        for (int i = lo; i < hi; i++) { const int v = p[i]; p[i] = e; e += v; }
+        if (threadIdx.x == 0) p[nb] = total;
         __syncthreads();
     }
 }
