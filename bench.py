@@ -372,8 +372,8 @@ def train_step_leg(s, scene, device, rank, world, dist, bg, patch=56, steps=10):
                             allreduce_bytes_per_step=int(ts.exchange_floats) * 4, dense_bucket_bytes=int(ts.flat_grad.numel()) * 4)
                 if world > 1:
                     info["exchange"] = ("MLP gradients + the point-table gradient rows some rank touched this step (sgn_rows_union / sgn_rows_pack), one "
-                                        "all-reduce sized by a host read of the row count that overlaps forward + backward: three CUDA graphs per "
-                                        "step") if ts.sparse else "dense bucket"
+                                        "all-reduce sized by the row count the host polls from pinned memory; the marks' exchange overlaps the forward: two CUDA "
+                                        "graphs per step") if ts.sparse else "dense bucket"
                 if world > 1:
                     # the same step without the exchange, in the same run on every rank: what the all-reduce costs at this N
                     sc2 = pipeline.RenderScene(scene.xyz, scene.embedding.clone(), scene.color.clone(), scene.dirs.clone(), scene.conf.clone(),

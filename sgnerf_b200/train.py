@@ -25,7 +25,8 @@ sample_pidx, so no kernel reads all N gradient rows to find them.
 Several ranks (sparse_exchange, the default): the marks are summed over the ranks right after the query, every rank derives the same
 ordered union of touched rows (sgn_rows_union) and packs its gradient rows of that union behind the MLP gradients (sgn_rows_pack);
 ONE all-reduce of [MLP gradients | packed rows] replaces the all-reduce of the whole bucket (16 MB instead of 161 MB at C2 on 2 ranks).
-Its size is read by the host while forward + backward run, so the device never waits: three CUDA graphs per step.
+The marks are exchanged on a side branch of the step's first CUDA graph while the aggregation forward runs; the size of the union reaches
+the host through pinned memory long before the backward ends, so the device never waits for the host (two graphs per step).
 
 AutogradTrainStep is the same iteration written with torch.autograd over the ops' autograd Functions and torch.optim.Adam on every
 parameter (the first implementation; kept as the cross-check of TrainStep in tests/test_gpu_train.py).
@@ -138,10 +139,12 @@ class TrainStep(_StepBase):
                 self.grads[i] = self.xbuf[offs[i]:offs[i] + sizes[i]].view_as(self.params[i])
             self.x_rows = self.xbuf[offs[len(self.net_params)]:]
             self.x_list = torch.zeros(n_rows, dtype=torch.int32, device=dev)
-            self.x_count = torch.zeros(1, dtype=torch.int32, device=dev)
-            self.x_count_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            self._graph_g = self._graph_b = None
-            self._count_ready = torch.cuda.Event()
+            self.x_meta = torch.zeros(2, dtype=torch.int32, device=dev)          # [rows in the union, step sequence number]
+            self.x_count = self.x_meta[0:1]
+            self.x_meta_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._seq = 0
+            self._side = torch.cuda.Stream(device=dev)
+            self._graph_b = None
         self.exchange_floats = 0 if self.world == 1 else self.flat_grad.numel()       # floats all-reduced by the last step
         self.n_net = offs[len(self.net_params)]           # the MLP gradients occupy flat_grad[:n_net]
         nl = len(scene.weights)
@@ -160,12 +163,11 @@ class TrainStep(_StepBase):
         # number of rays that hit the cloud (the normalisation of both loss terms): with the sparse exchange it sits right behind the
         # touched marks and is summed over the ranks by the same all-reduce
         self._touched_cnt = self.flat_grad[off:off + n_rows + 1]
-        self._cnt = self.flat_grad[off + n_rows] if self.sparse else torch.zeros((), dtype=torch.float32, device=dev)
+        self._cnt = self.flat_grad[off + n_rows]
 
     @torch.no_grad()
     def _body(self):
-        self._phase_query()
-        self._phase_grad()
+        self._phase_a()
         if self.sparse:
             self._exchange()
         self._phase_b()
@@ -173,9 +175,10 @@ class TrainStep(_StepBase):
     def step(self):
         if not (self.sparse and self.use_graph):
             return super().step()
-        # Sparse exchange: three graphs.  The rows the step can touch are known right after the query, so their union over the ranks and
-        # its size are produced by the first (short) graph; the host reads the size while the second graph (forward + backward + pack)
-        # runs, and enqueues the right-sized all-reduce and the third graph (unpack + Adam) behind it: the device never waits for the host.
+        # Sparse exchange: two graphs around the one all-reduce whose size is a host value.  The rows a step can touch are known right
+        # after the query: inside the first graph a side branch sums the marks over the ranks, derives the union and copies its size (with
+        # a sequence number) to pinned host memory while the main branch runs the aggregation forward.  The host polls that word, then
+        # enqueues the right-sized all-reduce and the second graph (unpack + Adam) behind the first: the device never waits for the host.
         self.scene.invalidate_point_cache()
         if self._graph is None:
             side = torch.cuda.Stream()
@@ -185,62 +188,59 @@ class TrainStep(_StepBase):
                     self._body()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            self._graph, self._graph_g, self._graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self._graph, self._graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
-                self._phase_query()
-            with torch.cuda.graph(self._graph_g, pool=self._graph.pool()):
-                self._phase_grad()
+                self._phase_a()
             with torch.cuda.graph(self._graph_b, pool=self._graph.pool()):
                 self._phase_b()
         self._graph.replay()
-        self._count_ready.record()
-        self._graph_g.replay()
         self._exchange()
         self._graph_b.replay()
 
     @torch.no_grad()
     def _exchange(self):
-        """Host side of the sparse exchange: read how many rows the ranks touched, all-reduce that much of the exchange buffer."""
-        self._count_ready.synchronize()
-        n = int(self.x_count_host[0])
+        """Host side of the sparse exchange: wait for this step's row count (a word in pinned memory the device writes early in the step),
+        all-reduce that much of the exchange buffer."""
+        self._seq += 1
+        spins = 0
+        while int(self.x_meta_host[1]) != self._seq:
+            spins += 1
+            if spins > 50_000_000:
+                raise RuntimeError("sgnerf_b200.TrainStep: the step's row count never arrived from the device")
+        n = int(self.x_meta_host[0])
         self.exchange_floats = self.n_net + n * self.x_stride
         if self.world > 1:
             dist.all_reduce(self.xbuf[:self.exchange_floats], group=self.group)
 
     @torch.no_grad()
-    def _phase_query(self):
+    def _phase_a(self):
         sc, q = self.scene, self.scene.qopt
         grid, hp = sc.grid()
         pidx, loc_w, _, rmask = ops.query(grid, self.campos, self.raydir, self.t, q.SR, q.K, q.kernel_size[0], hp.radius2)
         ops.adam_mark_rows(pidx, self.pt_touched)
+        # number of rays that hit the cloud (the normalisation of both loss terms); global after the exchange below
+        self._cnt.zero_()
+        ops.loss_hit_count(rmask, self._cnt)
+        self.n_hit.copy_(self._cnt)
+        main = torch.cuda.current_stream()
         if self.sparse:
-            self._cnt.zero_()
-            ops.loss_hit_count(rmask, self._cnt)
-            self.n_hit.copy_(self._cnt)
-            if self.world > 1:
-                dist.all_reduce(self._touched_cnt, group=self.group)   # 4 B / point: > 0 where some rank has a sample next to the point; + the hit count
-            ops.rows_union(self.pt_touched, self.x_list, self.x_count)
-            self.x_count_host.copy_(self.x_count, non_blocking=True)
-            if not torch.cuda.is_current_stream_capturing():
-                self._count_ready.record()
-        self._q = (pidx, loc_w, rmask, hp)
-
-    @torch.no_grad()
-    def _phase_grad(self):
-        sc = self.scene
-        pidx, loc_w, rmask, hp = self._q
+            # side branch, concurrent with the aggregation forward: marks (+ hit count) summed over the ranks -> union -> its size to the host
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                if self.world > 1:
+                    dist.all_reduce(self._touched_cnt, group=self.group)   # 4 B / point: > 0 where some rank has a sample next to the point
+                ops.rows_union(self.pt_touched, self.x_list, self.x_count)
+                self.x_meta[1:2].add_(1)
+                self.x_meta_host.copy_(self.x_meta, non_blocking=True)
+        elif self.world > 1:
+            dist.all_reduce(self._cnt, group=self.group)
         dec, valid, loc_pers, _, conf, ws, tb = ops.aggregate_train_forward(
             sc.agg_cfg, sc.weights, sc.biases, sc.xyz, sc.embedding, sc.color, sc.dirs, sc.conf, sc.label_emb, pidx, loc_w, self.raydir,
             self.campos, self.camrot, self.precision)
         rd = ops.ray_dist(loc_pers, valid, hp.vsize[2], 1)
         ray_color = ops.composite_forward_raw(dec, rd, valid, self.bg)
-        if not self.sparse:
-            # global number of rays that hit the cloud: the normalisation of both loss terms
-            self._cnt.zero_()
-            ops.loss_hit_count(rmask, self._cnt)
-            self.n_hit.copy_(self._cnt)
-            if self.world > 1:
-                dist.all_reduce(self._cnt, group=self.group)
+        if self.sparse:
+            main.wait_stream(self._side)
         d_color, d_conf = ops.loss_forward_backward(ray_color, self.gt, rmask, conf, self._cnt, self.loss, 1.0, self.conf_w, self.zero_eps,
                                                     1e-6 / self.world)
         d_dec = ops.composite_backward_raw(dec, rd, valid, self.bg, d_color)

@@ -346,7 +346,7 @@ def test_sparse_exchange_step_equals_the_dense_step(use_graph):
     for pa, pb in zip(a.params, b.params):
         assert float((pa.detach() - pb.detach()).abs().mean()) < 2e-4
     assert torch.equal(a.pt_active, b.pt_active)
-    n = int(b.x_count_host[0])
+    n = int(b.x_meta_host[0])
     assert 0 < n < b.scene.xyz.shape[0] // 2 and b.exchange_floats == b.n_net + n * b.x_stride
 
 
