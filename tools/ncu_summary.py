@@ -21,12 +21,15 @@ def main():
     rows = list(csv.reader(io.StringIO(txt)))
     H, units = rows[0], rows[1]
     lines = ["# ncu --set full --clock-control none --import-source on, one launch of every hot kernel", "# " + header, ""]
-    seen = set()
+    # one launch per kernel name: the longest one (a report may hold many launches of one kernel at different sizes)
+    best = {}
+    ti = H.index("gpu__time_duration.sum")
     for r in rows[2:]:
         name = r[H.index("Kernel Name")]
-        if name in seen:
-            continue
-        seen.add(name)
+        t = float(r[ti].replace(",", ""))
+        if name not in best or t > best[name][0]:
+            best[name] = (t, r)
+    for name, (_, r) in best.items():
         lines.append("== " + name[:110])
         for m in METRICS:
             if m in H:

@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "sgnerf_b200", "libsgnerf_b200.so")
 CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UBLKCP", "UTMALDG", "UTMAPF", "SYNCS", "UCGABAR", "HMMA", "FFMA", "RED", "ATOMG"]
+MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "UBLKCP", "UTMALDG", "UTMASTG", "UTMAPF", "SYNCS", "UCGABAR", "HMMA", "FFMA", "RED", "ATOMG"]
 
 
 def sass_counts():
@@ -68,7 +68,7 @@ def main():
     lines = [f"# SASS of {os.path.relpath(SO, ROOT)} ({', '.join(sorted(arch))}); regenerate with: python tools/sass_evidence.py", ""]
     tot = collections.Counter()
     for k, c in kernels.items():
-        hit = {m: c[m] for m in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "SYNCS", "UCGABAR", "RED", "ATOMG") if c[m]}
+        hit = {m: c[m] for m in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "UCGABAR", "RED", "ATOMG") if c[m]}
         tot.update({m: v for m, v in hit.items()})
         if any(m in hit for m in ("UTCHMMA", "LDTM", "UBLKCP", "UTCBAR", "UCGABAR")):
             short = re.sub(r"\(.*", "", names[k])
