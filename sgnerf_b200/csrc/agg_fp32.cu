@@ -142,8 +142,13 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     }
     const float* Hlast = cur;
     const int la = P.alpha_layer;
-    launch(agg_alpha_kernel, item_grid(Tm), 256, 0, st, Hlast, d.W, weights[la], biases[la], T_ptr, Tm, ws.araw);
-    launch(agg_ksum_kernel, item_grid(Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, ws.araw, ws.C0, ws.sigma);
+    // raw alpha of every tuple + the K-sums of every sample, one pass over H
+    if (K <= 8)
+        launch(agg_ksum_kernel<8>, item_grid(Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, weights[la], biases[la],
+               ws.araw, ws.C0, ws.sigma);
+    else
+        launch(agg_ksum_kernel<SGN_MAX_K>, item_grid(Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, weights[la],
+               biases[la], ws.araw, ws.C0, ws.sigma);
     SGN_LAUNCH_CHECK();
 
     // colour MLP

@@ -224,33 +224,20 @@ agg_gather_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict_
     }
 }
 
-// One warp per tuple: raw alpha = h . wa + ba   (alpha_branch, a single Linear)
-static __global__ void __launch_bounds__(256)
-agg_alpha_kernel(const float* __restrict__ H, int W, const float* __restrict__ wa, const float* __restrict__ ba,
-                 const int32_t* __restrict__ T_ptr, int T_max, float* __restrict__ araw)
-{
-    const int lane = lane_id();
-    const int T = min(*T_ptr, T_max);
-    // a fixed grid strides over the items: their number lives on the device, a grid sized for the maximum would be mostly empty blocks
-    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < T; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    float acc = 0.f;
-    for (int c = lane; c < W; c += 32) acc = fmaf(H[j * W + c], __ldg(wa + c), acc);
-    acc = warp_sum(acc);
-    if (lane == 0) araw[j] = acc + ba[0];
-    }
-}
-
 static __device__ __forceinline__ float softplus1(float x)  // torch.nn.Softplus(beta=1, threshold=20)
 {
     return x > 20.0f ? x : log1pf(expf(x));
 }
 
-// One warp per compact sample: sigma = sum_k wc * softplus(raw - 1), F = sum_k wc * h  -> C0[:, :W];
+// One warp per compact sample: raw alpha of its tuples (alpha_branch, a single Linear: araw = h . wa + ba, kept for the backward),
+// sigma = sum_k wc * softplus(raw - 1), F = sum_k wc * h  -> C0[:, :W] -- one pass over the sample's rows of H for all three;
 // C0[:, W:W+6*FV] = viewdir encoding (ori=True, first three stripped): sin(v_d 2^f) d-major, then cos (:579-585).
+template <int KT>                                  // K <= KT
 static __global__ void __launch_bounds__(256)
 agg_ksum_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ S_ptr, int S_max, const int32_t* __restrict__ csample,
                 const int32_t* __restrict__ tuple_start, const int32_t* __restrict__ nvalid, const float* __restrict__ wc,
-                const float* __restrict__ H, const float* __restrict__ araw, float* __restrict__ C0, float* __restrict__ sigma)
+                const float* __restrict__ H, const float* __restrict__ wa, const float* __restrict__ ba, float* __restrict__ araw,
+                float* __restrict__ C0, float* __restrict__ sigma)
 {
     const int lane = lane_id();
     const int Sv = min(*S_ptr, S_max);
@@ -259,23 +246,43 @@ agg_ksum_kernel(AggIn in, AggDims d, int K, int SR, const int32_t* __restrict__ 
     const int64_t s = csample[c];
     const int j0 = tuple_start[s], n = nvalid[s];
     const int W = d.W;
-    float wk[SGN_MAX_K];
+    float wk[KT], dotq[KT];
     {
         int q = 0;
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            wk[k] = 0.f; dotq[k] = 0.f;
+        }
         for (int k = 0; k < K; k++)
-            if (in.pidx[s * K + k] >= 0) wk[q++] = wc[s * K + k];
-    }
-    float sg = 0.f;
-    for (int q = 0; q < n; q++) {
-        const float a = araw[j0 + q];
-        sg += wk[q] * (d.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f));
+            if (in.pidx[s * K + k] >= 0) {
+                const float w = wc[s * K + k];
+#pragma unroll
+                for (int i = 0; i < KT; i++) if (i == q) wk[i] = w;
+                q++;
+            }
     }
     float* row = C0 + c * d.kc0pad;
     for (int col = lane; col < W; col += 32) {
+        const float wac = __ldg(wa + col);
         float acc = 0.f;
-        for (int q = 0; q < n; q++) acc += H[(int64_t)(j0 + q) * W + col] * wk[q];
+#pragma unroll
+        for (int q = 0; q < KT; q++)
+            if (q < n) {
+                const float h = H[(int64_t)(j0 + q) * W + col];
+                acc += h * wk[q];
+                dotq[q] = fmaf(h, wac, dotq[q]);
+            }
         row[col] = acc;
     }
+    float sg = 0.f;
+    const float b0 = ba[0];
+#pragma unroll
+    for (int q = 0; q < KT; q++)
+        if (q < n) {
+            const float a = warp_sum(dotq[q]) + b0;
+            if (lane == 0) araw[j0 + q] = a;
+            sg += wk[q] * (d.act_super ? softplus1(a - 1.0f) : fmaxf(a, 0.f));
+        }
     const int64_t r = s / SR;
     const int FV = d.FV;
     for (int i = lane; i < 3 * FV; i += 32) {
