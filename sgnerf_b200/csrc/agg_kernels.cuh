@@ -32,10 +32,9 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
         const int p8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
         if ((pa.x & pa.y & pa.z & pa.w & pb.x & pb.y & pb.z & pb.w) < 0) {
             // no neighbour at all (two thirds of the slots of a frame): zero weights; the confidence column still holds point 0's
+            // wc and weight_n are workspaces that are only ever read at valid tuples (tuple_src / pidx >= 0): nothing to write for this sample
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4* o = (float4*)(wc + s * 8);
-            o[0] = z4; o[1] = z4;
-            if (weight_n) { o = (float4*)(weight_n + s * 8); o[0] = z4; o[1] = z4; }
+            float4* o;
             if (weight_out) { o = (float4*)(weight_out + s * 8); o[0] = z4; o[1] = z4; }
             if (conf_out) {
                 const float c0 = in.tab.conf ? fminf(fmaxf(__ldg(in.tab.conf), 0.0001f), 1.0f) : 1.0f;

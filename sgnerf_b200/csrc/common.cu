@@ -157,20 +157,37 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_pair_apply_kernel(const int
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER_THREAD;
     int v[SCAN_PER_THREAD];
     int s = 0, c = 0;
+    // a thread's 8 values are 32 contiguous bytes: two 16-byte accesses per array when the run is whole and the arrays are aligned
+    const bool vec = SCAN_PER_THREAD == 8 && base + SCAN_PER_THREAD <= n && ((((uintptr_t)in | (uintptr_t)out_sum | (uintptr_t)out_cnt) & 15) == 0);
+    if (vec) {
+        const int4 a = *(const int4*)(in + base), b = *(const int4*)(in + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; i++) v[i] = base + i < n ? in[base + i] : 0;
+    }
 #pragma unroll
     for (int i = 0; i < SCAN_PER_THREAD; i++) {
-        v[i] = base + i < n ? in[base + i] : 0;
         s += v[i];
         c += v[i] > 0;
     }
     int total;
     int es = block_exclusive_scan(s, &total, sm) + partials[blockIdx.x];
     int ec = block_exclusive_scan(c, &total, sm) + partials[nb + 1 + blockIdx.x];
+    int os[SCAN_PER_THREAD], oc[SCAN_PER_THREAD];
 #pragma unroll
     for (int i = 0; i < SCAN_PER_THREAD; i++) {
-        if (base + i < n) { out_sum[base + i] = es; out_cnt[base + i] = ec; }
+        os[i] = es; oc[i] = ec;
         es += v[i];
         ec += v[i] > 0;
+    }
+    if (vec) {
+        *(int4*)(out_sum + base) = make_int4(os[0], os[1], os[2], os[3]); *(int4*)(out_sum + base + 4) = make_int4(os[4], os[5], os[6], os[7]);
+        *(int4*)(out_cnt + base) = make_int4(oc[0], oc[1], oc[2], oc[3]); *(int4*)(out_cnt + base + 4) = make_int4(oc[4], oc[5], oc[6], oc[7]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_PER_THREAD; i++)
+            if (base + i < n) { out_sum[base + i] = os[i]; out_cnt[base + i] = oc[i]; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { out_sum[n] = partials[nb]; out_cnt[n] = partials[2 * nb + 1]; }
 }
