@@ -16,6 +16,8 @@
 // The fused bf16 tcgen05 inference path lives in agg_tc.cu; this file is the layer-wise one (strict fp32 or TF32 GEMMs), the only
 // one with a backward.
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 #include "agg_kernels.cuh"
 #include "gemm_simt.cuh"
@@ -48,6 +50,27 @@ static inline bool use_sign_masks(const AggDims& d, bool tc) { return tc && d.W 
 
 // grid of the warp-per-item kernels (8 warps per block): they stride over the items, whose number is only known on the device
 static inline int item_grid(int64_t max_items) { return (int)std::min<int64_t>(cdiv(max_items, 8), 148 * 8); }
+// the same, sized to what is resident at once (one full wave: a second, partly filled wave of a strided loop only adds a tail)
+template <typename Kern>
+static int item_grid(Kern kernel, int64_t max_items, size_t smem = 0)
+{
+    static std::mutex mu;
+    static std::map<const void*, int> per_sm;
+    int occ;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = per_sm.find((const void*)kernel);
+        if (it == per_sm.end()) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, smem) != cudaSuccess || n < 1) n = 4;
+            it = per_sm.emplace((const void*)kernel, n).first;
+        }
+        occ = it->second;
+    }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::min<int64_t>(cdiv(max_items, 8), (int64_t)sms * occ);
+}
 
 // sign bits of a stored activation [M, N] (N a multiple of 32): the fallback producer of GemmNN::mask_out for layers the SIMT GEMM ran
 static __global__ void mask_from_act_kernel(const float* __restrict__ act, int ld, int nwords, const int32_t* __restrict__ m_ptr, int m_max, uint32_t* __restrict__ mask)
@@ -120,7 +143,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
     launch(agg_index_kernel, cdiv(S, 128), 128, 0, st, in.pidx, S, K, ws.tuple_start, ws.sample_cidx, ws.nvalid, ws.tuple_src, ws.csample, ws.tuple_pt, ws.tuple_cs);
-    launch(agg_gather_kernel, item_grid(Tm), 256, (size_t)8 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.tuple_pt, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
+    launch(agg_gather_kernel, item_grid(agg_gather_kernel, Tm, (size_t)8 * d.k0pad * sizeof(float)), 256, (size_t)8 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.tuple_pt, loc_pers, ws.X0, d.LD > 0 ? ws.L : nullptr, ws.E7);
     SGN_LAUNCH_CHECK();
 
     // per-tuple layers
@@ -144,7 +167,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
     const int la = P.alpha_layer;
     // raw alpha of every tuple + the K-sums of every sample, one pass over H
     if (K <= 8)
-        launch(agg_ksum_kernel<8>, item_grid(Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, weights[la], biases[la],
+        launch(agg_ksum_kernel<8>, item_grid(agg_ksum_kernel<8>, Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, weights[la], biases[la],
                ws.araw, ws.C0, ws.sigma);
     else
         launch(agg_ksum_kernel<SGN_MAX_K>, item_grid(Sm), 256, 0, st, in, d, K, SR, S_ptr, Sm, ws.csample, ws.tuple_start, ws.nvalid, ws.wc, Hlast, weights[la],
@@ -316,7 +339,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     float* dZ = ws.dZ[0];
     // also: weight + bias gradient of the alpha head and the bias gradient of the last tuple layer (reductions over the same rows)
     if (d.W <= 256)
-        launch(agg_ksum_bwd_kernel<8>, item_grid(Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.tuple_cs, ws.wc, ws.weight_n, Hlast, ws.araw,
+        launch(agg_ksum_bwd_kernel<8>, item_grid(agg_ksum_bwd_kernel<8>, Tm), 256, 0, st, in, d, K, T_ptr, Tm, ws.tuple_src, ws.tuple_cs, ws.wc, ws.weight_n, Hlast, ws.araw,
                weights[la], dF, d.W, d_decoded, dZ, ws.d_araw, g.conf, d_weights ? d_weights[la] : nullptr, d_biases ? d_biases[la] : nullptr,
                d_biases ? d_biases[nt - 1] : nullptr);
     else
@@ -364,7 +387,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         }
     }
     if (g.embedding || g.color || g.dir) {
-        launch(agg_scatter_kernel, item_grid(Tm), 256, (size_t)16 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.tuple_pt, ws.X0, ws.dX0, dE7, g);
+        launch(agg_scatter_kernel, item_grid(agg_scatter_kernel, Tm, (size_t)16 * d.k0pad * sizeof(float)), 256, (size_t)16 * d.k0pad * sizeof(float), st, in, d, K, SR, T_ptr, Tm, ws.tuple_src, ws.tuple_pt, ws.X0, ws.dX0, dE7, g);
         SGN_LAUNCH_CHECK();
     }
     return SGN_OK;
