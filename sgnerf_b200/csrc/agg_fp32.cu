@@ -44,9 +44,10 @@ static int launch_skinny(const float* A, int lda, int np, const float* X, int ld
 // GEMM dispatch: tc = TF32 tensor-core kernels (gemm_tc.cuh) where the operand shapes allow, fp32 SIMT otherwise.
 // g.colsum (column sums of the result = the bias gradient of the layer below) is fused into the tensor-core epilogue and is a
 // separate pass over C on the SIMT path.
-// The dgrad epilogues multiply by leaky'(activation): with the tensor-core GEMMs the forward layers also store the activations' sign bits
-// and the backward reads those (1/32 of the bytes); both sides decide with this predicate.
-static inline bool use_sign_masks(const AggDims& d, bool tc) { return tc && d.W % 32 == 0 && d.WC % 32 == 0; }
+// The dgrad epilogues multiply by leaky'(activation): a saving forward also stores the activations' sign bits (by the tensor-core GEMM's
+// epilogue, or by mask_from_act_kernel after a SIMT GEMM) and the tensor-core dgrads read those instead (1/32 of the bytes).  The masks
+// exist whatever arithmetic the forward ran in, so forward and backward may be called with different precisions.
+static inline bool use_sign_masks(const AggDims& d) { return d.W % 32 == 0 && d.WC % 32 == 0; }
 
 // grid of the warp-per-item kernels (8 warps per block): they stride over the items, whose number is only known on the device
 static inline int item_grid(int64_t max_items) { return (int)std::min<int64_t>(cdiv(max_items, 8), 148 * 8); }
@@ -159,7 +160,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
         if (L.extra == EXTRA_COLORDIR) { g.A2 = ws.E7; g.lda2 = 8; g.B2 = ws.Wt[t] + (size_t)cur_k * L.npad; g.ldb2 = L.npad; g.K2 = 8; }
         if (L.extra != EXTRA_NONE) { g.Bt2 = ws.Wp[t] + cur_k; g.ldbt2 = L.kpad; }
         g.C = out; g.ldc = d.W; g.N = d.W; g.m_ptr = T_ptr; g.m_max = Tm; g.bias = biases[t]; g.epi = EPI_BIAS_LEAKY; g.slope = d.slope;
-        if (save && use_sign_masks(d, tc)) { g.mask_out = ws.HM[t]; g.ldmask = d.W / 32; }
+        if (save && use_sign_masks(d)) { g.mask_out = ws.HM[t]; g.ldmask = d.W / 32; }
         if ((rc = run_gemm_nn(g, tc, st))) return rc;
         cur = out; cur_ld = d.W; cur_k = d.W;
     }
@@ -184,7 +185,7 @@ static int agg_forward_chunk(const AggPlan& P, const float* const* weights, cons
         g.A1 = cur; g.lda1 = cur_ld; g.B1 = ws.Wt[l]; g.ldb1 = L.npad; g.K1 = cur_k;
         g.Bt1 = ws.Wp[l]; g.ldbt1 = L.kpad;
         g.C = out; g.ldc = d.WC; g.N = d.WC; g.m_ptr = S_ptr; g.m_max = Sm; g.bias = biases[l]; g.epi = EPI_BIAS_LEAKY; g.slope = d.slope;
-        if (save && use_sign_masks(d, tc)) { g.mask_out = ws.CM[c]; g.ldmask = d.WC / 32; }
+        if (save && use_sign_masks(d)) { g.mask_out = ws.CM[c]; g.ldmask = d.WC / 32; }
         if ((rc = run_gemm_nn(g, tc, st))) return rc;
         cur = out; cur_ld = d.WC; cur_k = d.WC;
     }
@@ -307,7 +308,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         const bool to_c0 = P.n_color_hidden == 0;
         q.C = dcur; q.ldc = to_c0 ? d.W : d.WC; q.N = to_c0 ? d.W : d.WC; q.m_ptr = S_ptr; q.m_max = Sm;
         q.epi = to_c0 ? EPI_NONE : EPI_MUL_DLEAKY; q.aux = Clast; q.ldaux = Clast_ld; q.slope = d.slope;
-        if (!to_c0 && use_sign_masks(d, tc)) { q.mask_in = ws.CM[P.n_color_hidden - 1]; q.ldmask = d.WC / 32; }
+        if (!to_c0 && use_sign_masks(d)) { q.mask_in = ws.CM[P.n_color_hidden - 1]; q.ldmask = d.WC / 32; }
         if (!to_c0 && d_biases) q.colsum = d_biases[P.color_layer0 + P.n_color_hidden - 1];     // bias gradient of the layer that produced Clast
         if ((rc = run_gemm_nn(q, tc, st))) return rc;
         dcur_ld = q.ldc;
@@ -324,7 +325,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
         q.C = dnext; q.m_ptr = S_ptr; q.m_max = Sm; q.slope = d.slope;
         if (c > 0) {
             q.ldc = d.WC; q.N = d.WC; q.epi = EPI_MUL_DLEAKY; q.aux = a_in; q.ldaux = a_ld; q.colsum = d_biases ? d_biases[l - 1] : nullptr;
-            if (use_sign_masks(d, tc)) { q.mask_in = ws.CM[c - 1]; q.ldmask = d.WC / 32; }
+            if (use_sign_masks(d)) { q.mask_in = ws.CM[c - 1]; q.ldmask = d.WC / 32; }
         }
         else { q.ldc = d.W; q.N = d.W; q.epi = EPI_NONE; }      // only dF = dC0[:, :W] is needed (view encoding has no gradient)
         if ((rc = run_gemm_nn(q, tc, st))) return rc;
@@ -380,7 +381,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
             q.C = dnext; q.ldc = a_kpad; q.N = a_kpad; q.m_ptr = T_ptr; q.m_max = Tm; q.slope = d.slope;
             if (t > 0) {
                 q.epi = EPI_MUL_DLEAKY; q.aux = a_in; q.ldaux = a_ld; q.colsum = d_biases ? d_biases[t - 1] : nullptr;
-                if (use_sign_masks(d, tc)) { q.mask_in = ws.HM[t - 1]; q.ldmask = d.W / 32; }
+                if (use_sign_masks(d)) { q.mask_in = ws.HM[t - 1]; q.ldmask = d.W / 32; }
             } else { q.epi = EPI_NONE; }
             if ((rc = run_gemm_nn(q, tc, st))) return rc;
             dZ = dnext;

@@ -308,6 +308,16 @@ def test_tf32_backward_gemms_on_shared_activations(R, SR, semantic):
         assert rel_l2(g_tf[k], g_fp[k]) < 1e-2, (k, rel_l2(g_tf[k], g_fp[k]))
 
 
+def test_tf32_backward_after_an_fp32_forward():
+    """Forward and backward may run in different arithmetics: the tensor-core dgrads read the activations' sign bits, which an fp32 (SIMT)
+    forward provides too (mask_from_act_kernel).  TF32 backward vs fp32 backward on the same fp32 activations: relative L2 <= 1e-2."""
+    d0, v0, g_tf = _tf32_case(129, 24, True, ops.PRECISION_FP32, bwd_override=ops.PRECISION_TF32)
+    d1, v1, g_fp = _tf32_case(129, 24, True, ops.PRECISION_FP32)
+    assert torch.equal(d0, d1) and torch.equal(v0, v1)
+    for k in g_fp:
+        assert rel_l2(g_tf[k], g_fp[k]) < 1e-2, (k, rel_l2(g_tf[k], g_fp[k]))
+
+
 @pytest.mark.parametrize("width", [64, 128])
 def test_tf32_backward_gemms_narrow_layers(width):
     """Same check at shading_feature_num 64 / 128 (colour width 32 / 64): partial MMA tiles, one accumulator half in the wgrad."""
