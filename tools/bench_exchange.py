@@ -71,6 +71,22 @@ def main():
     out["rows_pack_us"] = timed(lambda: ops.rows_pack(tabs, lst, cnt, xbuf[n_net:], stride))
     out["packed_allreduce_us"] = timed(lambda: ar(xbuf[: n_net + n * stride]))
     out["packed_allreduce_bytes"] = (n_net + n * stride) * 4
+    if world > 1:
+        # the same bytes as two halves on two communicators / two streams at once (does one all-reduce of this size fill NVLink?)
+        g2 = dist.new_group()
+        side = torch.cuda.Stream()
+        half = (n_net + n * stride) // 2 // 64 * 64
+        def split():
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dist.all_reduce(xbuf[half: n_net + n * stride], group=g2)
+            dist.all_reduce(xbuf[:half])
+            main.wait_stream(side)
+        out["packed_allreduce_two_groups_us"] = timed(split)
+        quarter = half // 2 // 64 * 64
+        out["packed_allreduce_half_us"] = timed(lambda: ar(xbuf[:half]))
+        out["packed_allreduce_quarter_us"] = timed(lambda: ar(xbuf[:quarter]))
     out["rows_unpack_us"] = timed(lambda: ops.rows_pack(tabs, lst, cnt, xbuf[n_net:], stride, unpack=True))
     out["dense_allreduce_us"] = timed(lambda: ar(dense))
     out["dense_allreduce_bytes"] = dense.numel() * 4
