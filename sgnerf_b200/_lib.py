@@ -72,6 +72,9 @@ SIGNATURES = {
     "sgn_agg_forward_frame": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
                                       c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
                                       c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void, c_void]),
+    "sgn_agg_forward_frame_masked": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(c_void), C.POINTER(SgnPointTables),
+                                             c_void, c_void, c_void, c_void, c_void, c_void, c_i64, c_int, c_int, c_int, c_int,
+                                             c_void, c_void, c_void, c_void, c_void, c_void, c_void, c_size, c_void, c_void]),
     "sgn_agg_point_cache_bytes": (c_int, [C.POINTER(SgnAggCfg), c_i64, C.POINTER(c_size)]),
     "sgn_agg_point_cache_build": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(c_void), C.POINTER(SgnPointTables), c_void, c_size, c_void]),
     "sgn_agg_point_cache_update": (c_int, [C.POINTER(SgnAggCfg), C.POINTER(SgnPointTables), c_void, c_size, c_void, c_i64, c_void]),

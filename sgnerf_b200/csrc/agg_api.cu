@@ -69,6 +69,21 @@ extern "C" int sgn_agg_forward_frame(const SgnAggCfg* cfg, const float* const* w
                               weight, conf_coef, workspace, workspace_bytes, point_cache, (cudaStream_t)stream);
 }
 
+thread_local const int32_t* sgn::g_agg_sample_mask = nullptr;
+
+extern "C" int sgn_agg_forward_frame_masked(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
+                                            const int32_t* pidx, const int32_t* sample_mask, const float* loc_w, const float* raydir, const float* campos,
+                                            const float* camrotc2w, int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded,
+                                            uint8_t* ray_valid, float* loc_pers, float* loc_depth, float* weight, float* conf_coef, void* workspace,
+                                            size_t workspace_bytes, const void* point_cache, void* stream)
+{
+    g_agg_sample_mask = sample_mask;
+    const int rc = sgn_agg_forward_frame(cfg, weights, biases, tables, pidx, loc_w, raydir, campos, camrotc2w, R, SR, K, precision, save_for_backward, decoded,
+                                         ray_valid, loc_pers, loc_depth, weight, conf_coef, workspace, workspace_bytes, point_cache, stream);
+    g_agg_sample_mask = nullptr;
+    return rc;
+}
+
 extern "C" int sgn_agg_forward_cached(const SgnAggCfg* cfg, const float* const* weights, const float* const* biases, const SgnPointTables* tables,
                                const int32_t* pidx, const float* loc_w, const float* raydir, const float* campos, const float* camrotc2w,
                                int64_t R, int SR, int K, int precision, int save_for_backward, float* decoded, uint8_t* ray_valid,

@@ -84,7 +84,11 @@ struct AggIn {
     const float* raydir;    // [R,3]
     const float* campos;    // [3]
     const float* camrot;    // [3,3] camrotc2w, row-major
+    const int32_t* smask;   // optional [R,SR] (sgn_query's sample_mask): 0 = the slot holds no sample, its sample_pidx row is all -1 and is not read
 };
+
+// the sample mask handed to sgn_agg_forward_frame_masked for the call in progress on this thread (the inner forward functions pick it up)
+extern thread_local const int32_t* g_agg_sample_mask;
 
 // fp32-path workspace.  Sized for the worst case (every slot valid) so nothing depends on device counts.
 struct AggWs {

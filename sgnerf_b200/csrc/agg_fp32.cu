@@ -244,6 +244,7 @@ int sgn_agg_fp32_forward(const AggPlan& P, const float* const* weights, const fl
         AggIn in;
         in.tab = *tables;
         in.pidx = pidx + r0 * SR * K; in.loc_w = loc_w + r0 * SR * 3; in.raydir = raydir + r0 * 3;
+        in.smask = g_agg_sample_mask ? g_agg_sample_mask + r0 * SR : nullptr;
         in.campos = campos; in.camrot = camrotc2w;
         rc = agg_forward_chunk(P, weights, biases, in, Rc, SR, K, decoded + r0 * SR * 4, ray_valid + r0 * SR,
                                loc_pers ? loc_pers + r0 * SR * 3 : nullptr, loc_depth ? loc_depth + r0 * SR : nullptr, weight ? weight + r0 * SR * K : nullptr,
@@ -271,7 +272,7 @@ int sgn_agg_fp32_backward(const AggPlan& P, const float* const* weights, const f
     const int32_t* T_ptr = ws.tuple_start + S;
     const int32_t* S_ptr = ws.sample_cidx + S;
     AggIn in;
-    in.tab = *tables; in.pidx = pidx; in.loc_w = loc_w; in.raydir = raydir; in.campos = campos; in.camrot = camrotc2w;
+    in.tab = *tables; in.pidx = pidx; in.loc_w = loc_w; in.raydir = raydir; in.campos = campos; in.camrot = camrotc2w; in.smask = nullptr;
     SgnPointGrads g = {};
     if (d_tables) g = *d_tables;
     int rc;

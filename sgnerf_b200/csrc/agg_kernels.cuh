@@ -28,7 +28,10 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
     const int32_t* pi = in.pidx + s * K;
     if (K == 8 && (((uintptr_t)in.pidx | (uintptr_t)wc | (uintptr_t)weight_n | (uintptr_t)weight_out | (uintptr_t)conf_out) & 15) == 0) {
         // canonical K: the eight indices as two 16-byte loads, every output row as two 16-byte stores
-        const int4 pa = __ldg((const int4*)pi), pb = __ldg((const int4*)pi + 1);
+        // a slot without a sample (mask 0) has an all -1 row by construction: the 32 bytes are not even read
+        const bool slot = !in.smask || __ldg(in.smask + s) > 0;
+        int4 pa = make_int4(-1, -1, -1, -1), pb = pa;
+        if (slot) { pa = __ldg((const int4*)pi); pb = __ldg((const int4*)pi + 1); }
         const int p8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
         if ((pa.x & pa.y & pa.z & pa.w & pb.x & pb.y & pb.z & pb.w) < 0) {
             // no neighbour at all (two thirds of the slots of a frame): zero weights; the confidence column still holds point 0's

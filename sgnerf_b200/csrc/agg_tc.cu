@@ -1543,6 +1543,7 @@ int sgn_agg_tc_forward(const AggPlan& P, const float* const* weights, const floa
         AggIn in;
         in.tab = *tables;
         in.pidx = pidx + r0 * SR * K; in.loc_w = loc_w + r0 * SR * 3; in.raydir = raydir + r0 * 3; in.campos = campos; in.camrot = camrotc2w;
+        in.smask = g_agg_sample_mask ? g_agg_sample_mask + r0 * SR : nullptr;
         float* dec = decoded + r0 * SR * 4;
         float* loc_pers = loc_pers_out ? loc_pers_out + r0 * SR * 3 : ws.loc_pers;
         SGN_CUDA(cudaMemsetAsync(dec, 0, sizeof(float) * 4 * (size_t)S, st));

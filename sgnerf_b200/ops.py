@@ -433,8 +433,11 @@ class _Aggregate(torch.autograd.Function):
         conf_coef = torch.empty(R, SR, K, dtype=torch.float32, device=dev) if want_aux else None
         tb = _tables(xyz, embedding, color, dirs, conf, label_emb)
         cache = meta.point_cache if (precision == PRECISION_BF16 and not need_grad) else None
-        _lib.call("sgn_agg_forward_frame", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(loc_w),
-                  _ptr(raydir), _ptr(campos), _ptr(camrot), R, SR, K, precision, int(need_grad), _ptr(decoded), _ptr(ray_valid),
+        smask = getattr(meta, "sample_mask", None)            # sgn_query's sample_mask: slots without a sample are not read
+        if smask is not None:
+            smask = _dev(smask, torch.int32, "sample_mask")
+        _lib.call("sgn_agg_forward_frame_masked", C.byref(cfg), _ptr_array(weights), _ptr_array(biases), C.byref(tb), _ptr(pidx), _ptr(smask),
+                  _ptr(loc_w), _ptr(raydir), _ptr(campos), _ptr(camrot), R, SR, K, precision, int(need_grad), _ptr(decoded), _ptr(ray_valid),
                   _ptr(loc_pers), _ptr(loc_depth), _ptr(weight), _ptr(conf_coef), _ptr(ws), ws.numel() * 4, _ptr(cache), _stream())
         if depth_only:
             loc_pers = loc_depth
@@ -641,20 +644,21 @@ def update_point_cache(cfg, cache, embedding, rows, label_emb=None):
 
 
 def aggregate(cfg, weights, biases, xyz, embedding, color, dirs, conf, label_emb, pidx, loc_w, raydir, campos, camrotc2w,
-              precision=PRECISION_FP32, want_aux=True, point_cache=None, depth_only=False):
+              precision=PRECISION_FP32, want_aux=True, point_cache=None, depth_only=False, sample_mask=None):
     """Fused gather + aggregation MLPs (sgn_agg_forward / sgn_agg_backward).
 
     Tables: xyz [N,3], embedding [N,C], color [N,3], dirs [N,3], conf [N] (or None), label_emb [N,E] (or None).
     Query outputs: pidx int32 [R,SR,K], loc_w [R,SR,3]; raydir [R,3]; campos [3]; camrotc2w [3,3].
     Returns decoded [R,SR,4], ray_valid uint8 [R,SR], loc_pers [R,SR,3], weight [R,SR,K], conf_coef [R,SR,K].
     depth_only=True (inference, no autograd): the third result is the samples' camera depth [R,SR] (= loc_pers[..., 2]) for
-    render_composite(depth_array=True) instead of the full perspective positions (sgn_agg_forward_frame)."""
+    render_composite(depth_array=True) instead of the full perspective positions (sgn_agg_forward_frame).
+    sample_mask: ops.query's third result; slots it marks empty have all -1 index rows, which are then not read (same results)."""
     f32 = torch.float32
     meta = SimpleNamespace(cfg=cfg, xyz=_dev(xyz.reshape(-1, 3), f32, "xyz"), label_emb=_dev(label_emb, f32, "label_emb"),
                            pidx=_dev(pidx, torch.int32, "pidx"), loc_w=_dev(loc_w, f32, "loc_w"),
                            raydir=_dev(raydir.reshape(-1, 3), f32, "raydir"), campos=_dev(campos.reshape(3), f32, "campos"),
                            camrot=_dev(camrotc2w.reshape(3, 3), f32, "camrotc2w"), precision=int(precision), want_aux=bool(want_aux),
-                           grad_enabled=torch.is_grad_enabled(), point_cache=point_cache, depth_only=depth_only)
+                           grad_enabled=torch.is_grad_enabled(), point_cache=point_cache, depth_only=depth_only, sample_mask=sample_mask)
     N = meta.xyz.shape[0]
     embedding = _dev(embedding.reshape(N, -1), f32, "embedding")
     color = _dev(color.reshape(N, 3), f32, "color")

@@ -225,7 +225,8 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
     decoded, ray_valid, loc_pers, weight, conf_coef = ops.aggregate(
         scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf,
         scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux,
-        point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None, depth_only=inference)
+        point_cache=scene.point_cache() if (precision == ops.PRECISION_BF16 and use_point_cache) else None, depth_only=inference,
+        sample_mask=smask)
     if inference and not decoded.requires_grad:
         # inference: step sizes, compositing and fill_invalid in one kernel, no intermediate tensors; the aggregator hands over the
         # samples' camera depth as a dense array (the tail reads 4 bytes per sample instead of gathering z out of 12-byte rows)

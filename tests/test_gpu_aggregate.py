@@ -377,3 +377,31 @@ def test_training_path_with_no_valid_tuple(precision):
     rest = g_emb1.clone()
     rest[0, 11] = 0.0
     assert float(rest.abs().max()) == 0.0                                        # only the gathered point receives a gradient
+
+
+@pytest.mark.parametrize("precision", [ops.PRECISION_FP32, ops.PRECISION_BF16])
+def test_sample_mask_changes_nothing(precision):
+    """ops.aggregate(sample_mask=ops.query's mask): the all -1 index rows of slots without a sample are not read (sgn_agg_forward_frame_masked);
+    every output is bit for bit what the unmasked call gives."""
+    from sgnerf_b200 import pipeline, synth
+    s = synth.scene_c0(n_points=60_000, n_rays=700)
+    tabs = synth.make_point_tables(60_000, 32, 0, seed=0, conf_spread=0.2)
+    cfg = rr.agg_config()
+    P = rr.init_params(cfg, seed=1, bias_scale=0.05)
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    scene = pipeline.RenderScene(torch.from_numpy(s.xyz), tabs.embedding.reshape(60_000, -1), tabs.color.reshape(60_000, 3), tabs.dir.reshape(60_000, 3),
+                                 tabs.conf.reshape(60_000), [P[n + ".weight"] for n in names], [P[n + ".bias"] for n in names], cfg_to_c(cfg),
+                                 pipeline.query_options(), device="cuda")
+    grid, hp = scene.grid()
+    campos, rot = torch.from_numpy(s.campos).cuda(), torch.from_numpy(s.camrotc2w).cuda()
+    raydir = torch.from_numpy(s.raydir).cuda()
+    q = scene.qopt
+    pidx, loc_w, smask, rmask = ops.query(grid, campos, raydir, scene.depth_candidates(s.near, s.far), q.SR, q.K, q.kernel_size[0], hp.radius2)
+    assert 0 < int((smask > 0).sum()) < smask.numel() and bool((pidx[smask == 0] == -1).all())
+    with torch.no_grad():
+        a = ops.aggregate(scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf, None, pidx, loc_w,
+                          raydir, campos, rot, precision=precision, want_aux=True)
+        b = ops.aggregate(scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf, None, pidx, loc_w,
+                          raydir, campos, rot, precision=precision, want_aux=True, sample_mask=smask)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
