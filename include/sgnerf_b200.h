@@ -108,6 +108,14 @@ int sgn_query(const SgnGrid* g, const float* campos /*[3]*/, const float* raydir
               uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w, int32_t* sample_mask,
               int32_t* sample_label, int8_t* ray_mask, void* stream);
 
+/* The frame variant: identical, except that the sample_pidx rows of slots with sample_mask == 0 are left UNWRITTEN (sgn_query fills them
+ * with -1; at SR 200 they are nine tenths of a 4 GB array).  For consumers that take the mask: sgn_agg_forward_frame_masked. */
+int sgn_query_frame(const SgnGrid* g, const float* campos /*[3]*/, const float* raydir /*[R,3]*/, const float* t,
+              int t_per_ray, int64_t R, int D, int SR, int K, int kernel_size0, float radius2,
+              const int32_t* ray_label, const int32_t* pt_label, const int32_t* pt_label_prob_bits,
+              uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w, int32_t* sample_mask,
+              int32_t* sample_label, int8_t* ray_mask, void* stream);
+
 /* Tuning / test aid: sgn_query has two march kernels with identical results -- a thread-per-ray brick walk (frames) and a
  * warp-per-ray kernel (small ray counts, e.g. a training patch); mode 0 picks by ray count, 1 / 2 force one of them. */
 int sgn_query_march_mode(int mode);

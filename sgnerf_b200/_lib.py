@@ -58,6 +58,8 @@ SIGNATURES = {
     "sgn_grid_buffer": (c_int, [c_void, c_int, C.POINTER(c_void), C.POINTER(c_i64)]),
     "sgn_query": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_int, c_int, c_int, c_int, c_f32,
                           c_void, c_void, c_void, c_u64, c_void, c_void, c_void, c_void, c_void, c_void]),
+    "sgn_query_frame": (c_int, [c_void, c_void, c_void, c_void, c_int, c_i64, c_int, c_int, c_int, c_int, c_f32,
+                                c_void, c_void, c_void, c_u64, c_void, c_void, c_void, c_void, c_void, c_void]),
     "sgn_query_march_mode": (c_int, [c_int]),
     "sgn_gather_rows": (c_int, [c_void, c_int, c_void, c_i64, c_void, c_void]),
     "sgn_agg_num_layers": (c_int, [C.POINTER(SgnAggCfg)]),

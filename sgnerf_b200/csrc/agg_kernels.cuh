@@ -84,8 +84,9 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
     float w[SGN_MAX_K];
     float sum = 0.f;
     int n = 0;
+    const bool slot_g = !in.smask || __ldg(in.smask + s) > 0;     // mask 0: the row is all -1 by construction and may not even be written
     for (int k = 0; k < K; k++) {
-        const int p = pi[k];
+        const int p = slot_g ? pi[k] : -1;
         float wk = 0.f;
         if (p >= 0) {
             const float dx = in.tab.xyz[3 * (int64_t)p] - lx, dy = in.tab.xyz[3 * (int64_t)p + 1] - ly, dz = in.tab.xyz[3 * (int64_t)p + 2] - lz;
@@ -98,7 +99,7 @@ static __global__ void agg_prepare_kernel(AggIn in, int64_t S, int K, float* __r
     }
     const float den = fmaxf(sum, 1e-8f);
     for (int k = 0; k < K; k++) {
-        const int p = pi[k] < 0 ? 0 : pi[k];           // the reference gathers with clamp(pidx, 0) (neural_points.py:958)
+        const int p = (!slot_g || pi[k] < 0) ? 0 : pi[k];   // the reference gathers with clamp(pidx, 0) (neural_points.py:958)
         const float cf = in.tab.conf ? fminf(fmaxf(in.tab.conf[p], 0.0001f), 1.0f) : 1.0f;
         const float wn = w[k] / den;
         wc[s * K + k] = wn * cf;

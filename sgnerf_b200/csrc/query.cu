@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(KNN_THREADS, KT == 8 ? 8 : 3)
 knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, const float* __restrict__ sample_loc_w,
            const int32_t* __restrict__ sample_mask, const int32_t* __restrict__ sample_label, const int32_t* __restrict__ pt_label,
            const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
-           int8_t* __restrict__ ray_mask, int rays_per_block, int flat_ok)
+           int8_t* __restrict__ ray_mask, int rays_per_block, int flat_ok, int write_empty)
 {
     extern __shared__ int32_t s_list[];                       // [slots_cap] sample indices (relative to the block's first slot), then s_off / s_sorted / s_nent / s_key
     const int slots_cap = (rays_per_block * SR + 3) & ~3;
@@ -335,7 +335,7 @@ knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, con
         if (lane_id() == 0 && b) base = atomicAdd(&s_count, __popc(b));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (occ) s_list[base + __popc(b & ((1u << lane_id()) - 1u))] = i;
-        else if (i < nslot) {
+        else if (i < nslot && write_empty) {            // sgn_query_frame leaves these rows unwritten: its consumer takes the mask
             int32_t* o = sample_pidx + (slot0 + i) * K;
             if (KT == 8 && K == 8) { ((int4*)o)[0] = make_int4(-1, -1, -1, -1); ((int4*)o)[1] = make_int4(-1, -1, -1, -1); }
             else for (int k = 0; k < K; k++) o[k] = -1;
@@ -497,10 +497,10 @@ extern "C" int sgn_query_march_mode(int mode)
     return SGN_OK;
 }
 
-extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* raydir, const float* t, int t_per_ray, int64_t R, int D,
-                         int SR, int K, int kernel_size0, float radius2, const int32_t* ray_label, const int32_t* pt_label,
-                         const int32_t* pt_label_prob_bits, uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w,
-                         int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, void* stream)
+static int query_impl(const SgnGrid* G, const float* campos, const float* raydir, const float* t, int t_per_ray, int64_t R, int D,
+                      int SR, int K, int kernel_size0, float radius2, const int32_t* ray_label, const int32_t* pt_label,
+                      const int32_t* pt_label_prob_bits, uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w,
+                      int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, int write_empty, void* stream)
 {
     SGN_CHECK_ARG(G != nullptr, "sgn_query: grid is NULL");
     SGN_CHECK_ARG(R >= 0 && D > 0 && D <= 65535 && SR > 0 && SR <= 4096, "sgn_query: bad R/D/SR (D at most 65535, SR at most 4096)");
@@ -538,20 +538,38 @@ extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* ray
     if (K == 8) {
         if (semantic)
             launch(knn_kernel<8, true>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
-                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
+                                                     pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb, flat_ok, write_empty);
         else
             launch(knn_kernel<8, false>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr, nullptr,
-                                                      seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
+                                                      seconds_query, sample_pidx, ray_mask, rpb, flat_ok, write_empty);
     } else {
         if (semantic)
             launch(knn_kernel<SGN_MAX_K, true>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, sample_label, pt_label,
-                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
+                                                             pt_label_prob_bits, seconds_query, sample_pidx, ray_mask, rpb, flat_ok, write_empty);
         else
             launch(knn_kernel<SGN_MAX_K, false>, nb, KNN_THREADS, ksm, st, g, R, SR, K, nlayer, radius2, sample_loc_w, sample_mask, nullptr, nullptr,
-                                                              nullptr, seconds_query, sample_pidx, ray_mask, rpb, flat_ok);
+                                                              nullptr, seconds_query, sample_pidx, ray_mask, rpb, flat_ok, write_empty);
     }
     SGN_LAUNCH_CHECK();
     return SGN_OK;
+}
+
+extern "C" int sgn_query(const SgnGrid* G, const float* campos, const float* raydir, const float* t, int t_per_ray, int64_t R, int D,
+                         int SR, int K, int kernel_size0, float radius2, const int32_t* ray_label, const int32_t* pt_label,
+                         const int32_t* pt_label_prob_bits, uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w,
+                         int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, void* stream)
+{
+    return query_impl(G, campos, raydir, t, t_per_ray, R, D, SR, K, kernel_size0, radius2, ray_label, pt_label, pt_label_prob_bits, seconds_query,
+                      sample_pidx, sample_loc_w, sample_mask, sample_label, ray_mask, 1, stream);
+}
+
+extern "C" int sgn_query_frame(const SgnGrid* G, const float* campos, const float* raydir, const float* t, int t_per_ray, int64_t R, int D,
+                               int SR, int K, int kernel_size0, float radius2, const int32_t* ray_label, const int32_t* pt_label,
+                               const int32_t* pt_label_prob_bits, uint64_t seconds_query, int32_t* sample_pidx, float* sample_loc_w,
+                               int32_t* sample_mask, int32_t* sample_label, int8_t* ray_mask, void* stream)
+{
+    return query_impl(G, campos, raydir, t, t_per_ray, R, D, SR, K, kernel_size0, radius2, ray_label, pt_label, pt_label_prob_bits, seconds_query,
+                      sample_pidx, sample_loc_w, sample_mask, sample_label, ray_mask, 0, stream);
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, int C, const int32_t* __restrict__ pidx, int64_t n, float* __restrict__ out)

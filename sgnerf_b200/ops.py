@@ -125,9 +125,11 @@ class OccGrid:
 
 
 def query(grid, campos, raydir, t, SR, K, kernel_size0, radius2, ray_label=None, pt_label=None,
-          pt_label_prob_bits=None, seconds_query=0):
+          pt_label_prob_bits=None, seconds_query=0, sparse_rows=False):
     """sgn_query.  campos [3], raydir [R,3], t [D] or [R,D] (middle_point_ts).  Uncompacted outputs:
-    sample_pidx int32 [R,SR,K], sample_loc_w f32 [R,SR,3], sample_mask int32 [R,SR], ray_mask int8 [R]."""
+    sample_pidx int32 [R,SR,K], sample_loc_w f32 [R,SR,3], sample_mask int32 [R,SR], ray_mask int8 [R].
+    sparse_rows=True (sgn_query_frame): the sample_pidx rows of slots with sample_mask == 0 are left unwritten -- only for a consumer that
+    is given the mask (aggregate(sample_mask=...))."""
     raydir = _dev(raydir.reshape(-1, 3), torch.float32, "raydir")
     campos = _dev(campos.reshape(3), torch.float32, "campos")
     t = _dev(t, torch.float32, "t")
@@ -147,7 +149,7 @@ def query(grid, campos, raydir, t, SR, K, kernel_size0, radius2, ray_label=None,
         pt_label = _dev(pt_label.reshape(-1), torch.int32, "pt_label")
         pt_label_prob_bits = _dev(pt_label_prob_bits.reshape(-1, 20), torch.int32, "pt_label_prob_bits")
         slabel = torch.empty(R, SR, dtype=torch.int32, device=dev)
-    _lib.call("sgn_query", grid._handle, _ptr(campos), _ptr(raydir), _ptr(t), per_ray, R, D, SR, K, int(kernel_size0),
+    _lib.call("sgn_query_frame" if sparse_rows else "sgn_query", grid._handle, _ptr(campos), _ptr(raydir), _ptr(t), per_ray, R, D, SR, K, int(kernel_size0),
               float(radius2), _ptr(ray_label), _ptr(pt_label), _ptr(pt_label_prob_bits), int(seconds_query),
               _ptr(pidx), _ptr(loc_w), _ptr(smask), _ptr(slabel), _ptr(rmask), _stream())
     return pidx, loc_w, smask, rmask

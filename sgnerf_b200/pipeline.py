@@ -220,8 +220,10 @@ def render_rays(scene, campos, camrotc2w, raydir, near, far, bg_color, precision
     grid, hp = scene.grid()
     if t is None:
         t = scene.depth_candidates(near, far)
-    pidx, loc_w, smask, rmask = ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2)
-    inference = not want_aux and not (torch.is_grad_enabled() and any(t.requires_grad for t in scene.weights + [scene.embedding, scene.color]))
+    inference = not want_aux and not (torch.is_grad_enabled() and any(w.requires_grad for w in scene.weights + [scene.embedding, scene.color]))
+    # inference frames: nothing but the aggregator (which is given the sample mask) reads the neighbour indices, so the all -1 rows of
+    # the empty sample slots are neither written by the query nor read by the aggregator
+    pidx, loc_w, smask, rmask = ops.query(grid, campos, raydir, t, q.SR, q.K, q.kernel_size[0], hp.radius2, sparse_rows=inference)
     decoded, ray_valid, loc_pers, weight, conf_coef = ops.aggregate(
         scene.agg_cfg, scene.weights, scene.biases, scene.xyz, scene.embedding, scene.color, scene.dirs, scene.conf,
         scene.label_emb, pidx, loc_w, raydir, campos, camrotc2w, precision=precision, want_aux=want_aux,

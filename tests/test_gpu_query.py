@@ -226,3 +226,39 @@ def test_grid_without_neighbour_lists_gives_the_same_query(scene_c0):
         b = util.cuda_query(scene_c0, opt, t, seconds=seconds, grid=(g2, hp))
         assert torch.equal(a.pidx, b.pidx) and torch.equal(a.loc_w, b.loc_w) and torch.equal(a.rmask, b.rmask) and torch.equal(a.smask, b.smask)
         assert int(a.rmask.sum()) > 100
+
+
+@pytest.mark.parametrize("K", [8, 4])
+def test_query_frame_leaves_only_empty_rows_unwritten_and_the_masked_aggregator_does_not_care(K):
+    """sgn_query_frame (sparse_rows): identical to sgn_query on every slot with sample_mask > 0, rows of the other slots untouched (the
+    output buffer is poisoned first); the aggregator given the mask renders the same from both."""
+    from sgnerf_b200 import ops, pipeline
+    s = synth.scene_c0(n_points=60_000, n_rays=512)
+    opt = qr.default_opt(SR=24, K=K)
+    grid, hp = util.cuda_grid(s, opt)
+    t = util.shared_t(s.near, s.far, opt.z_depth_dim).cuda()
+    campos, raydir = torch.from_numpy(s.campos).cuda(), torch.from_numpy(s.raydir).cuda()
+    a = ops.query(grid, campos, raydir, t, opt.SR, K, opt.kernel_size[0], hp.radius2)
+    torch.empty(512, opt.SR, K, dtype=torch.int32, device="cuda").fill_(123456789)      # poison what the allocator hands out next
+    b = ops.query(grid, campos, raydir, t, opt.SR, K, opt.kernel_size[0], hp.radius2, sparse_rows=True)
+    torch.cuda.synchronize()
+    m = a[2] > 0
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[0][m], b[0][m]) and bool((a[0][~m] == -1).all())
+    tabs = synth.make_point_tables(60_000, 32, 0, seed=0, conf_spread=0.2)
+    from oracle import render_ref as rr
+    from tests.test_gpu_aggregate import cfg_to_c
+    cfg = rr.agg_config()
+    P = rr.init_params(cfg, seed=1, bias_scale=0.05)
+    names = [n for n, _, _ in rr.layer_shapes(cfg)]
+    W, Bs = [P[n + ".weight"].cuda() for n in names], [P[n + ".bias"].cuda() for n in names]
+    rot = torch.from_numpy(s.camrotc2w).cuda()
+    args = (cfg_to_c(cfg), W, Bs, torch.from_numpy(s.xyz).cuda(), tabs.embedding.reshape(60_000, -1).cuda(), tabs.color.reshape(60_000, 3).cuda(),
+            tabs.dir.reshape(60_000, 3).cuda(), tabs.conf.reshape(60_000).cuda(), None)
+    with torch.no_grad():
+        ra = ops.aggregate(*args, a[0], a[1], raydir, campos, rot, precision=ops.PRECISION_FP32, want_aux=True)
+        poisoned = b[0].clone()
+        poisoned[~m] = 123456789
+        rb = ops.aggregate(*args, poisoned, b[1], raydir, campos, rot, precision=ops.PRECISION_FP32, want_aux=True, sample_mask=b[2])
+    for x, y in zip(ra, rb):
+        assert torch.equal(x, y)
