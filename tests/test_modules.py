@@ -208,6 +208,32 @@ def test_grid_hyperparameters_match_the_oracle():
         assert np.float32(a.radius2).tobytes() == np.float32(b.radius2).tobytes()
 
 
+def test_perspective_hyperparameters_match_the_oracle_and_pers2w_inverts_w2pers():
+    """Host logic of the perspective querier (query_point_indices.py:48-73, :95-107) on the CPU: ops.pers_hyperparameters against the
+    oracle's restatement bit for bit (plain and inverse depth), and lighting_fast_querier_p.pers2w undoing w2pers."""
+    from oracle import query_pers_ref as qp
+    from sgnerf_b200 import modules, ops, synth
+    K = synth.SCANNET_INTRINSIC
+    for inverse, vscale in ((0, [2, 2, 2]), (1, [4, 4, 1]), (0, [3, 5, 7])):
+        opt = qp.default_opt(vscale=vscale, inverse=inverse, radius_limit_scale=5.0, depth_limit_scale=1.7)
+        a = qp.get_hyperparameters(opt, 480, 640, K, 0.1, 8.0)
+        b = ops.pers_hyperparameters(480, 640, K, 0.1, 8.0, opt.z_depth_dim, vscale, 5.0, 1.7, inverse)
+        for k in ("ranges", "vsize", "scaled_vsize", "ray_vsize"):
+            assert np.array_equal(getattr(a, k).view(np.int32), getattr(b, k).view(np.int32)), k
+        assert np.array_equal(a.scaled_vdim, b.scaled_vdim) and a.radius2 == b.radius2 and a.depth2 == b.depth2
+    g = torch.Generator().manual_seed(3)
+    s = synth.scene_c0(n_points=1000, n_rays=8)
+    rot, campos = torch.from_numpy(s.camrotc2w)[None], torch.from_numpy(s.campos)[None]
+    pts = torch.from_numpy(s.xyz)[None]
+    pers = modules.lighting_fast_querier.w2pers(pts, rot, campos).reshape(1, -1, 3)
+    front = pers[0, :, 2] > 0.2
+    back, dirs = modules.lighting_fast_querier_p.pers2w(pers[:, front], rot, campos)
+    torch.testing.assert_close(back, pts[:, front], rtol=0, atol=2e-5)
+    torch.testing.assert_close(dirs.norm(dim=-1), torch.ones_like(dirs[..., 0]), rtol=0, atol=1e-5)
+    o_back, o_dirs = qp.pers2w(pers[:, front], rot, campos)
+    assert torch.equal(back, o_back) and torch.equal(dirs, o_dirs)
+
+
 def test_commandline_flags_equal_the_reference(golden_dir):
     """modify_commandline_options of both drop-in classes registers the reference's flags (neural_points.py:80-309,
     point_aggregators.py:15-253): same names, order, type, default (after argparse's conversion) and nargs -- against
