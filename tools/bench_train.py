@@ -60,7 +60,6 @@ def main():
                              precision=ops.PRECISION_FP32 if args.precision == "fp32" else ops.PRECISION_TF32,
                              use_graph=args.mode == "graph")
         dgen = torch.Generator(device=dev).manual_seed(200 + rank)
-        nbytes_ar = sum(p.numel() for p in ts.params) * 4
 
         def step():
             pix = torch.randint(0, all_rays.shape[0], (n_patch,), generator=gen).to(dev, non_blocking=True)
@@ -70,7 +69,7 @@ def main():
             ts.step()
             for e in ev[1:]:
                 e.record()
-            return ev, nbytes_ar, ts.n_hit
+            return ev, int(ts.exchange_floats) * 4, ts.n_hit      # bytes all-reduced by this step (0 on one rank; the touched rows on several)
     else:
         step = None
     if step is None:
