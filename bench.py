@@ -710,18 +710,22 @@ def strong_scaling_leg(device, rank, world, dist, precision, args):
             return sdist.gather_frame(part.ray_color, idx_d, R, tile=256), part
         return one, R
 
-    def measure(one, n=3, warm=4):          # (the allocator needs a few frames of a new shape to settle: the 2nd frame still takes 3x)
+    def measure(one, n=5, warm=4):          # (the allocator needs a few frames of a new shape to settle: the 2nd frame still takes 3x)
         for _ in range(warm):
             one()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        a, b = ev(), ev()
-        a.record()
-        for _ in range(n):
+        # every frame timed by its own pair of events; the median of them (a frame that meets a cudaMalloc or a clock dip does not
+        # decide the figure), then the max over the ranks
+        pairs = [(ev(), ev()) for _ in range(n)]
+        for a, b in pairs:
+            a.record()
             r = one()
-        b.record(); torch.cuda.synchronize()
-        return tmax(a.elapsed_time(b) / n), r
+            b.record()
+        torch.cuda.synchronize()
+        times = sorted(a.elapsed_time(b) for a, b in pairs)
+        return tmax(times[len(times) // 2]), r
 
     with torch.no_grad():
         for name, mk, n_pts, qo in (("c1", lambda: synth.scene_room(N_POINTS, room=(8.0, 8.0, 3.0), width=WIDTH, height=HEIGHT, seed=1234), N_POINTS, dict(SR=24)),
