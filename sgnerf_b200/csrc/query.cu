@@ -314,7 +314,7 @@ __device__ __forceinline__ void knn_insert(int pidx, float d2, int K, int& kid, 
 //      candidate counts instead of the sum over voxels of the per-voxel maxima the nested loops cost.
 // The visiting order and the insertion rule are unchanged, so the K slots come out as in the sequential reference.
 template <int KT, bool SEMANTIC>
-__global__ void __launch_bounds__(KNN_THREADS, KT == 8 ? 8 : 3)
+__global__ void __launch_bounds__(KNN_THREADS, KT == 8 ? 10 : 3)
 knn_kernel(QueryGrid g, int64_t R, int SR, int K, int nlayer, float radius2, const float* __restrict__ sample_loc_w,
            const int32_t* __restrict__ sample_mask, const int32_t* __restrict__ sample_label, const int32_t* __restrict__ pt_label,
            const int32_t* __restrict__ pt_label_prob_bits, uint64_t seconds, int32_t* __restrict__ sample_pidx,
